@@ -1,0 +1,216 @@
+"""TEST INFRASTRUCTURE (oracle) — ctypes driver for the two CPU checkers.
+
+* ``RefDomain``    -> oracle/_ref/libwf_ref.so : the UNMODIFIED reference CPU sources driven
+                      member-by-member (oracle/ref_harness.cpp).  Exists only where it was built
+                      from /root/reference (it travels to the GPU box as a prebuilt .so).
+* ``OracleDomain`` -> oracle/_build/libwf_oracle.so : the plain-C restatement (oracle/wf_oracle.c).
+
+Both expose the same Python surface (the Domain_d call sequence) so a parity test reads the same
+whichever checker it uses.  Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
+--impl reference legs may import this module.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REF_SO = os.path.join(HERE, "_ref", "libwf_ref.so")
+PORT_SO = os.path.join(HERE, "_build", "libwf_oracle.so")
+
+_DBL = ("x v a u u_dt prev_a m_fi m_fe m_mdiag m_voln p_node m_dH_detJ_dx m_dH_detJ_dy m_dH_detJ_dz "
+        "m_detJ vol vol_0 rho rho_0 p pl_strain sigma_y m_radius m_str_rate m_rot_rate m_sigma m_tau "
+        "m_eps m_f_elem m_f_elem_hg m_hg_q m_voln_0 m_Jn").split()
+_INT = "m_nodel m_nodel_loc m_nodel_offset m_nodel_count".split()
+_UINT = ["m_elnod"]
+
+HOLLOMON = 1
+BILINEAR = 0
+
+STAB_FIELDS = ("alpha_free alpha_contact hg_coeff_free hg_coeff_contact av_coeff_div av_coeff_bulk "
+               "log_factor pspg_scale p_pspg_bulkfac J_min hg_visc hg_stiff").split()
+
+
+def build(target: str = "all", quiet: bool = True) -> None:
+    """Build the checkers (building the checker is not using it)."""
+    targets = []
+    if target in ("all", "port"):
+        targets.append("port")
+    if target in ("all", "ref") and os.path.isdir("/root/reference"):
+        targets.append("ref")
+    for t in targets:
+        subprocess.run(["make", "-C", HERE, t], check=True,
+                       stdout=subprocess.DEVNULL if quiet else None)
+
+
+def have_ref() -> bool:
+    return os.path.exists(REF_SO)
+
+
+def have_port() -> bool:
+    return os.path.exists(PORT_SO)
+
+
+class _Base:
+    _prefix = ""
+    _lib = None
+
+    @classmethod
+    def _load(cls, path):
+        lib = C.CDLL(path)
+        p = cls._prefix
+        vp, dp, ip = C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_int)
+        sig = {
+            "new": (vp, []), "free": (None, [vp]),
+            "set_domtype": (None, [vp, C.c_int, C.c_int]),
+            "box": (None, [vp, dp, dp, C.c_double, C.c_int]),
+            "set_mesh": (None, [vp, C.c_int, C.c_int, C.c_int, C.c_int, dp, ip]),
+            "set_material": (None, [vp] + [C.c_double] * 3 + [C.c_int] + [C.c_double] * 3),
+            "set_stab": (None, [vp, dp]),
+            "set_options": (None, [vp, C.c_int, C.c_double, C.c_double, C.c_double]),
+            "add_bc": (None, [vp, C.c_int, C.c_int, C.c_double]),
+            "allocate_bcs": (None, [vp]),
+            "init": (None, [vp, C.c_double]),
+            "step": (None, [vp, C.c_int]),
+            "time_steps": (C.c_double, [vp, C.c_int]),
+            "call": (C.c_int, [vp, C.c_char_p, C.c_double]),
+            "get": (C.c_long, [vp, C.c_char_p, vp, C.c_long]),
+            "set": (C.c_long, [vp, C.c_char_p, vp, C.c_long]),
+            "info": (None, [vp, ip]),
+            "consts": (None, [vp, dp]),
+            "energies": (None, [vp, dp, dp]),
+            "set_threads": (None, [C.c_int]),
+            "max_threads": (C.c_int, []),
+        }
+        for name, (res, args) in sig.items():
+            f = getattr(lib, p + name)
+            f.restype, f.argtypes = res, args
+        return lib
+
+    def __init__(self):
+        self.h = self._f("new")()
+
+    def _f(self, name):
+        return getattr(type(self)._lib, self._prefix + name)
+
+    def close(self):
+        if self.h:
+            self._f("free")(self.h)
+            self.h = None
+
+    # ---- setup (same order as src/explicit/main.C) -------------------------------------------
+    def set_domtype(self, domtype: int, vol_weight: bool = False):
+        self._f("set_domtype")(self.h, domtype, int(vol_weight))
+
+    def box(self, V, L, r, tritet=False):
+        V = (C.c_double * 3)(*V)
+        L = (C.c_double * 3)(*L)
+        self._f("box")(self.h, V, L, r, int(tritet))
+
+    def set_mesh(self, dim, k, x, elnod):
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        el = np.ascontiguousarray(elnod, dtype=np.int32)
+        nn, ne = x.size // dim, el.size // k
+        self._f("set_mesh")(self.h, dim, k, nn, ne, x.ctypes.data_as(C.POINTER(C.c_double)),
+                            el.ctypes.data_as(C.POINTER(C.c_int)))
+
+    def set_material(self, E, nu, rho0, model=BILINEAR, sy0=1.0e10, K=0.0, m=1.0):
+        self._f("set_material")(self.h, E, nu, rho0, model, sy0, K, m)
+
+    def set_stab(self, **kw):
+        vals = [float(kw.get(k, 0.0)) for k in STAB_FIELDS]
+        self._f("set_stab")(self.h, (C.c_double * 12)(*vals))
+
+    def set_options(self, press=0, av_alpha=0.0, av_beta=0.0, hexa_hg=0.0):
+        self._f("set_options")(self.h, press, av_alpha, av_beta, hexa_hg)
+
+    def add_bc(self, node, dim, val):
+        self._f("add_bc")(self.h, int(node), int(dim), float(val))
+
+    def allocate_bcs(self):
+        self._f("allocate_bcs")(self.h)
+
+    def init(self, dt):
+        self._f("init")(self.h, dt)
+
+    def step(self, n=1):
+        self._f("step")(self.h, n)
+
+    def time_steps(self, n):
+        return self._f("time_steps")(self.h, n)
+
+    def call(self, fn, arg=0.0):
+        rc = self._f("call")(self.h, fn.encode(), float(arg))
+        if rc != 0:
+            raise KeyError(fn)
+
+    @classmethod
+    def set_threads(cls, n):
+        getattr(cls._lib, cls._prefix + "set_threads")(int(n))
+
+    @classmethod
+    def max_threads(cls):
+        return getattr(cls._lib, cls._prefix + "max_threads")()
+
+    # ---- state ---------------------------------------------------------------------------------
+    def info(self):
+        out = (C.c_int * 8)()
+        self._f("info")(self.h, out)
+        keys = "dim nodxelem n_nodes n_elems bcx bcy bcz domtype".split()
+        return dict(zip(keys, list(out)))
+
+    def consts(self):
+        out = (C.c_double * 5)()
+        self._f("consts")(self.h, out)
+        return dict(zip("alpha beta gamma dt time".split(), list(out)))
+
+    def energies(self):
+        ek, de = C.c_double(), C.c_double()
+        self._f("energies")(self.h, C.byref(ek), C.byref(de))
+        return ek.value, de.value
+
+    def get(self, name):
+        dt = np.float64 if name in _DBL else (np.uint32 if name in _UINT else np.int32)
+        need = self._f("get")(self.h, name.encode(), None, 0)
+        if need == -1:
+            raise KeyError(name)
+        nbytes = -need if need < 0 else need
+        out = np.empty(nbytes // np.dtype(dt).itemsize, dtype=dt)
+        if nbytes:
+            got = self._f("get")(self.h, name.encode(), out.ctypes.data_as(C.c_void_p), nbytes)
+            assert got == nbytes, (name, got, nbytes)
+        return out
+
+    def set(self, name, arr):
+        dt = np.float64 if name in _DBL else (np.uint32 if name in _UINT else np.int32)
+        arr = np.ascontiguousarray(arr, dtype=dt)
+        rc = self._f("set")(self.h, name.encode(), arr.ctypes.data_as(C.c_void_p), arr.nbytes)
+        if rc != arr.nbytes:
+            raise ValueError(f"set({name}) size mismatch")
+
+
+class RefDomain(_Base):
+    """The unmodified reference, compiled from /root/reference (oracle/_ref)."""
+    _prefix = "wfref_"
+
+    def __init__(self):
+        if RefDomain._lib is None:
+            if not have_ref():
+                raise FileNotFoundError(REF_SO + " (run `make -C oracle ref` where /root/reference exists)")
+            RefDomain._lib = self._load(REF_SO)
+        super().__init__()
+
+
+class OracleDomain(_Base):
+    """The plain-C restatement (oracle/wf_oracle.c)."""
+    _prefix = "wfo_"
+
+    def __init__(self):
+        if OracleDomain._lib is None:
+            if not have_port():
+                build("port")
+            OracleDomain._lib = self._load(PORT_SO)
+        super().__init__()
