@@ -1,0 +1,168 @@
+/* wf_engine.h — C ABI of the B200-native explicit time-step engine for WeldFormFEM.
+ *
+ * The reference (luchete80/WeldFormFEM @ c68e50e) has no plugin ABI: the seam is
+ * the MetFEM::Domain_d object — its public setters, its flat SOA arrays
+ * (include/common/Domain_d.h:837-1044) and the fixed call sequence of
+ * Domain_d::SolveChungHulbert() (src/explicit/Solver_explicit.C:115-292 init,
+ * :524-978 one step).  Every entry point below names the reference interface it
+ * replaces.  Plain pointers and sizes only; no C++/torch types.
+ *
+ * Conventions
+ *   - all functions return 0 on success, non-zero on error; wf_last_error()
+ *     returns the message.  The engine has NO CPU fallback: without a CUDA
+ *     device wf_create() fails.
+ *   - host arrays passed in / out use the REFERENCE layouts and member names
+ *     ("xyzxyz" nodal vectors, 6-vectors [xx,yy,zz,xy,yz,xz] per element,
+ *     m_f_elem[e][local node][dim], ...).  Device-side layouts are private.
+ *   - indices are 32-bit like the reference (unsigned m_elnod, int m_nodel*).
+ */
+#ifndef WF_ENGINE_H
+#define WF_ENGINE_H
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct wf_engine wf_engine; /* opaque; owns all device memory of one GPU */
+
+/* dom_type, include/common/Domain_d.h:101 */
+enum { WF_PLANE_STRAIN = 0, WF_PLANE_STRESS = 1, WF_AXISYMM = 2, WF_3D = 3 };
+/* Material_model, include/common/Material.cuh:9-13 */
+enum { WF_BILINEAR = 0, WF_HOLLOMON = 1 };
+/* pressure law selected per step (Solver_explicit.C:735-746):
+ *   0 = m_press_algorithm 0: calcElemPressure (3D, Mechanical.C:691) / calcElemPressureLocal (2D, :1165)
+ *   1 = m_press_algorithm 1: calcElemPressureANP as shipped (Mechanical.C:1220; accumulates)
+ *   3 = calcElemPressureANP_Nodal (Mechanical.C:1253; corrected ANP, not wired in the reference solver) */
+enum { WF_PRESS_DEFAULT = 0, WF_PRESS_ANP_SHIPPED = 1, WF_PRESS_ANP_NODAL = 3 };
+/* numerics flavour */
+enum {
+  WF_STRICT = 1, /* operation-for-operation with the reference CPU path, no FMA contraction,
+                    separate m_f_elem_hg and two-pass assembly (Matrices.C:51-75) */
+  WF_FAST = 0    /* same algorithm, FMA + algebraically equivalent regrouping, hourglass force
+                    folded into m_f_elem; meets the 1e-10 / 1e-6 tolerances of BASELINE.json */
+};
+
+/* Material_ / Elastic_ (include/common/Material.cuh:15-156) as read by the hot path */
+typedef struct wf_material {
+  int model;     /* WF_BILINEAR | WF_HOLLOMON */
+  double E, nu;  /* Elastic_(E,nu): K = E/(3(1-2nu)), G = E/(2(1+nu)) */
+  double rho0;   /* setDensity(), Domain_d.C:951 */
+  double sy0;    /* yieldStress0 */
+  double K, m;   /* Hollomon constants; eps0 = sy0/E, eps1 = pow(sy0/K,1/m) (Material.cuh:90-104) */
+} wf_material;
+
+/* StabilizationParams (include/common/Domain_d.h:140-153) + the hexa hourglass coefficient of
+ * f90_ver/src/Mechanical.f90:307 (0.06; 0 = off = behaviour of the C++ at this commit) */
+typedef struct wf_stab {
+  double alpha_free, alpha_contact, hg_coeff_free, hg_coeff_contact, av_coeff_div, av_coeff_bulk;
+  double log_factor, pspg_scale, p_pspg_bulkfac, J_min, hg_visc, hg_stiff;
+  double hexa_hg_coeff;
+} wf_stab;
+
+/* ---- lifetime ------------------------------------------------------------------------------------ */
+/* new Domain_d + setAxiSymm/m_domtype (Domain_d.h:241-353, :666); device = CUDA ordinal */
+int wf_create(wf_engine **out, int dim, int nodxelem, int domtype, int device);
+void wf_destroy(wf_engine *);
+const char *wf_last_error(wf_engine *); /* engine may be NULL: last error of wf_create */
+/* run all engine work on a caller-owned CUDA stream (cudaStream_t as void*); default stream if never set */
+int wf_set_stream(wf_engine *, void *cuda_stream);
+int wf_synchronize(wf_engine *);
+
+/* ---- mesh ---------------------------------------------------------------------------------------- */
+/* SetDimension + copy x + setNodElem (Domain_d::CreateFromLSDyna, Domain_d.C:1647-1699; setNodElem :1508-1611) */
+int wf_set_mesh(wf_engine *, int n_nodes, int n_elems, const double *x /*N_n*dim*/, const unsigned *elnod /*N_e*k*/);
+/* Domain_d::AddBoxLength (Domain_d.C:1136-1504): same nel, numbering, coordinates by accumulation, tet/tri split */
+int wf_gen_box(wf_engine *, const double V[3], const double L[3], double r, int tritet);
+int wf_get_counts(wf_engine *, int *n_nodes, int *n_elems, int *nodel_total);
+int wf_set_axisymm_vol_weight(wf_engine *, int on); /* setAxiSymm(vol_weight), Domain_d.h:666 */
+
+/* ---- material / options / boundary conditions -------------------------------------------------- */
+int wf_set_material(wf_engine *, const wf_material *); /* main.C:460-581 + AssignMaterial (Domain_d.C:903) */
+int wf_set_stab(wf_engine *, const wf_stab *);          /* m_stab, main.C:84-120 */
+/* m_press_algorithm, m_artifvisc[0..1] (main.C:211-347), numerics flavour */
+int wf_set_options(wf_engine *, int press_algorithm, double av_alpha, double av_beta, int strict_reference);
+/* optional per-step products the reference always keeps: bit0 = integrate m_eps (Mechanical.C:1822),
+ * bit1 = store m_sigma every step instead of rebuilding it on wf_get_array (identical values) */
+int wf_set_tracking(wf_engine *, int flags);
+int wf_add_bc_vel(wf_engine *, int node, int dim, double val); /* AddBCVelNode, Domain_d.C:1057 */
+int wf_add_bc_vel_array(wf_engine *, int count, const int *node, const int *dim, const double *val);
+int wf_allocate_bcs(wf_engine *);                              /* AllocateBCs, Domain_d.C:1063 */
+
+/* ---- solve --------------------------------------------------------------------------------------- */
+int wf_init(wf_engine *, double dt);  /* Solver_explicit.C:115-292 incl. SetDT; CH constants rho_b = 0.8182 */
+int wf_step(wf_engine *, int nsteps); /* fused rows 1-22 of the step, Solver_explicit.C:524-978 */
+/* set after a step that scrubbed a non-finite internal force (Solver_explicit.C:779-784); clears the flag */
+int wf_nonfinite_flag(wf_engine *, int *flag);
+int wf_energies(wf_engine *, double *Ekin, double *dEint); /* computeEnergies, Mechanical.C:2145 */
+int wf_get_time(wf_engine *, double *time, long *step_count);
+
+/* 1:1 unfused entry points for parity bisecting; names = Domain_d members */
+int wf_UpdatePrediction(wf_engine *);          /* Domain_d.C:961 */
+int wf_ImposeBCV(wf_engine *, int d);          /* Domain_d.C:1109 */
+int wf_ImposeBCA(wf_engine *, int d);          /* Domain_d.C:1123 */
+int wf_calcElemJAndDerivatives(wf_engine *);   /* Domain_d.C:1701 */
+int wf_Calc_Element_Radius(wf_engine *);       /* Domain_d.C:2140 */
+int wf_CalcElemVol(wf_engine *);               /* Mechanical.C:264 */
+int wf_CalcNodalVol(wf_engine *);              /* Mechanical.C:1555 */
+int wf_CalcNodalMassFromVol(wf_engine *);      /* Mechanical.C:1576 */
+int wf_calcElemStrainRates(wf_engine *);       /* Mechanical.C:41 */
+int wf_calcElemPressure(wf_engine *);          /* Solver_explicit.C:735-746 dispatch */
+int wf_CalcStressStrain(wf_engine *, double dt); /* Mechanical.C:1664 */
+int wf_calcArtificialViscosity(wf_engine *);   /* Mechanical.C:1948 */
+int wf_calcElemForces(wf_engine *);            /* Mechanical.C:375 */
+int wf_calcElemHourglassForces(wf_engine *);   /* Mechanical.C:1842 (+ f90_ver hexa form) */
+int wf_assemblyForces(wf_engine *);            /* Matrices.C:42 (+ non-finite scrub, Solver_explicit.C:779) */
+int wf_calcAccel(wf_engine *);                 /* Mechanical.C:321 */
+int wf_UpdateCorrectionAccVel(wf_engine *);    /* Domain_d.C:981 */
+int wf_AxisConstraint(wf_engine *);            /* Solver_explicit.C:953-969 */
+int wf_UpdateCorrectionPos(wf_engine *);       /* Domain_d.C:1005 */
+
+/* ---- state access (checkpoint / parity dump); names = Domain_d member names --------------------- */
+int wf_get_array(wf_engine *, const char *name, void *host_dst, size_t bytes);
+int wf_set_array(wf_engine *, const char *name, const void *host_src, size_t bytes);
+size_t wf_array_bytes(wf_engine *, const char *name); /* 0 if unknown */
+/* raw device pointer of a private SoA array (for zero-copy interop, e.g. torch tensors); NULL if unknown */
+void *wf_device_ptr(wf_engine *, const char *name, size_t *pitch_elems);
+
+/* ---- multi-GPU: one engine per rank/GPU (one process per GPU) ------------------------------------ */
+/* Canonical partition (no reference exists): elements sorted by id, rank p owns the
+ * contiguous block [floor(p*Ne/P), floor((p+1)*Ne/P)); a node is local to every rank owning an element
+ * that references it; local node order = ascending global id; halo list per neighbour = shared global
+ * ids ascending.  Host-side, deterministic, no GPU needed. */
+typedef struct wf_partition wf_partition;
+int wf_partition_build(wf_partition **out, int nranks, int rank, int nodxelem, int n_nodes, int n_elems,
+                       const unsigned *elnod);
+/* same, for the AddBoxLength mesh without materialising the global connectivity */
+int wf_partition_build_box(wf_partition **out, int nranks, int rank, const double V[3], const double L[3],
+                           double r, int tritet);
+void wf_partition_free(wf_partition *);
+int wf_partition_info(const wf_partition *, int *elem_begin, int *elem_end, int *n_local_nodes, int *n_neigh);
+const int *wf_partition_node_l2g(const wf_partition *);            /* [n_local_nodes] */
+const unsigned *wf_partition_local_elnod(const wf_partition *);    /* [(elem_end-elem_begin)*k] */
+const int *wf_partition_neigh_ranks(const wf_partition *);         /* [n_neigh] ascending */
+const int *wf_partition_halo_offset(const wf_partition *);         /* [n_neigh+1] */
+const int *wf_partition_halo_nodes(const wf_partition *);          /* local node ids, grouped by neighbour */
+/* load the local part into an engine (replaces wf_set_mesh / wf_gen_box on that rank) */
+int wf_set_mesh_partition(wf_engine *, const wf_partition *, const double *x_local /*n_local*dim or NULL for box*/);
+/* split step: phases between which the caller exchanges halo partial sums (NCCL / peer memory).
+ *   phase 0: [predictor] + element volumes + local nodal partial sums -> pack halo (1 double / shared node)
+ *   phase 1: unpack+add remote partials (ascending rank order) + main element pass + local force partial
+ *            sums -> pack halo (dim doubles / shared node)
+ *   phase 2: unpack+add remote partials + integrate nodes */
+int wf_step_phase(wf_engine *, int phase, int last_step);
+int wf_halo_buffers(wf_engine *, void **send_dev, void **recv_dev, size_t *doubles_per_node_capacity);
+int wf_init_phase(wf_engine *, int phase, double dt); /* same split for wf_init (nodal vol_0 / mass sums) */
+
+/* ---- host-side helpers (no GPU needed; used by tests against the oracle) ------------------------- */
+int wf_host_box_counts(const double L[3], double r, int tritet, int *dim, int *nodxelem, int *n_nodes, int *n_elems);
+int wf_host_gen_box(const double V[3], const double L[3], double r, int tritet, double *x, unsigned *elnod);
+int wf_host_nodel(int n_nodes, int n_elems, int nodxelem, const unsigned *elnod, int *nodel_offset,
+                  int *nodel_count, int *nodel /*N_e*k*/, int *nodel_loc /*N_e*k*/);
+const char *wf_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* WF_ENGINE_H */

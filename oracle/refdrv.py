@@ -148,11 +148,18 @@ class _Base:
             raise KeyError(fn)
 
     @classmethod
+    def _ensure(cls):
+        if cls._lib is None:
+            cls().close()
+
+    @classmethod
     def set_threads(cls, n):
+        cls._ensure()
         getattr(cls._lib, cls._prefix + "set_threads")(int(n))
 
     @classmethod
     def max_threads(cls):
+        cls._ensure()
         return getattr(cls._lib, cls._prefix + "max_threads")()
 
     # ---- state ---------------------------------------------------------------------------------

@@ -1,0 +1,80 @@
+// wf_dev.h — private device-side view of one engine (passed by value to every kernel).
+//
+// HBM layout (private; the C ABI converts to/from the reference layouts):
+//   * every array is SoA ("component-major") with a pitch that is a multiple of 32
+//     elements, so lane i of a warp touches element i of a 256 B-aligned run:
+//       nodal vectors     q[c * np + n]           c < dim      (reference: q[dim*n + c])
+//       element 6-vectors t[c * ep + e]           c < 6        (reference: t[6*e + c])
+//       element-node recs f[(ln*dim + c) * ep + e]             (reference: f[(e*k + ln)*dim + c])
+//       connectivity      elnod[ln * ep + e]                   (reference: m_elnod[e*k + ln])
+//   * node->element connectivity (m_nodel / m_nodel_loc, Domain_d.h:1004-1007) is kept on the
+//     device as ONE packed array of "slots" slot = e*k + ln in sliced-ELL form: slice s = nodes
+//     [32s, 32s+32), width = max list length in the slice, entry j of node n at
+//     sell_ptr[s] + 32*j + (n & 31), -1 = padding.  List order == reference order (ascending
+//     element id), so gathers sum in exactly the reference's order and a warp reads 128 B rows.
+#pragma once
+#include <stdint.h>
+
+#define WF_MAXK 8
+
+struct WfDev {
+  int nn, ne, nslices;
+  int dim, k, domtype, vol_weight;
+  long long np, ep; /* pitches */
+
+  /* nodes */
+  double *x, *v, *prev_a, *u, *u_dt; /* [dim][np] persistent state */
+  double *fe;                        /* [dim][np] external force, NULL == 0 (m_fe) */
+  double *voln_sum;                  /* [np] sum of vol over nodel(n) (no /k) */
+  double *voln0_sum;                 /* [np] sum of vol_0 (press 0/1) or of vol_0/4.0 (press 3) */
+  double *nodal_p;                   /* [np] press 0: voln/voln_0 ; press 1/3: nodal pressure pn */
+  int *nodel_count;                  /* [np] */
+  int *bc_index;                     /* [np] -1 or row of bc_mask / bc_vals */
+  const unsigned char *bc_mask;      /* [nbc] bit c: dim c prescribed */
+  const double *bc_vals;             /* [nbc*3] */
+  const long long *sell_ptr;         /* [nslices+1] */
+  const int *sell_slots;
+  /* halo (multi-GPU): nodes whose partial sums are exchanged */
+  const int *halo_nodes; int n_halo;
+  double *halo_send, *halo_recv;
+
+  /* elements */
+  const int *elnod;                  /* [k][ep] */
+  double *tau;                       /* [6][ep] */
+  double *sigma;                     /* [6][ep] (optional per step) */
+  double *eps;                       /* [6][ep] (optional) */
+  double *p, *pl_strain, *sigma_y, *vol, *vol_0, *rho, *rho_0; /* [ep] */
+  double *hg_q;                      /* [2][ep] 2D quads (m_hg_q) */
+  double *f_elem;                    /* [k*dim][ep] */
+  double *f_elem_hg;                 /* [k*dim][ep] (strict / unfused only) */
+
+  /* unfused-path intermediates (allocated on first use) */
+  double *dH;                        /* [dim][k][ep] dN/dX * detJ (m_dH_detJ_dx/dy/dz) */
+  double *detJ, *radius;             /* [ep] */
+  double *str_rate, *rot_rate;       /* [6][ep] */
+  double *pl_incr;                   /* [6][ep] m_strain_pl_incr */
+  double *a, *fi;                    /* [dim][np] */
+  double *mdiag, *voln, *p_node;     /* [np] */
+
+  /* flags / reductions */
+  int *nonfinite;                    /* [1] */
+  unsigned long long *xmin_key;      /* [2] ordered-key of min x_r (axisymmetric axis constraint) */
+  double *red;                       /* [8] energy reductions */
+};
+
+struct WfPar {
+  /* material (Material.cuh) */
+  int model;
+  double Kbulk, G, sy0, Kh, mh, eps0, eps1, cs0;
+  /* StabilizationParams + hexa hourglass coefficient */
+  double alpha_free, hg_coeff_free, av_coeff_div, av_coeff_bulk, log_factor, pspg_scale, p_pspg_bulkfac, J_min;
+  double hg_visc, hg_stiff, hexa_hg;
+  int stab_simple; /* all pressure-stabilisation terms are zero -> p = -K (J_avg - 1) */
+  int press;
+  double av_alpha, av_beta;
+  int track_eps, store_sigma, strict;
+  /* time integration (Solver_explicit.C:193-197) */
+  double dt, alpha, beta, gamma;
+  double w; /* Gauss weight, Mechanical.C:269-282 */
+  int xmin_cur; /* which xmin_key slot holds min x_r of the current coordinates */
+};

@@ -1,0 +1,838 @@
+// wf_engine.cu — host side of the C ABI (include/wf_engine.h): owns device memory, mirrors the
+// call sequence of Domain_d::SolveChungHulbert() (src/explicit/Solver_explicit.C) and converts
+// between the reference's array layouts and the private device layouts (wf_dev.h).
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/wf_engine.h"
+#include "wf_dev.h"
+#include "wf_host.h"
+#include "wf_launch.h"
+#include "wf_math_ids.h"
+
+static std::string g_create_error;
+
+struct wf_engine {
+  int device = 0;
+  cudaStream_t stream = 0;
+  std::string err;
+  int dim = 3, k = 8, et = ET_HEX8, domtype = WF_3D;
+  int nn = 0, ne = 0;
+  WfDev d;
+  WfPar P;
+  const WfLaunch *L = nullptr;
+  bool strict = false;
+  int tracking = 0;
+  bool meshed = false, material_set = false, bcs_ready = false, inited = false, dbg = false;
+  bool predicted = false;  // v / u_dt currently hold next-step predictor values (only inside wf_step)
+  // which unfused-path products are current (cleared by wf_step)
+  bool a_in_dbg = false, fi_in_dbg = false, mdiag_in_dbg = false, sigma_in_dbg = false, rates_in_dbg = false;
+  double time = 0.0;
+  long step_count = 0;
+  wf_material mat;
+  wf_stab stab;
+  std::vector<void *> allocs;
+  // host copies of integer artefacts (reference layouts)
+  std::vector<unsigned> h_elnod;
+  std::vector<int> h_nodel, h_nodel_loc, h_offset, h_count;
+  std::vector<int> bc_nod[3];
+  std::vector<double> bc_val[3];
+  int nbc_rows = 0;
+  // partition / halo (multi-GPU)
+  std::vector<int> halo_nodes_h, halo_offset_h, neigh_h;
+  int *halo_nodes_d = nullptr;
+  double *halo_send = nullptr, *halo_recv = nullptr;
+  size_t halo_cap = 0;
+  bool distributed = false;
+};
+
+#define CK(call)                                                                          \
+  do {                                                                                    \
+    cudaError_t _e = (call);                                                              \
+    if (_e != cudaSuccess) {                                                              \
+      E->err = std::string(#call) + ": " + cudaGetErrorString(_e);                        \
+      return 1;                                                                           \
+    }                                                                                     \
+  } while (0)
+#define FAIL(msg) do { E->err = (msg); return 1; } while (0)
+#define NEED(cond, msg) do { if (!(cond)) FAIL(msg); } while (0)
+
+static inline long long round_up(long long a, long long b) { return (a + b - 1) / b * b; }
+
+template <class T>
+static int dalloc(wf_engine *E, T **p, size_t count) {
+  void *q = nullptr;
+  size_t bytes = std::max<size_t>(count, 1) * sizeof(T);
+  CK(cudaMalloc(&q, bytes));
+  CK(cudaMemsetAsync(q, 0, bytes, E->stream));
+  E->allocs.push_back(q);
+  *p = (T *)q;
+  return 0;
+}
+
+static int select_flavour(wf_engine *E) {
+  E->L = E->strict ? wf_strict_table() : wf_fast_table();
+  E->P.strict = E->strict ? 1 : 0;
+  return 0;
+}
+
+extern "C" const char *wf_version(void) { return "weldformfem_b200 0.1 (sm_100a, fp64)"; }
+
+extern "C" const char *wf_last_error(wf_engine *E) { return E ? E->err.c_str() : g_create_error.c_str(); }
+
+extern "C" int wf_create(wf_engine **out, int dim, int nodxelem, int domtype, int device) {
+  if (!out) return 1;
+  *out = nullptr;
+  int et = -1;
+  if (dim == 3 && nodxelem == 8) et = ET_HEX8;
+  else if (dim == 3 && nodxelem == 4) et = ET_TET4;
+  else if (dim == 2 && nodxelem == 4) et = ET_QUAD4;
+  else if (dim == 2 && nodxelem == 3) et = ET_TRI3;
+  if (et < 0) { g_create_error = "unsupported element: dim/nodxelem must be 3/8, 3/4, 2/4 or 2/3"; return 1; }
+  if ((dim == 3) != (domtype == WF_3D)) { g_create_error = "domtype does not match dim"; return 1; }
+  if (domtype == WF_PLANE_STRESS) { g_create_error = "plane stress is not implemented by the reference step either"; return 1; }
+  int ndev = 0;
+  cudaError_t ce = cudaGetDeviceCount(&ndev);
+  if (ce != cudaSuccess || ndev == 0) {
+    g_create_error = std::string("no CUDA device: ") + (ce != cudaSuccess ? cudaGetErrorString(ce) : "device count is 0") +
+                     " (this engine has no CPU fallback)";
+    return 2;
+  }
+  if (device < 0 || device >= ndev) { g_create_error = "bad device ordinal"; return 1; }
+  ce = cudaSetDevice(device);
+  if (ce != cudaSuccess) { g_create_error = cudaGetErrorString(ce); return 1; }
+  wf_engine *E = new wf_engine();
+  E->device = device; E->dim = dim; E->k = nodxelem; E->et = et; E->domtype = domtype;
+  memset(&E->d, 0, sizeof(E->d));
+  memset(&E->P, 0, sizeof(E->P));
+  memset(&E->mat, 0, sizeof(E->mat));
+  memset(&E->stab, 0, sizeof(E->stab));
+  E->stab.hg_stiff = 0.1; // Domain_d.h:294
+  E->d.dim = dim; E->d.k = nodxelem; E->d.domtype = domtype;
+  E->P.w = (et == ET_HEX8) ? 8.0 : (et == ET_TET4 ? 1.0 / 6.0 : (et == ET_QUAD4 ? 4.0 : 0.5));
+  E->P.stab_simple = 1;
+  E->P.hg_stiff = 0.1;
+  select_flavour(E);
+  *out = E;
+  return 0;
+}
+
+extern "C" void wf_destroy(wf_engine *E) {
+  if (!E) return;
+  cudaSetDevice(E->device);
+  cudaStreamSynchronize(E->stream);
+  for (void *p : E->allocs) cudaFree(p);
+  delete E;
+}
+
+extern "C" int wf_set_stream(wf_engine *E, void *s) { E->stream = (cudaStream_t)s; return 0; }
+extern "C" int wf_synchronize(wf_engine *E) { CK(cudaSetDevice(E->device)); CK(cudaStreamSynchronize(E->stream)); return 0; }
+
+extern "C" int wf_set_axisymm_vol_weight(wf_engine *E, int on) {
+  NEED(E->domtype == WF_AXISYMM, "vol_weight only applies to axisymmetric domains");
+  E->d.vol_weight = on ? 1 : 0;
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// mesh
+// ---------------------------------------------------------------------------------------------------
+static int upload_mesh(wf_engine *E, int nn, int ne, const double *x, const unsigned *elnod) {
+  NEED(!E->meshed, "mesh already set");
+  NEED(nn > 0 && ne > 0, "empty mesh");
+  CK(cudaSetDevice(E->device));
+  const int k = E->k, dim = E->dim;
+  NEED((long long)ne * k <= 2147483647LL, "connectivity exceeds 32-bit slot range");
+  E->nn = nn; E->ne = ne;
+  WfDev &d = E->d;
+  d.nn = nn; d.ne = ne;
+  d.np = round_up(nn, 32); d.ep = round_up(ne, 32);
+  d.nslices = (nn + 31) / 32;
+  // node -> element lists exactly like setNodElem
+  E->h_elnod.assign(elnod, elnod + (size_t)ne * k);
+  E->h_offset.resize(nn); E->h_count.resize(nn);
+  E->h_nodel.resize((size_t)ne * k); E->h_nodel_loc.resize((size_t)ne * k);
+  if (wf_host_nodel(nn, ne, k, elnod, E->h_offset.data(), E->h_count.data(), E->h_nodel.data(), E->h_nodel_loc.data()))
+    FAIL("connectivity entry out of range");
+  // sliced-ELL packing of slot = e*k + ln
+  std::vector<long long> sell_ptr(d.nslices + 1);
+  long long tot = 0;
+  for (int s = 0; s < d.nslices; s++) {
+    sell_ptr[s] = tot;
+    int w = 0;
+    for (int n = s * 32; n < std::min(nn, s * 32 + 32); n++) w = std::max(w, E->h_count[n]);
+    tot += (long long)w * 32;
+  }
+  sell_ptr[d.nslices] = tot;
+  std::vector<int> slots((size_t)tot, -1);
+  for (int n = 0; n < nn; n++) {
+    const long long base = sell_ptr[n >> 5];
+    const int off = E->h_offset[n];
+    for (int j = 0; j < E->h_count[n]; j++)
+      slots[(size_t)(base + (long long)j * 32 + (n & 31))] = E->h_nodel[off + j] * k + E->h_nodel_loc[off + j];
+  }
+  long long *dptr; int *dslots;
+  if (dalloc(E, &dptr, sell_ptr.size()) || dalloc(E, &dslots, slots.size())) return 1;
+  CK(cudaMemcpyAsync(dptr, sell_ptr.data(), sell_ptr.size() * sizeof(long long), cudaMemcpyHostToDevice, E->stream));
+  CK(cudaMemcpyAsync(dslots, slots.data(), slots.size() * sizeof(int), cudaMemcpyHostToDevice, E->stream));
+  d.sell_ptr = dptr; d.sell_slots = dslots;
+  // connectivity, SoA
+  {
+    std::vector<int> el((size_t)k * d.ep, 0);
+    for (int e = 0; e < ne; e++)
+      for (int n = 0; n < k; n++) el[(size_t)n * d.ep + e] = (int)elnod[(size_t)e * k + n];
+    int *del;
+    if (dalloc(E, &del, el.size())) return 1;
+    CK(cudaMemcpyAsync(del, el.data(), el.size() * sizeof(int), cudaMemcpyHostToDevice, E->stream));
+    d.elnod = del;
+    CK(cudaStreamSynchronize(E->stream));
+  }
+  // state
+  const size_t nv = (size_t)dim * d.np, e6 = (size_t)6 * d.ep, ekd = (size_t)k * dim * d.ep;
+  if (dalloc(E, &d.x, nv) || dalloc(E, &d.v, nv) || dalloc(E, &d.prev_a, nv) || dalloc(E, &d.u, nv) ||
+      dalloc(E, &d.u_dt, nv) || dalloc(E, &d.voln_sum, d.np) || dalloc(E, &d.voln0_sum, d.np) ||
+      dalloc(E, &d.nodal_p, d.np) || dalloc(E, &d.nodel_count, d.np) || dalloc(E, &d.bc_index, d.np) ||
+      dalloc(E, &d.tau, e6) || dalloc(E, &d.p, d.ep) || dalloc(E, &d.pl_strain, d.ep) ||
+      dalloc(E, &d.sigma_y, d.ep) || dalloc(E, &d.vol, d.ep) || dalloc(E, &d.vol_0, d.ep) ||
+      dalloc(E, &d.rho, d.ep) || dalloc(E, &d.rho_0, d.ep) || dalloc(E, &d.f_elem, ekd) ||
+      dalloc(E, &d.nonfinite, 1) || dalloc(E, &d.xmin_key, 2) || dalloc(E, &d.red, 8) || dalloc(E, &d.mdiag, d.np))
+    return 1;
+  if (E->et == ET_QUAD4 && dalloc(E, &d.hg_q, (size_t)2 * d.ep)) return 1;
+  {
+    std::vector<double> xs(nv, 0.0);
+    for (int n = 0; n < nn; n++)
+      for (int c = 0; c < dim; c++) xs[(size_t)c * d.np + n] = x[(size_t)n * dim + c];
+    CK(cudaMemcpyAsync(d.x, xs.data(), nv * sizeof(double), cudaMemcpyHostToDevice, E->stream));
+    std::vector<int> cnt(d.np, 1);
+    std::copy(E->h_count.begin(), E->h_count.end(), cnt.begin());
+    CK(cudaMemcpyAsync(d.nodel_count, cnt.data(), d.np * sizeof(int), cudaMemcpyHostToDevice, E->stream));
+    std::vector<int> bci(d.np, -1);
+    CK(cudaMemcpyAsync(d.bc_index, bci.data(), d.np * sizeof(int), cudaMemcpyHostToDevice, E->stream));
+    CK(cudaStreamSynchronize(E->stream));
+  }
+  E->meshed = true;
+  if (E->material_set) {
+    std::vector<double> r(d.ep, E->mat.rho0);
+    CK(cudaMemcpy(d.rho_0, r.data(), d.ep * sizeof(double), cudaMemcpyHostToDevice));
+  }
+  return 0;
+}
+
+extern "C" int wf_set_mesh(wf_engine *E, int nn, int ne, const double *x, const unsigned *elnod) {
+  NEED(x && elnod, "null mesh arrays");
+  return upload_mesh(E, nn, ne, x, elnod);
+}
+
+extern "C" int wf_gen_box(wf_engine *E, const double V[3], const double L[3], double r, int tritet) {
+  WfBox b;
+  wf_box_dims(L, r, tritet, &b);
+  NEED(b.dim == E->dim && b.k == E->k, "box element type does not match the engine's dim/nodxelem");
+  NEED(b.nn > 0 && b.ne > 0, "box has no elements");
+  NEED(b.nn <= 2147483647LL && b.ne * b.k <= 2147483647LL, "box exceeds 32-bit index range");
+  std::vector<double> x((size_t)b.nn * b.dim);
+  std::vector<unsigned> el((size_t)b.ne * b.k);
+  wf_host_gen_box(V, L, r, tritet, x.data(), el.data());
+  return upload_mesh(E, (int)b.nn, (int)b.ne, x.data(), el.data());
+}
+
+extern "C" int wf_get_counts(wf_engine *E, int *nn, int *ne, int *ntot) {
+  NEED(E->meshed, "no mesh");
+  if (nn) *nn = E->nn;
+  if (ne) *ne = E->ne;
+  if (ntot) *ntot = E->ne * E->k;
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// material / options / BCs
+// ---------------------------------------------------------------------------------------------------
+extern "C" int wf_set_material(wf_engine *E, const wf_material *m) {
+  NEED(m, "null material");
+  NEED(m->model == WF_BILINEAR || m->model == WF_HOLLOMON, "material model must be Bilinear or Hollomon");
+  E->mat = *m;
+  WfPar &P = E->P;
+  P.model = m->model;
+  P.Kbulk = m->E / (3.0 * (1.0 - 2.0 * m->nu)); // Elastic_, Material.cuh:24-28
+  P.G = m->E / (2.0 * (1.0 + m->nu));
+  P.sy0 = m->sy0;
+  if (m->model == WF_HOLLOMON) { // InitHollomon, Material.cuh:90-104
+    P.Kh = m->K; P.mh = m->m;
+    P.eps0 = m->sy0 / m->E;
+    P.eps1 = pow(m->sy0 / m->K, 1. / m->m);
+  }
+  P.cs0 = sqrt(P.Kbulk / m->rho0); // main.C:574
+  E->material_set = true;
+  if (E->meshed) {
+    CK(cudaSetDevice(E->device));
+    std::vector<double> r(E->d.ep, m->rho0);
+    CK(cudaMemcpy(E->d.rho_0, r.data(), E->d.ep * sizeof(double), cudaMemcpyHostToDevice));
+  }
+  return 0;
+}
+
+static void refresh_stab_simple(wf_engine *E) {
+  const wf_stab &s = E->stab;
+  E->P.stab_simple = (s.alpha_free == 0.0 && s.hg_coeff_free == 0.0 && s.av_coeff_div == 0.0 && s.av_coeff_bulk == 0.0 &&
+                      s.log_factor == 0.0 && s.pspg_scale == 0.0 && s.p_pspg_bulkfac == 0.0) ? 1 : 0;
+}
+
+extern "C" int wf_set_stab(wf_engine *E, const wf_stab *s) {
+  NEED(s, "null stab");
+  E->stab = *s;
+  WfPar &P = E->P;
+  P.alpha_free = s->alpha_free; P.hg_coeff_free = s->hg_coeff_free; P.av_coeff_div = s->av_coeff_div;
+  P.av_coeff_bulk = s->av_coeff_bulk; P.log_factor = s->log_factor; P.pspg_scale = s->pspg_scale;
+  P.p_pspg_bulkfac = s->p_pspg_bulkfac; P.J_min = s->J_min; P.hg_visc = s->hg_visc; P.hg_stiff = s->hg_stiff;
+  P.hexa_hg = s->hexa_hg_coeff;
+  refresh_stab_simple(E);
+  return 0;
+}
+
+extern "C" int wf_set_options(wf_engine *E, int press, double av_alpha, double av_beta, int strict) {
+  NEED(press == WF_PRESS_DEFAULT || press == WF_PRESS_ANP_SHIPPED || press == WF_PRESS_ANP_NODAL, "bad pressure algorithm");
+  NEED(!E->inited, "options must be set before wf_init");
+  E->P.press = press; E->P.av_alpha = av_alpha; E->P.av_beta = av_beta;
+  E->strict = strict != 0;
+  select_flavour(E);
+  return 0;
+}
+
+extern "C" int wf_set_tracking(wf_engine *E, int flags) {
+  NEED(!E->inited, "tracking must be set before wf_init");
+  E->tracking = flags;
+  return 0;
+}
+
+extern "C" int wf_add_bc_vel(wf_engine *E, int node, int dim, double val) {
+  NEED(dim >= 0 && dim < 3, "bad BC dim");
+  E->bc_nod[dim].push_back(node);
+  E->bc_val[dim].push_back(val);
+  E->bcs_ready = false;
+  return 0;
+}
+extern "C" int wf_add_bc_vel_array(wf_engine *E, int count, const int *node, const int *dim, const double *val) {
+  for (int i = 0; i < count; i++)
+    if (wf_add_bc_vel(E, node[i], dim[i], val[i])) return 1;
+  return 0;
+}
+
+extern "C" int wf_allocate_bcs(wf_engine *E) {
+  NEED(E->meshed, "AllocateBCs needs the mesh");
+  CK(cudaSetDevice(E->device));
+  // per node: mask of prescribed dims + values; a later AddBCVelNode on the same (node, dim) wins, which is
+  // what the serial scatter of ImposeBCV (Domain_d.C:1109-1121) produces
+  std::map<int, int> row_of;
+  std::vector<unsigned char> mask;
+  std::vector<double> vals;
+  for (int dd = 0; dd < E->dim; dd++)
+    for (size_t i = 0; i < E->bc_nod[dd].size(); i++) {
+      int n = E->bc_nod[dd][i];
+      NEED(n >= 0 && n < E->nn, "BC node out of range");
+      auto it = row_of.find(n);
+      int row;
+      if (it == row_of.end()) {
+        row = (int)mask.size();
+        row_of[n] = row;
+        mask.push_back(0);
+        vals.insert(vals.end(), 3, 0.0);
+      } else row = it->second;
+      mask[row] |= (unsigned char)(1u << dd);
+      vals[3 * (size_t)row + dd] = E->bc_val[dd][i];
+    }
+  std::vector<int> bci(E->d.np, -1);
+  for (auto &kv : row_of) bci[kv.first] = kv.second;
+  unsigned char *dm; double *dv;
+  if (dalloc(E, &dm, mask.size()) || dalloc(E, &dv, vals.size())) return 1;
+  if (!mask.empty()) {
+    CK(cudaMemcpyAsync(dm, mask.data(), mask.size(), cudaMemcpyHostToDevice, E->stream));
+    CK(cudaMemcpyAsync(dv, vals.data(), vals.size() * sizeof(double), cudaMemcpyHostToDevice, E->stream));
+  }
+  CK(cudaMemcpyAsync(E->d.bc_index, bci.data(), bci.size() * sizeof(int), cudaMemcpyHostToDevice, E->stream));
+  CK(cudaStreamSynchronize(E->stream));
+  E->d.bc_mask = dm; E->d.bc_vals = dv;
+  E->nbc_rows = (int)mask.size();
+  E->bcs_ready = true;
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// optional arrays
+// ---------------------------------------------------------------------------------------------------
+static int ensure_dbg(wf_engine *E) {
+  if (E->dbg) return 0;
+  WfDev &d = E->d;
+  const size_t nv = (size_t)E->dim * d.np, e6 = (size_t)6 * d.ep, ekd = (size_t)E->k * E->dim * d.ep;
+  if (dalloc(E, &d.dH, ekd) || dalloc(E, &d.detJ, d.ep) || dalloc(E, &d.radius, d.ep) || dalloc(E, &d.str_rate, e6) ||
+      dalloc(E, &d.rot_rate, e6) || dalloc(E, &d.a, nv) || dalloc(E, &d.fi, nv) || dalloc(E, &d.voln, d.np))
+    return 1;
+  if (!d.sigma && dalloc(E, &d.sigma, e6)) return 1;
+  if (!d.f_elem_hg && dalloc(E, &d.f_elem_hg, ekd)) return 1;
+  E->dbg = true;
+  return 0;
+}
+
+static int check_launch(wf_engine *E, const char *what) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) { E->err = std::string(what) + ": " + cudaGetErrorString(e); return 1; }
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// init + step
+// ---------------------------------------------------------------------------------------------------
+static int reset_xmin(wf_engine *E, int slot) {
+  // ordered key of 1000.0 (Solver_explicit.C:956 `double xmin = 1000.0`)
+  double v = 1000.0;
+  unsigned long long b;
+  memcpy(&b, &v, 8);
+  unsigned long long key = (b & 0x8000000000000000ull) ? ~b : (b | 0x8000000000000000ull);
+  CK(cudaMemcpyAsync(E->d.xmin_key + slot, &key, 8, cudaMemcpyHostToDevice, E->stream));
+  CK(cudaStreamSynchronize(E->stream));
+  return 0;
+}
+
+extern "C" int wf_init_phase(wf_engine *E, int phase, double dt) {
+  NEED(E->meshed && E->material_set, "wf_init needs mesh and material");
+  if (!E->bcs_ready && wf_allocate_bcs(E)) return 1;
+  CK(cudaSetDevice(E->device));
+  WfDev &d = E->d;
+  WfPar &P = E->P;
+  const size_t nv = (size_t)E->dim * d.np;
+  if (phase == 0) {
+    P.dt = dt;
+    const double rho_b = 0.818200; // Solver_explicit.C:193-197
+    P.alpha = (2.0 * rho_b - 1.0) / (1.0 + rho_b);
+    P.beta = (5.0 - 3.0 * rho_b) / ((1.0 + rho_b) * (1.0 + rho_b) * (2.0 - rho_b));
+    P.gamma = 1.5 - P.alpha;
+    P.track_eps = (E->tracking & 1) ? 1 : 0;
+    P.store_sigma = ((E->tracking & 2) || P.av_alpha != 0.0 || P.av_beta != 0.0) ? 1 : 0;
+    const size_t e6 = (size_t)6 * d.ep, ekd = (size_t)E->k * E->dim * d.ep;
+    if (P.track_eps && !d.eps && dalloc(E, &d.eps, e6)) return 1;
+    if (P.store_sigma && !d.sigma && dalloc(E, &d.sigma, e6)) return 1;
+    if (E->strict && !d.f_elem_hg && dalloc(E, &d.f_elem_hg, ekd)) return 1;
+    E->L->init_elem(d, P, E->stream); // InitValues
+    // Solver_explicit.C:176-190: v, a, u are zeroed inside the per-dimension loop, so only the LAST
+    // dimension's prescribed velocities survive initialisation
+    CK(cudaMemsetAsync(d.v, 0, nv * sizeof(double), E->stream));
+    CK(cudaMemsetAsync(d.u, 0, nv * sizeof(double), E->stream));
+    if (d.a) CK(cudaMemsetAsync(d.a, 0, nv * sizeof(double), E->stream));
+    E->L->impose_bc(d, E->dim - 1, 0, d.v, E->stream);
+    E->L->elem_vol(d, P, E->et, 0, E->stream);      // calcElemJAndDerivatives + CalcElemInitialVol/CalcElemVol
+    E->L->vol0_density(d, E->stream);               // vol_0 = vol ; calcElemDensity
+    E->L->node_vol(d, P, 0, E->distributed ? 1 : 0, E->stream); // sum vol_0 per node
+    if (check_launch(E, "wf_init phase 0")) return 1;
+    if (E->distributed) return 0;
+    phase = 1;
+  }
+  if (phase == 1) {
+    E->L->node_vol(d, P, 1, 0, E->stream);          // CalcNodalVol
+    if (E->domtype == WF_AXISYMM) {
+      P.xmin_cur = 0;
+      if (reset_xmin(E, 0)) return 1;
+      E->L->xmin(d, 0, E->stream);
+    }
+    if (check_launch(E, "wf_init phase 1")) return 1;
+    E->time = 0.0; E->step_count = 0; E->predicted = false;
+    E->a_in_dbg = E->fi_in_dbg = E->mdiag_in_dbg = E->sigma_in_dbg = E->rates_in_dbg = false;
+    E->inited = true;
+  }
+  return 0;
+}
+
+extern "C" int wf_init(wf_engine *E, double dt) {
+  NEED(!E->distributed, "distributed engines are initialised with wf_init_phase");
+  return wf_init_phase(E, 0, dt);
+}
+
+extern "C" int wf_step(wf_engine *E, int nsteps) {
+  NEED(E->inited, "wf_step before wf_init");
+  NEED(!E->distributed, "distributed engines step with wf_step_phase");
+  CK(cudaSetDevice(E->device));
+  WfDev &d = E->d;
+  WfPar &P = E->P;
+  const int sep = E->strict ? 1 : 0;
+  for (int s = 0; s < nsteps; s++) {
+    const bool last = (s == nsteps - 1);
+    if (!E->predicted) E->L->predict(d, P, 1, E->stream);
+    E->L->elem_vol(d, P, E->et, 0, E->stream);
+    E->L->node_vol(d, P, 1, 0, E->stream);
+    E->L->elem_main(d, P, E->et, sep, E->stream);
+    E->L->node_update(d, P, sep, last ? 0 : 1, 0, E->stream);
+    E->predicted = !last;
+    P.xmin_cur ^= 1;
+    E->time += P.dt;
+    E->step_count++;
+  }
+  E->a_in_dbg = E->fi_in_dbg = E->mdiag_in_dbg = E->sigma_in_dbg = E->rates_in_dbg = false;
+  return check_launch(E, "wf_step");
+}
+
+extern "C" int wf_step_phase(wf_engine *E, int phase, int last_step) {
+  (void)E; (void)phase; (void)last_step;
+  FAIL("wf_step_phase: distributed stepping is not wired yet");
+}
+extern "C" int wf_halo_buffers(wf_engine *E, void **s, void **r, size_t *cap) {
+  if (s) *s = E->halo_send;
+  if (r) *r = E->halo_recv;
+  if (cap) *cap = E->halo_cap;
+  return 0;
+}
+extern "C" int wf_set_mesh_partition(wf_engine *E, const wf_partition *p, const double *x_local) {
+  (void)p; (void)x_local;
+  FAIL("wf_set_mesh_partition: not wired yet");
+}
+
+extern "C" int wf_nonfinite_flag(wf_engine *E, int *flag) {
+  CK(cudaSetDevice(E->device));
+  int f = 0;
+  CK(cudaMemcpyAsync(&f, E->d.nonfinite, sizeof(int), cudaMemcpyDeviceToHost, E->stream));
+  CK(cudaStreamSynchronize(E->stream));
+  if (f) CK(cudaMemsetAsync(E->d.nonfinite, 0, sizeof(int), E->stream));
+  if (flag) *flag = f;
+  return 0;
+}
+
+extern "C" int wf_get_time(wf_engine *E, double *t, long *steps) {
+  if (t) *t = E->time;
+  if (steps) *steps = E->step_count;
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// unfused entry points (names = Domain_d members)
+// ---------------------------------------------------------------------------------------------------
+#define UNFUSED_PROLOGUE()                                        \
+  NEED(E->inited, "call wf_init first");                          \
+  NEED(!E->predicted, "engine is mid-batch");                     \
+  CK(cudaSetDevice(E->device));                                   \
+  if (ensure_dbg(E)) return 1;                                    \
+  WfDev &d = E->d; WfPar &P = E->P; (void)d; (void)P;
+
+extern "C" int wf_UpdatePrediction(wf_engine *E) { UNFUSED_PROLOGUE(); E->L->predict(d, P, 0, E->stream); return check_launch(E, __func__); }
+extern "C" int wf_ImposeBCV(wf_engine *E, int dd) { UNFUSED_PROLOGUE(); NEED(dd >= 0 && dd < E->dim, "bad dim"); E->L->impose_bc(d, dd, 0, d.v, E->stream); return check_launch(E, __func__); }
+extern "C" int wf_ImposeBCA(wf_engine *E, int dd) { UNFUSED_PROLOGUE(); NEED(dd >= 0 && dd < E->dim, "bad dim"); E->L->impose_bc(d, dd, 1, d.a, E->stream); return check_launch(E, __func__); }
+extern "C" int wf_calcElemJAndDerivatives(wf_engine *E) { UNFUSED_PROLOGUE(); E->L->elem_vol(d, P, E->et, 1, E->stream); return check_launch(E, __func__); }
+extern "C" int wf_Calc_Element_Radius(wf_engine *E) { UNFUSED_PROLOGUE(); E->L->elem_vol(d, P, E->et, 2, E->stream); return check_launch(E, __func__); }
+extern "C" int wf_CalcElemVol(wf_engine *E) { UNFUSED_PROLOGUE(); E->L->vol_from_detj(d, E->et, E->stream); return check_launch(E, __func__); }
+extern "C" int wf_CalcNodalVol(wf_engine *E) { UNFUSED_PROLOGUE(); E->L->u_nodal_vol(d, E->stream); return check_launch(E, __func__); }
+extern "C" int wf_CalcNodalMassFromVol(wf_engine *E) { UNFUSED_PROLOGUE(); E->L->node_mass(d, P, 1, E->stream); E->mdiag_in_dbg = true; return check_launch(E, __func__); }
+extern "C" int wf_calcElemStrainRates(wf_engine *E) { UNFUSED_PROLOGUE(); E->L->u_strain_rates(d, P, E->et, E->stream); E->rates_in_dbg = true; return check_launch(E, __func__); }
+extern "C" int wf_calcElemPressure(wf_engine *E) {
+  UNFUSED_PROLOGUE();
+  E->L->node_vol(d, P, 1, 0, E->stream);
+  E->L->u_pressure(d, P, E->et, E->stream);
+  return check_launch(E, __func__);
+}
+extern "C" int wf_CalcStressStrain(wf_engine *E, double dt) { UNFUSED_PROLOGUE(); E->L->u_stress(d, P, dt, E->stream); E->sigma_in_dbg = true; return check_launch(E, __func__); }
+extern "C" int wf_calcArtificialViscosity(wf_engine *E) { UNFUSED_PROLOGUE(); E->L->u_artvisc(d, P, E->stream); return check_launch(E, __func__); }
+extern "C" int wf_calcElemForces(wf_engine *E) { UNFUSED_PROLOGUE(); E->L->u_forces(d, P, E->et, E->stream); return check_launch(E, __func__); }
+extern "C" int wf_calcElemHourglassForces(wf_engine *E) { UNFUSED_PROLOGUE(); E->L->u_hourglass(d, P, E->et, E->stream); return check_launch(E, __func__); }
+extern "C" int wf_assemblyForces(wf_engine *E) { UNFUSED_PROLOGUE(); E->L->u_assembly(d, E->stream); E->fi_in_dbg = true; return check_launch(E, __func__); }
+extern "C" int wf_calcAccel(wf_engine *E) { UNFUSED_PROLOGUE(); E->L->u_accel(d, E->stream); E->a_in_dbg = true; return check_launch(E, __func__); }
+extern "C" int wf_UpdateCorrectionAccVel(wf_engine *E) { UNFUSED_PROLOGUE(); E->L->u_corr_accvel(d, P, E->stream); return check_launch(E, __func__); }
+extern "C" int wf_AxisConstraint(wf_engine *E) {
+  UNFUSED_PROLOGUE();
+  if (E->domtype != WF_AXISYMM) return 0;
+  if (reset_xmin(E, P.xmin_cur)) return 1;
+  E->L->xmin(d, P.xmin_cur, E->stream);
+  E->L->u_axis(d, P, E->stream);
+  return check_launch(E, __func__);
+}
+extern "C" int wf_UpdateCorrectionPos(wf_engine *E) {
+  UNFUSED_PROLOGUE();
+  E->L->u_corr_pos(d, P, E->stream);
+  E->time += P.dt; E->step_count++;
+  if (E->domtype == WF_AXISYMM) { // keep the fused path's running minimum consistent
+    if (reset_xmin(E, P.xmin_cur)) return 1;
+    E->L->xmin(d, P.xmin_cur, E->stream);
+  }
+  return check_launch(E, __func__);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// state access
+// ---------------------------------------------------------------------------------------------------
+enum Kind { K_NODEVEC, K_NODESCAL, K_ELEMSCAL, K_ELEM6, K_ELEMNODE, K_ELEMNODEVEC, K_HGQ, K_INT_HOST };
+
+struct ArrayRef {
+  Kind kind;
+  double *dev = nullptr;
+  const void *host = nullptr;
+  size_t bytes = 0;
+  int comp = 0; // for dH: which dimension
+  bool lazy_sigma = false, lazy_fi = false, lazy_mdiag = false, lazy_voln = false, lazy_pnode = false;
+};
+
+static bool lookup(wf_engine *E, const std::string &nm, ArrayRef &r, bool for_write) {
+  WfDev &d = E->d;
+  const size_t nd = sizeof(double) * (size_t)E->nn * E->dim, nnb = sizeof(double) * (size_t)E->nn;
+  const size_t neb = sizeof(double) * (size_t)E->ne, nk = neb * E->k;
+  auto nodevec = [&](double *p) { r.kind = K_NODEVEC; r.dev = p; r.bytes = nd; return p != nullptr; };
+  auto elems = [&](double *p) { r.kind = K_ELEMSCAL; r.dev = p; r.bytes = neb; return p != nullptr; };
+  auto elem6 = [&](double *p) { r.kind = K_ELEM6; r.dev = p; r.bytes = 6 * neb; return p != nullptr; };
+  if (nm == "x") return nodevec(d.x);
+  if (nm == "v") return nodevec(d.v);
+  if (nm == "u") return nodevec(d.u);
+  if (nm == "u_dt") return nodevec(d.u_dt);
+  if (nm == "prev_a") return nodevec(d.prev_a);
+  if (nm == "a") return nodevec((E->a_in_dbg || for_write) && d.a ? d.a : d.prev_a);
+  if (nm == "m_fe") return nodevec(d.fe);
+  if (nm == "m_fi") {
+    if (E->fi_in_dbg && d.fi) return nodevec(d.fi);
+    r.kind = K_NODEVEC; r.bytes = nd; r.lazy_fi = true; return !for_write;
+  }
+  if (nm == "m_mdiag") { r.kind = K_NODESCAL; r.dev = d.mdiag; r.bytes = nnb; r.lazy_mdiag = !E->mdiag_in_dbg; return true; }
+  if (nm == "m_voln") { r.kind = K_NODESCAL; r.dev = d.voln_sum; r.bytes = nnb; r.lazy_voln = true; return !for_write; }
+  if (nm == "p_node") { r.kind = K_NODESCAL; r.bytes = nnb; r.lazy_pnode = true; return !for_write; }
+  if (nm == "vol") return elems(d.vol);
+  if (nm == "vol_0") return elems(d.vol_0);
+  if (nm == "rho") return elems(d.rho);
+  if (nm == "rho_0") return elems(d.rho_0);
+  if (nm == "p") return elems(d.p);
+  if (nm == "pl_strain") return elems(d.pl_strain);
+  if (nm == "sigma_y") return elems(d.sigma_y);
+  if (nm == "m_detJ") return elems(d.detJ);
+  if (nm == "m_radius") return elems(d.radius);
+  if (nm == "m_tau") return elem6(d.tau);
+  if (nm == "m_eps") return elem6(d.eps);
+  if (nm == "m_str_rate") return elem6(d.str_rate);
+  if (nm == "m_rot_rate") return elem6(d.rot_rate);
+  if (nm == "m_sigma") {
+    if (d.sigma && (E->P.store_sigma || E->sigma_in_dbg || for_write)) return elem6(d.sigma);
+    r.kind = K_ELEM6; r.bytes = 6 * neb; r.lazy_sigma = true; return !for_write;
+  }
+  if (nm == "m_dH_detJ_dx" || nm == "m_dH_detJ_dy" || nm == "m_dH_detJ_dz") {
+    r.kind = K_ELEMNODE; r.dev = d.dH; r.bytes = nk; r.comp = nm.back() - 'x';
+    return d.dH != nullptr && r.comp < E->dim;
+  }
+  if (nm == "m_f_elem") { r.kind = K_ELEMNODEVEC; r.dev = d.f_elem; r.bytes = nk * E->dim; return true; }
+  if (nm == "m_f_elem_hg") { r.kind = K_ELEMNODEVEC; r.dev = d.f_elem_hg; r.bytes = nk * E->dim; return d.f_elem_hg != nullptr; }
+  if (nm == "m_hg_q") { r.kind = K_HGQ; r.dev = d.hg_q; r.bytes = nk * E->dim; return d.hg_q != nullptr; }
+  auto hosti = [&](const void *p, size_t b) { r.kind = K_INT_HOST; r.host = p; r.bytes = b; return !for_write; };
+  if (nm == "m_elnod") return hosti(E->h_elnod.data(), E->h_elnod.size() * sizeof(unsigned));
+  if (nm == "m_nodel") return hosti(E->h_nodel.data(), E->h_nodel.size() * sizeof(int));
+  if (nm == "m_nodel_loc") return hosti(E->h_nodel_loc.data(), E->h_nodel_loc.size() * sizeof(int));
+  if (nm == "m_nodel_offset") return hosti(E->h_offset.data(), E->h_offset.size() * sizeof(int));
+  if (nm == "m_nodel_count") return hosti(E->h_count.data(), E->h_count.size() * sizeof(int));
+  return false;
+}
+
+extern "C" size_t wf_array_bytes(wf_engine *E, const char *name) {
+  if (!E || !E->meshed || !name) return 0;
+  ArrayRef r;
+  if (!lookup(E, name, r, false)) return 0;
+  return r.bytes;
+}
+
+static int download(wf_engine *E, const double *dev, size_t count, std::vector<double> &h) {
+  h.resize(count);
+  CK(cudaMemcpyAsync(h.data(), dev, count * sizeof(double), cudaMemcpyDeviceToHost, E->stream));
+  CK(cudaStreamSynchronize(E->stream));
+  return 0;
+}
+
+extern "C" int wf_get_array(wf_engine *E, const char *name, void *dst, size_t bytes) {
+  NEED(E->meshed, "no mesh");
+  NEED(name && dst, "null argument");
+  NEED(!E->predicted, "engine is mid-batch");
+  CK(cudaSetDevice(E->device));
+  ArrayRef r;
+  if (!lookup(E, name, r, false))
+    FAIL(std::string("array '") + name + "' is unknown or only produced by the unfused entry points / tracking options");
+  NEED(bytes == r.bytes, std::string("size mismatch for '") + name + "'");
+  WfDev &d = E->d;
+  const int nn = E->nn, ne = E->ne, k = E->k, dim = E->dim;
+  double *out = (double *)dst;
+  std::vector<double> h;
+  if (r.kind == K_INT_HOST) { memcpy(dst, r.host, bytes); return 0; }
+  if (r.lazy_pnode) { // calcNodalPressureFromElemental (Mechanical.C:1187-1212), element-order scatter == nodel order
+    std::vector<double> p, vol;
+    if (download(E, d.p, d.ep, p) || download(E, d.vol, d.ep, vol)) return 1;
+    for (int n = 0; n < nn; n++) {
+      double acc = 0.0, pv = 0.0;
+      for (int j = 0; j < E->h_count[n]; j++) {
+        int e = E->h_nodel[E->h_offset[n] + j];
+        pv += p[e] * vol[e];
+        acc += vol[e];
+      }
+      if (acc > 0.0) pv /= acc;
+      out[n] = pv;
+    }
+    return 0;
+  }
+  if (r.lazy_sigma) {
+    double *tmp = nullptr;
+    CK(cudaMalloc((void **)&tmp, (size_t)6 * d.ep * sizeof(double)));
+    E->L->rebuild_sigma(d, tmp, E->stream);
+    int rc = download(E, tmp, (size_t)6 * d.ep, h);
+    cudaFree(tmp);
+    if (rc) return 1;
+  } else if (r.lazy_fi) {
+    NEED(E->step_count > 0 || E->dbg, "m_fi is available after a step");
+    double *save_fi = d.fi;
+    double *tmp = nullptr;
+    CK(cudaMalloc((void **)&tmp, (size_t)dim * d.np * sizeof(double)));
+    d.fi = tmp;
+    double *save_hg = d.f_elem_hg;
+    if (E->strict) {
+      E->L->u_assembly(d, E->stream);
+    } else { // fused hourglass: one-pass gather, exactly as k_node_update sums it
+      E->L->node_update(d, E->P, 0, 0, 1, E->stream);
+    }
+    int rc = download(E, tmp, (size_t)dim * d.np, h);
+    d.fi = save_fi; d.f_elem_hg = save_hg;
+    cudaFree(tmp);
+    if (rc) return 1;
+  } else {
+    if (r.lazy_mdiag) E->L->node_mass(d, E->P, 0, E->stream);
+    size_t count = 0;
+    switch (r.kind) {
+      case K_NODEVEC: count = (size_t)dim * d.np; break;
+      case K_NODESCAL: count = d.np; break;
+      case K_ELEMSCAL: count = d.ep; break;
+      case K_ELEM6: count = (size_t)6 * d.ep; break;
+      case K_ELEMNODE: case K_ELEMNODEVEC: count = (size_t)k * dim * d.ep; break;
+      case K_HGQ: count = (size_t)2 * d.ep; break;
+      default: break;
+    }
+    NEED(r.dev, std::string("array '") + name + "' is not allocated");
+    if (download(E, r.dev, count, h)) return 1;
+  }
+  switch (r.kind) {
+    case K_NODEVEC:
+      for (int n = 0; n < nn; n++)
+        for (int c = 0; c < dim; c++) out[(size_t)n * dim + c] = h[(size_t)c * d.np + n];
+      break;
+    case K_NODESCAL:
+      for (int n = 0; n < nn; n++) out[n] = r.lazy_voln ? h[n] / (double)k : h[n];
+      break;
+    case K_ELEMSCAL:
+      memcpy(out, h.data(), sizeof(double) * ne);
+      break;
+    case K_ELEM6:
+      for (int e = 0; e < ne; e++)
+        for (int c = 0; c < 6; c++) out[(size_t)e * 6 + c] = h[(size_t)c * d.ep + e];
+      break;
+    case K_ELEMNODE:
+      for (int e = 0; e < ne; e++)
+        for (int n = 0; n < k; n++) out[(size_t)e * k + n] = h[((size_t)r.comp * k + n) * d.ep + e];
+      break;
+    case K_ELEMNODEVEC:
+      for (int e = 0; e < ne; e++)
+        for (int n = 0; n < k; n++)
+          for (int c = 0; c < dim; c++) out[((size_t)e * k + n) * dim + c] = h[((size_t)n * dim + c) * d.ep + e];
+      break;
+    case K_HGQ:
+      memset(out, 0, bytes);
+      for (int e = 0; e < ne; e++)
+        for (int c = 0; c < 2; c++) out[(size_t)e * 2 + c] = h[(size_t)c * d.ep + e];
+      break;
+    default: break;
+  }
+  return 0;
+}
+
+extern "C" int wf_set_array(wf_engine *E, const char *name, const void *src, size_t bytes) {
+  NEED(E->meshed, "no mesh");
+  NEED(name && src, "null argument");
+  NEED(!E->predicted, "engine is mid-batch");
+  CK(cudaSetDevice(E->device));
+  WfDev &d = E->d;
+  const int nn = E->nn, ne = E->ne, k = E->k, dim = E->dim;
+  std::string nm(name);
+  if (nm == "m_fe" && !d.fe && dalloc(E, &d.fe, (size_t)dim * d.np)) return 1;
+  if (nm == "m_eps" && !d.eps) FAIL("m_eps needs wf_set_tracking(bit0) before wf_init");
+  if (nm == "m_sigma" && !d.sigma && dalloc(E, &d.sigma, (size_t)6 * d.ep)) return 1;
+  if (nm == "a") { if (ensure_dbg(E)) return 1; E->a_in_dbg = true; }
+  ArrayRef r;
+  if (!lookup(E, nm, r, true)) FAIL(std::string("array '") + name + "' cannot be set");
+  NEED(bytes == r.bytes, std::string("size mismatch for '") + name + "'");
+  const double *in = (const double *)src;
+  std::vector<double> h;
+  switch (r.kind) {
+    case K_NODEVEC:
+      h.assign((size_t)dim * d.np, 0.0);
+      for (int n = 0; n < nn; n++)
+        for (int c = 0; c < dim; c++) h[(size_t)c * d.np + n] = in[(size_t)n * dim + c];
+      break;
+    case K_NODESCAL:
+      h.assign(d.np, 0.0);
+      memcpy(h.data(), in, sizeof(double) * nn);
+      break;
+    case K_ELEMSCAL:
+      h.assign(d.ep, 0.0);
+      memcpy(h.data(), in, sizeof(double) * ne);
+      break;
+    case K_ELEM6:
+      h.assign((size_t)6 * d.ep, 0.0);
+      for (int e = 0; e < ne; e++)
+        for (int c = 0; c < 6; c++) h[(size_t)c * d.ep + e] = in[(size_t)e * 6 + c];
+      break;
+    case K_ELEMNODEVEC:
+      h.assign((size_t)k * dim * d.ep, 0.0);
+      for (int e = 0; e < ne; e++)
+        for (int n = 0; n < k; n++)
+          for (int c = 0; c < dim; c++) h[((size_t)n * dim + c) * d.ep + e] = in[((size_t)e * k + n) * dim + c];
+      break;
+    case K_HGQ:
+      h.assign((size_t)2 * d.ep, 0.0);
+      for (int e = 0; e < ne; e++)
+        for (int c = 0; c < 2; c++) h[(size_t)c * d.ep + e] = in[(size_t)e * 2 + c];
+      break;
+    default:
+      FAIL(std::string("array '") + name + "' cannot be set");
+  }
+  CK(cudaMemcpyAsync(r.dev, h.data(), h.size() * sizeof(double), cudaMemcpyHostToDevice, E->stream));
+  CK(cudaStreamSynchronize(E->stream));
+  if (nm == "x" && E->domtype == WF_AXISYMM && E->inited) {
+    if (reset_xmin(E, E->P.xmin_cur)) return 1;
+    E->L->xmin(d, E->P.xmin_cur, E->stream);
+  }
+  return 0;
+}
+
+extern "C" void *wf_device_ptr(wf_engine *E, const char *name, size_t *pitch) {
+  if (!E || !E->meshed) return nullptr;
+  ArrayRef r;
+  if (!lookup(E, name, r, true) || r.kind == K_INT_HOST) return nullptr;
+  if (pitch) *pitch = (r.kind == K_NODEVEC || r.kind == K_NODESCAL) ? (size_t)E->d.np : (size_t)E->d.ep;
+  return r.dev;
+}
+
+// computeEnergies (Mechanical.C:2145-2185).  Ekin from the current velocities and the nodal mass of the last
+// step; dEint needs the strain rates of the last step, which only the unfused path keeps.
+extern "C" int wf_energies(wf_engine *E, double *Ekin, double *dEint) {
+  NEED(E->inited, "wf_energies before wf_init");
+  NEED(!E->predicted, "engine is mid-batch");
+  CK(cudaSetDevice(E->device));
+  WfDev &d = E->d;
+  CK(cudaMemsetAsync(d.red, 0, 8 * sizeof(double), E->stream));
+  if (!E->mdiag_in_dbg) E->L->node_mass(d, E->P, 0, E->stream);
+  double *sig = d.sigma, *tmp = nullptr;
+  bool have_rates = d.str_rate != nullptr && E->rates_in_dbg;
+  if (have_rates && !(d.sigma && (E->P.store_sigma || E->sigma_in_dbg))) {
+    CK(cudaMalloc((void **)&tmp, (size_t)6 * d.ep * sizeof(double)));
+    E->L->rebuild_sigma(d, tmp, E->stream);
+    sig = tmp;
+  }
+  if (have_rates) E->L->energy(d, sig, E->stream);
+  else { // kinetic part only
+    WfDev d2 = d;
+    d2.ne = 0;
+    E->L->energy(d2, sig, E->stream);
+  }
+  double red[8];
+  CK(cudaMemcpyAsync(red, d.red, sizeof(red), cudaMemcpyDeviceToHost, E->stream));
+  CK(cudaStreamSynchronize(E->stream));
+  if (tmp) cudaFree(tmp);
+  if (Ekin) *Ekin = red[0];
+  if (dEint) *dEint = have_rates ? red[1] * E->P.dt : NAN;
+  return check_launch(E, "wf_energies");
+}

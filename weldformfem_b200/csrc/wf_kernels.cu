@@ -1,0 +1,868 @@
+// wf_kernels.cu — the CUDA kernels of the explicit step (sm_100a, fp64).
+//
+// Compiled TWICE into the same library:
+//   -DWF_NS=wf_strict -fmad=false : operation-for-operation with the reference CPU path
+//   -DWF_NS=wf_fast   -fmad=true  : same source, FMA contraction on; plus the regrouped hexa kernel
+// Each flavour exports one launcher table (wf_launch.h).
+//
+// Per step the fused schedule is four passes:
+//   E1 k_elem_vol    : x -> vol                                  (calcElemJAndDerivatives + CalcElemVol)
+//   N1 k_node_vol    : vol gather -> nodal sums / ratios         (CalcNodalVol, node part of calcElemPressure*)
+//   E2 k_elem_main   : J, dH, D, W, pressure, Jaumann + J2 return, element + hourglass forces
+//   N2 k_node_update : force gather, mass, accel, BCs, corrector, position, next-step predictor
+#include <cuda_runtime.h>
+#include <math.h>
+
+#include "wf_launch.h"
+#include "wf_math.cuh"
+
+#ifndef WF_NS
+#error "compile with -DWF_NS=wf_strict or -DWF_NS=wf_fast"
+#endif
+
+namespace WF_NS {
+
+constexpr int TPB_E = 128; // element kernels: register-heavy
+constexpr int TPB_N = 256; // node kernels (multiple of 32: one warp == one SELL slice)
+
+// ---------------------------------------------------------------------------------------------
+// gathers of element-local node data
+// ---------------------------------------------------------------------------------------------
+template <int ET>
+WF_DI void load_conn(const WfDev &d, int e, int (&nid)[Elem<ET>::K]) {
+#pragma unroll
+  for (int n = 0; n < Elem<ET>::K; n++) nid[n] = __ldg(d.elnod + (long long)n * d.ep + e);
+}
+template <int ET>
+WF_DI void gather_nodal(const double *__restrict__ q, long long np, const int (&nid)[Elem<ET>::K],
+                        double (&out)[Elem<ET>::K][Elem<ET>::D]) {
+#pragma unroll
+  for (int n = 0; n < Elem<ET>::K; n++)
+#pragma unroll
+    for (int c = 0; c < Elem<ET>::D; c++) out[n][c] = q[(long long)c * np + nid[n]];
+}
+
+// ---------------------------------------------------------------------------------------------
+// predictor (UpdatePrediction, Domain_d.C:961-974) + ImposeBCV for all dims (:1109-1121)
+// ---------------------------------------------------------------------------------------------
+template <int D>
+WF_DI void apply_bcv(const WfDev &d, int n, double (&v)[D]) {
+  int bi = d.bc_index[n];
+  if (bi >= 0) {
+    unsigned m = d.bc_mask[bi];
+#pragma unroll
+    for (int c = 0; c < D; c++)
+      if (m & (1u << c)) v[c] = d.bc_vals[3 * bi + c];
+  }
+}
+
+template <int D>
+__global__ void __launch_bounds__(TPB_N) k_predict(WfDev d, WfPar P, int with_bc) {
+  int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= d.nn) return;
+  double v[D];
+#pragma unroll
+  for (int c = 0; c < D; c++) {
+    long long i = (long long)c * d.np + n;
+    double pa = d.prev_a[i], vv = d.v[i];
+    d.u_dt[i] = P.dt * (vv + (0.5 - P.beta) * P.dt * pa);
+    v[c] = vv + (1.0 - P.gamma) * P.dt * pa;
+  }
+  if (with_bc) apply_bcv<D>(d, n, v);
+#pragma unroll
+  for (int c = 0; c < D; c++) d.v[(long long)c * d.np + n] = v[c];
+}
+
+// ImposeBCV(d) / ImposeBCA(d) as standalone kernels (unfused path)
+__global__ void k_impose_bc(WfDev d, int dim, int is_acc, double *a_or_v) {
+  int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= d.nn) return;
+  int bi = d.bc_index[n];
+  if (bi < 0) return;
+  if (d.bc_mask[bi] & (1u << dim)) a_or_v[(long long)dim * d.np + n] = is_acc ? 0.0 : d.bc_vals[3 * bi + dim];
+}
+
+// ---------------------------------------------------------------------------------------------
+// E1: element volume from current coordinates
+// ---------------------------------------------------------------------------------------------
+template <int ET>
+__global__ void __launch_bounds__(TPB_E) k_elem_vol(WfDev d, WfPar P, int store_jac) {
+  constexpr int K = Elem<ET>::K, D = Elem<ET>::D;
+  int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= d.ne) return;
+  int nid[K];
+  load_conn<ET>(d, e, nid);
+  double xl[K][D], A[D][D], detJ;
+  gather_nodal<ET>(d.x, d.np, nid, xl);
+  jac_adj_det<ET>(xl, A, detJ);
+  double radius = 0.0;
+  if (D == 2 && d.domtype == 2) radius = elem_radius<ET>(xl);
+  if (store_jac) { // unfused calcElemJAndDerivatives / Calc_Element_Radius products
+    double dH[D][K];
+    shape_derivs<ET>(A, dH);
+#pragma unroll
+    for (int c = 0; c < D; c++)
+#pragma unroll
+      for (int n = 0; n < K; n++) d.dH[((long long)c * K + n) * d.ep + e] = dH[c][n];
+    d.detJ[e] = detJ;
+    if (store_jac == 2) { d.radius[e] = radius; return; }
+    if (store_jac == 1) return;
+  }
+  d.vol[e] = elem_volume<ET>(detJ, radius, d.domtype, d.vol_weight);
+}
+
+// CalcElemVol on stored detJ / radius (unfused)
+template <int ET>
+__global__ void k_vol_from_detj(WfDev d) {
+  int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= d.ne) return;
+  d.vol[e] = elem_volume<ET>(d.detJ[e], d.radius ? d.radius[e] : 0.0, d.domtype, d.vol_weight);
+}
+
+// ---------------------------------------------------------------------------------------------
+// N1: nodal gathers of element volume (one warp == one SELL slice)
+//   mode 0 (init)  : voln0_sum = sum vol_0 (or sum vol_0/4.0 for press 3)
+//   mode 1 (step)  : voln_sum = sum vol ; nodal_p = ratio (press 0) or nodal pressure (press 1/3)
+// CalcNodalVol (Mechanical.C:1555-1572) and the node loops of calcElemPressure (:697-705),
+// calcElemPressureANP (:1228-1240), calcElemPressureANP_Nodal (:1262-1284).
+// ---------------------------------------------------------------------------------------------
+template <int K>
+__global__ void __launch_bounds__(TPB_N) k_node_vol(WfDev d, WfPar P, int mode, int local_only) {
+  int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n == 0 && mode == 1 && d.xmin_key) d.xmin_key[P.xmin_cur ^ 1] = dbl_key(1000.0);
+  int slice = n >> 5;
+  if (slice >= d.nslices) return;
+  const long long base = d.sell_ptr[slice];
+  const int width = (int)((d.sell_ptr[slice + 1] - base) >> 5);
+  const int lane = n & 31;
+  double s = 0.0, sq = 0.0;
+  const double *src = (mode == 0) ? d.vol_0 : d.vol;
+  const bool quarter = (P.press == 3);
+  for (int j = 0; j < width; j++) {
+    int slot = __ldg(d.sell_slots + base + ((long long)j << 5) + lane);
+    if (slot >= 0) {
+      double ve = src[slot / K];
+      s += ve;
+      if (quarter) sq += ve / 4.0;
+    }
+  }
+  if (n >= d.nn) return;
+  if (mode == 0) {
+    d.voln0_sum[n] = quarter ? sq : s;
+    return;
+  }
+  d.voln_sum[n] = s;
+  if (local_only) { // multi-GPU: partial sums; ratios are formed after the halo exchange
+    d.nodal_p[n] = quarter ? sq : s;
+    return;
+  }
+  if (P.press == 0) d.nodal_p[n] = s / d.voln0_sum[n];
+  else if (P.press == 1) d.nodal_p[n] = P.Kbulk * (1.0 - s / d.voln0_sum[n]);
+  else {
+    double v0 = d.voln0_sum[n], pn = 0.0;
+    if (v0 > 1e-12) { double Jn = sq / v0; pn = P.Kbulk * (1.0 - Jn); }
+    d.nodal_p[n] = pn;
+  }
+}
+
+// after a halo exchange the summed partials are turned into ratios / nodal pressures
+__global__ void k_node_vol_finish(WfDev d, WfPar P) {
+  int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= d.nn) return;
+  double s = d.nodal_p[n];
+  if (P.press == 0) d.nodal_p[n] = s / d.voln0_sum[n];
+  else if (P.press == 1) d.nodal_p[n] = P.Kbulk * (1.0 - s / d.voln0_sum[n]);
+  else {
+    double v0 = d.voln0_sum[n], pn = 0.0;
+    if (v0 > 1e-12) { double Jn = s / v0; pn = P.Kbulk * (1.0 - Jn); }
+    d.nodal_p[n] = pn;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// E2: the main element pass
+// ---------------------------------------------------------------------------------------------
+template <int ET>
+WF_DI double elem_pressure(const WfDev &d, const WfPar &P, int e, const int (&nid)[Elem<ET>::K], double vol,
+                           double vol0, double rho_e, const double (&dH)[Elem<ET>::D][Elem<ET>::K],
+                           const double (&vl)[Elem<ET>::K][Elem<ET>::D]) {
+  constexpr int K = Elem<ET>::K, D = Elem<ET>::D;
+  if (P.press == 0) {
+    if constexpr (D == 3) {
+      double J_avg = 0.0;
+#pragma unroll
+      for (int a = 0; a < K; a++) J_avg += d.nodal_p[nid[a]];
+      J_avg /= (double)K;
+      double div_v = 0.0;
+      if (!P.stab_simple) {
+#pragma unroll
+        for (int a = 0; a < K; a++) div_v += dH[0][a] * vl[a][0] + dH[1][a] * vl[a][1] + dH[2][a] * vl[a][2];
+      }
+      return pressure_default3d(P, J_avg, vol0, vol, rho_e, div_v);
+    } else {
+      return P.Kbulk * (1.0 - vol / vol0); // calcElemPressureLocal, Mechanical.C:1165-1170
+    }
+  } else if (P.press == 1) { // as shipped: p += sum pn ; p *= 0.25 k  (Mechanical.C:1243-1247)
+    double pe = d.p[e];
+#pragma unroll
+    for (int a = 0; a < K; a++) pe += d.nodal_p[nid[a]];
+    pe *= 0.25 * K;
+    return pe;
+  } else { // ANP_Nodal (Mechanical.C:1287-1294)
+    double pe = 0.0;
+#pragma unroll
+    for (int a = 0; a < K; a++) pe += d.nodal_p[nid[a]];
+    pe /= (double)K;
+    return pe;
+  }
+}
+
+// mode bits: 1 = hourglass force kept separate in f_elem_hg (strict two-pass assembly)
+template <int ET, bool SEPARATE_HG>
+__global__ void __launch_bounds__(TPB_E) k_elem_main(WfDev d, WfPar P) {
+  constexpr int K = Elem<ET>::K, D = Elem<ET>::D;
+  int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= d.ne) return;
+  int nid[K];
+  load_conn<ET>(d, e, nid);
+  double xl[K][D], vl[K][D], A[D][D], dH[D][K], detJ;
+  gather_nodal<ET>(d.x, d.np, nid, xl);
+  gather_nodal<ET>(d.v, d.np, nid, vl);
+  // independent loads issued early
+  double tau[6];
+#pragma unroll
+  for (int i = 0; i < 6; i++) tau[i] = d.tau[(long long)i * d.ep + e];
+  double pl = d.pl_strain[e];
+  const double rho_e = d.rho[e];
+  const double vol0 = d.vol_0[e];
+  const double sy_prev = d.sigma_y[e];
+
+  jac_adj_det<ET>(xl, A, detJ);
+  double radius = 0.0;
+  if (D == 2 && d.domtype == 2) radius = elem_radius<ET>(xl);
+  const double vol = elem_volume<ET>(detJ, radius, d.domtype, d.vol_weight);
+  shape_derivs<ET>(A, dH);
+  double Dr[6], Wr[3];
+  strain_rates<ET>(dH, detJ, vl, radius, d.domtype, Dr, Wr);
+  const double p = elem_pressure<ET>(d, P, e, nid, vol, vol0, rho_e, dH, vl);
+  StressOut so;
+  stress_update(P, P.dt, p, Dr, Wr, tau, pl, sy_prev, so);
+  if (P.track_eps) {
+#pragma unroll
+    for (int i = 0; i < 6; i++) {
+      long long o = (long long)i * d.ep + e;
+      d.eps[o] = d.eps[o] + P.dt * Dr[i];
+    }
+  }
+  if (P.av_alpha != 0.0 || P.av_beta != 0.0) artificial_viscosity(P, Dr, rho_e, vol, so.sig);
+#pragma unroll
+  for (int i = 0; i < 6; i++) d.tau[(long long)i * d.ep + e] = tau[i];
+  if (P.store_sigma) {
+#pragma unroll
+    for (int i = 0; i < 6; i++) d.sigma[(long long)i * d.ep + e] = so.sig[i];
+  }
+  d.pl_strain[e] = pl;
+  d.sigma_y[e] = so.sy;
+  d.p[e] = p;
+
+  double f[K][D];
+  elem_forces<ET>(dH, so.sig, detJ, radius, d.domtype, d.vol_weight, f);
+  // hourglass control
+  if constexpr (ET == ET_HEX8) {
+    if (P.hexa_hg != 0.0) {
+      double fh[K][D];
+      hexa_hourglass(P, vl, vol, rho_e, fh);
+      if (SEPARATE_HG) {
+#pragma unroll
+        for (int n = 0; n < K; n++)
+#pragma unroll
+          for (int c = 0; c < D; c++) d.f_elem_hg[((long long)n * D + c) * d.ep + e] = fh[n][c];
+      } else {
+#pragma unroll
+        for (int n = 0; n < K; n++)
+#pragma unroll
+          for (int c = 0; c < D; c++) f[n][c] -= fh[n][c];
+      }
+    }
+  } else if constexpr (ET == ET_QUAD4) {
+    double q[2] = {d.hg_q[e], d.hg_q[d.ep + e]};
+    double fh[K][D];
+    quad_hourglass(P, vl, vol, rho_e, q, fh);
+    d.hg_q[e] = q[0];
+    d.hg_q[d.ep + e] = q[1];
+    if (SEPARATE_HG) {
+#pragma unroll
+      for (int n = 0; n < K; n++)
+#pragma unroll
+        for (int c = 0; c < D; c++) d.f_elem_hg[((long long)n * D + c) * d.ep + e] = fh[n][c];
+    } else {
+#pragma unroll
+      for (int n = 0; n < K; n++)
+#pragma unroll
+        for (int c = 0; c < D; c++) f[n][c] -= fh[n][c];
+    }
+  }
+#pragma unroll
+  for (int n = 0; n < K; n++)
+#pragma unroll
+    for (int c = 0; c < D; c++) d.f_elem[((long long)n * D + c) * d.ep + e] = f[n][c];
+}
+
+// ---------------------------------------------------------------------------------------------
+// N2: force gather (assemblyForces, Matrices.C:42-87), nodal mass (CalcNodalMassFromVol,
+// Mechanical.C:1576-1601), calcAccel (:321-341), ImposeBCA, UpdateCorrectionAccVel
+// (Domain_d.C:981-997), ImposeBCV, axis constraint (Solver_explicit.C:953-969),
+// UpdateCorrectionPos (Domain_d.C:1005-1025) and, unless this is the last step of the batch,
+// the next step's UpdatePrediction + ImposeBCV.
+//   phase 0 = everything;  phase 1 = gather only, partial sums to d.fi (multi-GPU);
+//   phase 2 = integrate from d.fi / d.voln_sum (after halo exchange)
+// ---------------------------------------------------------------------------------------------
+template <int K, int D, bool SEPARATE_HG>
+__global__ void __launch_bounds__(TPB_N) k_node_update(WfDev d, WfPar P, int fuse_predictor, int phase) {
+  int n = blockIdx.x * blockDim.x + threadIdx.x;
+  int slice = n >> 5;
+  if (slice >= d.nslices) return;
+  const int lane = n & 31;
+  double fi[D];
+#pragma unroll
+  for (int c = 0; c < D; c++) fi[c] = 0.0;
+  double mass = 0.0;
+  if (phase != 2) {
+    const long long base = d.sell_ptr[slice];
+    const int width = (int)((d.sell_ptr[slice + 1] - base) >> 5);
+    const bool valid = n < d.nn;
+    const int cnt = valid ? d.nodel_count[n] : 1;
+    const double voln = valid ? d.voln_sum[n] / (double)K : 0.0; // m_voln[n] /= m_nodxelem
+    for (int j = 0; j < width; j++) {
+      int slot = __ldg(d.sell_slots + base + ((long long)j << 5) + lane);
+      if (slot >= 0) {
+        int e = slot / K, ln = slot - e * K;
+#pragma unroll
+        for (int c = 0; c < D; c++) fi[c] += d.f_elem[((long long)ln * D + c) * d.ep + e];
+        if (phase == 0) mass += 1.0 * d.rho[e] * voln / cnt;
+      }
+    }
+    if (SEPARATE_HG) {
+      for (int j = 0; j < width; j++) {
+        int slot = __ldg(d.sell_slots + base + ((long long)j << 5) + lane);
+        if (slot >= 0) {
+          int e = slot / K, ln = slot - e * K;
+#pragma unroll
+          for (int c = 0; c < D; c++) fi[c] -= d.f_elem_hg[((long long)ln * D + c) * d.ep + e];
+        }
+      }
+    }
+  }
+  if (n >= d.nn) return;
+  if (phase == 1) {
+#pragma unroll
+    for (int c = 0; c < D; c++) d.fi[(long long)c * d.np + n] = fi[c];
+    return;
+  }
+  if (phase == 2) {
+#pragma unroll
+    for (int c = 0; c < D; c++) fi[c] = d.fi[(long long)c * d.np + n];
+    mass = d.mdiag[n];
+  }
+  // non-finite scrub (Solver_explicit.C:779-784)
+#pragma unroll
+  for (int c = 0; c < D; c++)
+    if (!isfinite(fi[c])) { fi[c] = 0.0; *d.nonfinite = 1; }
+
+  int bi = d.bc_index[n];
+  unsigned bm = (bi >= 0) ? d.bc_mask[bi] : 0u;
+  const double f = 1.0 / (1.0 - P.alpha);
+  double a[D], v[D];
+#pragma unroll
+  for (int c = 0; c < D; c++) {
+    long long i = (long long)c * d.np + n;
+    double fe = d.fe ? d.fe[i] : 0.0;
+    a[c] = (fe - fi[c]) / mass;
+    if (bm & (1u << c)) a[c] = 0.0;
+    double pa = d.prev_a[i];
+    a[c] = f * (a[c] - P.alpha * pa);
+    v[c] = d.v[i] + P.gamma * P.dt * a[c];
+    if (bm & (1u << c)) v[c] = d.bc_vals[3 * bi + c];
+  }
+  double xr = d.x[n];
+  if (d.domtype == 2) {
+    double xmin = key_dbl(d.xmin_key[P.xmin_cur]);
+    if (xr <= xmin + 1.e-6) { a[0] = 0.0; v[0] = 0.0; }
+  }
+#pragma unroll
+  for (int c = 0; c < D; c++) {
+    long long i = (long long)c * d.np + n;
+    double udt = d.u_dt[i] + P.beta * P.dt * P.dt * a[c];
+    double xn = d.x[i] + udt;
+    d.x[i] = xn;
+    if (c == 0) xr = xn;
+    d.prev_a[i] = a[c];
+    d.u[i] = d.u[i] + udt;
+    if (fuse_predictor) {
+      d.u_dt[i] = P.dt * (v[c] + (0.5 - P.beta) * P.dt * a[c]);
+      v[c] = v[c] + (1.0 - P.gamma) * P.dt * a[c];
+      if (bm & (1u << c)) v[c] = d.bc_vals[3 * bi + c];
+    } else {
+      d.u_dt[i] = udt;
+    }
+    d.v[i] = v[c];
+  }
+  if (d.domtype == 2) atomicMin(d.xmin_key + (P.xmin_cur ^ 1), dbl_key(xr));
+}
+
+// nodal mass only (init, unfused CalcNodalVol + CalcNodalMassFromVol, lazy m_mdiag)
+template <int K>
+__global__ void __launch_bounds__(TPB_N) k_node_mass(WfDev d, WfPar P, int use_stored_voln) {
+  int n = blockIdx.x * blockDim.x + threadIdx.x;
+  int slice = n >> 5;
+  if (slice >= d.nslices) return;
+  const long long base = d.sell_ptr[slice];
+  const int width = (int)((d.sell_ptr[slice + 1] - base) >> 5);
+  const int lane = n & 31;
+  const bool valid = n < d.nn;
+  const int cnt = valid ? d.nodel_count[n] : 1;
+  const double voln = valid ? (use_stored_voln ? d.voln[n] : d.voln_sum[n] / (double)K) : 0.0;
+  double mass = 0.0;
+  for (int j = 0; j < width; j++) {
+    int slot = __ldg(d.sell_slots + base + ((long long)j << 5) + lane);
+    if (slot >= 0) mass += 1.0 * d.rho[slot / K] * voln / cnt;
+  }
+  if (valid) d.mdiag[n] = mass;
+}
+
+// ---------------------------------------------------------------------------------------------
+// small utility kernels
+// ---------------------------------------------------------------------------------------------
+__global__ void k_init_elem(WfDev d, WfPar P) { // InitValues (Domain_d.C:393-415)
+  int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= d.ne) return;
+  d.pl_strain[e] = 0.0;
+  d.sigma_y[e] = P.sy0;
+}
+__global__ void k_vol0_density(WfDev d) { // CalcElemInitialVol (:343) + calcElemDensity (:295)
+  int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= d.ne) return;
+  double v = d.vol[e];
+  d.vol_0[e] = v;
+  d.rho[e] = d.rho_0[e] * v / v;
+}
+__global__ void k_density(WfDev d) {
+  int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= d.ne) return;
+  d.rho[e] = d.rho_0[e] * d.vol_0[e] / d.vol[e];
+}
+__global__ void k_xmin(WfDev d, int slot) {
+  int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= d.nn) return;
+  atomicMin(d.xmin_key + slot, dbl_key(d.x[n]));
+}
+// sigma = -p I + tau, rebuilt on request when it is not stored per step (Mechanical.C:1775)
+__global__ void k_rebuild_sigma(WfDev d, double *out) {
+  int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= d.ne) return;
+  double mp = -d.p[e];
+#pragma unroll
+  for (int i = 0; i < 6; i++) out[(long long)i * d.ep + e] = mp * (i < 3 ? 1. : 0.) + d.tau[(long long)i * d.ep + e];
+}
+
+// computeEnergies (Mechanical.C:2145-2185): block-reduced, then atomics in double (diagnostic only)
+template <int D>
+__global__ void k_energy_kin(WfDev d) {
+  int n = blockIdx.x * blockDim.x + threadIdx.x;
+  double k = 0.0;
+  if (n < d.nn) {
+    double s = 0.0;
+#pragma unroll
+    for (int c = 0; c < D; c++) { double vv = d.v[(long long)c * d.np + n]; s += vv * vv; }
+    k = 0.5 * d.mdiag[n] * s;
+  }
+  for (int o = 16; o > 0; o >>= 1) k += __shfl_down_sync(0xffffffffu, k, o);
+  if ((threadIdx.x & 31) == 0 && k != 0.0) atomicAdd(d.red + 0, k);
+}
+__global__ void k_energy_int(WfDev d, const double *sig) {
+  int e = blockIdx.x * blockDim.x + threadIdx.x;
+  double k = 0.0;
+  if (e < d.ne) {
+    double s = 0.0;
+#pragma unroll
+    for (int i = 0; i < 6; i++) s += sig[(long long)i * d.ep + e] * d.str_rate[(long long)i * d.ep + e];
+    k = s * d.vol[e];
+  }
+  for (int o = 16; o > 0; o >>= 1) k += __shfl_down_sync(0xffffffffu, k, o);
+  if ((threadIdx.x & 31) == 0 && k != 0.0) atomicAdd(d.red + 1, k);
+}
+
+// ---------------------------------------------------------------------------------------------
+// unfused element kernels on stored intermediates (parity bisecting)
+// ---------------------------------------------------------------------------------------------
+template <int ET>
+WF_DI void load_dH(const WfDev &d, int e, double (&dH)[Elem<ET>::D][Elem<ET>::K]) {
+#pragma unroll
+  for (int c = 0; c < Elem<ET>::D; c++)
+#pragma unroll
+    for (int n = 0; n < Elem<ET>::K; n++) dH[c][n] = d.dH[((long long)c * Elem<ET>::K + n) * d.ep + e];
+}
+
+template <int ET>
+__global__ void k_u_strain_rates(WfDev d, WfPar P) {
+  constexpr int K = Elem<ET>::K, D = Elem<ET>::D;
+  int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= d.ne) return;
+  int nid[K];
+  load_conn<ET>(d, e, nid);
+  double vl[K][D], dH[D][K], Dr[6], Wr[3];
+  gather_nodal<ET>(d.v, d.np, nid, vl);
+  load_dH<ET>(d, e, dH);
+  strain_rates<ET>(dH, d.detJ[e], vl, d.radius ? d.radius[e] : 0.0, d.domtype, Dr, Wr);
+#pragma unroll
+  for (int i = 0; i < 6; i++) d.str_rate[(long long)i * d.ep + e] = Dr[i];
+#pragma unroll
+  for (int i = 0; i < 3; i++) {
+    d.rot_rate[(long long)i * d.ep + e] = 0.0;
+    d.rot_rate[(long long)(3 + i) * d.ep + e] = Wr[i];
+  }
+}
+
+template <int ET>
+__global__ void k_u_pressure(WfDev d, WfPar P) {
+  constexpr int K = Elem<ET>::K, D = Elem<ET>::D;
+  int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= d.ne) return;
+  int nid[K];
+  load_conn<ET>(d, e, nid);
+  double vl[K][D], dH[D][K];
+  gather_nodal<ET>(d.v, d.np, nid, vl);
+  load_dH<ET>(d, e, dH);
+  d.p[e] = elem_pressure<ET>(d, P, e, nid, d.vol[e], d.vol_0[e], d.rho[e], dH, vl);
+}
+
+__global__ void k_u_stress(WfDev d, WfPar P, double dt) {
+  int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= d.ne) return;
+  double tau[6], Dr[6], Wr[3];
+#pragma unroll
+  for (int i = 0; i < 6; i++) {
+    tau[i] = d.tau[(long long)i * d.ep + e];
+    Dr[i] = d.str_rate[(long long)i * d.ep + e];
+  }
+#pragma unroll
+  for (int i = 0; i < 3; i++) Wr[i] = d.rot_rate[(long long)(3 + i) * d.ep + e];
+  double pl = d.pl_strain[e];
+  StressOut so;
+  stress_update(P, dt, d.p[e], Dr, Wr, tau, pl, d.sigma_y[e], so);
+#pragma unroll
+  for (int i = 0; i < 6; i++) {
+    d.tau[(long long)i * d.ep + e] = tau[i];
+    d.sigma[(long long)i * d.ep + e] = so.sig[i];
+  }
+  if (P.track_eps) {
+#pragma unroll
+    for (int i = 0; i < 6; i++) {
+      long long o = (long long)i * d.ep + e;
+      d.eps[o] = d.eps[o] + dt * Dr[i];
+    }
+  }
+  d.pl_strain[e] = pl;
+  d.sigma_y[e] = so.sy;
+}
+
+__global__ void k_u_artvisc(WfDev d, WfPar P) {
+  int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= d.ne) return;
+  double Dr[6], sig[6];
+#pragma unroll
+  for (int i = 0; i < 6; i++) {
+    Dr[i] = d.str_rate[(long long)i * d.ep + e];
+    sig[i] = d.sigma[(long long)i * d.ep + e];
+  }
+  artificial_viscosity(P, Dr, d.rho[e], d.vol[e], sig);
+#pragma unroll
+  for (int i = 0; i < 3; i++) d.sigma[(long long)i * d.ep + e] = sig[i];
+}
+
+template <int ET>
+__global__ void k_u_forces(WfDev d, WfPar P) {
+  constexpr int K = Elem<ET>::K, D = Elem<ET>::D;
+  int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= d.ne) return;
+  double dH[D][K], sig[6], f[K][D];
+  load_dH<ET>(d, e, dH);
+#pragma unroll
+  for (int i = 0; i < 6; i++) sig[i] = d.sigma[(long long)i * d.ep + e];
+  elem_forces<ET>(dH, sig, d.detJ[e], d.radius ? d.radius[e] : 0.0, d.domtype, d.vol_weight, f);
+#pragma unroll
+  for (int n = 0; n < K; n++)
+#pragma unroll
+    for (int c = 0; c < D; c++) d.f_elem[((long long)n * D + c) * d.ep + e] = f[n][c];
+}
+
+template <int ET>
+__global__ void k_u_hourglass(WfDev d, WfPar P) {
+  constexpr int K = Elem<ET>::K, D = Elem<ET>::D;
+  int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= d.ne) return;
+  if constexpr (ET == ET_HEX8 || ET == ET_QUAD4) {
+    int nid[K];
+    load_conn<ET>(d, e, nid);
+    double vl[K][D], fh[K][D];
+    gather_nodal<ET>(d.v, d.np, nid, vl);
+    if constexpr (ET == ET_HEX8) {
+      if (P.hexa_hg == 0.0) return;
+      hexa_hourglass(P, vl, d.vol[e], d.rho[e], fh);
+    } else {
+      double q[2] = {d.hg_q[e], d.hg_q[d.ep + e]};
+      quad_hourglass(P, vl, d.vol[e], d.rho[e], q, fh);
+      d.hg_q[e] = q[0];
+      d.hg_q[d.ep + e] = q[1];
+    }
+#pragma unroll
+    for (int n = 0; n < K; n++)
+#pragma unroll
+      for (int c = 0; c < D; c++) d.f_elem_hg[((long long)n * D + c) * d.ep + e] = fh[n][c];
+  }
+}
+
+// unfused node kernels ------------------------------------------------------------------------
+template <int K>
+__global__ void k_u_nodal_vol(WfDev d) { // CalcNodalVol
+  int n = blockIdx.x * blockDim.x + threadIdx.x;
+  int slice = n >> 5;
+  if (slice >= d.nslices) return;
+  const long long base = d.sell_ptr[slice];
+  const int width = (int)((d.sell_ptr[slice + 1] - base) >> 5);
+  const int lane = n & 31;
+  double s = 0.0;
+  for (int j = 0; j < width; j++) {
+    int slot = __ldg(d.sell_slots + base + ((long long)j << 5) + lane);
+    if (slot >= 0) s += d.vol[slot / K];
+  }
+  if (n < d.nn) { d.voln_sum[n] = s; d.voln[n] = s / (double)K; }
+}
+
+template <int K, int D>
+__global__ void k_u_assembly(WfDev d) { // assemblyForces + scrub
+  int n = blockIdx.x * blockDim.x + threadIdx.x;
+  int slice = n >> 5;
+  if (slice >= d.nslices) return;
+  const long long base = d.sell_ptr[slice];
+  const int width = (int)((d.sell_ptr[slice + 1] - base) >> 5);
+  const int lane = n & 31;
+  double fi[D];
+#pragma unroll
+  for (int c = 0; c < D; c++) fi[c] = 0.0;
+  for (int j = 0; j < width; j++) {
+    int slot = __ldg(d.sell_slots + base + ((long long)j << 5) + lane);
+    if (slot >= 0) {
+      int e = slot / K, ln = slot - e * K;
+#pragma unroll
+      for (int c = 0; c < D; c++) fi[c] += d.f_elem[((long long)ln * D + c) * d.ep + e];
+    }
+  }
+  for (int j = 0; j < width; j++) {
+    int slot = __ldg(d.sell_slots + base + ((long long)j << 5) + lane);
+    if (slot >= 0) {
+      int e = slot / K, ln = slot - e * K;
+#pragma unroll
+      for (int c = 0; c < D; c++) fi[c] -= d.f_elem_hg[((long long)ln * D + c) * d.ep + e];
+    }
+  }
+  if (n >= d.nn) return;
+#pragma unroll
+  for (int c = 0; c < D; c++) {
+    if (!isfinite(fi[c])) { fi[c] = 0.0; *d.nonfinite = 1; }
+    d.fi[(long long)c * d.np + n] = fi[c];
+  }
+}
+
+template <int D>
+__global__ void k_u_accel(WfDev d) { // calcAccel
+  int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= d.nn) return;
+#pragma unroll
+  for (int c = 0; c < D; c++) {
+    long long i = (long long)c * d.np + n;
+    double fe = d.fe ? d.fe[i] : 0.0;
+    d.a[i] = (fe - d.fi[i]) / d.mdiag[n];
+  }
+}
+template <int D>
+__global__ void k_u_corr_accvel(WfDev d, WfPar P) { // UpdateCorrectionAccVel
+  int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= d.nn) return;
+  const double f = 1.0 / (1.0 - P.alpha);
+#pragma unroll
+  for (int c = 0; c < D; c++) {
+    long long i = (long long)c * d.np + n;
+    double a = f * (d.a[i] - P.alpha * d.prev_a[i]);
+    d.a[i] = a;
+    d.v[i] = d.v[i] + P.gamma * P.dt * a;
+  }
+}
+__global__ void k_u_axis(WfDev d, WfPar P) { // axis constraint with xmin of current x
+  int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= d.nn) return;
+  double xmin = key_dbl(d.xmin_key[P.xmin_cur]);
+  if (d.x[n] <= xmin + 1.e-6) { d.a[n] = 0.0; d.v[n] = 0.0; }
+}
+template <int D>
+__global__ void k_u_corr_pos(WfDev d, WfPar P) { // UpdateCorrectionPos
+  int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= d.nn) return;
+#pragma unroll
+  for (int c = 0; c < D; c++) {
+    long long i = (long long)c * d.np + n;
+    double a = d.a[i];
+    double udt = d.u_dt[i] + P.beta * P.dt * P.dt * a;
+    d.u_dt[i] = udt;
+    d.x[i] = d.x[i] + udt;
+    d.prev_a[i] = a;
+    d.u[i] = d.u[i] + udt;
+  }
+}
+
+// halo pack / unpack-add for the multi-GPU split step (nc doubles per shared node)
+__global__ void k_halo_pack(WfDev d, const double *src, long long pitch, int nc, const int *list, int count, double *buf) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= count) return;
+  int n = list[i];
+  for (int c = 0; c < nc; c++) buf[(long long)c * count + i] = src[(long long)c * pitch + n];
+}
+__global__ void k_halo_add(WfDev d, double *dst, long long pitch, int nc, const int *list, int count, const double *buf) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= count) return;
+  int n = list[i];
+  for (int c = 0; c < nc; c++) dst[(long long)c * pitch + n] += buf[(long long)c * count + i];
+}
+
+// ---------------------------------------------------------------------------------------------
+// launchers
+// ---------------------------------------------------------------------------------------------
+static inline int cdiv(long long a, int b) { return (int)((a + b - 1) / b); }
+#define ELEM_DISPATCH(et, ...)                                          \
+  switch (et) {                                                         \
+    case ET_HEX8: { constexpr int ET = ET_HEX8; __VA_ARGS__; } break;   \
+    case ET_TET4: { constexpr int ET = ET_TET4; __VA_ARGS__; } break;   \
+    case ET_QUAD4: { constexpr int ET = ET_QUAD4; __VA_ARGS__; } break; \
+    default: { constexpr int ET = ET_TRI3; __VA_ARGS__; } break;        \
+  }
+
+static void l_predict(const WfDev &d, const WfPar &P, int with_bc, cudaStream_t s) {
+  if (d.dim == 3) k_predict<3><<<cdiv(d.nn, TPB_N), TPB_N, 0, s>>>(d, P, with_bc);
+  else k_predict<2><<<cdiv(d.nn, TPB_N), TPB_N, 0, s>>>(d, P, with_bc);
+}
+static void l_impose_bc(const WfDev &d, int dim, int is_acc, double *arr, cudaStream_t s) {
+  k_impose_bc<<<cdiv(d.nn, 256), 256, 0, s>>>(d, dim, is_acc, arr);
+}
+static void l_elem_vol(const WfDev &d, const WfPar &P, int et, int store_jac, cudaStream_t s) {
+  ELEM_DISPATCH(et, k_elem_vol<ET><<<cdiv(d.ne, TPB_E), TPB_E, 0, s>>>(d, P, store_jac));
+}
+static void l_vol_from_detj(const WfDev &d, int et, cudaStream_t s) {
+  ELEM_DISPATCH(et, k_vol_from_detj<ET><<<cdiv(d.ne, 256), 256, 0, s>>>(d));
+}
+static void l_node_vol(const WfDev &d, const WfPar &P, int mode, int local_only, cudaStream_t s) {
+  int g = cdiv((long long)d.nslices * 32, TPB_N);
+  switch (d.k) {
+    case 8: k_node_vol<8><<<g, TPB_N, 0, s>>>(d, P, mode, local_only); break;
+    case 4: k_node_vol<4><<<g, TPB_N, 0, s>>>(d, P, mode, local_only); break;
+    default: k_node_vol<3><<<g, TPB_N, 0, s>>>(d, P, mode, local_only); break;
+  }
+}
+static void l_node_vol_finish(const WfDev &d, const WfPar &P, cudaStream_t s) {
+  k_node_vol_finish<<<cdiv(d.nn, 256), 256, 0, s>>>(d, P);
+}
+static void l_elem_main(const WfDev &d, const WfPar &P, int et, int separate_hg, cudaStream_t s) {
+  if (separate_hg) { ELEM_DISPATCH(et, k_elem_main<ET, true><<<cdiv(d.ne, TPB_E), TPB_E, 0, s>>>(d, P)); }
+  else { ELEM_DISPATCH(et, k_elem_main<ET, false><<<cdiv(d.ne, TPB_E), TPB_E, 0, s>>>(d, P)); }
+}
+template <bool SEP>
+static void node_update_t(const WfDev &d, const WfPar &P, int fuse, int phase, cudaStream_t s) {
+  int g = cdiv((long long)d.nslices * 32, TPB_N);
+  if (d.k == 8) k_node_update<8, 3, SEP><<<g, TPB_N, 0, s>>>(d, P, fuse, phase);
+  else if (d.k == 4 && d.dim == 3) k_node_update<4, 3, SEP><<<g, TPB_N, 0, s>>>(d, P, fuse, phase);
+  else if (d.k == 4) k_node_update<4, 2, SEP><<<g, TPB_N, 0, s>>>(d, P, fuse, phase);
+  else k_node_update<3, 2, SEP><<<g, TPB_N, 0, s>>>(d, P, fuse, phase);
+}
+static void l_node_update(const WfDev &d, const WfPar &P, int separate_hg, int fuse, int phase, cudaStream_t s) {
+  if (separate_hg) node_update_t<true>(d, P, fuse, phase, s);
+  else node_update_t<false>(d, P, fuse, phase, s);
+}
+static void l_node_mass(const WfDev &d, const WfPar &P, int use_stored_voln, cudaStream_t s) {
+  int g = cdiv((long long)d.nslices * 32, TPB_N);
+  switch (d.k) {
+    case 8: k_node_mass<8><<<g, TPB_N, 0, s>>>(d, P, use_stored_voln); break;
+    case 4: k_node_mass<4><<<g, TPB_N, 0, s>>>(d, P, use_stored_voln); break;
+    default: k_node_mass<3><<<g, TPB_N, 0, s>>>(d, P, use_stored_voln); break;
+  }
+}
+static void l_init_elem(const WfDev &d, const WfPar &P, cudaStream_t s) { k_init_elem<<<cdiv(d.ne, 256), 256, 0, s>>>(d, P); }
+static void l_vol0_density(const WfDev &d, cudaStream_t s) { k_vol0_density<<<cdiv(d.ne, 256), 256, 0, s>>>(d); }
+static void l_density(const WfDev &d, cudaStream_t s) { k_density<<<cdiv(d.ne, 256), 256, 0, s>>>(d); }
+static void l_xmin(const WfDev &d, int slot, cudaStream_t s) { k_xmin<<<cdiv(d.nn, 256), 256, 0, s>>>(d, slot); }
+static void l_rebuild_sigma(const WfDev &d, double *out, cudaStream_t s) { k_rebuild_sigma<<<cdiv(d.ne, 256), 256, 0, s>>>(d, out); }
+static void l_energy(const WfDev &d, const double *sig, cudaStream_t s) {
+  if (d.dim == 3) k_energy_kin<3><<<cdiv(d.nn, 256), 256, 0, s>>>(d);
+  else k_energy_kin<2><<<cdiv(d.nn, 256), 256, 0, s>>>(d);
+  if (d.ne > 0) k_energy_int<<<cdiv(d.ne, 256), 256, 0, s>>>(d, sig);
+}
+static void l_u_strain_rates(const WfDev &d, const WfPar &P, int et, cudaStream_t s) {
+  ELEM_DISPATCH(et, k_u_strain_rates<ET><<<cdiv(d.ne, TPB_E), TPB_E, 0, s>>>(d, P));
+}
+static void l_u_pressure(const WfDev &d, const WfPar &P, int et, cudaStream_t s) {
+  ELEM_DISPATCH(et, k_u_pressure<ET><<<cdiv(d.ne, TPB_E), TPB_E, 0, s>>>(d, P));
+}
+static void l_u_stress(const WfDev &d, const WfPar &P, double dt, cudaStream_t s) { k_u_stress<<<cdiv(d.ne, TPB_E), TPB_E, 0, s>>>(d, P, dt); }
+static void l_u_artvisc(const WfDev &d, const WfPar &P, cudaStream_t s) { k_u_artvisc<<<cdiv(d.ne, 256), 256, 0, s>>>(d, P); }
+static void l_u_forces(const WfDev &d, const WfPar &P, int et, cudaStream_t s) {
+  ELEM_DISPATCH(et, k_u_forces<ET><<<cdiv(d.ne, TPB_E), TPB_E, 0, s>>>(d, P));
+}
+static void l_u_hourglass(const WfDev &d, const WfPar &P, int et, cudaStream_t s) {
+  ELEM_DISPATCH(et, k_u_hourglass<ET><<<cdiv(d.ne, TPB_E), TPB_E, 0, s>>>(d, P));
+}
+static void l_u_nodal_vol(const WfDev &d, cudaStream_t s) {
+  int g = cdiv((long long)d.nslices * 32, TPB_N);
+  switch (d.k) {
+    case 8: k_u_nodal_vol<8><<<g, TPB_N, 0, s>>>(d); break;
+    case 4: k_u_nodal_vol<4><<<g, TPB_N, 0, s>>>(d); break;
+    default: k_u_nodal_vol<3><<<g, TPB_N, 0, s>>>(d); break;
+  }
+}
+static void l_u_assembly(const WfDev &d, cudaStream_t s) {
+  int g = cdiv((long long)d.nslices * 32, TPB_N);
+  if (d.k == 8) k_u_assembly<8, 3><<<g, TPB_N, 0, s>>>(d);
+  else if (d.k == 4 && d.dim == 3) k_u_assembly<4, 3><<<g, TPB_N, 0, s>>>(d);
+  else if (d.k == 4) k_u_assembly<4, 2><<<g, TPB_N, 0, s>>>(d);
+  else k_u_assembly<3, 2><<<g, TPB_N, 0, s>>>(d);
+}
+static void l_u_accel(const WfDev &d, cudaStream_t s) {
+  if (d.dim == 3) k_u_accel<3><<<cdiv(d.nn, 256), 256, 0, s>>>(d);
+  else k_u_accel<2><<<cdiv(d.nn, 256), 256, 0, s>>>(d);
+}
+static void l_u_corr_accvel(const WfDev &d, const WfPar &P, cudaStream_t s) {
+  if (d.dim == 3) k_u_corr_accvel<3><<<cdiv(d.nn, 256), 256, 0, s>>>(d, P);
+  else k_u_corr_accvel<2><<<cdiv(d.nn, 256), 256, 0, s>>>(d, P);
+}
+static void l_u_axis(const WfDev &d, const WfPar &P, cudaStream_t s) { k_u_axis<<<cdiv(d.nn, 256), 256, 0, s>>>(d, P); }
+static void l_u_corr_pos(const WfDev &d, const WfPar &P, cudaStream_t s) {
+  if (d.dim == 3) k_u_corr_pos<3><<<cdiv(d.nn, 256), 256, 0, s>>>(d, P);
+  else k_u_corr_pos<2><<<cdiv(d.nn, 256), 256, 0, s>>>(d, P);
+}
+static void l_halo_pack(const WfDev &d, const double *src, long long pitch, int nc, const int *list, int count, double *buf, cudaStream_t s) {
+  if (count > 0) k_halo_pack<<<cdiv(count, 256), 256, 0, s>>>(d, src, pitch, nc, list, count, buf);
+}
+static void l_halo_add(const WfDev &d, double *dst, long long pitch, int nc, const int *list, int count, const double *buf, cudaStream_t s) {
+  if (count > 0) k_halo_add<<<cdiv(count, 256), 256, 0, s>>>(d, dst, pitch, nc, list, count, buf);
+}
+
+} // namespace WF_NS
+
+#define WF_CAT2(a, b) a##b
+#define WF_CAT(a, b) WF_CAT2(a, b)
+extern "C" const WfLaunch *WF_CAT(WF_NS, _table)() {
+  using namespace WF_NS;
+  static const WfLaunch t = {l_predict, l_impose_bc, l_elem_vol, l_vol_from_detj, l_node_vol, l_node_vol_finish,
+                             l_elem_main, l_node_update, l_node_mass, l_init_elem, l_vol0_density, l_density, l_xmin,
+                             l_rebuild_sigma, l_energy, l_u_strain_rates, l_u_pressure, l_u_stress, l_u_artvisc,
+                             l_u_forces, l_u_hourglass, l_u_nodal_vol, l_u_assembly, l_u_accel, l_u_corr_accvel,
+                             l_u_axis, l_u_corr_pos, l_halo_pack, l_halo_add};
+  return &t;
+}

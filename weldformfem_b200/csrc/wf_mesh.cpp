@@ -1,0 +1,232 @@
+// wf_mesh.cpp — host-side integer work of the engine: box mesher, node->element connectivity,
+// element-block partition and halo lists.  No CUDA here, so the CPU test-suite can check every
+// integer artefact bit-exactly against the oracle without a GPU.
+#include <algorithm>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+#include "../../include/wf_engine.h"
+#include "wf_host.h"
+
+// ---- Domain_d::AddBoxLength (src/common/Domain_d.C:1136-1504) -------------------------------------
+// nel[i] = (int)(L_i/(2r)); node id = i + (nx+1)(j + (ny+1)k); coordinates by repeated "+= 2r";
+// hexa node order :1321-1332, quad :1273-1278, triangle split :1296-1303, 6-tet split :1383-1388.
+void wf_box_dims(const double L[3], double r, int tritet, WfBox *b) {
+  b->dim = (L[2] > 0.0) ? 3 : 2;
+  b->nel[0] = (int)(L[0] / (2.0 * r));
+  b->nel[1] = (int)(L[1] / (2.0 * r));
+  b->nel[2] = (b->dim == 3) ? (int)(L[2] / (2.0 * r)) : 1;
+  b->tritet = tritet;
+  b->k = (b->dim == 3) ? (tritet ? 4 : 8) : (tritet ? 3 : 4);
+  b->per_cell = tritet ? (b->dim == 3 ? 6 : 2) : 1;
+  b->nn = (long long)(b->nel[0] + 1) * (b->nel[1] + 1) * (b->dim == 3 ? b->nel[2] + 1 : 1);
+  b->ne = (long long)b->nel[0] * b->nel[1] * b->nel[2] * b->per_cell;
+}
+
+static const int kTetSplit[6][4] = {{0, 1, 3, 5}, {1, 2, 3, 5}, {0, 5, 3, 4}, {4, 5, 3, 7}, {5, 6, 3, 7}, {5, 2, 3, 6}};
+
+// connectivity of element e of the box (any e, O(1))
+void wf_box_elem_nodes(const WfBox &b, long long e, unsigned *out) {
+  const long long cell = e / b.per_cell;
+  const int sub = (int)(e - cell * b.per_cell);
+  const int nx1 = b.nel[0] + 1;
+  if (b.dim == 2) {
+    const int ey = (int)(cell / b.nel[0]), ex = (int)(cell - (long long)ey * b.nel[0]);
+    const unsigned nb1 = (unsigned)(nx1 * ey + ex), nb2 = (unsigned)(nx1 * (ey + 1) + ex);
+    if (!b.tritet) { out[0] = nb1; out[1] = nb1 + 1; out[2] = nb2 + 1; out[3] = nb2; }
+    else if (sub == 0) { out[0] = nb1; out[1] = nb1 + 1; out[2] = nb2; }
+    else { out[0] = nb1 + 1; out[1] = nb2 + 1; out[2] = nb2; }
+    return;
+  }
+  const long long nxy = (long long)b.nel[0] * b.nel[1];
+  const int ez = (int)(cell / nxy);
+  const long long rem = cell - (long long)ez * nxy;
+  const int ey = (int)(rem / b.nel[0]), ex = (int)(rem - (long long)ey * b.nel[0]);
+  const long long nnodz = (long long)nx1 * (b.nel[1] + 1);
+  const long long nb1 = nnodz * ez + (long long)nx1 * ey + ex, nb2 = nnodz * ez + (long long)nx1 * (ey + 1) + ex;
+  const unsigned nh[8] = {(unsigned)nb1, (unsigned)(nb1 + 1), (unsigned)(nb2 + 1), (unsigned)nb2,
+                          (unsigned)(nb1 + nnodz), (unsigned)(nb1 + nnodz + 1), (unsigned)(nb2 + nnodz + 1),
+                          (unsigned)(nb2 + nnodz)};
+  if (!b.tritet) { for (int i = 0; i < 8; i++) out[i] = nh[i]; }
+  else { for (int i = 0; i < 4; i++) out[i] = nh[kTetSplit[sub][i]]; }
+}
+
+// per-axis coordinate tables, accumulated exactly like the reference's nested loops (:1205-1234)
+void wf_box_axes(const WfBox &b, const double V[3], double r, std::vector<double> ax[3]) {
+  for (int a = 0; a < 3; a++) {
+    int cnt = (a < b.dim) ? b.nel[a] + 1 : 1;
+    ax[a].resize(cnt);
+    double X = V[a];
+    for (int i = 0; i < cnt; i++) { ax[a][i] = X; X = X + 2.0 * r; }
+  }
+}
+
+void wf_box_node_xyz(const WfBox &b, const std::vector<double> ax[3], long long n, double *out) {
+  const int nx1 = b.nel[0] + 1, ny1 = b.nel[1] + 1;
+  const long long kz = n / ((long long)nx1 * ny1);
+  const long long rem = n - kz * nx1 * ny1;
+  const int j = (int)(rem / nx1), i = (int)(rem - (long long)j * nx1);
+  out[0] = ax[0][i]; out[1] = ax[1][j];
+  if (b.dim == 3) out[2] = ax[2][kz];
+}
+
+extern "C" int wf_host_box_counts(const double L[3], double r, int tritet, int *dim, int *nodxelem, int *n_nodes,
+                                  int *n_elems) {
+  WfBox b;
+  wf_box_dims(L, r, tritet, &b);
+  if (b.nn > 2147483647LL || b.ne * b.k > 2147483647LL) return 1;
+  *dim = b.dim; *nodxelem = b.k; *n_nodes = (int)b.nn; *n_elems = (int)b.ne;
+  return 0;
+}
+
+extern "C" int wf_host_gen_box(const double V[3], const double L[3], double r, int tritet, double *x, unsigned *elnod) {
+  WfBox b;
+  wf_box_dims(L, r, tritet, &b);
+  std::vector<double> ax[3];
+  wf_box_axes(b, V, r, ax);
+  for (long long n = 0; n < b.nn; n++) wf_box_node_xyz(b, ax, n, x + n * b.dim);
+  for (long long e = 0; e < b.ne; e++) wf_box_elem_nodes(b, e, elnod + e * b.k);
+  return 0;
+}
+
+// ---- Domain_d::setNodElem (src/common/Domain_d.C:1508-1611) -----------------------------------------
+// count pass, exclusive prefix sum, fill in ascending element id then local node: every node's list is
+// sorted by element id.  Returns non-zero if a connectivity entry is out of range.
+extern "C" int wf_host_nodel(int n_nodes, int n_elems, int k, const unsigned *elnod, int *offset, int *count,
+                             int *nodel, int *nodel_loc) {
+  for (int n = 0; n < n_nodes; n++) count[n] = 0;
+  const long long tot_entries = (long long)n_elems * k;
+  for (long long i = 0; i < tot_entries; i++) {
+    if (elnod[i] >= (unsigned)n_nodes) return 1;
+    count[elnod[i]]++;
+  }
+  long long tot = 0;
+  for (int n = 0; n < n_nodes; n++) { offset[n] = (int)tot; tot += count[n]; }
+  for (int n = 0; n < n_nodes; n++) count[n] = 0;
+  for (int e = 0; e < n_elems; e++)
+    for (int ln = 0; ln < k; ln++) {
+      const int n = (int)elnod[(long long)e * k + ln];
+      nodel[offset[n] + count[n]] = e;
+      nodel_loc[offset[n] + count[n]] = ln;
+      count[n]++;
+    }
+  return 0;
+}
+
+// ---- canonical element-block partition + halo lists (the reference has none) ---------
+struct wf_partition {
+  int nranks, rank, k;
+  int elem_begin, elem_end;
+  std::vector<int> l2g;           // local node -> global id, ascending
+  std::vector<unsigned> elnod;    // local connectivity (local node ids)
+  std::vector<int> neigh, halo_offset, halo_nodes;
+  bool is_box = false;
+  WfBox box;
+  double V[3], r;
+};
+
+static inline long long block_begin(long long ne, int P, int p) { return (ne * p) / P; }
+
+template <class ConnFn>
+static void build_partition(wf_partition *pt, long long n_nodes, long long n_elems, ConnFn conn) {
+  const int P = pt->nranks, k = pt->k;
+  pt->elem_begin = (int)block_begin(n_elems, P, pt->rank);
+  pt->elem_end = (int)block_begin(n_elems, P, pt->rank + 1);
+  unsigned tmp[WF_MAXK_HOST];
+  // local nodes = nodes referenced by owned elements, ascending global id
+  std::vector<int> &l2g = pt->l2g;
+  l2g.clear();
+  l2g.reserve((size_t)(pt->elem_end - pt->elem_begin) * 2);
+  for (long long e = pt->elem_begin; e < pt->elem_end; e++) {
+    conn(e, tmp);
+    for (int i = 0; i < k; i++) l2g.push_back((int)tmp[i]);
+  }
+  std::sort(l2g.begin(), l2g.end());
+  l2g.erase(std::unique(l2g.begin(), l2g.end()), l2g.end());
+  auto g2l = [&](unsigned g) { return (unsigned)(std::lower_bound(l2g.begin(), l2g.end(), (int)g) - l2g.begin()); };
+  pt->elnod.resize((size_t)(pt->elem_end - pt->elem_begin) * k);
+  for (long long e = pt->elem_begin; e < pt->elem_end; e++) {
+    conn(e, tmp);
+    for (int i = 0; i < k; i++) pt->elnod[(size_t)(e - pt->elem_begin) * k + i] = g2l(tmp[i]);
+  }
+  // shared nodes: for every other rank q, the global ids it references that are also local here.
+  // Only elements of q can reference a node; scan q's block and keep hits (ascending, unique).
+  pt->neigh.clear(); pt->halo_offset.assign(1, 0); pt->halo_nodes.clear();
+  (void)n_nodes;
+  for (int q = 0; q < P; q++) {
+    if (q == pt->rank) continue;
+    const long long qb = block_begin(n_elems, P, q), qe = block_begin(n_elems, P, q + 1);
+    std::vector<int> hits;
+    for (long long e = qb; e < qe; e++) {
+      conn(e, tmp);
+      for (int i = 0; i < k; i++) {
+        const int g = (int)tmp[i];
+        if (g < l2g.front() || g > l2g.back()) continue;
+        auto it = std::lower_bound(l2g.begin(), l2g.end(), g);
+        if (it != l2g.end() && *it == g) hits.push_back((int)(it - l2g.begin()));
+      }
+    }
+    if (hits.empty()) continue;
+    std::sort(hits.begin(), hits.end());
+    hits.erase(std::unique(hits.begin(), hits.end()), hits.end());
+    pt->neigh.push_back(q);
+    pt->halo_nodes.insert(pt->halo_nodes.end(), hits.begin(), hits.end());
+    pt->halo_offset.push_back((int)pt->halo_nodes.size());
+  }
+}
+
+extern "C" int wf_partition_build(wf_partition **out, int nranks, int rank, int k, int n_nodes, int n_elems,
+                                  const unsigned *elnod) {
+  if (!out || nranks < 1 || rank < 0 || rank >= nranks || k < 1 || k > WF_MAXK_HOST) return 1;
+  wf_partition *pt = new wf_partition();
+  pt->nranks = nranks; pt->rank = rank; pt->k = k;
+  build_partition(pt, n_nodes, n_elems, [&](long long e, unsigned *o) {
+    for (int i = 0; i < k; i++) o[i] = elnod[e * k + i];
+  });
+  *out = pt;
+  return 0;
+}
+
+extern "C" int wf_partition_build_box(wf_partition **out, int nranks, int rank, const double V[3], const double L[3],
+                                      double r, int tritet) {
+  if (!out || nranks < 1 || rank < 0 || rank >= nranks) return 1;
+  wf_partition *pt = new wf_partition();
+  pt->nranks = nranks; pt->rank = rank;
+  pt->is_box = true;
+  wf_box_dims(L, r, tritet, &pt->box);
+  pt->k = pt->box.k;
+  for (int i = 0; i < 3; i++) pt->V[i] = V[i];
+  pt->r = r;
+  const WfBox b = pt->box;
+  build_partition(pt, b.nn, b.ne, [&](long long e, unsigned *o) { wf_box_elem_nodes(b, e, o); });
+  *out = pt;
+  return 0;
+}
+
+extern "C" void wf_partition_free(wf_partition *p) { delete p; }
+extern "C" int wf_partition_info(const wf_partition *p, int *eb, int *ee, int *nl, int *nn) {
+  if (!p) return 1;
+  if (eb) *eb = p->elem_begin;
+  if (ee) *ee = p->elem_end;
+  if (nl) *nl = (int)p->l2g.size();
+  if (nn) *nn = (int)p->neigh.size();
+  return 0;
+}
+extern "C" const int *wf_partition_node_l2g(const wf_partition *p) { return p->l2g.data(); }
+extern "C" const unsigned *wf_partition_local_elnod(const wf_partition *p) { return p->elnod.data(); }
+extern "C" const int *wf_partition_neigh_ranks(const wf_partition *p) { return p->neigh.data(); }
+extern "C" const int *wf_partition_halo_offset(const wf_partition *p) { return p->halo_offset.data(); }
+extern "C" const int *wf_partition_halo_nodes(const wf_partition *p) { return p->halo_nodes.data(); }
+
+// accessors used by the engine
+int wf_partition_k(const wf_partition *p) { return p->k; }
+bool wf_partition_is_box(const wf_partition *p) { return p->is_box; }
+void wf_partition_box_coords(const wf_partition *p, std::vector<double> &x) {
+  std::vector<double> ax[3];
+  wf_box_axes(p->box, p->V, p->r, ax);
+  const int dim = p->box.dim;
+  x.resize(p->l2g.size() * dim);
+  for (size_t i = 0; i < p->l2g.size(); i++) wf_box_node_xyz(p->box, ax, p->l2g[i], x.data() + i * dim);
+}
+int wf_partition_box_dim(const wf_partition *p) { return p->box.dim; }

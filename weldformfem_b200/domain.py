@@ -1,0 +1,236 @@
+"""Host-side mirror of the reference's ``MetFEM::Domain_d`` for the explicit step, over the C ABI.
+
+Method names and argument meaning follow the reference (include/common/Domain_d.h): ``AddBoxLength``,
+``AddBCVelNode``, ``AllocateBCs``, ``SetDT`` ..., plus the snake_case aliases the CPU checkers under
+``oracle/`` use so that a parity test can drive engine and checker with the same calls.  All work is
+done by hand-written CUDA kernels in ``libwf_b200.so``; there is no CPU or PyTorch fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import STAB_FIELDS, wf_material, wf_stab
+
+PLANE_STRAIN, AXISYMM, DOM_3D = 0, 2, 3
+BILINEAR, HOLLOMON = 0, 1
+STRICT, FAST = 1, 0
+
+_INT_ARRAYS = {"m_nodel": np.int32, "m_nodel_loc": np.int32, "m_nodel_offset": np.int32, "m_nodel_count": np.int32,
+               "m_elnod": np.uint32}
+
+
+class WfError(RuntimeError):
+    pass
+
+
+class Domain_d:
+    """One explicit-dynamics domain on one GPU."""
+
+    def __init__(self, device: int = 0, strict: bool = False):
+        self._lib = _lib.load()
+        self._h = C.c_void_p()
+        self._device = device
+        self._strict = bool(strict)
+        self._domtype = DOM_3D
+        self._vol_weight = False
+        self._pending_bcs = []
+        self._dt = None
+        self.dim = None
+        self.nodxelem = None
+        self._tracking = 0
+
+    # ---- plumbing ---------------------------------------------------------------------------------
+    def _ck(self, rc):
+        if rc != 0:
+            msg = self._lib.wf_last_error(self._h if self._h else None)
+            raise WfError(msg.decode() if msg else f"error {rc}")
+
+    def _create(self, dim, k):
+        if self._h:
+            raise WfError("mesh already created")
+        domtype = DOM_3D if dim == 3 else self._domtype
+        if dim == 2 and domtype == DOM_3D:
+            domtype = PLANE_STRAIN
+        h = C.c_void_p()
+        rc = self._lib.wf_create(C.byref(h), dim, k, domtype, self._device)
+        if rc != 0:
+            raise WfError(self._lib.wf_last_error(None).decode())
+        self._h = h
+        self.dim, self.nodxelem, self._domtype = dim, k, domtype
+        if domtype == AXISYMM and self._vol_weight:
+            self._ck(self._lib.wf_set_axisymm_vol_weight(self._h, 1))
+
+    def close(self):
+        if self._h:
+            self._lib.wf_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_stream(self, cuda_stream: int):
+        self._ck(self._lib.wf_set_stream(self._h, C.c_void_p(cuda_stream)))
+
+    def synchronize(self):
+        self._ck(self._lib.wf_synchronize(self._h))
+
+    # ---- setup: names of the reference ------------------------------------------------------------
+    def setAxiSymm(self, vol_weight: bool = False):           # Domain_d.h:666
+        self._domtype, self._vol_weight = AXISYMM, bool(vol_weight)
+
+    def set_domtype(self, domtype: int, vol_weight: bool = False):
+        self._domtype, self._vol_weight = int(domtype), bool(vol_weight)
+
+    def AddBoxLength(self, V, L, r, red_int: bool = True, tritetra: bool = False):   # Domain_d.C:1136
+        if not red_int:
+            raise WfError("full integration is not implemented by the reference step (Domain_d.C:1906-2008)")
+        dim = 3 if L[2] > 0.0 else 2
+        k = (4 if tritetra else 8) if dim == 3 else (3 if tritetra else 4)
+        self._create(dim, k)
+        Vd, Ld = (C.c_double * 3)(*V), (C.c_double * 3)(*L)
+        self._ck(self._lib.wf_gen_box(self._h, Vd, Ld, float(r), int(tritetra)))
+
+    def box(self, V, L, r, tritet=False):
+        self.AddBoxLength(V, L, r, True, bool(tritet))
+
+    def set_mesh(self, dim, k, x, elnod):                     # CreateFromLSDyna path, Domain_d.C:1647
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        el = np.ascontiguousarray(elnod, dtype=np.uint32)
+        self._create(dim, k)
+        self._ck(self._lib.wf_set_mesh(self._h, x.size // dim, el.size // k, x.ctypes.data_as(C.POINTER(C.c_double)),
+                                       el.ctypes.data_as(C.POINTER(C.c_uint))))
+
+    def set_material(self, E, nu, rho0, model=BILINEAR, sy0=1.0e10, K=0.0, m=1.0):   # main.C:460-581
+        mat = wf_material(int(model), float(E), float(nu), float(rho0), float(sy0), float(K), float(m))
+        self._ck(self._lib.wf_set_material(self._h, C.byref(mat)))
+
+    def set_stab(self, **kw):                                  # m_stab, main.C:84-120
+        self._stab_kw = {k: float(v) for k, v in kw.items()}
+        self._push_stab()
+
+    def _push_stab(self, hexa_hg=None):
+        kw = dict(getattr(self, "_stab_kw", {}))
+        if hexa_hg is not None:
+            kw["hexa_hg_coeff"] = hexa_hg
+            self._stab_kw = kw
+        st = wf_stab(*[float(kw.get(f, 0.0)) for f in STAB_FIELDS])
+        self._ck(self._lib.wf_set_stab(self._h, C.byref(st)))
+
+    def set_options(self, press=0, av_alpha=0.0, av_beta=0.0, hexa_hg=0.0, strict=None):
+        if strict is not None:
+            self._strict = bool(strict)
+        self._push_stab(hexa_hg=float(hexa_hg))
+        self._ck(self._lib.wf_set_options(self._h, int(press), float(av_alpha), float(av_beta), int(self._strict)))
+
+    def set_tracking(self, eps: bool = False, sigma: bool = False):
+        self._tracking = (1 if eps else 0) | (2 if sigma else 0)
+        self._ck(self._lib.wf_set_tracking(self._h, self._tracking))
+
+    def AddBCVelNode(self, node, dim, val):                    # Domain_d.C:1057
+        self._ck(self._lib.wf_add_bc_vel(self._h, int(node), int(dim), float(val)))
+
+    add_bc = AddBCVelNode
+
+    def add_bcs(self, nodes, dims, vals):
+        nodes = np.ascontiguousarray(nodes, dtype=np.int32)
+        dims = np.ascontiguousarray(dims, dtype=np.int32)
+        vals = np.ascontiguousarray(vals, dtype=np.float64)
+        self._ck(self._lib.wf_add_bc_vel_array(self._h, nodes.size, nodes.ctypes.data_as(C.POINTER(C.c_int)),
+                                               dims.ctypes.data_as(C.POINTER(C.c_int)),
+                                               vals.ctypes.data_as(C.POINTER(C.c_double))))
+
+    def AllocateBCs(self):                                     # Domain_d.C:1063
+        self._ck(self._lib.wf_allocate_bcs(self._h))
+
+    allocate_bcs = AllocateBCs
+
+    def SetDT(self, dt):                                       # Domain_d.h:629
+        self._dt = float(dt)
+
+    # ---- solve ------------------------------------------------------------------------------------
+    def init(self, dt=None):
+        """Initialisation part of SolveChungHulbert (Solver_explicit.C:115-292)."""
+        if dt is not None:
+            self._dt = float(dt)
+        if self._dt is None:
+            raise WfError("SetDT first")
+        self._ck(self._lib.wf_init(self._h, self._dt))
+
+    def step(self, n=1):
+        """n fused time steps (rows 1-22 of the loop body, Solver_explicit.C:524-978)."""
+        self._ck(self._lib.wf_step(self._h, int(n)))
+
+    def SolveChungHulbert(self, end_t):
+        """Run the explicit loop up to end_t with the fixed step set by SetDT (while Time < end_t)."""
+        self.init()
+        t, n = 0.0, 0
+        while t < end_t:
+            t += self._dt
+            n += 1
+        self.step(n)
+        return n
+
+    def call(self, fn, arg=0.0):
+        """Unfused entry points, names = Domain_d members (parity bisecting)."""
+        if fn in ("ImposeBCV", "ImposeBCA"):
+            self._ck(getattr(self._lib, "wf_" + fn)(self._h, int(arg)))
+        elif fn in ("ImposeBCVAllDim", "ImposeBCAAllDim"):
+            for d in range(self.dim):
+                self._ck(getattr(self._lib, "wf_" + fn[:9])(self._h, d))
+        elif fn == "CalcStressStrain":
+            self._ck(self._lib.wf_CalcStressStrain(self._h, float(arg)))
+        elif fn in _lib.UNFUSED:
+            self._ck(getattr(self._lib, "wf_" + fn)(self._h))
+        else:
+            raise KeyError(fn)
+
+    def nonfinite_flag(self) -> bool:
+        f = C.c_int(0)
+        self._ck(self._lib.wf_nonfinite_flag(self._h, C.byref(f)))
+        return bool(f.value)
+
+    def energies(self):
+        ek, de = C.c_double(), C.c_double()
+        self._ck(self._lib.wf_energies(self._h, C.byref(ek), C.byref(de)))
+        return ek.value, de.value
+
+    def time(self):
+        t, n = C.c_double(), C.c_long()
+        self._ck(self._lib.wf_get_time(self._h, C.byref(t), C.byref(n)))
+        return t.value, n.value
+
+    # ---- state ------------------------------------------------------------------------------------
+    def counts(self):
+        a, b, c = C.c_int(), C.c_int(), C.c_int()
+        self._ck(self._lib.wf_get_counts(self._h, C.byref(a), C.byref(b), C.byref(c)))
+        return a.value, b.value, c.value
+
+    def info(self):
+        nn, ne, _ = self.counts()
+        return dict(dim=self.dim, nodxelem=self.nodxelem, n_nodes=nn, n_elems=ne, domtype=self._domtype)
+
+    def get(self, name: str) -> np.ndarray:
+        nbytes = self._lib.wf_array_bytes(self._h, name.encode())
+        dt = _INT_ARRAYS.get(name, np.float64)
+        if nbytes == 0:
+            # distinguish "unknown" from "known but empty"
+            self._ck(self._lib.wf_get_array(self._h, name.encode(), C.c_void_p(1), 0))
+        out = np.empty(nbytes // np.dtype(dt).itemsize, dtype=dt)
+        self._ck(self._lib.wf_get_array(self._h, name.encode(), out.ctypes.data_as(C.c_void_p), nbytes))
+        return out
+
+    def set(self, name: str, arr):
+        dt = _INT_ARRAYS.get(name, np.float64)
+        arr = np.ascontiguousarray(arr, dtype=dt)
+        self._ck(self._lib.wf_set_array(self._h, name.encode(), arr.ctypes.data_as(C.c_void_p), arr.nbytes))
+
+    def device_ptr(self, name: str):
+        pitch = C.c_size_t()
+        p = self._lib.wf_device_ptr(self._h, name.encode(), C.byref(pitch))
+        return p, pitch.value
