@@ -1,0 +1,26 @@
+"""The small cases whose reference outputs are committed under tests/golden/ (shared by the generator
+and by the tests)."""
+import dataclasses
+
+from weldformfem_b200 import cases
+
+R = dataclasses.replace
+STAB = dict(alpha_free=0.3, hg_coeff_free=0.2, av_coeff_div=0.15, av_coeff_bulk=0.15, log_factor=0.8,
+            pspg_scale=0.2, p_pspg_bulkfac=0.05, J_min=0.1)
+
+GOLDEN = {
+    # name: (case, steps)
+    "c1_1hex_hg006": (cases.c1_one_hex(), 126),
+    "c1_1hex_nohg": (cases.c1_one_hex(hexa_hg=0.0), 126),
+    "hex_n4_plastic": (R(cases.c3_hexes(4), top_vel=-200.0), 80),
+    "tet_n3_plastic": (R(cases.c2_tets(3), top_vel=-200.0), 80),
+    "tet_n3_anp_nodal": (R(cases.c2_tets(3, press=3), top_vel=-200.0), 80),
+    "tet_n2_anp_shipped": (R(cases.c2_tets(2, press=1), top_vel=-200.0), 5),
+    "axiquad_n6": (R(cases.c4_axisymm_quads(6), top_vel=-50.0), 80),
+    "psquad_n6": (R(cases.plane_strain_quads(6), top_vel=-50.0), 80),
+    "pstri_n6": (R(cases.plane_strain_tris(6), top_vel=-50.0), 80),
+    "hex_n3_stab_av": (R(cases.c3_hexes(3), top_vel=-200.0, stab=STAB, av=(1.0, 0.2)), 60),
+}
+
+FLOAT_ARRAYS = "x v a u prev_a m_fi m_mdiag vol p pl_strain sigma_y m_sigma m_tau m_eps".split()
+INT_ARRAYS = "m_elnod m_nodel m_nodel_loc m_nodel_offset m_nodel_count".split()

@@ -1,0 +1,44 @@
+"""Generate tests/golden/*.npz from the UNMODIFIED reference build (oracle/_ref/libwf_ref.so).
+
+Run in the container that has /root/reference:   python tests/golden/make_golden.py
+Each file holds the reference-layout arrays after 1 step and after N steps of one small case
+(single OpenMP thread: the reference's 2D-quad hourglass has a data race, Mechanical.C:1848).
+"""
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, HERE)
+
+from cases_golden import FLOAT_ARRAYS, GOLDEN, INT_ARRAYS  # noqa: E402
+from oracle import refdrv  # noqa: E402
+
+
+def main():
+    refdrv.build("ref")
+    refdrv.RefDomain.set_threads(1)
+    for name, (case, steps) in GOLDEN.items():
+        d = refdrv.RefDomain()
+        case.apply(d)
+        out = {nm: d.get(nm) for nm in INT_ARRAYS}
+        out["x0"] = d.get("x")
+        d.step(1)
+        for nm in FLOAT_ARRAYS:
+            out[f"s1_{nm}"] = d.get(nm)
+        d.step(steps - 1)
+        for nm in FLOAT_ARRAYS:
+            out[f"sN_{nm}"] = d.get(nm)
+        if case.dim == 2 and not case.tritet:
+            out["sN_m_hg_q"] = d.get("m_hg_q")[: 2 * case.n_elems]
+        out["steps"] = np.array([steps])
+        path = os.path.join(HERE, name + ".npz")
+        np.savez_compressed(path, **out)
+        print(name, os.path.getsize(path), "bytes", "plastic frac", float((out["sN_pl_strain"] > 0).mean()))
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,72 @@
+"""The C-ABI library loads on a CPU-only box and exports every symbol include/wf_engine.h declares;
+without a GPU the product path fails loudly (no CPU fallback)."""
+import ctypes as C
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    src = open(os.path.join(ROOT, "include", "wf_engine.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(wf_[A-Za-z_0-9]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    from weldformfem_b200 import _lib, build
+    build.build()
+    lib = _lib.load()
+    names = declared_symbols()
+    assert len(names) > 50
+    missing = [n for n in names if not hasattr(lib, n)]
+    assert not missing, missing
+    assert sorted(_lib.DECLARED) == names, set(names) ^ set(_lib.DECLARED)
+    assert b"sm_100a" in lib.wf_version()
+
+
+def test_sass_is_sm100a_fp64():
+    """The cubin in the library targets sm_100a and the hot kernels use fp64 FMA/ADD/MUL (no tensor-core path)."""
+    import shutil
+    import subprocess
+    if not shutil.which("cuobjdump"):
+        pytest.skip("cuobjdump not available")
+    lib = os.path.join(ROOT, "weldformfem_b200", "libwf_b200.so")
+    out = subprocess.run(["cuobjdump", "-lelf", lib], capture_output=True, text=True).stdout
+    assert "sm_100a" in out
+
+
+def test_no_cpu_fallback_without_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from weldformfem_b200 import _lib
+    lib = _lib.load()
+    h = C.c_void_p()
+    rc = lib.wf_create(C.byref(h), 3, 8, 3, 0)
+    assert rc != 0 and not h
+    assert b"no CPU fallback" in lib.wf_last_error(None)
+    from weldformfem_b200.domain import Domain_d, WfError
+    with pytest.raises(WfError):
+        Domain_d().box((0, 0, 0), (1, 1, 1), 0.25)
+
+
+def test_product_never_imports_oracle():
+    """Only tests/, __graft_entry__.smoke() and bench.py's CPU legs may touch oracle/."""
+    pkg = os.path.join(ROOT, "weldformfem_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h")):
+                txt = open(os.path.join(dirpath, f)).read()
+                assert "import oracle" not in txt and "from oracle" not in txt and "wf_oracle" not in txt, f
+
+
+def test_bad_arguments():
+    from weldformfem_b200 import _lib
+    lib = _lib.load()
+    h = C.c_void_p()
+    assert lib.wf_create(C.byref(h), 3, 5, 3, 0) != 0
+    assert b"unsupported element" in lib.wf_last_error(None)
+    assert lib.wf_create(C.byref(h), 2, 4, 3, 0) != 0

@@ -1,0 +1,165 @@
+"""Integer work, bit-exact (no GPU): the engine's host-side box mesher, node->element connectivity and
+partition / halo lists against the oracle and the committed reference fixtures."""
+import ctypes as C
+import os
+import sys
+
+import numpy as np
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(HERE, "golden"))
+from cases_golden import GOLDEN, INT_ARRAYS  # noqa: E402
+
+
+def host_box(V, L, r, tritet):
+    from weldformfem_b200 import _lib
+    lib = _lib.load()
+    dim, k, nn, ne = C.c_int(), C.c_int(), C.c_int(), C.c_int()
+    Ld, Vd = (C.c_double * 3)(*L), (C.c_double * 3)(*V)
+    assert lib.wf_host_box_counts(Ld, r, int(tritet), C.byref(dim), C.byref(k), C.byref(nn), C.byref(ne)) == 0
+    x = np.empty(nn.value * dim.value)
+    el = np.empty(ne.value * k.value, dtype=np.uint32)
+    assert lib.wf_host_gen_box(Vd, Ld, r, int(tritet), x.ctypes.data_as(C.POINTER(C.c_double)),
+                               el.ctypes.data_as(C.POINTER(C.c_uint))) == 0
+    return dim.value, k.value, x, el
+
+
+def host_nodel(nn, k, el):
+    from weldformfem_b200 import _lib
+    lib = _lib.load()
+    ne = el.size // k
+    off, cnt = np.empty(nn, np.int32), np.empty(nn, np.int32)
+    nodel, loc = np.empty(ne * k, np.int32), np.empty(ne * k, np.int32)
+    ip = C.POINTER(C.c_int)
+    rc = lib.wf_host_nodel(nn, ne, k, el.ctypes.data_as(C.POINTER(C.c_uint)), off.ctypes.data_as(ip),
+                           cnt.ctypes.data_as(ip), nodel.ctypes.data_as(ip), loc.ctypes.data_as(ip))
+    return rc, off, cnt, nodel, loc
+
+
+BOXES = [((0, 0, 0), (0.3, 0.2, 0.5), 0.05, False), ((0.1, -0.2, 0.3), (0.31, 0.2, 0.11), 0.05, True),
+         ((0, 0, 0), (0.0127, 0.03, 0.0), 0.00025, False), ((1, 2, 0), (0.4, 0.3, 0.0), 0.05, True),
+         ((0, 0, 0), (0.1, 0.1, 0.1), 0.05, False), ((0, 0, 0), (0.7, 0.1, 0.1), 0.05, True)]
+
+
+@pytest.mark.parametrize("V,L,r,tritet", BOXES)
+def test_box_and_connectivity_match_oracle(V, L, r, tritet, oracle_port):
+    dim, k, x, el = host_box(V, L, r, tritet)
+    o = oracle_port()
+    o.box(V, L, r, tritet)
+    info = o.info()
+    assert (dim, k) == (info["dim"], info["nodxelem"])
+    assert np.array_equal(x, o.get("x"))            # coordinates by accumulation: bit-identical
+    assert np.array_equal(el, o.get("m_elnod"))
+    rc, off, cnt, nodel, loc = host_nodel(info["n_nodes"], k, el)
+    assert rc == 0
+    assert np.array_equal(off, o.get("m_nodel_offset"))
+    assert np.array_equal(cnt, o.get("m_nodel_count"))
+    assert np.array_equal(nodel, o.get("m_nodel"))
+    assert np.array_equal(loc, o.get("m_nodel_loc"))
+
+
+@pytest.mark.parametrize("name", sorted(GOLDEN))
+def test_connectivity_matches_reference_fixtures(name):
+    """Against arrays dumped from the unmodified reference build (tests/golden/make_golden.py)."""
+    case, _ = GOLDEN[name]
+    g = np.load(os.path.join(HERE, "golden", name + ".npz"))
+    pad = 1.0 + 1.0e-6
+    L = [case.n[0] * case.h * pad, case.n[1] * case.h * pad, (case.n[2] * case.h * pad) if case.dim == 3 else 0.0]
+    dim, k, x, el = host_box((0, 0, 0), L, 0.5 * case.h, case.tritet)
+    assert np.array_equal(x, g["x0"])
+    assert np.array_equal(el, g["m_elnod"])
+    rc, off, cnt, nodel, loc = host_nodel(x.size // dim, k, el)
+    assert rc == 0
+    for nm, arr in zip(("m_nodel_offset", "m_nodel_count", "m_nodel", "m_nodel_loc"), (off, cnt, nodel, loc)):
+        assert np.array_equal(arr, g[nm]), nm
+
+
+def test_nodel_rejects_out_of_range():
+    el = np.array([0, 1, 2, 9], dtype=np.uint32)
+    rc, *_ = host_nodel(4, 4, el)
+    assert rc != 0
+
+
+def test_nodel_ragged_unstructured():
+    """Random tet soup incl. unused nodes: lists sorted by element id, offsets = exclusive prefix sum."""
+    rng = np.random.default_rng(7)
+    nn, ne, k = 57, 200, 4
+    el = np.stack([rng.choice(nn - 5, size=k, replace=False) for _ in range(ne)]).astype(np.uint32).reshape(-1)
+    rc, off, cnt, nodel, loc = host_nodel(nn, k, el)
+    assert rc == 0
+    assert cnt[-5:].sum() == 0 and cnt.sum() == ne * k
+    assert np.array_equal(off, np.concatenate([[0], np.cumsum(cnt)[:-1]]))
+    for n in range(nn):
+        lst = nodel[off[n]:off[n] + cnt[n]]
+        assert np.all(np.diff(lst) > 0)
+        for e, ln in zip(lst, loc[off[n]:off[n] + cnt[n]]):
+            assert el[e * k + ln] == n
+
+
+# ---- partition / halo lists (canonical definition) -------------------------------------
+def py_partition(P, p, k, nn, el):
+    """Independent numpy restatement of the canonical partition."""
+    ne = el.size // k
+    el = el.reshape(ne, k).astype(np.int64)
+    beg = [(ne * q) // P for q in range(P + 1)]
+    mine = el[beg[p]:beg[p + 1]]
+    l2g = np.unique(mine)
+    lel = np.searchsorted(l2g, mine).astype(np.uint32)
+    neigh, offs, halo = [], [0], []
+    for q in range(P):
+        if q == p:
+            continue
+        shared = np.intersect1d(l2g, np.unique(el[beg[q]:beg[q + 1]]))
+        if shared.size:
+            neigh.append(q)
+            halo.extend(np.searchsorted(l2g, shared).tolist())
+            offs.append(len(halo))
+    return beg[p], beg[p + 1], l2g.astype(np.int32), lel.reshape(-1), neigh, offs, halo
+
+
+def c_partition(P, p, k, nn, el, box=None):
+    from weldformfem_b200 import _lib
+    lib = _lib.load()
+    h = C.c_void_p()
+    if box is None:
+        assert lib.wf_partition_build(C.byref(h), P, p, k, nn, el.size // k, el.ctypes.data_as(C.POINTER(C.c_uint))) == 0
+    else:
+        V, L, r, tritet = box
+        assert lib.wf_partition_build_box(C.byref(h), P, p, (C.c_double * 3)(*V), (C.c_double * 3)(*L), r, int(tritet)) == 0
+    eb, ee, nl, nng = C.c_int(), C.c_int(), C.c_int(), C.c_int()
+    assert lib.wf_partition_info(h, C.byref(eb), C.byref(ee), C.byref(nl), C.byref(nng)) == 0
+    l2g = np.ctypeslib.as_array(lib.wf_partition_node_l2g(h), (nl.value,)).copy()
+    lel = np.ctypeslib.as_array(lib.wf_partition_local_elnod(h), ((ee.value - eb.value) * k,)).copy()
+    neigh = list(np.ctypeslib.as_array(lib.wf_partition_neigh_ranks(h), (max(nng.value, 1),))[:nng.value])
+    offs = list(np.ctypeslib.as_array(lib.wf_partition_halo_offset(h), (nng.value + 1,)))
+    halo = list(np.ctypeslib.as_array(lib.wf_partition_halo_nodes(h), (max(offs[-1], 1),))[:offs[-1]])
+    lib.wf_partition_free(h)
+    return eb.value, ee.value, l2g, lel, neigh, offs, halo
+
+
+@pytest.mark.parametrize("P", [2, 3, 4, 8])
+@pytest.mark.parametrize("box", [((0, 0, 0), (0.5, 0.4, 0.9), 0.05, False), ((0, 0, 0), (0.3, 0.3, 0.4), 0.05, True),
+                                 ((0, 0, 0), (0.9, 0.7, 0.0), 0.05, False)])
+def test_partition_bit_exact(P, box):
+    dim, k, x, el = host_box(*box)
+    nn = x.size // dim
+    all_l2g = []
+    halos = {}
+    for p in range(P):
+        want = py_partition(P, p, k, nn, el)
+        got = c_partition(P, p, k, nn, el)
+        got_box = c_partition(P, p, k, nn, el, box=box)
+        for g in (got, got_box):
+            assert g[0] == want[0] and g[1] == want[1]
+            assert np.array_equal(g[2], want[2]) and np.array_equal(g[3], want[3])
+            assert [int(q) for q in g[4]] == want[4] and [int(q) for q in g[5]] == want[5]
+            assert [int(q) for q in g[6]] == want[6]
+        all_l2g.append(got[2])
+        for i, q in enumerate(got[4]):
+            halos[(p, int(q))] = got[2][np.array(got[6][got[5][i]:got[5][i + 1]], dtype=int)]
+    # every node is local somewhere; halo lists are identical on both sides (global ids, ascending)
+    assert np.array_equal(np.unique(np.concatenate(all_l2g)), np.arange(nn))
+    for (p, q), ids in halos.items():
+        assert np.array_equal(ids, halos[(q, p)])
+        assert np.all(np.diff(ids) > 0)
