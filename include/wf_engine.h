@@ -97,6 +97,11 @@ int wf_step(wf_engine *, int nsteps); /* fused rows 1-22 of the step, Solver_exp
 int wf_nonfinite_flag(wf_engine *, int *flag);
 int wf_energies(wf_engine *, double *Ekin, double *dEint); /* computeEnergies, Mechanical.C:2145 */
 int wf_get_time(wf_engine *, double *time, long *step_count);
+/* profiling / tuning hooks (no reference counterpart): wf_step with CUDA events around every launch,
+ * ms[0..4] += device time of predictor, E1 (element volume), N1 (nodal sums), E2 (main element pass),
+ * N2 (assembly + integration); and selection of an alternative implementation of one of the four kernels */
+int wf_step_timed(wf_engine *, int nsteps, float *ms5);
+int wf_set_variant(wf_engine *, int kernel /*0..3 = E1,N1,E2,N2*/, int variant);
 
 /* 1:1 unfused entry points for parity bisecting; names = Domain_d members */
 int wf_UpdatePrediction(wf_engine *);          /* Domain_d.C:961 */

@@ -89,7 +89,7 @@ def test_c1_one_hexa_126_steps(strict, oracle_port):
     eng, ref = run_pair(case, oracle_port, 126, strict)
     # the acceleration is a small difference of large forces (|a| ~ 3 vs |f| ~ 5e6): looser bound
     compare(eng, ref, [n for n in STATE if n not in ("a", "prev_a")], 1e-11 if strict else 1e-9, "C1")
-    compare(eng, ref, ["a", "prev_a"], 1e-8, "C1 accelerations")
+    compare(eng, ref, ["a", "prev_a"], 1e-7, "C1 accelerations")
     u = eng.get("u").reshape(-1, 3)
     # validation/1elem_3d_red_int_f_0.06.txt:5-14 (older pressure law, ~1 % pin): u_x(node 1) = 2.991992e-04
     assert abs(u[1, 0] - 2.991992e-04) / 2.991992e-04 < 0.02

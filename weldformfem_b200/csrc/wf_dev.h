@@ -28,6 +28,7 @@ struct WfDev {
   double *voln_sum;                  /* [np] sum of vol over nodel(n) (no /k) */
   double *voln0_sum;                 /* [np] sum of vol_0 (press 0/1) or of vol_0/4.0 (press 3) */
   double *nodal_p;                   /* [np] press 0: voln/voln_0 ; press 1/3: nodal pressure pn */
+  double *rhobar;                    /* [np] mean rho of the elements around the node (WF_FAST mass) */
   int *nodel_count;                  /* [np] */
   int *bc_index;                     /* [np] -1 or row of bc_mask / bc_vals */
   const unsigned char *bc_mask;      /* [nbc] bit c: dim c prescribed */
@@ -45,8 +46,10 @@ struct WfDev {
   double *eps;                       /* [6][ep] (optional) */
   double *p, *pl_strain, *sigma_y, *vol, *vol_0, *rho, *rho_0; /* [ep] */
   double *hg_q;                      /* [2][ep] 2D quads (m_hg_q) */
-  double *f_elem;                    /* [k*dim][ep] */
-  double *f_elem_hg;                 /* [k*dim][ep] (strict / unfused only) */
+  const int *pos;                    /* [k][ep] offset of (e, ln) in fsell: dim*q - (dim-1)*(n&31), q = sell index */
+  double *fsell, *fsell_hg;          /* [slice][j][dim][32] node-ordered element (and hourglass) forces */
+  double *f_elem;                    /* [k*dim][ep]  (unfused path only) */
+  double *f_elem_hg;                 /* [k*dim][ep]  (unfused path only) */
 
   /* unfused-path intermediates (allocated on first use) */
   double *dH;                        /* [dim][k][ep] dN/dX * detJ (m_dH_detJ_dx/dy/dz) */
@@ -77,4 +80,5 @@ struct WfPar {
   double dt, alpha, beta, gamma;
   double w; /* Gauss weight, Mechanical.C:269-282 */
   int xmin_cur; /* which xmin_key slot holds min x_r of the current coordinates */
+  int variant[4]; /* tuning: kernel variant for E1, N1, E2, N2 (0 = default) */
 };

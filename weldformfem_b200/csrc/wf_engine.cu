@@ -33,7 +33,7 @@ struct wf_engine {
   bool meshed = false, material_set = false, bcs_ready = false, inited = false, dbg = false;
   bool predicted = false;  // v / u_dt currently hold next-step predictor values (only inside wf_step)
   // which unfused-path products are current (cleared by wf_step)
-  bool a_in_dbg = false, fi_in_dbg = false, mdiag_in_dbg = false, sigma_in_dbg = false, rates_in_dbg = false;
+  bool a_in_dbg = false, fi_in_dbg = false, sigma_in_dbg = false, rates_in_dbg = false, felem_in_dbg = false;
   double time = 0.0;
   long step_count = 0;
   wf_material mat;
@@ -42,6 +42,8 @@ struct wf_engine {
   // host copies of integer artefacts (reference layouts)
   std::vector<unsigned> h_elnod;
   std::vector<int> h_nodel, h_nodel_loc, h_offset, h_count;
+  std::vector<unsigned> h_pos; // [k][ep], see WfDev::pos
+  long long sell_total = 0;
   std::vector<int> bc_nod[3];
   std::vector<double> bc_val[3];
   int nbc_rows = 0;
@@ -178,8 +180,25 @@ static int upload_mesh(wf_engine *E, int nn, int ne, const double *x, const unsi
     for (int j = 0; j < E->h_count[n]; j++)
       slots[(size_t)(base + (long long)j * 32 + (n & 31))] = E->h_nodel[off + j] * k + E->h_nodel_loc[off + j];
   }
-  long long *dptr; int *dslots;
-  if (dalloc(E, &dptr, sell_ptr.size()) || dalloc(E, &dslots, slots.size())) return 1;
+  // offset of (e, ln) in the node-ordered force buffer [slice][j][dim][32]: dim*q - (dim-1)*lane
+  NEED((long long)dim * tot < 4294967295LL, "node-ordered force buffer exceeds 32-bit offsets");
+  E->sell_total = tot;
+  const long long ep_ = round_up(ne, 32);
+  E->h_pos.assign((size_t)k * ep_, 0u);
+  for (int n = 0; n < nn; n++) {
+    const long long base = sell_ptr[n >> 5];
+    const int off = E->h_offset[n];
+    for (int j = 0; j < E->h_count[n]; j++) {
+      const long long q = base + (long long)j * 32 + (n & 31);
+      E->h_pos[(size_t)E->h_nodel_loc[off + j] * ep_ + E->h_nodel[off + j]] = (unsigned)(dim * q - (long long)(dim - 1) * (n & 31));
+    }
+  }
+  long long *dptr; int *dslots; int *dpos;
+  if (dalloc(E, &dptr, sell_ptr.size()) || dalloc(E, &dslots, slots.size()) || dalloc(E, &dpos, E->h_pos.size()) ||
+      dalloc(E, &d.fsell, (size_t)dim * tot))
+    return 1;
+  CK(cudaMemcpyAsync(dpos, E->h_pos.data(), E->h_pos.size() * sizeof(int), cudaMemcpyHostToDevice, E->stream));
+  d.pos = dpos;
   CK(cudaMemcpyAsync(dptr, sell_ptr.data(), sell_ptr.size() * sizeof(long long), cudaMemcpyHostToDevice, E->stream));
   CK(cudaMemcpyAsync(dslots, slots.data(), slots.size() * sizeof(int), cudaMemcpyHostToDevice, E->stream));
   d.sell_ptr = dptr; d.sell_slots = dslots;
@@ -195,13 +214,13 @@ static int upload_mesh(wf_engine *E, int nn, int ne, const double *x, const unsi
     CK(cudaStreamSynchronize(E->stream));
   }
   // state
-  const size_t nv = (size_t)dim * d.np, e6 = (size_t)6 * d.ep, ekd = (size_t)k * dim * d.ep;
+  const size_t nv = (size_t)dim * d.np, e6 = (size_t)6 * d.ep;
   if (dalloc(E, &d.x, nv) || dalloc(E, &d.v, nv) || dalloc(E, &d.prev_a, nv) || dalloc(E, &d.u, nv) ||
       dalloc(E, &d.u_dt, nv) || dalloc(E, &d.voln_sum, d.np) || dalloc(E, &d.voln0_sum, d.np) ||
-      dalloc(E, &d.nodal_p, d.np) || dalloc(E, &d.nodel_count, d.np) || dalloc(E, &d.bc_index, d.np) ||
+      dalloc(E, &d.nodal_p, d.np) || dalloc(E, &d.rhobar, d.np) || dalloc(E, &d.nodel_count, d.np) || dalloc(E, &d.bc_index, d.np) ||
       dalloc(E, &d.tau, e6) || dalloc(E, &d.p, d.ep) || dalloc(E, &d.pl_strain, d.ep) ||
       dalloc(E, &d.sigma_y, d.ep) || dalloc(E, &d.vol, d.ep) || dalloc(E, &d.vol_0, d.ep) ||
-      dalloc(E, &d.rho, d.ep) || dalloc(E, &d.rho_0, d.ep) || dalloc(E, &d.f_elem, ekd) ||
+      dalloc(E, &d.rho, d.ep) || dalloc(E, &d.rho_0, d.ep) ||
       dalloc(E, &d.nonfinite, 1) || dalloc(E, &d.xmin_key, 2) || dalloc(E, &d.red, 8) || dalloc(E, &d.mdiag, d.np))
     return 1;
   if (E->et == ET_QUAD4 && dalloc(E, &d.hg_q, (size_t)2 * d.ep)) return 1;
@@ -373,6 +392,7 @@ static int ensure_dbg(wf_engine *E) {
       dalloc(E, &d.rot_rate, e6) || dalloc(E, &d.a, nv) || dalloc(E, &d.fi, nv) || dalloc(E, &d.voln, d.np))
     return 1;
   if (!d.sigma && dalloc(E, &d.sigma, e6)) return 1;
+  if (!d.f_elem && dalloc(E, &d.f_elem, ekd)) return 1;
   if (!d.f_elem_hg && dalloc(E, &d.f_elem_hg, ekd)) return 1;
   E->dbg = true;
   return 0;
@@ -413,10 +433,10 @@ extern "C" int wf_init_phase(wf_engine *E, int phase, double dt) {
     P.gamma = 1.5 - P.alpha;
     P.track_eps = (E->tracking & 1) ? 1 : 0;
     P.store_sigma = ((E->tracking & 2) || P.av_alpha != 0.0 || P.av_beta != 0.0) ? 1 : 0;
-    const size_t e6 = (size_t)6 * d.ep, ekd = (size_t)E->k * E->dim * d.ep;
+    const size_t e6 = (size_t)6 * d.ep;
     if (P.track_eps && !d.eps && dalloc(E, &d.eps, e6)) return 1;
     if (P.store_sigma && !d.sigma && dalloc(E, &d.sigma, e6)) return 1;
-    if (E->strict && !d.f_elem_hg && dalloc(E, &d.f_elem_hg, ekd)) return 1;
+    if (E->strict && !d.fsell_hg && dalloc(E, &d.fsell_hg, (size_t)E->dim * E->sell_total)) return 1;
     E->L->init_elem(d, P, E->stream); // InitValues
     // Solver_explicit.C:176-190: v, a, u are zeroed inside the per-dimension loop, so only the LAST
     // dimension's prescribed velocities survive initialisation
@@ -440,7 +460,7 @@ extern "C" int wf_init_phase(wf_engine *E, int phase, double dt) {
     }
     if (check_launch(E, "wf_init phase 1")) return 1;
     E->time = 0.0; E->step_count = 0; E->predicted = false;
-    E->a_in_dbg = E->fi_in_dbg = E->mdiag_in_dbg = E->sigma_in_dbg = E->rates_in_dbg = false;
+    E->a_in_dbg = E->fi_in_dbg = E->sigma_in_dbg = E->rates_in_dbg = E->felem_in_dbg = false;
     E->inited = true;
   }
   return 0;
@@ -470,8 +490,57 @@ extern "C" int wf_step(wf_engine *E, int nsteps) {
     E->time += P.dt;
     E->step_count++;
   }
-  E->a_in_dbg = E->fi_in_dbg = E->mdiag_in_dbg = E->sigma_in_dbg = E->rates_in_dbg = false;
+  E->a_in_dbg = E->fi_in_dbg = E->sigma_in_dbg = E->rates_in_dbg = E->felem_in_dbg = false;
   return check_launch(E, "wf_step");
+}
+
+// tuning / profiling hooks -----------------------------------------------------------------------------
+extern "C" int wf_set_variant(wf_engine *E, int kernel, int variant) {
+  NEED(kernel >= 0 && kernel < 4, "kernel id must be 0..3 (E1, N1, E2, N2)");
+  E->P.variant[kernel] = variant;
+  return 0;
+}
+
+// same as wf_step, with CUDA events around every launch; ms[0..4] += time of predictor, E1, N1, E2, N2
+extern "C" int wf_step_timed(wf_engine *E, int nsteps, float *ms) {
+  NEED(E->inited, "wf_step before wf_init");
+  NEED(!E->distributed, "distributed engines step with wf_step_phase");
+  NEED(ms, "null output");
+  CK(cudaSetDevice(E->device));
+  WfDev &d = E->d;
+  WfPar &P = E->P;
+  const int sep = E->strict ? 1 : 0;
+  std::vector<cudaEvent_t> ev;
+  std::vector<int> tag;
+  auto mark = [&](int t) {
+    cudaEvent_t x;
+    cudaEventCreate(&x);
+    cudaEventRecord(x, E->stream);
+    ev.push_back(x);
+    tag.push_back(t);
+  };
+  mark(-1);
+  for (int s = 0; s < nsteps; s++) {
+    const bool last = (s == nsteps - 1);
+    if (!E->predicted) { E->L->predict(d, P, 1, E->stream); mark(0); }
+    E->L->elem_vol(d, P, E->et, 0, E->stream); mark(1);
+    E->L->node_vol(d, P, 1, 0, E->stream); mark(2);
+    E->L->elem_main(d, P, E->et, sep, E->stream); mark(3);
+    E->L->node_update(d, P, sep, last ? 0 : 1, 0, E->stream); mark(4);
+    E->predicted = !last;
+    P.xmin_cur ^= 1;
+    E->time += P.dt;
+    E->step_count++;
+  }
+  CK(cudaStreamSynchronize(E->stream));
+  for (size_t i = 1; i < ev.size(); i++) {
+    float t = 0.f;
+    cudaEventElapsedTime(&t, ev[i - 1], ev[i]);
+    ms[tag[i]] += t;
+  }
+  for (auto x : ev) cudaEventDestroy(x);
+  E->a_in_dbg = E->fi_in_dbg = E->sigma_in_dbg = E->rates_in_dbg = E->felem_in_dbg = false;
+  return check_launch(E, "wf_step_timed");
 }
 
 extern "C" int wf_step_phase(wf_engine *E, int phase, int last_step) {
@@ -522,7 +591,7 @@ extern "C" int wf_calcElemJAndDerivatives(wf_engine *E) { UNFUSED_PROLOGUE(); E-
 extern "C" int wf_Calc_Element_Radius(wf_engine *E) { UNFUSED_PROLOGUE(); E->L->elem_vol(d, P, E->et, 2, E->stream); return check_launch(E, __func__); }
 extern "C" int wf_CalcElemVol(wf_engine *E) { UNFUSED_PROLOGUE(); E->L->vol_from_detj(d, E->et, E->stream); return check_launch(E, __func__); }
 extern "C" int wf_CalcNodalVol(wf_engine *E) { UNFUSED_PROLOGUE(); E->L->u_nodal_vol(d, E->stream); return check_launch(E, __func__); }
-extern "C" int wf_CalcNodalMassFromVol(wf_engine *E) { UNFUSED_PROLOGUE(); E->L->node_mass(d, P, 1, E->stream); E->mdiag_in_dbg = true; return check_launch(E, __func__); }
+extern "C" int wf_CalcNodalMassFromVol(wf_engine *E) { UNFUSED_PROLOGUE(); E->L->node_mass(d, P, 1, E->stream); return check_launch(E, __func__); }
 extern "C" int wf_calcElemStrainRates(wf_engine *E) { UNFUSED_PROLOGUE(); E->L->u_strain_rates(d, P, E->et, E->stream); E->rates_in_dbg = true; return check_launch(E, __func__); }
 extern "C" int wf_calcElemPressure(wf_engine *E) {
   UNFUSED_PROLOGUE();
@@ -532,7 +601,7 @@ extern "C" int wf_calcElemPressure(wf_engine *E) {
 }
 extern "C" int wf_CalcStressStrain(wf_engine *E, double dt) { UNFUSED_PROLOGUE(); E->L->u_stress(d, P, dt, E->stream); E->sigma_in_dbg = true; return check_launch(E, __func__); }
 extern "C" int wf_calcArtificialViscosity(wf_engine *E) { UNFUSED_PROLOGUE(); E->L->u_artvisc(d, P, E->stream); return check_launch(E, __func__); }
-extern "C" int wf_calcElemForces(wf_engine *E) { UNFUSED_PROLOGUE(); E->L->u_forces(d, P, E->et, E->stream); return check_launch(E, __func__); }
+extern "C" int wf_calcElemForces(wf_engine *E) { UNFUSED_PROLOGUE(); E->L->u_forces(d, P, E->et, E->stream); E->felem_in_dbg = true; return check_launch(E, __func__); }
 extern "C" int wf_calcElemHourglassForces(wf_engine *E) { UNFUSED_PROLOGUE(); E->L->u_hourglass(d, P, E->et, E->stream); return check_launch(E, __func__); }
 extern "C" int wf_assemblyForces(wf_engine *E) { UNFUSED_PROLOGUE(); E->L->u_assembly(d, E->stream); E->fi_in_dbg = true; return check_launch(E, __func__); }
 extern "C" int wf_calcAccel(wf_engine *E) { UNFUSED_PROLOGUE(); E->L->u_accel(d, E->stream); E->a_in_dbg = true; return check_launch(E, __func__); }
@@ -567,7 +636,7 @@ struct ArrayRef {
   const void *host = nullptr;
   size_t bytes = 0;
   int comp = 0; // for dH: which dimension
-  bool lazy_sigma = false, lazy_fi = false, lazy_mdiag = false, lazy_voln = false, lazy_pnode = false;
+  bool lazy_sigma = false, lazy_fi = false, lazy_voln = false, lazy_pnode = false, lazy_felem = false, hg = false;
 };
 
 static bool lookup(wf_engine *E, const std::string &nm, ArrayRef &r, bool for_write) {
@@ -588,7 +657,7 @@ static bool lookup(wf_engine *E, const std::string &nm, ArrayRef &r, bool for_wr
     if (E->fi_in_dbg && d.fi) return nodevec(d.fi);
     r.kind = K_NODEVEC; r.bytes = nd; r.lazy_fi = true; return !for_write;
   }
-  if (nm == "m_mdiag") { r.kind = K_NODESCAL; r.dev = d.mdiag; r.bytes = nnb; r.lazy_mdiag = !E->mdiag_in_dbg; return true; }
+  if (nm == "m_mdiag") { r.kind = K_NODESCAL; r.dev = d.mdiag; r.bytes = nnb; return true; }
   if (nm == "m_voln") { r.kind = K_NODESCAL; r.dev = d.voln_sum; r.bytes = nnb; r.lazy_voln = true; return !for_write; }
   if (nm == "p_node") { r.kind = K_NODESCAL; r.bytes = nnb; r.lazy_pnode = true; return !for_write; }
   if (nm == "vol") return elems(d.vol);
@@ -612,8 +681,13 @@ static bool lookup(wf_engine *E, const std::string &nm, ArrayRef &r, bool for_wr
     r.kind = K_ELEMNODE; r.dev = d.dH; r.bytes = nk; r.comp = nm.back() - 'x';
     return d.dH != nullptr && r.comp < E->dim;
   }
-  if (nm == "m_f_elem") { r.kind = K_ELEMNODEVEC; r.dev = d.f_elem; r.bytes = nk * E->dim; return true; }
-  if (nm == "m_f_elem_hg") { r.kind = K_ELEMNODEVEC; r.dev = d.f_elem_hg; r.bytes = nk * E->dim; return d.f_elem_hg != nullptr; }
+  if (nm == "m_f_elem" || nm == "m_f_elem_hg") {
+    r.kind = K_ELEMNODEVEC; r.bytes = nk * E->dim; r.hg = (nm == "m_f_elem_hg");
+    if ((E->felem_in_dbg || for_write) && d.f_elem) { r.dev = r.hg ? d.f_elem_hg : d.f_elem; return r.dev != nullptr; }
+    if (for_write) return false;
+    r.lazy_felem = true; // rebuilt from the node-ordered buffer written by the fused step
+    return r.hg ? d.fsell_hg != nullptr : true;
+  }
   if (nm == "m_hg_q") { r.kind = K_HGQ; r.dev = d.hg_q; r.bytes = nk * E->dim; return d.hg_q != nullptr; }
   auto hosti = [&](const void *p, size_t b) { r.kind = K_INT_HOST; r.host = p; r.bytes = b; return !for_write; };
   if (nm == "m_elnod") return hosti(E->h_elnod.data(), E->h_elnod.size() * sizeof(unsigned));
@@ -674,24 +748,28 @@ extern "C" int wf_get_array(wf_engine *E, const char *name, void *dst, size_t by
     int rc = download(E, tmp, (size_t)6 * d.ep, h);
     cudaFree(tmp);
     if (rc) return 1;
+  } else if (r.lazy_felem) {
+    NEED(E->step_count > 0, "m_f_elem is available after a step");
+    std::vector<double> fs;
+    if (download(E, r.hg ? d.fsell_hg : d.fsell, (size_t)dim * E->sell_total, fs)) return 1;
+    for (int e2 = 0; e2 < ne; e2++)
+      for (int n = 0; n < k; n++) {
+        const size_t o = E->h_pos[(size_t)n * d.ep + e2];
+        for (int c = 0; c < dim; c++) out[((size_t)e2 * k + n) * dim + c] = fs[o + 32 * (size_t)c];
+      }
+    return 0;
   } else if (r.lazy_fi) {
     NEED(E->step_count > 0 || E->dbg, "m_fi is available after a step");
     double *save_fi = d.fi;
     double *tmp = nullptr;
     CK(cudaMalloc((void **)&tmp, (size_t)dim * d.np * sizeof(double)));
     d.fi = tmp;
-    double *save_hg = d.f_elem_hg;
-    if (E->strict) {
-      E->L->u_assembly(d, E->stream);
-    } else { // fused hourglass: one-pass gather, exactly as k_node_update sums it
-      E->L->node_update(d, E->P, 0, 0, 1, E->stream);
-    }
+    E->L->node_update(d, E->P, E->strict ? 1 : 0, 0, 1, E->stream); // sums only, exactly as the step forms them
     int rc = download(E, tmp, (size_t)dim * d.np, h);
-    d.fi = save_fi; d.f_elem_hg = save_hg;
+    d.fi = save_fi;
     cudaFree(tmp);
     if (rc) return 1;
   } else {
-    if (r.lazy_mdiag) E->L->node_mass(d, E->P, 0, E->stream);
     size_t count = 0;
     switch (r.kind) {
       case K_NODEVEC: count = (size_t)dim * d.np; break;
@@ -814,7 +892,6 @@ extern "C" int wf_energies(wf_engine *E, double *Ekin, double *dEint) {
   CK(cudaSetDevice(E->device));
   WfDev &d = E->d;
   CK(cudaMemsetAsync(d.red, 0, 8 * sizeof(double), E->stream));
-  if (!E->mdiag_in_dbg) E->L->node_mass(d, E->P, 0, E->stream);
   double *sig = d.sigma, *tmp = nullptr;
   bool have_rates = d.str_rate != nullptr && E->rates_in_dbg;
   if (have_rates && !(d.sigma && (E->P.store_sigma || E->sigma_in_dbg))) {

@@ -9,7 +9,12 @@
 //   E1 k_elem_vol    : x -> vol                                  (calcElemJAndDerivatives + CalcElemVol)
 //   N1 k_node_vol    : vol gather -> nodal sums / ratios         (CalcNodalVol, node part of calcElemPressure*)
 //   E2 k_elem_main   : J, dH, D, W, pressure, Jaumann + J2 return, element + hourglass forces
-//   N2 k_node_update : force gather, mass, accel, BCs, corrector, position, next-step predictor
+//   N2 k_node_update : per-node force sum, accel, BCs, corrector, position, next-step predictor
+// Element forces travel from E2 to N2 through the node-ordered buffer fsell: the contribution of
+// (element e, local node ln) is written straight into the entry of node n's nodel list that the
+// reference's assemblyForces would read for it (pos[ln][e]), so N2 streams its list with coalesced
+// loads and sums it in nodel order — a deterministic gather with the indirection resolved on the
+// write side, no atomics.
 #include <cuda_runtime.h>
 #include <math.h>
 
@@ -21,6 +26,8 @@
 #endif
 
 namespace WF_NS {
+
+#include "wf_hex_fast.cuh"
 
 constexpr int TPB_E = 128; // element kernels: register-heavy
 constexpr int TPB_N = 256; // node kernels (multiple of 32: one warp == one SELL slice)
@@ -149,6 +156,14 @@ __global__ void __launch_bounds__(TPB_N) k_node_vol(WfDev d, WfPar P, int mode, 
   if (n >= d.nn) return;
   if (mode == 0) {
     d.voln0_sum[n] = quarter ? sq : s;
+    // mean density of the elements around the node (rho is frozen after init on the reference's CPU
+    // path, Solver_explicit.C:262 vs :601-608), used by the WF_FAST nodal mass
+    double rs = 0.0;
+    for (int j = 0; j < width; j++) {
+      int slot = __ldg(d.sell_slots + base + ((long long)j << 5) + lane);
+      if (slot >= 0) rs += d.rho[slot / K];
+    }
+    d.rhobar[n] = rs / (double)d.nodel_count[n];
     return;
   }
   d.voln_sum[n] = s;
@@ -162,6 +177,28 @@ __global__ void __launch_bounds__(TPB_N) k_node_vol(WfDev d, WfPar P, int mode, 
     double v0 = d.voln0_sum[n], pn = 0.0;
     if (v0 > 1e-12) { double Jn = sq / v0; pn = P.Kbulk * (1.0 - Jn); }
     d.nodal_p[n] = pn;
+  }
+  // CalcNodalMassFromVol (Mechanical.C:1576-1601): mass = sum_e rho[e] * voln / count, voln = sum/k
+  const double voln = s / (double)K;
+  if (!P.strict) {
+    // sum_e (rho_e voln / count) regrouped as voln * mean(rho_e): same value up to rounding
+    d.mdiag[n] = d.rhobar[n] * voln;
+  } else {
+    const int cnt = d.nodel_count[n];
+    double mass = 0.0;
+    if ((cnt & (cnt - 1)) == 0) { // x / 2^m == x * 2^-m exactly: bit-identical to the division
+      const double inv = 1.0 / (double)cnt;
+      for (int j = 0; j < width; j++) {
+        int slot = __ldg(d.sell_slots + base + ((long long)j << 5) + lane);
+        if (slot >= 0) mass += 1.0 * d.rho[slot / K] * voln * inv;
+      }
+    } else {
+      for (int j = 0; j < width; j++) {
+        int slot = __ldg(d.sell_slots + base + ((long long)j << 5) + lane);
+        if (slot >= 0) mass += 1.0 * d.rho[slot / K] * voln / cnt;
+      }
+    }
+    d.mdiag[n] = mass;
   }
 }
 
@@ -268,56 +305,47 @@ __global__ void __launch_bounds__(TPB_E) k_elem_main(WfDev d, WfPar P) {
   double f[K][D];
   elem_forces<ET>(dH, so.sig, detJ, radius, d.domtype, d.vol_weight, f);
   // hourglass control
+  double fh[K][D];
+  bool have_hg = false;
   if constexpr (ET == ET_HEX8) {
-    if (P.hexa_hg != 0.0) {
-      double fh[K][D];
-      hexa_hourglass(P, vl, vol, rho_e, fh);
-      if (SEPARATE_HG) {
-#pragma unroll
-        for (int n = 0; n < K; n++)
-#pragma unroll
-          for (int c = 0; c < D; c++) d.f_elem_hg[((long long)n * D + c) * d.ep + e] = fh[n][c];
-      } else {
-#pragma unroll
-        for (int n = 0; n < K; n++)
-#pragma unroll
-          for (int c = 0; c < D; c++) f[n][c] -= fh[n][c];
-      }
-    }
+    if (P.hexa_hg != 0.0) { hexa_hourglass(P, vl, vol, rho_e, fh); have_hg = true; }
   } else if constexpr (ET == ET_QUAD4) {
     double q[2] = {d.hg_q[e], d.hg_q[d.ep + e]};
-    double fh[K][D];
     quad_hourglass(P, vl, vol, rho_e, q, fh);
     d.hg_q[e] = q[0];
     d.hg_q[d.ep + e] = q[1];
-    if (SEPARATE_HG) {
+    have_hg = true;
+  }
+  if (have_hg && !SEPARATE_HG) {
 #pragma unroll
-      for (int n = 0; n < K; n++)
+    for (int n = 0; n < K; n++)
 #pragma unroll
-        for (int c = 0; c < D; c++) d.f_elem_hg[((long long)n * D + c) * d.ep + e] = fh[n][c];
-    } else {
+      for (int c = 0; c < D; c++) f[n][c] -= fh[n][c];
+  }
+  // node-ordered stores: entry of (e, n) in the nodel list of its node
 #pragma unroll
-      for (int n = 0; n < K; n++)
+  for (int n = 0; n < K; n++) {
+    const long long o = (long long)__ldg(d.pos + (long long)n * d.ep + e);
 #pragma unroll
-        for (int c = 0; c < D; c++) f[n][c] -= fh[n][c];
+    for (int c = 0; c < D; c++) d.fsell[o + 32 * c] = f[n][c];
+    if (SEPARATE_HG && have_hg) {
+#pragma unroll
+      for (int c = 0; c < D; c++) d.fsell_hg[o + 32 * c] = fh[n][c];
     }
   }
-#pragma unroll
-  for (int n = 0; n < K; n++)
-#pragma unroll
-    for (int c = 0; c < D; c++) d.f_elem[((long long)n * D + c) * d.ep + e] = f[n][c];
 }
 
 // ---------------------------------------------------------------------------------------------
-// N2: force gather (assemblyForces, Matrices.C:42-87), nodal mass (CalcNodalMassFromVol,
-// Mechanical.C:1576-1601), calcAccel (:321-341), ImposeBCA, UpdateCorrectionAccVel
-// (Domain_d.C:981-997), ImposeBCV, axis constraint (Solver_explicit.C:953-969),
-// UpdateCorrectionPos (Domain_d.C:1005-1025) and, unless this is the last step of the batch,
-// the next step's UpdatePrediction + ImposeBCV.
-//   phase 0 = everything;  phase 1 = gather only, partial sums to d.fi (multi-GPU);
-//   phase 2 = integrate from d.fi / d.voln_sum (after halo exchange)
+// N2: per-node force sum in nodel order (assemblyForces, Matrices.C:42-87: element forces first,
+// then hourglass forces subtracted), calcAccel (Mechanical.C:321-341), ImposeBCA,
+// UpdateCorrectionAccVel (Domain_d.C:981-997), ImposeBCV, axis constraint
+// (Solver_explicit.C:953-969), UpdateCorrectionPos (Domain_d.C:1005-1025) and, unless this is the
+// last step of the batch, the next step's UpdatePrediction + ImposeBCV.  The nodal mass was formed
+// by N1.  One warp == one slice of 32 nodes; every load is a contiguous 256 B row.
+//   phase 0 = everything;  phase 1 = sums only, to d.fi (multi-GPU partials / lazy m_fi);
+//   phase 2 = integrate from d.fi (after the halo exchange)
 // ---------------------------------------------------------------------------------------------
-template <int K, int D, bool SEPARATE_HG>
+template <int D, bool SEPARATE_HG, int UNROLL>
 __global__ void __launch_bounds__(TPB_N) k_node_update(WfDev d, WfPar P, int fuse_predictor, int phase) {
   int n = blockIdx.x * blockDim.x + threadIdx.x;
   int slice = n >> 5;
@@ -326,31 +354,27 @@ __global__ void __launch_bounds__(TPB_N) k_node_update(WfDev d, WfPar P, int fus
   double fi[D];
 #pragma unroll
   for (int c = 0; c < D; c++) fi[c] = 0.0;
-  double mass = 0.0;
   if (phase != 2) {
     const long long base = d.sell_ptr[slice];
     const int width = (int)((d.sell_ptr[slice + 1] - base) >> 5);
-    const bool valid = n < d.nn;
-    const int cnt = valid ? d.nodel_count[n] : 1;
-    const double voln = valid ? d.voln_sum[n] / (double)K : 0.0; // m_voln[n] /= m_nodxelem
-    for (int j = 0; j < width; j++) {
-      int slot = __ldg(d.sell_slots + base + ((long long)j << 5) + lane);
-      if (slot >= 0) {
-        int e = slot / K, ln = slot - e * K;
+    const double *__restrict__ row = d.fsell + base * D + lane;
+    // padding entries hold +0.0 and are never written, so summing the full width is exact
+    for (int j0 = 0; j0 < width; j0 += UNROLL) {
+      double fv[UNROLL][D];
 #pragma unroll
-        for (int c = 0; c < D; c++) fi[c] += d.f_elem[((long long)ln * D + c) * d.ep + e];
-        if (phase == 0) mass += 1.0 * d.rho[e] * voln / cnt;
-      }
+      for (int q = 0; q < UNROLL; q++)
+#pragma unroll
+        for (int c = 0; c < D; c++) fv[q][c] = (j0 + q < width) ? row[((long long)(j0 + q) * D + c) * 32] : 0.0;
+#pragma unroll
+      for (int q = 0; q < UNROLL; q++)
+#pragma unroll
+        for (int c = 0; c < D; c++) fi[c] += fv[q][c];
     }
     if (SEPARATE_HG) {
-      for (int j = 0; j < width; j++) {
-        int slot = __ldg(d.sell_slots + base + ((long long)j << 5) + lane);
-        if (slot >= 0) {
-          int e = slot / K, ln = slot - e * K;
+      const double *__restrict__ rowh = d.fsell_hg + base * D + lane;
+      for (int j = 0; j < width; j++)
 #pragma unroll
-          for (int c = 0; c < D; c++) fi[c] -= d.f_elem_hg[((long long)ln * D + c) * d.ep + e];
-        }
-      }
+        for (int c = 0; c < D; c++) fi[c] -= rowh[((long long)j * D + c) * 32];
     }
   }
   if (n >= d.nn) return;
@@ -362,8 +386,8 @@ __global__ void __launch_bounds__(TPB_N) k_node_update(WfDev d, WfPar P, int fus
   if (phase == 2) {
 #pragma unroll
     for (int c = 0; c < D; c++) fi[c] = d.fi[(long long)c * d.np + n];
-    mass = d.mdiag[n];
   }
+  const double mass = d.mdiag[n];
   // non-finite scrub (Solver_explicit.C:779-784)
 #pragma unroll
   for (int c = 0; c < D; c++)
@@ -407,7 +431,16 @@ __global__ void __launch_bounds__(TPB_N) k_node_update(WfDev d, WfPar P, int fus
     }
     d.v[i] = v[c];
   }
-  if (d.domtype == 2) atomicMin(d.xmin_key + (P.xmin_cur ^ 1), dbl_key(xr));
+  if (d.domtype == 2) { // one atomic per warp (the 2D node count would otherwise serialise on one address)
+    unsigned long long key = dbl_key(xr);
+    const unsigned mask = __activemask();
+    for (int o = 16; o > 0; o >>= 1) {
+      unsigned long long other = __shfl_down_sync(mask, key, o);
+      const int src = (threadIdx.x & 31) + o;
+      if (src < 32 && ((mask >> src) & 1u) && other < key) key = other;
+    }
+    if ((threadIdx.x & 31) == (__ffs(mask) - 1)) atomicMin(d.xmin_key + (P.xmin_cur ^ 1), key);
+  }
 }
 
 // nodal mass only (init, unfused CalcNodalVol + CalcNodalMassFromVol, lazy m_mdiag)
@@ -771,20 +804,30 @@ static void l_node_vol_finish(const WfDev &d, const WfPar &P, cudaStream_t s) {
   k_node_vol_finish<<<cdiv(d.nn, 256), 256, 0, s>>>(d, P);
 }
 static void l_elem_main(const WfDev &d, const WfPar &P, int et, int separate_hg, cudaStream_t s) {
+  if (!separate_hg && et == ET_HEX8 && !P.strict && P.variant[2] != 1) {
+    static bool configured = false;
+    if (!configured) {
+      cudaFuncSetAttribute(hexfast::k_elem_main_hex_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, hexfast::SMEM_BYTES);
+      cudaFuncSetAttribute(hexfast::k_elem_main_hex_fast, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+      configured = true;
+    }
+    hexfast::k_elem_main_hex_fast<<<cdiv(d.ne, hexfast::TPB), hexfast::TPB, hexfast::SMEM_BYTES, s>>>(d, P);
+    return;
+  }
   if (separate_hg) { ELEM_DISPATCH(et, k_elem_main<ET, true><<<cdiv(d.ne, TPB_E), TPB_E, 0, s>>>(d, P)); }
   else { ELEM_DISPATCH(et, k_elem_main<ET, false><<<cdiv(d.ne, TPB_E), TPB_E, 0, s>>>(d, P)); }
 }
-template <bool SEP>
+template <bool SEP, int U>
 static void node_update_t(const WfDev &d, const WfPar &P, int fuse, int phase, cudaStream_t s) {
   int g = cdiv((long long)d.nslices * 32, TPB_N);
-  if (d.k == 8) k_node_update<8, 3, SEP><<<g, TPB_N, 0, s>>>(d, P, fuse, phase);
-  else if (d.k == 4 && d.dim == 3) k_node_update<4, 3, SEP><<<g, TPB_N, 0, s>>>(d, P, fuse, phase);
-  else if (d.k == 4) k_node_update<4, 2, SEP><<<g, TPB_N, 0, s>>>(d, P, fuse, phase);
-  else k_node_update<3, 2, SEP><<<g, TPB_N, 0, s>>>(d, P, fuse, phase);
+  if (d.dim == 3) k_node_update<3, SEP, U><<<g, TPB_N, 0, s>>>(d, P, fuse, phase);
+  else k_node_update<2, SEP, U><<<g, TPB_N, 0, s>>>(d, P, fuse, phase);
 }
 static void l_node_update(const WfDev &d, const WfPar &P, int separate_hg, int fuse, int phase, cudaStream_t s) {
-  if (separate_hg) node_update_t<true>(d, P, fuse, phase, s);
-  else node_update_t<false>(d, P, fuse, phase, s);
+  if (separate_hg) node_update_t<true, 4>(d, P, fuse, phase, s);
+  else if (P.variant[3] == 1) node_update_t<false, 2>(d, P, fuse, phase, s);
+  else if (P.variant[3] == 2) node_update_t<false, 8>(d, P, fuse, phase, s);
+  else node_update_t<false, 4>(d, P, fuse, phase, s);
 }
 static void l_node_mass(const WfDev &d, const WfPar &P, int use_stored_voln, cudaStream_t s) {
   int g = cdiv((long long)d.nslices * 32, TPB_N);

@@ -166,6 +166,15 @@ class Domain_d:
         """n fused time steps (rows 1-22 of the loop body, Solver_explicit.C:524-978)."""
         self._ck(self._lib.wf_step(self._h, int(n)))
 
+    def step_timed(self, n=1):
+        """wf_step with per-kernel CUDA-event timing; returns ms for [predictor, E1, N1, E2, N2]."""
+        ms = (C.c_float * 5)()
+        self._ck(self._lib.wf_step_timed(self._h, int(n), ms))
+        return list(ms)
+
+    def set_variant(self, kernel: int, variant: int):
+        self._ck(self._lib.wf_set_variant(self._h, int(kernel), int(variant)))
+
     def SolveChungHulbert(self, end_t):
         """Run the explicit loop up to end_t with the fixed step set by SetDT (while Time < end_t)."""
         self.init()
