@@ -15,6 +15,7 @@ Prints ONE JSON line (rank 0).  See the module docstring of each section for wha
 from __future__ import annotations
 
 import argparse
+import dataclasses
 import json
 import os
 import subprocess
@@ -88,12 +89,14 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def linear_velocity(case, nn):
-    """Uniform-compression velocity field v_z(z) = top_vel * z / H on the AddBoxLength lattice."""
+def linear_velocity(case, nodes):
+    """Uniform-compression velocity field v_z(z) = top_vel * z / H on the AddBoxLength lattice, for the given
+    (global) node ids — or for nodes 0..n-1 when an int is passed."""
     d = case.dim
     n1 = [q + 1 for q in case.n]
-    v = np.zeros((nn, d))
-    layer = np.arange(nn) // (n1[0] * (n1[1] if d == 3 else 1))
+    ids = np.arange(nodes) if np.isscalar(nodes) else np.asarray(nodes)
+    v = np.zeros((ids.size, d))
+    layer = ids // (n1[0] * (n1[1] if d == 3 else 1))
     v[:, d - 1] = case.top_vel * layer / case.n[d - 1]
     return v.reshape(-1)
 
@@ -155,26 +158,51 @@ def reference_arm(args):
 # ---------------------------------------------------------------------------------------------------
 # our arm
 # ---------------------------------------------------------------------------------------------------
+# algorithmic bytes per element of each pass, [E1, N1, E2, N2]
+PASS_BYTES = {"hex": (64.0, 88.0, 456.0, 488.0), "tet": (28.0, 45.0, 297.0, 167.0), "quad": (40.0, 72.0, 320.0, 256.0)}
+
+
+def ncu_traffic(kind):
+    """DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture (profiles/)."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    try:
+        return json.load(open(p)).get(kind)
+    except Exception:
+        return None
+
+
 def ours(args):
     import torch
     import torch.distributed as dist
     from weldformfem_b200.domain import Domain_d
+    from weldformfem_b200.distributed import RankDomain
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    torch.cuda.set_device(local)
     stream = torch.cuda.Stream()
     kind = args.kind
     case = build_case(args.n, kind)
-    dom = Domain_d(device=local, strict=args.strict)
+    if world > 1:
+        # weak scaling: every rank owns one n^(d-1) x n slab of an n^(d-1) x (n * world) box
+        nn_ = list(case.n)
+        nn_[-1] *= world
+        case = dataclasses.replace(case, n=tuple(nn_), name=case.name + f"_x{world}")
+        dom = RankDomain(rank, world, device=local, strict=args.strict, halo=args.halo)
+    else:
+        dom = Domain_d(device=local, strict=args.strict)
     case.apply(dom, init=False)
     dom.set_stream(stream.cuda_stream)
+    if world > 1:
+        dom.connect()
+        dist.barrier()
     dom.init(case.timestep)
     nn, ne, _ = dom.counts()
-    dom.set("v", linear_velocity(case, nn))
+    node_ids = dom.node_l2g if world > 1 else np.arange(nn)
+    dom.set("v", linear_velocity(case, node_ids))
     # pre-load: evolve until plastic (untimed workload construction)
     t0 = time.time()
     if args.preload:
@@ -191,7 +219,14 @@ def ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    # warm-up
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- value: K fused steps, state resident in HBM, CUDA events on the launch stream ------------
     for _ in range(args.warmup):
         dom.step(1)
     barrier()
@@ -199,43 +234,42 @@ def ours(args):
     if rank == 0:
         sampler.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    with torch.cuda.stream(stream):
-        ev0.record(stream)
-        dom.step(args.steps)
-        ev1.record(stream)
+    ev0.record(stream)
+    dom.step(args.steps)
+    ev1.record(stream)
     barrier()
-    ms = ev0.elapsed_time(ev1)
+    ms = max_over_ranks(ev0.elapsed_time(ev1))
     clocks = sampler.stop() if rank == 0 else None
-    if world > 1:
-        t = torch.tensor([ms], device="cuda", dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
     flag = dom.nonfinite_flag()
+    if world > 1:
+        dom.halo_status()
 
-    # e2e: every step goes through the public C-ABI call with host buffers: the prescribed-velocity table
-    # is re-uploaded from pinned host memory (H2D) and the step monitor (kinetic energy + non-finite flag)
-    # is read back (D2H) inside the timed region.
-    e2e_steps = max(3, min(args.steps, 20))
+    # ---- per-kernel device times (CUDA events around every launch), single GPU ----------------------
+    kms = None
+    if world == 1:
+        dom.step_timed(3)
+        kms = [t / args.steps for t in dom.step_timed(args.steps)]
+
+    # ---- e2e: the call sequence a host solver loop makes through the C ABI with HOST buffers ----------
+    # every step: new prescribed-velocity values for the moving plane (H2D from host memory via
+    # wf_set_bc_values), one step, and the step monitor (kinetic energy + non-finite flag, D2H) read back.
+    e2e_steps = max(3, min(args.steps, 50))
     bcn, bcd, bcv = case.bc_arrays()
-    bc_host = torch.from_numpy(bcv.copy()).pin_memory()
-    bc_dev = torch.empty_like(bc_host, device="cuda")
+    d_last = case.dim - 1
+    vals_last = np.ascontiguousarray(bcv[bcd == d_last])
+    nrows = len(np.unique(bcn if world == 1 else np.intersect1d(bcn, node_ids)))
     barrier()
     t0 = time.perf_counter()
     ek = 0.0
     for _ in range(e2e_steps):
-        with torch.cuda.stream(stream):
-            bc_dev.copy_(bc_host, non_blocking=True)
+        dom.set_bc_values(d_last, vals_last)
         dom.step(1)
         ek, _ = dom.energies()
         if dom.nonfinite_flag():
             flag = True
     barrier()
-    e2e_s = time.perf_counter() - t0
-    if world > 1:
-        t = torch.tensor([e2e_s], device="cuda", dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_s = float(t.item())
-    total_elems = ne * world
+    e2e_s = max_over_ranks(time.perf_counter() - t0)
+    total_elems = ne * world if world == 1 else case.n_elems
     value = total_elems * args.steps / (ms * 1e-3)
     e2e_value = total_elems * e2e_steps / e2e_s
 
@@ -245,7 +279,24 @@ def ours(args):
         return
     peak, peak_src = measured_peak()
     alg = ALG_BYTES[kind]
-    achieved = alg * ne * args.steps / (ms * 1e-3) / 1e9
+    step_gbs = alg * total_elems / world * args.steps / (ms * 1e-3) / 1e9
+    roof = {"bound": "hbm", "achieved": None, "peak": peak, "unit": "GB/s", "frac": None, "traffic": None,
+            "peak_source": peak_src}
+    if kms is not None:
+        names = ["E1 element volume", "N1 nodal sums", "E2 main element pass", "N2 assembly+integration"]
+        pb = PASS_BYTES[kind]
+        dom_i = int(np.argmax(kms[1:5]))
+        ach = pb[dom_i] * ne / (kms[1 + dom_i] * 1e-3) / 1e9
+        tr = ncu_traffic(kind)
+        roof.update({"achieved": ach, "frac": ach / peak, "kernel": names[dom_i],
+                     "algorithmic_bytes_per_launch": pb[dom_i] * ne, "kernel_ms": kms[1 + dom_i],
+                     "traffic": (tr or {}).get("bytes_per_launch") if tr and tr.get("n_elems") == ne else None,
+                     "traffic_source": (tr or {}).get("source"),
+                     "passes": {nm: {"ms": kms[1 + i], "GB/s": pb[i] * ne / (kms[1 + i] * 1e-3) / 1e9,
+                                     "frac": pb[i] * ne / (kms[1 + i] * 1e-3) / 1e9 / peak}
+                                for i, nm in enumerate(names)}})
+    roof["whole_step"] = {"bytes_per_element_step": alg, "achieved": step_gbs, "frac": step_gbs / peak,
+                          "note": "per GPU; all four passes, CUDA events on the launch stream"}
     cpu = None
     if world == 1 and not args.no_cpu:
         try:
@@ -253,23 +304,24 @@ def ours(args):
             cpu = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
         except Exception as ex:  # the checker is optional for the bench line
             cpu = {"value": None, "unit": "element-steps/s", "cores": 0, "kind": "port", "sample": f"unavailable: {ex}"}
+    launches_per_step = 4 if world == 1 else 9
     line = {
         "metric": "element-steps/s", "value": value, "unit": "element-steps/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"configs[2]: synthetic structured {kind} box compression n={args.n} "
-                               f"({ne} elements, {nn} nodes per GPU), Hollomon J2, viscous hourglass {case.hexa_hg}",
+        "config": {"workload": f"configs[2]: synthetic structured {kind} box compression, {ne} elements / {nn} nodes per GPU "
+                               f"(global box {'x'.join(str(q) for q in case.n)}), Hollomon J2, viscous hourglass {case.hexa_hg}",
                    "numerics": "strict" if args.strict else "fast", "preload_steps": args.preload,
                    "plastic_fraction": plastic_frac, "hardening_fraction": harden_frac,
-                   "l2_policy": "working set (>4 GB per step) exceeds the 126 MB L2; no flush needed",
+                   "l2_policy": "inputs larger than L2: every step streams >4 GB per GPU through the 126 MB L2, no flush needed",
+                   "halo": (args.halo if world > 1 else None),
                    "nonfinite": bool(flag), "preload_seconds": preload_s, "kinetic_energy": ek},
-        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": None, "peak_source": peak_src, "bytes_per_element_step": alg,
-                     "kernels": "whole step (E1+N1+E2+N2), CUDA events on the launch stream"},
+        "roofline": roof,
         "cpu_baseline": cpu,
-        "e2e": {"value": e2e_value, "unit": "element-steps/s", "h2d_bytes_per_step": int(bc_host.numel() * 8),
-                "d2h_bytes_per_step": 20, "steps": e2e_steps},
-        "gpu_launches": 4 * args.steps + 1,
+        "e2e": {"value": e2e_value, "unit": "element-steps/s", "h2d_bytes_per_step": int(3 * nrows * 8),
+                "d2h_bytes_per_step": 68, "steps": e2e_steps,
+                "what": "per step: wf_set_bc_values (host -> device) + wf_step(1) + wf_energies / wf_nonfinite_flag (device -> host)"},
+        "gpu_launches": launches_per_step * args.steps,
         "clocks": clocks,
     }
     print(json.dumps(line))
@@ -289,6 +341,7 @@ def main():
     ap.add_argument("--preload", type=int, default=1200)
     ap.add_argument("--strict", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--halo", default="peer", choices=["peer", "nccl"])
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

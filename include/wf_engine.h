@@ -89,6 +89,9 @@ int wf_set_tracking(wf_engine *, int flags);
 int wf_add_bc_vel(wf_engine *, int node, int dim, double val); /* AddBCVelNode, Domain_d.C:1057 */
 int wf_add_bc_vel_array(wf_engine *, int count, const int *node, const int *dim, const double *val);
 int wf_allocate_bcs(wf_engine *);                              /* AllocateBCs, Domain_d.C:1063 */
+/* overwrite bcx_val / bcy_val / bcz_val (Domain_d.h:901) of one dimension, insertion order, from host memory;
+ * asynchronous on the engine's stream (time-dependent prescribed velocities) */
+int wf_set_bc_values(wf_engine *, int dim, int count, const double *vals);
 
 /* ---- solve --------------------------------------------------------------------------------------- */
 int wf_init(wf_engine *, double dt);  /* Solver_explicit.C:115-292 incl. SetDT; CH constants rho_b = 0.8182 */
@@ -149,16 +152,43 @@ const unsigned *wf_partition_local_elnod(const wf_partition *);    /* [(elem_end
 const int *wf_partition_neigh_ranks(const wf_partition *);         /* [n_neigh] ascending */
 const int *wf_partition_halo_offset(const wf_partition *);         /* [n_neigh+1] */
 const int *wf_partition_halo_nodes(const wf_partition *);          /* local node ids, grouped by neighbour */
-/* load the local part into an engine (replaces wf_set_mesh / wf_gen_box on that rank) */
+/* load the local part into an engine (replaces wf_set_mesh / wf_gen_box on that rank).  From here on the node
+ * ids given to wf_add_bc_vel are GLOBAL ids (nodes of other ranks are skipped) and wf_get_array / wf_set_array
+ * move LOCAL arrays (local node order = ascending global id, wf_halo_info -> node_l2g). */
 int wf_set_mesh_partition(wf_engine *, const wf_partition *, const double *x_local /*n_local*dim or NULL for box*/);
-/* split step: phases between which the caller exchanges halo partial sums (NCCL / peer memory).
- *   phase 0: [predictor] + element volumes + local nodal partial sums -> pack halo (1 double / shared node)
- *   phase 1: unpack+add remote partials (ascending rank order) + main element pass + local force partial
- *            sums -> pack halo (dim doubles / shared node)
- *   phase 2: unpack+add remote partials + integrate nodes */
+int wf_halo_info(wf_engine *, int *rank, int *nranks, int *n_neigh, const int **neigh_ranks, const int **halo_offset,
+                 const int **node_l2g);
+
+/* Halo exchange, default transport = peer memory over NVLink: every engine owns one "comm block"
+ * [flags | receive regions]; a neighbour's send kernel stores its partial nodal sums straight into the region
+ * reserved for it and then publishes the exchange's sequence number in its flag slot; the consumer side waits on
+ * the flags with a one-CTA kernel.  After the neighbours are connected, wf_init / wf_step of a partitioned engine
+ * enqueue the complete distributed step (E1, N1, send, wait, finish, E2, send, wait, N2) with no host involvement.
+ * Two exchanges per step: 2 doubles per shared node after N1 (sum of element volumes), dim doubles after E2
+ * (internal force), summed in ascending rank order on every sharer so all copies of a shared node stay bit-identical. */
+int wf_halo_comm_block(wf_engine *, void **dev_base, size_t *bytes);
+/* where neighbour index i of THIS engine must write: offsets inside this engine's comm block */
+int wf_halo_slot_offsets(wf_engine *, int neigh_idx, size_t *flag_byte_offset, size_t *region_byte_offset, size_t *region_bytes);
+/* one process per GPU: export the comm block (cudaIpcGetMemHandle, 64 bytes) / map a neighbour's block */
+int wf_halo_ipc_export(wf_engine *, void *handle64);
+int wf_halo_ipc_open(wf_engine *, const void *handle64, void **mapped_base);
+/* tell this engine where neighbour neigh_idx receives: the neighbour's comm block as mapped in this process and
+ * the offsets the NEIGHBOUR reports from wf_halo_slot_offsets(neighbour, index of this rank in its list) */
+int wf_halo_connect(wf_engine *, int neigh_idx, void *peer_comm_base, size_t peer_flag_offset, size_t peer_region_offset);
+int wf_halo_status(wf_engine *, int *error); /* non-zero error: a wait timed out (WF_HALO_TIMEOUT_S, default 30 s) */
+/* all ranks inside one process (one host thread drives every GPU; also how two ranks are tested on one GPU) */
+int wf_connect_all(wf_engine **ranks, int nranks);
+int wf_init_all(wf_engine **ranks, int nranks, double dt);
+int wf_step_all(wf_engine **ranks, int nranks, int nsteps);
+
+/* Alternative transport, host-driven (NCCL send/recv issued by the caller between phases): sends are packed into
+ * a local staging block; after each of phases 0 and 1 the caller moves, for every neighbour i, n_doubles from
+ * send_ptr to the neighbour's recv_ptr (wf_halo_exchange_ptrs on both sides describe the same exchange).
+ *   wf_init_phase 0 | exchange | 1 | exchange | 2        wf_step_phase 0 | exchange | 1 | exchange | 2 */
+int wf_halo_set_transport(wf_engine *, int host_driven);
+int wf_halo_exchange_ptrs(wf_engine *, int neigh_idx, void **send_ptr, void **recv_ptr, size_t *n_doubles);
+int wf_init_phase(wf_engine *, int phase, double dt);
 int wf_step_phase(wf_engine *, int phase, int last_step);
-int wf_halo_buffers(wf_engine *, void **send_dev, void **recv_dev, size_t *doubles_per_node_capacity);
-int wf_init_phase(wf_engine *, int phase, double dt); /* same split for wf_init (nodal vol_0 / mass sums) */
 
 /* ---- host-side helpers (no GPU needed; used by tests against the oracle) ------------------------- */
 int wf_host_box_counts(const double L[3], double r, int tritet, int *dim, int *nodxelem, int *n_nodes, int *n_elems);

@@ -1,0 +1,132 @@
+"""GPU tests of the partitioned (multi-GPU) step.  All ranks run inside this process through
+wf_step_all (LocalCluster); when the box has fewer GPUs than ranks, several ranks share cuda:0 —
+the halo exchange (stores into the neighbour's receive region + flag, one-CTA wait kernel) is the
+same code either way.  The partitioned result must agree with the one-GPU engine up to the association
+of the shared-node sums, and with the CPU oracle within the tolerances of BASELINE.json."""
+import dataclasses
+import os
+
+import numpy as np
+import pytest
+
+from parity_util import compare, relerr
+from weldformfem_b200 import cases
+
+pytestmark = pytest.mark.gpu
+R = dataclasses.replace
+
+os.environ.setdefault("WF_HALO_TIMEOUT_S", "10")
+
+NAMES = "x v u prev_a m_mdiag vol p pl_strain sigma_y m_sigma m_tau".split()
+
+CASES = {
+    "hex": R(cases.c3_hexes(8), n=(6, 5, 9), top_vel=-200.0),
+    "tet": R(cases.c2_tets(6), n=(4, 4, 7), top_vel=-200.0),
+    "tet_anp_nodal": R(cases.c2_tets(6, press=3), n=(4, 4, 7), top_vel=-200.0),
+    "psquad": R(cases.plane_strain_quads(12), n=(10, 9), top_vel=-50.0),
+    "pstri": R(cases.plane_strain_tris(12), n=(10, 9), top_vel=-50.0),
+}
+
+
+def devices_for(nranks):
+    import torch
+    n = torch.cuda.device_count()
+    return [p % n for p in range(nranks)]
+
+
+def run_cluster(case, nranks, nsteps, strict=False):
+    from weldformfem_b200.distributed import LocalCluster
+    cl = LocalCluster(nranks, devices_for(nranks), strict=strict)
+    case.apply(cl)
+    if nsteps:
+        cl.step(nsteps)
+    return cl
+
+
+def run_single(case, nsteps, strict=False):
+    from weldformfem_b200.domain import Domain_d
+    e = Domain_d(strict=strict)
+    case.apply(e)
+    if nsteps:
+        e.step(nsteps)
+    return e
+
+
+@pytest.mark.parametrize("key", sorted(CASES))
+@pytest.mark.parametrize("nranks", [2, 3])
+def test_partitioned_matches_single_gpu(key, nranks):
+    case = CASES[key]
+    cl = run_cluster(case, nranks, 40)
+    one = run_single(case, 40)
+    assert (one.get("pl_strain") > 0).mean() > 0.3
+    worst = {nm: relerr(cl.get(nm), one.get(nm)) for nm in NAMES}
+    assert max(worst.values()) < 1e-11, worst
+    # interior state is untouched by the partition: elements away from the cuts are bit-identical after 1 step
+    cl.close(); one.close()
+
+
+@pytest.mark.parametrize("key", ["hex", "tet"])
+@pytest.mark.parametrize("strict", [True, False], ids=["strict", "fast"])
+def test_partitioned_matches_oracle(key, strict, oracle_port):
+    case = CASES[key]
+    ref = oracle_port()
+    case.apply(ref)
+    cl = run_cluster(case, 2, 1, strict)
+    ref.step(1)
+    compare(cl, ref, NAMES + ["m_fi"], 1e-10, f"{key} partitioned, 1 step")
+    cl.step(99); ref.step(99)
+    compare(cl, ref, NAMES, 1e-7, f"{key} partitioned, 100 steps")
+    assert not cl.nonfinite_flag()
+    cl.close()
+
+
+def test_shared_node_copies_are_bit_identical():
+    """Every sharer sums the partials in ascending rank order, so all copies of a shared node carry the
+    same bits (assemble_global raises otherwise) — including nodes shared by more than two ranks."""
+    case = R(cases.c2_tets(6), n=(3, 3, 3), top_vel=-200.0)   # 162 tets over 4 ranks: ragged cuts, 3- and 4-way sharing
+    cl = run_cluster(case, 4, 25)
+    multi = np.zeros(cl.n_nodes, dtype=int)
+    for r in cl.ranks:
+        multi[r.node_l2g] += 1
+    assert multi.max() >= 3
+    for nm in ("x", "v", "u", "prev_a", "m_mdiag", "m_fi"):
+        cl.get(nm)
+    one = run_single(case, 25)
+    assert relerr(cl.get("x"), one.get("x")) < 1e-12
+    cl.close(); one.close()
+
+
+def test_partitioned_is_deterministic():
+    case = CASES["hex"]
+    a = run_cluster(case, 2, 30)
+    b = run_cluster(case, 2, 30)
+    for nm in ("x", "m_tau", "pl_strain"):
+        assert np.array_equal(a.get(nm), b.get(nm))
+    # the python restatement of the comm-block layout used by the gloo tests matches the library
+    from weldformfem_b200.distributed import slot_table
+    for r in a.ranks:
+        tab = slot_table(r.partition.neigh_ranks, r.partition.halo_offset)
+        assert tab == {q: r.slot_offsets(i)[:2] for i, q in enumerate(r.neigh)}
+    a.close(); b.close()
+
+
+def test_global_mesh_entry_point_matches_box(oracle_port):
+    """wf_partition_build on explicit connectivity == wf_partition_build_box."""
+    from weldformfem_b200.distributed import LocalCluster
+    case = CASES["hex"]
+    a = run_cluster(case, 2, 5)
+    o = oracle_port()
+    case.apply(o)
+    x0 = o.get("x") - o.get("u")
+    cl = LocalCluster(2, devices_for(2))
+    cl.set_mesh(3, 8, x0, o.get("m_elnod"))
+    cl.set_material(case.E, case.nu, case.rho0, case.model, case.sy0, case.K, case.m)
+    cl.set_stab(**case.stab)
+    cl.set_options(case.press, case.av[0], case.av[1], case.hexa_hg)
+    cl.add_bcs(*case.bc_arrays())
+    cl.allocate_bcs()
+    cl.init(case.timestep)
+    cl.step(5)
+    for nm in ("x", "m_tau"):
+        assert np.array_equal(cl.get(nm), a.get(nm))
+    a.close(); cl.close()

@@ -32,12 +32,14 @@ UNFUSED = ("UpdatePrediction calcElemJAndDerivatives Calc_Element_Radius CalcEle
 # every symbol include/wf_engine.h declares (checked by tests/test_abi.py)
 DECLARED = (["wf_create", "wf_destroy", "wf_last_error", "wf_set_stream", "wf_synchronize", "wf_set_mesh", "wf_gen_box",
              "wf_get_counts", "wf_set_axisymm_vol_weight", "wf_set_material", "wf_set_stab", "wf_set_options",
-             "wf_set_tracking", "wf_add_bc_vel", "wf_add_bc_vel_array", "wf_allocate_bcs", "wf_init", "wf_step",
+             "wf_set_tracking", "wf_add_bc_vel", "wf_add_bc_vel_array", "wf_allocate_bcs", "wf_set_bc_values", "wf_init", "wf_step",
              "wf_nonfinite_flag", "wf_energies", "wf_get_time", "wf_step_timed", "wf_set_variant", "wf_ImposeBCV", "wf_ImposeBCA", "wf_CalcStressStrain",
              "wf_get_array", "wf_set_array", "wf_array_bytes", "wf_device_ptr", "wf_partition_build",
              "wf_partition_build_box", "wf_partition_free", "wf_partition_info", "wf_partition_node_l2g",
              "wf_partition_local_elnod", "wf_partition_neigh_ranks", "wf_partition_halo_offset",
-             "wf_partition_halo_nodes", "wf_set_mesh_partition", "wf_step_phase", "wf_halo_buffers", "wf_init_phase",
+             "wf_partition_halo_nodes", "wf_set_mesh_partition", "wf_step_phase", "wf_init_phase", "wf_halo_info",
+             "wf_halo_comm_block", "wf_halo_slot_offsets", "wf_halo_ipc_export", "wf_halo_ipc_open", "wf_halo_connect",
+             "wf_halo_status", "wf_connect_all", "wf_init_all", "wf_step_all", "wf_halo_set_transport", "wf_halo_exchange_ptrs",
              "wf_host_box_counts", "wf_host_gen_box", "wf_host_nodel", "wf_version"]
             + ["wf_" + n for n in UNFUSED])
 
@@ -70,6 +72,7 @@ def load():
         "wf_add_bc_vel": (C.c_int, [vp, C.c_int, C.c_int, C.c_double]),
         "wf_add_bc_vel_array": (C.c_int, [vp, C.c_int, ip, ip, dp]),
         "wf_allocate_bcs": (C.c_int, [vp]),
+        "wf_set_bc_values": (C.c_int, [vp, C.c_int, C.c_int, dp]),
         "wf_init": (C.c_int, [vp, C.c_double]),
         "wf_init_phase": (C.c_int, [vp, C.c_int, C.c_double]),
         "wf_step": (C.c_int, [vp, C.c_int]),
@@ -86,7 +89,18 @@ def load():
         "wf_set_array": (C.c_int, [vp, C.c_char_p, vp, C.c_size_t]),
         "wf_array_bytes": (C.c_size_t, [vp, C.c_char_p]),
         "wf_device_ptr": (vp, [vp, C.c_char_p, C.POINTER(C.c_size_t)]),
-        "wf_halo_buffers": (C.c_int, [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(C.c_size_t)]),
+        "wf_halo_info": (C.c_int, [vp, ip, ip, ip, C.POINTER(ip), C.POINTER(ip), C.POINTER(ip)]),
+        "wf_halo_comm_block": (C.c_int, [vp, C.POINTER(vp), C.POINTER(C.c_size_t)]),
+        "wf_halo_slot_offsets": (C.c_int, [vp, C.c_int, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]),
+        "wf_halo_ipc_export": (C.c_int, [vp, vp]),
+        "wf_halo_ipc_open": (C.c_int, [vp, vp, C.POINTER(vp)]),
+        "wf_halo_connect": (C.c_int, [vp, C.c_int, vp, C.c_size_t, C.c_size_t]),
+        "wf_halo_status": (C.c_int, [vp, ip]),
+        "wf_connect_all": (C.c_int, [C.POINTER(vp), C.c_int]),
+        "wf_init_all": (C.c_int, [C.POINTER(vp), C.c_int, C.c_double]),
+        "wf_step_all": (C.c_int, [C.POINTER(vp), C.c_int, C.c_int]),
+        "wf_halo_set_transport": (C.c_int, [vp, C.c_int]),
+        "wf_halo_exchange_ptrs": (C.c_int, [vp, C.c_int, C.POINTER(vp), C.POINTER(vp), C.POINTER(C.c_size_t)]),
         "wf_partition_build": (C.c_int, [C.POINTER(vp), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, up]),
         "wf_partition_build_box": (C.c_int, [C.POINTER(vp), C.c_int, C.c_int, dp, dp, C.c_double, C.c_int]),
         "wf_partition_free": (None, [vp]),

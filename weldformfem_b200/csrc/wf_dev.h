@@ -16,6 +16,14 @@
 #include <stdint.h>
 
 #define WF_MAXK 8
+#define WF_HALO_NC 3 /* doubles per shared node and exchange (max: dim force components / init triple) */
+
+struct WfHaloNb {
+  int offset, count;            /* slice of halo_nodes */
+  double *dst;                  /* receive region for this rank in the neighbour's memory (peer pointer), or the local staging region */
+  unsigned long long *flag;     /* this rank's flag slot in the neighbour's memory */
+  unsigned *counter;            /* local block-completion counter */
+};
 
 struct WfDev {
   int nn, ne, nslices;
@@ -35,9 +43,20 @@ struct WfDev {
   const double *bc_vals;             /* [nbc*3] */
   const long long *sell_ptr;         /* [nslices+1] */
   const int *sell_slots;
-  /* halo (multi-GPU): nodes whose partial sums are exchanged */
-  const int *halo_nodes; int n_halo;
-  double *halo_send, *halo_recv;
+  /* halo (multi-GPU, NULL / 0 on a single GPU): shared nodes whose partial nodal sums are exchanged.
+   * Send side: halo_nodes grouped by neighbour, described by nb[]; every neighbour owns one receive
+   * region [parity][WF_HALO_NC][count] in the peer's memory, written with plain stores over NVLink.
+   * Receive side: one record per UNIQUE shared node, listing its sharers in ascending rank order. */
+  const int *halo_nodes;             /* [n_halo] local node ids, grouped by neighbour */
+  const struct WfHaloNb *nb;         /* [n_neigh] */
+  const int *halo_slot;              /* [np] index into hu_* or -1 */
+  const int *hu_node;                /* [n_uniq] local node id */
+  const int *hu_ptr;                 /* [n_uniq+1] */
+  const int2 *hu_ent;                /* .x = index of (parity 0, comp 0) in recv, or -1 = this rank's own partial; .y = count of that neighbour */
+  const double *recv;                /* receive regions of this rank */
+  unsigned long long *flags;         /* [n_neigh] sequence number of the last exchange completed by that neighbour */
+  int *comm_error;                   /* [1] set when a wait timed out */
+  int n_halo, n_uniq, n_neigh;
 
   /* elements */
   const int *elnod;                  /* [k][ep] */
@@ -80,5 +99,6 @@ struct WfPar {
   double dt, alpha, beta, gamma;
   double w; /* Gauss weight, Mechanical.C:269-282 */
   int xmin_cur; /* which xmin_key slot holds min x_r of the current coordinates */
+  int halo_parity; /* multi-GPU: which half of the receive regions the current exchange uses */
   int variant[4]; /* tuning: kernel variant for E1, N1, E2, N2 (0 = default) */
 };

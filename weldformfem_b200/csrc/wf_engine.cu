@@ -6,6 +6,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <string>
@@ -47,12 +48,25 @@ struct wf_engine {
   std::vector<int> bc_nod[3];
   std::vector<double> bc_val[3];
   int nbc_rows = 0;
-  // partition / halo (multi-GPU)
-  std::vector<int> halo_nodes_h, halo_offset_h, neigh_h;
-  int *halo_nodes_d = nullptr;
-  double *halo_send = nullptr, *halo_recv = nullptr;
-  size_t halo_cap = 0;
-  bool distributed = false;
+  std::vector<int> bc_slot[3];             // index into bc_vals of BC i of each dimension (-1: node of another rank)
+  double *bc_stage[2] = {nullptr, nullptr}; // pinned staging of bc_vals for wf_set_bc_values
+  cudaEvent_t bc_ev[2] = {nullptr, nullptr};
+  int bc_stage_cur = 0;
+  double *bc_vals_d = nullptr;
+  // partition / halo (multi-GPU); see wf_set_mesh_partition
+  bool distributed = false, own_stream = false;
+  int rank = 0, nranks = 1;
+  int transport = 0;                       // 0 = stores into the neighbour's memory, 1 = host-driven (NCCL) via the staging block
+  std::vector<int> l2g, neigh, halo_offset, halo_nodes_h;
+  std::vector<WfHaloNb> nb_h;
+  WfHaloNb *nb_d = nullptr;
+  unsigned *counters_d = nullptr;
+  char *comm = nullptr, *staging = nullptr; // [flags | receive regions]
+  size_t comm_bytes = 0, flag_bytes = 0;
+  int max_halo_count = 0, n_connected = 0;
+  unsigned long long seq = 0, timeout_ns = 30000000000ull;
+  std::vector<void *> ipc_opened;
+  int init_stage = 0, step_stage = 0;
 };
 
 #define CK(call)                                                                          \
@@ -130,11 +144,23 @@ extern "C" void wf_destroy(wf_engine *E) {
   if (!E) return;
   cudaSetDevice(E->device);
   cudaStreamSynchronize(E->stream);
+  for (int b = 0; b < 2; b++) {
+    if (E->bc_stage[b]) cudaFreeHost(E->bc_stage[b]);
+    if (E->bc_ev[b]) cudaEventDestroy(E->bc_ev[b]);
+  }
+  for (void *p : E->ipc_opened) cudaIpcCloseMemHandle(p);
   for (void *p : E->allocs) cudaFree(p);
+  if (E->own_stream) cudaStreamDestroy(E->stream);
   delete E;
 }
 
-extern "C" int wf_set_stream(wf_engine *E, void *s) { E->stream = (cudaStream_t)s; return 0; }
+extern "C" int wf_set_stream(wf_engine *E, void *s) {
+  CK(cudaSetDevice(E->device));
+  CK(cudaStreamSynchronize(E->stream));
+  if (E->own_stream) { cudaStreamDestroy(E->stream); E->own_stream = false; }
+  E->stream = (cudaStream_t)s;
+  return 0;
+}
 extern "C" int wf_synchronize(wf_engine *E) { CK(cudaSetDevice(E->device)); CK(cudaStreamSynchronize(E->stream)); return 0; }
 
 extern "C" int wf_set_axisymm_vol_weight(wf_engine *E, int on) {
@@ -353,6 +379,12 @@ extern "C" int wf_allocate_bcs(wf_engine *E) {
   for (int dd = 0; dd < E->dim; dd++)
     for (size_t i = 0; i < E->bc_nod[dd].size(); i++) {
       int n = E->bc_nod[dd][i];
+      if (i == 0) E->bc_slot[dd].assign(E->bc_nod[dd].size(), -1);
+      if (E->distributed) { // ids are GLOBAL node ids; nodes of other ranks are skipped
+        auto it = std::lower_bound(E->l2g.begin(), E->l2g.end(), n);
+        if (it == E->l2g.end() || *it != n) continue;
+        n = (int)(it - E->l2g.begin());
+      }
       NEED(n >= 0 && n < E->nn, "BC node out of range");
       auto it = row_of.find(n);
       int row;
@@ -364,6 +396,7 @@ extern "C" int wf_allocate_bcs(wf_engine *E) {
       } else row = it->second;
       mask[row] |= (unsigned char)(1u << dd);
       vals[3 * (size_t)row + dd] = E->bc_val[dd][i];
+      E->bc_slot[dd][i] = 3 * row + dd;
     }
   std::vector<int> bci(E->d.np, -1);
   for (auto &kv : row_of) bci[kv.first] = kv.second;
@@ -376,8 +409,40 @@ extern "C" int wf_allocate_bcs(wf_engine *E) {
   CK(cudaMemcpyAsync(E->d.bc_index, bci.data(), bci.size() * sizeof(int), cudaMemcpyHostToDevice, E->stream));
   CK(cudaStreamSynchronize(E->stream));
   E->d.bc_mask = dm; E->d.bc_vals = dv;
+  E->bc_vals_d = dv;
   E->nbc_rows = (int)mask.size();
+  for (int b = 0; b < 2; b++) {
+    if (E->bc_stage[b]) { cudaFreeHost(E->bc_stage[b]); E->bc_stage[b] = nullptr; }
+    if (!vals.empty()) {
+      CK(cudaMallocHost((void **)&E->bc_stage[b], vals.size() * sizeof(double)));
+      memcpy(E->bc_stage[b], vals.data(), vals.size() * sizeof(double));
+    }
+    if (!E->bc_ev[b]) CK(cudaEventCreateWithFlags(&E->bc_ev[b], cudaEventDisableTiming));
+  }
   E->bcs_ready = true;
+  return 0;
+}
+
+// New prescribed values for the BCs of one dimension, in insertion order — the engine-side equivalent of writing
+// into Domain_d::bcx_val / bcy_val / bcz_val (Domain_d.h:901) between steps (time-dependent velocity BCs).
+// Host values are staged in pinned memory and uploaded asynchronously on the engine's stream.
+extern "C" int wf_set_bc_values(wf_engine *E, int dim, int count, const double *vals) {
+  NEED(E->bcs_ready, "wf_set_bc_values needs wf_allocate_bcs");
+  NEED(dim >= 0 && dim < E->dim, "bad BC dim");
+  NEED(count == (int)E->bc_slot[dim].size() || (count == 0 && E->bc_slot[dim].empty()), "count must equal the number of BCs of this dimension");
+  if (E->nbc_rows == 0 || count == 0) return 0;
+  CK(cudaSetDevice(E->device));
+  const int b = E->bc_stage_cur;
+  CK(cudaEventSynchronize(E->bc_ev[b])); // the copy that last used this staging buffer has finished
+  double *st = E->bc_stage[b];
+  if (st != E->bc_stage[b ^ 1]) memcpy(st, E->bc_stage[b ^ 1], (size_t)3 * E->nbc_rows * sizeof(double));
+  const std::vector<int> &slot = E->bc_slot[dim];
+  for (int i = 0; i < count; i++)
+    if (slot[i] >= 0) st[slot[i]] = vals[i];
+  for (int i = 0; i < count; i++) E->bc_val[dim][i] = vals[i];
+  CK(cudaMemcpyAsync(E->bc_vals_d, st, (size_t)3 * E->nbc_rows * sizeof(double), cudaMemcpyHostToDevice, E->stream));
+  CK(cudaEventRecord(E->bc_ev[b], E->stream));
+  E->bc_stage_cur ^= 1;
   return 0;
 }
 
@@ -418,25 +483,31 @@ static int reset_xmin(wf_engine *E, int slot) {
   return 0;
 }
 
-extern "C" int wf_init_phase(wf_engine *E, int phase, double dt) {
-  NEED(E->meshed && E->material_set, "wf_init needs mesh and material");
-  if (!E->bcs_ready && wf_allocate_bcs(E)) return 1;
-  CK(cudaSetDevice(E->device));
+// ---- stages ---------------------------------------------------------------------------------------
+// Both wf_init and wf_step are sequences of stages; between some of them a distributed engine exchanges
+// partial nodal sums with its neighbours (halo_exchange).  With the peer-memory transport the exchange is
+// part of the stream (stores into the neighbour's receive region + flag, then a one-CTA wait kernel), so
+// wf_init / wf_step enqueue everything without touching the host; with the host-driven transport the
+// caller moves the staging regions (NCCL send/recv) between wf_init_phase / wf_step_phase calls.
+static void halo_send(wf_engine *E, int mode) {
+  E->seq++;
+  E->P.halo_parity = (int)(E->seq & 1ull);
+  E->L->halo_send(E->d, E->P, mode, E->strict ? 1 : 0, E->seq, E->max_halo_count, E->stream);
+}
+static void halo_wait(wf_engine *E) {
+  if (E->transport == 0) E->L->halo_wait(E->d, E->seq, E->timeout_ns, E->stream);
+}
+
+static int init_stage(wf_engine *E, int stage, double dt) {
   WfDev &d = E->d;
   WfPar &P = E->P;
   const size_t nv = (size_t)E->dim * d.np;
-  if (phase == 0) {
+  if (stage == 0) {
     P.dt = dt;
     const double rho_b = 0.818200; // Solver_explicit.C:193-197
     P.alpha = (2.0 * rho_b - 1.0) / (1.0 + rho_b);
     P.beta = (5.0 - 3.0 * rho_b) / ((1.0 + rho_b) * (1.0 + rho_b) * (2.0 - rho_b));
     P.gamma = 1.5 - P.alpha;
-    P.track_eps = (E->tracking & 1) ? 1 : 0;
-    P.store_sigma = ((E->tracking & 2) || P.av_alpha != 0.0 || P.av_beta != 0.0) ? 1 : 0;
-    const size_t e6 = (size_t)6 * d.ep;
-    if (P.track_eps && !d.eps && dalloc(E, &d.eps, e6)) return 1;
-    if (P.store_sigma && !d.sigma && dalloc(E, &d.sigma, e6)) return 1;
-    if (E->strict && !d.fsell_hg && dalloc(E, &d.fsell_hg, (size_t)E->dim * E->sell_total)) return 1;
     E->L->init_elem(d, P, E->stream); // InitValues
     // Solver_explicit.C:176-190: v, a, u are zeroed inside the per-dimension loop, so only the LAST
     // dimension's prescribed velocities survive initialisation
@@ -446,52 +517,126 @@ extern "C" int wf_init_phase(wf_engine *E, int phase, double dt) {
     E->L->impose_bc(d, E->dim - 1, 0, d.v, E->stream);
     E->L->elem_vol(d, P, E->et, 0, E->stream);      // calcElemJAndDerivatives + CalcElemInitialVol/CalcElemVol
     E->L->vol0_density(d, E->stream);               // vol_0 = vol ; calcElemDensity
-    E->L->node_vol(d, P, 0, E->distributed ? 1 : 0, E->stream); // sum vol_0 per node
-    if (check_launch(E, "wf_init phase 0")) return 1;
-    if (E->distributed) return 0;
-    phase = 1;
-  }
-  if (phase == 1) {
-    E->L->node_vol(d, P, 1, 0, E->stream);          // CalcNodalVol
+    E->L->node_vol(d, P, 0, E->stream);             // sum vol_0 / mean rho per node
+    if (E->distributed) halo_send(E, 0);
+  } else if (stage == 1) {
+    if (E->distributed) E->L->halo_finish(d, P, 0, P.halo_parity, E->stream);
+    E->L->node_vol(d, P, 1, E->stream);             // CalcNodalVol
+    if (E->distributed) halo_send(E, 1);
+  } else {
+    if (E->distributed) E->L->halo_finish(d, P, 1, P.halo_parity, E->stream);
     if (E->domtype == WF_AXISYMM) {
       P.xmin_cur = 0;
       if (reset_xmin(E, 0)) return 1;
       E->L->xmin(d, 0, E->stream);
     }
-    if (check_launch(E, "wf_init phase 1")) return 1;
     E->time = 0.0; E->step_count = 0; E->predicted = false;
     E->a_in_dbg = E->fi_in_dbg = E->sigma_in_dbg = E->rates_in_dbg = E->felem_in_dbg = false;
     E->inited = true;
   }
-  return 0;
+  return check_launch(E, "wf_init");
+}
+
+static int init_prologue(wf_engine *E) {
+  NEED(E->meshed && E->material_set, "wf_init needs mesh and material");
+  if (!E->bcs_ready && wf_allocate_bcs(E)) return 1;
+  CK(cudaSetDevice(E->device));
+  { // allocations and kernel loading happen here, before any halo wait can be in flight
+    WfDev &d = E->d;
+    WfPar &P = E->P;
+    P.track_eps = (E->tracking & 1) ? 1 : 0;
+    P.store_sigma = ((E->tracking & 2) || P.av_alpha != 0.0 || P.av_beta != 0.0) ? 1 : 0;
+    const size_t e6 = (size_t)6 * d.ep;
+    if (P.track_eps && !d.eps && dalloc(E, &d.eps, e6)) return 1;
+    if (P.store_sigma && !d.sigma && dalloc(E, &d.sigma, e6)) return 1;
+    if (E->strict && !d.fsell_hg && dalloc(E, &d.fsell_hg, (size_t)E->dim * E->sell_total)) return 1;
+  }
+  E->L->preload(E->et, E->dim, E->k);
+  CK(cudaStreamSynchronize(E->stream));
+  return check_launch(E, "kernel preload");
 }
 
 extern "C" int wf_init(wf_engine *E, double dt) {
-  NEED(!E->distributed, "distributed engines are initialised with wf_init_phase");
-  return wf_init_phase(E, 0, dt);
+  if (init_prologue(E)) return 1;
+  if (E->distributed) {
+    NEED(E->transport == 0, "host-driven halo transport: initialise with wf_init_phase");
+    NEED(E->n_connected == (int)E->neigh.size(), "wf_init: connect every neighbour first (wf_halo_connect / wf_connect_all)");
+  }
+  for (int st = 0; st < 3; st++) {
+    if (init_stage(E, st, dt)) return 1;
+    if (E->distributed && st < 2) halo_wait(E);
+  }
+  return 0;
 }
 
-extern "C" int wf_step(wf_engine *E, int nsteps) {
-  NEED(E->inited, "wf_step before wf_init");
-  NEED(!E->distributed, "distributed engines step with wf_step_phase");
+extern "C" int wf_init_phase(wf_engine *E, int phase, double dt) {
+  NEED(phase >= 0 && phase < 3, "init phase must be 0, 1 or 2");
+  NEED(phase == E->init_stage, "init phases must be called in order 0, 1, 2");
+  if (phase == 0 && init_prologue(E)) return 1;
   CK(cudaSetDevice(E->device));
+  if (init_stage(E, phase, dt)) return 1;
+  E->init_stage = (phase + 1) % 3;
+  return 0;
+}
+
+// one explicit step = stages 0..2 (Solver_explicit.C:524-978, rows 1-22)
+static int step_stage(wf_engine *E, int stage, bool last) {
   WfDev &d = E->d;
   WfPar &P = E->P;
   const int sep = E->strict ? 1 : 0;
-  for (int s = 0; s < nsteps; s++) {
-    const bool last = (s == nsteps - 1);
+  if (stage == 0) {
     if (!E->predicted) E->L->predict(d, P, 1, E->stream);
     E->L->elem_vol(d, P, E->et, 0, E->stream);
-    E->L->node_vol(d, P, 1, 0, E->stream);
+    E->L->node_vol(d, P, 1, E->stream);
+    if (E->distributed) halo_send(E, 1);
+  } else if (stage == 1) {
+    if (E->distributed) E->L->halo_finish(d, P, 1, P.halo_parity, E->stream);
     E->L->elem_main(d, P, E->et, sep, E->stream);
+    if (E->distributed) halo_send(E, 2);
+  } else {
     E->L->node_update(d, P, sep, last ? 0 : 1, 0, E->stream);
     E->predicted = !last;
     P.xmin_cur ^= 1;
     E->time += P.dt;
     E->step_count++;
   }
+  return 0;
+}
+
+static int step_once(wf_engine *E, bool last) {
+  for (int st = 0; st < 3; st++) {
+    if (step_stage(E, st, last)) return 1;
+    if (E->distributed && st < 2) halo_wait(E);
+  }
+  return 0;
+}
+
+static int step_prologue(wf_engine *E) {
+  NEED(E->inited, "wf_step before wf_init");
+  if (E->distributed) NEED(E->transport == 0, "host-driven halo transport: step with wf_step_phase");
+  CK(cudaSetDevice(E->device));
+  return 0;
+}
+static int step_epilogue(wf_engine *E, const char *what) {
   E->a_in_dbg = E->fi_in_dbg = E->sigma_in_dbg = E->rates_in_dbg = E->felem_in_dbg = false;
-  return check_launch(E, "wf_step");
+  return check_launch(E, what);
+}
+
+extern "C" int wf_step(wf_engine *E, int nsteps) {
+  if (step_prologue(E)) return 1;
+  for (int s = 0; s < nsteps; s++)
+    if (step_once(E, s == nsteps - 1)) return 1;
+  return step_epilogue(E, "wf_step");
+}
+
+extern "C" int wf_step_phase(wf_engine *E, int phase, int last_step) {
+  NEED(E->inited, "wf_step_phase before wf_init");
+  NEED(phase >= 0 && phase < 3, "step phase must be 0, 1 or 2");
+  NEED(phase == E->step_stage, "step phases must be called in order 0, 1, 2");
+  CK(cudaSetDevice(E->device));
+  if (step_stage(E, phase, last_step != 0)) return 1;
+  E->step_stage = (phase + 1) % 3;
+  return step_epilogue(E, "wf_step_phase");
 }
 
 // tuning / profiling hooks -----------------------------------------------------------------------------
@@ -501,12 +646,11 @@ extern "C" int wf_set_variant(wf_engine *E, int kernel, int variant) {
   return 0;
 }
 
-// same as wf_step, with CUDA events around every launch; ms[0..4] += time of predictor, E1, N1, E2, N2
+// same as wf_step on one GPU, with CUDA events around every launch; ms[0..4] += time of predictor, E1, N1, E2, N2
 extern "C" int wf_step_timed(wf_engine *E, int nsteps, float *ms) {
-  NEED(E->inited, "wf_step before wf_init");
-  NEED(!E->distributed, "distributed engines step with wf_step_phase");
+  if (step_prologue(E)) return 1;
+  NEED(!E->distributed, "wf_step_timed is a single-GPU profiling hook");
   NEED(ms, "null output");
-  CK(cudaSetDevice(E->device));
   WfDev &d = E->d;
   WfPar &P = E->P;
   const int sep = E->strict ? 1 : 0;
@@ -524,7 +668,7 @@ extern "C" int wf_step_timed(wf_engine *E, int nsteps, float *ms) {
     const bool last = (s == nsteps - 1);
     if (!E->predicted) { E->L->predict(d, P, 1, E->stream); mark(0); }
     E->L->elem_vol(d, P, E->et, 0, E->stream); mark(1);
-    E->L->node_vol(d, P, 1, 0, E->stream); mark(2);
+    E->L->node_vol(d, P, 1, E->stream); mark(2);
     E->L->elem_main(d, P, E->et, sep, E->stream); mark(3);
     E->L->node_update(d, P, sep, last ? 0 : 1, 0, E->stream); mark(4);
     E->predicted = !last;
@@ -539,23 +683,267 @@ extern "C" int wf_step_timed(wf_engine *E, int nsteps, float *ms) {
     ms[tag[i]] += t;
   }
   for (auto x : ev) cudaEventDestroy(x);
-  E->a_in_dbg = E->fi_in_dbg = E->sigma_in_dbg = E->rates_in_dbg = E->felem_in_dbg = false;
-  return check_launch(E, "wf_step_timed");
+  return step_epilogue(E, "wf_step_timed");
 }
 
-extern "C" int wf_step_phase(wf_engine *E, int phase, int last_step) {
-  (void)E; (void)phase; (void)last_step;
-  FAIL("wf_step_phase: distributed stepping is not wired yet");
-}
-extern "C" int wf_halo_buffers(wf_engine *E, void **s, void **r, size_t *cap) {
-  if (s) *s = E->halo_send;
-  if (r) *r = E->halo_recv;
-  if (cap) *cap = E->halo_cap;
+// ---------------------------------------------------------------------------------------------------
+// multi-GPU: local part of a partitioned mesh + halo plumbing
+// ---------------------------------------------------------------------------------------------------
+extern "C" int wf_set_mesh_partition(wf_engine *E, const wf_partition *p, const double *x_local) {
+  NEED(p, "null partition");
+  NEED(wf_partition_k(p) == E->k, "partition nodxelem does not match the engine");
+  NEED(E->domtype != WF_AXISYMM, "axisymmetric domains are not partitioned (the axis constraint needs a global min over x_r)");
+  int eb = 0, ee = 0, nl = 0, nng = 0;
+  wf_partition_info(p, &eb, &ee, &nl, &nng);
+  NEED(ee > eb && nl > 0, "this rank owns no elements");
+  std::vector<double> xb;
+  if (!x_local) {
+    NEED(wf_partition_is_box(p), "x_local is required unless the partition was built by wf_partition_build_box");
+    NEED(wf_partition_box_dim(p) == E->dim, "box dimension does not match the engine");
+    wf_partition_box_coords(p, xb);
+    x_local = xb.data();
+  }
+  CK(cudaSetDevice(E->device));
+  if (E->stream == 0) { // engines of one process must not serialise on the legacy default stream
+    CK(cudaStreamCreateWithFlags(&E->stream, cudaStreamNonBlocking));
+    E->own_stream = true;
+  }
+  if (upload_mesh(E, nl, ee - eb, x_local, wf_partition_local_elnod(p))) return 1;
+  WfDev &d = E->d;
+  E->distributed = true;
+  wf_partition_ranks(p, &E->rank, &E->nranks);
+  E->l2g.assign(wf_partition_node_l2g(p), wf_partition_node_l2g(p) + nl);
+  E->neigh.assign(wf_partition_neigh_ranks(p), wf_partition_neigh_ranks(p) + nng);
+  E->halo_offset.assign(wf_partition_halo_offset(p), wf_partition_halo_offset(p) + nng + 1);
+  const int nh = E->halo_offset[nng];
+  E->halo_nodes_h.assign(wf_partition_halo_nodes(p), wf_partition_halo_nodes(p) + nh);
+  if (const char *t = getenv("WF_HALO_TIMEOUT_S")) {
+    double sec = atof(t);
+    if (sec > 0.0) E->timeout_ns = (unsigned long long)(sec * 1e9);
+  }
+  // unique shared nodes, each with its sharers in ascending rank order (this rank included)
+  std::vector<int> uniq(E->halo_nodes_h);
+  std::sort(uniq.begin(), uniq.end());
+  uniq.erase(std::unique(uniq.begin(), uniq.end()), uniq.end());
+  const int nu = (int)uniq.size();
+  std::vector<int> slot(d.np, -1), ptr(nu + 1, 0);
+  for (int u = 0; u < nu; u++) slot[uniq[u]] = u;
+  struct Sharer { int rank; int2 e; };
+  std::vector<std::vector<Sharer>> ent(nu);
+  for (int u = 0; u < nu; u++) ent[u].push_back({E->rank, make_int2(-1, 0)});
+  E->max_halo_count = 0;
+  for (int i = 0; i < nng; i++) {
+    const int off = E->halo_offset[i], cnt = E->halo_offset[i + 1] - off;
+    E->max_halo_count = std::max(E->max_halo_count, cnt);
+    for (int j = 0; j < cnt; j++)
+      ent[slot[E->halo_nodes_h[off + j]]].push_back({E->neigh[i], make_int2(2 * WF_HALO_NC * off + j, cnt)});
+  }
+  std::vector<int2> flat;
+  for (int u = 0; u < nu; u++) {
+    std::sort(ent[u].begin(), ent[u].end(), [](const Sharer &a, const Sharer &b) { return a.rank < b.rank; });
+    ptr[u] = (int)flat.size();
+    for (auto &q : ent[u]) flat.push_back(q.e);
+  }
+  ptr[nu] = (int)flat.size();
+  // device copies
+  int *d_halo = nullptr, *d_slot = nullptr, *d_unode = nullptr, *d_ptr = nullptr;
+  int2 *d_ent = nullptr;
+  if (dalloc(E, &d_halo, (size_t)nh) || dalloc(E, &d_slot, (size_t)d.np) || dalloc(E, &d_unode, (size_t)nu) ||
+      dalloc(E, &d_ptr, (size_t)nu + 1) || dalloc(E, &d_ent, flat.size()) || dalloc(E, &E->counters_d, (size_t)nng) ||
+      dalloc(E, &E->nb_d, (size_t)nng) || dalloc(E, &d.comm_error, 1))
+    return 1;
+  E->flag_bytes = (size_t)round_up(8LL * std::max(nng, 1), 256);
+  E->comm_bytes = E->flag_bytes + sizeof(double) * 2 * WF_HALO_NC * (size_t)nh;
+  if (dalloc(E, &E->comm, E->comm_bytes)) return 1;
+  auto up = [&](void *dst, const void *src, size_t bytes) {
+    return bytes == 0 ? cudaSuccess : cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, E->stream);
+  };
+  CK(up(d_halo, E->halo_nodes_h.data(), sizeof(int) * nh));
+  CK(up(d_slot, slot.data(), sizeof(int) * d.np));
+  CK(up(d_unode, uniq.data(), sizeof(int) * nu));
+  CK(up(d_ptr, ptr.data(), sizeof(int) * (nu + 1)));
+  CK(up(d_ent, flat.data(), sizeof(int2) * flat.size()));
+  CK(cudaStreamSynchronize(E->stream));
+  d.halo_nodes = d_halo; d.halo_slot = d_slot; d.hu_node = d_unode; d.hu_ptr = d_ptr; d.hu_ent = d_ent;
+  d.n_halo = nh; d.n_uniq = nu; d.n_neigh = nng;
+  d.flags = (unsigned long long *)E->comm;
+  d.recv = (const double *)(E->comm + E->flag_bytes);
+  d.nb = E->nb_d;
+  E->nb_h.assign(nng, WfHaloNb());
+  for (int i = 0; i < nng; i++) {
+    E->nb_h[i].offset = E->halo_offset[i];
+    E->nb_h[i].count = E->halo_offset[i + 1] - E->halo_offset[i];
+    E->nb_h[i].dst = nullptr; E->nb_h[i].flag = nullptr;
+    E->nb_h[i].counter = E->counters_d + i;
+  }
+  E->n_connected = 0;
   return 0;
 }
-extern "C" int wf_set_mesh_partition(wf_engine *E, const wf_partition *p, const double *x_local) {
-  (void)p; (void)x_local;
-  FAIL("wf_set_mesh_partition: not wired yet");
+
+extern "C" int wf_halo_info(wf_engine *E, int *rank, int *nranks, int *n_neigh, const int **neigh_ranks, const int **halo_offset,
+                            const int **node_l2g) {
+  NEED(E->distributed, "not a partitioned engine");
+  if (rank) *rank = E->rank;
+  if (nranks) *nranks = E->nranks;
+  if (n_neigh) *n_neigh = (int)E->neigh.size();
+  if (neigh_ranks) *neigh_ranks = E->neigh.data();
+  if (halo_offset) *halo_offset = E->halo_offset.data();
+  if (node_l2g) *node_l2g = E->l2g.data();
+  return 0;
+}
+
+extern "C" int wf_halo_comm_block(wf_engine *E, void **base, size_t *bytes) {
+  NEED(E->distributed, "not a partitioned engine");
+  if (base) *base = E->comm;
+  if (bytes) *bytes = E->comm_bytes;
+  return 0;
+}
+
+extern "C" int wf_halo_slot_offsets(wf_engine *E, int i, size_t *flag_off, size_t *region_off, size_t *region_bytes) {
+  NEED(E->distributed, "not a partitioned engine");
+  NEED(i >= 0 && i < (int)E->neigh.size(), "bad neighbour index");
+  if (flag_off) *flag_off = 8 * (size_t)i;
+  if (region_off) *region_off = E->flag_bytes + sizeof(double) * 2 * WF_HALO_NC * (size_t)E->halo_offset[i];
+  if (region_bytes) *region_bytes = sizeof(double) * 2 * WF_HALO_NC * (size_t)(E->halo_offset[i + 1] - E->halo_offset[i]);
+  return 0;
+}
+
+static int push_nb(wf_engine *E) {
+  CK(cudaSetDevice(E->device));
+  if (!E->nb_h.empty())
+    CK(cudaMemcpy(E->nb_d, E->nb_h.data(), sizeof(WfHaloNb) * E->nb_h.size(), cudaMemcpyHostToDevice));
+  return 0;
+}
+
+extern "C" int wf_halo_connect(wf_engine *E, int i, void *peer_base, size_t flag_off, size_t region_off) {
+  NEED(E->distributed, "not a partitioned engine");
+  NEED(E->transport == 0, "wf_halo_connect belongs to the peer-memory transport");
+  NEED(i >= 0 && i < (int)E->neigh.size(), "bad neighbour index");
+  NEED(peer_base, "null peer pointer");
+  if (!E->nb_h[i].dst) E->n_connected++;
+  E->nb_h[i].dst = (double *)((char *)peer_base + region_off);
+  E->nb_h[i].flag = (unsigned long long *)((char *)peer_base + flag_off);
+  return push_nb(E);
+}
+
+extern "C" int wf_halo_set_transport(wf_engine *E, int host_driven) {
+  NEED(E->distributed, "not a partitioned engine");
+  NEED(!E->inited, "choose the halo transport before wf_init");
+  E->transport = host_driven ? 1 : 0;
+  if (E->transport == 1) { // sends land in a local staging block with the layout of the comm block
+    CK(cudaSetDevice(E->device));
+    if (!E->staging && dalloc(E, &E->staging, E->comm_bytes)) return 1;
+    for (size_t i = 0; i < E->nb_h.size(); i++) {
+      E->nb_h[i].dst = (double *)(E->staging + E->flag_bytes + sizeof(double) * 2 * WF_HALO_NC * (size_t)E->halo_offset[i]);
+      E->nb_h[i].flag = (unsigned long long *)(E->staging + 8 * i);
+    }
+    E->n_connected = (int)E->nb_h.size();
+    return push_nb(E);
+  }
+  return 0;
+}
+
+// host-driven transport: what to send to / receive from neighbour i for the exchange just packed
+extern "C" int wf_halo_exchange_ptrs(wf_engine *E, int i, void **send_ptr, void **recv_ptr, size_t *n_doubles) {
+  NEED(E->distributed && E->transport == 1, "host-driven halo transport is not selected");
+  NEED(i >= 0 && i < (int)E->neigh.size(), "bad neighbour index");
+  const size_t cnt = (size_t)(E->halo_offset[i + 1] - E->halo_offset[i]);
+  const size_t off = E->flag_bytes + sizeof(double) * (2 * WF_HALO_NC * (size_t)E->halo_offset[i] + (E->seq & 1ull) * WF_HALO_NC * cnt);
+  if (send_ptr) *send_ptr = E->staging + off;
+  if (recv_ptr) *recv_ptr = E->comm + off;
+  if (n_doubles) *n_doubles = WF_HALO_NC * cnt;
+  return 0;
+}
+
+extern "C" int wf_halo_ipc_export(wf_engine *E, void *handle64) {
+  NEED(E->distributed && E->comm, "not a partitioned engine");
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  CK(cudaSetDevice(E->device));
+  cudaIpcMemHandle_t h;
+  CK(cudaIpcGetMemHandle(&h, E->comm));
+  memcpy(handle64, &h, 64);
+  return 0;
+}
+
+extern "C" int wf_halo_ipc_open(wf_engine *E, const void *handle64, void **mapped) {
+  NEED(handle64 && mapped, "null argument");
+  CK(cudaSetDevice(E->device));
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle64, 64);
+  void *p = nullptr;
+  CK(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+  E->ipc_opened.push_back(p);
+  *mapped = p;
+  return 0;
+}
+
+extern "C" int wf_halo_status(wf_engine *E, int *error) {
+  int e = 0;
+  if (E->distributed) {
+    CK(cudaSetDevice(E->device));
+    CK(cudaMemcpyAsync(&e, E->d.comm_error, sizeof(int), cudaMemcpyDeviceToHost, E->stream));
+    CK(cudaStreamSynchronize(E->stream));
+  }
+  if (error) *error = e;
+  if (e) FAIL("halo exchange timed out waiting for neighbour index " + std::to_string(e - 1));
+  return 0;
+}
+
+// ---- all ranks of a job inside ONE process (one host thread drives every GPU) -------------------------
+extern "C" int wf_connect_all(wf_engine **R, int n) {
+  for (int p = 0; p < n; p++) {
+    wf_engine *E = R[p];
+    NEED(E->distributed && E->rank == p && E->nranks == n, "wf_connect_all: engines must be given in rank order");
+    for (size_t i = 0; i < E->neigh.size(); i++) {
+      wf_engine *Q = R[E->neigh[i]];
+      int me = -1;
+      for (size_t j = 0; j < Q->neigh.size(); j++)
+        if (Q->neigh[j] == p) me = (int)j;
+      NEED(me >= 0, "wf_connect_all: halo lists are not symmetric");
+      if (Q->device != E->device) {
+        CK(cudaSetDevice(E->device));
+        int can = 0;
+        CK(cudaDeviceCanAccessPeer(&can, E->device, Q->device));
+        NEED(can, "no peer access between the GPUs of two neighbouring ranks");
+        cudaError_t ce = cudaDeviceEnablePeerAccess(Q->device, 0);
+        if (ce != cudaSuccess && ce != cudaErrorPeerAccessAlreadyEnabled) CK(ce);
+        cudaGetLastError();
+      }
+      size_t fo, ro;
+      if (wf_halo_slot_offsets(Q, me, &fo, &ro, nullptr)) { E->err = Q->err; return 1; }
+      if (wf_halo_connect(E, (int)i, Q->comm, fo, ro)) return 1;
+    }
+  }
+  return 0;
+}
+
+extern "C" int wf_init_all(wf_engine **R, int n, double dt) {
+  for (int p = 0; p < n; p++)
+    if (init_prologue(R[p])) return 1;
+  for (int st = 0; st < 3; st++)
+    for (int p = 0; p < n; p++) {
+      wf_engine *E = R[p];
+      CK(cudaSetDevice(E->device));
+      if (init_stage(E, st, dt)) return 1;
+      if (st < 2) halo_wait(E);
+    }
+  return 0;
+}
+
+extern "C" int wf_step_all(wf_engine **R, int n, int nsteps) {
+  for (int p = 0; p < n; p++)
+    if (step_prologue(R[p])) return 1;
+  // interleave the ranks step by step so that no stream's launch queue fills up while it waits for a
+  // neighbour whose work has not been enqueued yet
+  for (int s = 0; s < nsteps; s++)
+    for (int p = 0; p < n; p++) {
+      wf_engine *E = R[p];
+      CK(cudaSetDevice(E->device));
+      if (step_once(E, s == nsteps - 1)) return 1;
+    }
+  for (int p = 0; p < n; p++)
+    if (step_epilogue(R[p], "wf_step_all")) return 1;
+  return 0;
 }
 
 extern "C" int wf_nonfinite_flag(wf_engine *E, int *flag) {
@@ -595,7 +983,7 @@ extern "C" int wf_CalcNodalMassFromVol(wf_engine *E) { UNFUSED_PROLOGUE(); E->L-
 extern "C" int wf_calcElemStrainRates(wf_engine *E) { UNFUSED_PROLOGUE(); E->L->u_strain_rates(d, P, E->et, E->stream); E->rates_in_dbg = true; return check_launch(E, __func__); }
 extern "C" int wf_calcElemPressure(wf_engine *E) {
   UNFUSED_PROLOGUE();
-  E->L->node_vol(d, P, 1, 0, E->stream);
+  E->L->node_vol(d, P, 1, E->stream);
   E->L->u_pressure(d, P, E->et, E->stream);
   return check_launch(E, __func__);
 }

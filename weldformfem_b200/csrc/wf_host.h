@@ -17,6 +17,7 @@ void wf_box_node_xyz(const WfBox &b, const std::vector<double> ax[3], long long 
 
 struct wf_partition;
 int wf_partition_k(const wf_partition *p);
+void wf_partition_ranks(const wf_partition *p, int *rank, int *nranks);
 bool wf_partition_is_box(const wf_partition *p);
 void wf_partition_box_coords(const wf_partition *p, std::vector<double> &x);
 int wf_partition_box_dim(const wf_partition *p);

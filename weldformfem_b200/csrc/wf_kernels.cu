@@ -134,7 +134,7 @@ __global__ void k_vol_from_detj(WfDev d) {
 // calcElemPressureANP (:1228-1240), calcElemPressureANP_Nodal (:1262-1284).
 // ---------------------------------------------------------------------------------------------
 template <int K>
-__global__ void __launch_bounds__(TPB_N) k_node_vol(WfDev d, WfPar P, int mode, int local_only) {
+__global__ void __launch_bounds__(TPB_N) k_node_vol(WfDev d, WfPar P, int mode) {
   int n = blockIdx.x * blockDim.x + threadIdx.x;
   if (n == 0 && mode == 1 && d.xmin_key) d.xmin_key[P.xmin_cur ^ 1] = dbl_key(1000.0);
   int slice = n >> 5;
@@ -167,10 +167,6 @@ __global__ void __launch_bounds__(TPB_N) k_node_vol(WfDev d, WfPar P, int mode, 
     return;
   }
   d.voln_sum[n] = s;
-  if (local_only) { // multi-GPU: partial sums; ratios are formed after the halo exchange
-    d.nodal_p[n] = quarter ? sq : s;
-    return;
-  }
   if (P.press == 0) d.nodal_p[n] = s / d.voln0_sum[n];
   else if (P.press == 1) d.nodal_p[n] = P.Kbulk * (1.0 - s / d.voln0_sum[n]);
   else {
@@ -199,20 +195,6 @@ __global__ void __launch_bounds__(TPB_N) k_node_vol(WfDev d, WfPar P, int mode, 
       }
     }
     d.mdiag[n] = mass;
-  }
-}
-
-// after a halo exchange the summed partials are turned into ratios / nodal pressures
-__global__ void k_node_vol_finish(WfDev d, WfPar P) {
-  int n = blockIdx.x * blockDim.x + threadIdx.x;
-  if (n >= d.nn) return;
-  double s = d.nodal_p[n];
-  if (P.press == 0) d.nodal_p[n] = s / d.voln0_sum[n];
-  else if (P.press == 1) d.nodal_p[n] = P.Kbulk * (1.0 - s / d.voln0_sum[n]);
-  else {
-    double v0 = d.voln0_sum[n], pn = 0.0;
-    if (v0 > 1e-12) { double Jn = s / v0; pn = P.Kbulk * (1.0 - Jn); }
-    d.nodal_p[n] = pn;
   }
 }
 
@@ -336,14 +318,74 @@ __global__ void __launch_bounds__(TPB_E) k_elem_main(WfDev d, WfPar P) {
 }
 
 // ---------------------------------------------------------------------------------------------
+// device helpers of the multi-GPU halo exchange (kernels further below)
+// ---------------------------------------------------------------------------------------------
+WF_DI void st_release_sys(unsigned long long *p, unsigned long long v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+WF_DI unsigned long long ld_acquire_sys(const unsigned long long *p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+WF_DI unsigned long long global_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+
+// partial sums over the local nodel list of node n, in list order
+WF_DI void halo_node_sums(const WfDev &d, int n, const double *__restrict__ src, double &s, double &sq, double &rs, int &cnt) {
+  const long long base = d.sell_ptr[n >> 5];
+  const int width = (int)((d.sell_ptr[(n >> 5) + 1] - base) >> 5);
+  const int lane = n & 31;
+  s = 0.0; sq = 0.0; rs = 0.0; cnt = 0;
+  for (int j = 0; j < width; j++) {
+    int slot = __ldg(d.sell_slots + base + ((long long)j << 5) + lane);
+    if (slot >= 0) {
+      const int e = slot / d.k;
+      const double ve = src[e];
+      s += ve;
+      sq += ve / 4.0;
+      rs += d.rho[e];
+      cnt++;
+    }
+  }
+}
+WF_DI void halo_node_force(const WfDev &d, int n, int sep, double (&fi)[3]) {
+  const long long base = d.sell_ptr[n >> 5];
+  const int width = (int)((d.sell_ptr[(n >> 5) + 1] - base) >> 5);
+  const int D = d.dim;
+  const double *__restrict__ row = d.fsell + base * D + (n & 31);
+  fi[0] = fi[1] = fi[2] = 0.0;
+  for (int j = 0; j < width; j++)
+    for (int c = 0; c < D; c++) fi[c] += row[((long long)j * D + c) * 32];
+  if (sep) {
+    const double *__restrict__ rowh = d.fsell_hg + base * D + (n & 31);
+    for (int j = 0; j < width; j++)
+      for (int c = 0; c < D; c++) fi[c] -= rowh[((long long)j * D + c) * 32];
+  }
+}
+// sum of the sharers' partials of unique shared node u, component comp, ascending rank order
+WF_DI double halo_total(const WfDev &d, int u, int comp, int parity, double own) {
+  double acc = 0.0;
+  const int q1 = d.hu_ptr[u + 1];
+  for (int q = d.hu_ptr[u]; q < q1; q++) {
+    const int2 en = d.hu_ent[q];
+    acc += (en.x < 0) ? own : __ldcg(d.recv + en.x + (long long)(parity * WF_HALO_NC + comp) * en.y);
+  }
+  return acc;
+}
+
+// ---------------------------------------------------------------------------------------------
 // N2: per-node force sum in nodel order (assemblyForces, Matrices.C:42-87: element forces first,
 // then hourglass forces subtracted), calcAccel (Mechanical.C:321-341), ImposeBCA,
 // UpdateCorrectionAccVel (Domain_d.C:981-997), ImposeBCV, axis constraint
 // (Solver_explicit.C:953-969), UpdateCorrectionPos (Domain_d.C:1005-1025) and, unless this is the
 // last step of the batch, the next step's UpdatePrediction + ImposeBCV.  The nodal mass was formed
 // by N1.  One warp == one slice of 32 nodes; every load is a contiguous 256 B row.
-//   phase 0 = everything;  phase 1 = sums only, to d.fi (multi-GPU partials / lazy m_fi);
-//   phase 2 = integrate from d.fi (after the halo exchange)
+//   phase 0 = everything;  phase 1 = sums only, to d.fi (lazy m_fi);  phase 2 = integrate from d.fi.
+// On a partitioned mesh the sums of shared nodes are completed with the neighbours' partials (halo_total).
 // ---------------------------------------------------------------------------------------------
 template <int D, bool SEPARATE_HG, int UNROLL>
 __global__ void __launch_bounds__(TPB_N) k_node_update(WfDev d, WfPar P, int fuse_predictor, int phase) {
@@ -378,6 +420,13 @@ __global__ void __launch_bounds__(TPB_N) k_node_update(WfDev d, WfPar P, int fus
     }
   }
   if (n >= d.nn) return;
+  if (d.halo_slot && phase != 2) { // shared node: add the other sharers' partials, ascending rank order
+    const int u = d.halo_slot[n];
+    if (u >= 0) {
+#pragma unroll
+      for (int c = 0; c < D; c++) fi[c] = halo_total(d, u, c, P.halo_parity, fi[c]);
+    }
+  }
   if (phase == 1) {
 #pragma unroll
     for (int c = 0; c < D; c++) d.fi[(long long)c * d.np + n] = fi[c];
@@ -753,18 +802,94 @@ __global__ void k_u_corr_pos(WfDev d, WfPar P) { // UpdateCorrectionPos
   }
 }
 
-// halo pack / unpack-add for the multi-GPU split step (nc doubles per shared node)
-__global__ void k_halo_pack(WfDev d, const double *src, long long pitch, int nc, const int *list, int count, double *buf) {
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= count) return;
-  int n = list[i];
-  for (int c = 0; c < nc; c++) buf[(long long)c * count + i] = src[(long long)c * pitch + n];
+// ---------------------------------------------------------------------------------------------
+// multi-GPU halo exchange of partial nodal sums over peer memory (no reference exists)
+//   k_halo_send<MODE>   : recompute this rank's partial sums for its shared nodes (same list order as the
+//                         node kernels, so the values are the ones those kernels form) and store them
+//                         straight into the neighbour's receive region over NVLink; the last block to
+//                         finish publishes the exchange's sequence number in the neighbour's flag slot
+//                         (system-scope release).  MODE 0 = init triple (sum vol_0, sum rho, count),
+//                         1 = sum vol (+ sum vol/4 for ANP_Nodal), 2 = internal-force partial.
+//   k_halo_wait         : one block; spins (acquire, system scope) until every neighbour has published
+//                         the sequence number.  Kept separate from the consumers so that a waiting rank
+//                         never occupies more than one CTA.
+//   k_halo_finish<MODE> : per unique shared node, total = sum of the sharers' partials in ascending rank
+//                         order (identical on every sharer, so all copies stay bit-identical), then the
+//                         same epilogue as k_node_vol.  The force totals are formed inside k_node_update.
+// ---------------------------------------------------------------------------------------------
+template <int MODE>
+__global__ void __launch_bounds__(128) k_halo_send(WfDev d, WfPar P, int sep, unsigned long long seq) {
+  const WfHaloNb nb = d.nb[blockIdx.y];
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j < nb.count) {
+    const int n = d.halo_nodes[nb.offset + j];
+    double vals[WF_HALO_NC] = {0.0, 0.0, 0.0};
+    int nc = WF_HALO_NC;
+    if (MODE == 2) {
+      halo_node_force(d, n, sep, vals);
+      nc = d.dim;
+    } else {
+      double s, sq, rs;
+      int cnt;
+      halo_node_sums(d, n, MODE == 0 ? d.vol_0 : d.vol, s, sq, rs, cnt);
+      if (MODE == 0) { vals[0] = (P.press == 3) ? sq : s; vals[1] = rs; vals[2] = (double)cnt; }
+      else { vals[0] = s; vals[1] = sq; nc = 2; }
+    }
+    double *dst = nb.dst + (long long)(seq & 1ull) * WF_HALO_NC * nb.count + j;
+    for (int c = 0; c < nc; c++) dst[(long long)c * nb.count] = vals[c];
+    __threadfence_system();
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    const unsigned done = atomicAdd(nb.counter, 1u);
+    if (done == gridDim.x - 1) {
+      *nb.counter = 0u;
+      __threadfence_system();
+      st_release_sys(nb.flag, seq);
+    }
+  }
 }
-__global__ void k_halo_add(WfDev d, double *dst, long long pitch, int nc, const int *list, int count, const double *buf) {
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= count) return;
-  int n = list[i];
-  for (int c = 0; c < nc; c++) dst[(long long)c * pitch + n] += buf[(long long)c * count + i];
+
+__global__ void k_halo_wait(WfDev d, unsigned long long seq, unsigned long long timeout_ns) {
+  const int i = threadIdx.x;
+  if (i >= d.n_neigh) return;
+  const unsigned long long t0 = global_ns();
+  while (ld_acquire_sys(d.flags + i) < seq) {
+    if (global_ns() - t0 > timeout_ns) { atomicExch(d.comm_error, 1 + i); break; }
+    __nanosleep(200);
+  }
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(128) k_halo_finish(WfDev d, WfPar P, int parity) {
+  const int u = blockIdx.x * blockDim.x + threadIdx.x;
+  if (u >= d.n_uniq) return;
+  const int n = d.hu_node[u];
+  double s, sq, rs;
+  int cnt;
+  halo_node_sums(d, n, MODE == 0 ? d.vol_0 : d.vol, s, sq, rs, cnt);
+  if (MODE == 0) {
+    const double t0 = halo_total(d, u, 0, parity, (P.press == 3) ? sq : s);
+    const double t1 = halo_total(d, u, 1, parity, rs);
+    const double t2 = halo_total(d, u, 2, parity, (double)cnt);
+    d.voln0_sum[n] = t0;
+    d.rhobar[n] = t1 / t2;
+    d.nodel_count[n] = (int)t2;
+    return;
+  }
+  s = halo_total(d, u, 0, parity, s);
+  d.voln_sum[n] = s;
+  if (P.press == 0) d.nodal_p[n] = s / d.voln0_sum[n];
+  else if (P.press == 1) d.nodal_p[n] = P.Kbulk * (1.0 - s / d.voln0_sum[n]);
+  else {
+    sq = halo_total(d, u, 1, parity, sq);
+    double v0 = d.voln0_sum[n], pn = 0.0;
+    if (v0 > 1e-12) { double Jn = sq / v0; pn = P.Kbulk * (1.0 - Jn); }
+    d.nodal_p[n] = pn;
+  }
+  // nodal mass of a shared node: sum_e rho_e voln / count regrouped as voln * mean(rho_e) over ALL sharers
+  d.mdiag[n] = d.rhobar[n] * (s / (double)d.k);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -792,25 +917,16 @@ static void l_elem_vol(const WfDev &d, const WfPar &P, int et, int store_jac, cu
 static void l_vol_from_detj(const WfDev &d, int et, cudaStream_t s) {
   ELEM_DISPATCH(et, k_vol_from_detj<ET><<<cdiv(d.ne, 256), 256, 0, s>>>(d));
 }
-static void l_node_vol(const WfDev &d, const WfPar &P, int mode, int local_only, cudaStream_t s) {
+static void l_node_vol(const WfDev &d, const WfPar &P, int mode, cudaStream_t s) {
   int g = cdiv((long long)d.nslices * 32, TPB_N);
   switch (d.k) {
-    case 8: k_node_vol<8><<<g, TPB_N, 0, s>>>(d, P, mode, local_only); break;
-    case 4: k_node_vol<4><<<g, TPB_N, 0, s>>>(d, P, mode, local_only); break;
-    default: k_node_vol<3><<<g, TPB_N, 0, s>>>(d, P, mode, local_only); break;
+    case 8: k_node_vol<8><<<g, TPB_N, 0, s>>>(d, P, mode); break;
+    case 4: k_node_vol<4><<<g, TPB_N, 0, s>>>(d, P, mode); break;
+    default: k_node_vol<3><<<g, TPB_N, 0, s>>>(d, P, mode); break;
   }
-}
-static void l_node_vol_finish(const WfDev &d, const WfPar &P, cudaStream_t s) {
-  k_node_vol_finish<<<cdiv(d.nn, 256), 256, 0, s>>>(d, P);
 }
 static void l_elem_main(const WfDev &d, const WfPar &P, int et, int separate_hg, cudaStream_t s) {
   if (!separate_hg && et == ET_HEX8 && !P.strict && P.variant[2] != 1) {
-    static bool configured = false;
-    if (!configured) {
-      cudaFuncSetAttribute(hexfast::k_elem_main_hex_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, hexfast::SMEM_BYTES);
-      cudaFuncSetAttribute(hexfast::k_elem_main_hex_fast, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
-      configured = true;
-    }
     hexfast::k_elem_main_hex_fast<<<cdiv(d.ne, hexfast::TPB), hexfast::TPB, hexfast::SMEM_BYTES, s>>>(d, P);
     return;
   }
@@ -889,11 +1005,45 @@ static void l_u_corr_pos(const WfDev &d, const WfPar &P, cudaStream_t s) {
   if (d.dim == 3) k_u_corr_pos<3><<<cdiv(d.nn, 256), 256, 0, s>>>(d, P);
   else k_u_corr_pos<2><<<cdiv(d.nn, 256), 256, 0, s>>>(d, P);
 }
-static void l_halo_pack(const WfDev &d, const double *src, long long pitch, int nc, const int *list, int count, double *buf, cudaStream_t s) {
-  if (count > 0) k_halo_pack<<<cdiv(count, 256), 256, 0, s>>>(d, src, pitch, nc, list, count, buf);
+static void l_halo_send(const WfDev &d, const WfPar &P, int mode, int sep, unsigned long long seq, int max_count, cudaStream_t s) {
+  if (d.n_neigh <= 0) return;
+  dim3 g(cdiv(max_count > 0 ? max_count : 1, 128), d.n_neigh);
+  if (mode == 0) k_halo_send<0><<<g, 128, 0, s>>>(d, P, sep, seq);
+  else if (mode == 1) k_halo_send<1><<<g, 128, 0, s>>>(d, P, sep, seq);
+  else k_halo_send<2><<<g, 128, 0, s>>>(d, P, sep, seq);
 }
-static void l_halo_add(const WfDev &d, double *dst, long long pitch, int nc, const int *list, int count, const double *buf, cudaStream_t s) {
-  if (count > 0) k_halo_add<<<cdiv(count, 256), 256, 0, s>>>(d, dst, pitch, nc, list, count, buf);
+static void l_halo_wait(const WfDev &d, unsigned long long seq, unsigned long long timeout_ns, cudaStream_t s) {
+  if (d.n_neigh > 0) k_halo_wait<<<1, 32 * ((d.n_neigh + 31) / 32), 0, s>>>(d, seq, timeout_ns);
+}
+static void l_halo_finish(const WfDev &d, const WfPar &P, int mode, int parity, cudaStream_t s) {
+  if (d.n_uniq <= 0) return;
+  if (mode == 0) k_halo_finish<0><<<cdiv(d.n_uniq, 128), 128, 0, s>>>(d, P, parity);
+  else k_halo_finish<1><<<cdiv(d.n_uniq, 128), 128, 0, s>>>(d, P, parity);
+}
+
+// Force-load every kernel of the step (CUDA loads kernels lazily, and loading one synchronises the context:
+// a first launch issued while a halo wait kernel is spinning for work that the same host thread has not
+// enqueued yet would deadlock).
+template <class F>
+static void touch(F *f) {
+  cudaFuncAttributes a;
+  cudaFuncGetAttributes(&a, f);
+}
+static void l_preload(int et, int dim, int k) {
+  (void)k;
+  touch(k_predict<2>); touch(k_predict<3>); touch(k_impose_bc);
+  ELEM_DISPATCH(et, touch(k_elem_vol<ET>); touch(k_elem_main<ET, true>); touch(k_elem_main<ET, false>));
+  touch(k_node_vol<8>); touch(k_node_vol<4>); touch(k_node_vol<3>);
+  // per device: the regrouped hexa kernel stages 48 KB of node data per CTA
+  cudaFuncSetAttribute(hexfast::k_elem_main_hex_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, hexfast::SMEM_BYTES);
+  cudaFuncSetAttribute(hexfast::k_elem_main_hex_fast, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+  touch(hexfast::k_elem_main_hex_fast);
+  touch(k_node_update<3, true, 4>); touch(k_node_update<3, false, 4>); touch(k_node_update<3, false, 2>); touch(k_node_update<3, false, 8>);
+  touch(k_node_update<2, true, 4>); touch(k_node_update<2, false, 4>); touch(k_node_update<2, false, 2>); touch(k_node_update<2, false, 8>);
+  touch(k_halo_send<0>); touch(k_halo_send<1>); touch(k_halo_send<2>); touch(k_halo_wait);
+  touch(k_halo_finish<0>); touch(k_halo_finish<1>);
+  touch(k_init_elem); touch(k_vol0_density); touch(k_xmin);
+  (void)dim;
 }
 
 } // namespace WF_NS
@@ -902,10 +1052,10 @@ static void l_halo_add(const WfDev &d, double *dst, long long pitch, int nc, con
 #define WF_CAT(a, b) WF_CAT2(a, b)
 extern "C" const WfLaunch *WF_CAT(WF_NS, _table)() {
   using namespace WF_NS;
-  static const WfLaunch t = {l_predict, l_impose_bc, l_elem_vol, l_vol_from_detj, l_node_vol, l_node_vol_finish,
+  static const WfLaunch t = {l_predict, l_impose_bc, l_elem_vol, l_vol_from_detj, l_node_vol,
                              l_elem_main, l_node_update, l_node_mass, l_init_elem, l_vol0_density, l_density, l_xmin,
                              l_rebuild_sigma, l_energy, l_u_strain_rates, l_u_pressure, l_u_stress, l_u_artvisc,
                              l_u_forces, l_u_hourglass, l_u_nodal_vol, l_u_assembly, l_u_accel, l_u_corr_accvel,
-                             l_u_axis, l_u_corr_pos, l_halo_pack, l_halo_add};
+                             l_u_axis, l_u_corr_pos, l_halo_send, l_halo_wait, l_halo_finish, l_preload};
   return &t;
 }

@@ -8,8 +8,7 @@ struct WfLaunch {
   void (*impose_bc)(const WfDev &, int dim, int is_acc, double *arr, cudaStream_t);
   void (*elem_vol)(const WfDev &, const WfPar &, int et, int store_jac, cudaStream_t);
   void (*vol_from_detj)(const WfDev &, int et, cudaStream_t);
-  void (*node_vol)(const WfDev &, const WfPar &, int mode, int local_only, cudaStream_t);
-  void (*node_vol_finish)(const WfDev &, const WfPar &, cudaStream_t);
+  void (*node_vol)(const WfDev &, const WfPar &, int mode, cudaStream_t);
   void (*elem_main)(const WfDev &, const WfPar &, int et, int separate_hg, cudaStream_t);
   void (*node_update)(const WfDev &, const WfPar &, int separate_hg, int fuse_predictor, int phase, cudaStream_t);
   void (*node_mass)(const WfDev &, const WfPar &, int use_stored_voln, cudaStream_t);
@@ -31,8 +30,10 @@ struct WfLaunch {
   void (*u_corr_accvel)(const WfDev &, const WfPar &, cudaStream_t);
   void (*u_axis)(const WfDev &, const WfPar &, cudaStream_t);
   void (*u_corr_pos)(const WfDev &, const WfPar &, cudaStream_t);
-  void (*halo_pack)(const WfDev &, const double *src, long long pitch, int nc, const int *list, int count, double *buf, cudaStream_t);
-  void (*halo_add)(const WfDev &, double *dst, long long pitch, int nc, const int *list, int count, const double *buf, cudaStream_t);
+  void (*halo_send)(const WfDev &, const WfPar &, int mode, int separate_hg, unsigned long long seq, int max_count, cudaStream_t);
+  void (*halo_wait)(const WfDev &, unsigned long long seq, unsigned long long timeout_ns, cudaStream_t);
+  void (*halo_finish)(const WfDev &, const WfPar &, int mode, int parity, cudaStream_t);
+  void (*preload)(int et, int dim, int k);
 };
 
 extern "C" const WfLaunch *wf_strict_table();

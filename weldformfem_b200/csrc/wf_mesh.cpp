@@ -221,6 +221,7 @@ extern "C" const int *wf_partition_halo_nodes(const wf_partition *p) { return p-
 
 // accessors used by the engine
 int wf_partition_k(const wf_partition *p) { return p->k; }
+void wf_partition_ranks(const wf_partition *p, int *rank, int *nranks) { *rank = p->rank; *nranks = p->nranks; }
 bool wf_partition_is_box(const wf_partition *p) { return p->is_box; }
 void wf_partition_box_coords(const wf_partition *p, std::vector<double> &x) {
   std::vector<double> ax[3];

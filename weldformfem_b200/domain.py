@@ -150,6 +150,11 @@ class Domain_d:
 
     allocate_bcs = AllocateBCs
 
+    def set_bc_values(self, dim, vals):
+        """New values for bcx_val / bcy_val / bcz_val of one dimension (insertion order), uploaded asynchronously."""
+        vals = np.ascontiguousarray(vals, dtype=np.float64)
+        self._ck(self._lib.wf_set_bc_values(self._h, int(dim), vals.size, vals.ctypes.data_as(C.POINTER(C.c_double))))
+
     def SetDT(self, dt):                                       # Domain_d.h:629
         self._dt = float(dt)
 
