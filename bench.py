@@ -190,7 +190,8 @@ def ours(args):
         # weak scaling: every rank owns one n^(d-1) x n slab of an n^(d-1) x (n * world) box
         nn_ = list(case.n)
         nn_[-1] *= world
-        case = dataclasses.replace(case, n=tuple(nn_), name=case.name + f"_x{world}")
+        # same strain rate as the one-GPU workload: the moving plane is `world` times further from the clamped one
+        case = dataclasses.replace(case, n=tuple(nn_), name=case.name + f"_x{world}", top_vel=case.top_vel * world)
         dom = RankDomain(rank, world, device=local, strict=args.strict, halo=args.halo)
     else:
         dom = Domain_d(device=local, strict=args.strict)

@@ -68,6 +68,7 @@ void wf_destroy(wf_engine *);
 const char *wf_last_error(wf_engine *); /* engine may be NULL: last error of wf_create */
 /* run all engine work on a caller-owned CUDA stream (cudaStream_t as void*); default stream if never set */
 int wf_set_stream(wf_engine *, void *cuda_stream);
+int wf_get_stream(wf_engine *, void **cuda_stream);
 int wf_synchronize(wf_engine *);
 
 /* ---- mesh ---------------------------------------------------------------------------------------- */

@@ -30,7 +30,7 @@ UNFUSED = ("UpdatePrediction calcElemJAndDerivatives Calc_Element_Radius CalcEle
            "UpdateCorrectionPos").split()
 
 # every symbol include/wf_engine.h declares (checked by tests/test_abi.py)
-DECLARED = (["wf_create", "wf_destroy", "wf_last_error", "wf_set_stream", "wf_synchronize", "wf_set_mesh", "wf_gen_box",
+DECLARED = (["wf_create", "wf_destroy", "wf_last_error", "wf_set_stream", "wf_get_stream", "wf_synchronize", "wf_set_mesh", "wf_gen_box",
              "wf_get_counts", "wf_set_axisymm_vol_weight", "wf_set_material", "wf_set_stab", "wf_set_options",
              "wf_set_tracking", "wf_add_bc_vel", "wf_add_bc_vel_array", "wf_allocate_bcs", "wf_set_bc_values", "wf_init", "wf_step",
              "wf_nonfinite_flag", "wf_energies", "wf_get_time", "wf_step_timed", "wf_set_variant", "wf_ImposeBCV", "wf_ImposeBCA", "wf_CalcStressStrain",
@@ -60,6 +60,7 @@ def load():
         "wf_destroy": (None, [vp]),
         "wf_last_error": (C.c_char_p, [vp]),
         "wf_set_stream": (C.c_int, [vp, vp]),
+        "wf_get_stream": (C.c_int, [vp, C.POINTER(vp)]),
         "wf_synchronize": (C.c_int, [vp]),
         "wf_set_mesh": (C.c_int, [vp, C.c_int, C.c_int, dp, up]),
         "wf_gen_box": (C.c_int, [vp, dp, dp, C.c_double, C.c_int]),

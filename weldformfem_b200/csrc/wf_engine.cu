@@ -161,6 +161,7 @@ extern "C" int wf_set_stream(wf_engine *E, void *s) {
   E->stream = (cudaStream_t)s;
   return 0;
 }
+extern "C" int wf_get_stream(wf_engine *E, void **s) { if (s) *s = (void *)E->stream; return 0; }
 extern "C" int wf_synchronize(wf_engine *E) { CK(cudaSetDevice(E->device)); CK(cudaStreamSynchronize(E->stream)); return 0; }
 
 extern "C" int wf_set_axisymm_vol_weight(wf_engine *E, int on) {

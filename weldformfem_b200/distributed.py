@@ -199,21 +199,24 @@ class RankDomain(Domain_d):
         return plan
 
     def _nccl_exchange(self):
+        """Grouped ncclSend/ncclRecv of the exchange just packed, ordered on the ENGINE's stream: NCCL starts
+        after the pack kernel and the consumer kernels wait for it — no host synchronisation."""
         import torch
         import torch.distributed as dist
+        dev = torch.device("cuda", self._device)
         ops, keep = [], []
-        for i, q in enumerate(self.neigh):
-            sp, rp, n = C.c_void_p(), C.c_void_p(), C.c_size_t()
-            self._ck(self._lib.wf_halo_exchange_ptrs(self._h, i, C.byref(sp), C.byref(rp), C.byref(n)))
-            dev = torch.device("cuda", self._device)
-            st = torch.as_tensor(_CudaBuffer(sp.value, n.value), device=dev)
-            rt = torch.as_tensor(_CudaBuffer(rp.value, n.value), device=dev)
-            keep += [st, rt]
-            ops.append(dist.P2POp(dist.isend, st, q))
-            ops.append(dist.P2POp(dist.irecv, rt, q))
-        if ops:
-            for w in dist.batch_isend_irecv(ops):
-                w.wait()
+        with torch.cuda.stream(torch.cuda.ExternalStream(self.get_stream(), device=dev)):
+            for i, q in enumerate(self.neigh):
+                sp, rp, n = C.c_void_p(), C.c_void_p(), C.c_size_t()
+                self._ck(self._lib.wf_halo_exchange_ptrs(self._h, i, C.byref(sp), C.byref(rp), C.byref(n)))
+                st = torch.as_tensor(_CudaBuffer(sp.value, n.value), device=dev)
+                rt = torch.as_tensor(_CudaBuffer(rp.value, n.value), device=dev)
+                keep += [st, rt]
+                ops.append(dist.P2POp(dist.isend, st, q))
+                ops.append(dist.P2POp(dist.irecv, rt, q))
+            if ops:
+                for w in dist.batch_isend_irecv(ops):
+                    w.wait()
 
     # ---- solve ----------------------------------------------------------------------------------
     def init(self, dt=None):

@@ -77,6 +77,11 @@ class Domain_d:
     def set_stream(self, cuda_stream: int):
         self._ck(self._lib.wf_set_stream(self._h, C.c_void_p(cuda_stream)))
 
+    def get_stream(self) -> int:
+        s = C.c_void_p()
+        self._ck(self._lib.wf_get_stream(self._h, C.byref(s)))
+        return s.value or 0
+
     def synchronize(self):
         self._ck(self._lib.wf_synchronize(self._h))
 
