@@ -16,6 +16,7 @@
 #include <stdint.h>
 
 #define WF_MAXK 8
+#define WF_EBLK 128 /* elements per CTA of the element passes */
 #define WF_HALO_NC 3 /* doubles per shared node and exchange (max: dim force components / init triple) */
 
 struct WfHaloNb {
@@ -65,6 +66,13 @@ struct WfDev {
   double *eps;                       /* [6][ep] (optional) */
   double *p, *pl_strain, *sigma_y, *vol, *vol_0, *rho, *rho_0; /* [ep] */
   double *hg_q;                      /* [2][ep] 2D quads (m_hg_q) */
+  /* element-block node tables: CTA b of the element passes owns elements [b*WF_EBLK, (b+1)*WF_EBLK); its
+   * UNIQUE nodes (ascending id) are blk_nodes[blk_off[b] .. blk_off[b+1]) and lidx gives every element-node its
+   * index in that list, so the CTA stages each node's data in shared memory once instead of once per element. */
+  const int *blk_off;                /* [nblk+1] */
+  const int *blk_nodes;
+  const unsigned short *lidx;        /* [k][ep] */
+  int blk_umax;                      /* longest unique list */
   const int *pos;                    /* [k][ep] offset of (e, ln) in fsell: dim*q - (dim-1)*(n&31), q = sell index */
   double *fsell, *fsell_hg;          /* [slice][j][dim][32] node-ordered element (and hourglass) forces */
   double *f_elem;                    /* [k*dim][ep]  (unfused path only) */

@@ -240,6 +240,35 @@ static int upload_mesh(wf_engine *E, int nn, int ne, const double *x, const unsi
     d.elnod = del;
     CK(cudaStreamSynchronize(E->stream));
   }
+  // element-block node tables (see WfDev::blk_off)
+  {
+    const int nblk = (ne + WF_EBLK - 1) / WF_EBLK;
+    std::vector<int> boff(nblk + 1, 0), bnodes;
+    std::vector<unsigned short> lidx((size_t)k * d.ep, 0);
+    bnodes.reserve((size_t)ne * 2);
+    std::vector<int> tmp;
+    int umax = 0;
+    for (int b = 0; b < nblk; b++) {
+      const int e0 = b * WF_EBLK, e1 = std::min(ne, e0 + WF_EBLK);
+      tmp.assign(elnod + (size_t)e0 * k, elnod + (size_t)e1 * k);
+      std::sort(tmp.begin(), tmp.end());
+      tmp.erase(std::unique(tmp.begin(), tmp.end()), tmp.end());
+      for (int e = e0; e < e1; e++)
+        for (int n = 0; n < k; n++)
+          lidx[(size_t)n * d.ep + e] =
+              (unsigned short)(std::lower_bound(tmp.begin(), tmp.end(), (int)elnod[(size_t)e * k + n]) - tmp.begin());
+      bnodes.insert(bnodes.end(), tmp.begin(), tmp.end());
+      boff[b + 1] = (int)bnodes.size();
+      umax = std::max(umax, (int)tmp.size());
+    }
+    int *doff, *dnodes; unsigned short *dl;
+    if (dalloc(E, &doff, boff.size()) || dalloc(E, &dnodes, bnodes.size()) || dalloc(E, &dl, lidx.size())) return 1;
+    CK(cudaMemcpyAsync(doff, boff.data(), boff.size() * sizeof(int), cudaMemcpyHostToDevice, E->stream));
+    CK(cudaMemcpyAsync(dnodes, bnodes.data(), bnodes.size() * sizeof(int), cudaMemcpyHostToDevice, E->stream));
+    CK(cudaMemcpyAsync(dl, lidx.data(), lidx.size() * sizeof(unsigned short), cudaMemcpyHostToDevice, E->stream));
+    CK(cudaStreamSynchronize(E->stream));
+    d.blk_off = doff; d.blk_nodes = dnodes; d.lidx = dl; d.blk_umax = umax;
+  }
   // state
   const size_t nv = (size_t)dim * d.np, e6 = (size_t)6 * d.ep;
   if (dalloc(E, &d.x, nv) || dalloc(E, &d.v, nv) || dalloc(E, &d.prev_a, nv) || dalloc(E, &d.u, nv) ||

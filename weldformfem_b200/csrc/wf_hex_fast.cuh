@@ -33,9 +33,8 @@ WF_DI void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::: "me
 // forward butterfly: q[0..7] nodal values -> G[0..2] (xi, eta, zeta modes) and optionally h[0..3]
 // (hourglass modes in the order of the reference table: eta*zeta, xi*zeta, xi*eta, xi*eta*zeta)
 template <bool WITH_HG>
-WF_DI void wht_fwd(const double *col /*stride TPB*/, double (&G)[3], double (&h)[4]) {
-  const double q0 = col[0 * TPB], q1 = col[1 * TPB], q2 = col[2 * TPB], q3 = col[3 * TPB];
-  const double q4 = col[4 * TPB], q5 = col[5 * TPB], q6 = col[6 * TPB], q7 = col[7 * TPB];
+WF_DI void wht_fwd8(double q0, double q1, double q2, double q3, double q4, double q5, double q6, double q7, double (&G)[3],
+                    double (&h)[4]) {
   const double sa = q1 + q0, da = q1 - q0, sb = q2 + q3, db = q2 - q3;
   const double sc = q5 + q4, dc = q5 - q4, sd = q6 + q7, dd = q6 - q7;
   const double ss1 = sb + sa, sd1 = sb - sa, ds1 = db + da;
@@ -50,6 +49,23 @@ WF_DI void wht_fwd(const double *col /*stride TPB*/, double (&G)[3], double (&h)
     h[2] = dd2 + dd1;
     h[3] = dd2 - dd1;
   }
+}
+// node data staged as one private column per thread: value n of a component at col[n * TPB]
+struct ColSrc {
+  const double *col;
+  WF_DI double operator()(int comp, int n) const { return col[(comp * 8 + n) * TPB]; }
+};
+// node data staged once per CTA: value of node n of this element at s[comp * stride + li[n]]
+struct StagedSrc {
+  const double *s;
+  int stride;
+  unsigned li[8];
+  WF_DI double operator()(int comp, int n) const { return s[comp * stride + li[n]]; }
+};
+template <bool WITH_HG, class Src>
+WF_DI void wht_fwd(const Src &src, int comp, double (&G)[3], double (&h)[4]) {
+  wht_fwd8<WITH_HG>(src(comp, 0), src(comp, 1), src(comp, 2), src(comp, 3), src(comp, 4), src(comp, 5), src(comp, 6),
+                    src(comp, 7), G, h);
 }
 
 // inverse butterfly: q_n = sum_r B[r] s_r(n) + sum_j c[j] Sig_j(n), stored to the node-ordered
@@ -74,6 +90,161 @@ WF_DI void wht_inv_store(const double (&B)[3], const double (&c)[4], double *__r
 // x^y for x > 0 as exp(y log x) (relative error ~1e-15; WF_FAST only)
 WF_DI double fast_pow(double x, double y) { return exp(y * log(x)); }
 
+// ---- front half: geometry, velocity gradient and hourglass modes from the staged node data ---------------
+struct HexFront {
+  double A[3][3]; // A'(c,r) = 0.125 * adj(J)(c,r)
+  double detJ;
+  double Dr[6], Wr[3];
+  double trL;     // un-normalised div v = sum_a gradN_a . v_a
+  double hm[3][4];
+};
+
+template <class Src>
+WF_DI void hex_front(const Src &src, HexFront &g) {
+  double J[3][3], dummy[4];
+#pragma unroll
+  for (int c = 0; c < 3; c++) {
+    double G[3];
+    wht_fwd<false>(src, c, G, dummy);
+    J[0][c] = 0.125 * G[0]; J[1][c] = 0.125 * G[1]; J[2][c] = 0.125 * G[2];
+  }
+  double (&A)[3][3] = g.A;
+  A[0][0] = 0.125 * (J[1][1] * J[2][2] - J[1][2] * J[2][1]);
+  A[1][0] = -0.125 * (J[1][0] * J[2][2] - J[1][2] * J[2][0]);
+  A[2][0] = 0.125 * (J[1][0] * J[2][1] - J[1][1] * J[2][0]);
+  A[0][1] = -0.125 * (J[0][1] * J[2][2] - J[0][2] * J[2][1]);
+  A[1][1] = 0.125 * (J[0][0] * J[2][2] - J[0][2] * J[2][0]);
+  A[2][1] = -0.125 * (J[0][0] * J[2][1] - J[0][1] * J[2][0]);
+  A[0][2] = 0.125 * (J[0][1] * J[1][2] - J[0][2] * J[1][1]);
+  A[1][2] = -0.125 * (J[0][0] * J[1][2] - J[0][2] * J[1][0]);
+  A[2][2] = 0.125 * (J[0][0] * J[1][1] - J[0][1] * J[1][0]);
+  // det J = sum_c J(0,c) adj(c,0)
+  g.detJ = 8.0 * (J[0][0] * A[0][0] + J[0][1] * A[1][0] + J[0][2] * A[2][0]);
+  double L[3][3];
+#pragma unroll
+  for (int i = 0; i < 3; i++) {
+    double G[3];
+    wht_fwd<true>(src, 3 + i, G, g.hm[i]);
+#pragma unroll
+    for (int c = 0; c < 3; c++) L[i][c] = A[c][0] * G[0] + A[c][1] * G[1] + A[c][2] * G[2];
+  }
+  const double f = 1.0 / g.detJ;
+  g.Dr[0] = L[0][0] * f; g.Dr[1] = L[1][1] * f; g.Dr[2] = L[2][2] * f;
+  const double hf = 0.5 * f;
+  g.Dr[3] = hf * (L[0][1] + L[1][0]); g.Dr[4] = hf * (L[1][2] + L[2][1]); g.Dr[5] = hf * (L[0][2] + L[2][0]);
+  g.Wr[0] = hf * (L[0][1] - L[1][0]); g.Wr[1] = hf * (L[1][2] - L[2][1]); g.Wr[2] = hf * (L[0][2] - L[2][0]);
+  g.trL = L[0][0] + L[1][1] + L[2][2];
+}
+
+// ---- back half: pressure, Jaumann rate + J2 radial return, element + hourglass nodal forces --------------
+// J_sum = sum of nodal_p over the 8 nodes; p_prev = stored pressure (press == 1 only); off[n] = offset of
+// (e, n) in the node-ordered force buffer
+template <class OffT>
+WF_DI void hex_back(const WfDev &d, const WfPar &P, int e, bool active, const HexFront &g, const double (&tau)[6],
+                    double pl, double rho_e, double sy, double J_sum, double p_prev, const OffT &off) {
+  const double vol = g.detJ * 8.0;
+  double p;
+  if (P.press == 0) {
+    const double J_avg = J_sum * 0.125;
+    if (P.stab_simple) {
+      double J_bar = J_avg;
+      if (J_bar < P.J_min) J_bar = 0.2;
+      p = -P.Kbulk * (J_bar - 1.0);
+    } else {
+      // J_local uses the volume stored by E1 so that vol/vol_0 is exactly 1 for an undeformed element
+      p = pressure_default3d(P, J_avg, d.vol_0[e], d.vol[e], rho_e, g.trL);
+    }
+  } else if (P.press == 1) {
+    p = (p_prev + J_sum) * (0.25 * 8);
+  } else {
+    p = J_sum * 0.125;
+  }
+
+  // CalcStressStrain, Mechanical.C:1664-1839
+  double sig[6];
+  const double (&Dr)[6] = g.Dr;
+  const double (&Wr)[3] = g.Wr;
+  const double txx = tau[0], tyy = tau[1], tzz = tau[2], txy = tau[3], tyz = tau[4], txz = tau[5];
+  const double wxy = Wr[0], wyz = Wr[1], wxz = Wr[2];
+  // SRT + RS with the reference's tensor3 operator* (Tensor3.C:290-304), zero products dropped
+  const double r_xx = 2.0 * (txy * wxy + txz * wxz);
+  // (SRT+RS)_yy and (SRT+RS)_zz cancel identically under that operator
+  const double r_xy = (txx * wxy - txz * wyz) + (wxy * tyy + wxz * tyz);
+  const double r_yz = (txy * wxz + tyy * wyz) + (wyz * tzz - wxy * txz);
+  const double r_xz = (txx * wxz + txy * wyz) + (wxy * tyz + wxz * tzz);
+  const double trD3 = (1.0 / 3.0) * (Dr[0] + Dr[1] + Dr[2]);
+  const double g2 = 2.0 * P.G, dt = P.dt;
+  double tt[6];
+  tt[0] = txx + dt * ((Dr[0] - trD3) * g2 + r_xx);
+  tt[1] = tyy + dt * ((Dr[1] - trD3) * g2);
+  tt[2] = tzz + dt * ((Dr[2] - trD3) * g2);
+  tt[3] = txy + dt * (Dr[3] * g2 + r_xy);
+  tt[4] = tyz + dt * (Dr[4] * g2 + r_yz);
+  tt[5] = txz + dt * (Dr[5] * g2 + r_xz);
+  // s = dev(-p I + tau) = tau - tr(tau)/3 I   (the -p I part cancels in the deviator)
+  const double tr3 = (1.0 / 3.0) * (tt[0] + tt[1] + tt[2]);
+  const double s0 = tt[0] - tr3, s1 = tt[1] - tr3, s2 = tt[2] - tr3;
+  const double J2 = 0.5 * (s0 * s0 + s1 * s1 + s2 * s2) + (tt[3] * tt[3] + tt[4] * tt[4] + tt[5] * tt[5]);
+  const double sig_trial = sqrt(3.0 * J2);
+  double b = 0.0;
+  bool hard = false;
+  if (P.model == 1) {
+    b = pl + P.eps0;
+    hard = b > P.eps1;
+    sy = hard ? P.Kh * fast_pow(b, P.mh) : P.sy0;
+  }
+  if (sy < sig_trial) {
+    const double H = hard ? P.mh * sy / b : 0.0; // K m b^(m-1) = m sy / b
+    const double G3 = 3.0 * P.G;
+    const double dgamma = (sig_trial - sy) / (G3 + H);
+    const double factor = 1.0 - (G3 * dgamma) / sig_trial;
+    tt[0] = s0 * factor; tt[1] = s1 * factor; tt[2] = s2 * factor;
+    tt[3] *= factor; tt[4] *= factor; tt[5] *= factor;
+    pl += dgamma;
+  }
+  sig[0] = tt[0] - p; sig[1] = tt[1] - p; sig[2] = tt[2] - p;
+  sig[3] = tt[3]; sig[4] = tt[4]; sig[5] = tt[5];
+  if (P.av_alpha != 0.0 || P.av_beta != 0.0) artificial_viscosity(P, Dr, rho_e, vol, sig);
+  if (!active) return;
+#pragma unroll
+  for (int i = 0; i < 6; i++) d.tau[(long long)i * d.ep + e] = tt[i];
+  if (P.store_sigma) {
+#pragma unroll
+    for (int i = 0; i < 6; i++) d.sigma[(long long)i * d.ep + e] = sig[i];
+  }
+  if (P.track_eps) {
+#pragma unroll
+    for (int i = 0; i < 6; i++) {
+      long long o = (long long)i * d.ep + e;
+      d.eps[o] = d.eps[o] + dt * Dr[i];
+    }
+  }
+  d.pl_strain[e] = pl;
+  d.sigma_y[e] = sy;
+  d.p[e] = p;
+
+  // element + hourglass nodal forces; symmetric sigma(c,i): (0,0)=0 (1,1)=1 (2,2)=2 (0,1)=3 (1,2)=4 (0,2)=5
+  double ch = 0.0;
+  if (P.hexa_hg != 0.0) ch = P.hexa_hg * fast_pow(vol, 0.6666666) * rho_e * 0.25 * P.cs0;
+  unsigned o8[8];
+#pragma unroll
+  for (int n = 0; n < 8; n++) o8[n] = off(n);
+  const double w = 8.0;
+#pragma unroll
+  for (int i = 0; i < 3; i++) {
+    const double sxi = (i == 0) ? sig[0] : (i == 1 ? sig[3] : sig[5]);
+    const double syi = (i == 0) ? sig[3] : (i == 1 ? sig[1] : sig[4]);
+    const double szi = (i == 0) ? sig[5] : (i == 1 ? sig[4] : sig[2]);
+    double B[3], c[4];
+#pragma unroll
+    for (int r = 0; r < 3; r++) B[r] = w * (g.A[0][r] * sxi + g.A[1][r] * syi + g.A[2][r] * szi);
+#pragma unroll
+    for (int j = 0; j < 4; j++) c[j] = ch * g.hm[i][j];
+    wht_inv_store(B, c, d.fsell, o8, i);
+  }
+}
+
+// one element per thread, one tile per CTA
 __global__ void __launch_bounds__(TPB, 4) k_elem_main_hex_fast(WfDev d, WfPar P) {
   extern __shared__ double sm[];
   const int t = threadIdx.x;
@@ -99,156 +270,208 @@ __global__ void __launch_bounds__(TPB, 4) k_elem_main_hex_fast(WfDev d, WfPar P)
   double tau[6];
 #pragma unroll
   for (int i = 0; i < 6; i++) tau[i] = d.tau[(long long)i * d.ep + e];
-  double pl = d.pl_strain[e];
+  const double pl = d.pl_strain[e];
   const double rho_e = d.rho[e];
-  double sy = d.sigma_y[e];
-  double J_avg = 0.0, p;
-  if (P.press == 1) p = d.p[e];
+  const double sy = d.sigma_y[e];
+  double J_sum = 0.0, p_prev = 0.0;
+  if (P.press == 1) p_prev = d.p[e];
 #pragma unroll
-  for (int a = 0; a < 8; a++) J_avg += d.nodal_p[nid[a]];
+  for (int a = 0; a < 8; a++) J_sum += d.nodal_p[nid[a]];
 
   cp_async_wait_all();
+  HexFront g;
+  hex_front(ColSrc{col}, g);
+  hex_back(d, P, e, active, g, tau, pl, rho_e, sy, J_sum, p_prev,
+           [&](int n) { return (unsigned)__ldg(d.pos + (long long)n * d.ep + e); });
+}
 
-  // ---- geometry ---------------------------------------------------------------------------------
-  double J[3][3], dummy[4];
+// Persistent, software-pipelined variant: every CTA walks tiles blockIdx.x, += gridDim.x.  While a tile's
+// stress update / force stores run, the node data (x, v), the force-buffer offsets of the NEXT tile are already
+// in flight (cp.async into the staging columns the front half has just drained), and the connectivity of the
+// tile after that is being loaded — the three dependent memory round trips of the one-shot kernel
+// (connectivity -> gathers -> offsets) overlap with arithmetic instead of adding up.
+constexpr int PIPE_SMEM_BYTES = SMEM_BYTES + 2 * 8 * TPB * 4;
+
+WF_DI void cp_async4(unsigned *smem_dst, const int *gsrc) {
+  unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(s), "l"(gsrc));
+}
+
+__global__ void __launch_bounds__(TPB, 4) k_elem_main_hex_pipe(WfDev d, WfPar P) {
+  extern __shared__ double sm[];
+  const int t = threadIdx.x;
+  double *col = sm + t;
+  unsigned *posbuf = reinterpret_cast<unsigned *>(sm + ITEMS * TPB) + t; // [2][8][TPB]
+  const int ntiles = (d.ne + TPB - 1) / TPB;
+  int tile = blockIdx.x;
+  if (tile >= ntiles) return;
+  const int last = d.ne - 1;
+
+  auto issue = [&](const int (&nid)[8], int e, int buf) {
 #pragma unroll
-  for (int c = 0; c < 3; c++) {
-    double G[3];
-    wht_fwd<false>(col + (c * 8) * TPB, G, dummy);
-    J[0][c] = 0.125 * G[0]; J[1][c] = 0.125 * G[1]; J[2][c] = 0.125 * G[2];
+    for (int c = 0; c < 3; c++)
+#pragma unroll
+      for (int n = 0; n < 8; n++) cp_async8(col + (c * 8 + n) * TPB, d.x + (long long)c * d.np + nid[n]);
+#pragma unroll
+    for (int c = 0; c < 3; c++)
+#pragma unroll
+      for (int n = 0; n < 8; n++) cp_async8(col + (24 + c * 8 + n) * TPB, d.v + (long long)c * d.np + nid[n]);
+#pragma unroll
+    for (int n = 0; n < 8; n++) cp_async4(posbuf + (buf * 8 + n) * TPB, d.pos + (long long)n * d.ep + e);
+    cp_async_commit();
+  };
+
+  int nid[8];
+  int e = min(tile * TPB + t, last);
+#pragma unroll
+  for (int n = 0; n < 8; n++) nid[n] = __ldg(d.elnod + (long long)n * d.ep + e);
+  issue(nid, e, 0);
+  int buf = 0;
+  for (; tile < ntiles; tile += gridDim.x, buf ^= 1) {
+    const int e0 = tile * TPB + t;
+    const bool active = e0 < d.ne;
+    e = active ? e0 : last;
+    // streaming state of this tile (consumed by the back half) and the nodal ratios of its nodes
+    double tau[6];
+#pragma unroll
+    for (int i = 0; i < 6; i++) tau[i] = d.tau[(long long)i * d.ep + e];
+    const double pl = d.pl_strain[e];
+    const double rho_e = d.rho[e];
+    const double sy = d.sigma_y[e];
+    double p_prev = 0.0;
+    if (P.press == 1) p_prev = d.p[e];
+    double jn[8];
+#pragma unroll
+    for (int a = 0; a < 8; a++) jn[a] = d.nodal_p[nid[a]];
+    // connectivity of the next tile of this CTA
+    const int tnext = tile + gridDim.x;
+    const bool more = tnext < ntiles;
+    const int en = min((more ? tnext : tile) * TPB + t, last);
+#pragma unroll
+    for (int n = 0; n < 8; n++) nid[n] = __ldg(d.elnod + (long long)n * d.ep + en);
+
+    cp_async_wait_all();
+    HexFront g;
+    hex_front(ColSrc{col}, g);
+    if (more) issue(nid, en, buf ^ 1); // staging columns are drained: refill them for the next tile
+    double J_sum = 0.0;
+#pragma unroll
+    for (int a = 0; a < 8; a++) J_sum += jn[a];
+    const unsigned *pb = posbuf + buf * 8 * TPB;
+    hex_back(d, P, e, active, g, tau, pl, rho_e, sy, J_sum, p_prev, [&](int n) { return pb[n * TPB]; });
   }
-  double A[3][3]; // A'(c,r) = 0.125 * adj(J)(c,r)
-  A[0][0] = 0.125 * (J[1][1] * J[2][2] - J[1][2] * J[2][1]);
-  A[1][0] = -0.125 * (J[1][0] * J[2][2] - J[1][2] * J[2][0]);
-  A[2][0] = 0.125 * (J[1][0] * J[2][1] - J[1][1] * J[2][0]);
-  A[0][1] = -0.125 * (J[0][1] * J[2][2] - J[0][2] * J[2][1]);
-  A[1][1] = 0.125 * (J[0][0] * J[2][2] - J[0][2] * J[2][0]);
-  A[2][1] = -0.125 * (J[0][0] * J[2][1] - J[0][1] * J[2][0]);
-  A[0][2] = 0.125 * (J[0][1] * J[1][2] - J[0][2] * J[1][1]);
-  A[1][2] = -0.125 * (J[0][0] * J[1][2] - J[0][2] * J[1][0]);
-  A[2][2] = 0.125 * (J[0][0] * J[1][1] - J[0][1] * J[1][0]);
-  // det J = sum_c J(0,c) adj(c,0)
-  const double detJ = 8.0 * (J[0][0] * A[0][0] + J[0][1] * A[1][0] + J[0][2] * A[2][0]);
-  const double vol = detJ * 8.0;
+}
 
-  // ---- velocity gradient + hourglass modes ----------------------------------------------------------
-  double L[3][3], hm[3][4];
+
+
+// Block-staged variant: the CTA loads the data of its UNIQUE nodes (x, v, nodal ratio: 7 doubles per node) into
+// shared memory once, coalesced along the ascending node list, instead of every element gathering its eight
+// nodes separately (a structured 128-element tile has ~520 unique nodes for 1024 element-nodes).  Element-nodes
+// are addressed by 16-bit block-local indices (WfDev::lidx).
+__global__ void __launch_bounds__(TPB, 4) k_elem_main_hex_staged(WfDev d, WfPar P, int stride) {
+  extern __shared__ double sm[];
+  const int t = threadIdx.x;
+  const int b = blockIdx.x;
+  const int u0 = __ldg(d.blk_off + b), U = __ldg(d.blk_off + b + 1) - u0;
+  for (int i = t; i < U; i += TPB) {
+    const int g = __ldg(d.blk_nodes + u0 + i);
 #pragma unroll
-  for (int i = 0; i < 3; i++) {
-    double G[3];
-    wht_fwd<true>(col + (24 + i * 8) * TPB, G, hm[i]);
+    for (int c = 0; c < 3; c++) cp_async8(sm + c * stride + i, d.x + (long long)c * d.np + g);
 #pragma unroll
-    for (int c = 0; c < 3; c++) L[i][c] = A[c][0] * G[0] + A[c][1] * G[1] + A[c][2] * G[2];
+    for (int c = 0; c < 3; c++) cp_async8(sm + (3 + c) * stride + i, d.v + (long long)c * d.np + g);
+    cp_async8(sm + 6 * stride + i, d.nodal_p + g);
   }
-  const double f = 1.0 / detJ;
-  double Dr[6], Wr[3];
-  Dr[0] = L[0][0] * f; Dr[1] = L[1][1] * f; Dr[2] = L[2][2] * f;
-  const double hf = 0.5 * f;
-  Dr[3] = hf * (L[0][1] + L[1][0]); Dr[4] = hf * (L[1][2] + L[2][1]); Dr[5] = hf * (L[0][2] + L[2][0]);
-  Wr[0] = hf * (L[0][1] - L[1][0]); Wr[1] = hf * (L[1][2] - L[2][1]); Wr[2] = hf * (L[0][2] - L[2][0]);
-
-  // ---- pressure ---------------------------------------------------------------------------------------
-  if (P.press == 0) {
-    J_avg *= 0.125;
-    if (P.stab_simple) {
-      double J_bar = J_avg;
-      if (J_bar < P.J_min) J_bar = 0.2;
-      p = -P.Kbulk * (J_bar - 1.0);
-    } else {
-      // div_v = sum_a gradN_a . v_a = trace of the un-normalised velocity gradient
-      // J_local uses the volume stored by E1 so that vol/vol_0 is exactly 1 for an undeformed element
-      p = pressure_default3d(P, J_avg, d.vol_0[e], d.vol[e], rho_e, L[0][0] + L[1][1] + L[2][2]);
-    }
-  } else if (P.press == 1) {
-    p = (p + J_avg) * (0.25 * 8);
-  } else {
-    p = J_avg * 0.125;
-  }
-
-  // ---- Jaumann rate + J2 radial return (CalcStressStrain, Mechanical.C:1664-1839) ------------------
-  double sig[6];
-  {
-    const double txx = tau[0], tyy = tau[1], tzz = tau[2], txy = tau[3], tyz = tau[4], txz = tau[5];
-    const double wxy = Wr[0], wyz = Wr[1], wxz = Wr[2];
-    // SRT + RS with the reference's tensor3 operator* (Tensor3.C:290-304), zero products dropped
-    const double r_xx = 2.0 * (txy * wxy + txz * wxz);
-    // (SRT+RS)_yy and (SRT+RS)_zz cancel identically under that operator
-    const double r_xy = (txx * wxy - txz * wyz) + (wxy * tyy + wxz * tyz);
-    const double r_yz = (txy * wxz + tyy * wyz) + (wyz * tzz - wxy * txz);
-    const double r_xz = (txx * wxz + txy * wyz) + (wxy * tyz + wxz * tzz);
-    const double trD3 = (1.0 / 3.0) * (Dr[0] + Dr[1] + Dr[2]);
-    const double g2 = 2.0 * P.G, dt = P.dt;
-    double tt[6];
-    tt[0] = txx + dt * ((Dr[0] - trD3) * g2 + r_xx);
-    tt[1] = tyy + dt * ((Dr[1] - trD3) * g2);
-    tt[2] = tzz + dt * ((Dr[2] - trD3) * g2);
-    tt[3] = txy + dt * (Dr[3] * g2 + r_xy);
-    tt[4] = tyz + dt * (Dr[4] * g2 + r_yz);
-    tt[5] = txz + dt * (Dr[5] * g2 + r_xz);
-    // s = dev(-p I + tau) = tau - tr(tau)/3 I   (the -p I part cancels in the deviator)
-    const double tr3 = (1.0 / 3.0) * (tt[0] + tt[1] + tt[2]);
-    const double s0 = tt[0] - tr3, s1 = tt[1] - tr3, s2 = tt[2] - tr3;
-    const double J2 = 0.5 * (s0 * s0 + s1 * s1 + s2 * s2) + (tt[3] * tt[3] + tt[4] * tt[4] + tt[5] * tt[5]);
-    const double sig_trial = sqrt(3.0 * J2);
-    double b = 0.0;
-    bool hard = false;
-    if (P.model == 1) {
-      b = pl + P.eps0;
-      hard = b > P.eps1;
-      sy = hard ? P.Kh * fast_pow(b, P.mh) : P.sy0;
-    }
-    if (sy < sig_trial) {
-      const double H = hard ? P.mh * sy / b : 0.0; // K m b^(m-1) = m sy / b
-      const double G3 = 3.0 * P.G;
-      const double dgamma = (sig_trial - sy) / (G3 + H);
-      const double factor = 1.0 - (G3 * dgamma) / sig_trial;
-      tt[0] = s0 * factor; tt[1] = s1 * factor; tt[2] = s2 * factor;
-      tt[3] *= factor; tt[4] *= factor; tt[5] *= factor;
-      pl += dgamma;
-    }
-    sig[0] = tt[0] - p; sig[1] = tt[1] - p; sig[2] = tt[2] - p;
-    sig[3] = tt[3]; sig[4] = tt[4]; sig[5] = tt[5];
-    if (P.av_alpha != 0.0 || P.av_beta != 0.0) artificial_viscosity(P, Dr, rho_e, vol, sig);
-    if (active) {
+  cp_async_commit();
+  const int e0 = b * TPB + t;
+  const bool active = e0 < d.ne;
+  const int e = active ? e0 : d.ne - 1;
+  StagedSrc src;
+  src.s = sm; src.stride = stride;
 #pragma unroll
-      for (int i = 0; i < 6; i++) d.tau[(long long)i * d.ep + e] = tt[i];
-      if (P.store_sigma) {
-#pragma unroll
-        for (int i = 0; i < 6; i++) d.sigma[(long long)i * d.ep + e] = sig[i];
-      }
-      if (P.track_eps) {
-#pragma unroll
-        for (int i = 0; i < 6; i++) {
-          long long o = (long long)i * d.ep + e;
-          d.eps[o] = d.eps[o] + dt * Dr[i];
-        }
-      }
-      d.pl_strain[e] = pl;
-      d.sigma_y[e] = sy;
-      d.p[e] = p;
-    }
-  }
-
-  // ---- element + hourglass nodal forces ----------------------------------------------------------------
-  // symmetric sigma(c,i): (0,0)=0 (1,1)=1 (2,2)=2 (0,1)=3 (1,2)=4 (0,2)=5
-  double ch = 0.0;
-  if (P.hexa_hg != 0.0) ch = P.hexa_hg * fast_pow(vol, 0.6666666) * rho_e * 0.25 * P.cs0;
-  if (!active) return;
+  for (int n = 0; n < 8; n++) src.li[n] = d.lidx[(long long)n * d.ep + e];
   unsigned off[8];
 #pragma unroll
   for (int n = 0; n < 8; n++) off[n] = (unsigned)__ldg(d.pos + (long long)n * d.ep + e);
-  const double w = 8.0;
+  double tau[6];
 #pragma unroll
-  for (int i = 0; i < 3; i++) {
-    const double sxi = (i == 0) ? sig[0] : (i == 1 ? sig[3] : sig[5]);
-    const double syi = (i == 0) ? sig[3] : (i == 1 ? sig[1] : sig[4]);
-    const double szi = (i == 0) ? sig[5] : (i == 1 ? sig[4] : sig[2]);
-    double B[3], c[4];
+  for (int i = 0; i < 6; i++) tau[i] = d.tau[(long long)i * d.ep + e];
+  const double pl = d.pl_strain[e];
+  const double rho_e = d.rho[e];
+  const double sy = d.sigma_y[e];
+  double p_prev = 0.0;
+  if (P.press == 1) p_prev = d.p[e];
+  cp_async_wait_all();
+  __syncthreads();
+  HexFront g;
+  hex_front(src, g);
+  double J_sum = 0.0;
 #pragma unroll
-    for (int r = 0; r < 3; r++) B[r] = w * (A[0][r] * sxi + A[1][r] * syi + A[2][r] * szi);
+  for (int a = 0; a < 8; a++) J_sum += sm[6 * stride + src.li[a]];
+  hex_back(d, P, e, active, g, tau, pl, rho_e, sy, J_sum, p_prev, [&](int n) { return off[n]; });
+}
+
+// ---- memory skeleton of the hexa main pass (tuning aid only: same loads / stores, trivial arithmetic, results are
+// garbage).  MODE bit0: force records scattered through pos (1) or stored element-ordered (0); bit1: node data
+// staged with cp.async (1) or loaded straight to registers (0); bit2: skip the x/v gathers; bit3: skip force stores.
+template <int MODE>
+__global__ void __launch_bounds__(TPB, 4) k_elem_main_hex_skel(WfDev d, WfPar P) {
+  extern __shared__ double sm[];
+  const int t = threadIdx.x;
+  const int e0 = blockIdx.x * TPB + t;
+  if (e0 >= d.ne) return;
+  const int e = e0;
+  double *col = sm + t;
+  int nid[8];
 #pragma unroll
-    for (int j = 0; j < 4; j++) c[j] = ch * hm[i][j];
-    wht_inv_store(B, c, d.fsell, off, i);
+  for (int n = 0; n < 8; n++) nid[n] = __ldg(d.elnod + (long long)n * d.ep + e);
+  double acc = 0.0;
+  if (!(MODE & 4)) {
+    if (MODE & 2) {
+#pragma unroll
+      for (int c = 0; c < 3; c++)
+#pragma unroll
+        for (int n = 0; n < 8; n++) cp_async8(col + (c * 8 + n) * TPB, d.x + (long long)c * d.np + nid[n]);
+#pragma unroll
+      for (int c = 0; c < 3; c++)
+#pragma unroll
+        for (int n = 0; n < 8; n++) cp_async8(col + (24 + c * 8 + n) * TPB, d.v + (long long)c * d.np + nid[n]);
+      cp_async_commit();
+    } else {
+#pragma unroll
+      for (int c = 0; c < 3; c++)
+#pragma unroll
+        for (int n = 0; n < 8; n++) acc += d.x[(long long)c * d.np + nid[n]] + d.v[(long long)c * d.np + nid[n]];
+    }
+  }
+  double tau[6];
+#pragma unroll
+  for (int i = 0; i < 6; i++) tau[i] = d.tau[(long long)i * d.ep + e];
+  acc += d.pl_strain[e] + d.rho[e] + d.sigma_y[e];
+#pragma unroll
+  for (int a = 0; a < 8; a++) acc += d.nodal_p[nid[a]];
+  if ((MODE & 2) && !(MODE & 4)) {
+    cp_async_wait_all();
+#pragma unroll
+    for (int i = 0; i < ITEMS; i++) acc += col[i * TPB];
+  }
+#pragma unroll
+  for (int i = 0; i < 6; i++) d.tau[(long long)i * d.ep + e] = tau[i] + acc;
+  d.pl_strain[e] = acc;
+  d.sigma_y[e] = acc + 1.0;
+  d.p[e] = acc + 2.0;
+  if (MODE & 8) return;
+  if (MODE & 1) {
+#pragma unroll
+    for (int n = 0; n < 8; n++) {
+      const long long o = (long long)(unsigned)__ldg(d.pos + (long long)n * d.ep + e);
+#pragma unroll
+      for (int c = 0; c < 3; c++) d.fsell[o + 32 * c] = acc + n + c;
+    }
+  } else {
+#pragma unroll
+    for (int n = 0; n < 8; n++)
+#pragma unroll
+      for (int c = 0; c < 3; c++) d.fsell[(long long)(n * 3 + c) * d.ep + e] = acc + n + c;
   }
 }
 

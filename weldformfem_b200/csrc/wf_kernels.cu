@@ -118,6 +118,37 @@ __global__ void __launch_bounds__(TPB_E) k_elem_vol(WfDev d, WfPar P, int store_
   d.vol[e] = elem_volume<ET>(detJ, radius, d.domtype, d.vol_weight);
 }
 
+// E1 with the CTA's unique nodes staged once in shared memory (WfDev::blk_off / lidx)
+template <int ET>
+__global__ void __launch_bounds__(WF_EBLK) k_elem_vol_staged(WfDev d, WfPar P, int stride) {
+  constexpr int K = Elem<ET>::K, D = Elem<ET>::D;
+  extern __shared__ double sm[];
+  const int t = threadIdx.x, b = blockIdx.x;
+  const int u0 = __ldg(d.blk_off + b), U = __ldg(d.blk_off + b + 1) - u0;
+  for (int i = t; i < U; i += WF_EBLK) {
+    const int g = __ldg(d.blk_nodes + u0 + i);
+#pragma unroll
+    for (int c = 0; c < D; c++) sm[c * stride + i] = d.x[(long long)c * d.np + g];
+  }
+  const int e = b * WF_EBLK + t;
+  unsigned li[K];
+  if (e < d.ne) {
+#pragma unroll
+    for (int n = 0; n < K; n++) li[n] = d.lidx[(long long)n * d.ep + e];
+  }
+  __syncthreads();
+  if (e >= d.ne) return;
+  double xl[K][D], A[D][D], detJ;
+#pragma unroll
+  for (int n = 0; n < K; n++)
+#pragma unroll
+    for (int c = 0; c < D; c++) xl[n][c] = sm[c * stride + li[n]];
+  jac_adj_det<ET>(xl, A, detJ);
+  double radius = 0.0;
+  if (D == 2 && d.domtype == 2) radius = elem_radius<ET>(xl);
+  d.vol[e] = elem_volume<ET>(detJ, radius, d.domtype, d.vol_weight);
+}
+
 // CalcElemVol on stored detJ / radius (unfused)
 template <int ET>
 __global__ void k_vol_from_detj(WfDev d) {
@@ -145,13 +176,20 @@ __global__ void __launch_bounds__(TPB_N) k_node_vol(WfDev d, WfPar P, int mode) 
   double s = 0.0, sq = 0.0;
   const double *src = (mode == 0) ? d.vol_0 : d.vol;
   const bool quarter = (P.press == 3);
-  for (int j = 0; j < width; j++) {
-    int slot = __ldg(d.sell_slots + base + ((long long)j << 5) + lane);
-    if (slot >= 0) {
-      double ve = src[slot / K];
-      s += ve;
-      if (quarter) sq += ve / 4.0;
-    }
+  // eight list entries per trip: the slot loads, then the volume gathers, are independent and in flight together
+  for (int j0 = 0; j0 < width; j0 += 8) {
+    int sl[8];
+    double ve[8];
+#pragma unroll
+    for (int q = 0; q < 8; q++) sl[q] = (j0 + q < width) ? __ldg(d.sell_slots + base + ((long long)(j0 + q) << 5) + lane) : -1;
+#pragma unroll
+    for (int q = 0; q < 8; q++) ve[q] = (sl[q] >= 0) ? src[sl[q] / K] : 0.0;
+#pragma unroll
+    for (int q = 0; q < 8; q++)
+      if (sl[q] >= 0) {
+        s += ve[q];
+        if (quarter) sq += ve[q] / 4.0;
+      }
   }
   if (n >= d.nn) return;
   if (mode == 0) {
@@ -912,6 +950,11 @@ static void l_impose_bc(const WfDev &d, int dim, int is_acc, double *arr, cudaSt
   k_impose_bc<<<cdiv(d.nn, 256), 256, 0, s>>>(d, dim, is_acc, arr);
 }
 static void l_elem_vol(const WfDev &d, const WfPar &P, int et, int store_jac, cudaStream_t s) {
+  if (!store_jac && P.variant[0] == 1) {
+    const int stride = (d.blk_umax + 31) / 32 * 32;
+    ELEM_DISPATCH(et, k_elem_vol_staged<ET><<<cdiv(d.ne, WF_EBLK), WF_EBLK, Elem<ET>::D * stride * 8, s>>>(d, P, stride));
+    return;
+  }
   ELEM_DISPATCH(et, k_elem_vol<ET><<<cdiv(d.ne, TPB_E), TPB_E, 0, s>>>(d, P, store_jac));
 }
 static void l_vol_from_detj(const WfDev &d, int et, cudaStream_t s) {
@@ -927,6 +970,31 @@ static void l_node_vol(const WfDev &d, const WfPar &P, int mode, cudaStream_t s)
 }
 static void l_elem_main(const WfDev &d, const WfPar &P, int et, int separate_hg, cudaStream_t s) {
   if (!separate_hg && et == ET_HEX8 && !P.strict && P.variant[2] != 1) {
+    if (P.variant[2] >= 100) { // memory skeletons (tuning aid, garbage results)
+      const int g = cdiv(d.ne, hexfast::TPB);
+      switch (P.variant[2] - 100) {
+#define WF_SKEL(M) case M: cudaFuncSetAttribute(hexfast::k_elem_main_hex_skel<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, hexfast::SMEM_BYTES); \
+                   hexfast::k_elem_main_hex_skel<M><<<g, hexfast::TPB, (M & 2) ? hexfast::SMEM_BYTES : 0, s>>>(d, P); break;
+        WF_SKEL(0) WF_SKEL(1) WF_SKEL(2) WF_SKEL(3) WF_SKEL(4) WF_SKEL(5) WF_SKEL(8) WF_SKEL(10) WF_SKEL(12)
+#undef WF_SKEL
+        default: break;
+      }
+      return;
+    }
+    if (P.variant[2] == 0) { // default: unique nodes of the CTA staged once in shared memory
+      const int stride = (d.blk_umax + 31) / 32 * 32;
+      hexfast::k_elem_main_hex_staged<<<cdiv(d.ne, hexfast::TPB), hexfast::TPB, 7 * stride * 8, s>>>(d, P, stride);
+      return;
+    }
+    if (P.variant[2] >= 2 && P.variant[2] <= 4) { // persistent pipelined variant; variant = CTAs per SM
+      static int sms = 0;
+      if (!sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); }
+      const int per_sm = P.variant[2];
+      const int g = min(cdiv(d.ne, hexfast::TPB), sms * per_sm);
+      hexfast::k_elem_main_hex_pipe<<<g, hexfast::TPB, hexfast::PIPE_SMEM_BYTES, s>>>(d, P);
+      return;
+    }
+    // variant 1 is the strict-order generic kernel (below); anything else: per-thread cp.async columns
     hexfast::k_elem_main_hex_fast<<<cdiv(d.ne, hexfast::TPB), hexfast::TPB, hexfast::SMEM_BYTES, s>>>(d, P);
     return;
   }
@@ -1031,6 +1099,9 @@ static void touch(F *f) {
 }
 static void l_preload(int et, int dim, int k) {
   (void)k;
+  // staged hexa kernel: up to 7 arrays x (128 elements x 8 nodes) doubles of shared memory
+  cudaFuncSetAttribute(hexfast::k_elem_main_hex_staged, cudaFuncAttributeMaxDynamicSharedMemorySize, 7 * 1024 * 8);
+  touch(hexfast::k_elem_main_hex_staged);
   touch(k_predict<2>); touch(k_predict<3>); touch(k_impose_bc);
   ELEM_DISPATCH(et, touch(k_elem_vol<ET>); touch(k_elem_main<ET, true>); touch(k_elem_main<ET, false>));
   touch(k_node_vol<8>); touch(k_node_vol<4>); touch(k_node_vol<3>);
@@ -1038,6 +1109,9 @@ static void l_preload(int et, int dim, int k) {
   cudaFuncSetAttribute(hexfast::k_elem_main_hex_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, hexfast::SMEM_BYTES);
   cudaFuncSetAttribute(hexfast::k_elem_main_hex_fast, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
   touch(hexfast::k_elem_main_hex_fast);
+  cudaFuncSetAttribute(hexfast::k_elem_main_hex_pipe, cudaFuncAttributeMaxDynamicSharedMemorySize, hexfast::PIPE_SMEM_BYTES);
+  cudaFuncSetAttribute(hexfast::k_elem_main_hex_pipe, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+  touch(hexfast::k_elem_main_hex_pipe);
   touch(k_node_update<3, true, 4>); touch(k_node_update<3, false, 4>); touch(k_node_update<3, false, 2>); touch(k_node_update<3, false, 8>);
   touch(k_node_update<2, true, 4>); touch(k_node_update<2, false, 4>); touch(k_node_update<2, false, 2>); touch(k_node_update<2, false, 8>);
   touch(k_halo_send<0>); touch(k_halo_send<1>); touch(k_halo_send<2>); touch(k_halo_wait);
