@@ -101,6 +101,10 @@ int wf_step(wf_engine *, int nsteps); /* fused rows 1-22 of the step, Solver_exp
 int wf_nonfinite_flag(wf_engine *, int *flag);
 int wf_energies(wf_engine *, double *Ekin, double *dEint); /* computeEnergies, Mechanical.C:2145 */
 int wf_get_time(wf_engine *, double *time, long *step_count);
+/* step monitor that does not drain the stream: enqueue {kinetic energy, non-finite flag} -> pinned host memory;
+ * wf_monitor_wait returns the oldest pending result (at most two pending) */
+int wf_monitor_async(wf_engine *);
+int wf_monitor_wait(wf_engine *, double *Ekin, int *nonfinite);
 /* profiling / tuning hooks (no reference counterpart): wf_step with CUDA events around every launch,
  * ms[0..4] += device time of predictor, E1 (element volume), N1 (nodal sums), E2 (main element pass),
  * N2 (assembly + integration); and selection of an alternative implementation of one of the four kernels */

@@ -23,7 +23,7 @@ PORT_SO = os.path.join(HERE, "_build", "libwf_oracle.so")
 
 _DBL = ("x v a u u_dt prev_a m_fi m_fe m_mdiag m_voln p_node m_dH_detJ_dx m_dH_detJ_dy m_dH_detJ_dz "
         "m_detJ vol vol_0 rho rho_0 p pl_strain sigma_y m_radius m_str_rate m_rot_rate m_sigma m_tau "
-        "m_eps m_f_elem m_f_elem_hg m_hg_q m_voln_0 m_Jn").split()
+        "m_eps m_f_elem m_f_elem_hg m_hg_q m_voln_0 m_Jn bcx_val bcy_val bcz_val").split()
 _INT = "m_nodel m_nodel_loc m_nodel_offset m_nodel_count".split()
 _UINT = ["m_elnod"]
 

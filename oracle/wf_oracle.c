@@ -942,6 +942,9 @@ static view_t view(wfo_domain *d, const char *nm) {
   V("m_tau", d->m_tau, 6 * ne) V("m_eps", d->m_eps, 6 * ne)
   V("m_f_elem", d->m_f_elem, nk * d->dim) V("m_f_elem_hg", d->m_f_elem_hg, nk * d->dim)
   V("m_hg_q", d->dim == 2 ? d->m_hg_q : NULL, d->dim == 2 ? nk * d->dim : 0)
+  V("bcx_val", d->bc_val[0], sizeof(double) * (size_t)d->bc_count[0]) /* Domain_d.h:901 */
+  V("bcy_val", d->bc_val[1], sizeof(double) * (size_t)d->bc_count[1])
+  V("bcz_val", d->bc_val[2], sizeof(double) * (size_t)d->bc_count[2])
   V("m_elnod", d->m_elnod, sizeof(unsigned) * (size_t)d->ne * d->k)
   V("m_nodel", d->m_nodel, sizeof(int) * (size_t)d->nodel_tot)
   V("m_nodel_loc", d->m_nodel_loc, sizeof(int) * (size_t)d->nodel_tot)

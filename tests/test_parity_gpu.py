@@ -177,3 +177,26 @@ def test_deterministic_repeat():
         outs.append((e.get("x"), e.get("m_tau"), e.get("m_fi")))
     for a, b in zip(*outs):
         assert np.array_equal(a, b)
+
+
+def test_time_dependent_bc_values_and_async_monitor(oracle_port):
+    """wf_set_bc_values == rewriting bcz_val between steps (Domain_d.h:901); wf_monitor_async/wait returns the
+    kinetic energy of computeEnergies (Mechanical.C:2145) for the step it was enqueued after."""
+    case = SMALL["hex"]
+    eng, ref = run_pair(case, oracle_port, 5, False)
+    _, dims, vals = case.bc_arrays()
+    vz = vals[dims == 2]
+    for i in range(6):
+        newv = vz * (1.0 + 0.1 * (i + 1))
+        eng.set_bc_values(2, newv)
+        ref.set("bcz_val", newv)
+        eng.step(1)
+        ref.step(1)
+        eng.monitor_async()
+        if i >= 1:
+            ek_prev, bad = eng.monitor_wait()
+            assert not bad and abs(ek_prev - ek_ref_prev) <= 1e-9 * abs(ek_ref_prev)
+        ek_ref_prev = ref.energies()[0]
+    ek, bad = eng.monitor_wait()
+    assert not bad and abs(ek - ek_ref_prev) <= 1e-9 * abs(ek_ref_prev)
+    compare(eng, ref, STATE, 1e-9, "time-dependent BC values")

@@ -53,6 +53,14 @@ struct wf_engine {
   cudaEvent_t bc_ev[2] = {nullptr, nullptr};
   int bc_stage_cur = 0;
   double *bc_vals_d = nullptr;
+  std::vector<double> bc_master;           // host copy of bc_vals
+  int bc_version[3] = {0, 0, 0}, bc_stage_version[2][3] = {{0, 0, 0}, {0, 0, 0}};
+  // asynchronous step monitor (wf_monitor_async / wf_monitor_wait): 2-deep ring of pinned results
+  struct MonSlot { double ekin; double pad; int nonfinite; int halo_error; };
+  MonSlot *mon_host = nullptr;
+  double *mon_red = nullptr;               // [2][2] device partial sums
+  cudaEvent_t mon_ev[2] = {nullptr, nullptr};
+  int mon_head = 0, mon_pending = 0;
   // partition / halo (multi-GPU); see wf_set_mesh_partition
   bool distributed = false, own_stream = false;
   int rank = 0, nranks = 1;
@@ -80,6 +88,7 @@ struct wf_engine {
 #define FAIL(msg) do { E->err = (msg); return 1; } while (0)
 #define NEED(cond, msg) do { if (!(cond)) FAIL(msg); } while (0)
 
+static int check_launch(wf_engine *E, const char *what);
 static inline long long round_up(long long a, long long b) { return (a + b - 1) / b * b; }
 
 template <class T>
@@ -148,6 +157,9 @@ extern "C" void wf_destroy(wf_engine *E) {
     if (E->bc_stage[b]) cudaFreeHost(E->bc_stage[b]);
     if (E->bc_ev[b]) cudaEventDestroy(E->bc_ev[b]);
   }
+  if (E->mon_host) cudaFreeHost(E->mon_host);
+  for (int b = 0; b < 2; b++)
+    if (E->mon_ev[b]) cudaEventDestroy(E->mon_ev[b]);
   for (void *p : E->ipc_opened) cudaIpcCloseMemHandle(p);
   for (void *p : E->allocs) cudaFree(p);
   if (E->own_stream) cudaStreamDestroy(E->stream);
@@ -448,7 +460,9 @@ extern "C" int wf_allocate_bcs(wf_engine *E) {
       memcpy(E->bc_stage[b], vals.data(), vals.size() * sizeof(double));
     }
     if (!E->bc_ev[b]) CK(cudaEventCreateWithFlags(&E->bc_ev[b], cudaEventDisableTiming));
+    for (int dd = 0; dd < 3; dd++) E->bc_stage_version[b][dd] = 0;
   }
+  for (int dd = 0; dd < 3; dd++) E->bc_version[dd] = 0;
   E->bcs_ready = true;
   return 0;
 }
@@ -459,20 +473,63 @@ extern "C" int wf_allocate_bcs(wf_engine *E) {
 extern "C" int wf_set_bc_values(wf_engine *E, int dim, int count, const double *vals) {
   NEED(E->bcs_ready, "wf_set_bc_values needs wf_allocate_bcs");
   NEED(dim >= 0 && dim < E->dim, "bad BC dim");
-  NEED(count == (int)E->bc_slot[dim].size() || (count == 0 && E->bc_slot[dim].empty()), "count must equal the number of BCs of this dimension");
+  NEED(count == (int)E->bc_slot[dim].size(), "count must equal the number of BCs of this dimension");
   if (E->nbc_rows == 0 || count == 0) return 0;
   CK(cudaSetDevice(E->device));
+  for (int i = 0; i < count; i++) E->bc_val[dim][i] = vals[i];
+  E->bc_version[dim]++;
   const int b = E->bc_stage_cur;
   CK(cudaEventSynchronize(E->bc_ev[b])); // the copy that last used this staging buffer has finished
   double *st = E->bc_stage[b];
-  if (st != E->bc_stage[b ^ 1]) memcpy(st, E->bc_stage[b ^ 1], (size_t)3 * E->nbc_rows * sizeof(double));
-  const std::vector<int> &slot = E->bc_slot[dim];
-  for (int i = 0; i < count; i++)
-    if (slot[i] >= 0) st[slot[i]] = vals[i];
-  for (int i = 0; i < count; i++) E->bc_val[dim][i] = vals[i];
+  for (int dd = 0; dd < E->dim; dd++) {   // bring this staging buffer up to date (only dimensions that changed)
+    if (E->bc_stage_version[b][dd] == E->bc_version[dd]) continue;
+    const std::vector<int> &slot = E->bc_slot[dd];
+    const std::vector<double> &v = E->bc_val[dd];
+    for (size_t i = 0; i < slot.size(); i++)
+      if (slot[i] >= 0) st[slot[i]] = v[i];
+    E->bc_stage_version[b][dd] = E->bc_version[dd];
+  }
   CK(cudaMemcpyAsync(E->bc_vals_d, st, (size_t)3 * E->nbc_rows * sizeof(double), cudaMemcpyHostToDevice, E->stream));
   CK(cudaEventRecord(E->bc_ev[b], E->stream));
   E->bc_stage_cur ^= 1;
+  return 0;
+}
+
+// Step monitor without draining the stream: wf_monitor_async enqueues the kinetic-energy reduction
+// (computeEnergies, Mechanical.C:2145) and a copy of {Ekin, non-finite flag (Solver_explicit.C:779), halo error}
+// into pinned host memory; wf_monitor_wait returns the OLDEST pending result.  Up to two may be pending, so a
+// host loop can read step i's monitor while step i+1 is already running.
+extern "C" int wf_monitor_async(wf_engine *E) {
+  NEED(E->inited, "wf_monitor_async before wf_init");
+  NEED(E->mon_pending < 2, "two monitors already pending: call wf_monitor_wait");
+  CK(cudaSetDevice(E->device));
+  const int b = (E->mon_head + E->mon_pending) & 1;
+  WfDev d2 = E->d;
+  d2.ne = 0;                       // kinetic part only
+  d2.red = E->mon_red + 8 * b;
+  CK(cudaMemsetAsync(d2.red, 0, 2 * sizeof(double), E->stream));
+  E->L->energy(d2, nullptr, E->stream);
+  wf_engine::MonSlot *h = E->mon_host + b;
+  CK(cudaMemcpyAsync(&h->ekin, d2.red, sizeof(double), cudaMemcpyDeviceToHost, E->stream));
+  CK(cudaMemcpyAsync(&h->nonfinite, E->d.nonfinite, sizeof(int), cudaMemcpyDeviceToHost, E->stream));
+  if (E->distributed) CK(cudaMemcpyAsync(&h->halo_error, E->d.comm_error, sizeof(int), cudaMemcpyDeviceToHost, E->stream));
+  else h->halo_error = 0;
+  CK(cudaEventRecord(E->mon_ev[b], E->stream));
+  E->mon_pending++;
+  return check_launch(E, "wf_monitor_async");
+}
+
+extern "C" int wf_monitor_wait(wf_engine *E, double *Ekin, int *nonfinite) {
+  NEED(E->mon_pending > 0, "no monitor pending");
+  CK(cudaSetDevice(E->device));
+  const int b = E->mon_head;
+  CK(cudaEventSynchronize(E->mon_ev[b]));
+  const wf_engine::MonSlot h = E->mon_host[b];
+  E->mon_head ^= 1;
+  E->mon_pending--;
+  if (Ekin) *Ekin = h.ekin;
+  if (nonfinite) *nonfinite = h.nonfinite;
+  if (h.halo_error) FAIL("halo exchange timed out waiting for neighbour index " + std::to_string(h.halo_error - 1));
   return 0;
 }
 
@@ -580,6 +637,11 @@ static int init_prologue(wf_engine *E) {
     if (P.track_eps && !d.eps && dalloc(E, &d.eps, e6)) return 1;
     if (P.store_sigma && !d.sigma && dalloc(E, &d.sigma, e6)) return 1;
     if (E->strict && !d.fsell_hg && dalloc(E, &d.fsell_hg, (size_t)E->dim * E->sell_total)) return 1;
+  }
+  if (!E->mon_host) { // pinned result ring of wf_monitor_async (page pinning can take milliseconds: do it here)
+    CK(cudaMallocHost((void **)&E->mon_host, 2 * sizeof(wf_engine::MonSlot)));
+    if (dalloc(E, &E->mon_red, 16)) return 1;
+    for (int b = 0; b < 2; b++) CK(cudaEventCreateWithFlags(&E->mon_ev[b], cudaEventDisableTiming));
   }
   E->L->preload(E->et, E->dim, E->k);
   CK(cudaStreamSynchronize(E->stream));

@@ -585,7 +585,20 @@ __global__ void k_rebuild_sigma(WfDev d, double *out) {
   for (int i = 0; i < 6; i++) out[(long long)i * d.ep + e] = mp * (i < 3 ? 1. : 0.) + d.tau[(long long)i * d.ep + e];
 }
 
-// computeEnergies (Mechanical.C:2145-2185): block-reduced, then atomics in double (diagnostic only)
+// sum over the CTA (blockDim.x a multiple of 32, <= 1024); result valid in thread 0
+WF_DI double block_sum(double k) {
+  __shared__ double part[32];
+  for (int o = 16; o > 0; o >>= 1) k += __shfl_down_sync(0xffffffffu, k, o);
+  if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = k;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    k = (threadIdx.x < (blockDim.x >> 5)) ? part[threadIdx.x] : 0.0;
+    for (int o = 16; o > 0; o >>= 1) k += __shfl_down_sync(0xffffffffu, k, o);
+  }
+  return k;
+}
+
+// computeEnergies (Mechanical.C:2145-2185): block-reduced, then one double atomic per CTA (diagnostic only)
 template <int D>
 __global__ void k_energy_kin(WfDev d) {
   int n = blockIdx.x * blockDim.x + threadIdx.x;
@@ -596,8 +609,8 @@ __global__ void k_energy_kin(WfDev d) {
     for (int c = 0; c < D; c++) { double vv = d.v[(long long)c * d.np + n]; s += vv * vv; }
     k = 0.5 * d.mdiag[n] * s;
   }
-  for (int o = 16; o > 0; o >>= 1) k += __shfl_down_sync(0xffffffffu, k, o);
-  if ((threadIdx.x & 31) == 0 && k != 0.0) atomicAdd(d.red + 0, k);
+  k = block_sum(k);
+  if (threadIdx.x == 0 && k != 0.0) atomicAdd(d.red + 0, k);
 }
 __global__ void k_energy_int(WfDev d, const double *sig) {
   int e = blockIdx.x * blockDim.x + threadIdx.x;
@@ -608,8 +621,8 @@ __global__ void k_energy_int(WfDev d, const double *sig) {
     for (int i = 0; i < 6; i++) s += sig[(long long)i * d.ep + e] * d.str_rate[(long long)i * d.ep + e];
     k = s * d.vol[e];
   }
-  for (int o = 16; o > 0; o >>= 1) k += __shfl_down_sync(0xffffffffu, k, o);
-  if ((threadIdx.x & 31) == 0 && k != 0.0) atomicAdd(d.red + 1, k);
+  k = block_sum(k);
+  if (threadIdx.x == 0 && k != 0.0) atomicAdd(d.red + 1, k);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1116,7 +1129,7 @@ static void l_preload(int et, int dim, int k) {
   touch(k_node_update<2, true, 4>); touch(k_node_update<2, false, 4>); touch(k_node_update<2, false, 2>); touch(k_node_update<2, false, 8>);
   touch(k_halo_send<0>); touch(k_halo_send<1>); touch(k_halo_send<2>); touch(k_halo_wait);
   touch(k_halo_finish<0>); touch(k_halo_finish<1>);
-  touch(k_init_elem); touch(k_vol0_density); touch(k_xmin);
+  touch(k_init_elem); touch(k_vol0_density); touch(k_xmin); touch(k_energy_kin<2>); touch(k_energy_kin<3>);
   (void)dim;
 }
 

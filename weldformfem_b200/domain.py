@@ -219,6 +219,14 @@ class Domain_d:
         self._ck(self._lib.wf_energies(self._h, C.byref(ek), C.byref(de)))
         return ek.value, de.value
 
+    def monitor_async(self):
+        self._ck(self._lib.wf_monitor_async(self._h))
+
+    def monitor_wait(self):
+        ek, f = C.c_double(), C.c_int()
+        self._ck(self._lib.wf_monitor_wait(self._h, C.byref(ek), C.byref(f)))
+        return ek.value, bool(f.value)
+
     def time(self):
         t, n = C.c_double(), C.c_long()
         self._ck(self._lib.wf_get_time(self._h, C.byref(t), C.byref(n)))
