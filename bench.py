@@ -190,7 +190,12 @@ def ours(args):
     stream = torch.cuda.Stream()
     kind = args.kind
     case = build_case(args.n, kind)
-    if world > 1:
+    if world > 1 and args.cube:
+        # configs[4]: one n^3 block (e.g. --cube 431 = 80 062 991 hexes) domain-decomposed across the ranks
+        case = build_case(args.cube, kind)
+        case = dataclasses.replace(case, top_vel=case.top_vel * args.cube / args.n)
+        dom = RankDomain(rank, world, device=local, strict=args.strict, halo=args.halo)
+    elif world > 1:
         # weak scaling: every rank owns one n^(d-1) x n slab of an n^(d-1) x (n * world) box
         nn_ = list(case.n)
         nn_[-1] *= world
@@ -317,9 +322,9 @@ def ours(args):
     launches_per_step = 4 if world == 1 else 9
     line = {
         "metric": "element-steps/s", "value": value, "unit": "element-steps/s", "n_gpus": world, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+        "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong" if (world > 1 and args.cube) else "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": WORKLOAD[kind] + f": {ne} elements / {nn} nodes per GPU "
+        "config": {"workload": (WORKLOAD[kind] if not (world > 1 and args.cube) else "configs[4]: synthetic hexa/tet block domain-decomposed across the GPUs") + f": {ne} elements / {nn} nodes per GPU "
                                f"(global box {'x'.join(str(q) for q in case.n)}), Hollomon J2" +
                                (f", viscous hourglass {case.hexa_hg}" if kind == "hex" else ""),
                    "why_this_config": "BASELINE.json quotes its target (>=60 % of HBM roofline) on the 10M-element hexa "
@@ -356,6 +361,7 @@ def main():
     ap.add_argument("--strict", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--halo", default="peer", choices=["peer", "nccl"])
+    ap.add_argument("--cube", type=int, default=0, help="N>1: partition one cube of this many elements per side (configs[4]: 431)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":
