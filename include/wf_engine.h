@@ -101,6 +101,14 @@ int wf_step(wf_engine *, int nsteps); /* fused rows 1-22 of the step, Solver_exp
 int wf_nonfinite_flag(wf_engine *, int *flag);
 int wf_energies(wf_engine *, double *Ekin, double *dEint); /* computeEnergies, Mechanical.C:2145 */
 int wf_get_time(wf_engine *, double *time, long *step_count);
+/* diagnostics computed on the device: calcMinEdgeLength (Domain_d.C:2224; also fills "m_elem_length"), max |v| and the
+ * variable step of the explicit loop dt = cfl * min_length / (cs + max|v|) (Solver_explicit.C:579-598); wf_set_dt
+ * applies a new step between batches ("p_node", calcNodalPressureFromElemental Mechanical.C:1187, is produced by
+ * wf_get_array on request) */
+int wf_calcMinEdgeLength(wf_engine *, double *min_length, double *min_height);
+int wf_max_velocity(wf_engine *, double *vmax);
+int wf_cfl_dt(wf_engine *, double cfl_factor, double *dt);
+int wf_set_dt(wf_engine *, double dt);
 /* step monitor that does not drain the stream: enqueue {kinetic energy, non-finite flag} -> pinned host memory;
  * wf_monitor_wait returns the oldest pending result (at most two pending) */
 int wf_monitor_async(wf_engine *);

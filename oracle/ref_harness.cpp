@@ -261,6 +261,8 @@ class Harness : public Domain_d {
     else if (f == "calcElemStrainRates") calcElemStrainRates();
     else if (f == "calcElemPressure") pressure();
     else if (f == "calcNodalPressureFromElemental") calcNodalPressureFromElemental();
+    else if (f == "SetDT") SetDT(arg);
+    else if (f == "calcMinEdgeLength") { if (m_dim == 2 && m_nodxelem != 4) return -1; calcMinEdgeLength(); }
     else if (f == "CalcStressStrain") CalcStressStrain(arg);
     else if (f == "calcArtificialViscosity") calcArtificialViscosity();
     else if (f == "calcElemForces") calcElemForces();
@@ -314,6 +316,10 @@ class Harness : public Domain_d {
     if (nm == "m_f_elem") return {m_f_elem, nk * m_dim};
     if (nm == "m_f_elem_hg") return {m_f_elem_hg, nk * m_dim};
     if (nm == "m_hg_q") return {m_dim == 2 ? m_hg_q : nullptr, m_dim == 2 ? nk * m_dim : 0};
+    if (nm == "m_elem_length") return {m_elem_length, ne};
+    if (nm == "bcx_val") return {bcx_val, sizeof(double) * (size_t)bc_count[0]};
+    if (nm == "bcy_val") return {bcy_val, sizeof(double) * (size_t)bc_count[1]};
+    if (nm == "bcz_val") return {bcz_val, sizeof(double) * (size_t)bc_count[2]};
     if (nm == "m_elnod") return {m_elnod, sizeof(unsigned) * (size_t)m_elem_count * m_nodxelem};
     if (nm == "m_nodel") return {m_nodel, sizeof(int) * ntot};
     if (nm == "m_nodel_loc") return {m_nodel_loc, sizeof(int) * ntot};
@@ -327,7 +333,10 @@ class Harness : public Domain_d {
     out[4] = bc_count[0]; out[5] = bc_count[1]; out[6] = bc_count[2];
     out[7] = (int)m_domtype;
   }
-  void consts(double *out) { out[0] = m_alpha; out[1] = m_beta; out[2] = m_gamma; out[3] = dt; out[4] = time_; }
+  void consts(double *out) {
+    out[0] = m_alpha; out[1] = m_beta; out[2] = m_gamma; out[3] = dt; out[4] = time_;
+    out[5] = m_min_length; out[6] = m_min_height;
+  }
   void energies(double *ek, double *dei) {
     double ev = 0.0;
     computeEnergies(dt, *ek, *dei, ev);

@@ -23,7 +23,7 @@ PORT_SO = os.path.join(HERE, "_build", "libwf_oracle.so")
 
 _DBL = ("x v a u u_dt prev_a m_fi m_fe m_mdiag m_voln p_node m_dH_detJ_dx m_dH_detJ_dy m_dH_detJ_dz "
         "m_detJ vol vol_0 rho rho_0 p pl_strain sigma_y m_radius m_str_rate m_rot_rate m_sigma m_tau "
-        "m_eps m_f_elem m_f_elem_hg m_hg_q m_voln_0 m_Jn bcx_val bcy_val bcz_val").split()
+        "m_eps m_f_elem m_f_elem_hg m_hg_q m_voln_0 m_Jn bcx_val bcy_val bcz_val m_elem_length").split()
 _INT = "m_nodel m_nodel_loc m_nodel_offset m_nodel_count".split()
 _UINT = ["m_elnod"]
 
@@ -170,9 +170,9 @@ class _Base:
         return dict(zip(keys, list(out)))
 
     def consts(self):
-        out = (C.c_double * 5)()
+        out = (C.c_double * 7)()
         self._f("consts")(self.h, out)
-        return dict(zip("alpha beta gamma dt time".split(), list(out)))
+        return dict(zip("alpha beta gamma dt time min_length min_height".split(), list(out)))
 
     def energies(self):
         ek, de = C.c_double(), C.c_double()

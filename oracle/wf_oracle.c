@@ -44,6 +44,7 @@ struct wfo_domain {
   int press_variant;
   double av[2], hexa_hg;
   double dt, alpha, beta, gamma, time;
+  double *m_elem_length, m_min_length, m_min_height; /* calcMinEdgeLength products */
 };
 
 static void *zalloc(size_t n, size_t sz) { return calloc(n ? n : 1, sz); }
@@ -572,6 +573,73 @@ static void pressure(wfo_domain *d) { /* Solver_explicit.C:735-746 */
   else if (d->press_variant == 3) calcElemPressureANP_Nodal(d);
 }
 
+/* calcMinEdgeLength (Domain_d.C:2224-2468): minimum edge length and minimum height; every 3D element is treated
+ * as the tetrahedron of its first four nodes (:2243-2247), every 2D element as the quadrilateral of four nodes
+ * (:2381-2413).  The angle / Jnorm diagnostics of the same function feed only the remesher and are not restated. */
+static double len3(const double *a) { return sqrt(a[0] * a[0] + a[1] * a[1] + a[2] * a[2]); }
+static void calcMinEdgeLength(wfo_domain *d) {
+  double min_len = 1.0e6, min_height = 1.0e6;
+  if (!d->m_elem_length) d->m_elem_length = (double *)zalloc((size_t)d->ne, sizeof(double));
+  for (int e = 0; e < d->ne; e++) {
+    double elem_min_height = 1.0e6;
+    const unsigned *en = d->m_elnod + (size_t)d->k * e;
+    if (d->dim == 3) {
+      double P[4][3];
+      for (int i = 0; i < 4; i++)
+        for (int c = 0; c < 3; c++) P[i][c] = d->x[3 * (size_t)en[i] + c];
+      const int ed[6][2] = {{1, 0}, {2, 0}, {3, 0}, {2, 1}, {3, 1}, {3, 2}};
+      for (int i = 0; i < 6; i++) {
+        double v[3];
+        for (int c = 0; c < 3; c++) v[c] = P[ed[i][0]][c] - P[ed[i][1]][c];
+        double len = len3(v);
+        if (len < min_len) min_len = len;
+      }
+      const int fc[4][3] = {{1, 2, 3}, {0, 2, 3}, {0, 1, 3}, {0, 1, 2}};
+      for (int i = 0; i < 4; i++) {
+        double x1[3], x2[3], nrm[3], vec[3];
+        for (int c = 0; c < 3; c++) {
+          x1[c] = P[fc[i][1]][c] - P[fc[i][0]][c];
+          x2[c] = P[fc[i][2]][c] - P[fc[i][0]][c];
+        }
+        nrm[0] = x1[1] * x2[2] - x1[2] * x2[1];
+        nrm[1] = x1[2] * x2[0] - x1[0] * x2[2];
+        nrm[2] = x1[0] * x2[1] - x1[1] * x2[0];
+        double area = len3(nrm);
+        if (area < 1e-12) continue;
+        const double inv = 1.0 / area; /* double3 operator/ multiplies by the reciprocal (double3_c.h:95-99) */
+        for (int c = 0; c < 3; c++) nrm[c] = nrm[c] * inv;
+        for (int c = 0; c < 3; c++) vec[c] = P[i][c] - P[fc[i][0]][c];
+        double height = fabs(vec[0] * nrm[0] + vec[1] * nrm[1] + vec[2] * nrm[2]);
+        if (height < elem_min_height) elem_min_height = height;
+      }
+      d->m_elem_length[e] = elem_min_height;
+      if (elem_min_height < min_height) min_height = elem_min_height;
+    } else {
+      double A[2], B[2], Cc[2], D[2];
+      for (int c = 0; c < 2; c++) {
+        A[c] = d->x[2 * (size_t)en[0] + c]; B[c] = d->x[2 * (size_t)en[1] + c];
+        Cc[c] = d->x[2 * (size_t)en[2] + c]; D[c] = d->x[2 * (size_t)en[3] + c];
+      }
+      double lenAB = sqrt((B[0] - A[0]) * (B[0] - A[0]) + (B[1] - A[1]) * (B[1] - A[1]));
+      double lenBC = sqrt((Cc[0] - B[0]) * (Cc[0] - B[0]) + (Cc[1] - B[1]) * (Cc[1] - B[1]));
+      double lenCD = sqrt((D[0] - Cc[0]) * (D[0] - Cc[0]) + (D[1] - Cc[1]) * (D[1] - Cc[1]));
+      double lenDA = sqrt((A[0] - D[0]) * (A[0] - D[0]) + (A[1] - D[1]) * (A[1] - D[1]));
+      min_len = fmin(min_len, fmin(fmin(lenAB, lenBC), fmin(lenCD, lenDA)));
+      double area1 = 0.5 * fabs((B[0] - A[0]) * (Cc[1] - A[1]) - (Cc[0] - A[0]) * (B[1] - A[1]));
+      double area2 = 0.5 * fabs((Cc[0] - A[0]) * (D[1] - A[1]) - (D[0] - A[0]) * (Cc[1] - A[1]));
+      double area = area1 + area2;
+      if (area > 1e-14) {
+        double h1 = 2.0 * area / lenAB, h2 = 2.0 * area / lenBC, h3 = 2.0 * area / lenCD, h4 = 2.0 * area / lenDA;
+        elem_min_height = fmin(fmin(h1, h2), fmin(h3, h4));
+        min_height = fmin(min_height, elem_min_height);
+      }
+      d->m_elem_length[e] = elem_min_height;
+    }
+  }
+  d->m_min_length = min_len;
+  d->m_min_height = min_height;
+}
+
 /* calcNodalPressureFromElemental (Mechanical.C:1187-1212) */
 static void calcNodalPressureFromElemental(wfo_domain *d) {
   double *acc = calloc(d->nn ? d->nn : 1, sizeof(double));
@@ -911,6 +979,8 @@ int wfo_call(wfo_domain *d, const char *f, double arg) {
   else if (IS("calcElemStrainRates")) calcElemStrainRates(d);
   else if (IS("calcElemPressure")) pressure(d);
   else if (IS("calcNodalPressureFromElemental")) calcNodalPressureFromElemental(d);
+  else if (IS("SetDT")) d->dt = arg; /* Domain_d::SetDT, Domain_d.h:635 */
+  else if (IS("calcMinEdgeLength")) { if (d->dim == 2 && d->k != 4) return -1; calcMinEdgeLength(d); }
   else if (IS("CalcStressStrain")) CalcStressStrain(d, arg);
   else if (IS("calcArtificialViscosity")) calcArtificialViscosity(d);
   else if (IS("calcElemForces")) calcElemForces(d);
@@ -942,6 +1012,7 @@ static view_t view(wfo_domain *d, const char *nm) {
   V("m_tau", d->m_tau, 6 * ne) V("m_eps", d->m_eps, 6 * ne)
   V("m_f_elem", d->m_f_elem, nk * d->dim) V("m_f_elem_hg", d->m_f_elem_hg, nk * d->dim)
   V("m_hg_q", d->dim == 2 ? d->m_hg_q : NULL, d->dim == 2 ? nk * d->dim : 0)
+  V("m_elem_length", d->m_elem_length, d->m_elem_length ? ne : 0)
   V("bcx_val", d->bc_val[0], sizeof(double) * (size_t)d->bc_count[0]) /* Domain_d.h:901 */
   V("bcy_val", d->bc_val[1], sizeof(double) * (size_t)d->bc_count[1])
   V("bcz_val", d->bc_val[2], sizeof(double) * (size_t)d->bc_count[2])
@@ -973,4 +1044,5 @@ void wfo_info(wfo_domain *d, int *out) {
 }
 void wfo_consts(wfo_domain *d, double *out) {
   out[0] = d->alpha; out[1] = d->beta; out[2] = d->gamma; out[3] = d->dt; out[4] = d->time;
+  out[5] = d->m_min_length; out[6] = d->m_min_height;
 }

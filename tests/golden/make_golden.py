@@ -34,6 +34,14 @@ def main():
             out[f"sN_{nm}"] = d.get(nm)
         if case.dim == 2 and not case.tritet:
             out["sN_m_hg_q"] = d.get("m_hg_q")[: 2 * case.n_elems]
+        # diagnostics of SURVEY §8f-1: calcNodalPressureFromElemental (Mechanical.C:1187), calcMinEdgeLength (Domain_d.C:2224)
+        d.call("calcNodalPressureFromElemental")
+        out["sN_p_node"] = d.get("p_node")
+        if not (case.dim == 2 and case.tritet):
+            d.call("calcMinEdgeLength")
+            c = d.consts()
+            out["sN_min_edge"] = np.array([c["min_length"], c["min_height"]])
+            out["sN_m_elem_length"] = d.get("m_elem_length")
         out["steps"] = np.array([steps])
         path = os.path.join(HERE, name + ".npz")
         np.savez_compressed(path, **out)

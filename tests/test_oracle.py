@@ -33,6 +33,13 @@ def test_oracle_matches_reference_fixtures_bit_for_bit(name, oracle_port):
         assert np.array_equal(d.get(nm), g["sN_" + nm]), (f"step {steps}", nm)
     if "sN_m_hg_q" in g:
         assert np.array_equal(d.get("m_hg_q")[: 2 * case.n_elems], g["sN_m_hg_q"])
+    d.call("calcNodalPressureFromElemental")
+    assert np.array_equal(d.get("p_node"), g["sN_p_node"])
+    if "sN_min_edge" in g:
+        d.call("calcMinEdgeLength")
+        c = d.consts()
+        assert np.array_equal([c["min_length"], c["min_height"]], g["sN_min_edge"])
+        assert np.array_equal(d.get("m_elem_length"), g["sN_m_elem_length"])
 
 
 LIVE = [dataclasses.replace(cases.c3_hexes(9), top_vel=-150.0), dataclasses.replace(cases.c2_tets(7), top_vel=-150.0),

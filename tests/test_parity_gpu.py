@@ -200,3 +200,34 @@ def test_time_dependent_bc_values_and_async_monitor(oracle_port):
     ek, bad = eng.monitor_wait()
     assert not bad and abs(ek - ek_ref_prev) <= 1e-9 * abs(ek_ref_prev)
     compare(eng, ref, STATE, 1e-9, "time-dependent BC values")
+
+
+@pytest.mark.parametrize("key", ["hex", "tet", "axiquad"])
+@pytest.mark.parametrize("strict", [True, False], ids=["strict", "fast"])
+def test_device_diagnostics(key, strict, oracle_port):
+    """SURVEY §8f-1 on the device: calcMinEdgeLength (Domain_d.C:2224), p_node (Mechanical.C:1187), max |v| and the
+    variable step dt = cfl * min_length / (cs + max|v|) (Solver_explicit.C:579-598), then stepping with the new dt."""
+    case = SMALL[key]
+    eng, ref = run_pair(case, oracle_port, 40, strict)
+    ref.call("calcMinEdgeLength")
+    ml, mh = eng.calcMinEdgeLength()
+    c = ref.consts()
+    # heights of a hexa's first four (coplanar) nodes are pure cancellation noise (Domain_d.C:2243-2247 reads every 3D
+    # element as a tetrahedron): compare on the scale of the edge length
+    assert abs(ml - c["min_length"]) <= 1e-12 * c["min_length"]
+    assert abs(mh - c["min_height"]) <= 1e-9 * c["min_length"]
+    assert np.allclose(eng.get("m_elem_length"), ref.get("m_elem_length"), rtol=1e-9, atol=1e-9 * c["min_length"])
+    ref.call("calcNodalPressureFromElemental")
+    assert relerr(eng.get("p_node"), ref.get("p_node")) <= (1e-13 if strict else 1e-10)
+    v = ref.get("v").reshape(-1, case.dim)
+    vmax = float(np.sqrt((v * v).sum(axis=1)).max())
+    assert abs(eng.max_velocity() - vmax) <= 1e-10 * vmax
+    cs = np.sqrt(case.bulk / ref.get("rho")[0])
+    dt_ref = 0.25 * c["min_length"] / (cs + vmax)
+    dt = eng.cfl_dt(0.25)
+    assert abs(dt - dt_ref) <= 1e-10 * dt_ref
+    eng.set_dt(dt)
+    ref.call("SetDT", dt)
+    eng.step(10)
+    ref.step(10)
+    compare(eng, ref, _names(case), 1e-9 if strict else 1e-8, f"{key} after a time-step change")

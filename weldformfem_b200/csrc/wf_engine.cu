@@ -75,6 +75,12 @@ struct wf_engine {
   unsigned long long seq = 0, timeout_ns = 30000000000ull;
   std::vector<void *> ipc_opened;
   int init_stage = 0, step_stage = 0;
+  // scratch for device-side layout conversion (wf_get_array / wf_set_array), diagnostics
+  double *scratch = nullptr;
+  size_t scratch_count = 0;
+  double *elem_length = nullptr;           // m_elem_length (calcMinEdgeLength)
+  unsigned long long *diag_keys = nullptr; // [3] ordered keys: min length, min height, max |v|
+  bool elem_length_valid = false;
 };
 
 #define CK(call)                                                                          \
@@ -99,6 +105,14 @@ static int dalloc(wf_engine *E, T **p, size_t count) {
   CK(cudaMemsetAsync(q, 0, bytes, E->stream));
   E->allocs.push_back(q);
   *p = (T *)q;
+  return 0;
+}
+
+static int need_scratch(wf_engine *E, size_t count) {
+  if (count <= E->scratch_count) return 0;
+  if (E->scratch) { CK(cudaStreamSynchronize(E->stream)); cudaFree(E->scratch); E->scratch = nullptr; E->scratch_count = 0; }
+  CK(cudaMalloc((void **)&E->scratch, count * sizeof(double)));
+  E->scratch_count = count;
   return 0;
 }
 
@@ -162,6 +176,7 @@ extern "C" void wf_destroy(wf_engine *E) {
     if (E->mon_ev[b]) cudaEventDestroy(E->mon_ev[b]);
   for (void *p : E->ipc_opened) cudaIpcCloseMemHandle(p);
   for (void *p : E->allocs) cudaFree(p);
+  if (E->scratch) cudaFree(E->scratch);
   if (E->own_stream) cudaStreamDestroy(E->stream);
   delete E;
 }
@@ -1149,6 +1164,7 @@ static bool lookup(wf_engine *E, const std::string &nm, ArrayRef &r, bool for_wr
   if (nm == "sigma_y") return elems(d.sigma_y);
   if (nm == "m_detJ") return elems(d.detJ);
   if (nm == "m_radius") return elems(d.radius);
+  if (nm == "m_elem_length") return E->elem_length_valid ? elems(E->elem_length) : false;
   if (nm == "m_tau") return elem6(d.tau);
   if (nm == "m_eps") return elem6(d.eps);
   if (nm == "m_str_rate") return elem6(d.str_rate);
@@ -1206,28 +1222,21 @@ extern "C" int wf_get_array(wf_engine *E, const char *name, void *dst, size_t by
   double *out = (double *)dst;
   std::vector<double> h;
   if (r.kind == K_INT_HOST) { memcpy(dst, r.host, bytes); return 0; }
-  if (r.lazy_pnode) { // calcNodalPressureFromElemental (Mechanical.C:1187-1212), element-order scatter == nodel order
-    std::vector<double> p, vol;
-    if (download(E, d.p, d.ep, p) || download(E, d.vol, d.ep, vol)) return 1;
-    for (int n = 0; n < nn; n++) {
-      double acc = 0.0, pv = 0.0;
-      for (int j = 0; j < E->h_count[n]; j++) {
-        int e = E->h_nodel[E->h_offset[n] + j];
-        pv += p[e] * vol[e];
-        acc += vol[e];
-      }
-      if (acc > 0.0) pv /= acc;
-      out[n] = pv;
-    }
-    return 0;
+  if (r.lazy_pnode) { // calcNodalPressureFromElemental (Mechanical.C:1187-1212) on the device
+    if (need_scratch(E, (size_t)d.np)) return 1;
+    E->L->p_node(d, E->scratch, E->stream);
+    CK(cudaMemcpyAsync(dst, E->scratch, bytes, cudaMemcpyDeviceToHost, E->stream));
+    CK(cudaStreamSynchronize(E->stream));
+    return check_launch(E, "p_node");
   }
-  if (r.lazy_sigma) {
-    double *tmp = nullptr;
-    CK(cudaMalloc((void **)&tmp, (size_t)6 * d.ep * sizeof(double)));
-    E->L->rebuild_sigma(d, tmp, E->stream);
-    int rc = download(E, tmp, (size_t)6 * d.ep, h);
-    cudaFree(tmp);
-    if (rc) return 1;
+  if (r.lazy_sigma) { // sigma = -p I + tau rebuilt, converted and copied without touching host scratch
+    const size_t c6 = (size_t)6 * d.ep;
+    if (need_scratch(E, 2 * c6)) return 1;
+    E->L->rebuild_sigma(d, E->scratch, E->stream);
+    E->L->soa_to_aos(E->scratch, d.ep, 6, ne, 1.0, E->scratch + c6, E->stream);
+    CK(cudaMemcpyAsync(dst, E->scratch + c6, bytes, cudaMemcpyDeviceToHost, E->stream));
+    CK(cudaStreamSynchronize(E->stream));
+    return check_launch(E, "m_sigma");
   } else if (r.lazy_felem) {
     NEED(E->step_count > 0, "m_f_elem is available after a step");
     std::vector<double> fs;
@@ -1240,52 +1249,53 @@ extern "C" int wf_get_array(wf_engine *E, const char *name, void *dst, size_t by
     return 0;
   } else if (r.lazy_fi) {
     NEED(E->step_count > 0 || E->dbg, "m_fi is available after a step");
+    const size_t cv = (size_t)dim * d.np;
+    if (need_scratch(E, 2 * cv)) return 1;
     double *save_fi = d.fi;
-    double *tmp = nullptr;
-    CK(cudaMalloc((void **)&tmp, (size_t)dim * d.np * sizeof(double)));
-    d.fi = tmp;
+    d.fi = E->scratch;
     E->L->node_update(d, E->P, E->strict ? 1 : 0, 0, 1, E->stream); // sums only, exactly as the step forms them
-    int rc = download(E, tmp, (size_t)dim * d.np, h);
     d.fi = save_fi;
-    cudaFree(tmp);
-    if (rc) return 1;
+    E->L->soa_to_aos(E->scratch, d.np, dim, nn, 1.0, E->scratch + cv, E->stream);
+    CK(cudaMemcpyAsync(dst, E->scratch + cv, bytes, cudaMemcpyDeviceToHost, E->stream));
+    CK(cudaStreamSynchronize(E->stream));
+    return check_launch(E, "m_fi");
   } else {
-    size_t count = 0;
-    switch (r.kind) {
-      case K_NODEVEC: count = (size_t)dim * d.np; break;
-      case K_NODESCAL: count = d.np; break;
-      case K_ELEMSCAL: count = d.ep; break;
-      case K_ELEM6: count = (size_t)6 * d.ep; break;
-      case K_ELEMNODE: case K_ELEMNODEVEC: count = (size_t)k * dim * d.ep; break;
-      case K_HGQ: count = (size_t)2 * d.ep; break;
-      default: break;
-    }
     NEED(r.dev, std::string("array '") + name + "' is not allocated");
-    if (download(E, r.dev, count, h)) return 1;
+    if (r.kind != K_HGQ) {
+      // convert to the reference layout on the device, then ONE device->host copy straight into the caller's buffer
+      long long cnt = 0, pitch = 0; int nc = 1; const double *src = r.dev; double scale = 1.0;
+      switch (r.kind) {
+        case K_NODEVEC: cnt = nn; pitch = d.np; nc = dim; break;
+        case K_NODESCAL: cnt = nn; pitch = d.np; nc = 1; if (r.lazy_voln) scale = 1.0 / (double)k; break;
+        case K_ELEMSCAL: cnt = ne; pitch = d.ep; nc = 1; break;
+        case K_ELEM6: cnt = ne; pitch = d.ep; nc = 6; break;
+        case K_ELEMNODE: cnt = ne; pitch = d.ep; nc = k; src = r.dev + (size_t)r.comp * k * d.ep; break;
+        case K_ELEMNODEVEC: cnt = ne; pitch = d.ep; nc = k * dim; break;
+        default: break;
+      }
+      if (nc == 1 && scale == 1.0) {
+        CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, E->stream));
+      } else {
+        if (need_scratch(E, (size_t)cnt * nc)) return 1;
+        if (r.lazy_voln) E->L->soa_to_aos(src, pitch, nc, cnt, 1.0, E->scratch, E->stream); // then divide exactly like the host did
+        else E->L->soa_to_aos(src, pitch, nc, cnt, scale, E->scratch, E->stream);
+        CK(cudaMemcpyAsync(dst, E->scratch, bytes, cudaMemcpyDeviceToHost, E->stream));
+      }
+      CK(cudaStreamSynchronize(E->stream));
+      if (r.lazy_voln) for (int n = 0; n < nn; n++) out[n] = out[n] / (double)k;
+      return check_launch(E, "wf_get_array");
+    }
+    if (download(E, r.dev, (size_t)2 * d.ep, h)) return 1;
   }
+  // host-side conversions of the rebuilt / rare arrays
   switch (r.kind) {
     case K_NODEVEC:
       for (int n = 0; n < nn; n++)
         for (int c = 0; c < dim; c++) out[(size_t)n * dim + c] = h[(size_t)c * d.np + n];
       break;
-    case K_NODESCAL:
-      for (int n = 0; n < nn; n++) out[n] = r.lazy_voln ? h[n] / (double)k : h[n];
-      break;
-    case K_ELEMSCAL:
-      memcpy(out, h.data(), sizeof(double) * ne);
-      break;
     case K_ELEM6:
       for (int e = 0; e < ne; e++)
         for (int c = 0; c < 6; c++) out[(size_t)e * 6 + c] = h[(size_t)c * d.ep + e];
-      break;
-    case K_ELEMNODE:
-      for (int e = 0; e < ne; e++)
-        for (int n = 0; n < k; n++) out[(size_t)e * k + n] = h[((size_t)r.comp * k + n) * d.ep + e];
-      break;
-    case K_ELEMNODEVEC:
-      for (int e = 0; e < ne; e++)
-        for (int n = 0; n < k; n++)
-          for (int c = 0; c < dim; c++) out[((size_t)e * k + n) * dim + c] = h[((size_t)n * dim + c) * d.ep + e];
       break;
     case K_HGQ:
       memset(out, 0, bytes);
@@ -1313,42 +1323,32 @@ extern "C" int wf_set_array(wf_engine *E, const char *name, const void *src, siz
   if (!lookup(E, nm, r, true)) FAIL(std::string("array '") + name + "' cannot be set");
   NEED(bytes == r.bytes, std::string("size mismatch for '") + name + "'");
   const double *in = (const double *)src;
-  std::vector<double> h;
-  switch (r.kind) {
-    case K_NODEVEC:
-      h.assign((size_t)dim * d.np, 0.0);
-      for (int n = 0; n < nn; n++)
-        for (int c = 0; c < dim; c++) h[(size_t)c * d.np + n] = in[(size_t)n * dim + c];
-      break;
-    case K_NODESCAL:
-      h.assign(d.np, 0.0);
-      memcpy(h.data(), in, sizeof(double) * nn);
-      break;
-    case K_ELEMSCAL:
-      h.assign(d.ep, 0.0);
-      memcpy(h.data(), in, sizeof(double) * ne);
-      break;
-    case K_ELEM6:
-      h.assign((size_t)6 * d.ep, 0.0);
-      for (int e = 0; e < ne; e++)
-        for (int c = 0; c < 6; c++) h[(size_t)c * d.ep + e] = in[(size_t)e * 6 + c];
-      break;
-    case K_ELEMNODEVEC:
-      h.assign((size_t)k * dim * d.ep, 0.0);
-      for (int e = 0; e < ne; e++)
-        for (int n = 0; n < k; n++)
-          for (int c = 0; c < dim; c++) h[((size_t)n * dim + c) * d.ep + e] = in[((size_t)e * k + n) * dim + c];
-      break;
-    case K_HGQ:
-      h.assign((size_t)2 * d.ep, 0.0);
-      for (int e = 0; e < ne; e++)
-        for (int c = 0; c < 2; c++) h[(size_t)c * d.ep + e] = in[(size_t)e * 2 + c];
-      break;
-    default:
-      FAIL(std::string("array '") + name + "' cannot be set");
+  if (r.kind == K_HGQ) {
+    std::vector<double> h((size_t)2 * d.ep, 0.0);
+    for (int e = 0; e < ne; e++)
+      for (int c = 0; c < 2; c++) h[(size_t)c * d.ep + e] = in[(size_t)e * 2 + c];
+    CK(cudaMemcpyAsync(r.dev, h.data(), h.size() * sizeof(double), cudaMemcpyHostToDevice, E->stream));
+    CK(cudaStreamSynchronize(E->stream));
+  } else {
+    long long cnt = 0, pitch = 0; int nc = 1;
+    switch (r.kind) {
+      case K_NODEVEC: cnt = nn; pitch = d.np; nc = dim; break;
+      case K_NODESCAL: cnt = nn; pitch = d.np; nc = 1; break;
+      case K_ELEMSCAL: cnt = ne; pitch = d.ep; nc = 1; break;
+      case K_ELEM6: cnt = ne; pitch = d.ep; nc = 6; break;
+      case K_ELEMNODEVEC: cnt = ne; pitch = d.ep; nc = k * dim; break;
+      default: FAIL(std::string("array '") + name + "' cannot be set");
+    }
+    if (nc == 1) {
+      CK(cudaMemcpyAsync(r.dev, in, bytes, cudaMemcpyHostToDevice, E->stream));
+    } else { // one host->device copy of the caller's buffer, layout conversion on the device
+      if (need_scratch(E, (size_t)cnt * nc)) return 1;
+      CK(cudaMemcpyAsync(E->scratch, in, bytes, cudaMemcpyHostToDevice, E->stream));
+      E->L->aos_to_soa(E->scratch, pitch, nc, cnt, r.dev, E->stream);
+    }
+    CK(cudaStreamSynchronize(E->stream));
+    if (check_launch(E, "wf_set_array")) return 1;
   }
-  CK(cudaMemcpyAsync(r.dev, h.data(), h.size() * sizeof(double), cudaMemcpyHostToDevice, E->stream));
-  CK(cudaStreamSynchronize(E->stream));
   if (nm == "x" && E->domtype == WF_AXISYMM && E->inited) {
     if (reset_xmin(E, E->P.xmin_cur)) return 1;
     E->L->xmin(d, E->P.xmin_cur, E->stream);
@@ -1362,6 +1362,82 @@ extern "C" void *wf_device_ptr(wf_engine *E, const char *name, size_t *pitch) {
   if (!lookup(E, name, r, true) || r.kind == K_INT_HOST) return nullptr;
   if (pitch) *pitch = (r.kind == K_NODEVEC || r.kind == K_NODESCAL) ? (size_t)E->d.np : (size_t)E->d.ep;
   return r.dev;
+}
+
+// ---- diagnostics on the device -----------------------------------------------------
+static unsigned long long host_key(double v) {
+  unsigned long long b;
+  memcpy(&b, &v, 8);
+  return (b & 0x8000000000000000ull) ? ~b : (b | 0x8000000000000000ull);
+}
+static double host_unkey(unsigned long long k) {
+  unsigned long long b = (k & 0x8000000000000000ull) ? (k & 0x7fffffffffffffffull) : ~k;
+  double v;
+  memcpy(&v, &b, 8);
+  return v;
+}
+static int diag_reduce(wf_engine *E, bool edges, bool vel, double out[3]) {
+  CK(cudaSetDevice(E->device));
+  WfDev &d = E->d;
+  if (!E->diag_keys && dalloc(E, &E->diag_keys, 3)) return 1;
+  if (edges && !E->elem_length && dalloc(E, &E->elem_length, (size_t)d.ep)) return 1;
+  const unsigned long long init[3] = {host_key(1.0e6), host_key(1.0e6), host_key(0.0)};
+  CK(cudaMemcpyAsync(E->diag_keys, init, sizeof(init), cudaMemcpyHostToDevice, E->stream));
+  if (edges) { E->L->min_edge(d, E->elem_length, E->diag_keys, E->stream); E->elem_length_valid = true; }
+  if (vel) E->L->max_vel(d, E->diag_keys, E->stream);
+  unsigned long long k[3];
+  CK(cudaMemcpyAsync(k, E->diag_keys, sizeof(k), cudaMemcpyDeviceToHost, E->stream));
+  CK(cudaStreamSynchronize(E->stream));
+  for (int i = 0; i < 3; i++) out[i] = host_unkey(k[i]);
+  return check_launch(E, "diagnostics");
+}
+
+// Domain_d::calcMinEdgeLength (Domain_d.C:2224-2468): m_min_length, m_min_height, m_elem_length
+extern "C" int wf_calcMinEdgeLength(wf_engine *E, double *min_length, double *min_height) {
+  NEED(E->meshed, "no mesh");
+  NEED(!E->predicted, "engine is mid-batch");
+  NEED(E->dim == 3 || E->k == 4, "calcMinEdgeLength reads four nodes per element (Domain_d.C:2381-2384): not defined for triangles");
+  double o[3];
+  if (diag_reduce(E, true, false, o)) return 1;
+  if (min_length) *min_length = o[0];
+  if (min_height) *min_height = o[1];
+  return 0;
+}
+
+// max |v| over the nodes (Solver_explicit.C:583-587)
+extern "C" int wf_max_velocity(wf_engine *E, double *vmax) {
+  NEED(E->meshed, "no mesh");
+  NEED(!E->predicted, "engine is mid-batch");
+  double o[3];
+  if (diag_reduce(E, false, true, o)) return 1;
+  if (vmax) *vmax = o[2];
+  return 0;
+}
+
+// variable time step of the explicit loop (Solver_explicit.C:579-598): dt = cfl * min_length / (cs + max|v|),
+// cs = sqrt(K / rho[0])
+extern "C" int wf_cfl_dt(wf_engine *E, double cfl_factor, double *dt) {
+  NEED(E->meshed && E->material_set, "wf_cfl_dt needs mesh and material");
+  NEED(!E->predicted, "engine is mid-batch");
+  NEED(E->dim == 3 || E->k == 4, "calcMinEdgeLength is not defined for triangles");
+  double o[3], rho0 = E->mat.rho0;
+  if (diag_reduce(E, true, true, o)) return 1;
+  if (E->inited) {
+    CK(cudaMemcpyAsync(&rho0, E->d.rho, sizeof(double), cudaMemcpyDeviceToHost, E->stream));
+    CK(cudaStreamSynchronize(E->stream));
+  }
+  const double cs = sqrt(E->P.Kbulk / rho0);
+  if (dt) *dt = cfl_factor * o[0] / (cs + o[2]);
+  return 0;
+}
+
+// change the step size between batches (variable-dt loop); takes effect at the next wf_step
+extern "C" int wf_set_dt(wf_engine *E, double dt) {
+  NEED(E->inited, "wf_set_dt after wf_init");
+  NEED(!E->predicted, "engine is mid-batch");
+  NEED(dt > 0.0, "dt must be positive");
+  E->P.dt = dt;
+  return 0;
 }
 
 // computeEnergies (Mechanical.C:2145-2185).  Ekin from the current velocities and the nodal mass of the last

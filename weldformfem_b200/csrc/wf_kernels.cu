@@ -625,6 +625,142 @@ __global__ void k_energy_int(WfDev d, const double *sig) {
   if (threadIdx.x == 0 && k != 0.0) atomicAdd(d.red + 1, k);
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// diagnostics and output on the device
+// ---------------------------------------------------------------------------------------------
+// calcNodalPressureFromElemental (Mechanical.C:1187-1212): p_node = sum p[e] vol[e] / sum vol[e]; the reference
+// scatters in ascending element order, which is the order of the node's nodel list
+template <int K>
+__global__ void __launch_bounds__(TPB_N) k_p_node(WfDev d, double *__restrict__ out) {
+  int n = blockIdx.x * blockDim.x + threadIdx.x;
+  int slice = n >> 5;
+  if (slice >= d.nslices) return;
+  const long long base = d.sell_ptr[slice];
+  const int width = (int)((d.sell_ptr[slice + 1] - base) >> 5);
+  const int lane = n & 31;
+  double pv = 0.0, acc = 0.0;
+  for (int j = 0; j < width; j++) {
+    int slot = __ldg(d.sell_slots + base + ((long long)j << 5) + lane);
+    if (slot >= 0) {
+      const int e = slot / K;
+      const double ve = d.vol[e];
+      pv += d.p[e] * ve;
+      acc += ve;
+    }
+  }
+  if (n >= d.nn) return;
+  if (acc > 0.0) pv /= acc;
+  out[n] = pv;
+}
+
+WF_DI double warp_min(double v) {
+  for (int o = 16; o > 0; o >>= 1) v = fmin(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+WF_DI double warp_max(double v) {
+  for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// calcMinEdgeLength (Domain_d.C:2224-2468): min edge length / min height; 3D elements are read as the tetrahedron of
+// their first four nodes (:2243-2247), 2D elements as quadrilaterals (:2381-2413).  keys[0] = min length,
+// keys[1] = min height as ordered keys (min is order-independent, so the result is the reference's bit for bit in
+// the strict flavour).  Values start at 1.0e6 like the reference.
+template <int D>
+__global__ void __launch_bounds__(128) k_min_edge(WfDev d, double *__restrict__ elem_length, unsigned long long *keys) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  double min_len = 1.0e6, eh = 1.0e6;
+  bool have_h = false;
+  if (e < d.ne) {
+    double P[4][D];
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      const int g = __ldg(d.elnod + (long long)i * d.ep + e);
+#pragma unroll
+      for (int c = 0; c < D; c++) P[i][c] = d.x[(long long)c * d.np + g];
+    }
+    if constexpr (D == 3) {
+      const int ed[6][2] = {{1, 0}, {2, 0}, {3, 0}, {2, 1}, {3, 1}, {3, 2}};
+#pragma unroll
+      for (int i = 0; i < 6; i++) {
+        const double a = P[ed[i][0]][0] - P[ed[i][1]][0], b = P[ed[i][0]][1] - P[ed[i][1]][1], c = P[ed[i][0]][2] - P[ed[i][1]][2];
+        const double len = sqrt(a * a + b * b + c * c);
+        if (len < min_len) min_len = len;
+      }
+      const int fc[4][3] = {{1, 2, 3}, {0, 2, 3}, {0, 1, 3}, {0, 1, 2}};
+#pragma unroll
+      for (int i = 0; i < 4; i++) {
+        double x1[3], x2[3], nr[3];
+#pragma unroll
+        for (int c = 0; c < 3; c++) { x1[c] = P[fc[i][1]][c] - P[fc[i][0]][c]; x2[c] = P[fc[i][2]][c] - P[fc[i][0]][c]; }
+        nr[0] = x1[1] * x2[2] - x1[2] * x2[1];
+        nr[1] = x1[2] * x2[0] - x1[0] * x2[2];
+        nr[2] = x1[0] * x2[1] - x1[1] * x2[0];
+        const double area = sqrt(nr[0] * nr[0] + nr[1] * nr[1] + nr[2] * nr[2]);
+        if (area < 1e-12) continue;
+        const double inv = 1.0 / area;
+        const double h = fabs((P[i][0] - P[fc[i][0]][0]) * (nr[0] * inv) + (P[i][1] - P[fc[i][0]][1]) * (nr[1] * inv) +
+                              (P[i][2] - P[fc[i][0]][2]) * (nr[2] * inv));
+        if (h < eh) eh = h;
+      }
+      have_h = true; // the reference updates min_height for every 3D element, even with the 1.0e6 sentinel
+    } else {
+      const double *A = P[0], *B = P[1], *C = P[2], *Dd = P[3];
+      const double lenAB = sqrt((B[0] - A[0]) * (B[0] - A[0]) + (B[1] - A[1]) * (B[1] - A[1]));
+      const double lenBC = sqrt((C[0] - B[0]) * (C[0] - B[0]) + (C[1] - B[1]) * (C[1] - B[1]));
+      const double lenCD = sqrt((Dd[0] - C[0]) * (Dd[0] - C[0]) + (Dd[1] - C[1]) * (Dd[1] - C[1]));
+      const double lenDA = sqrt((A[0] - Dd[0]) * (A[0] - Dd[0]) + (A[1] - Dd[1]) * (A[1] - Dd[1]));
+      min_len = fmin(min_len, fmin(fmin(lenAB, lenBC), fmin(lenCD, lenDA)));
+      const double area1 = 0.5 * fabs((B[0] - A[0]) * (C[1] - A[1]) - (C[0] - A[0]) * (B[1] - A[1]));
+      const double area2 = 0.5 * fabs((C[0] - A[0]) * (Dd[1] - A[1]) - (Dd[0] - A[0]) * (C[1] - A[1]));
+      const double area = area1 + area2;
+      if (area > 1e-14) {
+        eh = fmin(fmin(2.0 * area / lenAB, 2.0 * area / lenBC), fmin(2.0 * area / lenCD, 2.0 * area / lenDA));
+        have_h = true;
+      }
+    }
+    elem_length[e] = eh;
+  }
+  const double wl = warp_min(min_len), wh = warp_min(have_h ? eh : 1.0e6);
+  if ((threadIdx.x & 31) == 0) {
+    atomicMin(keys + 0, dbl_key(wl));
+    atomicMin(keys + 1, dbl_key(wh));
+  }
+}
+
+// max |v| over the nodes (Solver_explicit.C:583-587), keys[2]
+template <int D>
+__global__ void __launch_bounds__(256) k_max_vel(WfDev d, unsigned long long *keys) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  double m = 0.0;
+  if (n < d.nn) {
+    double s = 0.0;
+#pragma unroll
+    for (int c = 0; c < D; c++) { const double vv = d.v[(long long)c * d.np + n]; s += vv * vv; }
+    m = sqrt(s);
+  }
+  m = warp_max(m);
+  if ((threadIdx.x & 31) == 0) atomicMax(keys + 2, dbl_key(m));
+}
+
+// layout conversion between the private component-major arrays and the reference's interleaved records:
+//   aos[i * nc + c] <-> soa[c * pitch + i]   (scale: m_voln = sum / k)
+__global__ void k_soa_to_aos(const double *__restrict__ soa, long long pitch, int nc, long long n, double scale, double *__restrict__ aos) {
+  const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n * nc) return;
+  const long long i = j / nc;
+  const int c = (int)(j - i * nc);
+  aos[j] = soa[(long long)c * pitch + i] * scale;
+}
+__global__ void k_aos_to_soa(const double *__restrict__ aos, long long pitch, int nc, long long n, double *__restrict__ soa) {
+  const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n * nc) return;
+  const long long i = j / nc;
+  const int c = (int)(j - i * nc);
+  soa[(long long)c * pitch + i] = aos[j];
+}
+
 // ---------------------------------------------------------------------------------------------
 // unfused element kernels on stored intermediates (parity bisecting)
 // ---------------------------------------------------------------------------------------------
@@ -1102,6 +1238,29 @@ static void l_halo_finish(const WfDev &d, const WfPar &P, int mode, int parity, 
   else k_halo_finish<1><<<cdiv(d.n_uniq, 128), 128, 0, s>>>(d, P, parity);
 }
 
+static void l_p_node(const WfDev &d, double *out, cudaStream_t s) {
+  int g = cdiv((long long)d.nslices * 32, TPB_N);
+  switch (d.k) {
+    case 8: k_p_node<8><<<g, TPB_N, 0, s>>>(d, out); break;
+    case 4: k_p_node<4><<<g, TPB_N, 0, s>>>(d, out); break;
+    default: k_p_node<3><<<g, TPB_N, 0, s>>>(d, out); break;
+  }
+}
+static void l_min_edge(const WfDev &d, double *elem_length, unsigned long long *keys, cudaStream_t s) {
+  if (d.dim == 3) k_min_edge<3><<<cdiv(d.ne, 128), 128, 0, s>>>(d, elem_length, keys);
+  else k_min_edge<2><<<cdiv(d.ne, 128), 128, 0, s>>>(d, elem_length, keys);
+}
+static void l_max_vel(const WfDev &d, unsigned long long *keys, cudaStream_t s) {
+  if (d.dim == 3) k_max_vel<3><<<cdiv(d.nn, 256), 256, 0, s>>>(d, keys);
+  else k_max_vel<2><<<cdiv(d.nn, 256), 256, 0, s>>>(d, keys);
+}
+static void l_soa_to_aos(const double *soa, long long pitch, int nc, long long n, double scale, double *aos, cudaStream_t s) {
+  if (n > 0) k_soa_to_aos<<<(unsigned)((n * nc + 255) / 256), 256, 0, s>>>(soa, pitch, nc, n, scale, aos);
+}
+static void l_aos_to_soa(const double *aos, long long pitch, int nc, long long n, double *soa, cudaStream_t s) {
+  if (n > 0) k_aos_to_soa<<<(unsigned)((n * nc + 255) / 256), 256, 0, s>>>(aos, pitch, nc, n, soa);
+}
+
 // Force-load every kernel of the step (CUDA loads kernels lazily, and loading one synchronises the context:
 // a first launch issued while a halo wait kernel is spinning for work that the same host thread has not
 // enqueued yet would deadlock).
@@ -1143,6 +1302,7 @@ extern "C" const WfLaunch *WF_CAT(WF_NS, _table)() {
                              l_elem_main, l_node_update, l_node_mass, l_init_elem, l_vol0_density, l_density, l_xmin,
                              l_rebuild_sigma, l_energy, l_u_strain_rates, l_u_pressure, l_u_stress, l_u_artvisc,
                              l_u_forces, l_u_hourglass, l_u_nodal_vol, l_u_assembly, l_u_accel, l_u_corr_accvel,
-                             l_u_axis, l_u_corr_pos, l_halo_send, l_halo_wait, l_halo_finish, l_preload};
+                             l_u_axis, l_u_corr_pos, l_halo_send, l_halo_wait, l_halo_finish, l_preload, l_p_node, l_min_edge, l_max_vel, l_soa_to_aos,
+                             l_aos_to_soa};
   return &t;
 }

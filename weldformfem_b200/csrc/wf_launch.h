@@ -34,6 +34,11 @@ struct WfLaunch {
   void (*halo_wait)(const WfDev &, unsigned long long seq, unsigned long long timeout_ns, cudaStream_t);
   void (*halo_finish)(const WfDev &, const WfPar &, int mode, int parity, cudaStream_t);
   void (*preload)(int et, int dim, int k);
+  void (*p_node)(const WfDev &, double *out, cudaStream_t);
+  void (*min_edge)(const WfDev &, double *elem_length, unsigned long long *keys3, cudaStream_t);
+  void (*max_vel)(const WfDev &, unsigned long long *keys3, cudaStream_t);
+  void (*soa_to_aos)(const double *soa, long long pitch, int nc, long long n, double scale, double *aos, cudaStream_t);
+  void (*aos_to_soa)(const double *aos, long long pitch, int nc, long long n, double *soa, cudaStream_t);
 };
 
 extern "C" const WfLaunch *wf_strict_table();

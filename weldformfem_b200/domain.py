@@ -219,6 +219,25 @@ class Domain_d:
         self._ck(self._lib.wf_energies(self._h, C.byref(ek), C.byref(de)))
         return ek.value, de.value
 
+    def calcMinEdgeLength(self):                               # Domain_d.C:2224
+        a, b = C.c_double(), C.c_double()
+        self._ck(self._lib.wf_calcMinEdgeLength(self._h, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+    def max_velocity(self):
+        a = C.c_double()
+        self._ck(self._lib.wf_max_velocity(self._h, C.byref(a)))
+        return a.value
+
+    def cfl_dt(self, cfl_factor):                              # Solver_explicit.C:579-598
+        a = C.c_double()
+        self._ck(self._lib.wf_cfl_dt(self._h, float(cfl_factor), C.byref(a)))
+        return a.value
+
+    def set_dt(self, dt):
+        self._ck(self._lib.wf_set_dt(self._h, float(dt)))
+        self._dt = float(dt)
+
     def monitor_async(self):
         self._ck(self._lib.wf_monitor_async(self._h))
 
