@@ -240,7 +240,7 @@ __global__ void __launch_bounds__(TPB_N) k_node_vol(WfDev d, WfPar P, int mode) 
 // E2: the main element pass
 // ---------------------------------------------------------------------------------------------
 template <int ET>
-WF_DI double elem_pressure(const WfDev &d, const WfPar &P, int e, const int (&nid)[Elem<ET>::K], double vol,
+WF_DI double elem_pressure(const WfDev &d, const WfPar &P, int e, const double (&np_)[Elem<ET>::K], double vol,
                            double vol0, double rho_e, const double (&dH)[Elem<ET>::D][Elem<ET>::K],
                            const double (&vl)[Elem<ET>::K][Elem<ET>::D]) {
   constexpr int K = Elem<ET>::K, D = Elem<ET>::D;
@@ -248,7 +248,7 @@ WF_DI double elem_pressure(const WfDev &d, const WfPar &P, int e, const int (&ni
     if constexpr (D == 3) {
       double J_avg = 0.0;
 #pragma unroll
-      for (int a = 0; a < K; a++) J_avg += d.nodal_p[nid[a]];
+      for (int a = 0; a < K; a++) J_avg += np_[a];
       J_avg /= (double)K;
       double div_v = 0.0;
       if (!P.stab_simple) {
@@ -262,29 +262,68 @@ WF_DI double elem_pressure(const WfDev &d, const WfPar &P, int e, const int (&ni
   } else if (P.press == 1) { // as shipped: p += sum pn ; p *= 0.25 k  (Mechanical.C:1243-1247)
     double pe = d.p[e];
 #pragma unroll
-    for (int a = 0; a < K; a++) pe += d.nodal_p[nid[a]];
+    for (int a = 0; a < K; a++) pe += np_[a];
     pe *= 0.25 * K;
     return pe;
   } else { // ANP_Nodal (Mechanical.C:1287-1294)
     double pe = 0.0;
 #pragma unroll
-    for (int a = 0; a < K; a++) pe += d.nodal_p[nid[a]];
+    for (int a = 0; a < K; a++) pe += np_[a];
     pe /= (double)K;
     return pe;
   }
 }
+template <int ET>
+WF_DI void gather_nodal_p(const WfDev &d, const int (&nid)[Elem<ET>::K], double (&np_)[Elem<ET>::K]) {
+#pragma unroll
+  for (int a = 0; a < Elem<ET>::K; a++) np_[a] = d.nodal_p[nid[a]];
+}
 
 // mode bits: 1 = hourglass force kept separate in f_elem_hg (strict two-pass assembly)
-template <int ET, bool SEPARATE_HG>
-__global__ void __launch_bounds__(TPB_E) k_elem_main(WfDev d, WfPar P) {
+// STAGED: the CTA first loads x, v and the nodal ratio of its UNIQUE nodes into shared memory (WfDev::blk_off),
+// then every element reads its nodes through 16-bit block-local indices; otherwise every element gathers its own.
+template <int ET, bool SEPARATE_HG, bool STAGED>
+__global__ void __launch_bounds__(TPB_E) k_elem_main(WfDev d, WfPar P, int stride) {
   constexpr int K = Elem<ET>::K, D = Elem<ET>::D;
+  extern __shared__ double sm[];
   int e = blockIdx.x * blockDim.x + threadIdx.x;
-  if (e >= d.ne) return;
-  int nid[K];
-  load_conn<ET>(d, e, nid);
-  double xl[K][D], vl[K][D], A[D][D], dH[D][K], detJ;
-  gather_nodal<ET>(d.x, d.np, nid, xl);
-  gather_nodal<ET>(d.v, d.np, nid, vl);
+  double xl[K][D], vl[K][D], npn[K], A[D][D], dH[D][K], detJ;
+  if constexpr (STAGED) {
+    static_assert(TPB_E == WF_EBLK, "block node tables are built for WF_EBLK elements per CTA");
+    const int b = blockIdx.x;
+    const int u0 = __ldg(d.blk_off + b), U = __ldg(d.blk_off + b + 1) - u0;
+    for (int i = threadIdx.x; i < U; i += TPB_E) {
+      const int g = __ldg(d.blk_nodes + u0 + i);
+#pragma unroll
+      for (int c = 0; c < D; c++) {
+        sm[c * stride + i] = d.x[(long long)c * d.np + g];
+        sm[(D + c) * stride + i] = d.v[(long long)c * d.np + g];
+      }
+      sm[2 * D * stride + i] = d.nodal_p[g];
+    }
+    unsigned li[K];
+    const int ee = e < d.ne ? e : d.ne - 1;
+#pragma unroll
+    for (int n = 0; n < K; n++) li[n] = d.lidx[(long long)n * d.ep + ee];
+    __syncthreads();
+    if (e >= d.ne) return;
+#pragma unroll
+    for (int n = 0; n < K; n++) {
+#pragma unroll
+      for (int c = 0; c < D; c++) {
+        xl[n][c] = sm[c * stride + li[n]];
+        vl[n][c] = sm[(D + c) * stride + li[n]];
+      }
+      npn[n] = sm[2 * D * stride + li[n]];
+    }
+  } else {
+    if (e >= d.ne) return;
+    int nid[K];
+    load_conn<ET>(d, e, nid);
+    gather_nodal<ET>(d.x, d.np, nid, xl);
+    gather_nodal<ET>(d.v, d.np, nid, vl);
+    gather_nodal_p<ET>(d, nid, npn);
+  }
   // independent loads issued early
   double tau[6];
 #pragma unroll
@@ -301,7 +340,7 @@ __global__ void __launch_bounds__(TPB_E) k_elem_main(WfDev d, WfPar P) {
   shape_derivs<ET>(A, dH);
   double Dr[6], Wr[3];
   strain_rates<ET>(dH, detJ, vl, radius, d.domtype, Dr, Wr);
-  const double p = elem_pressure<ET>(d, P, e, nid, vol, vol0, rho_e, dH, vl);
+  const double p = elem_pressure<ET>(d, P, e, npn, vol, vol0, rho_e, dH, vl);
   StressOut so;
   stress_update(P, P.dt, p, Dr, Wr, tau, pl, sy_prev, so);
   if (P.track_eps) {
@@ -799,10 +838,11 @@ __global__ void k_u_pressure(WfDev d, WfPar P) {
   if (e >= d.ne) return;
   int nid[K];
   load_conn<ET>(d, e, nid);
-  double vl[K][D], dH[D][K];
+  double vl[K][D], dH[D][K], npn[K];
   gather_nodal<ET>(d.v, d.np, nid, vl);
+  gather_nodal_p<ET>(d, nid, npn);
   load_dH<ET>(d, e, dH);
-  d.p[e] = elem_pressure<ET>(d, P, e, nid, d.vol[e], d.vol_0[e], d.rho[e], dH, vl);
+  d.p[e] = elem_pressure<ET>(d, P, e, npn, d.vol[e], d.vol_0[e], d.rho[e], dH, vl);
 }
 
 __global__ void k_u_stress(WfDev d, WfPar P, double dt) {
@@ -1147,8 +1187,17 @@ static void l_elem_main(const WfDev &d, const WfPar &P, int et, int separate_hg,
     hexfast::k_elem_main_hex_fast<<<cdiv(d.ne, hexfast::TPB), hexfast::TPB, hexfast::SMEM_BYTES, s>>>(d, P);
     return;
   }
-  if (separate_hg) { ELEM_DISPATCH(et, k_elem_main<ET, true><<<cdiv(d.ne, TPB_E), TPB_E, 0, s>>>(d, P)); }
-  else { ELEM_DISPATCH(et, k_elem_main<ET, false><<<cdiv(d.ne, TPB_E), TPB_E, 0, s>>>(d, P)); }
+  const int stride = (d.blk_umax + 31) / 32 * 32;
+  // measured (tools/kbench.py): per-element gathers beat block staging for tets, quads and the strict hexa kernel
+  // (0.71 vs 0.78 ms at 10M tets); the staged form is kept as variant 8
+  const bool staged = P.variant[2] == 8;
+  if (staged) {
+    if (separate_hg) { ELEM_DISPATCH(et, k_elem_main<ET, true, true><<<cdiv(d.ne, TPB_E), TPB_E, (2 * Elem<ET>::D + 1) * stride * 8, s>>>(d, P, stride)); }
+    else { ELEM_DISPATCH(et, k_elem_main<ET, false, true><<<cdiv(d.ne, TPB_E), TPB_E, (2 * Elem<ET>::D + 1) * stride * 8, s>>>(d, P, stride)); }
+  } else {
+    if (separate_hg) { ELEM_DISPATCH(et, k_elem_main<ET, true, false><<<cdiv(d.ne, TPB_E), TPB_E, 0, s>>>(d, P, 0)); }
+    else { ELEM_DISPATCH(et, k_elem_main<ET, false, false><<<cdiv(d.ne, TPB_E), TPB_E, 0, s>>>(d, P, 0)); }
+  }
 }
 template <bool SEP, int U>
 static void node_update_t(const WfDev &d, const WfPar &P, int fuse, int phase, cudaStream_t s) {
@@ -1275,7 +1324,10 @@ static void l_preload(int et, int dim, int k) {
   cudaFuncSetAttribute(hexfast::k_elem_main_hex_staged, cudaFuncAttributeMaxDynamicSharedMemorySize, 7 * 1024 * 8);
   touch(hexfast::k_elem_main_hex_staged);
   touch(k_predict<2>); touch(k_predict<3>); touch(k_impose_bc);
-  ELEM_DISPATCH(et, touch(k_elem_vol<ET>); touch(k_elem_main<ET, true>); touch(k_elem_main<ET, false>));
+  ELEM_DISPATCH(et, touch(k_elem_vol<ET>); touch(k_elem_main<ET, true, false>); touch(k_elem_main<ET, false, false>);
+                cudaFuncSetAttribute(k_elem_main<ET, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 7 * 1024 * 8);
+                cudaFuncSetAttribute(k_elem_main<ET, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 7 * 1024 * 8);
+                touch(k_elem_main<ET, true, true>); touch(k_elem_main<ET, false, true>));
   touch(k_node_vol<8>); touch(k_node_vol<4>); touch(k_node_vol<3>);
   // per device: the regrouped hexa kernel stages 48 KB of node data per CTA
   cudaFuncSetAttribute(hexfast::k_elem_main_hex_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, hexfast::SMEM_BYTES);
