@@ -94,6 +94,24 @@ int wf_allocate_bcs(wf_engine *);                              /* AllocateBCs, D
  * asynchronous on the engine's stream (time-dependent prescribed velocities) */
 int wf_set_bc_values(wf_engine *, int dim, int count, const double *vals);
 
+/* ---- contact with rigid tool surfaces (tetrahedra in 3D, quadrilaterals in 2D like the reference) --- */
+/* Domain_d::SearchExtNodes (Domain_d.C:110-205): external faces / nodes + CalcExtFaceAreas; call after the mesh is set */
+int wf_SearchExtNodes(wf_engine *);
+int wf_CalcExtFaceAreas(wf_engine *); /* Domain_d.C:210-315; the step recomputes it every 10th step in 3D (Solver_explicit.C:445-450) */
+/* Domain_d::setTriMesh with the flattened TriMesh_d (include/common/Mesh.h:72-140) the reference holds after
+ * AxisPlaneMesh / AddMesh (main.C:672-708, :775-828): node and node_v as xyz triples, elnode with 3 (3D) or 2 (2D) node
+ * ids per facet, initial facet normals, ele_mesh_id.  The engine moves the surfaces itself every step
+ * (velocity ramp, Move, CalcNormals, UpdatePlaneCoeff; Solver_explicit.C:981-1005). */
+int wf_set_trimesh(wf_engine *, int dimension, int n_nodes, int n_elems, const double *node, const double *node_v,
+                   const int *elnode, const double *normal, const int *ele_mesh_id);
+/* friction coefficients mu_sta[0] / mu_dyn[0], setContactPF (penalty_factor <= -1 keeps the default 0.1), CalcSpheres +
+ * setContactOn (main.C:716-725, :842-847) and SetEndTime (the surface velocity ramps over the first 1 % of end_time);
+ * needs wf_calcMinEdgeLength (m_elem_length, main.C:862) before wf_init */
+int wf_set_contact(wf_engine *, double mu_sta, double mu_dyn, double penalty_factor, double end_time);
+int wf_CalcContactForces(wf_engine *); /* Contact.C:31-336, unfused entry point */
+int wf_MoveTriMesh(wf_engine *);       /* Solver_explicit.C:981-1005, unfused entry point */
+int wf_get_trimesh_counts(wf_engine *, int *dimension, int *n_nodes, int *n_elems);
+
 /* ---- solve --------------------------------------------------------------------------------------- */
 int wf_init(wf_engine *, double dt);  /* Solver_explicit.C:115-292 incl. SetDT; CH constants rho_b = 0.8182 */
 int wf_step(wf_engine *, int nsteps); /* fused rows 1-22 of the step, Solver_explicit.C:524-978 */
@@ -208,6 +226,14 @@ int wf_host_box_counts(const double L[3], double r, int tritet, int *dim, int *n
 int wf_host_gen_box(const double V[3], const double L[3], double r, int tritet, double *x, unsigned *elnod);
 int wf_host_nodel(int n_nodes, int n_elems, int nodxelem, const unsigned *elnod, int *nodel_offset,
                   int *nodel_count, int *nodel /*N_e*k*/, int *nodel_loc /*N_e*k*/);
+/* SearchExtNodes, integer part: ext_nodes[n_nodes] flags, m_faceCount, and the external faces in faceList order
+ * (ext_face_nodes: 3 (tets) / 2 (quads) ids per face, capacity 4*n_elems faces; ext_face_elem: owning element) */
+int wf_host_ext_faces(int dim, int nodxelem, int n_nodes, int n_elems, const unsigned *elnod, unsigned char *ext_nodes,
+                      int *n_faces_total, int *n_ext_faces, int *ext_face_nodes, int *ext_face_elem);
+/* TriMesh_d::AxisPlaneMesh (Mesh.C:48-283): one rigid plane (3D: 2*dens^2 triangles) or line (2D: dens segments) */
+int wf_host_axis_plane_counts(int dimension, int dens, int *n_nodes, int *n_elems);
+int wf_host_axis_plane_mesh(int dimension, int mesh_id, int axis, int positaxisorent, const double p1[3], const double p2[3],
+                            int dens, double *node, int *elnode, double *normal, int *ele_mesh_id);
 const char *wf_version(void);
 
 #ifdef __cplusplus

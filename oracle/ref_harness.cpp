@@ -26,6 +26,7 @@
 #include <unistd.h>
 
 #include "Domain_d.h"
+#include "Mesh.h"
 
 using namespace MetFEM;
 
@@ -60,6 +61,8 @@ class Harness : public Domain_d {
   double hexa_hg_coeff = 0;  // 0 = off (reference C++ behaviour); 0.06 = F90 value
   Material_ *mat_h = nullptr;
   double time_ = 0.0;
+  long step_count_ = 0;
+  double3 *v_orig_ = nullptr;  // m_v_orig, Solver_explicit.C:168-173
 
   Harness() {
     m_faceCount = 0;
@@ -85,7 +88,10 @@ class Harness : public Domain_d {
     z(vol, ne); z(vol_0, ne); z(m_detJ, ne);
     z(m_f_elem, nk); z(m_f_elem_hg, nk);
     z(m_mdiag, m_node_count); z(m_voln, m_node_count); z(p_node, m_node_count);
-    z(T, m_node_count);
+    z(T, m_node_count); z(node_area, m_node_count); z(q_cont_conv, m_node_count); z(m_elem_area, ne);
+    z(m_elem_length, ne);
+    if (ext_nodes) memset(ext_nodes, 0, sizeof(bool) * m_node_count);
+    if (m_mesh_in_contact) memset(m_mesh_in_contact, 0xff, sizeof(int) * m_node_count);
     if (m_dim == 2 && m_hg_q) z(m_hg_q, nk);
     m_faceCount = 0;
     contact = false;
@@ -153,6 +159,87 @@ class Harness : public Domain_d {
     CalcNodalMassFromVol();
     for (int n = 0; n < m_node_count * m_dim; n++) ut_prev[n] = 0.0;
     time_ = 0.0;
+    step_count_ = 0;
+    if (contact) {  // Solver_explicit.C:168-173
+      v_orig_ = new double3[trimesh->nodecount];
+      for (int n = 0; n < trimesh->nodecount; n++) v_orig_[n] = trimesh->node_v[n];
+    }
+  }
+
+  // ---- contact with rigid surfaces ----------------------------------------------------
+  // main.C:672-708 (first body) / :775-828 (further bodies): AxisPlaneMesh, node velocities, AddMesh
+  void add_plane(int dimension, int id, int axis, int positaxisorent, const double *p1, const double *p2, int dens,
+                 const double *vel) {
+    CoutSilencer s; StdoutSilencer s2;
+    double3 a = make_double3(p1[0], p1[1], p1[2]), b = make_double3(p2[0], p2[1], p2[2]);
+    double3 vv = make_double3(vel[0], vel[1], vel[2]);
+    if (!trimesh) {
+      TriMesh_d *m = new TriMesh_d();
+      m->dimension = dimension;
+      m->AxisPlaneMesh(id, axis, positaxisorent != 0, a, b, dens);
+      setTriMesh(m);
+      for (int nc = 0; nc < m->nodecount; nc++) m->node_v[nc] = vv;
+      m->mu_sta[0] = m->mu_dyn[0] = 0.0;
+    } else {
+      TriMesh_d *m = new TriMesh_d();
+      m->dimension = dimension;
+      m->AxisPlaneMesh(id, axis, positaxisorent != 0, a, b, dens);
+      m->SetMeshVel(vv);
+      addMeshData(*m);
+      delete m;
+    }
+  }
+  // the same TriMesh_d state from raw arrays (what a caller of the engine's wf_set_trimesh holds)
+  void set_trimesh(int dimension, int nn, int ne, const double *node, const double *node_v, const int *elnode,
+                   const double *normal, const int *mesh_id) {
+    TriMesh_d *m = new TriMesh_d();
+    const int nen = dimension == 3 ? 3 : 2;
+    m->dimension = dimension; m->nodecount = nn; m->elemcount = ne; m->mesh_count = 1;
+    m->node = (double3 *)malloc(sizeof(double3) * nn);
+    m->node_v = (double3 *)malloc(sizeof(double3) * nn);
+    m->elnode = (int *)malloc(sizeof(int) * nen * ne);
+    m->centroid = (double3 *)malloc(sizeof(double3) * ne);
+    m->normal = (double3 *)malloc(sizeof(double3) * ne);
+    m->pplane = (double *)malloc(sizeof(double) * ne);
+    m->nfar = (int *)malloc(sizeof(int) * ne);
+    m->ele_mesh_id = (int *)malloc(sizeof(int) * ne);
+    m->mu_sta = (double *)calloc(1, sizeof(double));
+    m->mu_dyn = (double *)calloc(1, sizeof(double));
+    m->react_force = (double3 *)calloc(1, sizeof(double3));
+    m->react_p_force = (double *)calloc(1, sizeof(double));
+    for (int i = 0; i < nn; i++) {
+      m->node[i] = make_double3(node[3 * i], node[3 * i + 1], node[3 * i + 2]);
+      m->node_v[i] = make_double3(node_v[3 * i], node_v[3 * i + 1], node_v[3 * i + 2]);
+    }
+    memcpy(m->elnode, elnode, sizeof(int) * nen * ne);
+    for (int e = 0; e < ne; e++) {
+      m->normal[e] = make_double3(normal[3 * e], normal[3 * e + 1], normal[3 * e + 2]);
+      m->ele_mesh_id[e] = mesh_id[e];
+    }
+    m->CalcCentroids();
+    setTriMesh(m);
+  }
+  // main.C:716-725 (friction, penalty factor), :842-847 (CalcSpheres, setContactOn), SetEndTime
+  void contact_on(double mu_sta, double mu_dyn, double pf, double end_time) {
+    CoutSilencer s; StdoutSilencer s2;
+    trimesh->mu_sta[0] = mu_sta; trimesh->mu_dyn[0] = mu_dyn;
+    trimesh->heat_cond = 0.0;
+    if (pf > -1.0) setContactPF(pf);
+    trimesh->CalcSpheres();
+    setContactOn();
+    SetEndTime(end_time);
+  }
+  void search_ext_nodes() { CoutSilencer s; StdoutSilencer s2; SearchExtNodes(); }  // main.C:650
+  // Solver_explicit.C:981-1005: velocity ramp of the rigid surfaces, Move, centroids, normals, plane coefficients
+  void move_trimesh() {
+    const double RAMP_FRACTION = 1.0e-2;  // Solver_explicit.C:309
+    double f = 1.0;
+    if (time_ < RAMP_FRACTION * end_t) f = pow(time_ / (RAMP_FRACTION * end_t), 0.5);
+    for (int n = 0; n < trimesh->nodecount; n++) trimesh->node_v[n] = f * v_orig_[n];
+    trimesh->Move(dt);
+    trimesh->CalcCentroids();
+    trimesh->CalcNormals();
+    trimesh->UpdatePlaneCoeff();
   }
 
   // 3D hexa viscous hourglass, f90_ver/src/Mechanical.f90:241-344 (Goudreau 1982):
@@ -213,6 +300,7 @@ class Harness : public Domain_d {
 
   // one time step: Solver_explicit.C:524-978 (rows 1-22 of SURVEY.md §3.3)
   void step_once() {
+    if (m_dim > 2 && m_faceCount > 0 && step_count_ % 10 == 0) CalcExtFaceAreas();  // Solver_explicit.C:445-450
     UpdatePrediction();
     for (int d = 0; d < m_dim; d++) ImposeBCV(d);
     calcElemJAndDerivatives();
@@ -227,6 +315,7 @@ class Harness : public Domain_d {
     calcArtificialViscosity();
     calcElemForces();
     hourglass();
+    if (contact) CalcContactForces();  // Solver_explicit.C:769-770
     assemblyForces();
     for (int i = 0; i < m_node_count * m_dim; ++i)
       if (!std::isfinite(m_fi[i])) m_fi[i] = 0.0;
@@ -236,7 +325,9 @@ class Harness : public Domain_d {
     ImposeBCVAllDim();
     axis_constraint();
     UpdateCorrectionPos();
+    if (contact) move_trimesh();
     time_ += dt;
+    step_count_++;
   }
 
   void steps(int n) {
@@ -272,6 +363,10 @@ class Harness : public Domain_d {
     else if (f == "UpdateCorrectionAccVel") UpdateCorrectionAccVel();
     else if (f == "AxisConstraint") axis_constraint();
     else if (f == "UpdateCorrectionPos") UpdateCorrectionPos();
+    else if (f == "SearchExtNodes") SearchExtNodes();
+    else if (f == "CalcExtFaceAreas") CalcExtFaceAreas();
+    else if (f == "CalcContactForces") CalcContactForces();
+    else if (f == "MoveTriMesh") move_trimesh();
     else return -1;
     return 0;
   }
@@ -317,6 +412,21 @@ class Harness : public Domain_d {
     if (nm == "m_f_elem_hg") return {m_f_elem_hg, nk * m_dim};
     if (nm == "m_hg_q") return {m_dim == 2 ? m_hg_q : nullptr, m_dim == 2 ? nk * m_dim : 0};
     if (nm == "m_elem_length") return {m_elem_length, ne};
+    if (nm == "contforce") return {contforce, nd};
+    if (nm == "ut_prev") return {ut_prev, nd};
+    if (nm == "node_area") return {node_area, nn};
+    if (nm == "m_elem_area") return {m_elem_area, ne};
+    if (nm == "ext_nodes") return {ext_nodes, sizeof(bool) * (size_t)m_node_count};
+    if (nm == "m_mesh_in_contact") return {m_mesh_in_contact, sizeof(int) * (size_t)m_node_count};
+    if (trimesh) {
+      const size_t tn = sizeof(double3) * (size_t)trimesh->nodecount, te = (size_t)trimesh->elemcount;
+      if (nm == "trimesh.node") return {trimesh->node, tn};
+      if (nm == "trimesh.node_v") return {trimesh->node_v, tn};
+      if (nm == "trimesh.normal") return {trimesh->normal, sizeof(double3) * te};
+      if (nm == "trimesh.pplane") return {trimesh->pplane, sizeof(double) * te};
+      if (nm == "trimesh.elnode") return {trimesh->elnode, sizeof(int) * te * (trimesh->dimension == 3 ? 3 : 2)};
+      if (nm == "trimesh.ele_mesh_id") return {trimesh->ele_mesh_id, sizeof(int) * te};
+    }
     if (nm == "bcx_val") return {bcx_val, sizeof(double) * (size_t)bc_count[0]};
     if (nm == "bcy_val") return {bcy_val, sizeof(double) * (size_t)bc_count[1]};
     if (nm == "bcz_val") return {bcz_val, sizeof(double) * (size_t)bc_count[2]};
@@ -379,6 +489,24 @@ void wfref_set_options(void *h, int press_variant, double av_alpha, double av_be
   d->m_artifvisc[0] = av_alpha;
   d->m_artifvisc[1] = av_beta;
   d->hexa_hg_coeff = hexa_hg_coeff;
+}
+void wfref_add_plane(void *h, int dimension, int id, int axis, int positaxisorent, const double *p1, const double *p2,
+                     int dens, const double *vel) {
+  ((Harness *)h)->add_plane(dimension, id, axis, positaxisorent, p1, p2, dens, vel);
+}
+void wfref_set_trimesh(void *h, int dimension, int nn, int ne, const double *node, const double *node_v,
+                       const int *elnode, const double *normal, const int *mesh_id) {
+  ((Harness *)h)->set_trimesh(dimension, nn, ne, node, node_v, elnode, normal, mesh_id);
+}
+void wfref_contact_on(void *h, double mu_sta, double mu_dyn, double pf, double end_time) {
+  ((Harness *)h)->contact_on(mu_sta, mu_dyn, pf, end_time);
+}
+void wfref_trimesh_counts(void *h, int *out) {
+  Harness *d = (Harness *)h;
+  TriMesh_d *m = d->getTriMesh();
+  out[0] = m ? m->dimension : 0;
+  out[1] = m ? m->nodecount : 0;
+  out[2] = m ? m->elemcount : 0;
 }
 void wfref_add_bc(void *h, int node, int dim, double val) { ((Harness *)h)->AddBCVelNode(node, dim, val); }
 void wfref_allocate_bcs(void *h) { CoutSilencer s; ((Harness *)h)->AllocateBCs(); }

@@ -23,9 +23,22 @@ PORT_SO = os.path.join(HERE, "_build", "libwf_oracle.so")
 
 _DBL = ("x v a u u_dt prev_a m_fi m_fe m_mdiag m_voln p_node m_dH_detJ_dx m_dH_detJ_dy m_dH_detJ_dz "
         "m_detJ vol vol_0 rho rho_0 p pl_strain sigma_y m_radius m_str_rate m_rot_rate m_sigma m_tau "
-        "m_eps m_f_elem m_f_elem_hg m_hg_q m_voln_0 m_Jn bcx_val bcy_val bcz_val m_elem_length").split()
-_INT = "m_nodel m_nodel_loc m_nodel_offset m_nodel_count".split()
+        "m_eps m_f_elem m_f_elem_hg m_hg_q m_voln_0 m_Jn bcx_val bcy_val bcz_val m_elem_length "
+        "contforce ut_prev node_area m_elem_area trimesh.node trimesh.node_v trimesh.normal trimesh.pplane").split()
+_INT = ("m_nodel m_nodel_loc m_nodel_offset m_nodel_count m_mesh_in_contact trimesh.elnode "
+        "trimesh.ele_mesh_id").split()
 _UINT = ["m_elnod"]
+_BYTE = ["ext_nodes"]
+
+
+def _dtype_of(name):
+    if name in _DBL:
+        return np.float64
+    if name in _UINT:
+        return np.uint32
+    if name in _BYTE:
+        return np.uint8
+    return np.int32
 
 HOLLOMON = 1
 BILINEAR = 0
@@ -72,6 +85,10 @@ class _Base:
             "set_stab": (None, [vp, dp]),
             "set_options": (None, [vp, C.c_int, C.c_double, C.c_double, C.c_double]),
             "add_bc": (None, [vp, C.c_int, C.c_int, C.c_double]),
+            "add_plane": (None, [vp, C.c_int, C.c_int, C.c_int, C.c_int, dp, dp, C.c_int, dp]),
+            "set_trimesh": (None, [vp, C.c_int, C.c_int, C.c_int, dp, dp, ip, dp, ip]),
+            "contact_on": (None, [vp] + [C.c_double] * 4),
+            "trimesh_counts": (None, [vp, ip]),
             "allocate_bcs": (None, [vp]),
             "init": (None, [vp, C.c_double]),
             "step": (None, [vp, C.c_int]),
@@ -133,6 +150,33 @@ class _Base:
     def allocate_bcs(self):
         self._f("allocate_bcs")(self.h)
 
+    # ---- contact with rigid surfaces (src/explicit/main.C:636-848) ------------------------------
+    def add_plane(self, dimension, mesh_id, axis, positaxisorent, p1, p2, dens, vel=(0.0, 0.0, 0.0)):
+        """TriMesh_d::AxisPlaneMesh (+ AddMesh for every body after the first) with node velocity ``vel``."""
+        a3 = lambda q: (C.c_double * 3)(*[float(t) for t in q])
+        self._f("add_plane")(self.h, int(dimension), int(mesh_id), int(axis), int(bool(positaxisorent)), a3(p1),
+                             a3(p2), int(dens), a3(vel))
+
+    def set_trimesh(self, dimension, node, node_v, elnode, normal, mesh_id):
+        node = np.ascontiguousarray(node, dtype=np.float64)
+        node_v = np.ascontiguousarray(node_v, dtype=np.float64)
+        elnode = np.ascontiguousarray(elnode, dtype=np.int32)
+        normal = np.ascontiguousarray(normal, dtype=np.float64)
+        mesh_id = np.ascontiguousarray(mesh_id, dtype=np.int32)
+        dp, ip = C.POINTER(C.c_double), C.POINTER(C.c_int)
+        self._f("set_trimesh")(self.h, int(dimension), node.size // 3, mesh_id.size, node.ctypes.data_as(dp),
+                               node_v.ctypes.data_as(dp), elnode.ctypes.data_as(ip), normal.ctypes.data_as(dp),
+                               mesh_id.ctypes.data_as(ip))
+
+    def contact_on(self, mu_sta=0.0, mu_dyn=0.0, penalty_factor=-1.0, end_time=1.0):
+        """friction + penalty factor (main.C:716-725), CalcSpheres + setContactOn (:842-847), SetEndTime."""
+        self._f("contact_on")(self.h, float(mu_sta), float(mu_dyn), float(penalty_factor), float(end_time))
+
+    def trimesh_counts(self):
+        out = (C.c_int * 3)()
+        self._f("trimesh_counts")(self.h, out)
+        return dict(zip("dimension nodecount elemcount".split(), list(out)))
+
     def init(self, dt):
         self._f("init")(self.h, dt)
 
@@ -180,7 +224,7 @@ class _Base:
         return ek.value, de.value
 
     def get(self, name):
-        dt = np.float64 if name in _DBL else (np.uint32 if name in _UINT else np.int32)
+        dt = _dtype_of(name)
         need = self._f("get")(self.h, name.encode(), None, 0)
         if need == -1:
             raise KeyError(name)
@@ -192,7 +236,7 @@ class _Base:
         return out
 
     def set(self, name, arr):
-        dt = np.float64 if name in _DBL else (np.uint32 if name in _UINT else np.int32)
+        dt = _dtype_of(name)
         arr = np.ascontiguousarray(arr, dtype=dt)
         rc = self._f("set")(self.h, name.encode(), arr.ctypes.data_as(C.c_void_p), arr.nbytes)
         if rc != arr.nbytes:

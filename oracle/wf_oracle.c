@@ -45,6 +45,17 @@ struct wfo_domain {
   double av[2], hexa_hg;
   double dt, alpha, beta, gamma, time;
   double *m_elem_length, m_min_length, m_min_height; /* calcMinEdgeLength products */
+  /* contact with rigid surfaces (Contact.C, Mesh.h/Mesh.C) */
+  int contact, faceCount, *face_nodes /*[faceCount][4]*/, *face_count, *face_elem, *m_mesh_in_contact;
+  unsigned char *ext_nodes;
+  double *contforce, *ut_prev, *node_area, *m_elem_area;
+  double m_contPF, end_t;
+  long step_count;
+  struct { /* TriMesh_d */
+    int dimension, nodecount, elemcount, *elnode, *ele_mesh_id, *nfar;
+    double *node, *node_v, *v_orig, *centroid, *normal, *pplane; /* double3 arrays as xyzxyz */
+    double mu_sta, mu_dyn;
+  } tm;
 };
 
 static void *zalloc(size_t n, size_t sz) { return calloc(n ? n : 1, sz); }
@@ -54,9 +65,11 @@ wfo_domain *wfo_new(void) {
   d->dim = 3;
   d->domtype = DOM_3D;
   d->stab[11] = 0.1; /* hg_stiff default, Domain_d.h:294 */
+  d->m_contPF = 0.1;  /* Domain_d.h:256 */
   return d;
 }
 
+static void tm_free(wfo_domain *d);
 static void free_mesh(wfo_domain *d) {
   double **dp[] = {&d->x, &d->v, &d->a, &d->u, &d->u_dt, &d->prev_a, &d->m_fi, &d->m_fe, &d->m_mdiag, &d->m_voln,
                    &d->p_node, &d->m_voln_0, &d->m_Jn, &d->dHx, &d->dHy, &d->dHz, &d->m_detJ, &d->vol, &d->vol_0,
@@ -65,6 +78,10 @@ static void free_mesh(wfo_domain *d) {
                    &d->m_f_elem_hg, &d->m_hg_q};
   for (size_t i = 0; i < sizeof(dp) / sizeof(dp[0]); i++) { free(*dp[i]); *dp[i] = NULL; }
   free(d->m_elnod); d->m_elnod = NULL;
+  free(d->contforce); free(d->ut_prev); free(d->node_area); free(d->m_elem_area); free(d->ext_nodes);
+  free(d->m_mesh_in_contact); free(d->face_nodes); free(d->face_count); free(d->face_elem);
+  d->contforce = d->ut_prev = d->node_area = d->m_elem_area = NULL; d->ext_nodes = NULL;
+  d->m_mesh_in_contact = d->face_nodes = d->face_count = d->face_elem = NULL; d->faceCount = 0; d->contact = 0;
   free(d->m_nodel); free(d->m_nodel_loc); free(d->m_nodel_offset); free(d->m_nodel_count);
   d->m_nodel = d->m_nodel_loc = d->m_nodel_offset = d->m_nodel_count = NULL;
 }
@@ -72,6 +89,7 @@ static void free_mesh(wfo_domain *d) {
 void wfo_free(wfo_domain *d) {
   if (!d) return;
   free_mesh(d);
+  tm_free(d);
   for (int i = 0; i < 3; i++) { free(d->bc_nod[i]); free(d->bc_val[i]); }
   free(d);
 }
@@ -104,6 +122,11 @@ static void set_dimension(wfo_domain *d, int nn, int ne) {
   d->m_f_elem = zalloc(nk * d->dim, 8); d->m_f_elem_hg = zalloc(nk * d->dim, 8);
   d->m_hg_q = zalloc(nk * d->dim, 8);
   d->m_elnod = zalloc(nk, sizeof(unsigned));
+  d->contforce = zalloc(nd + 3, 8); d->ut_prev = zalloc(nd + 3, 8); /* +3: the reference writes ut_prev[dim*i+2] in 2D */
+  d->node_area = zalloc(nn, 8); d->m_elem_area = zalloc(ne, 8);
+  d->ext_nodes = zalloc(nn, 1);
+  d->m_mesh_in_contact = zalloc(nn, sizeof(int));
+  for (int n = 0; n < nn; n++) d->m_mesh_in_contact[n] = -1;
 }
 
 /* Domain_d::setNodElem (Domain_d.C:1508-1611) == tail of AddBoxLength (:1435-1481):
@@ -469,7 +492,7 @@ static void calcElemStrainRates(wfo_domain *d) {
   }
 }
 
-/* calcElemPressure (Mechanical.C:691-819), contact off */
+/* calcElemPressure (Mechanical.C:691-819) */
 static void calcElemPressure(wfo_domain *d) {
   const int dim = d->dim, k = d->k;
   const double *s = d->stab;
@@ -494,7 +517,14 @@ static void calcElemPressure(wfo_domain *d) {
       J_avg += voln[nid] / voln_0[nid];
     }
     J_avg /= k;
-    double alpha = s[0];
+    int is_contact = 0; /* Mechanical.C:729-747: any element node with a non-zero contact force */
+    if (d->contact)
+      for (int a = 0; a < k && !is_contact; ++a) {
+        const double *cf = d->contforce + (size_t)dim * d->m_elnod[(size_t)e * k + a];
+        double c2 = cf[0] * cf[0] + cf[1] * cf[1] + (dim == 3 ? cf[2] * cf[2] : 0.0 * 0.0);
+        if (c2 > 0) is_contact = 1;
+      }
+    double alpha = is_contact ? s[1] : s[0];
     double J_bar = alpha * J_local + (1 - alpha) * J_avg;
     if (J_bar < s[9]) J_bar = 0.2;
     double p_physical = -K * (s[6] * log(J_bar) + (1.0 - s[6]) * (J_bar - 1.0));
@@ -505,14 +535,15 @@ static void calcElemPressure(wfo_domain *d) {
       for (int a = 0; a < k; ++a)
         div_v += DH(0, e, a) * VEL(e, a, 0) + DH(1, e, a) * VEL(e, a, 1) + DH(2, e, a) * VEL(e, a, 2);
     double p_pspg = 0.0;
-    double p_hg = s[2] * K * fabs(J_local - J_avg);
+    double p_hg = (is_contact ? s[3] : s[2]) * K * fabs(J_local - J_avg);
     double p_q = 0.0;
     if (div_v < 0.0) {
       p_pspg = fmin(s[7] * tau * div_v * K, s[8] * K);
       double q1 = s[4] * rho_e * h * c * (-div_v);
       double delta_J = 1.0 - J_local;
       double q2 = s[5] * K * delta_J;
-      p_q = q1 > q2 ? q1 : q2; /* std::max(q1,q2) */
+      if (is_contact) p_q = 0.5 * (q1 + q2);
+      else p_q = q1 > q2 ? q1 : q2; /* std::max(q1,q2) */
     }
     d->p[e] = p_physical + p_pspg + p_hg + p_q;
   }
@@ -863,19 +894,368 @@ static void assemblyForces(wfo_domain *d) {
   }
 }
 
+
+/* ---- contact with rigid surfaces ------------------------------------------------------------------- */
+typedef struct { double x, y, z; } v3;
+static v3 V3(double x, double y, double z) { v3 r = {x, y, z}; return r; }
+static v3 vadd(v3 a, v3 b) { return V3(a.x + b.x, a.y + b.y, a.z + b.z); }
+static v3 vsub(v3 a, v3 b) { return V3(a.x - b.x, a.y - b.y, a.z - b.z); }
+static v3 vmul(v3 a, double s) { return V3(a.x * s, a.y * s, a.z * s); }
+static v3 vdiv(v3 a, double s) { double inv = 1.0 / s; return vmul(a, inv); } /* double3_c.h:95-99 */
+static double vdot(v3 a, v3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+static v3 vcross(v3 a, v3 b) { return V3(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x); }
+static double vlen(v3 a) { return sqrt(vdot(a, a)); }
+static v3 ld3(const double *p, int i) { return V3(p[3 * i], p[3 * i + 1], p[3 * i + 2]); }
+static void st3(double *p, int i, v3 a) { p[3 * i] = a.x; p[3 * i + 1] = a.y; p[3 * i + 2] = a.z; }
+static v3 node3(const wfo_domain *d, const double *q, int n) { /* getPosVec3 / getVelVec / getAccVec, Domain_d.h:447-481 */
+  return V3(q[d->dim * n], q[d->dim * n + 1], d->dim == 3 ? q[d->dim * n + 2] : 0.0);
+}
+
+/* face tables, Domain_d.h:172-193; the constructor selects tetra faces (:246-249), set2DFacesValues quad edges (:785-791) */
+static const int TETRA_FACES[4][4] = {{0, 1, 2, -1}, {0, 1, 3, -1}, {1, 2, 3, -1}, {0, 2, 3, -1}};
+static const int QUAD_EDGES[4][4] = {{0, 1, -1, -1}, {1, 2, -1, -1}, {2, 3, -1, -1}, {3, 0, -1, -1}};
+
+static int cmp_face(const void *a, const void *b) {
+  const int *p = (const int *)a, *q = (const int *)b;
+  for (int i = 0; i < 4; i++) if (p[i] != q[i]) return p[i] < q[i] ? -1 : 1;
+  return p[4] < q[4] ? -1 : (p[4] > q[4]);
+}
+/* CalcExtFaceAreas (Domain_d.C:210-315): nodal areas from the faces that occur once, in faceList order */
+static void CalcExtFaceAreas(wfo_domain *d) {
+  unsigned char *elem_flags = zalloc(d->ne, 1);
+  for (int i = 0; i < d->nn; i++) d->node_area[i] = 0.0;
+  for (int i = 0; i < d->ne; i++) d->m_elem_area[i] = 0.0;
+  for (int i = 0; i < d->faceCount; i++) {
+    if (d->face_count[i] != 1) continue;
+    const int *fn = d->face_nodes + 4 * i;
+    int elem_id = d->face_elem[i];
+    if (d->dim == 2) {
+      double dx = d->x[2 * fn[1]] - d->x[2 * fn[0]], dy = d->x[2 * fn[1] + 1] - d->x[2 * fn[0] + 1];
+      double length = sqrt(dx * dx + dy * dy);
+      double share = 0.5 * length;
+      d->node_area[fn[0]] += share;
+      d->node_area[fn[1]] += share;
+      d->m_elem_area[elem_id] += length;
+    } else {
+      v3 p0 = node3(d, d->x, fn[0]), p1 = node3(d, d->x, fn[1]), p2 = node3(d, d->x, fn[2]);
+      v3 cr = vcross(vsub(p1, p0), vsub(p2, p0));
+      double area = 0.5 * sqrt(cr.x * cr.x + cr.y * cr.y + cr.z * cr.z);
+      double area_share = area / 3.0;
+      d->node_area[fn[0]] += area_share;
+      d->node_area[fn[1]] += area_share;
+      d->node_area[fn[2]] += area_share;
+      if (!elem_flags[elem_id]) { d->m_elem_area[elem_id] = area; elem_flags[elem_id] = 1; }
+      else if (area > d->m_elem_area[elem_id]) d->m_elem_area[elem_id] = area;
+    }
+  }
+  free(elem_flags);
+}
+/* SearchExtNodes (Domain_d.C:110-205).  The reference matches every new face against the whole list (O(F^2));
+ * the list it ends with holds each distinct node set once, in order of first occurrence (element, then local
+ * face), with its multiplicity and first element.  Restated with a sort: same list, same order. */
+static int SearchExtNodes(wfo_domain *d) {
+  const int (*tab)[4];
+  int elfac, facenod;
+  if (d->dim == 3 && d->k == 4) { tab = TETRA_FACES; elfac = 4; facenod = 3; }
+  else if (d->dim == 2 && d->k == 4) { tab = QUAD_EDGES; elfac = 4; facenod = 2; }
+  else return -1; /* the reference's face tables cover tets (3D) and quads (2D) only */
+  size_t nf = (size_t)d->ne * elfac;
+  int *rec = malloc(sizeof(int) * 6 * (nf ? nf : 1)); /* sorted node set [4], serial, pad */
+  int *raw = malloc(sizeof(int) * 4 * (nf ? nf : 1));
+  for (int e = 0; e < d->ne; e++)
+    for (int f = 0; f < elfac; f++) {
+      size_t i = (size_t)e * elfac + f;
+      int q[4] = {-1, -1, -1, -1};
+      for (int n = 0; n < facenod; n++) q[n] = raw[4 * i + n] = (int)d->m_elnod[(size_t)e * d->k + tab[f][n]];
+      for (int n = facenod; n < 4; n++) raw[4 * i + n] = -1;
+      for (int a = 1; a < facenod; a++) for (int b = a; b > 0 && q[b - 1] > q[b]; b--) { int t = q[b]; q[b] = q[b - 1]; q[b - 1] = t; }
+      memcpy(rec + 6 * i, q, sizeof(q));
+      rec[6 * i + 4] = (int)i;
+      rec[6 * i + 5] = 0;
+    }
+  qsort(rec, nf, 6 * sizeof(int), cmp_face);
+  int *first = malloc(sizeof(int) * (nf ? nf : 1)); /* serial -> multiplicity if first of its group, else 0 */
+  memset(first, 0, sizeof(int) * nf);
+  for (size_t i = 0; i < nf;) {
+    size_t j = i + 1;
+    while (j < nf && memcmp(rec + 6 * i, rec + 6 * j, 4 * sizeof(int)) == 0) j++;
+    first[rec[6 * i + 4]] = (int)(j - i);
+    i = j;
+  }
+  free(d->face_nodes); free(d->face_count); free(d->face_elem);
+  d->face_nodes = malloc(sizeof(int) * 4 * (nf ? nf : 1));
+  d->face_count = malloc(sizeof(int) * (nf ? nf : 1));
+  d->face_elem = malloc(sizeof(int) * (nf ? nf : 1));
+  d->faceCount = 0;
+  for (size_t i = 0; i < nf; i++)
+    if (first[i]) {
+      memcpy(d->face_nodes + 4 * d->faceCount, raw + 4 * i, 4 * sizeof(int));
+      d->face_count[d->faceCount] = first[i];
+      d->face_elem[d->faceCount] = (int)(i / elfac);
+      d->faceCount++;
+    }
+  free(rec); free(raw); free(first);
+  for (int n = 0; n < d->nn; n++) d->ext_nodes[n] = 0;
+  for (int i = 0; i < d->faceCount; i++)
+    if (d->face_count[i] == 1)
+      for (int j = 0; j < facenod; j++) d->ext_nodes[d->face_nodes[4 * i + j]] = 1;
+  CalcExtFaceAreas(d);
+  return 0;
+}
+
+/* TriMesh_d::CalcCentroids / CalcNormals / UpdatePlaneCoeff / CalcSpheres / Move (Mesh.h:228-328) */
+static void tm_CalcCentroids(wfo_domain *d) {
+  int nen = d->tm.dimension == 3 ? 3 : 2;
+  for (int e = 0; e < d->tm.elemcount; e++) {
+    v3 c = V3(0.0, 0.0, 0.0);
+    for (int ne = 0; ne < nen; ne++) c = vadd(c, ld3(d->tm.node, d->tm.elnode[nen * e + ne]));
+    st3(d->tm.centroid, e, vdiv(c, nen));
+  }
+}
+static void tm_CalcNormals(wfo_domain *d) {
+  if (d->tm.dimension == 3) {
+    for (int e = 0; e < d->tm.elemcount; e++) {
+      v3 u = vsub(ld3(d->tm.node, d->tm.elnode[3 * e + 1]), ld3(d->tm.node, d->tm.elnode[3 * e]));
+      v3 v = vsub(ld3(d->tm.node, d->tm.elnode[3 * e + 2]), ld3(d->tm.node, d->tm.elnode[3 * e]));
+      v3 w = vcross(u, v);
+      st3(d->tm.normal, e, vdiv(w, vlen(w)));
+    }
+  } else {
+    for (int e = 0; e < d->tm.elemcount; e++) {
+      v3 u = vsub(ld3(d->tm.node, d->tm.elnode[2 * e + 1]), ld3(d->tm.node, d->tm.elnode[2 * e]));
+      v3 v = V3(-u.y, u.x, 0.0);
+      st3(d->tm.normal, e, vdiv(v, vlen(v)));
+    }
+  }
+}
+static void tm_UpdatePlaneCoeff(wfo_domain *d) {
+  for (int e = 0; e < d->tm.elemcount; e++)
+    d->tm.pplane[e] = vdot(ld3(d->tm.node, d->tm.elnode[d->tm.dimension * e + d->tm.nfar[e]]), ld3(d->tm.normal, e));
+}
+static void tm_CalcSpheres(wfo_domain *d) { /* nfar ends as the last local node whatever the distances (Mesh.h:308-316) */
+  for (int e = 0; e < d->tm.elemcount; e++) d->tm.nfar[e] = d->tm.dimension - 1;
+  tm_UpdatePlaneCoeff(d);
+}
+/* Solver_explicit.C:981-1005 */
+static void move_trimesh(wfo_domain *d) {
+  const double RAMP_FRACTION = 1.0e-2; /* Solver_explicit.C:309 */
+  double f = 1.0;
+  if (d->time < RAMP_FRACTION * d->end_t) f = pow(d->time / (RAMP_FRACTION * d->end_t), 0.5);
+  for (int n = 0; n < d->tm.nodecount; n++) st3(d->tm.node_v, n, vmul(ld3(d->tm.v_orig, n), f));
+  for (int n = 0; n < d->tm.nodecount; n++) st3(d->tm.node, n, vadd(ld3(d->tm.node, n), vmul(ld3(d->tm.node_v, n), d->dt)));
+  tm_CalcCentroids(d);
+  tm_CalcNormals(d);
+  tm_UpdatePlaneCoeff(d);
+}
+
+static void tm_free(wfo_domain *d) {
+  free(d->tm.elnode); free(d->tm.ele_mesh_id); free(d->tm.nfar); free(d->tm.node); free(d->tm.node_v);
+  free(d->tm.v_orig); free(d->tm.centroid); free(d->tm.normal); free(d->tm.pplane);
+  memset(&d->tm, 0, sizeof(d->tm));
+}
+static void tm_grow(wfo_domain *d, int nn, int ne, int dimension) {
+  int nen = dimension == 3 ? 3 : 2;
+  d->tm.dimension = dimension;
+  d->tm.node = realloc(d->tm.node, sizeof(double) * 3 * nn);
+  d->tm.node_v = realloc(d->tm.node_v, sizeof(double) * 3 * nn);
+  d->tm.v_orig = realloc(d->tm.v_orig, sizeof(double) * 3 * nn);
+  d->tm.elnode = realloc(d->tm.elnode, sizeof(int) * nen * ne);
+  d->tm.ele_mesh_id = realloc(d->tm.ele_mesh_id, sizeof(int) * ne);
+  d->tm.nfar = realloc(d->tm.nfar, sizeof(int) * ne);
+  d->tm.centroid = realloc(d->tm.centroid, sizeof(double) * 3 * ne);
+  d->tm.normal = realloc(d->tm.normal, sizeof(double) * 3 * ne);
+  d->tm.pplane = realloc(d->tm.pplane, sizeof(double) * ne);
+}
+
+/* TriMesh_d::AxisPlaneMesh (Mesh.C:48-283) appended to the surface set the way main.C:672-708 (first body: every
+ * node gets the body velocity) and TriMesh_d::AddMesh (Mesh.C:438-539; further bodies: node ids offset, velocity =
+ * m_v of the new mesh) do.  As in the reference the nodes always lie in a z = const (3D) / y = const (2D) plane
+ * spanned from p1 with spacing dl = (p2-p1).x / dens whatever `axis` says; `axis` only picks the initial normal. */
+void wfo_add_plane(wfo_domain *d, int dimension, int id, int axis, int positaxisorent, const double *p1, const double *p2,
+                   int dens, const double *vel) {
+  int nn0 = d->tm.nodecount, ne0 = d->tm.elemcount;
+  int nn = dimension == 3 ? (dens + 1) * (dens + 1) : dens + 1;
+  int ne = dimension == 3 ? dens * dens * 2 : dens;
+  tm_grow(d, nn0 + nn, ne0 + ne, dimension);
+  double px = p2[0] - p1[0];
+  double x2 = p1[1], x3 = p1[2];
+  double dl = px / dens;
+  int vi = nn0, test = dimension == 2 ? 1 : dens + 1;
+  for (int j = 0; j < test; j++) {
+    double x1 = p1[0];
+    for (int i = 0; i < dens + 1; i++) {
+      st3(d->tm.node, vi, V3(x1, x2, x3));
+      st3(d->tm.node_v, vi, V3(vel[0], vel[1], vel[2]));
+      vi++;
+      x1 += dl;
+    }
+    x2 += dl;
+  }
+  int el = ne0;
+  if (dimension == 3) {
+    for (int j = 0; j < dens; j++)
+      for (int i = 0; i < dens; i++) {
+        int n[4];
+        n[0] = (dens + 1) * j + i; n[1] = n[0] + 1; n[2] = (dens + 1) * (j + 1) + i; n[3] = n[2] + 1;
+        int elcon[2][3];
+        if (positaxisorent) { elcon[0][0] = n[0]; elcon[0][1] = n[1]; elcon[0][2] = n[2]; elcon[1][0] = n[1]; elcon[1][1] = n[3]; elcon[1][2] = n[2]; }
+        else { elcon[0][0] = n[0]; elcon[0][1] = n[2]; elcon[0][2] = n[1]; elcon[1][0] = n[1]; elcon[1][1] = n[2]; elcon[1][2] = n[3]; }
+        for (int e = 0; e < 2; e++) {
+          for (int q = 0; q < 3; q++) d->tm.elnode[3 * el + q] = elcon[e][q] + nn0;
+          el++;
+        }
+      }
+  } else {
+    for (int i = 0; i < dens; i++) {
+      int n0 = i, n1 = i + 1;
+      d->tm.elnode[2 * el] = (positaxisorent ? n0 : n1) + nn0;
+      d->tm.elnode[2 * el + 1] = (positaxisorent ? n1 : n0) + nn0;
+      el++;
+    }
+  }
+  double f = positaxisorent ? 1. : -1.;
+  for (int e = ne0; e < ne0 + ne; e++) {
+    v3 nrm = V3(0.0, 0.0, 0.0);
+    if (dimension == 3) { if (axis == 0) nrm.x = f; else if (axis == 1) nrm.y = f; else nrm.z = f; }
+    else { if (axis == 0) nrm.x = f; else if (axis == 1) nrm.y = f; }
+    st3(d->tm.normal, e, nrm);
+    d->tm.ele_mesh_id[e] = id;
+  }
+  d->tm.nodecount = nn0 + nn;
+  d->tm.elemcount = ne0 + ne;
+  tm_CalcCentroids(d);
+}
+
+void wfo_set_trimesh(wfo_domain *d, int dimension, int nn, int ne, const double *node, const double *node_v,
+                     const int *elnode, const double *normal, const int *mesh_id) {
+  tm_free(d);
+  tm_grow(d, nn, ne, dimension);
+  int nen = dimension == 3 ? 3 : 2;
+  memcpy(d->tm.node, node, sizeof(double) * 3 * nn);
+  memcpy(d->tm.node_v, node_v, sizeof(double) * 3 * nn);
+  memcpy(d->tm.elnode, elnode, sizeof(int) * nen * ne);
+  memcpy(d->tm.normal, normal, sizeof(double) * 3 * ne);
+  memcpy(d->tm.ele_mesh_id, mesh_id, sizeof(int) * ne);
+  d->tm.nodecount = nn; d->tm.elemcount = ne;
+  tm_CalcCentroids(d);
+}
+
+/* main.C:716-725, :842-847 */
+void wfo_contact_on(wfo_domain *d, double mu_sta, double mu_dyn, double pf, double end_time) {
+  d->tm.mu_sta = mu_sta; d->tm.mu_dyn = mu_dyn;
+  if (pf > -1.0) d->m_contPF = pf;
+  tm_CalcSpheres(d);
+  d->contact = 1;
+  d->end_t = end_time;
+}
+void wfo_trimesh_counts(wfo_domain *d, int *out) { out[0] = d->tm.dimension; out[1] = d->tm.nodecount; out[2] = d->tm.elemcount; }
+
+/* CalcContactForces (Contact.C:31-336), serial order (the reference's 2D friction reset touches the next node) */
+static void CalcContactForces(wfo_domain *d) {
+  const int dim = d->dim, nen = d->tm.dimension == 3 ? 3 : 2;
+  const double dt = d->dt;
+  for (int i = 0; i < d->nn; i++) d->m_mesh_in_contact[i] = -1;
+  for (int i = 0; i < d->nn; i++) {
+    if (!d->ext_nodes[i]) continue;
+    int j = 0, end = d->tm.elemcount == 0;
+    while (!end) {
+      v3 nj = ld3(d->tm.normal, j);
+      v3 xi = node3(d, d->x, i), vi = node3(d, d->v, i), ai = node3(d, d->a, i);
+      double dist = vdot(nj, xi) - d->tm.pplane[j];
+      v3 x_pred = vadd(vadd(xi, vmul(vi, dt)), vdiv(vmul(vmul(ai, dt), dt), 2.0));
+      if (dist < 0) {
+        v3 Qj = vsub(xi, vmul(nj, dist)); /* d * normal -> operator*(double, double3) = a*s */
+        int inside = 1;
+        if (d->tm.dimension == 3) {
+          int l = 0, n;
+          while (l < 3 && inside) {
+            n = l + 1; if (n > 2) n = 0;
+            v3 nl = ld3(d->tm.node, d->tm.elnode[nen * j + l]);
+            double crit = vdot(vcross(vsub(ld3(d->tm.node, d->tm.elnode[nen * j + n]), nl), vsub(Qj, nl)), nj);
+            if (crit < 0.0) inside = 0;
+            l++;
+          }
+        } else {
+          int l = 0, n;
+          while (l < 2 && inside) {
+            n = l + 1; if (n > 1) n = 0;
+            v3 nl = ld3(d->tm.node, d->tm.elnode[nen * j + l]);
+            double crit = vdot(vsub(ld3(d->tm.node, d->tm.elnode[nen * j + n]), nl), vsub(Qj, nl));
+            if (crit < 0.0) inside = 0;
+            l++;
+          }
+        }
+        if (inside) {
+          double nodlen = 0.0;
+          for (int e = 0; e < d->m_nodel_count[i]; e++) nodlen += d->m_elem_length[d->m_nodel[d->m_nodel_offset[i] + e]];
+          nodlen /= d->m_nodel_count[i];
+          v3 v_rel = vi;
+          double v_reln = vdot(v_rel, nj);
+          double kcont_geo = d->E * d->node_area[i] / nodlen;
+          double kcont_mass = 0.2 * d->m_mdiag[i] / (dt * dt);
+          double kcont = kcont_geo < kcont_mass ? kcont_geo : kcont_mass; /* std::min(geo, mass) */
+          double damping_ratio = 0.2;
+          double omega = sqrt(kcont / d->m_mdiag[i]);
+          double ccrit = 2.0 * d->m_mdiag[i] * omega;
+          double F_damp = damping_ratio * ccrit * v_reln;
+          double F_normal = d->m_contPF * kcont * dist;
+          v3 cf = vmul(nj, -(F_normal + F_damp));
+          d->contforce[dim * i] = cf.x; d->contforce[dim * i + 1] = cf.y;
+          if (dim == 3) d->contforce[dim * i + 2] = cf.z;
+          d->m_mesh_in_contact[i] = d->tm.ele_mesh_id[j];
+          v3 v_tan = vsub(v_rel, vmul(nj, vdot(v_rel, nj)));
+          v3 du_tangent = vmul(v_tan, dt);
+          if (dim == 2) du_tangent.z = 0.0;
+          double utz = 0.0;
+          if (dim == 3) utz = d->ut_prev[3 * i + 2];
+          v3 ut_acc = V3(d->ut_prev[dim * i], d->ut_prev[dim * i + 1], utz);
+          ut_acc = vadd(ut_acc, du_tangent);
+          d->ut_prev[dim * i] += du_tangent.x;
+          d->ut_prev[dim * i + 1] += du_tangent.y; d->ut_prev[dim * i + 2] += du_tangent.z;
+          v3 Ft_trial = vmul(ut_acc, -kcont);
+          double Ft_mag = vlen(Ft_trial);
+          v3 Fn = vmul(nj, vdot(cf, nj));
+          double normFn = sqrt(Fn.x * Fn.x + Fn.y * Fn.y + Fn.z * Fn.z);
+          v3 Ft;
+          double Ft_max_static = d->tm.mu_sta * normFn;
+          if (Ft_mag <= Ft_max_static) Ft = Ft_trial;
+          else {
+            double Ft_max_dynamic = d->tm.mu_dyn * normFn;
+            double nvt = sqrt(v_tan.x * v_tan.x + v_tan.y * v_tan.y + v_tan.z * v_tan.z);
+            Ft = vdiv(vmul(v_tan, -Ft_max_dynamic), nvt);
+            for (int c = 0; c < 3; c++) d->ut_prev[dim * i + c] = 0;
+          }
+          d->contforce[dim * i + 0] += Ft.x;
+          d->contforce[dim * i + 1] += Ft.y;
+          if (dim == 3) d->contforce[dim * i + 2] += Ft.z;
+          end = 1;
+        }
+      }
+      j++;
+      if (j == d->tm.elemcount) end = 1;
+    }
+  }
+}
+
 static void scrub_nonfinite(wfo_domain *d) { /* Solver_explicit.C:779-784 */
   for (int i = 0; i < d->nn * d->dim; ++i)
     if (!isfinite(d->m_fi[i])) d->m_fi[i] = 0.0;
 }
 
-/* calcAccel (Mechanical.C:321-341), contact off */
+/* calcAccel (Mechanical.C:321-341) */
 static void calcAccel(wfo_domain *d) {
 #pragma omp parallel for
-  for (int n = 0; n < d->nn; n++)
+  for (int n = 0; n < d->nn; n++) {
     for (int c = 0; c < d->dim; c++) {
       int i = n * d->dim + c;
       d->a[i] = (d->m_fe[i] - d->m_fi[i]) / d->m_mdiag[n];
     }
+    if (d->contact)
+      for (int c = 0; c < d->dim; c++) {
+        int i = n * d->dim + c;
+        d->a[i] += d->contforce[i] / d->m_mdiag[n];
+      }
+  }
 }
 
 /* axis constraint (Solver_explicit.C:953-969) */
@@ -925,11 +1305,15 @@ void wfo_init(wfo_domain *d, double dt) {
   calcElemDensity(d);
   CalcNodalVol(d);
   CalcNodalMassFromVol(d);
+  for (int n = 0; n < d->nn * d->dim; n++) d->ut_prev[n] = 0.0; /* Solver_explicit.C:286-289 */
   d->time = 0.0;
+  d->step_count = 0;
+  if (d->contact) memcpy(d->tm.v_orig, d->tm.node_v, sizeof(double) * 3 * d->tm.nodecount); /* m_v_orig, :168-173 */
 }
 
 /* one step: Solver_explicit.C:524-978, rows 1-22 of SURVEY.md §3.3 */
 static void step_once(wfo_domain *d) {
+  if (d->dim > 2 && d->faceCount > 0 && d->step_count % 10 == 0) CalcExtFaceAreas(d); /* Solver_explicit.C:445-450 */
   UpdatePrediction(d);
   for (int c = 0; c < d->dim; c++) ImposeBCV(d, c);
   calcElemJAndDerivatives(d);
@@ -944,6 +1328,7 @@ static void step_once(wfo_domain *d) {
   calcArtificialViscosity(d);
   calcElemForces(d);
   calcElemHourglassForces(d);
+  if (d->contact) CalcContactForces(d); /* Solver_explicit.C:769-770 */
   assemblyForces(d);
   scrub_nonfinite(d);
   calcAccel(d);
@@ -952,7 +1337,9 @@ static void step_once(wfo_domain *d) {
   for (int c = 0; c < d->dim; c++) ImposeBCV(d, c);
   axis_constraint(d);
   UpdateCorrectionPos(d);
+  if (d->contact) move_trimesh(d);
   d->time += d->dt;
+  d->step_count++;
 }
 
 void wfo_step(wfo_domain *d, int n) { for (int i = 0; i < n; i++) step_once(d); }
@@ -990,6 +1377,10 @@ int wfo_call(wfo_domain *d, const char *f, double arg) {
   else if (IS("UpdateCorrectionAccVel")) UpdateCorrectionAccVel(d);
   else if (IS("AxisConstraint")) axis_constraint(d);
   else if (IS("UpdateCorrectionPos")) UpdateCorrectionPos(d);
+  else if (IS("SearchExtNodes")) return SearchExtNodes(d);
+  else if (IS("CalcExtFaceAreas")) CalcExtFaceAreas(d);
+  else if (IS("CalcContactForces")) CalcContactForces(d);
+  else if (IS("MoveTriMesh")) move_trimesh(d);
   else return -1;
 #undef IS
   return 0;
@@ -1013,6 +1404,16 @@ static view_t view(wfo_domain *d, const char *nm) {
   V("m_f_elem", d->m_f_elem, nk * d->dim) V("m_f_elem_hg", d->m_f_elem_hg, nk * d->dim)
   V("m_hg_q", d->dim == 2 ? d->m_hg_q : NULL, d->dim == 2 ? nk * d->dim : 0)
   V("m_elem_length", d->m_elem_length, d->m_elem_length ? ne : 0)
+  V("contforce", d->contforce, nd) V("ut_prev", d->ut_prev, nd) V("node_area", d->node_area, nn)
+  V("m_elem_area", d->m_elem_area, ne) V("ext_nodes", d->ext_nodes, (size_t)d->nn)
+  V("m_mesh_in_contact", d->m_mesh_in_contact, sizeof(int) * (size_t)d->nn)
+  if (d->tm.nodecount) {
+    size_t tn = 24 * (size_t)d->tm.nodecount, te = (size_t)d->tm.elemcount;
+    V("trimesh.node", d->tm.node, tn) V("trimesh.node_v", d->tm.node_v, tn)
+    V("trimesh.normal", d->tm.normal, 24 * te) V("trimesh.pplane", d->tm.pplane, 8 * te)
+    V("trimesh.elnode", d->tm.elnode, sizeof(int) * te * (d->tm.dimension == 3 ? 3 : 2))
+    V("trimesh.ele_mesh_id", d->tm.ele_mesh_id, sizeof(int) * te)
+  }
   V("bcx_val", d->bc_val[0], sizeof(double) * (size_t)d->bc_count[0]) /* Domain_d.h:901 */
   V("bcy_val", d->bc_val[1], sizeof(double) * (size_t)d->bc_count[1])
   V("bcz_val", d->bc_val[2], sizeof(double) * (size_t)d->bc_count[2])

@@ -32,6 +32,13 @@ void wfo_set_stab(wfo_domain *, const double *s12);
 void wfo_set_options(wfo_domain *, int press_variant, double av_alpha, double av_beta, double hexa_hg_coeff);
 void wfo_add_bc(wfo_domain *, int node, int dim, double val);
 void wfo_allocate_bcs(wfo_domain *);
+/* contact with rigid surfaces: TriMesh_d::AxisPlaneMesh / AddMesh, raw arrays, main.C:716-725 + :842-847 */
+void wfo_add_plane(wfo_domain *, int dimension, int id, int axis, int positaxisorent, const double *p1,
+                   const double *p2, int dens, const double *vel);
+void wfo_set_trimesh(wfo_domain *, int dimension, int nn, int ne, const double *node, const double *node_v,
+                     const int *elnode, const double *normal, const int *mesh_id);
+void wfo_contact_on(wfo_domain *, double mu_sta, double mu_dyn, double penalty_factor, double end_time);
+void wfo_trimesh_counts(wfo_domain *, int *out3);
 void wfo_init(wfo_domain *, double dt);
 void wfo_step(wfo_domain *, int n);
 double wfo_time_steps(wfo_domain *, int n);

@@ -20,7 +20,12 @@ GOLDEN = {
     "psquad_n6": (R(cases.plane_strain_quads(6), top_vel=-50.0), 80),
     "pstri_n6": (R(cases.plane_strain_tris(6), top_vel=-50.0), 80),
     "hex_n3_stab_av": (R(cases.c3_hexes(3), top_vel=-200.0, stab=STAB, av=(1.0, 0.2)), 60),
+    # penalty contact with rigid surfaces: two planes + friction + contact-dependent stabilisation
+    "contact_tet_n3": (cases.contact_tets(3, stab=dict(STAB, alpha_contact=0.6, hg_coeff_contact=0.1)), 80),
+    "contact_quad_n6": (cases.contact_quads(6), 80),
 }
+CONTACT_ARRAYS = ("contforce ut_prev node_area m_elem_area m_mesh_in_contact ext_nodes trimesh.node trimesh.node_v "
+                  "trimesh.normal trimesh.pplane").split()
 
 FLOAT_ARRAYS = "x v a u prev_a m_fi m_mdiag vol p pl_strain sigma_y m_sigma m_tau m_eps".split()
 INT_ARRAYS = "m_elnod m_nodel m_nodel_loc m_nodel_offset m_nodel_count".split()

@@ -14,23 +14,29 @@ ROOT = os.path.dirname(os.path.dirname(HERE))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, HERE)
 
-from cases_golden import FLOAT_ARRAYS, GOLDEN, INT_ARRAYS  # noqa: E402
+from cases_golden import CONTACT_ARRAYS, FLOAT_ARRAYS, GOLDEN, INT_ARRAYS  # noqa: E402
 from oracle import refdrv  # noqa: E402
 
 
 def main():
     refdrv.build("ref")
     refdrv.RefDomain.set_threads(1)
+    only_missing = "--missing" in sys.argv
     for name, (case, steps) in GOLDEN.items():
+        if only_missing and os.path.exists(os.path.join(HERE, name + ".npz")):
+            continue
         d = refdrv.RefDomain()
         case.apply(d)
         out = {nm: d.get(nm) for nm in INT_ARRAYS}
         out["x0"] = d.get("x")
+        extra = CONTACT_ARRAYS if case.contact is not None else []
+        for nm in extra:
+            out[f"s0_{nm}"] = d.get(nm)
         d.step(1)
         for nm in FLOAT_ARRAYS:
             out[f"s1_{nm}"] = d.get(nm)
         d.step(steps - 1)
-        for nm in FLOAT_ARRAYS:
+        for nm in FLOAT_ARRAYS + list(extra):
             out[f"sN_{nm}"] = d.get(nm)
         if case.dim == 2 and not case.tritet:
             out["sN_m_hg_q"] = d.get("m_hg_q")[: 2 * case.n_elems]

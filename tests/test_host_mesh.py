@@ -163,3 +163,101 @@ def test_partition_bit_exact(P, box):
     for (p, q), ids in halos.items():
         assert np.array_equal(ids, halos[(q, p)])
         assert np.all(np.diff(ids) > 0)
+
+
+# ---- contact: integer artefacts of SearchExtNodes and the rigid-plane mesher -----------------
+def host_ext_faces(dim, k, nn, el):
+    from weldformfem_b200 import _lib
+    lib = _lib.load()
+    ne = el.size // k
+    facenod = 3 if dim == 3 else 2
+    ext = np.zeros(nn, np.uint8)
+    fn, fe = np.full(ne * 4 * facenod, -1, np.int32), np.full(ne * 4, -1, np.int32)
+    tot, nx = C.c_int(), C.c_int()
+    ip = C.POINTER(C.c_int)
+    rc = lib.wf_host_ext_faces(dim, k, nn, ne, el.ctypes.data_as(C.POINTER(C.c_uint)), ext.ctypes.data_as(C.POINTER(C.c_ubyte)),
+                               C.byref(tot), C.byref(nx), fn.ctypes.data_as(ip), fe.ctypes.data_as(ip))
+    return rc, ext, tot.value, fn[: nx.value * facenod].reshape(-1, facenod), fe[: nx.value]
+
+
+def brute_force_faces(dim, k, el):
+    """SearchExtNodes as the reference does it (Domain_d.C:74-156): linear search of every new face in the list."""
+    tab = [(0, 1, 2), (0, 1, 3), (1, 2, 3), (0, 2, 3)] if dim == 3 else [(0, 1), (1, 2), (2, 3), (3, 0)]
+    faces, count, elem = [], [], []
+    for e, nodes in enumerate(el.reshape(-1, k)):
+        for f in tab:
+            fn = [int(nodes[q]) for q in f]
+            key = sorted(fn)
+            for i, g in enumerate(faces):
+                if sorted(g) == key:
+                    count[i] += 1
+                    break
+            else:
+                faces.append(fn); count.append(1); elem.append(e)
+    ext = [(f, e) for f, c, e in zip(faces, count, elem) if c == 1]
+    return len(faces), np.array([f for f, _ in ext], np.int32), np.array([e for _, e in ext], np.int32)
+
+
+@pytest.mark.parametrize("V,L,r,tritet", [((0, 0, 0), (0.31, 0.2, 0.11), 0.05, True), ((0, 0, 0), (0.2, 0.2, 0.2), 0.05, True),
+                                          ((0, 0, 0), (0.4, 0.3, 0.0), 0.05, False), ((0, 0, 0), (0.1, 0.1, 0.0), 0.05, False)])
+def test_ext_faces_match_reference_search_and_oracle(V, L, r, tritet, oracle_port):
+    dim, k, x, el = host_box(V, L, r, tritet)
+    nn = x.size // dim
+    rc, ext, tot, fn, fe = host_ext_faces(dim, k, nn, el)
+    assert rc == 0
+    btot, bfn, bfe = brute_force_faces(dim, k, el)
+    assert tot == btot
+    assert np.array_equal(fn, bfn) and np.array_equal(fe, bfe)       # same faces, same (faceList) order
+    o = oracle_port()
+    o.box(V, L, r, tritet)
+    o.call("SearchExtNodes")
+    assert np.array_equal(ext, o.get("ext_nodes"))
+    # a box: every boundary node is external, no interior node is
+    X = x.reshape(-1, dim)
+    onb = np.zeros(nn, bool)
+    for c in range(dim):
+        onb |= np.isclose(X[:, c], X[:, c].min()) | np.isclose(X[:, c], X[:, c].max())
+    assert np.array_equal(ext.astype(bool), onb)
+
+
+def test_ext_faces_refuses_elements_the_reference_tables_do_not_cover():
+    dim, k, x, el = host_box((0, 0, 0), (0.2, 0.2, 0.2), 0.05, False)   # hexahedra
+    rc, *_ = host_ext_faces(dim, k, x.size // dim, el)
+    assert rc != 0
+
+
+@pytest.mark.parametrize("dimension,axis,orient,dens", [(3, 2, False, 4), (3, 2, True, 1), (3, 0, True, 3), (2, 1, False, 5), (2, 0, True, 2)])
+def test_axis_plane_mesh_matches_oracle(dimension, axis, orient, dens, oracle_port):
+    from weldformfem_b200.domain import axis_plane_mesh
+    p1, p2 = (-0.013, 0.02, 0.031), (0.027, 0.06, 0.031)
+    node, elnode, normal, mid = axis_plane_mesh(dimension, 7, axis, orient, p1, p2, dens)
+    o = oracle_port()
+    if dimension == 3:
+        o.box((0, 0, 0), (0.2, 0.2, 0.2), 0.05, True)
+    else:
+        o.set_domtype(0, False)
+        o.box((0, 0, 0), (0.2, 0.2, 0.0), 0.05, False)
+    o.add_plane(dimension, 7, axis, orient, p1, p2, dens, (0.0, 0.0, -1.0))
+    assert np.array_equal(node.reshape(-1), o.get("trimesh.node"))
+    assert np.array_equal(elnode.reshape(-1), o.get("trimesh.elnode"))
+    assert np.array_equal(normal.reshape(-1), o.get("trimesh.normal"))
+    assert np.array_equal(mid, o.get("trimesh.ele_mesh_id"))
+
+
+def test_axis_plane_mesh_matches_compiled_reference(oracle_ref):
+    """TriMesh_d::AxisPlaneMesh + AddMesh of the unmodified reference against the host mirror's add_plane merge."""
+    from weldformfem_b200.domain import axis_plane_mesh
+    r = oracle_ref()
+    r.box((0, 0, 0), (0.2, 0.2, 0.2), 0.05, True)
+    specs = [(0, 2, False, (-0.1, -0.1, 0.21), (0.3, 0.3, 0.21), 4, (0.5, 0.0, -2.0)),
+             (1, 2, True, (-0.1, -0.1, -0.01), (0.3, 0.3, -0.01), 2, (0.0, 0.0, 0.0))]
+    nodes, els, vels, ids, off = [], [], [], [], 0
+    for mid, axis, orient, p1, p2, dens, vel in specs:
+        r.add_plane(3, mid, axis, orient, p1, p2, dens, vel)
+        n, e, _, m = axis_plane_mesh(3, mid, axis, orient, p1, p2, dens)
+        nodes.append(n); els.append(e + off); ids.append(m); vels.append(np.tile(vel, (n.shape[0], 1)))
+        off += n.shape[0]
+    assert np.array_equal(np.concatenate(nodes).reshape(-1), r.get("trimesh.node"))
+    assert np.array_equal(np.concatenate(els).reshape(-1), r.get("trimesh.elnode"))
+    assert np.array_equal(np.concatenate(ids), r.get("trimesh.ele_mesh_id"))
+    assert np.array_equal(np.concatenate(vels).reshape(-1), r.get("trimesh.node_v"))

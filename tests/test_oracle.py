@@ -10,7 +10,7 @@ import pytest
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.join(HERE, "golden"))
-from cases_golden import FLOAT_ARRAYS, GOLDEN, INT_ARRAYS  # noqa: E402
+from cases_golden import CONTACT_ARRAYS, FLOAT_ARRAYS, GOLDEN, INT_ARRAYS  # noqa: E402
 
 from weldformfem_b200 import cases  # noqa: E402
 
@@ -25,12 +25,17 @@ def test_oracle_matches_reference_fixtures_bit_for_bit(name, oracle_port):
     for nm in INT_ARRAYS:
         assert np.array_equal(d.get(nm), g[nm]), nm
     assert np.array_equal(d.get("x"), g["x0"])
+    extra = CONTACT_ARRAYS if case.contact is not None else []
+    for nm in extra:
+        assert np.array_equal(d.get(nm), g["s0_" + nm]), ("setup", nm)
     d.step(1)
     for nm in FLOAT_ARRAYS:
         assert np.array_equal(d.get(nm), g["s1_" + nm]), ("step 1", nm)
     d.step(steps - 1)
-    for nm in FLOAT_ARRAYS:
+    for nm in FLOAT_ARRAYS + list(extra):
         assert np.array_equal(d.get(nm), g["sN_" + nm]), (f"step {steps}", nm)
+    if extra:
+        assert (g["sN_m_mesh_in_contact"] >= 0).sum() > 0, "fixture should end with nodes in contact"
     if "sN_m_hg_q" in g:
         assert np.array_equal(d.get("m_hg_q")[: 2 * case.n_elems], g["sN_m_hg_q"])
     d.call("calcNodalPressureFromElemental")
@@ -43,7 +48,11 @@ def test_oracle_matches_reference_fixtures_bit_for_bit(name, oracle_port):
 
 
 LIVE = [dataclasses.replace(cases.c3_hexes(9), top_vel=-150.0), dataclasses.replace(cases.c2_tets(7), top_vel=-150.0),
-        dataclasses.replace(cases.c4_axisymm_quads(20), top_vel=-40.0)]
+        dataclasses.replace(cases.c4_axisymm_quads(20), top_vel=-40.0),
+        cases.contact_tets(6, stab=dict(alpha_free=0.3, alpha_contact=0.6, hg_coeff_free=0.2, hg_coeff_contact=0.1,
+                                        av_coeff_div=0.15, av_coeff_bulk=0.15, log_factor=0.8, pspg_scale=0.2,
+                                        p_pspg_bulkfac=0.05, J_min=0.1)),
+        cases.contact_quads(12), cases.contact_quads(10, domtype=cases.AXISYMM)]
 
 
 @pytest.mark.parametrize("case", LIVE, ids=lambda c: c.name)
@@ -54,7 +63,8 @@ def test_oracle_matches_compiled_reference_live(case, oracle_port, oracle_ref):
     case.apply(b)
     a.step(40)
     b.step(40)
-    for nm in FLOAT_ARRAYS + ["m_f_elem", "m_str_rate", "m_rot_rate", "m_detJ", "u_dt"]:
+    extra = CONTACT_ARRAYS if case.contact is not None else []
+    for nm in FLOAT_ARRAYS + ["m_f_elem", "m_str_rate", "m_rot_rate", "m_detJ", "u_dt"] + list(extra):
         assert np.array_equal(a.get(nm), b.get(nm)), nm
 
 

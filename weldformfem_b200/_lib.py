@@ -27,7 +27,7 @@ _lib = None
 UNFUSED = ("UpdatePrediction calcElemJAndDerivatives Calc_Element_Radius CalcElemVol CalcNodalVol "
            "CalcNodalMassFromVol calcElemStrainRates calcElemPressure calcArtificialViscosity calcElemForces "
            "calcElemHourglassForces assemblyForces calcAccel UpdateCorrectionAccVel AxisConstraint "
-           "UpdateCorrectionPos").split()
+           "UpdateCorrectionPos SearchExtNodes CalcExtFaceAreas CalcContactForces MoveTriMesh").split()
 
 # every symbol include/wf_engine.h declares (checked by tests/test_abi.py)
 DECLARED = (["wf_create", "wf_destroy", "wf_last_error", "wf_set_stream", "wf_get_stream", "wf_synchronize", "wf_set_mesh", "wf_gen_box",
@@ -40,7 +40,9 @@ DECLARED = (["wf_create", "wf_destroy", "wf_last_error", "wf_set_stream", "wf_ge
              "wf_partition_halo_nodes", "wf_set_mesh_partition", "wf_step_phase", "wf_init_phase", "wf_halo_info",
              "wf_halo_comm_block", "wf_halo_slot_offsets", "wf_halo_ipc_export", "wf_halo_ipc_open", "wf_halo_connect",
              "wf_halo_status", "wf_connect_all", "wf_init_all", "wf_step_all", "wf_halo_set_transport", "wf_halo_exchange_ptrs",
-             "wf_host_box_counts", "wf_host_gen_box", "wf_host_nodel", "wf_version"]
+             "wf_host_box_counts", "wf_host_gen_box", "wf_host_nodel", "wf_version",
+             "wf_set_trimesh", "wf_set_contact", "wf_get_trimesh_counts", "wf_host_ext_faces",
+             "wf_host_axis_plane_counts", "wf_host_axis_plane_mesh"]
             + ["wf_" + n for n in UNFUSED])
 
 
@@ -122,6 +124,12 @@ def load():
         "wf_host_gen_box": (C.c_int, [dp, dp, C.c_double, C.c_int, dp, up]),
         "wf_host_nodel": (C.c_int, [C.c_int, C.c_int, C.c_int, up, ip, ip, ip, ip]),
         "wf_version": (C.c_char_p, []),
+        "wf_set_trimesh": (C.c_int, [vp, C.c_int, C.c_int, C.c_int, dp, dp, ip, dp, ip]),
+        "wf_set_contact": (C.c_int, [vp, C.c_double, C.c_double, C.c_double, C.c_double]),
+        "wf_get_trimesh_counts": (C.c_int, [vp, ip, ip, ip]),
+        "wf_host_ext_faces": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, up, C.POINTER(C.c_ubyte), ip, ip, ip, ip]),
+        "wf_host_axis_plane_counts": (C.c_int, [C.c_int, C.c_int, ip, ip]),
+        "wf_host_axis_plane_mesh": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, dp, dp, C.c_int, dp, ip, dp, ip]),
     }
     for n in UNFUSED:
         sig["wf_" + n] = (C.c_int, [vp])

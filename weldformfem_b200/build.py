@@ -50,6 +50,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         (["-fmad=false", "-DWF_NS=wf_strict"], "wf_kernels.cu", "wf_kernels_strict.o"),
         (["-fmad=true", "-DWF_NS=wf_fast"], "wf_kernels.cu", "wf_kernels_fast.o"),
         ([], "wf_engine.cu", "wf_engine.o"),
+        (["-fmad=false"], "wf_contact.cu", "wf_contact.o"),
         ([], "wf_mesh.cpp", "wf_mesh.o"),
     ]
     procs = []

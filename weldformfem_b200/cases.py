@@ -47,7 +47,12 @@ class Case:
     stab: dict = field(default_factory=dict)
     av: tuple = (0.0, 0.0)
     top_vel: float = -10.0
-    bc_style: str = "clamp"   # "clamp": bottom all dims 0, top (0,..,top_vel); "c1": main_1_elem_3d.C
+    bc_style: str = "clamp"   # "clamp": bottom all dims 0, top (0,..,top_vel); "c1": main_1_elem_3d.C;
+                              # "bottom": bottom clamped only (the top is pushed by a rigid surface)
+    # contact with rigid surfaces (examples/input/Contact_Compression_*.json): planes = dicts with the arguments of
+    # TriMesh_d::AxisPlaneMesh + "vel"; contact = dict(mu_sta, mu_dyn, penalty_factor, end_steps)
+    planes: tuple = ()
+    contact: dict | None = None
 
     # ---- derived -------------------------------------------------------------------------
     @property
@@ -92,6 +97,8 @@ class Case:
         out = []
         for nd in bottom:
             out += [(int(nd), dd, 0.0) for dd in range(d)]
+        if self.bc_style == "bottom":
+            return out
         for nd in top:
             out += [(int(nd), dd, (self.top_vel if dd == d - 1 else 0.0)) for dd in range(d)]
         return out
@@ -120,6 +127,13 @@ class Case:
             for nd, dd, val in self.bc_nodes():
                 dom.add_bc(nd, dd, val)
         dom.allocate_bcs()
+        if self.contact is not None:   # order of src/explicit/main.C:650-862
+            dom.call("SearchExtNodes")
+            for pl in self.planes:
+                dom.add_plane(self.dim, pl["id"], pl["axis"], pl["positaxisorent"], pl["p1"], pl["p2"], pl["dens"], pl["vel"])
+            c = self.contact
+            dom.contact_on(c["mu_sta"], c["mu_dyn"], c["penalty_factor"], c["end_steps"] * self.timestep)
+            dom.call("calcMinEdgeLength")
         if init:
             dom.init(self.timestep)
         return dom
@@ -152,6 +166,30 @@ def c5_block(n: int = 431, tritet: bool = False) -> Case:
     if tritet:
         return Case(f"c5_tet_n{n}", 3, (n, n, n), 1.0e-3, tritet=True, cfl=0.1)
     return Case(f"c5_hex_n{n}", 3, (n, n, n), 1.0e-3, cfl=0.3, hexa_hg=0.06)
+
+
+def contact_tets(n: int = 6, tool_vel: float = -200.0, mu=(0.3, 0.2), two_planes: bool = True, stab: dict | None = None) -> Case:
+    """Tet block upset between rigid planes (examples/input/Contact_Compression_tetra.json scaled down): bottom clamped,
+    a rigid plane with normal -z comes down on the top face (plus, optionally, a resting plane under the bottom)."""
+    h, L = 1.0e-3, n * 1.0e-3
+    planes = [dict(id=0, axis=2, positaxisorent=False, p1=(-0.5 * L, -0.5 * L, L + 0.01 * h), p2=(1.5 * L, 1.5 * L, L + 0.01 * h),
+                   dens=4, vel=(0.5, 0.0, tool_vel))]
+    if two_planes:
+        planes.append(dict(id=1, axis=2, positaxisorent=True, p1=(-0.5 * L, -0.5 * L, -1.0e-4), p2=(1.5 * L, 1.5 * L, -1.0e-4),
+                           dens=2, vel=(0.0, 0.0, 0.0)))
+    return Case(f"contact_tet_n{n}", 3, (n, n, n), h, tritet=True, cfl=0.1, top_vel=0.0, bc_style="bottom",
+                stab=stab or {}, planes=tuple(planes),
+                contact=dict(mu_sta=mu[0], mu_dyn=mu[1], penalty_factor=0.6, end_steps=100))
+
+
+def contact_quads(n: int = 12, tool_vel: float = -100.0, mu=(0.3, 0.2), domtype: int = PLANE_STRAIN) -> Case:
+    """2D counterpart (examples/input/Contact_Compression_axisymm_quad.json): rigid line with normal -y above the top edge."""
+    h, L = 0.5e-3, n * 0.5e-3
+    planes = (dict(id=0, axis=1, positaxisorent=False, p1=(-0.5 * L, L + 0.01 * h, 0.0), p2=(1.5 * L, L + 0.01 * h, 0.0),
+                   dens=4, vel=(0.5, tool_vel, 0.0)),)
+    return Case(f"contact_quad_n{n}", 2, (n, n), h, domtype=domtype, cfl=0.3, stab=dict(hg_visc=0.1, hg_stiff=0.1),
+                top_vel=0.0, bc_style="bottom", planes=planes,
+                contact=dict(mu_sta=mu[0], mu_dyn=mu[1], penalty_factor=0.6, end_steps=100))
 
 
 def plane_strain_quads(n: int = 16) -> Case:

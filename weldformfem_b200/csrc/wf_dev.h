@@ -86,6 +86,11 @@ struct WfDev {
   double *a, *fi;                    /* [dim][np] */
   double *mdiag, *voln, *p_node;     /* [np] */
 
+  /* contact (NULL when contact is off): contact force per node (persists between steps like the reference's
+   * contforce, Contact.C:211-213) and the "has a non-zero contact force" flag read by calcElemPressure */
+  double *contforce;                 /* [dim][np] */
+  unsigned char *cflag;              /* [np] */
+
   /* flags / reductions */
   int *nonfinite;                    /* [1] */
   unsigned long long *xmin_key;      /* [2] ordered-key of min x_r (axisymmetric axis constraint) */
@@ -97,6 +102,7 @@ struct WfPar {
   int model;
   double Kbulk, G, sy0, Kh, mh, eps0, eps1, cs0;
   /* StabilizationParams + hexa hourglass coefficient */
+  double alpha_contact, hg_coeff_contact; /* used instead of the _free values by elements touching a contact node */
   double alpha_free, hg_coeff_free, av_coeff_div, av_coeff_bulk, log_factor, pspg_scale, p_pspg_bulkfac, J_min;
   double hg_visc, hg_stiff, hexa_hg;
   int stab_simple; /* all pressure-stabilisation terms are zero -> p = -K (J_avg - 1) */
@@ -109,4 +115,30 @@ struct WfPar {
   int xmin_cur; /* which xmin_key slot holds min x_r of the current coordinates */
   int halo_parity; /* multi-GPU: which half of the receive regions the current exchange uses */
   int variant[4]; /* tuning: kernel variant for E1, N1, E2, N2 (0 = default) */
+};
+
+/* Contact with rigid surfaces (Contact.C, Mesh.h): everything the contact kernels need besides WfDev. */
+struct WfContact {
+  /* external nodes (SearchExtNodes, Domain_d.C:110-205), ascending node id */
+  int n_ext;
+  const int *ext_nodes;              /* [n_ext] */
+  double *nodlen;                    /* [n_ext] mean m_elem_length of the elements around the node (Contact.C:146-153) */
+  double *node_area;                 /* [np] CalcExtFaceAreas */
+  double *ut_prev;                   /* [dim][np + 32] accumulated tangential slip */
+  int *mesh_in_contact;              /* [np] m_mesh_in_contact */
+  double *rec;                       /* [8][n_ext] 2D only: per-node records handed to the serial friction pass */
+  /* external faces in faceList order (= ascending element, then local face) */
+  int n_xf, facenod;
+  const int *xf_nodes;               /* [facenod][n_xf] */
+  const int *xf_elem;                /* [n_xf] */
+  double *xf_area;                   /* [n_xf] face area (3D) / edge length (2D) */
+  const int *xn_ptr;                 /* [n_ext+1] faces of external node t: xn_faces[xn_ptr[t] .. xn_ptr[t+1]) ascending */
+  const int *xn_faces;
+  double *elem_area;                 /* [ep] m_elem_area */
+  /* rigid surfaces: TriMesh_d, arrays of double3 as xyzxyz */
+  int tm_dim, tm_nn, tm_ne;
+  double *tm_node, *tm_node_v, *tm_normal, *tm_pplane;
+  const double *tm_v_orig;
+  const int *tm_elnode, *tm_mesh_id;
+  double mu_sta, mu_dyn, contPF, young;
 };

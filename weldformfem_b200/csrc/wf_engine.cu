@@ -20,101 +20,9 @@
 
 static std::string g_create_error;
 
-struct wf_engine {
-  int device = 0;
-  cudaStream_t stream = 0;
-  std::string err;
-  int dim = 3, k = 8, et = ET_HEX8, domtype = WF_3D;
-  int nn = 0, ne = 0;
-  WfDev d;
-  WfPar P;
-  const WfLaunch *L = nullptr;
-  bool strict = false;
-  int tracking = 0;
-  bool meshed = false, material_set = false, bcs_ready = false, inited = false, dbg = false;
-  bool predicted = false;  // v / u_dt currently hold next-step predictor values (only inside wf_step)
-  // which unfused-path products are current (cleared by wf_step)
-  bool a_in_dbg = false, fi_in_dbg = false, sigma_in_dbg = false, rates_in_dbg = false, felem_in_dbg = false;
-  double time = 0.0;
-  long step_count = 0;
-  wf_material mat;
-  wf_stab stab;
-  std::vector<void *> allocs;
-  // host copies of integer artefacts (reference layouts)
-  std::vector<unsigned> h_elnod;
-  std::vector<int> h_nodel, h_nodel_loc, h_offset, h_count;
-  std::vector<unsigned> h_pos; // [k][ep], see WfDev::pos
-  long long sell_total = 0;
-  std::vector<int> bc_nod[3];
-  std::vector<double> bc_val[3];
-  int nbc_rows = 0;
-  std::vector<int> bc_slot[3];             // index into bc_vals of BC i of each dimension (-1: node of another rank)
-  double *bc_stage[2] = {nullptr, nullptr}; // pinned staging of bc_vals for wf_set_bc_values
-  cudaEvent_t bc_ev[2] = {nullptr, nullptr};
-  int bc_stage_cur = 0;
-  double *bc_vals_d = nullptr;
-  std::vector<double> bc_master;           // host copy of bc_vals
-  int bc_version[3] = {0, 0, 0}, bc_stage_version[2][3] = {{0, 0, 0}, {0, 0, 0}};
-  // asynchronous step monitor (wf_monitor_async / wf_monitor_wait): 2-deep ring of pinned results
-  struct MonSlot { double ekin; double pad; int nonfinite; int halo_error; };
-  MonSlot *mon_host = nullptr;
-  double *mon_red = nullptr;               // [2][2] device partial sums
-  cudaEvent_t mon_ev[2] = {nullptr, nullptr};
-  int mon_head = 0, mon_pending = 0;
-  // partition / halo (multi-GPU); see wf_set_mesh_partition
-  bool distributed = false, own_stream = false;
-  int rank = 0, nranks = 1;
-  int transport = 0;                       // 0 = stores into the neighbour's memory, 1 = host-driven (NCCL) via the staging block
-  std::vector<int> l2g, neigh, halo_offset, halo_nodes_h;
-  std::vector<WfHaloNb> nb_h;
-  WfHaloNb *nb_d = nullptr;
-  unsigned *counters_d = nullptr;
-  char *comm = nullptr, *staging = nullptr; // [flags | receive regions]
-  size_t comm_bytes = 0, flag_bytes = 0;
-  int max_halo_count = 0, n_connected = 0;
-  unsigned long long seq = 0, timeout_ns = 30000000000ull;
-  std::vector<void *> ipc_opened;
-  int init_stage = 0, step_stage = 0;
-  // scratch for device-side layout conversion (wf_get_array / wf_set_array), diagnostics
-  double *scratch = nullptr;
-  size_t scratch_count = 0;
-  double *elem_length = nullptr;           // m_elem_length (calcMinEdgeLength)
-  unsigned long long *diag_keys = nullptr; // [3] ordered keys: min length, min height, max |v|
-  bool elem_length_valid = false;
-};
+#include "wf_engine_priv.h"
 
-#define CK(call)                                                                          \
-  do {                                                                                    \
-    cudaError_t _e = (call);                                                              \
-    if (_e != cudaSuccess) {                                                              \
-      E->err = std::string(#call) + ": " + cudaGetErrorString(_e);                        \
-      return 1;                                                                           \
-    }                                                                                     \
-  } while (0)
-#define FAIL(msg) do { E->err = (msg); return 1; } while (0)
-#define NEED(cond, msg) do { if (!(cond)) FAIL(msg); } while (0)
-
-static int check_launch(wf_engine *E, const char *what);
-static inline long long round_up(long long a, long long b) { return (a + b - 1) / b * b; }
-
-template <class T>
-static int dalloc(wf_engine *E, T **p, size_t count) {
-  void *q = nullptr;
-  size_t bytes = std::max<size_t>(count, 1) * sizeof(T);
-  CK(cudaMalloc(&q, bytes));
-  CK(cudaMemsetAsync(q, 0, bytes, E->stream));
-  E->allocs.push_back(q);
-  *p = (T *)q;
-  return 0;
-}
-
-static int need_scratch(wf_engine *E, size_t count) {
-  if (count <= E->scratch_count) return 0;
-  if (E->scratch) { CK(cudaStreamSynchronize(E->stream)); cudaFree(E->scratch); E->scratch = nullptr; E->scratch_count = 0; }
-  CK(cudaMalloc((void **)&E->scratch, count * sizeof(double)));
-  E->scratch_count = count;
-  return 0;
-}
+static int check_launch(wf_engine *E, const char *what) { return wf_check_launch(E, what); }
 
 static int select_flavour(wf_engine *E) {
   E->L = E->strict ? wf_strict_table() : wf_fast_table();
@@ -153,6 +61,7 @@ extern "C" int wf_create(wf_engine **out, int dim, int nodxelem, int domtype, in
   memset(&E->P, 0, sizeof(E->P));
   memset(&E->mat, 0, sizeof(E->mat));
   memset(&E->stab, 0, sizeof(E->stab));
+  memset(&E->C, 0, sizeof(E->C));
   E->stab.hg_stiff = 0.1; // Domain_d.h:294
   E->d.dim = dim; E->d.k = nodxelem; E->d.domtype = domtype;
   E->P.w = (et == ET_HEX8) ? 8.0 : (et == ET_TET4 ? 1.0 / 6.0 : (et == ET_QUAD4 ? 4.0 : 0.5));
@@ -381,7 +290,7 @@ extern "C" int wf_set_material(wf_engine *E, const wf_material *m) {
 
 static void refresh_stab_simple(wf_engine *E) {
   const wf_stab &s = E->stab;
-  E->P.stab_simple = (s.alpha_free == 0.0 && s.hg_coeff_free == 0.0 && s.av_coeff_div == 0.0 && s.av_coeff_bulk == 0.0 &&
+  E->P.stab_simple = (s.alpha_free == 0.0 && s.alpha_contact == 0.0 && s.hg_coeff_contact == 0.0 && s.hg_coeff_free == 0.0 && s.av_coeff_div == 0.0 && s.av_coeff_bulk == 0.0 &&
                       s.log_factor == 0.0 && s.pspg_scale == 0.0 && s.p_pspg_bulkfac == 0.0) ? 1 : 0;
 }
 
@@ -393,6 +302,7 @@ extern "C" int wf_set_stab(wf_engine *E, const wf_stab *s) {
   P.av_coeff_bulk = s->av_coeff_bulk; P.log_factor = s->log_factor; P.pspg_scale = s->pspg_scale;
   P.p_pspg_bulkfac = s->p_pspg_bulkfac; P.J_min = s->J_min; P.hg_visc = s->hg_visc; P.hg_stiff = s->hg_stiff;
   P.hexa_hg = s->hexa_hg_coeff;
+  P.alpha_contact = s->alpha_contact; P.hg_coeff_contact = s->hg_coeff_contact;
   refresh_stab_simple(E);
   return 0;
 }
@@ -565,7 +475,7 @@ static int ensure_dbg(wf_engine *E) {
   return 0;
 }
 
-static int check_launch(wf_engine *E, const char *what) {
+int wf_check_launch(wf_engine *E, const char *what) {
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { E->err = std::string(what) + ": " + cudaGetErrorString(e); return 1; }
   return 0;
@@ -632,6 +542,7 @@ static int init_stage(wf_engine *E, int stage, double dt) {
       if (reset_xmin(E, 0)) return 1;
       E->L->xmin(d, 0, E->stream);
     }
+    if (wf_contact_init(E)) return 1;
     E->time = 0.0; E->step_count = 0; E->predicted = false;
     E->a_in_dbg = E->fi_in_dbg = E->sigma_in_dbg = E->rates_in_dbg = E->felem_in_dbg = false;
     E->inited = true;
@@ -692,6 +603,7 @@ static int step_stage(wf_engine *E, int stage, bool last) {
   WfPar &P = E->P;
   const int sep = E->strict ? 1 : 0;
   if (stage == 0) {
+    if (wf_contact_step_begin(E)) return 1;      // CalcExtFaceAreas every 10th step (Solver_explicit.C:445-450)
     if (!E->predicted) E->L->predict(d, P, 1, E->stream);
     E->L->elem_vol(d, P, E->et, 0, E->stream);
     E->L->node_vol(d, P, 1, E->stream);
@@ -701,7 +613,9 @@ static int step_stage(wf_engine *E, int stage, bool last) {
     E->L->elem_main(d, P, E->et, sep, E->stream);
     if (E->distributed) halo_send(E, 2);
   } else {
+    if (wf_contact_forces(E)) return 1;          // CalcContactForces (Solver_explicit.C:769-770)
     E->L->node_update(d, P, sep, last ? 0 : 1, 0, E->stream);
+    if (wf_contact_step_end(E)) return 1;        // rigid surfaces: ramp, Move, normals, plane coefficients (:981-1005)
     E->predicted = !last;
     P.xmin_cur ^= 1;
     E->time += P.dt;
@@ -773,11 +687,15 @@ extern "C" int wf_step_timed(wf_engine *E, int nsteps, float *ms) {
   mark(-1);
   for (int s = 0; s < nsteps; s++) {
     const bool last = (s == nsteps - 1);
+    if (wf_contact_step_begin(E)) return 1;
     if (!E->predicted) { E->L->predict(d, P, 1, E->stream); mark(0); }
     E->L->elem_vol(d, P, E->et, 0, E->stream); mark(1);
     E->L->node_vol(d, P, 1, E->stream); mark(2);
     E->L->elem_main(d, P, E->et, sep, E->stream); mark(3);
-    E->L->node_update(d, P, sep, last ? 0 : 1, 0, E->stream); mark(4);
+    if (wf_contact_forces(E)) return 1;
+    E->L->node_update(d, P, sep, last ? 0 : 1, 0, E->stream);
+    if (wf_contact_step_end(E)) return 1;
+    mark(4);
     E->predicted = !last;
     P.xmin_cur ^= 1;
     E->time += P.dt;
@@ -1123,7 +1041,7 @@ extern "C" int wf_UpdateCorrectionPos(wf_engine *E) {
 // ---------------------------------------------------------------------------------------------------
 // state access
 // ---------------------------------------------------------------------------------------------------
-enum Kind { K_NODEVEC, K_NODESCAL, K_ELEMSCAL, K_ELEM6, K_ELEMNODE, K_ELEMNODEVEC, K_HGQ, K_INT_HOST };
+enum Kind { K_NODEVEC, K_NODESCAL, K_ELEMSCAL, K_ELEM6, K_ELEMNODE, K_ELEMNODEVEC, K_HGQ, K_INT_HOST, K_RAW_DEV };
 
 struct ArrayRef {
   Kind kind;
@@ -1185,6 +1103,16 @@ static bool lookup(wf_engine *E, const std::string &nm, ArrayRef &r, bool for_wr
     return r.hg ? d.fsell_hg != nullptr : true;
   }
   if (nm == "m_hg_q") { r.kind = K_HGQ; r.dev = d.hg_q; r.bytes = nk * E->dim; return d.hg_q != nullptr; }
+  { // contact / rigid-surface arrays (wf_contact.cu)
+    void *p = nullptr; size_t b = 0; int kind = 0;
+    if (wf_contact_lookup(E, nm, &p, &b, &kind)) {
+      r.bytes = b;
+      if (kind == 4) { r.kind = K_INT_HOST; r.host = p; return !for_write; }
+      r.dev = (double *)p;
+      r.kind = kind == 0 ? K_NODEVEC : (kind == 1 ? K_NODESCAL : (kind == 2 ? K_ELEMSCAL : K_RAW_DEV));
+      return !(for_write && r.kind == K_RAW_DEV);
+    }
+  }
   auto hosti = [&](const void *p, size_t b) { r.kind = K_INT_HOST; r.host = p; r.bytes = b; return !for_write; };
   if (nm == "m_elnod") return hosti(E->h_elnod.data(), E->h_elnod.size() * sizeof(unsigned));
   if (nm == "m_nodel") return hosti(E->h_nodel.data(), E->h_nodel.size() * sizeof(int));
@@ -1222,6 +1150,11 @@ extern "C" int wf_get_array(wf_engine *E, const char *name, void *dst, size_t by
   double *out = (double *)dst;
   std::vector<double> h;
   if (r.kind == K_INT_HOST) { memcpy(dst, r.host, bytes); return 0; }
+  if (r.kind == K_RAW_DEV) {
+    CK(cudaMemcpyAsync(dst, r.dev, bytes, cudaMemcpyDeviceToHost, E->stream));
+    CK(cudaStreamSynchronize(E->stream));
+    return 0;
+  }
   if (r.lazy_pnode) { // calcNodalPressureFromElemental (Mechanical.C:1187-1212) on the device
     if (need_scratch(E, (size_t)d.np)) return 1;
     E->L->p_node(d, E->scratch, E->stream);
@@ -1349,6 +1282,7 @@ extern "C" int wf_set_array(wf_engine *E, const char *name, const void *src, siz
     CK(cudaStreamSynchronize(E->stream));
     if (check_launch(E, "wf_set_array")) return 1;
   }
+  if (wf_contact_after_set(E, nm)) return 1;
   if (nm == "x" && E->domtype == WF_AXISYMM && E->inited) {
     if (reset_xmin(E, E->P.xmin_cur)) return 1;
     E->L->xmin(d, E->P.xmin_cur, E->stream);
@@ -1399,6 +1333,7 @@ extern "C" int wf_calcMinEdgeLength(wf_engine *E, double *min_length, double *mi
   NEED(E->dim == 3 || E->k == 4, "calcMinEdgeLength reads four nodes per element (Domain_d.C:2381-2384): not defined for triangles");
   double o[3];
   if (diag_reduce(E, true, false, o)) return 1;
+  if (wf_contact_refresh_nodlen(E)) return 1;
   if (min_length) *min_length = o[0];
   if (min_height) *min_height = o[1];
   return 0;

@@ -242,7 +242,7 @@ __global__ void __launch_bounds__(TPB_N) k_node_vol(WfDev d, WfPar P, int mode) 
 template <int ET>
 WF_DI double elem_pressure(const WfDev &d, const WfPar &P, int e, const double (&np_)[Elem<ET>::K], double vol,
                            double vol0, double rho_e, const double (&dH)[Elem<ET>::D][Elem<ET>::K],
-                           const double (&vl)[Elem<ET>::K][Elem<ET>::D]) {
+                           const double (&vl)[Elem<ET>::K][Elem<ET>::D], bool is_contact = false) {
   constexpr int K = Elem<ET>::K, D = Elem<ET>::D;
   if (P.press == 0) {
     if constexpr (D == 3) {
@@ -255,7 +255,7 @@ WF_DI double elem_pressure(const WfDev &d, const WfPar &P, int e, const double (
 #pragma unroll
         for (int a = 0; a < K; a++) div_v += dH[0][a] * vl[a][0] + dH[1][a] * vl[a][1] + dH[2][a] * vl[a][2];
       }
-      return pressure_default3d(P, J_avg, vol0, vol, rho_e, div_v);
+      return pressure_default3d(P, J_avg, vol0, vol, rho_e, div_v, is_contact);
     } else {
       return P.Kbulk * (1.0 - vol / vol0); // calcElemPressureLocal, Mechanical.C:1165-1170
     }
@@ -272,6 +272,16 @@ WF_DI double elem_pressure(const WfDev &d, const WfPar &P, int e, const double (
     pe /= (double)K;
     return pe;
   }
+}
+// Mechanical.C:729-747: the element counts as "in contact" when any of its nodes carries a non-zero contact force
+template <int ET>
+WF_DI bool elem_in_contact(const WfDev &d, int e) {
+  bool c = false;
+  if (Elem<ET>::D == 3 && d.cflag) {
+#pragma unroll
+    for (int a = 0; a < Elem<ET>::K; a++) c = c || d.cflag[__ldg(d.elnod + (long long)a * d.ep + e)] != 0;
+  }
+  return c;
 }
 template <int ET>
 WF_DI void gather_nodal_p(const WfDev &d, const int (&nid)[Elem<ET>::K], double (&np_)[Elem<ET>::K]) {
@@ -340,7 +350,7 @@ __global__ void __launch_bounds__(TPB_E) k_elem_main(WfDev d, WfPar P, int strid
   shape_derivs<ET>(A, dH);
   double Dr[6], Wr[3];
   strain_rates<ET>(dH, detJ, vl, radius, d.domtype, Dr, Wr);
-  const double p = elem_pressure<ET>(d, P, e, npn, vol, vol0, rho_e, dH, vl);
+  const double p = elem_pressure<ET>(d, P, e, npn, vol, vol0, rho_e, dH, vl, elem_in_contact<ET>(d, e));
   StressOut so;
   stress_update(P, P.dt, p, Dr, Wr, tau, pl, sy_prev, so);
   if (P.track_eps) {
@@ -528,6 +538,7 @@ __global__ void __launch_bounds__(TPB_N) k_node_update(WfDev d, WfPar P, int fus
     long long i = (long long)c * d.np + n;
     double fe = d.fe ? d.fe[i] : 0.0;
     a[c] = (fe - fi[c]) / mass;
+    if (d.contforce) a[c] += d.contforce[i] / mass; // calcAccel with contact, Mechanical.C:330-335
     if (bm & (1u << c)) a[c] = 0.0;
     double pa = d.prev_a[i];
     a[c] = f * (a[c] - P.alpha * pa);
@@ -842,7 +853,7 @@ __global__ void k_u_pressure(WfDev d, WfPar P) {
   gather_nodal<ET>(d.v, d.np, nid, vl);
   gather_nodal_p<ET>(d, nid, npn);
   load_dH<ET>(d, e, dH);
-  d.p[e] = elem_pressure<ET>(d, P, e, npn, d.vol[e], d.vol_0[e], d.rho[e], dH, vl);
+  d.p[e] = elem_pressure<ET>(d, P, e, npn, d.vol[e], d.vol_0[e], d.rho[e], dH, vl, elem_in_contact<ET>(d, e));
 }
 
 __global__ void k_u_stress(WfDev d, WfPar P, double dt) {
@@ -992,6 +1003,7 @@ __global__ void k_u_accel(WfDev d) { // calcAccel
     long long i = (long long)c * d.np + n;
     double fe = d.fe ? d.fe[i] : 0.0;
     d.a[i] = (fe - d.fi[i]) / d.mdiag[n];
+    if (d.contforce) d.a[i] += d.contforce[i] / d.mdiag[n]; // Mechanical.C:330-335
   }
 }
 template <int D>

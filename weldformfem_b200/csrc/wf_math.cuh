@@ -153,9 +153,10 @@ WF_DI void strain_rates(const double (&dH)[Elem<ET>::D][Elem<ET>::K], double det
   Wr[0] = wxy * 0.5; Wr[1] = wyz * 0.5; Wr[2] = wxz * 0.5;
 }
 
-// calcElemPressure (Mechanical.C:691-819), contact off.  J_avg is the mean of the nodal volume
-// ratios; div_v the un-normalised sum_a gradN_a . v_a (3D only).
-WF_DI double pressure_default3d(const WfPar &P, double J_avg, double vol0, double vol1, double rho_e, double div_v) {
+// calcElemPressure (Mechanical.C:691-819).  J_avg is the mean of the nodal volume ratios; div_v the
+// un-normalised sum_a gradN_a . v_a (3D only); is_contact = an element node carries a contact force (:729-747).
+WF_DI double pressure_default3d(const WfPar &P, double J_avg, double vol0, double vol1, double rho_e, double div_v,
+                                bool is_contact = false) {
   const double K = P.Kbulk;
   if (P.stab_simple) {
     double J_bar = (1 - 0.0) * J_avg; // alpha = 0
@@ -164,14 +165,14 @@ WF_DI double pressure_default3d(const WfPar &P, double J_avg, double vol0, doubl
   }
   double J_local = vol1 / vol0;
   double h = pow(vol1, 1.0 / 3.0);
-  double alpha = P.alpha_free;
+  double alpha = is_contact ? P.alpha_contact : P.alpha_free;
   double J_bar = alpha * J_local + (1 - alpha) * J_avg;
   if (J_bar < P.J_min) J_bar = 0.2;
   double p_physical = -K * (P.log_factor * log(J_bar) + (1.0 - P.log_factor) * (J_bar - 1.0));
   double c = sqrt(K / rho_e);
   double tau = h / (2.0 * c);
   double p_pspg = 0.0;
-  double p_hg = P.hg_coeff_free * K * fabs(J_local - J_avg);
+  double p_hg = (is_contact ? P.hg_coeff_contact : P.hg_coeff_free) * K * fabs(J_local - J_avg);
   double p_q = 0.0;
   if (div_v < 0.0) {
     double a1 = P.pspg_scale * tau * div_v * K, a2 = P.p_pspg_bulkfac * K;
@@ -179,7 +180,8 @@ WF_DI double pressure_default3d(const WfPar &P, double J_avg, double vol0, doubl
     double q1 = P.av_coeff_div * rho_e * h * c * (-div_v);
     double delta_J = 1.0 - J_local;
     double q2 = P.av_coeff_bulk * K * delta_J;
-    p_q = (q1 < q2) ? q2 : q1;
+    if (is_contact) p_q = 0.5 * (q1 + q2);
+    else p_q = (q1 < q2) ? q2 : q1;
   }
   return p_physical + p_pspg + p_hg + p_q;
 }

@@ -231,3 +231,127 @@ void wf_partition_box_coords(const wf_partition *p, std::vector<double> &x) {
   for (size_t i = 0; i < p->l2g.size(); i++) wf_box_node_xyz(p->box, ax, p->l2g[i], x.data() + i * dim);
 }
 int wf_partition_box_dim(const wf_partition *p) { return p->box.dim; }
+
+// ---- Domain_d::SearchExtNodes (src/common/Domain_d.C:110-205), integer part --------------------------------
+// The reference appends every element face to faceList unless a face with the same node set is already there
+// (then it counts it), matching by linear search.  What it ends with: every distinct node set once, ordered by
+// first occurrence (ascending element, then local face), with its multiplicity; nodes of faces that occur once
+// are the external nodes.  Same result here from one sort of the canonical (sorted-node) keys.
+// Face tables: tetra_faces / quad_edges (Domain_d.h:172-193); the constructor wires the tetra table for 3D
+// (Domain_d.h:246-249) and set2DFacesValues the quad edges for 2D (:785-791).
+namespace {
+const int kTetraFaces[4][3] = {{0, 1, 2}, {0, 1, 3}, {1, 2, 3}, {0, 2, 3}};
+const int kQuadEdges[4][2] = {{0, 1}, {1, 2}, {2, 3}, {3, 0}};
+struct FaceKey {
+  int n[3];
+  int serial;
+  bool same(const FaceKey &o) const { return n[0] == o.n[0] && n[1] == o.n[1] && n[2] == o.n[2]; }
+};
+}  // namespace
+
+extern "C" int wf_host_ext_faces(int dim, int nodxelem, int n_nodes, int n_elems, const unsigned *elnod, unsigned char *ext_nodes,
+                                 int *n_faces_total, int *n_ext_faces, int *ext_face_nodes, int *ext_face_elem) {
+  int facenod;
+  if (dim == 3 && nodxelem == 4) facenod = 3;
+  else if (dim == 2 && nodxelem == 4) facenod = 2;
+  else return 1;
+  const size_t nf = (size_t)n_elems * 4;
+  std::vector<FaceKey> keys(nf);
+  for (int e = 0; e < n_elems; e++)
+    for (int f = 0; f < 4; f++) {
+      FaceKey &k = keys[(size_t)e * 4 + f];
+      k.n[2] = -1;
+      for (int q = 0; q < facenod; q++) {
+        const unsigned g = elnod[(size_t)e * nodxelem + (facenod == 3 ? kTetraFaces[f][q] : kQuadEdges[f][q])];
+        if (g >= (unsigned)n_nodes) return 2;
+        k.n[q] = (int)g;
+      }
+      std::sort(k.n, k.n + facenod);
+      k.serial = (int)((size_t)e * 4 + f);
+    }
+  std::sort(keys.begin(), keys.end(), [](const FaceKey &a, const FaceKey &b) {
+    for (int q = 0; q < 3; q++)
+      if (a.n[q] != b.n[q]) return a.n[q] < b.n[q];
+    return a.serial < b.serial;
+  });
+  std::vector<int> mult(nf, 0); // multiplicity, stored at the serial of the first occurrence
+  int total = 0;
+  for (size_t i = 0; i < nf;) {
+    size_t j = i + 1;
+    while (j < nf && keys[j].same(keys[i])) j++;
+    mult[keys[i].serial] = (int)(j - i);
+    total++;
+    i = j;
+  }
+  memset(ext_nodes, 0, (size_t)n_nodes);
+  int nx = 0;
+  for (size_t s = 0; s < nf; s++) {
+    if (mult[s] != 1) continue;
+    const int e = (int)(s / 4), f = (int)(s % 4);
+    for (int q = 0; q < facenod; q++) {
+      const int g = (int)elnod[(size_t)e * nodxelem + (facenod == 3 ? kTetraFaces[f][q] : kQuadEdges[f][q])];
+      ext_face_nodes[(size_t)nx * facenod + q] = g;
+      ext_nodes[g] = 1;
+    }
+    ext_face_elem[nx] = e;
+    nx++;
+  }
+  if (n_faces_total) *n_faces_total = total;
+  if (n_ext_faces) *n_ext_faces = nx;
+  return 0;
+}
+
+// ---- TriMesh_d::AxisPlaneMesh (src/common/Mesh.C:48-283) ----------------------------------------------------
+// (dens+1)^2 nodes / 2 dens^2 triangles (3D) or dens+1 nodes / dens segments (2D).  As in the reference the nodes
+// start at p1 and advance by dl = (p2 - p1).x / dens along x (and y in 3D) whatever `axis` says — `axis` only
+// selects the component of the initial normal (+1 if positaxisorent, else -1) — and the winding follows
+// positaxisorent (:156-163, :184-190).
+extern "C" int wf_host_axis_plane_counts(int dimension, int dens, int *n_nodes, int *n_elems) {
+  if ((dimension != 2 && dimension != 3) || dens < 1) return 1;
+  *n_nodes = dimension == 3 ? (dens + 1) * (dens + 1) : dens + 1;
+  *n_elems = dimension == 3 ? dens * dens * 2 : dens;
+  return 0;
+}
+extern "C" int wf_host_axis_plane_mesh(int dimension, int mesh_id, int axis, int positaxisorent, const double p1[3], const double p2[3],
+                                       int dens, double *node, int *elnode, double *normal, int *ele_mesh_id) {
+  int nn, ne;
+  if (wf_host_axis_plane_counts(dimension, dens, &nn, &ne)) return 1;
+  const double dl = (p2[0] - p1[0]) / dens;
+  double x2 = p1[1];
+  const double x3 = p1[2];
+  int vi = 0;
+  const int rows = dimension == 2 ? 1 : dens + 1;
+  for (int j = 0; j < rows; j++) {
+    double x1 = p1[0];
+    for (int i = 0; i < dens + 1; i++) {
+      node[3 * vi] = x1; node[3 * vi + 1] = x2; node[3 * vi + 2] = x3;
+      vi++;
+      x1 += dl;
+    }
+    x2 += dl;
+  }
+  int el = 0;
+  if (dimension == 3) {
+    for (int j = 0; j < dens; j++)
+      for (int i = 0; i < dens; i++) {
+        const int a = (dens + 1) * j + i, b = a + 1, c = (dens + 1) * (j + 1) + i, d = c + 1;
+        const int t[2][2][3] = {{{a, c, b}, {b, c, d}}, {{a, b, c}, {b, d, c}}};
+        for (int e = 0; e < 2; e++, el++)
+          for (int q = 0; q < 3; q++) elnode[3 * el + q] = t[positaxisorent ? 1 : 0][e][q];
+      }
+  } else {
+    for (int i = 0; i < dens; i++, el++) {
+      elnode[2 * el] = positaxisorent ? i : i + 1;
+      elnode[2 * el + 1] = positaxisorent ? i + 1 : i;
+    }
+  }
+  const double f = positaxisorent ? 1. : -1.;
+  for (int e = 0; e < ne; e++) {
+    normal[3 * e] = normal[3 * e + 1] = normal[3 * e + 2] = 0.0;
+    if (axis == 0) normal[3 * e] = f;
+    else if (axis == 1) normal[3 * e + 1] = f;
+    else if (dimension == 3) normal[3 * e + 2] = f;
+    ele_mesh_id[e] = mesh_id;
+  }
+  return 0;
+}

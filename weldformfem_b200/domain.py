@@ -19,7 +19,26 @@ BILINEAR, HOLLOMON = 0, 1
 STRICT, FAST = 1, 0
 
 _INT_ARRAYS = {"m_nodel": np.int32, "m_nodel_loc": np.int32, "m_nodel_offset": np.int32, "m_nodel_count": np.int32,
-               "m_elnod": np.uint32}
+               "m_elnod": np.uint32, "ext_nodes": np.uint8, "m_mesh_in_contact": np.int32}
+
+
+def axis_plane_mesh(dimension, mesh_id, axis, positaxisorent, p1, p2, dens):
+    """TriMesh_d::AxisPlaneMesh (src/common/Mesh.C:48-283) on the host: (node[n,3], elnode[e,nen], normal[e,3], mesh_id[e])."""
+    lib = _lib.load()
+    nn, ne = C.c_int(), C.c_int()
+    if lib.wf_host_axis_plane_counts(int(dimension), int(dens), C.byref(nn), C.byref(ne)):
+        raise WfError("bad plane mesh parameters")
+    nen = 3 if dimension == 3 else 2
+    node = np.zeros((nn.value, 3)); elnode = np.zeros((ne.value, nen), dtype=np.int32)
+    normal = np.zeros((ne.value, 3)); mid = np.zeros(ne.value, dtype=np.int32)
+    a3 = lambda q: (C.c_double * 3)(*[float(t) for t in q])
+    dp, ip = C.POINTER(C.c_double), C.POINTER(C.c_int)
+    rc = lib.wf_host_axis_plane_mesh(int(dimension), int(mesh_id), int(axis), int(bool(positaxisorent)), a3(p1), a3(p2),
+                                     int(dens), node.ctypes.data_as(dp), elnode.ctypes.data_as(ip),
+                                     normal.ctypes.data_as(dp), mid.ctypes.data_as(ip))
+    if rc:
+        raise WfError("wf_host_axis_plane_mesh failed")
+    return node, elnode, normal, mid
 
 
 class WfError(RuntimeError):
@@ -160,6 +179,52 @@ class Domain_d:
         vals = np.ascontiguousarray(vals, dtype=np.float64)
         self._ck(self._lib.wf_set_bc_values(self._h, int(dim), vals.size, vals.ctypes.data_as(C.POINTER(C.c_double))))
 
+    # ---- contact with rigid tool surfaces (src/explicit/main.C:636-848) ---------------------------
+    def SearchExtNodes(self):                                  # Domain_d.C:110
+        self._ck(self._lib.wf_SearchExtNodes(self._h))
+
+    def add_plane(self, dimension, mesh_id, axis, positaxisorent, p1, p2, dens, vel=(0.0, 0.0, 0.0)):
+        """One more rigid body: AxisPlaneMesh, every node moving with ``vel`` (main.C:672-708 for the first body,
+        TriMesh_d::AddMesh, Mesh.C:438-539, for the others: node ids offset by the nodes already present)."""
+        node, elnode, normal, mid = axis_plane_mesh(dimension, mesh_id, axis, positaxisorent, p1, p2, dens)
+        tm = getattr(self, "_trimesh", None)
+        if tm is None:
+            tm = self._trimesh = dict(dimension=int(dimension), node=[], node_v=[], elnode=[], normal=[], mesh_id=[], nn=0)
+        if tm["dimension"] != int(dimension):
+            raise WfError("all rigid bodies must have the same dimension")
+        tm["node"].append(node)
+        tm["node_v"].append(np.tile(np.asarray(vel, dtype=np.float64), (node.shape[0], 1)))
+        tm["elnode"].append(elnode + tm["nn"])
+        tm["normal"].append(normal)
+        tm["mesh_id"].append(mid)
+        tm["nn"] += node.shape[0]
+
+    def set_trimesh(self, dimension, node, node_v, elnode, normal, mesh_id):   # Domain_d::setTriMesh, Domain_d.h:464
+        node = np.ascontiguousarray(node, dtype=np.float64)
+        node_v = np.ascontiguousarray(node_v, dtype=np.float64)
+        elnode = np.ascontiguousarray(elnode, dtype=np.int32)
+        normal = np.ascontiguousarray(normal, dtype=np.float64)
+        mesh_id = np.ascontiguousarray(mesh_id, dtype=np.int32)
+        dp, ip = C.POINTER(C.c_double), C.POINTER(C.c_int)
+        self._ck(self._lib.wf_set_trimesh(self._h, int(dimension), node.size // 3, mesh_id.size, node.ctypes.data_as(dp),
+                                          node_v.ctypes.data_as(dp), elnode.ctypes.data_as(ip), normal.ctypes.data_as(dp),
+                                          mesh_id.ctypes.data_as(ip)))
+        self._trimesh = None
+
+    def contact_on(self, mu_sta=0.0, mu_dyn=0.0, penalty_factor=-1.0, end_time=1.0):
+        """fricCoeffStatic / fricCoeffDynamic / penaltyFactor (main.C:716-725), CalcSpheres + setContactOn (:842-847),
+        SetEndTime.  Rigid bodies collected by add_plane are handed to the engine here."""
+        tm = getattr(self, "_trimesh", None)
+        if tm:
+            self.set_trimesh(tm["dimension"], np.concatenate(tm["node"]), np.concatenate(tm["node_v"]),
+                             np.concatenate(tm["elnode"]), np.concatenate(tm["normal"]), np.concatenate(tm["mesh_id"]))
+        self._ck(self._lib.wf_set_contact(self._h, float(mu_sta), float(mu_dyn), float(penalty_factor), float(end_time)))
+
+    def trimesh_counts(self):
+        a, b, c = C.c_int(), C.c_int(), C.c_int()
+        self._ck(self._lib.wf_get_trimesh_counts(self._h, C.byref(a), C.byref(b), C.byref(c)))
+        return dict(dimension=a.value, nodecount=b.value, elemcount=c.value)
+
     def SetDT(self, dt):                                       # Domain_d.h:629
         self._dt = float(dt)
 
@@ -204,6 +269,8 @@ class Domain_d:
                 self._ck(getattr(self._lib, "wf_" + fn[:9])(self._h, d))
         elif fn == "CalcStressStrain":
             self._ck(self._lib.wf_CalcStressStrain(self._h, float(arg)))
+        elif fn == "calcMinEdgeLength":
+            self.calcMinEdgeLength()
         elif fn in _lib.UNFUSED:
             self._ck(getattr(self._lib, "wf_" + fn)(self._h))
         else:
