@@ -67,6 +67,55 @@ struct StabilizationParams {
          av_coeff_bulk = 0, log_factor = 0, pspg_scale = 0, p_pspg_bulkfac = 0, J_min = 0, hg_visc = 0, hg_stiff = 0;
 };
 
+// TriMesh_d (include/common/Mesh.h:72-140, src/common/Mesh.C): the rigid tool surfaces, flattened the way the
+// reference keeps them (all bodies in one node / facet list).  Built on the host, handed to the engine by
+// Domain_d::setTriMesh; from then on the engine moves the surfaces itself (Solver_explicit.C:981-1005).
+class TriMesh_d {
+ public:
+  int dimension = 3;
+  int nodecount = 0, elemcount = 0, mesh_count = 0;
+  std::vector<double> node, node_v, normal;  // xyz triples
+  std::vector<int> elnode, ele_mesh_id;
+  double3 m_v{0, 0, 0};
+  double mu_sta[1] = {0.0}, mu_dyn[1] = {0.0};
+  double heat_cond = 0.0, T_const = 0.0;
+  // TriMesh_d::AxisPlaneMesh (Mesh.C:48-283)
+  void AxisPlaneMesh(int id, int axis, bool positaxisorent, double3 p1, double3 p2, int dens) {
+    int nn = 0, ne = 0;
+    if (wf_host_axis_plane_counts(dimension, dens, &nn, &ne)) throw std::runtime_error("AxisPlaneMesh: bad arguments");
+    const int nen = dimension == 3 ? 3 : 2;
+    node.assign(3 * (size_t)nn, 0.0);
+    node_v.assign(3 * (size_t)nn, 0.0);
+    normal.assign(3 * (size_t)ne, 0.0);
+    elnode.assign((size_t)nen * ne, 0);
+    ele_mesh_id.assign(ne, id);
+    double a[3] = {p1.x, p1.y, p1.z}, b[3] = {p2.x, p2.y, p2.z};
+    if (wf_host_axis_plane_mesh(dimension, id, axis, positaxisorent ? 1 : 0, a, b, dens, node.data(), elnode.data(), normal.data(),
+                                ele_mesh_id.data()))
+      throw std::runtime_error("AxisPlaneMesh failed");
+    nodecount = nn;
+    elemcount = ne;
+    mesh_count = 1;
+  }
+  void SetMeshVel(double3 v) { m_v = v; }  // Mesh.h:117
+  void SetNodesVel(double3 v) {            // main.C:707-708
+    m_v = v;
+    for (int n = 0; n < nodecount; n++) { node_v[3 * n] = v.x; node_v[3 * n + 1] = v.y; node_v[3 * n + 2] = v.z; }
+  }
+  // TriMesh_d::AddMesh (Mesh.C:438-539): node ids offset by the nodes already present, new nodes move with m.m_v
+  void AddMesh(const TriMesh_d &m) {
+    if (m.dimension != dimension) throw std::runtime_error("AddMesh: dimension mismatch");
+    for (int q : m.elnode) elnode.push_back(q + nodecount);
+    node.insert(node.end(), m.node.begin(), m.node.end());
+    for (int n = 0; n < m.nodecount; n++) { node_v.push_back(m.m_v.x); node_v.push_back(m.m_v.y); node_v.push_back(m.m_v.z); }
+    normal.insert(normal.end(), m.normal.begin(), m.normal.end());
+    ele_mesh_id.insert(ele_mesh_id.end(), m.ele_mesh_id.begin(), m.ele_mesh_id.end());
+    nodecount += m.nodecount;
+    elemcount += m.elemcount;
+    mesh_count++;
+  }
+};
+
 enum dom_type { _Plane_Strain_ = WF_PLANE_STRAIN, _Plane_Stress_ = WF_PLANE_STRESS, _Axi_Symm_ = WF_AXISYMM, _3D_ = WF_3D };
 
 class Domain_d {
@@ -113,6 +162,17 @@ class Domain_d {
   double m_artifvisc[2] = {0.0, 0.0};               // main.C:340-347
   void AddBCVelNode(int node, int dim, double val) { ck(wf_add_bc_vel(need(), node, dim, val)); }  // Domain_d.C:1057
   void AllocateBCs() { ck(wf_allocate_bcs(need())); }                                              // Domain_d.C:1063
+  // ---- contact with rigid tool surfaces (main.C:636-848) -------------------------------------------
+  void SearchExtNodes() { ck(wf_SearchExtNodes(need())); }  // Domain_d.C:110
+  void setTriMesh(TriMesh_d *m) { trimesh = m; }            // Domain_d.h:464
+  void addMeshData(const TriMesh_d &m) {                    // Domain_d.C:2780
+    if (!trimesh) throw std::runtime_error("addMeshData: setTriMesh first");
+    trimesh->AddMesh(m);
+  }
+  TriMesh_d *getTriMesh() { return trimesh; }
+  void setContactPF(double pf) { m_contPF = pf; }           // Domain_d.h:771
+  void setContactOn() { contact = true; }                   // Domain_d.h:642
+  bool isContactOn() const { return contact; }
   void SetDT(double dt) { dt_ = dt; }            // Domain_d.h:629
   void SetEndTime(double t) { end_t_ = t; }      // Domain_d.h:630
   int getElemCount() const { return n_elems_; }
@@ -127,6 +187,14 @@ class Domain_d {
   void InitSolve() {
     pushSettings();
     if (!(dt_ > 0.0)) throw std::runtime_error("SetDT first");
+    if (contact) {  // main.C:700-725, :842-847, :862 (m_elem_length for the contact stiffness)
+      if (!trimesh) throw std::runtime_error("contact is on but no TriMesh_d was set");
+      ck(wf_set_trimesh(eng_, trimesh->dimension, trimesh->nodecount, trimesh->elemcount, trimesh->node.data(),
+                        trimesh->node_v.data(), trimesh->elnode.data(), trimesh->normal.data(), trimesh->ele_mesh_id.data()));
+      ck(wf_set_contact(eng_, trimesh->mu_sta[0], trimesh->mu_dyn[0], m_contPF, end_t_));
+      double ml = 0, mh = 0;
+      ck(wf_calcMinEdgeLength(eng_, &ml, &mh));
+    }
     ck(wf_init(eng_, dt_));
     inited_ = true;
   }
@@ -223,6 +291,9 @@ class Domain_d {
     ck(wf_set_options(eng_, m_press_algorithm, m_artifvisc[0], m_artifvisc[1], strict_ ? WF_STRICT : WF_FAST));
   }
 
+  TriMesh_d *trimesh = nullptr;
+  bool contact = false;
+  double m_contPF = 0.1;  // Domain_d.h:256
   wf_engine *eng_ = nullptr;
   int device_ = 0, dim_ = 0, nodxelem_ = 0, n_nodes_ = 0, n_elems_ = 0;
   dom_type domtype_ = _3D_;

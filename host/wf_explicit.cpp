@@ -4,7 +4,9 @@
 // steps on the GPU and (optionally) dumps reference-layout arrays for the parity tests.
 //
 //   wf_explicit --kind hex|tet|quad|tri|axiquad --n N [--steps S] [--vtop V] [--hg C] [--press P] [--strict]
-//               [--cfl F] [--dump FILE] [--time]
+//               [--cfl F] [--dump FILE] [--time] [--contact]
+// --contact (tet / quad): instead of prescribing the top plane, a rigid plane / line comes down on it with velocity
+// (0.5, .., vtop), friction 0.3 / 0.2 and penalty factor 0.6, like examples/input/Contact_Compression_*.json.
 // dump format: for every array  "<name> <count>\n" followed by <count> raw little-endian doubles.
 #include <chrono>
 #include <cstdio>
@@ -20,7 +22,7 @@ int main(int argc, char **argv) {
   std::string kind = "hex", dump;
   int n = 8, steps = 10, press = 0;
   double vtop = -10.0, hg = -1.0, cfl = -1.0;
-  bool strict = false, timeit = false;
+  bool strict = false, timeit = false, contact = false;
   for (int i = 1; i < argc; i++) {
     std::string a = argv[i];
     auto val = [&]() -> const char * { return i + 1 < argc ? argv[++i] : ""; };
@@ -34,6 +36,7 @@ int main(int argc, char **argv) {
     else if (a == "--dump") dump = val();
     else if (a == "--strict") strict = true;
     else if (a == "--time") timeit = true;
+    else if (a == "--contact") contact = true;
     else { fprintf(stderr, "unknown argument %s\n", a.c_str()); return 2; }
   }
   bool three_d = kind == "hex" || kind == "tet";
@@ -66,12 +69,28 @@ int main(int argc, char **argv) {
     int nplane = (n + 1) * (dim == 3 ? n + 1 : 1);
     for (int nd = 0; nd < nplane; nd++)
       for (int d = 0; d < dim; d++) dom.AddBCVelNode(nd, d, 0.0);
-    for (int nd = nplane * n; nd < nplane * (n + 1); nd++)
-      for (int d = 0; d < dim; d++) dom.AddBCVelNode(nd, d, d == dim - 1 ? vtop : 0.0);
+    if (!contact)
+      for (int nd = nplane * n; nd < nplane * (n + 1); nd++)
+        for (int d = 0; d < dim; d++) dom.AddBCVelNode(nd, d, d == dim - 1 ? vtop : 0.0);
     dom.AllocateBCs();
 
     double dt = cfl * h / mat.cs0;                            // src/explicit/main.C:862-879
     dom.SetDT(dt);
+    TriMesh_d msh;
+    if (contact) {                                            // src/explicit/main.C:636-848
+      dom.SearchExtNodes();
+      const double Lb = n * h, top = Lb + 0.01 * h;
+      msh.dimension = dim;
+      if (dim == 3) msh.AxisPlaneMesh(0, 2, false, make_double3(-0.5 * Lb, -0.5 * Lb, top), make_double3(1.5 * Lb, 1.5 * Lb, top), 4);
+      else msh.AxisPlaneMesh(0, 1, false, make_double3(-0.5 * Lb, top, 0.0), make_double3(1.5 * Lb, top, 0.0), 4);
+      msh.SetNodesVel(dim == 3 ? make_double3(0.5, 0.0, vtop) : make_double3(0.5, vtop, 0.0));
+      msh.mu_sta[0] = 0.3;
+      msh.mu_dyn[0] = 0.2;
+      dom.setTriMesh(&msh);
+      dom.setContactPF(0.6);
+      dom.setContactOn();
+      dom.SetEndTime(100 * dt);
+    }
     dom.InitSolve();
     auto t0 = std::chrono::steady_clock::now();
     dom.Step(steps);
@@ -84,7 +103,8 @@ int main(int argc, char **argv) {
     if (!dump.empty()) {
       FILE *f = fopen(dump.c_str(), "wb");
       if (!f) { perror("dump"); return 1; }
-      const char *names[] = {"x", "v", "a", "u", "prev_a", "m_fi", "m_mdiag", "vol", "p", "pl_strain", "sigma_y", "m_sigma", "m_tau"};
+      std::vector<const char *> names = {"x", "v", "a", "u", "prev_a", "m_fi", "m_mdiag", "vol", "p", "pl_strain", "sigma_y", "m_sigma", "m_tau"};
+      if (contact) { names.push_back("contforce"); names.push_back("ut_prev"); names.push_back("node_area"); }
       for (const char *nm : names) {
         std::vector<double> q = dom.get(nm);
         fprintf(f, "%s %zu\n", nm, q.size());

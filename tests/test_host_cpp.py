@@ -91,3 +91,23 @@ def test_cpp_wf_explicit_matches_oracle(host_bins, oracle_port, tmp_path, kind, 
     ref.step(20)
     for nm in ("x", "v", "u", "m_fi", "m_sigma", "pl_strain", "p"):
         assert relerr(got[nm], ref.get(nm)) < 1e-8, (kind, nm)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("kind,n", [("tet", 6), ("quad", 12)])
+def test_cpp_wf_explicit_contact_matches_oracle(host_bins, oracle_port, tmp_path, kind, n):
+    """The C++ TriMesh_d / setTriMesh / setContactOn path (host/wf_domain.hpp) against the oracle's contact step."""
+    from weldformfem_b200 import cases
+    vt = -200.0 if kind == "tet" else -100.0
+    case = cases.contact_tets(n, tool_vel=vt, two_planes=False) if kind == "tet" else cases.contact_quads(n, tool_vel=vt)
+    dump = str(tmp_path / "c.bin")
+    r = subprocess.run([os.path.join(host_bins, "wf_explicit"), "--kind", kind, "--n", str(n), "--steps", "40", "--vtop", str(vt),
+                        "--contact", "--dump", dump], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    got = _read_dump(dump)
+    ref = oracle_port()
+    case.apply(ref)
+    ref.step(40)
+    assert (ref.get("m_mesh_in_contact") >= 0).any()
+    for nm in ("x", "v", "u", "m_fi", "m_sigma", "pl_strain", "p", "contforce", "ut_prev", "node_area"):
+        assert relerr(got[nm], ref.get(nm)) < 1e-8, (kind, nm)
