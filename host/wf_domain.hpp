@@ -54,8 +54,17 @@ class Material_ {
     Material_model = HOLLOMON;
   }
   const Elastic_ &Elastic() const { return elastic_; }
+  // Material_::Init_JohnsonCook (Material.cuh:105-116)
+  void Init_JohnsonCook(const Elastic_ &el, double a, double b, double n_, double c, double eps_0_, double m_, double T_m_, double T_t_) {
+    elastic_ = el;
+    Material_model = JOHNSON_COOK;
+    A = a; B = b; C = c; m = m_; n = n_; eps_0 = eps_0_; T_m = T_m_; T_t = T_t_;
+  }
   int Material_model = BILINEAR;
   double sy0 = 1.0e10, K = 0.0, m = 1.0, cs0 = 0.0, Ep = 0.0;
+  double A = 0, B = 0, C = 0, n = 0, eps_0 = 1.0, T_m = 1.0e10, T_t = 0.0;                   // Johnson-Cook (Material.cuh:67-72)
+  double C1 = 0, C2 = 0, m1 = 0, m2 = 0, n1 = 0, n2 = 0, I1 = 0, I2 = 0;                    // GMT (Material.cuh:76)
+  double e_min = 0, e_max = 1.0e10, er_min = 0, er_max = 1.0e10, T_min = 0, T_max = 1.0e10;  // Material.cuh:63-65
 
  private:
   Elastic_ elastic_;
@@ -153,6 +162,8 @@ class Domain_d {
     fetchCounts();
   }
   void setDensity(double rho) { rho0_ = rho; }  // Domain_d.C:951
+  void setTemp(double T) { temp_ = T; }         // Domain_d::setTemp (uniform initial temperature, main.C:441)
+  double m_max_edot = 1.0e6;                    // Domain_d.h:824
   void AssignMaterial(const Material_ *mat) {    // Domain_d.C:903
     mat_ = *mat;
     have_mat_ = true;
@@ -283,6 +294,16 @@ class Domain_d {
     m.sy0 = mat_.sy0;
     m.K = mat_.K;
     m.m = mat_.m;
+    if (mat_.Material_model == JOHNSON_COOK) {
+      const double q[8] = {mat_.A, mat_.B, mat_.n, mat_.C, mat_.eps_0, mat_.m, mat_.T_m, mat_.T_t};
+      for (int i = 0; i < 8; i++) m.q[i] = q[i];
+    } else if (mat_.Material_model == GMT) {
+      const double q[14] = {mat_.n1, mat_.n2, mat_.C1, mat_.C2, mat_.m1, mat_.m2, mat_.I1, mat_.I2,
+                            mat_.e_min, mat_.e_max, mat_.er_min, mat_.er_max, mat_.T_min, mat_.T_max};
+      for (int i = 0; i < 14; i++) m.q[i] = q[i];
+    }
+    m.temp = temp_;
+    m.max_edot = m_max_edot;
     ck(wf_set_material(eng_, &m));
     wf_stab s{m_stab.alpha_free, m_stab.alpha_contact, m_stab.hg_coeff_free, m_stab.hg_coeff_contact,
               m_stab.av_coeff_div, m_stab.av_coeff_bulk, m_stab.log_factor, m_stab.pspg_scale,
@@ -298,7 +319,7 @@ class Domain_d {
   int device_ = 0, dim_ = 0, nodxelem_ = 0, n_nodes_ = 0, n_elems_ = 0;
   dom_type domtype_ = _3D_;
   bool vol_weight_ = false, strict_ = false, have_mat_ = false, inited_ = false;
-  double rho0_ = 0.0, dt_ = 0.0, end_t_ = 0.0, hexa_hg_ = 0.0;
+  double rho0_ = 0.0, dt_ = 0.0, end_t_ = 0.0, hexa_hg_ = 0.0, temp_ = 20.0;
   Material_ mat_;
 };
 

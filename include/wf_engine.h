@@ -30,7 +30,7 @@ typedef struct wf_engine wf_engine; /* opaque; owns all device memory of one GPU
 /* dom_type, include/common/Domain_d.h:101 */
 enum { WF_PLANE_STRAIN = 0, WF_PLANE_STRESS = 1, WF_AXISYMM = 2, WF_3D = 3 };
 /* Material_model, include/common/Material.cuh:9-13 */
-enum { WF_BILINEAR = 0, WF_HOLLOMON = 1 };
+enum { WF_BILINEAR = 0, WF_HOLLOMON = 1, WF_JOHNSON_COOK = 2, WF_GMT = 3 };
 /* pressure law selected per step (Solver_explicit.C:735-746):
  *   0 = m_press_algorithm 0: calcElemPressure (3D, Mechanical.C:691) / calcElemPressureLocal (2D, :1165)
  *   1 = m_press_algorithm 1: calcElemPressureANP as shipped (Mechanical.C:1220; accumulates)
@@ -51,6 +51,12 @@ typedef struct wf_material {
   double rho0;   /* setDensity(), Domain_d.C:951 */
   double sy0;    /* yieldStress0 */
   double K, m;   /* Hollomon constants; eps0 = sy0/E, eps1 = pow(sy0/K,1/m) (Material.cuh:90-104) */
+  /* WF_JOHNSON_COOK: q[0..7] = A B n C eps_0 m T_m T_t (Material_::Init_JohnsonCook, Material.cuh:105-116);
+   * WF_GMT: q[0..13] = n1 n2 C1 C2 m1 m2 I1 I2 e_min e_max er_min er_max T_min T_max (GMT, Material.cuh:237-262).
+   * These are the PUBLIC Material_ fields the free functions CalcJohnsonCook* / CalcGMT* (Material.cuh:377-483) read. */
+  double q[14];
+  double temp;     /* temperature seen by the flow stress: the reference reads T[e] (Mechanical.C:1731), uniform with thermal off */
+  double max_edot; /* m_max_edot (Domain_d.h:824, config "maxStrRate"); <= 0 selects the default 1e6 */
 } wf_material;
 
 /* StabilizationParams (include/common/Domain_d.h:140-153) + the hexa hourglass coefficient of

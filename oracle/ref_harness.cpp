@@ -136,6 +136,32 @@ class Harness : public Domain_d {
     AssignMaterial(mat_h);
   }
 
+  // Johnson-Cook / GMT.  main.C:535-558 builds `JohnsonCook` / `GMT` objects whose constructor arguments
+  // land in PRIVATE members that shadow the public Material_ fields of the same names (Material.cuh:176-197, 237-274),
+  // while the free functions CalcStressStrain calls (Material.cuh:377-483) read the PUBLIC Material_ fields — which
+  // that path leaves uninitialised.  The defined behaviour of those functions is therefore pinned by filling the public
+  // fields: Material_::Init_JohnsonCook (Material.cuh:105-116) for JC, plain assignment for GMT.  The temperature is
+  // the nodal array T indexed by ELEMENT id (Mechanical.C:1731); with thermal coupling off it is uniform.
+  void material_ext(double E, double nu, double rho0, int model, double sy0v, const double *q, double temp) {
+    CoutSilencer s; StdoutSilencer s2;
+    setDensity(rho0);
+    Elastic_ el(E, nu);
+    mat_h = new Material_(el);
+    if (model == JOHNSON_COOK) {
+      mat_h->Init_JohnsonCook(el, q[0], q[1], q[2], q[3], q[4], q[5], q[6], q[7]);  // a, b, n, c, eps_0, m, T_m, T_t
+    } else {
+      mat_h->Material_model = _GMT_;
+      mat_h->n1 = q[0]; mat_h->n2 = q[1]; mat_h->C1 = q[2]; mat_h->C2 = q[3]; mat_h->m1 = q[4]; mat_h->m2 = q[5];
+      mat_h->I1 = q[6]; mat_h->I2 = q[7];
+      mat_h->e_min = q[8]; mat_h->e_max = q[9]; mat_h->er_min = q[10]; mat_h->er_max = q[11];
+      mat_h->T_min = q[12]; mat_h->T_max = q[13];
+    }
+    mat_h->cs0 = sqrt(mat_h->Elastic().BulkMod() / rho0);
+    mat_h->sy0 = sy0v;
+    AssignMaterial(mat_h);
+    for (int n = 0; n < m_node_count; n++) T[n] = temp;
+  }
+
   // src/explicit/Solver_explicit.C:115-292, CPU branch
   void init(double dt_) {
     CoutSilencer s; StdoutSilencer s2;
@@ -475,6 +501,10 @@ void wfref_set_mesh(void *h, int dim, int k, int nn, int ne, const double *x, co
 void wfref_set_material(void *h, double E, double nu, double rho0, int model, double sy0, double K, double m) {
   ((Harness *)h)->material(E, nu, rho0, model, sy0, K, m);
 }
+void wfref_set_material_ext(void *h, double E, double nu, double rho0, int model, double sy0, const double *q, double temp) {
+  ((Harness *)h)->material_ext(E, nu, rho0, model, sy0, q, temp);
+}
+void wfref_set_max_edot(void *h, double v) { ((Harness *)h)->m_max_edot = v; }
 // order = StabilizationParams fields (Domain_d.h:140-153)
 void wfref_set_stab(void *h, const double *s) {
   StabilizationParams &p = ((Harness *)h)->m_stab;

@@ -42,6 +42,8 @@ def _dtype_of(name):
 
 HOLLOMON = 1
 BILINEAR = 0
+JOHNSON_COOK = 2
+GMT = 3
 
 STAB_FIELDS = ("alpha_free alpha_contact hg_coeff_free hg_coeff_contact av_coeff_div av_coeff_bulk "
                "log_factor pspg_scale p_pspg_bulkfac J_min hg_visc hg_stiff").split()
@@ -82,6 +84,8 @@ class _Base:
             "box": (None, [vp, dp, dp, C.c_double, C.c_int]),
             "set_mesh": (None, [vp, C.c_int, C.c_int, C.c_int, C.c_int, dp, ip]),
             "set_material": (None, [vp] + [C.c_double] * 3 + [C.c_int] + [C.c_double] * 3),
+            "set_material_ext": (None, [vp] + [C.c_double] * 3 + [C.c_int, C.c_double, dp, C.c_double]),
+            "set_max_edot": (None, [vp, C.c_double]),
             "set_stab": (None, [vp, dp]),
             "set_options": (None, [vp, C.c_int, C.c_double, C.c_double, C.c_double]),
             "add_bc": (None, [vp, C.c_int, C.c_int, C.c_double]),
@@ -136,6 +140,14 @@ class _Base:
 
     def set_material(self, E, nu, rho0, model=BILINEAR, sy0=1.0e10, K=0.0, m=1.0):
         self._f("set_material")(self.h, E, nu, rho0, model, sy0, K, m)
+
+    def set_material_ext(self, E, nu, rho0, model, sy0, params, temp=20.0, max_edot=None):
+        """Johnson-Cook (params = A B n C eps_0 m T_m T_t) or GMT (n1 n2 C1 C2 m1 m2 I1 I2 e_min e_max er_min er_max
+        T_min T_max) through the public Material_ fields the free functions of Material.cuh:377-483 read."""
+        q = (C.c_double * 14)(*([float(v) for v in params] + [0.0] * (14 - len(params))))
+        self._f("set_material_ext")(self.h, E, nu, rho0, int(model), sy0, q, float(temp))
+        if max_edot is not None:
+            self._f("set_max_edot")(self.h, float(max_edot))
 
     def set_stab(self, **kw):
         vals = [float(kw.get(k, 0.0)) for k in STAB_FIELDS]

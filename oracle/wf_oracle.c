@@ -17,6 +17,8 @@
 
 #define BILINEAR 0
 #define HOLLOMON 1
+#define JOHNSON_COOK 2
+#define GMT 3
 #define DOM_PLANE_STRAIN 0
 #define DOM_AXISYMM 2
 #define DOM_3D 3
@@ -38,6 +40,7 @@ struct wfo_domain {
   /* material (Material.cuh:15-34, 90-104) */
   int model;
   double E, nu, Kbulk, G, rho0, sy0, Kh, mh, eps0, eps1, cs0;
+  double mq[14], temp, max_edot; /* JC: A B n C eps_0 m T_m T_t ; GMT: n1 n2 C1 C2 m1 m2 I1 I2 e_min e_max er_min er_max T_min T_max */
   /* options */
   double stab[12]; /* alpha_free alpha_contact hg_coeff_free hg_coeff_contact av_coeff_div av_coeff_bulk
                       log_factor pspg_scale p_pspg_bulkfac J_min hg_visc hg_stiff */
@@ -66,6 +69,7 @@ wfo_domain *wfo_new(void) {
   d->domtype = DOM_3D;
   d->stab[11] = 0.1; /* hg_stiff default, Domain_d.h:294 */
   d->m_contPF = 0.1;  /* Domain_d.h:256 */
+  d->max_edot = 1.0e6; /* Domain_d.h:824 */
   return d;
 }
 
@@ -236,6 +240,14 @@ void wfo_set_material(wfo_domain *d, double E, double nu, double rho0, int model
   for (int e = 0; e < d->ne; e++) d->rho_0[e] = rho0; /* setDensity, Domain_d.C:951-958 */
 }
 
+/* Johnson-Cook (model 2, q = A B n C eps_0 m T_m T_t) / GMT (model 3, q = n1 n2 C1 C2 m1 m2 I1 I2 + 6 range limits) */
+void wfo_set_material_ext(wfo_domain *d, double E, double nu, double rho0, int model, double sy0, const double *q, double temp) {
+  wfo_set_material(d, E, nu, rho0, BILINEAR, sy0, 0.0, 1.0);
+  d->model = model;
+  memcpy(d->mq, q, sizeof(double) * (model == JOHNSON_COOK ? 8 : 14));
+  d->temp = temp;
+}
+void wfo_set_max_edot(wfo_domain *d, double v) { d->max_edot = v; }
 void wfo_set_stab(wfo_domain *d, const double *s) { memcpy(d->stab, s, sizeof(d->stab)); }
 void wfo_set_options(wfo_domain *d, int press_variant, double av_alpha, double av_beta, double hexa_hg) {
   d->press_variant = press_variant; d->av[0] = av_alpha; d->av[1] = av_beta; d->hexa_hg = hexa_hg;
@@ -722,6 +734,41 @@ static double hollomon_et(const wfo_domain *d, double strain) {
   return 0.;
 }
 
+/* CalcJohnsonCookYieldStress / TangentModulus (Material.cuh:377-387, 397-412) on the public Material_ fields */
+static double jc_sy(const wfo_domain *d, double strain, double strain_rate, double temp) {
+  const double *q = d->mq; /* A B n C eps_0 m T_m T_t */
+  double T_h = (temp - q[7]) / (q[6] - q[7]);
+  double sr = strain_rate;
+  if (strain_rate == 0.0) sr = 1.e-5;
+  return (q[0] + q[1] * pow(strain, q[2])) * (1.0 + q[3] * log(sr / q[4])) * (1.0 - pow(T_h, q[5]));
+}
+static double jc_et(const wfo_domain *d, double plstrain, double strain_rate, double temp) {
+  const double *q = d->mq;
+  double T_h = (temp - q[7]) / (q[6] - q[7]);
+  if (plstrain > 0.) return q[2] * q[1] * pow(plstrain, q[2] - 1.) * (1.0 + q[3] * log(strain_rate / q[4])) * (1.0 - pow(T_h, q[5]));
+  return d->E * 0.1;
+}
+/* CalcGMTYieldStress / TangentModulus (Material.cuh:418-483) */
+static void gmt_clamp(const wfo_domain *d, double *e, double *er, double *T) {
+  const double *q = d->mq;
+  if (*e < q[8]) *e = q[8]; else if (*e > q[9]) *e = q[9];
+  if (*er < q[10]) *er = q[10]; else if (*er > q[11]) *er = q[11];
+  if (*T < q[12]) *T = q[12]; else if (*T > q[13]) *T = q[13];
+}
+static double gmt_sy(const wfo_domain *d, double strain, double strain_rate, double temp) {
+  const double *q = d->mq; /* n1 n2 C1 C2 m1 m2 I1 I2 */
+  double e = strain, er = strain_rate, T = temp;
+  gmt_clamp(d, &e, &er, &T);
+  return q[2] * exp(q[3] * T) * pow(e, q[0] * T + q[1]) * exp((q[6] * T + q[7]) / e) * pow(er, q[4] * T + q[5]);
+}
+static double gmt_et(const wfo_domain *d, double plstrain, double strain_rate, double temp) {
+  const double *q = d->mq;
+  double e = plstrain, er = strain_rate, T = temp;
+  gmt_clamp(d, &e, &er, &T);
+  return q[2] * exp(q[3] * T) * pow(er, q[4] * T + q[5]) *
+         pow(e, T * q[0] + q[1] - 2.0) * (-q[6] * T - q[7] + e * (q[0] * T + q[1])) * exp((q[6] * T + q[7]) / e);
+}
+
 /* CalcStressStrain (Mechanical.C:1664-1839), Hardening plasticity, thermal off */
 static void CalcStressStrain(wfo_domain *d, double dt) {
 #pragma omp parallel for
@@ -737,11 +784,18 @@ static void CalcStressStrain(wfo_domain *d, double dt) {
     t3 s = t3sub(Strial, t3scale(t3ident(), (1.0 / 3.0) * t3trace(Strial)));
     double J2 = 0.5 * (s.xx * s.xx + 2.0 * s.xy * s.xy + 2.0 * s.xz * s.xz + s.yy * s.yy + 2.0 * s.yz * s.yz + s.zz * s.zz);
     double sig_trial = sqrt(3.0 * J2);
+    double eff_strain_rate = sqrt(0.5 * ((D.xx - D.yy) * (D.xx - D.yy) + (D.yy - D.zz) * (D.yy - D.zz) + (D.zz - D.xx) * (D.zz - D.xx)) +
+                                  3.0 * (D.xy * D.xy + D.yz * D.yz + D.zx * D.zx));
     if (d->model == HOLLOMON) d->sigma_y[e] = hollomon_sy(d, d->pl_strain[e]);
+    else if (d->model == JOHNSON_COOK) d->sigma_y[e] = jc_sy(d, d->pl_strain[e], eff_strain_rate, d->temp);
+    else if (d->model == GMT) d->sigma_y[e] = gmt_sy(d, d->pl_strain[e], eff_strain_rate, d->temp);
     double dep = 0.0;
+    eff_strain_rate = eff_strain_rate < d->max_edot ? eff_strain_rate : d->max_edot; /* min(eff_strain_rate, m_max_edot), :1739 */
     if (d->sigma_y[e] < sig_trial) {
       double Et = 0.0; /* BILINEAR: uninitialised in the reference (UB); H = 0 here */
       if (d->model == HOLLOMON) Et = hollomon_et(d, d->pl_strain[e]);
+      else if (d->model == JOHNSON_COOK) Et = jc_et(d, d->pl_strain[e], eff_strain_rate, d->temp);
+      else if (d->model == GMT) Et = gmt_et(d, d->pl_strain[e], eff_strain_rate, d->temp);
       double H = Et, G = d->G;
       double dgamma = (sig_trial - d->sigma_y[e]) / (3.0 * G + H);
       double factor = 1.0 - (3.0 * G * dgamma) / sig_trial;

@@ -28,6 +28,8 @@ void wfo_set_domtype(wfo_domain *, int domtype, int vol_weight);
 void wfo_box(wfo_domain *, const double *V, const double *L, double r, int tritet);
 void wfo_set_mesh(wfo_domain *, int dim, int k, int nn, int ne, const double *x, const int *elnod);
 void wfo_set_material(wfo_domain *, double E, double nu, double rho0, int model, double sy0, double K, double m);
+void wfo_set_material_ext(wfo_domain *, double E, double nu, double rho0, int model, double sy0, const double *q, double temp);
+void wfo_set_max_edot(wfo_domain *, double v);
 void wfo_set_stab(wfo_domain *, const double *s12);
 void wfo_set_options(wfo_domain *, int press_variant, double av_alpha, double av_beta, double hexa_hg_coeff);
 void wfo_add_bc(wfo_domain *, int node, int dim, double val);

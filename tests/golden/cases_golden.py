@@ -23,6 +23,9 @@ GOLDEN = {
     # penalty contact with rigid surfaces: two planes + friction + contact-dependent stabilisation
     "contact_tet_n3": (cases.contact_tets(3, stab=dict(STAB, alpha_contact=0.6, hg_coeff_contact=0.1)), 80),
     "contact_quad_n6": (cases.contact_quads(6), 80),
+    # rate-dependent flow stresses: Johnson-Cook and GMT at a uniform temperature
+    "hex_n3_jc": (cases.with_johnson_cook(R(cases.c3_hexes(3), top_vel=-200.0)), 80),
+    "psquad_n6_gmt": (cases.with_gmt(R(cases.plane_strain_quads(6), top_vel=-50.0)), 80),
 }
 CONTACT_ARRAYS = ("contforce ut_prev node_area m_elem_area m_mesh_in_contact ext_nodes trimesh.node trimesh.node_v "
                   "trimesh.normal trimesh.pplane").split()

@@ -52,7 +52,12 @@ LIVE = [dataclasses.replace(cases.c3_hexes(9), top_vel=-150.0), dataclasses.repl
         cases.contact_tets(6, stab=dict(alpha_free=0.3, alpha_contact=0.6, hg_coeff_free=0.2, hg_coeff_contact=0.1,
                                         av_coeff_div=0.15, av_coeff_bulk=0.15, log_factor=0.8, pspg_scale=0.2,
                                         p_pspg_bulkfac=0.05, J_min=0.1)),
-        cases.contact_quads(12), cases.contact_quads(10, domtype=cases.AXISYMM)]
+        cases.contact_quads(12), cases.contact_quads(10, domtype=cases.AXISYMM),
+        # Johnson-Cook / GMT: hexes and quads only — the reference reads the NODAL temperature array with the ELEMENT id
+        # (Mechanical.C:1731), which runs past its end on tet meshes (more elements than nodes)
+        cases.with_johnson_cook(dataclasses.replace(cases.c3_hexes(6), top_vel=-150.0)),
+        cases.with_gmt(dataclasses.replace(cases.c3_hexes(5), top_vel=-150.0)),
+        cases.with_johnson_cook(dataclasses.replace(cases.c4_axisymm_quads(12), top_vel=-40.0))]
 
 
 @pytest.mark.parametrize("case", LIVE, ids=lambda c: c.name)

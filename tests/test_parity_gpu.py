@@ -47,6 +47,15 @@ SMALL = {
 }
 
 
+SMALL.update({
+    # Johnson-Cook / GMT flow stress (Material.cuh:377-483) at a uniform temperature, SURVEY 8f-3
+    "hex_jc": cases.with_johnson_cook(R(cases.c3_hexes(6), top_vel=-200.0)),
+    "hex_gmt": cases.with_gmt(R(cases.c3_hexes(6), top_vel=-200.0)),
+    "tet_jc": cases.with_johnson_cook(R(cases.c2_tets(5), top_vel=-200.0)),
+    "axiquad_gmt": cases.with_gmt(R(cases.c4_axisymm_quads(12), top_vel=-50.0)),
+})
+
+
 def _names(case):
     n = list(STATE)
     if case.dim == 2 and not case.tritet:

@@ -11,7 +11,8 @@ LIB_PATH = os.path.join(HERE, "libwf_b200.so")
 
 class wf_material(C.Structure):
     _fields_ = [("model", C.c_int), ("E", C.c_double), ("nu", C.c_double), ("rho0", C.c_double),
-                ("sy0", C.c_double), ("K", C.c_double), ("m", C.c_double)]
+                ("sy0", C.c_double), ("K", C.c_double), ("m", C.c_double), ("q", C.c_double * 14),
+                ("temp", C.c_double), ("max_edot", C.c_double)]
 
 
 STAB_FIELDS = ("alpha_free alpha_contact hg_coeff_free hg_coeff_contact av_coeff_div av_coeff_bulk "

@@ -20,7 +20,7 @@ from dataclasses import dataclass, field
 
 import numpy as np
 
-BILINEAR, HOLLOMON = 0, 1
+BILINEAR, HOLLOMON, JOHNSON_COOK, GMT = 0, 1, 2, 3
 PLANE_STRAIN, AXISYMM, DOM_3D = 0, 2, 3
 
 
@@ -40,6 +40,10 @@ class Case:
     sy0: float = 190.4e6
     K: float = 386.796e6
     m: float = 0.154
+    # Johnson-Cook (A B n C eps_0 m T_m T_t) / GMT (n1 n2 C1 C2 m1 m2 I1 I2 e_min e_max er_min er_max T_min T_max)
+    # constants read by the free functions of include/common/Material.cuh:377-483, and the uniform temperature
+    mat_params: tuple = ()
+    temp: float = 20.0
     cfl: float = 0.3
     dt: float | None = None
     press: int = 0
@@ -118,7 +122,10 @@ class Case:
         L = [self.n[0] * self.h * pad, self.n[1] * self.h * pad,
              (self.n[2] * self.h * pad) if self.dim == 3 else 0.0]
         dom.box((0.0, 0.0, 0.0), L, 0.5 * self.h, self.tritet)
-        dom.set_material(self.E, self.nu, self.rho0, self.model, self.sy0, self.K, self.m)
+        if self.model in (JOHNSON_COOK, GMT):
+            dom.set_material_ext(self.E, self.nu, self.rho0, self.model, self.sy0, self.mat_params, self.temp)
+        else:
+            dom.set_material(self.E, self.nu, self.rho0, self.model, self.sy0, self.K, self.m)
         dom.set_stab(**self.stab)
         dom.set_options(self.press, self.av[0], self.av[1], self.hexa_hg)
         if hasattr(dom, "add_bcs"):
@@ -190,6 +197,22 @@ def contact_quads(n: int = 12, tool_vel: float = -100.0, mu=(0.3, 0.2), domtype:
     return Case(f"contact_quad_n{n}", 2, (n, n), h, domtype=domtype, cfl=0.3, stab=dict(hg_visc=0.1, hg_stiff=0.1),
                 top_vel=0.0, bc_style="bottom", planes=planes,
                 contact=dict(mu_sta=mu[0], mu_dyn=mu[1], penalty_factor=0.6, end_steps=100))
+
+
+JC_AL6061 = (324.0e6, 114.0e6, 0.42, 0.002, 1.0, 1.34, 925.0, 294.0)     # A B n C eps_0 m T_m T_t (Johnson & Cook 1983, Al 6061-T6)
+GMT_DEMO = (0.0, 0.15, 400.0e6, -0.002, 0.0, 0.02, 0.0, -0.002, 0.01, 3.0, 1.0e-3, 1.0e5, 20.0, 500.0)
+
+
+def with_johnson_cook(case: Case, temp: float = 400.0) -> Case:
+    """Same workload with the Johnson-Cook flow stress (Material.cuh:377-412) at a uniform temperature."""
+    import dataclasses
+    return dataclasses.replace(case, name=case.name + "_jc", model=JOHNSON_COOK, sy0=JC_AL6061[0], mat_params=JC_AL6061, temp=temp)
+
+
+def with_gmt(case: Case, temp: float = 100.0) -> Case:
+    """Same workload with the GMT flow stress (Material.cuh:418-483)."""
+    import dataclasses
+    return dataclasses.replace(case, name=case.name + "_gmt", model=GMT, sy0=100.0e6, mat_params=GMT_DEMO, temp=temp)
 
 
 def plane_strain_quads(n: int = 16) -> Case:

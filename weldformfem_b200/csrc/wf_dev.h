@@ -101,6 +101,7 @@ struct WfPar {
   /* material (Material.cuh) */
   int model;
   double Kbulk, G, sy0, Kh, mh, eps0, eps1, cs0;
+  double young, mq[14], temp, max_edot; /* Johnson-Cook / GMT constants (wf_material::q), uniform temperature */
   /* StabilizationParams + hexa hourglass coefficient */
   double alpha_contact, hg_coeff_contact; /* used instead of the _free values by elements touching a contact node */
   double alpha_free, hg_coeff_free, av_coeff_div, av_coeff_bulk, log_factor, pspg_scale, p_pspg_bulkfac, J_min;

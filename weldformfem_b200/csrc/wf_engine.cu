@@ -266,7 +266,7 @@ extern "C" int wf_get_counts(wf_engine *E, int *nn, int *ne, int *ntot) {
 // ---------------------------------------------------------------------------------------------------
 extern "C" int wf_set_material(wf_engine *E, const wf_material *m) {
   NEED(m, "null material");
-  NEED(m->model == WF_BILINEAR || m->model == WF_HOLLOMON, "material model must be Bilinear or Hollomon");
+  NEED(m->model >= WF_BILINEAR && m->model <= WF_GMT, "material model must be Bilinear, Hollomon, JohnsonCook or GMT");
   E->mat = *m;
   WfPar &P = E->P;
   P.model = m->model;
@@ -279,6 +279,10 @@ extern "C" int wf_set_material(wf_engine *E, const wf_material *m) {
     P.eps1 = pow(m->sy0 / m->K, 1. / m->m);
   }
   P.cs0 = sqrt(P.Kbulk / m->rho0); // main.C:574
+  P.young = m->E;
+  for (int i = 0; i < 14; i++) P.mq[i] = m->q[i];
+  P.temp = m->temp;
+  P.max_edot = m->max_edot > 0.0 ? m->max_edot : 1.0e6; // Domain_d.h:824
   E->material_set = true;
   if (E->meshed) {
     CK(cudaSetDevice(E->device));

@@ -1170,7 +1170,8 @@ static void l_node_vol(const WfDev &d, const WfPar &P, int mode, cudaStream_t s)
   }
 }
 static void l_elem_main(const WfDev &d, const WfPar &P, int et, int separate_hg, cudaStream_t s) {
-  if (!separate_hg && et == ET_HEX8 && !P.strict && P.variant[2] != 1) {
+  // the regrouped hexa kernel inlines Bilinear / Hollomon; the rate-dependent laws (Johnson-Cook, GMT) take the generic kernel
+  if (!separate_hg && et == ET_HEX8 && !P.strict && P.variant[2] != 1 && P.model < 2) {
     if (P.variant[2] >= 100) { // memory skeletons (tuning aid, garbage results)
       const int g = cdiv(d.ne, hexfast::TPB);
       switch (P.variant[2] - 100) {

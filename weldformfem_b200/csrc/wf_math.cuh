@@ -196,6 +196,37 @@ WF_DI double hollomon_et(const WfPar &P, double strain) {
   return 0.;
 }
 
+// CalcJohnsonCookYieldStress / TangentModulus (Material.cuh:377-387, 397-412); mq = A B n C eps_0 m T_m T_t
+WF_DI double jc_sy(const WfPar &P, double strain, double strain_rate) {
+  const double T_h = (P.temp - P.mq[7]) / (P.mq[6] - P.mq[7]);
+  double sr = strain_rate;
+  if (strain_rate == 0.0) sr = 1.e-5;
+  return (P.mq[0] + P.mq[1] * pow(strain, P.mq[2])) * (1.0 + P.mq[3] * log(sr / P.mq[4])) * (1.0 - pow(T_h, P.mq[5]));
+}
+WF_DI double jc_et(const WfPar &P, double plstrain, double strain_rate) {
+  const double T_h = (P.temp - P.mq[7]) / (P.mq[6] - P.mq[7]);
+  if (plstrain > 0.)
+    return P.mq[2] * P.mq[1] * pow(plstrain, P.mq[2] - 1.) * (1.0 + P.mq[3] * log(strain_rate / P.mq[4])) * (1.0 - pow(T_h, P.mq[5]));
+  return P.young * 0.1;
+}
+// CalcGMTYieldStress / TangentModulus (Material.cuh:418-483); mq = n1 n2 C1 C2 m1 m2 I1 I2 + ranges of e, er, T
+WF_DI void gmt_clamp(const WfPar &P, double &e, double &er, double &T) {
+  if (e < P.mq[8]) e = P.mq[8]; else if (e > P.mq[9]) e = P.mq[9];
+  if (er < P.mq[10]) er = P.mq[10]; else if (er > P.mq[11]) er = P.mq[11];
+  if (T < P.mq[12]) T = P.mq[12]; else if (T > P.mq[13]) T = P.mq[13];
+}
+WF_DI double gmt_sy(const WfPar &P, double strain, double strain_rate) {
+  double e = strain, er = strain_rate, T = P.temp;
+  gmt_clamp(P, e, er, T);
+  return P.mq[2] * exp(P.mq[3] * T) * pow(e, P.mq[0] * T + P.mq[1]) * exp((P.mq[6] * T + P.mq[7]) / e) * pow(er, P.mq[4] * T + P.mq[5]);
+}
+WF_DI double gmt_et(const WfPar &P, double plstrain, double strain_rate) {
+  double e = plstrain, er = strain_rate, T = P.temp;
+  gmt_clamp(P, e, er, T);
+  return P.mq[2] * exp(P.mq[3] * T) * pow(er, P.mq[4] * T + P.mq[5]) *
+         pow(e, T * P.mq[0] + P.mq[1] - 2.0) * (-P.mq[6] * T - P.mq[7] + e * (P.mq[0] * T + P.mq[1])) * exp((P.mq[6] * T + P.mq[7]) / e);
+}
+
 // CalcStressStrain (Mechanical.C:1664-1839): Jaumann rate + J2 radial return.
 // tau, eps: flat symmetric; Dr flat symmetric; Wr = (Wxy, Wyz, Wxz).
 // The SRT / RS terms follow the nine expressions of tensor3 operator* (Tensor3.C:290-304)
@@ -245,11 +276,21 @@ WF_DI void stress_update(const WfPar &P, double dt, double p, const double (&Dr)
   const double sig_trial = sqrt(3.0 * J2);
 
   double sy = sy_prev;
+  double esr = 0.0; // effective strain rate (Mechanical.C:1701-1705), only the rate-dependent laws use it
+  if (P.model >= 2) {
+    esr = sqrt(0.5 * ((Dr[0] - Dr[1]) * (Dr[0] - Dr[1]) + (Dr[1] - Dr[2]) * (Dr[1] - Dr[2]) + (Dr[2] - Dr[0]) * (Dr[2] - Dr[0])) +
+               3.0 * (Dr[3] * Dr[3] + Dr[4] * Dr[4] + Dr[5] * Dr[5]));
+  }
   if (P.model == 1) sy = hollomon_sy(P, pl);
+  else if (P.model == 2) sy = jc_sy(P, pl, esr);
+  else if (P.model == 3) sy = gmt_sy(P, pl, esr);
   double dep = 0.0;
+  if (P.model >= 2) esr = esr < P.max_edot ? esr : P.max_edot; // min(eff_strain_rate, m_max_edot), :1739
   if (sy < sig_trial) {
     double Et = 0.0; // BILINEAR: uninitialised in the reference (UB); treated as perfectly plastic
     if (P.model == 1) Et = hollomon_et(P, pl);
+    else if (P.model == 2) Et = jc_et(P, pl, esr);
+    else if (P.model == 3) Et = gmt_et(P, pl, esr);
     const double H = Et, G = P.G;
     const double dgamma = (sig_trial - sy) / (3.0 * G + H);
     const double factor = 1.0 - (3.0 * G * dgamma) / sig_trial;

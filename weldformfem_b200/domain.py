@@ -15,7 +15,7 @@ from . import _lib
 from ._lib import STAB_FIELDS, wf_material, wf_stab
 
 PLANE_STRAIN, AXISYMM, DOM_3D = 0, 2, 3
-BILINEAR, HOLLOMON = 0, 1
+BILINEAR, HOLLOMON, JOHNSON_COOK, GMT = 0, 1, 2, 3
 STRICT, FAST = 1, 0
 
 _INT_ARRAYS = {"m_nodel": np.int32, "m_nodel_loc": np.int32, "m_nodel_offset": np.int32, "m_nodel_count": np.int32,
@@ -132,6 +132,17 @@ class Domain_d:
 
     def set_material(self, E, nu, rho0, model=BILINEAR, sy0=1.0e10, K=0.0, m=1.0):   # main.C:460-581
         mat = wf_material(int(model), float(E), float(nu), float(rho0), float(sy0), float(K), float(m))
+        self._ck(self._lib.wf_set_material(self._h, C.byref(mat)))
+
+    def set_material_ext(self, E, nu, rho0, model, sy0, params, temp=20.0, max_edot=None):
+        """Johnson-Cook (params = A B n C eps_0 m T_m T_t) / GMT (n1 n2 C1 C2 m1 m2 I1 I2 e_min e_max er_min er_max T_min
+        T_max): the public Material_ fields read by CalcJohnsonCook* / CalcGMT* (Material.cuh:377-483); ``temp`` is the
+        uniform temperature the flow stress sees with thermal coupling off; ``max_edot`` = m_max_edot (Domain_d.h:824)."""
+        mat = wf_material(int(model), float(E), float(nu), float(rho0), float(sy0), 0.0, 1.0)
+        for i, v in enumerate(params):
+            mat.q[i] = float(v)
+        mat.temp = float(temp)
+        mat.max_edot = float(max_edot) if max_edot is not None else 0.0
         self._ck(self._lib.wf_set_material(self._h, C.byref(mat)))
 
     def set_stab(self, **kw):                                  # m_stab, main.C:84-120
