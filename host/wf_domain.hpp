@@ -65,6 +65,7 @@ class Material_ {
   double A = 0, B = 0, C = 0, n = 0, eps_0 = 1.0, T_m = 1.0e10, T_t = 0.0;                   // Johnson-Cook (Material.cuh:67-72)
   double C1 = 0, C2 = 0, m1 = 0, m2 = 0, n1 = 0, n2 = 0, I1 = 0, I2 = 0;                    // GMT (Material.cuh:76)
   double e_min = 0, e_max = 1.0e10, er_min = 0, er_max = 1.0e10, T_min = 0, T_max = 1.0e10;  // Material.cuh:63-65
+  double k_T = 0.0, cp_T = 0.0, exp_T = 0.0;                                                 // thermal (Material.cuh:79-81)
 
  private:
   Elastic_ elastic_;
@@ -163,6 +164,8 @@ class Domain_d {
   }
   void setDensity(double rho) { rho0_ = rho; }  // Domain_d.C:951
   void setTemp(double T) { temp_ = T; }         // Domain_d::setTemp (uniform initial temperature, main.C:441)
+  void setThermalOn() { m_thermal = true; }     // Domain_d.h:676
+  double m_plheatfraction = 0.9;                // Domain_d.h:271 (config "plHeatFrac")
   double m_max_edot = 1.0e6;                    // Domain_d.h:824
   void AssignMaterial(const Material_ *mat) {    // Domain_d.C:903
     mat_ = *mat;
@@ -203,6 +206,7 @@ class Domain_d {
       ck(wf_set_trimesh(eng_, trimesh->dimension, trimesh->nodecount, trimesh->elemcount, trimesh->node.data(),
                         trimesh->node_v.data(), trimesh->elnode.data(), trimesh->normal.data(), trimesh->ele_mesh_id.data()));
       ck(wf_set_contact(eng_, trimesh->mu_sta[0], trimesh->mu_dyn[0], m_contPF, end_t_));
+      if (m_thermal) ck(wf_set_contact_heat(eng_, trimesh->heat_cond, trimesh->T_const));
       double ml = 0, mh = 0;
       ck(wf_calcMinEdgeLength(eng_, &ml, &mh));
     }
@@ -310,10 +314,11 @@ class Domain_d {
               m_stab.p_pspg_bulkfac, m_stab.J_min, m_stab.hg_visc, m_stab.hg_stiff, hexa_hg_};
     ck(wf_set_stab(eng_, &s));
     ck(wf_set_options(eng_, m_press_algorithm, m_artifvisc[0], m_artifvisc[1], strict_ ? WF_STRICT : WF_FAST));
+    if (m_thermal) ck(wf_set_thermal(eng_, mat_.k_T, mat_.cp_T, mat_.exp_T, m_plheatfraction, temp_));
   }
 
   TriMesh_d *trimesh = nullptr;
-  bool contact = false;
+  bool contact = false, m_thermal = false;
   double m_contPF = 0.1;  // Domain_d.h:256
   wf_engine *eng_ = nullptr;
   int device_ = 0, dim_ = 0, nodxelem_ = 0, n_nodes_ = 0, n_elems_ = 0;

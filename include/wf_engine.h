@@ -93,6 +93,11 @@ int wf_set_options(wf_engine *, int press_algorithm, double av_alpha, double av_
 /* optional per-step products the reference always keeps: bit0 = integrate m_eps (Mechanical.C:1822),
  * bit1 = store m_sigma every step instead of rebuilding it on wf_get_array (identical values) */
 int wf_set_tracking(wf_engine *, int flags);
+/* thermal coupling (config "thermal"): setThermalOn + setTemp(T0) (main.C:436-441), Material_::k_T / cp_T / exp_T
+ * (thermalCond / thermalHeatCap / thermalExp, main.C:567-570) and m_plheatfraction (plHeatFrac, main.C:218).  Per step:
+ * calcThermalExpansion (Thermal.C:151-166), the plastic work rate m_q_plheat (Mechanical.C:1784-1818) and ThermalCalcs
+ * (Thermal.C:28-127), fused into the element and node passes.  Arrays: "T", "m_q_plheat", "m_dTedt", "q_cont_conv". */
+int wf_set_thermal(wf_engine *, double k_T, double cp_T, double exp_T, double plheatfrac, double T0);
 int wf_add_bc_vel(wf_engine *, int node, int dim, double val); /* AddBCVelNode, Domain_d.C:1057 */
 int wf_add_bc_vel_array(wf_engine *, int count, const int *node, const int *dim, const double *val);
 int wf_allocate_bcs(wf_engine *);                              /* AllocateBCs, Domain_d.C:1063 */
@@ -114,6 +119,9 @@ int wf_set_trimesh(wf_engine *, int dimension, int n_nodes, int n_elems, const d
  * setContactOn (main.C:716-725, :842-847) and SetEndTime (the surface velocity ramps over the first 1 % of end_time);
  * needs wf_calcMinEdgeLength (m_elem_length, main.C:862) before wf_init */
 int wf_set_contact(wf_engine *, double mu_sta, double mu_dyn, double penalty_factor, double end_time);
+/* TriMesh_d::heat_cond / T_const (heatCondCoeff, dieTemp; main.C:718-719): heat flow q_cont_conv = heat_cond * node_area *
+ * (T_const - T) into every node in contact (Contact.C:309); needs wf_set_thermal */
+int wf_set_contact_heat(wf_engine *, double heat_cond, double T_const);
 int wf_CalcContactForces(wf_engine *); /* Contact.C:31-336, unfused entry point */
 int wf_MoveTriMesh(wf_engine *);       /* Solver_explicit.C:981-1005, unfused entry point */
 int wf_get_trimesh_counts(wf_engine *, int *dimension, int *n_nodes, int *n_elems);

@@ -88,6 +88,7 @@ class Harness : public Domain_d {
     z(vol, ne); z(vol_0, ne); z(m_detJ, ne);
     z(m_f_elem, nk); z(m_f_elem_hg, nk);
     z(m_mdiag, m_node_count); z(m_voln, m_node_count); z(p_node, m_node_count);
+    z(m_dTedt, ne * m_nodxelem); z(m_q_plheat, ne);
     z(T, m_node_count); z(node_area, m_node_count); z(q_cont_conv, m_node_count); z(m_elem_area, ne);
     z(m_elem_length, ne);
     if (ext_nodes) memset(ext_nodes, 0, sizeof(bool) * m_node_count);
@@ -160,6 +161,16 @@ class Harness : public Domain_d {
     mat_h->sy0 = sy0v;
     AssignMaterial(mat_h);
     for (int n = 0; n < m_node_count; n++) T[n] = temp;
+  }
+
+  // thermal coupling: main.C:218, 436-441, 567-570 (plHeatFrac, setThermalOn + setTemp, k_T / cp_T / exp_T)
+  void thermal_on(double k_T, double cp_T, double exp_T, double plheatfrac, double T0) {
+    setThermalOn();
+    setTemp(T0);
+    // main.C:567-570 fills these BEFORE AssignMaterial copies the object (Domain_d.C:903-907); here the copy exists already
+    mat_h->k_T = k_T; mat_h->cp_T = cp_T; mat_h->exp_T = exp_T;
+    materials[0].k_T = k_T; materials[0].cp_T = cp_T; materials[0].exp_T = exp_T;
+    m_plheatfraction = plheatfrac;
   }
 
   // src/explicit/Solver_explicit.C:115-292, CPU branch
@@ -249,7 +260,6 @@ class Harness : public Domain_d {
   void contact_on(double mu_sta, double mu_dyn, double pf, double end_time) {
     CoutSilencer s; StdoutSilencer s2;
     trimesh->mu_sta[0] = mu_sta; trimesh->mu_dyn[0] = mu_dyn;
-    trimesh->heat_cond = 0.0;
     if (pf > -1.0) setContactPF(pf);
     trimesh->CalcSpheres();
     setContactOn();
@@ -335,6 +345,7 @@ class Harness : public Domain_d {
     CalcNodalVol();
     CalcNodalMassFromVol();
     calcElemStrainRates();
+    if (m_thermal) calcThermalExpansion();  // Solver_explicit.C:719-720
     pressure();
     calcNodalPressureFromElemental();
     CalcStressStrain(dt);
@@ -352,6 +363,7 @@ class Harness : public Domain_d {
     axis_constraint();
     UpdateCorrectionPos();
     if (contact) move_trimesh();
+    if (m_thermal) ThermalCalcs();  // Solver_explicit.C:1008-1012
     time_ += dt;
     step_count_++;
   }
@@ -389,6 +401,8 @@ class Harness : public Domain_d {
     else if (f == "UpdateCorrectionAccVel") UpdateCorrectionAccVel();
     else if (f == "AxisConstraint") axis_constraint();
     else if (f == "UpdateCorrectionPos") UpdateCorrectionPos();
+    else if (f == "calcThermalExpansion") calcThermalExpansion();
+    else if (f == "ThermalCalcs") ThermalCalcs();
     else if (f == "SearchExtNodes") SearchExtNodes();
     else if (f == "CalcExtFaceAreas") CalcExtFaceAreas();
     else if (f == "CalcContactForces") CalcContactForces();
@@ -438,6 +452,10 @@ class Harness : public Domain_d {
     if (nm == "m_f_elem_hg") return {m_f_elem_hg, nk * m_dim};
     if (nm == "m_hg_q") return {m_dim == 2 ? m_hg_q : nullptr, m_dim == 2 ? nk * m_dim : 0};
     if (nm == "m_elem_length") return {m_elem_length, ne};
+    if (nm == "T") return {T, nn};
+    if (nm == "m_dTedt") return {m_dTedt, nk};
+    if (nm == "m_q_plheat") return {m_q_plheat, ne};
+    if (nm == "q_cont_conv") return {q_cont_conv, nn};
     if (nm == "contforce") return {contforce, nd};
     if (nm == "ut_prev") return {ut_prev, nd};
     if (nm == "node_area") return {node_area, nn};
@@ -503,6 +521,13 @@ void wfref_set_material(void *h, double E, double nu, double rho0, int model, do
 }
 void wfref_set_material_ext(void *h, double E, double nu, double rho0, int model, double sy0, const double *q, double temp) {
   ((Harness *)h)->material_ext(E, nu, rho0, model, sy0, q, temp);
+}
+void wfref_thermal_on(void *h, double k_T, double cp_T, double exp_T, double plheatfrac, double T0) {
+  ((Harness *)h)->thermal_on(k_T, cp_T, exp_T, plheatfrac, T0);
+}
+void wfref_set_contact_heat(void *h, double heat_cond, double T_const) {
+  TriMesh_d *m = ((Harness *)h)->getTriMesh();
+  if (m) { m->heat_cond = heat_cond; m->T_const = T_const; }
 }
 void wfref_set_max_edot(void *h, double v) { ((Harness *)h)->m_max_edot = v; }
 // order = StabilizationParams fields (Domain_d.h:140-153)

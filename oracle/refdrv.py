@@ -24,7 +24,7 @@ PORT_SO = os.path.join(HERE, "_build", "libwf_oracle.so")
 _DBL = ("x v a u u_dt prev_a m_fi m_fe m_mdiag m_voln p_node m_dH_detJ_dx m_dH_detJ_dy m_dH_detJ_dz "
         "m_detJ vol vol_0 rho rho_0 p pl_strain sigma_y m_radius m_str_rate m_rot_rate m_sigma m_tau "
         "m_eps m_f_elem m_f_elem_hg m_hg_q m_voln_0 m_Jn bcx_val bcy_val bcz_val m_elem_length "
-        "contforce ut_prev node_area m_elem_area trimesh.node trimesh.node_v trimesh.normal trimesh.pplane").split()
+        "T m_dTedt m_q_plheat q_cont_conv contforce ut_prev node_area m_elem_area trimesh.node trimesh.node_v trimesh.normal trimesh.pplane").split()
 _INT = ("m_nodel m_nodel_loc m_nodel_offset m_nodel_count m_mesh_in_contact trimesh.elnode "
         "trimesh.ele_mesh_id").split()
 _UINT = ["m_elnod"]
@@ -86,6 +86,8 @@ class _Base:
             "set_material": (None, [vp] + [C.c_double] * 3 + [C.c_int] + [C.c_double] * 3),
             "set_material_ext": (None, [vp] + [C.c_double] * 3 + [C.c_int, C.c_double, dp, C.c_double]),
             "set_max_edot": (None, [vp, C.c_double]),
+            "thermal_on": (None, [vp] + [C.c_double] * 5),
+            "set_contact_heat": (None, [vp, C.c_double, C.c_double]),
             "set_stab": (None, [vp, dp]),
             "set_options": (None, [vp, C.c_int, C.c_double, C.c_double, C.c_double]),
             "add_bc": (None, [vp, C.c_int, C.c_int, C.c_double]),
@@ -148,6 +150,14 @@ class _Base:
         self._f("set_material_ext")(self.h, E, nu, rho0, int(model), sy0, q, float(temp))
         if max_edot is not None:
             self._f("set_max_edot")(self.h, float(max_edot))
+
+    def thermal_on(self, k_T, cp_T, exp_T=0.0, plheatfrac=0.9, T0=20.0):
+        """setThermalOn + setTemp(T0) + thermalCond / thermalHeatCap / thermalExp + plHeatFrac (main.C:218, 436-441, 567-570)."""
+        self._f("thermal_on")(self.h, float(k_T), float(cp_T), float(exp_T), float(plheatfrac), float(T0))
+
+    def set_contact_heat(self, heat_cond, T_const):
+        """heatCondCoeff / dieTemp of the rigid surfaces (main.C:718-719); call after contact_on."""
+        self._f("set_contact_heat")(self.h, float(heat_cond), float(T_const))
 
     def set_stab(self, **kw):
         vals = [float(kw.get(k, 0.0)) for k in STAB_FIELDS]

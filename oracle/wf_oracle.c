@@ -40,6 +40,8 @@ struct wfo_domain {
   /* material (Material.cuh:15-34, 90-104) */
   int model;
   double E, nu, Kbulk, G, rho0, sy0, Kh, mh, eps0, eps1, cs0;
+  int thermal; /* m_thermal */
+  double k_T, cp_T, exp_T, plheatfraction, *T, *m_dTedt, *m_q_plheat, *q_cont_conv, tm_heat_cond, tm_T_const;
   double mq[14], temp, max_edot; /* JC: A B n C eps_0 m T_m T_t ; GMT: n1 n2 C1 C2 m1 m2 I1 I2 e_min e_max er_min er_max T_min T_max */
   /* options */
   double stab[12]; /* alpha_free alpha_contact hg_coeff_free hg_coeff_contact av_coeff_div av_coeff_bulk
@@ -70,6 +72,7 @@ wfo_domain *wfo_new(void) {
   d->stab[11] = 0.1; /* hg_stiff default, Domain_d.h:294 */
   d->m_contPF = 0.1;  /* Domain_d.h:256 */
   d->max_edot = 1.0e6; /* Domain_d.h:824 */
+  d->plheatfraction = 0.9; /* Domain_d.h:271 */
   return d;
 }
 
@@ -82,6 +85,8 @@ static void free_mesh(wfo_domain *d) {
                    &d->m_f_elem_hg, &d->m_hg_q};
   for (size_t i = 0; i < sizeof(dp) / sizeof(dp[0]); i++) { free(*dp[i]); *dp[i] = NULL; }
   free(d->m_elnod); d->m_elnod = NULL;
+  free(d->T); free(d->m_dTedt); free(d->m_q_plheat); free(d->q_cont_conv);
+  d->T = d->m_dTedt = d->m_q_plheat = d->q_cont_conv = NULL;
   free(d->contforce); free(d->ut_prev); free(d->node_area); free(d->m_elem_area); free(d->ext_nodes);
   free(d->m_mesh_in_contact); free(d->face_nodes); free(d->face_count); free(d->face_elem);
   d->contforce = d->ut_prev = d->node_area = d->m_elem_area = NULL; d->ext_nodes = NULL;
@@ -128,6 +133,8 @@ static void set_dimension(wfo_domain *d, int nn, int ne) {
   d->m_elnod = zalloc(nk, sizeof(unsigned));
   d->contforce = zalloc(nd + 3, 8); d->ut_prev = zalloc(nd + 3, 8); /* +3: the reference writes ut_prev[dim*i+2] in 2D */
   d->node_area = zalloc(nn, 8); d->m_elem_area = zalloc(ne, 8);
+  d->T = zalloc(nn > ne ? nn : ne, 8); d->m_dTedt = zalloc(nk > (size_t)nn ? nk : (size_t)nn, 8); d->m_q_plheat = zalloc(ne, 8);
+  d->q_cont_conv = zalloc(nn, 8);
   d->ext_nodes = zalloc(nn, 1);
   d->m_mesh_in_contact = zalloc(nn, sizeof(int));
   for (int n = 0; n < nn; n++) d->m_mesh_in_contact[n] = -1;
@@ -787,15 +794,18 @@ static void CalcStressStrain(wfo_domain *d, double dt) {
     double eff_strain_rate = sqrt(0.5 * ((D.xx - D.yy) * (D.xx - D.yy) + (D.yy - D.zz) * (D.yy - D.zz) + (D.zz - D.xx) * (D.zz - D.xx)) +
                                   3.0 * (D.xy * D.xy + D.yz * D.yz + D.zx * D.zx));
     if (d->model == HOLLOMON) d->sigma_y[e] = hollomon_sy(d, d->pl_strain[e]);
-    else if (d->model == JOHNSON_COOK) d->sigma_y[e] = jc_sy(d, d->pl_strain[e], eff_strain_rate, d->temp);
-    else if (d->model == GMT) d->sigma_y[e] = gmt_sy(d, d->pl_strain[e], eff_strain_rate, d->temp);
+    /* the reference passes T[e]: the NODAL temperature array indexed by the element id (Mechanical.C:1731); defined
+     * while e < node count, the uniform set_material_ext temperature stands in beyond that */
+    const double temp_e = (d->thermal && e < d->nn) ? d->T[e] : d->temp;
+    if (d->model == JOHNSON_COOK) d->sigma_y[e] = jc_sy(d, d->pl_strain[e], eff_strain_rate, temp_e);
+    else if (d->model == GMT) d->sigma_y[e] = gmt_sy(d, d->pl_strain[e], eff_strain_rate, temp_e);
     double dep = 0.0;
     eff_strain_rate = eff_strain_rate < d->max_edot ? eff_strain_rate : d->max_edot; /* min(eff_strain_rate, m_max_edot), :1739 */
     if (d->sigma_y[e] < sig_trial) {
       double Et = 0.0; /* BILINEAR: uninitialised in the reference (UB); H = 0 here */
       if (d->model == HOLLOMON) Et = hollomon_et(d, d->pl_strain[e]);
-      else if (d->model == JOHNSON_COOK) Et = jc_et(d, d->pl_strain[e], eff_strain_rate, d->temp);
-      else if (d->model == GMT) Et = gmt_et(d, d->pl_strain[e], eff_strain_rate, d->temp);
+      else if (d->model == JOHNSON_COOK) Et = jc_et(d, d->pl_strain[e], eff_strain_rate, temp_e);
+      else if (d->model == GMT) Et = gmt_et(d, d->pl_strain[e], eff_strain_rate, temp_e);
       double H = Et, G = d->G;
       double dgamma = (sig_trial - d->sigma_y[e]) / (3.0 * G + H);
       double factor = 1.0 - (3.0 * G * dgamma) / sig_trial;
@@ -804,6 +814,7 @@ static void CalcStressStrain(wfo_domain *d, double dt) {
       dep = dgamma;
     }
     t3 Sigma = t3add(t3scale(t3ident(), -d->p[e]), Tau);
+    if (d->thermal) d->m_q_plheat[e] = 0.0;
     if (dep > 0.0) {
       double f = dep / d->sigma_y[e];
       Epl.xx = f * (Sigma.xx - 0.5 * (Sigma.yy + Sigma.zz));
@@ -812,6 +823,11 @@ static void CalcStressStrain(wfo_domain *d, double dt) {
       Epl.xy = Epl.yx = 1.5 * f * (Sigma.xy);
       Epl.xz = Epl.zx = 1.5 * f * (Sigma.xz);
       Epl.yz = Epl.zy = 1.5 * f * (Sigma.yz);
+      if (d->thermal) { /* plastic work rate, Mechanical.C:1798-1818 */
+        t3 depdt = t3scale(Epl, 1. / dt);
+        d->m_q_plheat[e] = d->plheatfraction * (Sigma.xx * depdt.xx + 2.0 * Sigma.xy * depdt.yx + 2.0 * Sigma.xz * depdt.zx +
+                                                Sigma.yy * depdt.yy + 2.0 * Sigma.yz * depdt.yz + Sigma.zz * depdt.zz);
+      }
     }
     Eps = t3add(Eps, t3scale(D, dt));
     t3flat(Sigma, d->m_sigma + ot);
@@ -820,6 +836,63 @@ static void CalcStressStrain(wfo_domain *d, double dt) {
     t3flat(Epl, d->m_strain_pl_incr + ot); /* reference stores an uninitialised tensor when dep == 0 */
   }
 }
+
+/* calcThermalExpansion (Thermal.C:151-166): the element-node array m_dTedt is read with NODE ids, as the reference does */
+static void calcThermalExpansion(wfo_domain *d) {
+#pragma omp parallel for
+  for (int e = 0; e < d->ne; e++) {
+    double dTdt_gp = 0.0;
+    for (int i = 0; i < d->k; ++i) {
+      int node = d->m_elnod[(size_t)e * d->k + i];
+      dTdt_gp += 1.0 / d->k * d->m_dTedt[node];
+    }
+    double *sr = d->m_str_rate + 6 * (size_t)e;
+    double f = d->exp_T * dTdt_gp;
+    sr[0] = sr[0] - f * 1.; sr[1] = sr[1] - f * 1.; sr[2] = sr[2] - f * 1.;
+    sr[3] = sr[3] - f * 0.; sr[4] = sr[4] - f * 0.; sr[5] = sr[5] - f * 0.;
+  }
+}
+/* ThermalCalcs (Thermal.C:28-127) */
+static void ThermalCalcs(wfo_domain *d) {
+  const int k = d->k, dim = d->dim;
+  const double w = gauss_w(d);
+#pragma omp parallel for
+  for (int e = 0; e < d->ne; e++) {
+    double Kt[8][8], Te[8], dTde[8];
+    for (int i = 0; i < k; ++i)
+      for (int j = 0; j < k; ++j) {
+        double kk = 0.0;
+        for (int c = 0; c < dim; ++c) kk += DH(c, e, i) * DH(c, e, j);
+        Kt[i][j] = kk * d->k_T / d->m_detJ[e] * w;
+      }
+    for (int i = 0; i < k; ++i) Te[i] = d->T[d->m_elnod[(size_t)e * k + i]];
+    double heat = 0.9 * d->m_q_plheat[e];
+    double elem_pow = heat * d->vol[e];
+    double pow_per_node = elem_pow / k;
+    for (int i = 0; i < k; ++i) { dTde[i] = 0.0; for (int j = 0; j < k; ++j) dTde[i] += Kt[i][j] * Te[j]; }
+    for (int i = 0; i < k; ++i) {
+      int node_id = d->m_elnod[(size_t)e * k + i];
+      double m_inv = 1.0 / d->m_mdiag[node_id];
+      d->m_dTedt[(size_t)e * k + i] = -m_inv * dTde[i];
+      d->m_dTedt[(size_t)e * k + i] += pow_per_node / (d->m_mdiag[node_id] * d->cp_T);
+    }
+  }
+#pragma omp parallel for
+  for (int n = 0; n < d->nn; n++) {
+    double dTdt = 0;
+    for (int e = 0; e < d->m_nodel_count[n]; e++) {
+      int eglob = d->m_nodel[d->m_nodel_offset[n] + e], ne = d->m_nodel_loc[d->m_nodel_offset[n] + e];
+      dTdt += d->m_dTedt[(size_t)eglob * k + ne];
+    }
+    d->T[n] += (dTdt + d->q_cont_conv[n] * 1.0 / (d->m_mdiag[n] * d->cp_T)) * d->dt;
+  }
+}
+void wfo_thermal_on(wfo_domain *d, double k_T, double cp_T, double exp_T, double plheatfrac, double T0) {
+  d->thermal = 1;
+  for (int n = 0; n < d->nn; n++) d->T[n] = T0; /* setTemp, Domain_d.h:678-685 */
+  d->k_T = k_T; d->cp_T = cp_T; d->exp_T = exp_T; d->plheatfraction = plheatfrac;
+}
+void wfo_set_contact_heat(wfo_domain *d, double heat_cond, double T_const) { d->tm_heat_cond = heat_cond; d->tm_T_const = T_const; }
 
 /* calcArtificialViscosity (Mechanical.C:1948-1977) */
 static void calcArtificialViscosity(wfo_domain *d) {
@@ -1282,6 +1355,7 @@ static void CalcContactForces(wfo_domain *d) {
           d->contforce[dim * i + 0] += Ft.x;
           d->contforce[dim * i + 1] += Ft.y;
           if (dim == 3) d->contforce[dim * i + 2] += Ft.z;
+          d->q_cont_conv[i] = d->tm_heat_cond * d->node_area[i] * (d->tm_T_const - d->T[i]); /* Contact.C:309 */
           end = 1;
         }
       }
@@ -1376,6 +1450,7 @@ static void step_once(wfo_domain *d) {
   CalcNodalVol(d);
   CalcNodalMassFromVol(d);
   calcElemStrainRates(d);
+  if (d->thermal) calcThermalExpansion(d); /* Solver_explicit.C:719-720 */
   pressure(d);
   calcNodalPressureFromElemental(d);
   CalcStressStrain(d, d->dt);
@@ -1392,6 +1467,7 @@ static void step_once(wfo_domain *d) {
   axis_constraint(d);
   UpdateCorrectionPos(d);
   if (d->contact) move_trimesh(d);
+  if (d->thermal) ThermalCalcs(d); /* Solver_explicit.C:1008-1012 */
   d->time += d->dt;
   d->step_count++;
 }
@@ -1431,6 +1507,8 @@ int wfo_call(wfo_domain *d, const char *f, double arg) {
   else if (IS("UpdateCorrectionAccVel")) UpdateCorrectionAccVel(d);
   else if (IS("AxisConstraint")) axis_constraint(d);
   else if (IS("UpdateCorrectionPos")) UpdateCorrectionPos(d);
+  else if (IS("calcThermalExpansion")) calcThermalExpansion(d);
+  else if (IS("ThermalCalcs")) ThermalCalcs(d);
   else if (IS("SearchExtNodes")) return SearchExtNodes(d);
   else if (IS("CalcExtFaceAreas")) CalcExtFaceAreas(d);
   else if (IS("CalcContactForces")) CalcContactForces(d);
@@ -1458,6 +1536,7 @@ static view_t view(wfo_domain *d, const char *nm) {
   V("m_f_elem", d->m_f_elem, nk * d->dim) V("m_f_elem_hg", d->m_f_elem_hg, nk * d->dim)
   V("m_hg_q", d->dim == 2 ? d->m_hg_q : NULL, d->dim == 2 ? nk * d->dim : 0)
   V("m_elem_length", d->m_elem_length, d->m_elem_length ? ne : 0)
+  V("T", d->T, nn) V("m_dTedt", d->m_dTedt, nk) V("m_q_plheat", d->m_q_plheat, ne) V("q_cont_conv", d->q_cont_conv, nn)
   V("contforce", d->contforce, nd) V("ut_prev", d->ut_prev, nd) V("node_area", d->node_area, nn)
   V("m_elem_area", d->m_elem_area, ne) V("ext_nodes", d->ext_nodes, (size_t)d->nn)
   V("m_mesh_in_contact", d->m_mesh_in_contact, sizeof(int) * (size_t)d->nn)

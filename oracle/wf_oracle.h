@@ -30,6 +30,9 @@ void wfo_set_mesh(wfo_domain *, int dim, int k, int nn, int ne, const double *x,
 void wfo_set_material(wfo_domain *, double E, double nu, double rho0, int model, double sy0, double K, double m);
 void wfo_set_material_ext(wfo_domain *, double E, double nu, double rho0, int model, double sy0, const double *q, double temp);
 void wfo_set_max_edot(wfo_domain *, double v);
+/* thermal coupling: setThermalOn + setTemp + k_T / cp_T / exp_T + plHeatFrac (main.C:218, 436-441, 567-570); contact heat */
+void wfo_thermal_on(wfo_domain *, double k_T, double cp_T, double exp_T, double plheatfrac, double T0);
+void wfo_set_contact_heat(wfo_domain *, double heat_cond, double T_const);
 void wfo_set_stab(wfo_domain *, const double *s12);
 void wfo_set_options(wfo_domain *, int press_variant, double av_alpha, double av_beta, double hexa_hg_coeff);
 void wfo_add_bc(wfo_domain *, int node, int dim, double val);

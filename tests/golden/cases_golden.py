@@ -26,7 +26,11 @@ GOLDEN = {
     # rate-dependent flow stresses: Johnson-Cook and GMT at a uniform temperature
     "hex_n3_jc": (cases.with_johnson_cook(R(cases.c3_hexes(3), top_vel=-200.0)), 80),
     "psquad_n6_gmt": (cases.with_gmt(R(cases.plane_strain_quads(6), top_vel=-50.0)), 80),
+    # thermal coupling (Thermal.C): conduction, plastic heating, thermal expansion; with contact heat exchange
+    "tet_n3_thermal": (cases.with_thermal(R(cases.c2_tets(3), top_vel=-200.0)), 80),
+    "contact_quad_n6_thermal": (cases.with_thermal(cases.contact_quads(6), heat_cond=25000.0, T_die=200.0), 80),
 }
+THERMAL_ARRAYS = "T m_dTedt m_q_plheat q_cont_conv".split()
 CONTACT_ARRAYS = ("contforce ut_prev node_area m_elem_area m_mesh_in_contact ext_nodes trimesh.node trimesh.node_v "
                   "trimesh.normal trimesh.pplane").split()
 

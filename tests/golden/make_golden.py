@@ -14,7 +14,7 @@ ROOT = os.path.dirname(os.path.dirname(HERE))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, HERE)
 
-from cases_golden import CONTACT_ARRAYS, FLOAT_ARRAYS, GOLDEN, INT_ARRAYS  # noqa: E402
+from cases_golden import CONTACT_ARRAYS, FLOAT_ARRAYS, GOLDEN, INT_ARRAYS, THERMAL_ARRAYS  # noqa: E402
 from oracle import refdrv  # noqa: E402
 
 
@@ -29,7 +29,7 @@ def main():
         case.apply(d)
         out = {nm: d.get(nm) for nm in INT_ARRAYS}
         out["x0"] = d.get("x")
-        extra = CONTACT_ARRAYS if case.contact is not None else []
+        extra = (CONTACT_ARRAYS if case.contact is not None else []) + (THERMAL_ARRAYS if case.thermal is not None else [])
         for nm in extra:
             out[f"s0_{nm}"] = d.get(nm)
         d.step(1)

@@ -135,3 +135,35 @@ def test_large_contact_case_runs_and_matches_small_step_count(oracle_port):
     assert (ref.get("m_mesh_in_contact") >= 0).sum() > 500
     assert np.array_equal(eng.get("m_mesh_in_contact"), ref.get("m_mesh_in_contact"))
     compare(eng, ref, _names(case), 1e-8, "contact 105k tets, 30 steps")
+
+
+# ---- thermal coupling: Thermal.C fused into the element / node passes -------------------------------
+THERMAL = {
+    "hex_th": cases.with_thermal(R(cases.c3_hexes(6), top_vel=-200.0)),
+    "tet_th": cases.with_thermal(R(cases.c2_tets(5), top_vel=-200.0)),
+    "axiquad_th": cases.with_thermal(R(cases.c4_axisymm_quads(12), top_vel=-50.0)),
+    "hex_jc_th": cases.with_thermal(cases.with_johnson_cook(R(cases.c3_hexes(5), top_vel=-200.0)), T0=400.0),
+    "contact_tet_th": cases.with_thermal(cases.contact_tets(5), heat_cond=25000.0, T_die=200.0),
+    "contact_quad_th": cases.with_thermal(cases.contact_quads(10), heat_cond=25000.0, T_die=200.0),
+}
+
+
+@pytest.mark.parametrize("key", sorted(THERMAL))
+@pytest.mark.parametrize("strict", [True, False], ids=["strict", "fast"])
+def test_thermal_coupling(key, strict, oracle_port):
+    """Conduction + plastic heating + thermal expansion (+ the Johnson-Cook T[e] read, + contact heat exchange): one step
+    to 1e-10 / 1e-12, 100 steps within the many-step tolerance."""
+    case = THERMAL[key]
+    eng, ref = run_pair(case, oracle_port, 1, strict)
+    names = list(STATE) + ["T", "m_dTedt", "m_q_plheat"]
+    if case.contact is not None:
+        names += CONTACT + ["q_cont_conv"]
+    compare(eng, ref, names, 1e-12 if strict else 1e-10, f"{key} 1 step")
+    eng.step(99)
+    ref.step(99)
+    T = ref.get("T")
+    assert T.max() > 1.5 * case.thermal["T0"] and (ref.get("m_q_plheat") > 0).any(), "case should heat up"
+    if case.contact is not None:
+        assert (ref.get("q_cont_conv") != 0).any()
+    compare(eng, ref, names, 1e-8 if strict else 1e-6, f"{key} 100 steps")
+    assert not eng.nonfinite_flag()

@@ -10,7 +10,7 @@ import pytest
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.join(HERE, "golden"))
-from cases_golden import CONTACT_ARRAYS, FLOAT_ARRAYS, GOLDEN, INT_ARRAYS  # noqa: E402
+from cases_golden import CONTACT_ARRAYS, FLOAT_ARRAYS, GOLDEN, INT_ARRAYS, THERMAL_ARRAYS  # noqa: E402
 
 from weldformfem_b200 import cases  # noqa: E402
 
@@ -25,7 +25,7 @@ def test_oracle_matches_reference_fixtures_bit_for_bit(name, oracle_port):
     for nm in INT_ARRAYS:
         assert np.array_equal(d.get(nm), g[nm]), nm
     assert np.array_equal(d.get("x"), g["x0"])
-    extra = CONTACT_ARRAYS if case.contact is not None else []
+    extra = (CONTACT_ARRAYS if case.contact is not None else []) + (THERMAL_ARRAYS if case.thermal is not None else [])
     for nm in extra:
         assert np.array_equal(d.get(nm), g["s0_" + nm]), ("setup", nm)
     d.step(1)
@@ -34,7 +34,7 @@ def test_oracle_matches_reference_fixtures_bit_for_bit(name, oracle_port):
     d.step(steps - 1)
     for nm in FLOAT_ARRAYS + list(extra):
         assert np.array_equal(d.get(nm), g["sN_" + nm]), (f"step {steps}", nm)
-    if extra:
+    if case.contact is not None:
         assert (g["sN_m_mesh_in_contact"] >= 0).sum() > 0, "fixture should end with nodes in contact"
     if "sN_m_hg_q" in g:
         assert np.array_equal(d.get("m_hg_q")[: 2 * case.n_elems], g["sN_m_hg_q"])
@@ -57,7 +57,10 @@ LIVE = [dataclasses.replace(cases.c3_hexes(9), top_vel=-150.0), dataclasses.repl
         # (Mechanical.C:1731), which runs past its end on tet meshes (more elements than nodes)
         cases.with_johnson_cook(dataclasses.replace(cases.c3_hexes(6), top_vel=-150.0)),
         cases.with_gmt(dataclasses.replace(cases.c3_hexes(5), top_vel=-150.0)),
-        cases.with_johnson_cook(dataclasses.replace(cases.c4_axisymm_quads(12), top_vel=-40.0))]
+        cases.with_johnson_cook(dataclasses.replace(cases.c4_axisymm_quads(12), top_vel=-40.0)),
+        cases.with_thermal(dataclasses.replace(cases.c3_hexes(5), top_vel=-150.0)),
+        cases.with_thermal(cases.with_johnson_cook(dataclasses.replace(cases.c3_hexes(4), top_vel=-150.0)), T0=400.0),
+        cases.with_thermal(cases.contact_tets(5), heat_cond=25000.0, T_die=200.0)]
 
 
 @pytest.mark.parametrize("case", LIVE, ids=lambda c: c.name)
@@ -68,7 +71,7 @@ def test_oracle_matches_compiled_reference_live(case, oracle_port, oracle_ref):
     case.apply(b)
     a.step(40)
     b.step(40)
-    extra = CONTACT_ARRAYS if case.contact is not None else []
+    extra = (CONTACT_ARRAYS if case.contact is not None else []) + (THERMAL_ARRAYS if case.thermal is not None else [])
     for nm in FLOAT_ARRAYS + ["m_f_elem", "m_str_rate", "m_rot_rate", "m_detJ", "u_dt"] + list(extra):
         assert np.array_equal(a.get(nm), b.get(nm)), nm
 

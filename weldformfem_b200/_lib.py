@@ -43,7 +43,7 @@ DECLARED = (["wf_create", "wf_destroy", "wf_last_error", "wf_set_stream", "wf_ge
              "wf_halo_status", "wf_connect_all", "wf_init_all", "wf_step_all", "wf_halo_set_transport", "wf_halo_exchange_ptrs",
              "wf_host_box_counts", "wf_host_gen_box", "wf_host_nodel", "wf_version",
              "wf_set_trimesh", "wf_set_contact", "wf_get_trimesh_counts", "wf_host_ext_faces",
-             "wf_host_axis_plane_counts", "wf_host_axis_plane_mesh"]
+             "wf_host_axis_plane_counts", "wf_host_axis_plane_mesh", "wf_set_thermal", "wf_set_contact_heat"]
             + ["wf_" + n for n in UNFUSED])
 
 
@@ -128,6 +128,8 @@ def load():
         "wf_set_trimesh": (C.c_int, [vp, C.c_int, C.c_int, C.c_int, dp, dp, ip, dp, ip]),
         "wf_set_contact": (C.c_int, [vp, C.c_double, C.c_double, C.c_double, C.c_double]),
         "wf_get_trimesh_counts": (C.c_int, [vp, ip, ip, ip]),
+        "wf_set_thermal": (C.c_int, [vp] + [C.c_double] * 5),
+        "wf_set_contact_heat": (C.c_int, [vp, C.c_double, C.c_double]),
         "wf_host_ext_faces": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, up, C.POINTER(C.c_ubyte), ip, ip, ip, ip]),
         "wf_host_axis_plane_counts": (C.c_int, [C.c_int, C.c_int, ip, ip]),
         "wf_host_axis_plane_mesh": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, dp, dp, C.c_int, dp, ip, dp, ip]),

@@ -57,6 +57,8 @@ class Case:
     # TriMesh_d::AxisPlaneMesh + "vel"; contact = dict(mu_sta, mu_dyn, penalty_factor, end_steps)
     planes: tuple = ()
     contact: dict | None = None
+    # thermal coupling (config "thermal", Thermal.C): dict(k_T, cp_T, exp_T, plheatfrac, T0[, heat_cond, T_die])
+    thermal: dict | None = None
 
     # ---- derived -------------------------------------------------------------------------
     @property
@@ -126,6 +128,9 @@ class Case:
             dom.set_material_ext(self.E, self.nu, self.rho0, self.model, self.sy0, self.mat_params, self.temp)
         else:
             dom.set_material(self.E, self.nu, self.rho0, self.model, self.sy0, self.K, self.m)
+        if self.thermal is not None:   # main.C:436-441, 567-570
+            t = self.thermal
+            dom.thermal_on(t["k_T"], t["cp_T"], t.get("exp_T", 0.0), t.get("plheatfrac", 0.9), t.get("T0", 20.0))
         dom.set_stab(**self.stab)
         dom.set_options(self.press, self.av[0], self.av[1], self.hexa_hg)
         if hasattr(dom, "add_bcs"):
@@ -140,6 +145,8 @@ class Case:
                 dom.add_plane(self.dim, pl["id"], pl["axis"], pl["positaxisorent"], pl["p1"], pl["p2"], pl["dens"], pl["vel"])
             c = self.contact
             dom.contact_on(c["mu_sta"], c["mu_dyn"], c["penalty_factor"], c["end_steps"] * self.timestep)
+            if self.thermal is not None and "heat_cond" in self.thermal:   # heatCondCoeff / dieTemp, main.C:718-719
+                dom.set_contact_heat(self.thermal["heat_cond"], self.thermal["T_die"])
             dom.call("calcMinEdgeLength")
         if init:
             dom.init(self.timestep)
@@ -207,6 +214,16 @@ def with_johnson_cook(case: Case, temp: float = 400.0) -> Case:
     """Same workload with the Johnson-Cook flow stress (Material.cuh:377-412) at a uniform temperature."""
     import dataclasses
     return dataclasses.replace(case, name=case.name + "_jc", model=JOHNSON_COOK, sy0=JC_AL6061[0], mat_params=JC_AL6061, temp=temp)
+
+
+# aluminium of examples/input/Contact_Compression_tetra.json (thermalCond 190, thermalHeatCap 87.5 as shipped), plus a
+# thermal expansion coefficient and die heat exchange so every coupling term is exercised
+THERMAL_AL = dict(k_T=190.0, cp_T=87.5, exp_T=2.3e-5, plheatfrac=0.9, T0=20.0)
+
+
+def with_thermal(case: Case, **over) -> Case:
+    import dataclasses
+    return dataclasses.replace(case, name=case.name + "_th", thermal=dict(THERMAL_AL, **over))
 
 
 def with_gmt(case: Case, temp: float = 100.0) -> Case:

@@ -230,6 +230,7 @@ __global__ void __launch_bounds__(128) k_contact(WfDev d, WfContact c, const dou
     const V3 cf = mk(h.cf.x + Ft.x, h.cf.y + Ft.y, h.cf.z + Ft.z);
     d.contforce[i] = cf.x; d.contforce[d.np + i] = cf.y; d.contforce[2 * d.np + i] = cf.z;
     d.cflag[i] = (dot(cf, cf) > 0) ? 1 : 0;
+    if (d.q_cont_conv) d.q_cont_conv[i] = c.heat_cond * c.node_area[i] * (c.T_const - d.T[i]); // Contact.C:309
   } else {
     // 2D: the reference's friction code touches ut_prev[2*i+2] — the x slot of node i+1 (Contact.C:258, 297) — so
     // node i+1 sees a zeroed slip if node i slid in the same pass.  Record what the serial pass needs.
@@ -244,6 +245,7 @@ __global__ void __launch_bounds__(128) k_contact(WfDev d, WfContact c, const dou
     r[5 * S] = h.du.x; r[6 * S] = h.du.y;
     r[7 * S] = h.v_tan.x; r[8 * S] = h.v_tan.y;
     d.contforce[i] = h.cf.x; d.contforce[d.np + i] = h.cf.y;
+    if (d.q_cont_conv) d.q_cont_conv[i] = c.heat_cond * c.node_area[i] * (c.T_const - d.T[i]); // Contact.C:309
   }
 }
 
@@ -442,6 +444,17 @@ extern "C" int wf_set_contact(wf_engine *E, double mu_sta, double mu_dyn, double
   E->P.alpha_contact = E->stab.alpha_contact;
   E->P.hg_coeff_contact = E->stab.hg_coeff_contact;
   return wf_check_launch(E, "wf_set_contact");
+}
+
+// heatCondCoeff / dieTemp of the rigid surfaces (main.C:718-719): contact heat flow into the nodal temperature
+extern "C" int wf_set_contact_heat(wf_engine *E, double heat_cond, double T_const) {
+  NEED(E->contact, "wf_set_contact_heat needs wf_set_contact");
+  NEED(E->d.T, "wf_set_contact_heat needs wf_set_thermal");
+  NEED(!E->inited, "contact heat must be set before wf_init");
+  CK(cudaSetDevice(E->device));
+  if (!E->d.q_cont_conv && dalloc(E, &E->d.q_cont_conv, (size_t)E->d.np)) return 1;
+  E->C.heat_cond = heat_cond; E->C.T_const = T_const;
+  return 0;
 }
 
 int wf_contact_refresh_nodlen(wf_engine *E) {

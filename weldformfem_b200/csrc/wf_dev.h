@@ -91,6 +91,16 @@ struct WfDev {
   double *contforce;                 /* [dim][np] */
   unsigned char *cflag;              /* [np] */
 
+  /* thermal coupling (NULL when off; Thermal.C): nodal temperature, node-ordered element contributions m_dTedt
+   * (one double per (e, ln), same ordering as fsell), plastic heat source, and the first n_nodes entries of the
+   * reference's flat m_dTedt[e*k+ln] of the previous / current step (calcThermalExpansion reads that array with
+   * NODE ids, Thermal.C:157-160) */
+  double *T;                         /* [np] */
+  double *tsell;                     /* [sell_total] */
+  double *q_plheat;                  /* [ep] m_q_plheat */
+  double *dtedt_low[2];              /* [np] each */
+  double *q_cont_conv;               /* [np] contact heat flow (Contact.C:309), persists like contforce */
+
   /* flags / reductions */
   int *nonfinite;                    /* [1] */
   unsigned long long *xmin_key;      /* [2] ordered-key of min x_r (axisymmetric axis constraint) */
@@ -101,6 +111,8 @@ struct WfPar {
   /* material (Material.cuh) */
   int model;
   double Kbulk, G, sy0, Kh, mh, eps0, eps1, cs0;
+  int thermal, dtedt_cur;               /* thermal coupling on; which dtedt_low buffer this step writes */
+  double k_T, cp_T, exp_T, plheatfrac;  /* Material_::k_T / cp_T / exp_T (Material.cuh:79-81), m_plheatfraction */
   double young, mq[14], temp, max_edot; /* Johnson-Cook / GMT constants (wf_material::q), uniform temperature */
   /* StabilizationParams + hexa hourglass coefficient */
   double alpha_contact, hg_coeff_contact; /* used instead of the _free values by elements touching a contact node */
@@ -142,4 +154,5 @@ struct WfContact {
   const double *tm_v_orig;
   const int *tm_elnode, *tm_mesh_id;
   double mu_sta, mu_dyn, contPF, young;
+  double heat_cond, T_const;         /* TriMesh_d::heat_cond / T_const (main.C:718-719) */
 };

@@ -326,6 +326,25 @@ extern "C" int wf_set_tracking(wf_engine *E, int flags) {
   return 0;
 }
 
+// thermal coupling: setThermalOn + setTemp(T0) + thermalCond / thermalHeatCap / thermalExp + plHeatFrac
+// (main.C:218, 436-441, 567-570; Thermal.C)
+extern "C" int wf_set_thermal(wf_engine *E, double k_T, double cp_T, double exp_T, double plheatfrac, double T0) {
+  NEED(E->meshed, "wf_set_thermal needs the mesh");
+  NEED(!E->inited, "thermal coupling must be switched on before wf_init");
+  NEED(!E->distributed, "thermal coupling is not available on a partitioned mesh");
+  CK(cudaSetDevice(E->device));
+  WfDev &d = E->d;
+  if (!d.T && (dalloc(E, &d.T, (size_t)d.np) || dalloc(E, &d.tsell, (size_t)E->sell_total) || dalloc(E, &d.q_plheat, (size_t)d.ep) ||
+               dalloc(E, &d.dtedt_low[0], (size_t)d.np) || dalloc(E, &d.dtedt_low[1], (size_t)d.np)))
+    return 1;
+  std::vector<double> t0(d.np, T0);
+  CK(cudaMemcpyAsync(d.T, t0.data(), sizeof(double) * d.np, cudaMemcpyHostToDevice, E->stream));
+  CK(cudaStreamSynchronize(E->stream));
+  E->P.thermal = 1; E->P.dtedt_cur = 0;
+  E->P.k_T = k_T; E->P.cp_T = cp_T; E->P.exp_T = exp_T; E->P.plheatfrac = plheatfrac;
+  return 0;
+}
+
 extern "C" int wf_add_bc_vel(wf_engine *E, int node, int dim, double val) {
   NEED(dim >= 0 && dim < 3, "bad BC dim");
   E->bc_nod[dim].push_back(node);
@@ -620,6 +639,7 @@ static int step_stage(wf_engine *E, int stage, bool last) {
     if (wf_contact_forces(E)) return 1;          // CalcContactForces (Solver_explicit.C:769-770)
     E->L->node_update(d, P, sep, last ? 0 : 1, 0, E->stream);
     if (wf_contact_step_end(E)) return 1;        // rigid surfaces: ramp, Move, normals, plane coefficients (:981-1005)
+    if (P.thermal) { E->L->node_thermal(d, P, E->stream); P.dtedt_cur ^= 1; }  // ThermalCalcs, node part (:1008-1012)
     E->predicted = !last;
     P.xmin_cur ^= 1;
     E->time += P.dt;
@@ -699,6 +719,7 @@ extern "C" int wf_step_timed(wf_engine *E, int nsteps, float *ms) {
     if (wf_contact_forces(E)) return 1;
     E->L->node_update(d, P, sep, last ? 0 : 1, 0, E->stream);
     if (wf_contact_step_end(E)) return 1;
+    if (P.thermal) { E->L->node_thermal(d, P, E->stream); P.dtedt_cur ^= 1; }
     mark(4);
     E->predicted = !last;
     P.xmin_cur ^= 1;
@@ -997,6 +1018,7 @@ extern "C" int wf_get_time(wf_engine *E, double *t, long *steps) {
 #define UNFUSED_PROLOGUE()                                        \
   NEED(E->inited, "call wf_init first");                          \
   NEED(!E->predicted, "engine is mid-batch");                     \
+  NEED(!E->P.thermal, "the unfused entry points do not cover thermal coupling: step with wf_step"); \
   CK(cudaSetDevice(E->device));                                   \
   if (ensure_dbg(E)) return 1;                                    \
   WfDev &d = E->d; WfPar &P = E->P; (void)d; (void)P;
@@ -1053,6 +1075,7 @@ struct ArrayRef {
   const void *host = nullptr;
   size_t bytes = 0;
   int comp = 0; // for dH: which dimension
+  bool lazy_dtedt = false;
   bool lazy_sigma = false, lazy_fi = false, lazy_voln = false, lazy_pnode = false, lazy_felem = false, hg = false;
 };
 
@@ -1087,6 +1110,10 @@ static bool lookup(wf_engine *E, const std::string &nm, ArrayRef &r, bool for_wr
   if (nm == "m_detJ") return elems(d.detJ);
   if (nm == "m_radius") return elems(d.radius);
   if (nm == "m_elem_length") return E->elem_length_valid ? elems(E->elem_length) : false;
+  if (nm == "T") { r.kind = K_NODESCAL; r.dev = d.T; r.bytes = nnb; return d.T != nullptr; }
+  if (nm == "m_q_plheat") return elems(d.q_plheat);
+  if (nm == "q_cont_conv") { r.kind = K_NODESCAL; r.dev = d.q_cont_conv; r.bytes = nnb; return d.q_cont_conv != nullptr; }
+  if (nm == "m_dTedt") { r.kind = K_ELEMNODE; r.bytes = nk; r.lazy_dtedt = true; return d.tsell != nullptr && !for_write; }
   if (nm == "m_tau") return elem6(d.tau);
   if (nm == "m_eps") return elem6(d.eps);
   if (nm == "m_str_rate") return elem6(d.str_rate);
@@ -1174,6 +1201,16 @@ extern "C" int wf_get_array(wf_engine *E, const char *name, void *dst, size_t by
     CK(cudaMemcpyAsync(dst, E->scratch + c6, bytes, cudaMemcpyDeviceToHost, E->stream));
     CK(cudaStreamSynchronize(E->stream));
     return check_launch(E, "m_sigma");
+  } else if (r.lazy_dtedt) { // m_dTedt[e*k+ln] back from the node-ordered buffer
+    std::vector<double> ts;
+    if (download(E, d.tsell, (size_t)E->sell_total, ts)) return 1;
+    for (int e2 = 0; e2 < ne; e2++)
+      for (int n = 0; n < k; n++) {
+        const size_t o = E->h_pos[(size_t)n * d.ep + e2];
+        const size_t lane = o & 31;
+        out[(size_t)e2 * k + n] = ts[(o + (size_t)(dim - 1) * lane) / dim];
+      }
+    return 0;
   } else if (r.lazy_felem) {
     NEED(E->step_count > 0, "m_f_elem is available after a step");
     std::vector<double> fs;

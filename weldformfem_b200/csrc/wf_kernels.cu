@@ -292,12 +292,14 @@ WF_DI void gather_nodal_p(const WfDev &d, const int (&nid)[Elem<ET>::K], double 
 // mode bits: 1 = hourglass force kept separate in f_elem_hg (strict two-pass assembly)
 // STAGED: the CTA first loads x, v and the nodal ratio of its UNIQUE nodes into shared memory (WfDev::blk_off),
 // then every element reads its nodes through 16-bit block-local indices; otherwise every element gathers its own.
-template <int ET, bool SEPARATE_HG, bool STAGED>
+template <int ET, bool SEPARATE_HG, bool STAGED, bool THERMAL = false>
 __global__ void __launch_bounds__(TPB_E) k_elem_main(WfDev d, WfPar P, int stride) {
   constexpr int K = Elem<ET>::K, D = Elem<ET>::D;
+  static_assert(!(STAGED && THERMAL), "the thermal terms gather by global node id");
   extern __shared__ double sm[];
   int e = blockIdx.x * blockDim.x + threadIdx.x;
   double xl[K][D], vl[K][D], npn[K], A[D][D], dH[D][K], detJ;
+  int nid[K];
   if constexpr (STAGED) {
     static_assert(TPB_E == WF_EBLK, "block node tables are built for WF_EBLK elements per CTA");
     const int b = blockIdx.x;
@@ -328,7 +330,6 @@ __global__ void __launch_bounds__(TPB_E) k_elem_main(WfDev d, WfPar P, int strid
     }
   } else {
     if (e >= d.ne) return;
-    int nid[K];
     load_conn<ET>(d, e, nid);
     gather_nodal<ET>(d.x, d.np, nid, xl);
     gather_nodal<ET>(d.v, d.np, nid, vl);
@@ -350,9 +351,55 @@ __global__ void __launch_bounds__(TPB_E) k_elem_main(WfDev d, WfPar P, int strid
   shape_derivs<ET>(A, dH);
   double Dr[6], Wr[3];
   strain_rates<ET>(dH, detJ, vl, radius, d.domtype, Dr, Wr);
+  double temp_e = P.temp;
+  if constexpr (THERMAL) {
+    // calcThermalExpansion (Thermal.C:151-166): D -= exp_T * dTdt_gp * I with dTdt_gp read from the previous step's
+    // flat m_dTedt at the NODE ids, as the reference does
+    const double *__restrict__ prev = d.dtedt_low[P.dtedt_cur ^ 1];
+    double dTdt_gp = 0.0;
+#pragma unroll
+    for (int i = 0; i < K; i++) dTdt_gp += 1.0 / K * prev[nid[i]];
+    const double f = P.exp_T * dTdt_gp;
+    Dr[0] = Dr[0] - f * 1.; Dr[1] = Dr[1] - f * 1.; Dr[2] = Dr[2] - f * 1.;
+    Dr[3] = Dr[3] - f * 0.; Dr[4] = Dr[4] - f * 0.; Dr[5] = Dr[5] - f * 0.;
+    if (e < d.nn) temp_e = d.T[e]; // T[e]: nodal array read with the element id (Mechanical.C:1731)
+  }
   const double p = elem_pressure<ET>(d, P, e, npn, vol, vol0, rho_e, dH, vl, elem_in_contact<ET>(d, e));
   StressOut so;
-  stress_update(P, P.dt, p, Dr, Wr, tau, pl, sy_prev, so);
+  stress_update(P, P.dt, p, Dr, Wr, tau, pl, sy_prev, so, temp_e);
+  if constexpr (THERMAL) {
+    // m_q_plheat (Mechanical.C:1784-1818) and ThermalCalcs' element part (Thermal.C:41-93): conduction Kt T + plastic
+    // heating, one value per element node, stored where the node's nodel list expects it (tsell, same order as fsell)
+    const double qpl = plastic_heat(P, P.dt, so);
+    d.q_plheat[e] = qpl;
+    double Te[K], md[K];
+#pragma unroll
+    for (int i = 0; i < K; i++) { Te[i] = d.T[nid[i]]; md[i] = d.mdiag[nid[i]]; }
+    const double w = gauss_w<ET>();
+    const double heat = 0.9 * qpl;
+    const double elem_pow = heat * vol;
+    const double pow_per_node = elem_pow / K;
+    double *__restrict__ cur = d.dtedt_low[P.dtedt_cur];
+#pragma unroll
+    for (int i = 0; i < K; i++) {
+      double dTde = 0.0;
+#pragma unroll
+      for (int j = 0; j < K; j++) {
+        double kk = 0.0;
+#pragma unroll
+        for (int c = 0; c < D; c++) kk += dH[c][i] * dH[c][j];
+        dTde += (kk * P.k_T / detJ * w) * Te[j];
+      }
+      const double m_inv = 1.0 / md[i];
+      double val = -m_inv * dTde;
+      val += pow_per_node / (md[i] * P.cp_T);
+      const long long o = (long long)__ldg(d.pos + (long long)i * d.ep + e);
+      const long long lane = o & 31;
+      d.tsell[(o + (D - 1) * lane) / D] = val; // fsell offset D*q - (D-1)*lane  ->  q
+      const long long flat = (long long)e * K + i;
+      if (flat < d.nn) cur[flat] = val;
+    }
+  }
   if (P.track_eps) {
 #pragma unroll
     for (int i = 0; i < 6; i++) {
@@ -578,6 +625,22 @@ __global__ void __launch_bounds__(TPB_N) k_node_update(WfDev d, WfPar P, int fus
     }
     if ((threadIdx.x & 31) == (__ffs(mask) - 1)) atomicMin(d.xmin_key + (P.xmin_cur ^ 1), key);
   }
+}
+
+// ThermalCalcs, node part (Thermal.C:103-125): dTdt = sum of the element contributions in nodel order;
+// T += (dTdt + q_cont_conv / (m cp)) dt.  One warp == one SELL slice, rows of tsell are contiguous.
+__global__ void __launch_bounds__(TPB_N) k_node_thermal(WfDev d, WfPar P) {
+  int n = blockIdx.x * blockDim.x + threadIdx.x;
+  int slice = n >> 5;
+  if (slice >= d.nslices) return;
+  const long long base = d.sell_ptr[slice];
+  const int width = (int)((d.sell_ptr[slice + 1] - base) >> 5);
+  const double *__restrict__ row = d.tsell + base + (n & 31);
+  double dTdt = 0;
+  for (int j = 0; j < width; j++) dTdt += row[(long long)j * 32]; // padding entries stay +0.0
+  if (n >= d.nn) return;
+  const double qc = d.q_cont_conv ? d.q_cont_conv[n] : 0.0;
+  d.T[n] += (dTdt + qc * 1.0 / (d.mdiag[n] * P.cp_T)) * P.dt;
 }
 
 // nodal mass only (init, unfused CalcNodalVol + CalcNodalMassFromVol, lazy m_mdiag)
@@ -869,7 +932,7 @@ __global__ void k_u_stress(WfDev d, WfPar P, double dt) {
   for (int i = 0; i < 3; i++) Wr[i] = d.rot_rate[(long long)(3 + i) * d.ep + e];
   double pl = d.pl_strain[e];
   StressOut so;
-  stress_update(P, dt, d.p[e], Dr, Wr, tau, pl, d.sigma_y[e], so);
+  stress_update(P, dt, d.p[e], Dr, Wr, tau, pl, d.sigma_y[e], so, P.temp);
 #pragma unroll
   for (int i = 0; i < 6; i++) {
     d.tau[(long long)i * d.ep + e] = tau[i];
@@ -1171,7 +1234,7 @@ static void l_node_vol(const WfDev &d, const WfPar &P, int mode, cudaStream_t s)
 }
 static void l_elem_main(const WfDev &d, const WfPar &P, int et, int separate_hg, cudaStream_t s) {
   // the regrouped hexa kernel inlines Bilinear / Hollomon; the rate-dependent laws (Johnson-Cook, GMT) take the generic kernel
-  if (!separate_hg && et == ET_HEX8 && !P.strict && P.variant[2] != 1 && P.model < 2) {
+  if (!separate_hg && et == ET_HEX8 && !P.strict && P.variant[2] != 1 && P.model < 2 && !P.thermal) {
     if (P.variant[2] >= 100) { // memory skeletons (tuning aid, garbage results)
       const int g = cdiv(d.ne, hexfast::TPB);
       switch (P.variant[2] - 100) {
@@ -1203,10 +1266,13 @@ static void l_elem_main(const WfDev &d, const WfPar &P, int et, int separate_hg,
   const int stride = (d.blk_umax + 31) / 32 * 32;
   // measured (tools/kbench.py): per-element gathers beat block staging for tets, quads and the strict hexa kernel
   // (0.71 vs 0.78 ms at 10M tets); the staged form is kept as variant 8
-  const bool staged = P.variant[2] == 8;
+  const bool staged = P.variant[2] == 8 && !P.thermal;
   if (staged) {
     if (separate_hg) { ELEM_DISPATCH(et, k_elem_main<ET, true, true><<<cdiv(d.ne, TPB_E), TPB_E, (2 * Elem<ET>::D + 1) * stride * 8, s>>>(d, P, stride)); }
     else { ELEM_DISPATCH(et, k_elem_main<ET, false, true><<<cdiv(d.ne, TPB_E), TPB_E, (2 * Elem<ET>::D + 1) * stride * 8, s>>>(d, P, stride)); }
+  } else if (P.thermal) {
+    if (separate_hg) { ELEM_DISPATCH(et, k_elem_main<ET, true, false, true><<<cdiv(d.ne, TPB_E), TPB_E, 0, s>>>(d, P, 0)); }
+    else { ELEM_DISPATCH(et, k_elem_main<ET, false, false, true><<<cdiv(d.ne, TPB_E), TPB_E, 0, s>>>(d, P, 0)); }
   } else {
     if (separate_hg) { ELEM_DISPATCH(et, k_elem_main<ET, true, false><<<cdiv(d.ne, TPB_E), TPB_E, 0, s>>>(d, P, 0)); }
     else { ELEM_DISPATCH(et, k_elem_main<ET, false, false><<<cdiv(d.ne, TPB_E), TPB_E, 0, s>>>(d, P, 0)); }
@@ -1223,6 +1289,9 @@ static void l_node_update(const WfDev &d, const WfPar &P, int separate_hg, int f
   else if (P.variant[3] == 1) node_update_t<false, 2>(d, P, fuse, phase, s);
   else if (P.variant[3] == 2) node_update_t<false, 8>(d, P, fuse, phase, s);
   else node_update_t<false, 4>(d, P, fuse, phase, s);
+}
+static void l_node_thermal(const WfDev &d, const WfPar &P, cudaStream_t s) {
+  k_node_thermal<<<cdiv((long long)d.nslices * 32, TPB_N), TPB_N, 0, s>>>(d, P);
 }
 static void l_node_mass(const WfDev &d, const WfPar &P, int use_stored_voln, cudaStream_t s) {
   int g = cdiv((long long)d.nslices * 32, TPB_N);
@@ -1368,6 +1437,6 @@ extern "C" const WfLaunch *WF_CAT(WF_NS, _table)() {
                              l_rebuild_sigma, l_energy, l_u_strain_rates, l_u_pressure, l_u_stress, l_u_artvisc,
                              l_u_forces, l_u_hourglass, l_u_nodal_vol, l_u_assembly, l_u_accel, l_u_corr_accvel,
                              l_u_axis, l_u_corr_pos, l_halo_send, l_halo_wait, l_halo_finish, l_preload, l_p_node, l_min_edge, l_max_vel, l_soa_to_aos,
-                             l_aos_to_soa};
+                             l_aos_to_soa, l_node_thermal};
   return &t;
 }

@@ -39,6 +39,7 @@ struct WfLaunch {
   void (*max_vel)(const WfDev &, unsigned long long *keys3, cudaStream_t);
   void (*soa_to_aos)(const double *soa, long long pitch, int nc, long long n, double scale, double *aos, cudaStream_t);
   void (*aos_to_soa)(const double *aos, long long pitch, int nc, long long n, double *soa, cudaStream_t);
+  void (*node_thermal)(const WfDev &, const WfPar &, cudaStream_t);
 };
 
 extern "C" const WfLaunch *wf_strict_table();

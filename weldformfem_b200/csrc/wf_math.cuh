@@ -197,14 +197,14 @@ WF_DI double hollomon_et(const WfPar &P, double strain) {
 }
 
 // CalcJohnsonCookYieldStress / TangentModulus (Material.cuh:377-387, 397-412); mq = A B n C eps_0 m T_m T_t
-WF_DI double jc_sy(const WfPar &P, double strain, double strain_rate) {
-  const double T_h = (P.temp - P.mq[7]) / (P.mq[6] - P.mq[7]);
+WF_DI double jc_sy(const WfPar &P, double strain, double strain_rate, double temp) {
+  const double T_h = (temp - P.mq[7]) / (P.mq[6] - P.mq[7]);
   double sr = strain_rate;
   if (strain_rate == 0.0) sr = 1.e-5;
   return (P.mq[0] + P.mq[1] * pow(strain, P.mq[2])) * (1.0 + P.mq[3] * log(sr / P.mq[4])) * (1.0 - pow(T_h, P.mq[5]));
 }
-WF_DI double jc_et(const WfPar &P, double plstrain, double strain_rate) {
-  const double T_h = (P.temp - P.mq[7]) / (P.mq[6] - P.mq[7]);
+WF_DI double jc_et(const WfPar &P, double plstrain, double strain_rate, double temp) {
+  const double T_h = (temp - P.mq[7]) / (P.mq[6] - P.mq[7]);
   if (plstrain > 0.)
     return P.mq[2] * P.mq[1] * pow(plstrain, P.mq[2] - 1.) * (1.0 + P.mq[3] * log(strain_rate / P.mq[4])) * (1.0 - pow(T_h, P.mq[5]));
   return P.young * 0.1;
@@ -215,13 +215,13 @@ WF_DI void gmt_clamp(const WfPar &P, double &e, double &er, double &T) {
   if (er < P.mq[10]) er = P.mq[10]; else if (er > P.mq[11]) er = P.mq[11];
   if (T < P.mq[12]) T = P.mq[12]; else if (T > P.mq[13]) T = P.mq[13];
 }
-WF_DI double gmt_sy(const WfPar &P, double strain, double strain_rate) {
-  double e = strain, er = strain_rate, T = P.temp;
+WF_DI double gmt_sy(const WfPar &P, double strain, double strain_rate, double temp) {
+  double e = strain, er = strain_rate, T = temp;
   gmt_clamp(P, e, er, T);
   return P.mq[2] * exp(P.mq[3] * T) * pow(e, P.mq[0] * T + P.mq[1]) * exp((P.mq[6] * T + P.mq[7]) / e) * pow(er, P.mq[4] * T + P.mq[5]);
 }
-WF_DI double gmt_et(const WfPar &P, double plstrain, double strain_rate) {
-  double e = plstrain, er = strain_rate, T = P.temp;
+WF_DI double gmt_et(const WfPar &P, double plstrain, double strain_rate, double temp) {
+  double e = plstrain, er = strain_rate, T = temp;
   gmt_clamp(P, e, er, T);
   return P.mq[2] * exp(P.mq[3] * T) * pow(er, P.mq[4] * T + P.mq[5]) *
          pow(e, T * P.mq[0] + P.mq[1] - 2.0) * (-P.mq[6] * T - P.mq[7] + e * (P.mq[0] * T + P.mq[1])) * exp((P.mq[6] * T + P.mq[7]) / e);
@@ -233,7 +233,7 @@ WF_DI double gmt_et(const WfPar &P, double plstrain, double strain_rate) {
 // applied to (tau, Trans(W)) and (W, tau); only the six stored components are formed.
 struct StressOut { double sig[6]; double sy; double dep; };
 WF_DI void stress_update(const WfPar &P, double dt, double p, const double (&Dr)[6], const double (&Wr)[3],
-                         double (&tau)[6], double &pl, double sy_prev, StressOut &o) {
+                         double (&tau)[6], double &pl, double sy_prev, StressOut &o, double temp) {
   // tau: xx=0 yy=1 zz=2 xy=3 yz=4 xz=5
   const double txx = tau[0], tyy = tau[1], tzz = tau[2], txy = tau[3], tyz = tau[4], txz = tau[5];
   const double wxy = Wr[0], wyz = Wr[1], wxz = Wr[2];
@@ -282,15 +282,15 @@ WF_DI void stress_update(const WfPar &P, double dt, double p, const double (&Dr)
                3.0 * (Dr[3] * Dr[3] + Dr[4] * Dr[4] + Dr[5] * Dr[5]));
   }
   if (P.model == 1) sy = hollomon_sy(P, pl);
-  else if (P.model == 2) sy = jc_sy(P, pl, esr);
-  else if (P.model == 3) sy = gmt_sy(P, pl, esr);
+  else if (P.model == 2) sy = jc_sy(P, pl, esr, temp);
+  else if (P.model == 3) sy = gmt_sy(P, pl, esr, temp);
   double dep = 0.0;
   if (P.model >= 2) esr = esr < P.max_edot ? esr : P.max_edot; // min(eff_strain_rate, m_max_edot), :1739
   if (sy < sig_trial) {
     double Et = 0.0; // BILINEAR: uninitialised in the reference (UB); treated as perfectly plastic
     if (P.model == 1) Et = hollomon_et(P, pl);
-    else if (P.model == 2) Et = jc_et(P, pl, esr);
-    else if (P.model == 3) Et = gmt_et(P, pl, esr);
+    else if (P.model == 2) Et = jc_et(P, pl, esr, temp);
+    else if (P.model == 3) Et = gmt_et(P, pl, esr, temp);
     const double H = Et, G = P.G;
     const double dgamma = (sig_trial - sy) / (3.0 * G + H);
     const double factor = 1.0 - (3.0 * G * dgamma) / sig_trial;
@@ -305,6 +305,18 @@ WF_DI void stress_update(const WfPar &P, double dt, double p, const double (&Dr)
   for (int i = 0; i < 6; i++) tau[i] = t[i];
   o.sy = sy;
   o.dep = dep;
+}
+
+// plastic work rate m_q_plheat (Mechanical.C:1787-1818): plheatfrac * sigma : (strain_pl_incr / dt)
+WF_DI double plastic_heat(const WfPar &P, double dt, const StressOut &o) {
+  if (!(o.dep > 0.0)) return 0.0;
+  const double f = o.dep / o.sy;
+  const double (&S)[6] = o.sig; // xx yy zz xy yz xz
+  const double idt = 1. / dt;
+  const double exx = (f * (S[0] - 0.5 * (S[1] + S[2]))) * idt, eyy = (f * (S[1] - 0.5 * (S[0] + S[2]))) * idt;
+  const double ezz = (f * (S[2] - 0.5 * (S[0] + S[1]))) * idt;
+  const double exy = (1.5 * f * (S[3])) * idt, exz = (1.5 * f * (S[5])) * idt, eyz = (1.5 * f * (S[4])) * idt;
+  return P.plheatfrac * (S[0] * exx + 2.0 * S[3] * exy + 2.0 * S[5] * exz + S[1] * eyy + 2.0 * S[4] * eyz + S[2] * ezz);
 }
 
 // calcArtificialViscosity (Mechanical.C:1948-1977): Wilkins q added to the stress diagonal

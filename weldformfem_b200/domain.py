@@ -145,6 +145,13 @@ class Domain_d:
         mat.max_edot = float(max_edot) if max_edot is not None else 0.0
         self._ck(self._lib.wf_set_material(self._h, C.byref(mat)))
 
+    def thermal_on(self, k_T, cp_T, exp_T=0.0, plheatfrac=0.9, T0=20.0):
+        """setThermalOn + setTemp(T0) + thermalCond / thermalHeatCap / thermalExp + plHeatFrac (main.C:218, 436-441, 567-570)."""
+        self._ck(self._lib.wf_set_thermal(self._h, float(k_T), float(cp_T), float(exp_T), float(plheatfrac), float(T0)))
+
+    def set_contact_heat(self, heat_cond, T_const):            # heatCondCoeff / dieTemp, main.C:718-719
+        self._ck(self._lib.wf_set_contact_heat(self._h, float(heat_cond), float(T_const)))
+
     def set_stab(self, **kw):                                  # m_stab, main.C:84-120
         self._stab_kw = {k: float(v) for k, v in kw.items()}
         self._push_stab()
