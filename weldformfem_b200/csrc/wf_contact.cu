@@ -165,39 +165,172 @@ __device__ __forceinline__ V3 friction(const WfContact &c, const Hit &h, double 
   return vdiv(h.v_tan * (-Ft_max_dynamic), nvt);
 }
 
-// one thread per external node.  acc = the acceleration array Contact.C reads through getAccVec (the previous
-// step's corrected acceleration: prev_a in the fused schedule).
-__global__ void __launch_bounds__(128) k_contact(WfDev d, WfContact c, const double *__restrict__ acc, double dt) {
-  const int t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= c.n_ext) return;
-  const int i = c.ext_nodes[t];
+// facet test of Contact.C:68-139: the node lies behind facet j's plane and its projection falls inside the facet
+__device__ __forceinline__ bool facet_hit(const WfContact &c, const V3 &xi, int j, V3 &nj, double &dist) {
   const int nen = c.tm_dim == 3 ? 3 : 2;
+  nj = ld3(c.tm_normal, j);
+  dist = dot(nj, xi) - c.tm_pplane[j];
+  if (!(dist < 0)) return false;
+  const V3 Qj = xi - nj * dist;
+  if (c.tm_dim == 3) {
+    for (int l = 0; l < 3; l++) {
+      const int n = (l + 1 > 2) ? 0 : l + 1;
+      const V3 nl = ld3(c.tm_node, c.tm_elnode[nen * j + l]);
+      const double crit = dot(cross(ld3(c.tm_node, c.tm_elnode[nen * j + n]) - nl, Qj - nl), nj);
+      if (crit < 0.0) return false;
+    }
+  } else {
+    for (int l = 0; l < 2; l++) {
+      const int n = (l + 1 > 1) ? 0 : l + 1;
+      const V3 nl = ld3(c.tm_node, c.tm_elnode[nen * j + l]);
+      const double crit = dot(ld3(c.tm_node, c.tm_elnode[nen * j + n]) - nl, Qj - nl);
+      if (crit < 0.0) return false;
+    }
+  }
+  return true;
+}
+
+struct Hit;
+__device__ void contact_force(const WfDev &d, const WfContact &c, double dt, int t, int i, const V3 &xi, int jhit);
+
+// Contact search in two kernels.
+// k_contact_filter — one THREAD per external node walks the facets in ascending order against a single-precision copy
+// of the plane coefficients staged per CTA in shared memory as float4 (nx, ny, nz, pplane); all threads of a warp read
+// the SAME facet, so every load is one broadcast.  The fp32 distance is only a conservative filter: a facet is ruled
+// out when d32 exceeds the rounding bound 1e-6 * ((|nx|+|ny|+|nz|) * max|x_c| + |pplane|) (inputs rounded to fp32,
+// relative error 2^-24 each, four products).  Nodes in front of every plane are finished here (no contact); the others
+// are appended, with the first facet that could not be ruled out, to a candidate list.
+// k_contact_exact — one WARP per candidate: the 32 lanes run the reference's double-precision test (Contact.C:68-139)
+// on 32 consecutive facets at a time, ascending; the lowest hit lane of the first chunk with a hit is the reference's
+// "first facet that contains the projection" (Contact.C:311: one master facet per slave node).  Candidates are the
+// nodes at or behind a tool surface — they sit next to each other in the node numbering, so giving each its own warp
+// is what spreads the fp64 work over the whole GPU.
+constexpr int CONTACT_TPB = 64;
+constexpr int CONTACT_CHUNK = 2048; // facets per shared-memory chunk (32 KB)
+__global__ void __launch_bounds__(CONTACT_TPB) k_contact_filter(WfDev d, WfContact c, double dt, int *__restrict__ cand_count,
+                                                                int2 *__restrict__ cand) {
+  __shared__ float4 pl[CONTACT_CHUNK];
+  const int t = blockIdx.x * CONTACT_TPB + threadIdx.x;
+  const bool valid = t < c.n_ext;
+  const int i = valid ? c.ext_nodes[t] : 0;
+  const V3 xi = valid ? node3(d, d.x, i) : mk(0.0, 0.0, 0.0);
+  const float xf = (float)xi.x, yf = (float)xi.y, zf = (float)xi.z;
+  const float xinf = fmaxf(fabsf(xf), fmaxf(fabsf(yf), fabsf(zf)));
+  int first = -1;
+  for (int base = 0; base < c.tm_ne; base += CONTACT_CHUNK) {
+    const int cnt = min(CONTACT_CHUNK, c.tm_ne - base);
+    __syncthreads();
+    for (int j = threadIdx.x; j < ((cnt + 7) & ~7); j += CONTACT_TPB)
+      pl[j] = j < cnt ? make_float4((float)c.tm_normal[3 * (base + j)], (float)c.tm_normal[3 * (base + j) + 1],
+                                    (float)c.tm_normal[3 * (base + j) + 2], (float)c.tm_pplane[base + j])
+                      : make_float4(0.f, 0.f, 0.f, -1.0e30f); // padding: infinitely far in front
+    __syncthreads();
+    if (valid && first < 0) {
+      // eight facets per trip, flags first and one branch after: the loads and FMAs of a trip overlap
+      for (int jj = 0; jj < cnt && first < 0; jj += 8) {
+        unsigned m = 0;
+#pragma unroll
+        for (int q8 = 0; q8 < 8; q8++) {
+          const float4 q = pl[jj + q8];
+          const float d32 = fmaf(q.x, xf, fmaf(q.y, yf, q.z * zf)) - q.w;
+          const float bound = 1.0e-6f * fmaf(fabsf(q.x) + fabsf(q.y) + fabsf(q.z), xinf, fabsf(q.w));
+          if (d32 <= bound) m |= 1u << q8; // cannot be ruled out in single precision
+        }
+        if (m) first = base + jj + (__ffs(m) - 1);
+      }
+    }
+  }
+  if (!valid) return;
+  if (first < 0) contact_force(d, c, dt, t, i, xi, -1);
+  else cand[atomicAdd(cand_count, 1)] = make_int2(t, first);
+}
+
+// single-precision classification of (node, facet): false = the reference's test certainly fails (in front of the
+// plane, or the projection certainly outside one edge), true = possible hit, to be decided in double precision.
+// Rounding bounds: coordinates carry 2^-24 relative error, the fp32 distance at most `bound`; every edge criterion is
+// a sum of products of two coordinate differences (times a normal component), hence the margin 1e-5 * s * (|e| + |r|)
+// with s the largest coordinate magnitude involved — several times the worst case.
+template <bool D3>
+__device__ __forceinline__ bool facet_possible32(const WfContact &c, float xf, float yf, float zf, float xinf, int j) {
+  constexpr int NEN = D3 ? 3 : 2;
+  // branch-free: all loads are issued up front so that several facets per lane overlap their memory round trips
+  int g[NEN];
+#pragma unroll
+  for (int l = 0; l < NEN; l++) g[l] = c.tm_elnode[NEN * j + l];
+  const float nx = (float)c.tm_normal[3 * j], ny = (float)c.tm_normal[3 * j + 1], nz = (float)c.tm_normal[3 * j + 2];
+  const float pp = (float)c.tm_pplane[j];
+  float vx[NEN], vy[NEN], vz[NEN];
+#pragma unroll
+  for (int l = 0; l < NEN; l++) {
+    vx[l] = (float)c.tm_node[3 * g[l]]; vy[l] = (float)c.tm_node[3 * g[l] + 1]; vz[l] = (float)c.tm_node[3 * g[l] + 2];
+  }
+  const float nsum = fabsf(nx) + fabsf(ny) + fabsf(nz);
+  const float d32 = fmaf(nx, xf, fmaf(ny, yf, nz * zf)) - pp;
+  const float bound = 1.0e-6f * fmaf(nsum, xinf, fabsf(pp));
+  bool ok = !(d32 > bound);
+  const float qx = xf - nx * d32, qy = yf - ny * d32, qz = zf - nz * d32;
+  float s = xinf + fabsf(d32);
+#pragma unroll
+  for (int l = 0; l < NEN; l++) s = fmaxf(s, fmaxf(fabsf(vx[l]), fmaxf(fabsf(vy[l]), fabsf(vz[l]))));
+#pragma unroll
+  for (int l = 0; l < NEN; l++) {
+    const int n = (l + 1 == NEN) ? 0 : l + 1;
+    const float ex = vx[n] - vx[l], ey = vy[n] - vy[l], ez = vz[n] - vz[l];
+    const float rx = qx - vx[l], ry = qy - vy[l], rz = qz - vz[l];
+    const float einf = fmaxf(fabsf(ex), fmaxf(fabsf(ey), fabsf(ez))), rinf = fmaxf(fabsf(rx), fmaxf(fabsf(ry), fabsf(rz)));
+    float crit, margin = 1.0e-5f * s * (einf + rinf);
+    if (D3) {
+      crit = (ey * rz - ez * ry) * nx + (ez * rx - ex * rz) * ny + (ex * ry - ey * rx) * nz;
+      margin *= fmaxf(nsum, 1.0f);
+    } else {
+      crit = ex * rx + ey * ry + ez * rz;
+    }
+    ok = ok && !(crit < -margin);
+  }
+  return ok;
+}
+
+template <bool D3>
+__global__ void __launch_bounds__(256) k_contact_exact(WfDev d, WfContact c, double dt, const int *__restrict__ cand_count,
+                                                       const int2 *__restrict__ cand) {
+  const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (w >= *cand_count) return;
+  const int2 cd = cand[w];
+  const int t = cd.x, i = c.ext_nodes[t];
   const V3 xi = node3(d, d.x, i);
+  const float xf = (float)xi.x, yf = (float)xi.y, zf = (float)xi.z;
+  const float xinf = fmaxf(fabsf(xf), fmaxf(fabsf(yf), fabsf(zf)));
+  int jhit = -1;
+  for (int j0 = cd.y & ~31; j0 < c.tm_ne && jhit < 0; j0 += 128) { // four facets per lane and trip
+    bool poss[4];
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+      const int j = min(j0 + 32 * q + lane, c.tm_ne - 1);
+      poss[q] = facet_possible32<D3>(c, xf, yf, zf, xinf, j) && (j0 + 32 * q + lane < c.tm_ne);
+    }
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+      V3 nj;
+      double dist;
+      const bool mine = poss[q] && facet_hit(c, xi, j0 + 32 * q + lane, nj, dist);
+      const unsigned any = __ballot_sync(0xffffffffu, mine);
+      if (any && jhit < 0) jhit = j0 + 32 * q + (__ffs(any) - 1);
+    }
+  }
+  if (lane == 0) contact_force(d, c, dt, t, i, xi, jhit);
+}
+
+// force on external node i (list index t) from facet jhit (< 0: no contact), Contact.C:141-309
+__device__ void contact_force(const WfDev &d, const WfContact &c, double dt, int t, int i, const V3 &xi, int jhit) {
   bool hit = false;
   Hit h;
   int mesh = -1;
-  for (int j = 0; j < c.tm_ne && !hit; j++) {
-    const V3 nj = ld3(c.tm_normal, j);
-    const double dist = dot(nj, xi) - c.tm_pplane[j];
-    if (!(dist < 0)) continue;
-    const V3 Qj = xi - nj * dist;
-    bool inside = true;
-    if (c.tm_dim == 3) {
-      for (int l = 0; l < 3 && inside; l++) {
-        const int n = (l + 1 > 2) ? 0 : l + 1;
-        const V3 nl = ld3(c.tm_node, c.tm_elnode[nen * j + l]);
-        const double crit = dot(cross(ld3(c.tm_node, c.tm_elnode[nen * j + n]) - nl, Qj - nl), nj);
-        if (crit < 0.0) inside = false;
-      }
-    } else {
-      for (int l = 0; l < 2 && inside; l++) {
-        const int n = (l + 1 > 1) ? 0 : l + 1;
-        const V3 nl = ld3(c.tm_node, c.tm_elnode[nen * j + l]);
-        const double crit = dot(ld3(c.tm_node, c.tm_elnode[nen * j + n]) - nl, Qj - nl);
-        if (crit < 0.0) inside = false;
-      }
-    }
-    if (!inside) continue;
+  if (jhit >= 0) {
+    const int j = jhit;
+    V3 nj;
+    double dist;
+    facet_hit(c, xi, j, nj, dist);
     hit = true;
     mesh = c.tm_mesh_id[j];
     const V3 v_rel = node3(d, d.v, i);
@@ -219,7 +352,6 @@ __global__ void __launch_bounds__(128) k_contact(WfDev d, WfContact c, const dou
     const V3 Fn = nj * dot(h.cf, nj);
     h.normFn = sqrt(Fn.x * Fn.x + Fn.y * Fn.y + Fn.z * Fn.z);
   }
-  (void)acc; // x_pred = x + v dt + a dt^2/2 only feeds quantities the reference computes and never uses (Contact.C:77-79, 236-238)
   c.mesh_in_contact[i] = mesh;
   if (d.dim == 3) {
     if (!hit) return;
@@ -383,7 +515,7 @@ extern "C" int wf_SearchExtNodes(wf_engine *E) {
   const size_t nv = (size_t)E->dim * d.np;
   if (dalloc(E, &C.nodlen, (size_t)C.n_ext) || dalloc(E, &C.node_area, (size_t)d.np) || dalloc(E, &C.ut_prev, nv) ||
       dalloc(E, &C.mesh_in_contact, (size_t)d.np) || dalloc(E, &C.xf_area, (size_t)n_xf) || dalloc(E, &C.elem_area, (size_t)d.ep) ||
-      dalloc(E, &C.rec, (size_t)10 * std::max(C.n_ext, 1)))
+      dalloc(E, &C.rec, (size_t)10 * std::max(C.n_ext, 1)) || dalloc(E, &C.cand_count, 1) || dalloc(E, &C.cand, (size_t)std::max(C.n_ext, 1)))
     return 1;
   k_fill_int<<<cdiv(d.np, 256), 256, 0, E->stream>>>(C.mesh_in_contact, (int)d.np, -1);
   if (calc_ext_face_areas(E)) return 1;
@@ -439,7 +571,7 @@ extern "C" int wf_set_contact(wf_engine *E, double mu_sta, double mu_dyn, double
   C.young = E->mat.E;
   E->end_t = end_time;
   if (!d.contforce && (dalloc(E, &d.contforce, (size_t)E->dim * d.np) || dalloc(E, &d.cflag, (size_t)d.np))) return 1;
-  k_trimesh_update<<<1, 256, 0, E->stream>>>(C, 1.0, 0.0, 0); // CalcSpheres -> UpdatePlaneCoeff with the initial normals
+  k_trimesh_update<<<1, 1024, 0, E->stream>>>(C, 1.0, 0.0, 0); // CalcSpheres -> UpdatePlaneCoeff with the initial normals
   E->contact = true;
   E->P.alpha_contact = E->stab.alpha_contact;
   E->P.hg_coeff_contact = E->stab.hg_coeff_contact;
@@ -483,7 +615,11 @@ int wf_contact_step_begin(wf_engine *E) {
 static int contact_forces(wf_engine *E, const double *acc) {
   WfContact &C = E->C;
   if (C.n_ext == 0) return 0;
-  k_contact<<<cdiv(C.n_ext, 128), 128, 0, E->stream>>>(E->d, C, acc, E->P.dt);
+  (void)acc; // x_pred = x + v dt + a dt^2/2 only feeds quantities the reference computes and never uses (Contact.C:77-79, 236-238)
+  CK(cudaMemsetAsync(C.cand_count, 0, sizeof(int), E->stream));
+  k_contact_filter<<<cdiv(C.n_ext, CONTACT_TPB), CONTACT_TPB, 0, E->stream>>>(E->d, C, E->P.dt, C.cand_count, C.cand);
+  if (E->dim == 3) k_contact_exact<true><<<cdiv((long long)C.n_ext * 32, 256), 256, 0, E->stream>>>(E->d, C, E->P.dt, C.cand_count, C.cand);
+  else k_contact_exact<false><<<cdiv((long long)C.n_ext * 32, 256), 256, 0, E->stream>>>(E->d, C, E->P.dt, C.cand_count, C.cand);
   if (E->dim == 2) {
     k_friction2d_chain<<<1, 1024, 0, E->stream>>>(C);
     k_friction2d_apply<<<cdiv(C.n_ext, 128), 128, 0, E->stream>>>(E->d, C);
@@ -497,7 +633,7 @@ int wf_contact_step_end(wf_engine *E) {
   const double RAMP_FRACTION = 1.0e-2; // Solver_explicit.C:309
   double f = 1.0;
   if (E->time < RAMP_FRACTION * E->end_t) f = pow(E->time / (RAMP_FRACTION * E->end_t), 0.5);
-  k_trimesh_update<<<1, 256, 0, E->stream>>>(E->C, f, E->P.dt, 1);
+  k_trimesh_update<<<1, 1024, 0, E->stream>>>(E->C, f, E->P.dt, 1);
   return 0;
 }
 

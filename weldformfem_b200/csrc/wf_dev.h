@@ -139,7 +139,9 @@ struct WfContact {
   double *node_area;                 /* [np] CalcExtFaceAreas */
   double *ut_prev;                   /* [dim][np + 32] accumulated tangential slip */
   int *mesh_in_contact;              /* [np] m_mesh_in_contact */
-  double *rec;                       /* [8][n_ext] 2D only: per-node records handed to the serial friction pass */
+  double *rec;                       /* [10][n_ext] 2D only: per-node records handed to the serial friction pass */
+  int *cand_count;                   /* [1] number of candidate nodes of this step's contact search */
+  int2 *cand;                        /* [n_ext] (external-node index, first facet not ruled out by the fp32 filter) */
   /* external faces in faceList order (= ascending element, then local face) */
   int n_xf, facenod;
   const int *xf_nodes;               /* [facenod][n_xf] */
