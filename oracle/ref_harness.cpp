@@ -118,6 +118,31 @@ class Harness : public Domain_d {
     zero_state();
   }
 
+  // ---- hooks for the reference's own front-end --------------------------------------------------------
+  // src/explicit/main.C is compiled UNMODIFIED at the end of this file with `Domain_d` spelled `Harness`, so that its
+  // `new Domain_d` creates this subclass and the three calls below resolve (by name hiding) to these wrappers: the two
+  // mesh builders add the zero-fill of malloc'ed state (as box() / mesh() above do), and the final
+  // `dom_d->SolveChungHulbert()` hands the fully set-up domain to the test instead of running the VTK-writing loop.
+  static Harness *&deck_captured() { static Harness *p = nullptr; return p; }
+  void AddBoxLength(double3 const &V, double3 const &L, const double &r, const bool &red_int = true, const bool &tritetra = false) {
+    MetFEM::Domain_d::AddBoxLength(V, L, r, red_int, tritetra);
+    zero_state();
+  }
+  void CreateFromLSDyna(LS_Dyna::lsdynaReader &reader) {
+    MetFEM::Domain_d::CreateFromLSDyna(reader);
+    zero_state();
+  }
+  void SolveChungHulbert() {
+    press_variant = m_press_algorithm == 1 ? 1 : 0;
+    deck_captured() = this;
+    // leave main.C by unwinding: renamed, its `int main` falls off the end without a return (fine for main, undefined
+    // for any other function)
+    throw DeckDone{};
+  }
+  struct DeckDone {};
+  double deck_dt() const { return dt; }
+  double deck_end_t() const { return end_t; }
+
   // src/explicit/main.C:460-581
   void material(double E, double nu, double rho0, int model, double sy0v, double K, double mexp) {
     CoutSilencer s; StdoutSilencer s2;
@@ -579,7 +604,7 @@ void wfref_solve_chung_hulbert(void *h, double dt, double end_t) {
   Harness *d = (Harness *)h;
   StdoutSilencer s2; CoutSilencer s;
   d->SetDT(dt); d->SetEndTime(end_t); d->setdtOut(1.0e10); d->setFixedDt(true);
-  d->SolveChungHulbert();
+  d->MetFEM::Domain_d::SolveChungHulbert();
 }
 int wfref_call(void *h, const char *fn, double arg) { return ((Harness *)h)->call(fn, arg); }
 long wfref_get(void *h, const char *name, void *dst, long cap) {
@@ -600,3 +625,47 @@ void wfref_consts(void *h, double *out) { ((Harness *)h)->consts(out); }
 void wfref_energies(void *h, double *ek, double *dei) { ((Harness *)h)->energies(ek, dei); }
 
 }  // extern "C"
+
+// ---- the reference's deck front-end: src/explicit/main.C, unmodified, with its Domain_d spelled Harness ------------
+// (`#include "Domain_d.h"` inside main.C is not macro-expanded and is include-guarded.)  main() becomes wf_ref_main().
+// NastranReader::read is declared `inline` in src/common/NastranReader.cpp:34, so its definition must be visible in the
+// translation unit that calls it (main.C:690, rigid bodies of type "File").
+#include "src/common/NastranReader.cpp"
+#define Domain_d Harness
+#define main wf_ref_main
+#include "src/explicit/main.C"
+#undef main
+#undef Domain_d
+
+extern "C" {
+// Run main.C on `deck` (path relative to the current directory, as the reference resolves `fileName` relative to it).
+// Returns the set-up domain (not initialised, not stepped) or NULL.  out[0] = dt chosen by main.C, out[1] = end time.
+void *wfref_load_deck(const char *deck, double *out) {
+  Harness::deck_captured() = nullptr;
+  const int threads = omp_get_max_threads();
+  char a0[] = "WeldFormFEM";
+  std::string d = deck;
+  char *argv[] = {a0, d.data(), nullptr};
+  std::streambuf *olderr = std::cerr.rdbuf();
+  try {
+    if (getenv("WF_REF_VERBOSE")) {
+      wf_ref_main(2, argv);
+    } else {
+      StdoutSilencer s2; CoutSilencer s;
+      std::cerr.rdbuf(nullptr);
+      wf_ref_main(2, argv);
+    }
+    Harness::deck_captured() = nullptr;  // main.C returned without reaching the solver call
+  } catch (const Harness::DeckDone &) {
+  } catch (const std::exception &e) {  // nlohmann::json parse / type errors
+    std::cerr.rdbuf(olderr);
+    fprintf(stderr, "wfref_load_deck: %s\n", e.what());
+    Harness::deck_captured() = nullptr;
+  }
+  std::cerr.rdbuf(olderr);
+  omp_set_num_threads(threads);  // main.C:338 sets it from "Nproc"
+  Harness *h = Harness::deck_captured();
+  if (h && out) { out[0] = h->deck_dt(); out[1] = h->deck_end_t(); }
+  return h;
+}
+}

@@ -276,6 +276,30 @@ class RefDomain(_Base):
             RefDomain._lib = self._load(REF_SO)
         super().__init__()
 
+    @classmethod
+    def from_deck(cls, deck_path):
+        """Set a domain up by running the reference's own front-end (src/explicit/main.C, compiled unmodified into the
+        harness) on a JSON deck; the process changes into the deck's directory for the call because main.C resolves
+        `fileName` and its `.out` log relative to the current directory.  Returns (domain, dt, end_time); the domain
+        still needs init(dt)."""
+        import os
+        cls._ensure()
+        lib = cls._lib
+        lib.wfref_load_deck.restype = C.c_void_p
+        lib.wfref_load_deck.argtypes = [C.c_char_p, C.POINTER(C.c_double)]
+        out = (C.c_double * 2)()
+        cwd = os.getcwd()
+        os.chdir(os.path.dirname(os.path.abspath(deck_path)))
+        try:
+            h = lib.wfref_load_deck(os.path.basename(deck_path).encode(), out)
+        finally:
+            os.chdir(cwd)
+        if not h:
+            raise RuntimeError("the reference front-end did not reach SolveChungHulbert for " + deck_path)
+        self = cls.__new__(cls)
+        self.h = h
+        return self, out[0], out[1]
+
 
 class OracleDomain(_Base):
     """The plain-C restatement (oracle/wf_oracle.c)."""

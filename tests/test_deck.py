@@ -1,0 +1,109 @@
+"""The deck front-end: host/wf_weldform + host/wf_deck.hpp run a WeldFormFEM JSON deck (+ LS-Dyna
+`.k` mesh) on the engine.  The checker is the reference's OWN front-end: src/explicit/main.C compiled unmodified into
+oracle/_ref/libwf_ref.so sets the domain up from the same deck (tests/golden/decks/), the harness steps it, and the
+result is committed as tests/golden/deck_*.npz (tests/golden/make_deck_golden.py).
+
+CPU tests: the fixtures still match the reference front-end (when oracle/_ref is built) and `wf_weldform --parse-only`
+finds the same mesh / BC / rigid-surface counts.  GPU tests: the state after N steps matches the fixture."""
+import json
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from parity_util import relerr
+from test_host_cpp import _read_dump, host_bins  # noqa: F401  (fixture)
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+DECKS = os.path.join(ROOT, "tests", "golden", "decks")
+PINNED = ["box_axiquad", "box_psquad", "file_tet_contact", "file_tet_zones", "box_axiquad_contact"]
+
+
+def _gold(name):
+    return np.load(os.path.join(ROOT, "tests", "golden", f"deck_{name}.npz"))
+
+
+def _summary(host_bins, deck, *extra):
+    r = subprocess.run([os.path.join(host_bins, "wf_weldform"), os.path.join(DECKS, deck + ".json"), *extra],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    return json.loads(r.stdout.strip().splitlines()[-1])
+
+
+@pytest.mark.parametrize("name", PINNED)
+def test_deck_fixture_is_what_the_reference_front_end_produces(oracle_ref, name):
+    """Pins the fixture: re-run main.C on the deck and compare bit for bit (skipped where oracle/_ref is not built)."""
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+    import make_deck_golden
+    oracle_ref.set_threads(1)
+    gold = _gold(name)
+    try:
+        got = make_deck_golden.run(name, int(gold["steps"][0]))
+    finally:
+        for f in os.listdir(DECKS):
+            if f.endswith(".out"):
+                os.remove(os.path.join(DECKS, f))
+    assert sorted(got) == sorted(gold.files)
+    for k in gold.files:
+        assert np.array_equal(np.asarray(got[k]), gold[k]), k
+
+
+@pytest.mark.parametrize("name", PINNED)
+def test_deck_parse_only_counts_match_reference(host_bins, name):
+    gold = _gold(name)
+    s = _summary(host_bins, name, "--parse-only")
+    dim, k, nn, ne, bcx, bcy, bcz, _ = [int(v) for v in gold["info"]]
+    assert (s["dim"], s["nodxelem"], s["nodes"], s["elements"]) == (dim, k, nn, ne)
+    assert s["bc_count"][:dim] == [bcx, bcy, bcz][:dim]
+    assert s["rigid_facets"] == int(gold["trimesh"][2])
+    assert s["contact"] == bool(gold["trimesh"][1] > 0)
+    assert s["end_time"] == float(gold["end_t"][0])
+
+
+def test_deck_k_reader_maps_sparse_ids_and_truncates_tets(host_bins):
+    """tet_block.k has ids 7, 10, 13, ... and 8-slot solids padded with the last node; hex_block.k is a plain hex file."""
+    s = _summary(host_bins, "file_tet_zones", "--parse-only")
+    assert (s["nodxelem"], s["nodes"], s["elements"]) == (4, 5 * 5 * 7, 5 * 4 * 4 * 6)
+    deck = {"Configuration": {"simTime": 1e-5}, "Materials": [{"type": "Bilinear", "const": [1e9], "density0": 7850.0,
+            "youngsModulus": 2e11, "poissonsRatio": 0.3, "yieldStress0": 3e8}],
+            "DomainBlocks": [{"type": "File", "fileName": "hex_block.k"}], "BoundaryConditions": []}
+    path = os.path.join(DECKS, "_tmp_hex.json")
+    with open(path, "w") as f:
+        json.dump(deck, f)
+    try:
+        s = _summary(host_bins, "_tmp_hex", "--parse-only")
+    finally:
+        os.remove(path)
+    assert (s["nodxelem"], s["nodes"], s["elements"]) == (8, 5 * 4 * 6, 4 * 3 * 5)
+
+
+def test_deck_errors_are_loud(host_bins, tmp_path):
+    bad = tmp_path / "bad.json"
+    bad.write_text('{"Configuration": {}, "Materials": [{"type": "Hollomon"}], "DomainBlocks": [{"type": "Sphere"}]}')
+    r = subprocess.run([os.path.join(host_bins, "wf_weldform"), str(bad), "--parse-only"], capture_output=True, text=True)
+    assert r.returncode == 1 and "File or Box" in r.stderr
+    bad.write_text('{"Configuration": {')
+    r = subprocess.run([os.path.join(host_bins, "wf_weldform"), str(bad), "--parse-only"], capture_output=True, text=True)
+    assert r.returncode == 1 and r.stderr.strip()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", PINNED)
+def test_deck_run_matches_reference_front_end(host_bins, tmp_path, name):
+    gold = _gold(name)
+    steps = int(gold["steps"][0])
+    dump = str(tmp_path / "d.bin")
+    s = _summary(host_bins, name, "--steps", str(steps), "--dump", dump, "--strict")
+    assert s["steps"] == steps
+    assert abs(s["dt"] - float(gold["dt"][0])) <= 1e-15 * float(gold["dt"][0]) * 4, (s["dt"], gold["dt"])
+    got = _read_dump(dump)
+    worst = {}
+    for key in gold.files:
+        if not key.startswith("sN_"):
+            continue
+        nm = key[3:]
+        worst[nm] = relerr(got[nm], gold[key])
+    bad = {k: v for k, v in worst.items() if not v <= 1e-8}
+    assert not bad, (name, bad, worst)
