@@ -75,6 +75,18 @@ struct WfDev {
   int blk_umax;                      /* longest unique list */
   const int *pos;                    /* [k][ep] offset of (e, ln) in fsell: dim*q - (dim-1)*(n&31), q = sell index */
   double *fsell, *fsell_hg;          /* [slice][j][dim][32] node-ordered element (and hourglass) forces */
+  /* tile-reduced forces (hexa, WF_FAST only; NULL when the mesh does not qualify): instead of one force record per
+   * element node, every WARP of the main element pass (32 consecutive elements = one "force tile") sums the
+   * contributions of its elements per UNIQUE node in shared memory — one round per local corner, each round a
+   * conflict-free read-modify-write, so the order of additions is fixed — and writes one partial per (tile, unique
+   * node): ftile[(tile*3 + c) * tf_stride + u], u = tf_idx[corner][e] = index of the node in the tile's ascending
+   * unique list.  Node n then adds its tile partials in ascending tile order: entry j of node n is
+   * tf_slots[tf_ptr[n >> 5] + 32*j + (n & 31)] = offset of component 0, ~0u = padding. */
+  double *ftile;
+  const long long *tf_ptr;           /* [nslices+1] */
+  const unsigned *tf_slots;
+  const unsigned char *tf_idx;       /* [k][ep] */
+  int tf_stride;                     /* longest unique list of a force tile, rounded up to a multiple of 4 */
   double *f_elem;                    /* [k*dim][ep]  (unfused path only) */
   double *f_elem_hg;                 /* [k*dim][ep]  (unfused path only) */
 

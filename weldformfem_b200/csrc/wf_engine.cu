@@ -204,6 +204,66 @@ static int upload_mesh(wf_engine *E, int nn, int ne, const double *x, const unsi
     CK(cudaMemcpyAsync(dl, lidx.data(), lidx.size() * sizeof(unsigned short), cudaMemcpyHostToDevice, E->stream));
     CK(cudaStreamSynchronize(E->stream));
     d.blk_off = doff; d.blk_nodes = dnodes; d.lidx = dl; d.blk_umax = umax;
+    // tile-reduced force path (WfDev::ftile; hexahedra): force tile = the 32 consecutive elements of one warp.
+    // Usable when inside every tile no two elements reference the same node through the same local corner, so
+    // that the accumulation rounds of the main pass are conflict-free.  Node n owns one entry per tile that
+    // references it, in ascending tile order.
+    d.ftile = nullptr; d.tf_ptr = nullptr; d.tf_slots = nullptr; d.tf_idx = nullptr; d.tf_stride = 0;
+    if (k == 8 && dim == 3) {
+      const int ntile = (ne + 31) / 32;
+      std::vector<unsigned char> tidx((size_t)k * d.ep, 0);
+      std::vector<int> toff((size_t)ntile + 1, 0), tnodes;
+      tnodes.reserve((size_t)ne * 5);
+      int wmax = 0;
+      bool ok = true;
+      std::vector<int> stamp(256, -1);
+      for (int w = 0; w < ntile && ok; w++) {
+        const int e0 = w * 32, e1 = std::min(ne, e0 + 32);
+        tmp.assign(elnod + (size_t)e0 * k, elnod + (size_t)e1 * k);
+        std::sort(tmp.begin(), tmp.end());
+        tmp.erase(std::unique(tmp.begin(), tmp.end()), tmp.end());
+        for (int n = 0; n < k && ok; n++)
+          for (int e = e0; e < e1; e++) {
+            const int u = (int)(std::lower_bound(tmp.begin(), tmp.end(), (int)elnod[(size_t)e * k + n]) - tmp.begin());
+            if (stamp[u] == w * k + n) { ok = false; break; }
+            stamp[u] = w * k + n;
+            tidx[(size_t)n * d.ep + e] = (unsigned char)u;
+          }
+        tnodes.insert(tnodes.end(), tmp.begin(), tmp.end());
+        toff[w + 1] = (int)tnodes.size();
+        wmax = std::max(wmax, (int)tmp.size());
+      }
+      const int stride = (wmax + 3) / 4 * 4;
+      ok = ok && (long long)ntile * 3 * stride < 4294967295LL;
+      if (ok) {
+        std::vector<int> cnt((size_t)nn, 0);
+        for (int g : tnodes) cnt[g]++;
+        const int nsl = d.nslices;
+        std::vector<long long> tptr((size_t)nsl + 1, 0);
+        for (int sl = 0; sl < nsl; sl++) {
+          int wd = 0;
+          for (int n = sl * 32; n < std::min(nn, sl * 32 + 32); n++) wd = std::max(wd, cnt[n]);
+          tptr[sl + 1] = tptr[sl] + 32LL * wd;
+        }
+        std::vector<unsigned> tslots((size_t)tptr[nsl], 0xFFFFFFFFu);
+        std::fill(cnt.begin(), cnt.end(), 0);
+        for (int w = 0; w < ntile; w++)
+          for (int i = toff[w]; i < toff[w + 1]; i++) {
+            const int g = tnodes[i];
+            tslots[(size_t)(tptr[g >> 5] + 32LL * cnt[g] + (g & 31))] = (unsigned)((long long)w * 3 * stride + (i - toff[w]));
+            cnt[g]++;
+          }
+        long long *dtp; unsigned *dts; unsigned char *dti;
+        if (dalloc(E, &dtp, tptr.size()) || dalloc(E, &dts, std::max<size_t>(tslots.size(), 1)) || dalloc(E, &dti, tidx.size()) ||
+            dalloc(E, &d.ftile, (size_t)ntile * 3 * stride))
+          return 1;
+        CK(cudaMemcpyAsync(dtp, tptr.data(), tptr.size() * sizeof(long long), cudaMemcpyHostToDevice, E->stream));
+        CK(cudaMemcpyAsync(dts, tslots.data(), tslots.size() * sizeof(unsigned), cudaMemcpyHostToDevice, E->stream));
+        CK(cudaMemcpyAsync(dti, tidx.data(), tidx.size(), cudaMemcpyHostToDevice, E->stream));
+        CK(cudaStreamSynchronize(E->stream));
+        d.tf_ptr = dtp; d.tf_slots = dts; d.tf_idx = dti; d.tf_stride = stride;
+      }
+    }
   }
   // state
   const size_t nv = (size_t)dim * d.np, e6 = (size_t)6 * d.ep;
@@ -1213,6 +1273,8 @@ extern "C" int wf_get_array(wf_engine *E, const char *name, void *dst, size_t by
     return 0;
   } else if (r.lazy_felem) {
     NEED(E->step_count > 0, "m_f_elem is available after a step");
+    NEED(!E->L->tile_forces(d, E->P, E->strict ? 1 : 0),
+         "m_f_elem is not kept by the tile-reduced force path; use the strict engine or wf_set_variant(2, 9)");
     std::vector<double> fs;
     if (download(E, r.hg ? d.fsell_hg : d.fsell, (size_t)dim * E->sell_total, fs)) return 1;
     for (int e2 = 0; e2 < ne; e2++)

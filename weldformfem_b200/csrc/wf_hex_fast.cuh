@@ -68,24 +68,44 @@ WF_DI void wht_fwd(const Src &src, int comp, double (&G)[3], double (&h)[4]) {
                     src(comp, 7), G, h);
 }
 
-// inverse butterfly: q_n = sum_r B[r] s_r(n) + sum_j c[j] Sig_j(n), stored to the node-ordered
-// force buffer at f[off[n] + 32*i] (component i of the entry of this element in node n's list)
-WF_DI void wht_inv_store(const double (&B)[3], const double (&c)[4], double *__restrict__ f, const unsigned (&off)[8], int i) {
+// inverse butterfly: q_n = sum_r B[r] s_r(n) + sum_j c[j] Sig_j(n) for the eight corners
+WF_DI void wht_inv8(const double (&B)[3], const double (&c)[4], double (&q)[8]) {
   const double SS1 = -B[2], SS2 = B[2];
   const double SD1 = B[1] - c[0], SD2 = B[1] + c[0];
   const double DS1 = B[0] - c[1], DS2 = B[0] + c[1];
   const double DD1 = c[2] - c[3], DD2 = c[2] + c[3];
   const double Sa = SS1 - SD1, Sb = SS1 + SD1, Da = DS1 - DD1, Db = DS1 + DD1;
   const double Sc = SS2 - SD2, Sd = SS2 + SD2, Dc = DS2 - DD2, Dd = DS2 + DD2;
-  f[(long long)off[0] + 32 * i] = Sa - Da;
-  f[(long long)off[1] + 32 * i] = Sa + Da;
-  f[(long long)off[2] + 32 * i] = Sb + Db;
-  f[(long long)off[3] + 32 * i] = Sb - Db;
-  f[(long long)off[4] + 32 * i] = Sc - Dc;
-  f[(long long)off[5] + 32 * i] = Sc + Dc;
-  f[(long long)off[6] + 32 * i] = Sd + Dd;
-  f[(long long)off[7] + 32 * i] = Sd - Dd;
+  q[0] = Sa - Da; q[1] = Sa + Da; q[2] = Sb + Db; q[3] = Sb - Db;
+  q[4] = Sc - Dc; q[5] = Sc + Dc; q[6] = Sd + Dd; q[7] = Sd - Dd;
 }
+// ... stored to the node-ordered force buffer at f[off[n] + 32*i] (component i of the entry of this element in
+// node n's list)
+WF_DI void wht_inv_store(const double (&B)[3], const double (&c)[4], double *__restrict__ f, const unsigned (&off)[8], int i) {
+  double q[8];
+  wht_inv8(B, c, q);
+#pragma unroll
+  for (int n = 0; n < 8; n++) f[(long long)off[n] + 32 * i] = q[n];
+}
+// the two ways the main pass hands nodal forces on: scattered into the node-ordered buffer (one record per element
+// node), or kept in registers for the tile reduction (k_elem_main_hex_tile)
+template <class OffT>
+struct EmitScatter {
+  double *__restrict__ f;
+  const OffT &off;
+  unsigned o8[8];
+  WF_DI void operator()(int i, const double (&B)[3], const double (&c)[4]) {
+    if (i == 0) {
+#pragma unroll
+      for (int n = 0; n < 8; n++) o8[n] = off(n);
+    }
+    wht_inv_store(B, c, f, o8, i);
+  }
+};
+struct EmitRegs {
+  double (&q)[3][8];
+  WF_DI void operator()(int i, const double (&B)[3], const double (&c)[4]) { wht_inv8(B, c, q[i]); }
+};
 
 // x^y for x > 0 as exp(y log x) (relative error ~1e-15; WF_FAST only)
 WF_DI double fast_pow(double x, double y) { return exp(y * log(x)); }
@@ -137,11 +157,11 @@ WF_DI void hex_front(const Src &src, HexFront &g) {
 }
 
 // ---- back half: pressure, Jaumann rate + J2 radial return, element + hourglass nodal forces --------------
-// J_sum = sum of nodal_p over the 8 nodes; p_prev = stored pressure (press == 1 only); off[n] = offset of
-// (e, n) in the node-ordered force buffer
-template <class OffT>
+// J_sum = sum of nodal_p over the 8 nodes; p_prev = stored pressure (press == 1 only); emit(i, B, c) receives the
+// Walsh coefficients of force component i (EmitScatter / EmitRegs)
+template <class Emit>
 WF_DI void hex_back(const WfDev &d, const WfPar &P, int e, bool active, const HexFront &g, const double (&tau)[6],
-                    double pl, double rho_e, double sy, double J_sum, double p_prev, const OffT &off) {
+                    double pl, double rho_e, double sy, double J_sum, double p_prev, Emit &&emit) {
   const double vol = g.detJ * 8.0;
   double p;
   if (P.press == 0) {
@@ -226,9 +246,6 @@ WF_DI void hex_back(const WfDev &d, const WfPar &P, int e, bool active, const He
   // element + hourglass nodal forces; symmetric sigma(c,i): (0,0)=0 (1,1)=1 (2,2)=2 (0,1)=3 (1,2)=4 (0,2)=5
   double ch = 0.0;
   if (P.hexa_hg != 0.0) ch = P.hexa_hg * fast_pow(vol, 0.6666666) * rho_e * 0.25 * P.cs0;
-  unsigned o8[8];
-#pragma unroll
-  for (int n = 0; n < 8; n++) o8[n] = off(n);
   const double w = 8.0;
 #pragma unroll
   for (int i = 0; i < 3; i++) {
@@ -240,7 +257,7 @@ WF_DI void hex_back(const WfDev &d, const WfPar &P, int e, bool active, const He
     for (int r = 0; r < 3; r++) B[r] = w * (g.A[0][r] * sxi + g.A[1][r] * syi + g.A[2][r] * szi);
 #pragma unroll
     for (int j = 0; j < 4; j++) c[j] = ch * g.hm[i][j];
-    wht_inv_store(B, c, d.fsell, o8, i);
+    emit(i, B, c);
   }
 }
 
@@ -281,8 +298,8 @@ __global__ void __launch_bounds__(TPB, 4) k_elem_main_hex_fast(WfDev d, WfPar P)
   cp_async_wait_all();
   HexFront g;
   hex_front(ColSrc{col}, g);
-  hex_back(d, P, e, active, g, tau, pl, rho_e, sy, J_sum, p_prev,
-           [&](int n) { return (unsigned)__ldg(d.pos + (long long)n * d.ep + e); });
+  auto off = [&](int n) { return (unsigned)__ldg(d.pos + (long long)n * d.ep + e); };
+  hex_back(d, P, e, active, g, tau, pl, rho_e, sy, J_sum, p_prev, EmitScatter<decltype(off)>{d.fsell, off});
 }
 
 // Persistent, software-pipelined variant: every CTA walks tiles blockIdx.x, += gridDim.x.  While a tile's
@@ -358,7 +375,8 @@ __global__ void __launch_bounds__(TPB, 4) k_elem_main_hex_pipe(WfDev d, WfPar P)
 #pragma unroll
     for (int a = 0; a < 8; a++) J_sum += jn[a];
     const unsigned *pb = posbuf + buf * 8 * TPB;
-    hex_back(d, P, e, active, g, tau, pl, rho_e, sy, J_sum, p_prev, [&](int n) { return pb[n * TPB]; });
+    auto off = [&](int n) { return pb[n * TPB]; };
+    hex_back(d, P, e, active, g, tau, pl, rho_e, sy, J_sum, p_prev, EmitScatter<decltype(off)>{d.fsell, off});
   }
 }
 
@@ -407,7 +425,100 @@ __global__ void __launch_bounds__(TPB, 4) k_elem_main_hex_staged(WfDev d, WfPar 
   double J_sum = 0.0;
 #pragma unroll
   for (int a = 0; a < 8; a++) J_sum += sm[6 * stride + src.li[a]];
-  hex_back(d, P, e, active, g, tau, pl, rho_e, sy, J_sum, p_prev, [&](int n) { return off[n]; });
+  auto offf = [&](int n) { return off[n]; };
+  hex_back(d, P, e, active, g, tau, pl, rho_e, sy, J_sum, p_prev, EmitScatter<decltype(offf)>{d.fsell, offf});
+}
+
+// Tile-reduced variant of the block-staged kernel (WfDev::ftile): the nodal forces of the 32 elements of a warp (one
+// "force tile") are summed per unique node in shared memory and ONE partial per (tile, unique node) goes to HBM,
+// instead of one record per element node (a 32-element row segment of a structured mesh has 132 unique nodes for
+// 256 element nodes, so the force traffic of E2 and N2 halves, and the scatter offsets `pos` are not read at all).
+// The sum is formed in rounds, one per (component, local corner): the host verified that within a tile no two
+// elements share a node at the same corner (always true on structured meshes), so every round is a conflict-free
+// read-modify-write separated by __syncwarp and the order of additions per node is fixed (corner 0 first ... corner
+// 7 last): deterministic, no atomics, no block-level barrier.
+struct EmitTile {
+  double *acc;       // [3][ws] accumulators of this warp
+  int ws;
+  const unsigned (&ri)[8];
+  unsigned amask;    // lanes that own an element
+  WF_DI void operator()(int i, const double (&B)[3], const double (&c)[4]) {
+    double q[8];
+    wht_inv8(B, c, q);
+    double *a = acc + i * ws;
+#pragma unroll
+    for (int n = 0; n < 8; n++) {
+      a[ri[n]] += q[n];
+      __syncwarp(amask);
+    }
+  }
+};
+
+template <int MINB>
+__global__ void __launch_bounds__(TPB, MINB) k_elem_main_hex_tile(WfDev d, WfPar P, int stride) {
+  extern __shared__ double sm[];
+  const int t = threadIdx.x;
+  const int b = blockIdx.x;
+  const int e0 = b * TPB + t;
+  const bool active = e0 < d.ne;
+  const int e = active ? e0 : d.ne - 1;
+  const unsigned amask = __ballot_sync(0xffffffffu, active);
+  // everything that does not depend on the node tables goes in flight first
+  StagedSrc src;
+  src.s = sm; src.stride = stride;
+#pragma unroll
+  for (int n = 0; n < 8; n++) src.li[n] = d.lidx[(long long)n * d.ep + e];
+  unsigned ri[8];
+#pragma unroll
+  for (int n = 0; n < 8; n++) ri[n] = d.tf_idx[(long long)n * d.ep + e];
+  double tau[6];
+#pragma unroll
+  for (int i = 0; i < 6; i++) tau[i] = d.tau[(long long)i * d.ep + e];
+  const double pl = d.pl_strain[e];
+  const double rho_e = d.rho[e];
+  const double sy = d.sigma_y[e];
+  double p_prev = 0.0;
+  if (P.press == 1) p_prev = d.p[e];
+  // stage the CTA's unique nodes: node ids of four rounds at a time, then their 7 values each
+  const int u0 = __ldg(d.blk_off + b), U = __ldg(d.blk_off + b + 1) - u0;
+  for (int i0 = 0; i0 < U; i0 += 4 * TPB) {
+    int g[4];
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+      const int i = i0 + q * TPB + t;
+      g[q] = (i < U) ? __ldg(d.blk_nodes + u0 + i) : -1;
+    }
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+      const int i = i0 + q * TPB + t;
+      if (g[q] >= 0) {
+#pragma unroll
+        for (int c = 0; c < 3; c++) cp_async8(sm + c * stride + i, d.x + (long long)c * d.np + g[q]);
+#pragma unroll
+        for (int c = 0; c < 3; c++) cp_async8(sm + (3 + c) * stride + i, d.v + (long long)c * d.np + g[q]);
+        cp_async8(sm + 6 * stride + i, d.nodal_p + g[q]);
+      }
+    }
+  }
+  cp_async_commit();
+  // this warp's accumulators
+  const int ws = d.tf_stride, lane = t & 31, warp = t >> 5;
+  double *acc = sm + 7 * stride + warp * 3 * ws;
+  for (int i = lane; i < 3 * ws; i += 32) acc[i] = 0.0;
+  cp_async_wait_all();
+  __syncthreads();
+  HexFront g;
+  hex_front(src, g);
+  double J_sum = 0.0;
+#pragma unroll
+  for (int a = 0; a < 8; a++) J_sum += sm[6 * stride + src.li[a]];
+  hex_back(d, P, e, active, g, tau, pl, rho_e, sy, J_sum, p_prev, EmitTile{acc, ws, ri, amask});
+  __syncwarp();
+  const long long tile = (long long)b * (TPB / 32) + warp;
+  if (tile * 32 < d.ne) {
+    double *__restrict__ out = d.ftile + tile * 3 * ws;
+    for (int i = lane; i < 3 * ws; i += 32) out[i] = acc[i];
+  }
 }
 
 // ---- memory skeleton of the hexa main pass (tuning aid only: same loads / stores, trivial arithmetic, results are

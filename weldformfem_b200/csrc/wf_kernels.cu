@@ -486,7 +486,20 @@ WF_DI void halo_node_sums(const WfDev &d, int n, const double *__restrict__ src,
     }
   }
 }
+// sum of the tile partials of node n (tile-reduced force path, WfDev::ftile), ascending tile order
+WF_DI void tile_node_force(const WfDev &d, int n, double (&fi)[3]) {
+  const long long base = d.tf_ptr[n >> 5];
+  const int width = (int)((d.tf_ptr[(n >> 5) + 1] - base) >> 5);
+  fi[0] = fi[1] = fi[2] = 0.0;
+  for (int j = 0; j < width; j++) {
+    const unsigned o = __ldg(d.tf_slots + base + ((long long)j << 5) + (n & 31));
+    if (o == 0xFFFFFFFFu) continue;
+#pragma unroll
+    for (int c = 0; c < 3; c++) fi[c] += d.ftile[(long long)o + (long long)c * d.tf_stride];
+  }
+}
 WF_DI void halo_node_force(const WfDev &d, int n, int sep, double (&fi)[3]) {
+  if (sep == 2) { tile_node_force(d, n, fi); return; }
   const long long base = d.sell_ptr[n >> 5];
   const int width = (int)((d.sell_ptr[(n >> 5) + 1] - base) >> 5);
   const int D = d.dim;
@@ -521,7 +534,7 @@ WF_DI double halo_total(const WfDev &d, int u, int comp, int parity, double own)
 //   phase 0 = everything;  phase 1 = sums only, to d.fi (lazy m_fi);  phase 2 = integrate from d.fi.
 // On a partitioned mesh the sums of shared nodes are completed with the neighbours' partials (halo_total).
 // ---------------------------------------------------------------------------------------------
-template <int D, bool SEPARATE_HG, int UNROLL>
+template <int D, bool SEPARATE_HG, int UNROLL, bool TILE_F = false>
 __global__ void __launch_bounds__(TPB_N) k_node_update(WfDev d, WfPar P, int fuse_predictor, int phase) {
   int n = blockIdx.x * blockDim.x + threadIdx.x;
   int slice = n >> 5;
@@ -530,7 +543,27 @@ __global__ void __launch_bounds__(TPB_N) k_node_update(WfDev d, WfPar P, int fus
   double fi[D];
 #pragma unroll
   for (int c = 0; c < D; c++) fi[c] = 0.0;
-  if (phase != 2) {
+  if (TILE_F && phase != 2) {
+    // tile-reduced forces: one partial per tile that touches the node, gathered through the tile-entry table
+    const long long base = d.tf_ptr[slice];
+    const int width = (int)((d.tf_ptr[slice + 1] - base) >> 5);
+    const unsigned *__restrict__ sl = d.tf_slots + base + lane;
+    const long long cs = d.tf_stride;
+    for (int j0 = 0; j0 < width; j0 += UNROLL) {
+      unsigned o[UNROLL];
+      double fv[UNROLL][D];
+#pragma unroll
+      for (int q = 0; q < UNROLL; q++) o[q] = (j0 + q < width) ? __ldg(sl + ((long long)(j0 + q) << 5)) : 0xFFFFFFFFu;
+#pragma unroll
+      for (int q = 0; q < UNROLL; q++)
+#pragma unroll
+        for (int c = 0; c < D; c++) fv[q][c] = (o[q] != 0xFFFFFFFFu) ? d.ftile[(long long)o[q] + c * cs] : 0.0;
+#pragma unroll
+      for (int q = 0; q < UNROLL; q++)
+#pragma unroll
+        for (int c = 0; c < D; c++) fi[c] += fv[q][c];
+    }
+  } else if (phase != 2) {
     const long long base = d.sell_ptr[slice];
     const int width = (int)((d.sell_ptr[slice + 1] - base) >> 5);
     const double *__restrict__ row = d.fsell + base * D + lane;
@@ -1232,7 +1265,20 @@ static void l_node_vol(const WfDev &d, const WfPar &P, int mode, cudaStream_t s)
     default: k_node_vol<3><<<g, TPB_N, 0, s>>>(d, P, mode); break;
   }
 }
+// the tile-reduced force path (WfDev::ftile): same eligibility as the regrouped hexa kernel, default variant only
+static int l_tile_forces(const WfDev &d, const WfPar &P, int separate_hg) {
+  return d.ftile && !separate_hg && d.k == 8 && d.dim == 3 && !P.strict && P.model < 2 && !P.thermal &&
+         (P.variant[2] == 0 || P.variant[2] == 5 || P.variant[2] == 6);
+}
 static void l_elem_main(const WfDev &d, const WfPar &P, int et, int separate_hg, cudaStream_t s) {
+  if (et == ET_HEX8 && l_tile_forces(d, P, separate_hg)) {
+    const int stride = (d.blk_umax + 31) / 32 * 32, g = cdiv(d.ne, hexfast::TPB);
+    const size_t smem = ((size_t)7 * stride + (size_t)(hexfast::TPB / 32) * 3 * d.tf_stride) * 8;
+    if (P.variant[2] == 5) hexfast::k_elem_main_hex_tile<5><<<g, hexfast::TPB, smem, s>>>(d, P, stride);
+    else if (P.variant[2] == 6) hexfast::k_elem_main_hex_tile<6><<<g, hexfast::TPB, smem, s>>>(d, P, stride);
+    else hexfast::k_elem_main_hex_tile<4><<<g, hexfast::TPB, smem, s>>>(d, P, stride);
+    return;
+  }
   // the regrouped hexa kernel inlines Bilinear / Hollomon; the rate-dependent laws (Johnson-Cook, GMT) take the generic kernel
   if (!separate_hg && et == ET_HEX8 && !P.strict && P.variant[2] != 1 && P.model < 2 && !P.thermal) {
     if (P.variant[2] >= 100) { // memory skeletons (tuning aid, garbage results)
@@ -1246,7 +1292,7 @@ static void l_elem_main(const WfDev &d, const WfPar &P, int et, int separate_hg,
       }
       return;
     }
-    if (P.variant[2] == 0) { // default: unique nodes of the CTA staged once in shared memory
+    if (P.variant[2] == 0 || P.variant[2] == 9) { // unique nodes of the CTA staged once in shared memory (9: without the tile reduction)
       const int stride = (d.blk_umax + 31) / 32 * 32;
       hexfast::k_elem_main_hex_staged<<<cdiv(d.ne, hexfast::TPB), hexfast::TPB, 7 * stride * 8, s>>>(d, P, stride);
       return;
@@ -1285,6 +1331,13 @@ static void node_update_t(const WfDev &d, const WfPar &P, int fuse, int phase, c
   else k_node_update<2, SEP, U><<<g, TPB_N, 0, s>>>(d, P, fuse, phase);
 }
 static void l_node_update(const WfDev &d, const WfPar &P, int separate_hg, int fuse, int phase, cudaStream_t s) {
+  if (l_tile_forces(d, P, separate_hg)) {
+    const int g = cdiv((long long)d.nslices * 32, TPB_N);
+    if (P.variant[3] == 1) k_node_update<3, false, 2, true><<<g, TPB_N, 0, s>>>(d, P, fuse, phase);
+    else if (P.variant[3] == 2) k_node_update<3, false, 8, true><<<g, TPB_N, 0, s>>>(d, P, fuse, phase);
+    else k_node_update<3, false, 4, true><<<g, TPB_N, 0, s>>>(d, P, fuse, phase);
+    return;
+  }
   if (separate_hg) node_update_t<true, 4>(d, P, fuse, phase, s);
   else if (P.variant[3] == 1) node_update_t<false, 2>(d, P, fuse, phase, s);
   else if (P.variant[3] == 2) node_update_t<false, 8>(d, P, fuse, phase, s);
@@ -1356,6 +1409,7 @@ static void l_u_corr_pos(const WfDev &d, const WfPar &P, cudaStream_t s) {
 static void l_halo_send(const WfDev &d, const WfPar &P, int mode, int sep, unsigned long long seq, int max_count, cudaStream_t s) {
   if (d.n_neigh <= 0) return;
   dim3 g(cdiv(max_count > 0 ? max_count : 1, 128), d.n_neigh);
+  if (mode == 2 && l_tile_forces(d, P, sep)) sep = 2; // partial force sums come from the tile partials
   if (mode == 0) k_halo_send<0><<<g, 128, 0, s>>>(d, P, sep, seq);
   else if (mode == 1) k_halo_send<1><<<g, 128, 0, s>>>(d, P, sep, seq);
   else k_halo_send<2><<<g, 128, 0, s>>>(d, P, sep, seq);
@@ -1405,6 +1459,11 @@ static void l_preload(int et, int dim, int k) {
   // staged hexa kernel: up to 7 arrays x (128 elements x 8 nodes) doubles of shared memory
   cudaFuncSetAttribute(hexfast::k_elem_main_hex_staged, cudaFuncAttributeMaxDynamicSharedMemorySize, 7 * 1024 * 8);
   touch(hexfast::k_elem_main_hex_staged);
+  cudaFuncSetAttribute(hexfast::k_elem_main_hex_tile<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (7 * 1024 + 12 * 256) * 8);
+  cudaFuncSetAttribute(hexfast::k_elem_main_hex_tile<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (7 * 1024 + 12 * 256) * 8);
+  cudaFuncSetAttribute(hexfast::k_elem_main_hex_tile<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (7 * 1024 + 12 * 256) * 8);
+  touch(hexfast::k_elem_main_hex_tile<4>); touch(hexfast::k_elem_main_hex_tile<5>); touch(hexfast::k_elem_main_hex_tile<6>);
+  touch(k_node_update<3, false, 2, true>); touch(k_node_update<3, false, 4, true>); touch(k_node_update<3, false, 8, true>);
   touch(k_predict<2>); touch(k_predict<3>); touch(k_impose_bc);
   ELEM_DISPATCH(et, touch(k_elem_vol<ET>); touch(k_elem_main<ET, true, false>); touch(k_elem_main<ET, false, false>);
                 cudaFuncSetAttribute(k_elem_main<ET, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 7 * 1024 * 8);
@@ -1437,6 +1496,6 @@ extern "C" const WfLaunch *WF_CAT(WF_NS, _table)() {
                              l_rebuild_sigma, l_energy, l_u_strain_rates, l_u_pressure, l_u_stress, l_u_artvisc,
                              l_u_forces, l_u_hourglass, l_u_nodal_vol, l_u_assembly, l_u_accel, l_u_corr_accvel,
                              l_u_axis, l_u_corr_pos, l_halo_send, l_halo_wait, l_halo_finish, l_preload, l_p_node, l_min_edge, l_max_vel, l_soa_to_aos,
-                             l_aos_to_soa, l_node_thermal};
+                             l_aos_to_soa, l_node_thermal, l_tile_forces};
   return &t;
 }

@@ -40,6 +40,7 @@ struct WfLaunch {
   void (*soa_to_aos)(const double *soa, long long pitch, int nc, long long n, double scale, double *aos, cudaStream_t);
   void (*aos_to_soa)(const double *aos, long long pitch, int nc, long long n, double *soa, cudaStream_t);
   void (*node_thermal)(const WfDev &, const WfPar &, cudaStream_t);
+  int (*tile_forces)(const WfDev &, const WfPar &, int separate_hg); /* does the step use WfDev::ftile instead of fsell? */
 };
 
 extern "C" const WfLaunch *wf_strict_table();
