@@ -73,6 +73,7 @@ struct WfDev {
   const int *blk_nodes;
   const unsigned short *lidx;        /* [k][ep] */
   int blk_umax;                      /* longest unique list */
+  const int *blk_pad;                /* [nblk][round32(blk_umax)] the same lists at a fixed pitch, -1 padded (no blk_off round trip) */
   const int *pos;                    /* [k][ep] offset of (e, ln) in fsell: dim*q - (dim-1)*(n&31), q = sell index */
   double *fsell, *fsell_hg;          /* [slice][j][dim][32] node-ordered element (and hourglass) forces */
   /* tile-reduced forces (hexa, WF_FAST only; NULL when the mesh does not qualify): instead of one force record per

@@ -204,6 +204,16 @@ static int upload_mesh(wf_engine *E, int nn, int ne, const double *x, const unsi
     CK(cudaMemcpyAsync(dl, lidx.data(), lidx.size() * sizeof(unsigned short), cudaMemcpyHostToDevice, E->stream));
     CK(cudaStreamSynchronize(E->stream));
     d.blk_off = doff; d.blk_nodes = dnodes; d.lidx = dl; d.blk_umax = umax;
+    {
+      const int pitch = (umax + 31) / 32 * 32;
+      std::vector<int> pad((size_t)nblk * pitch, -1);
+      for (int b = 0; b < nblk; b++) std::copy(bnodes.begin() + boff[b], bnodes.begin() + boff[b + 1], pad.begin() + (size_t)b * pitch);
+      int *dpad;
+      if (dalloc(E, &dpad, std::max<size_t>(pad.size(), 1))) return 1;
+      CK(cudaMemcpyAsync(dpad, pad.data(), pad.size() * sizeof(int), cudaMemcpyHostToDevice, E->stream));
+      CK(cudaStreamSynchronize(E->stream));
+      d.blk_pad = dpad;
+    }
     // tile-reduced force path (WfDev::ftile; hexahedra): force tile = the 32 consecutive elements of one warp.
     // Usable when inside every tile no two elements reference the same node through the same local corner, so
     // that the accumulation rounds of the main pass are conflict-free.  Node n owns one entry per tile that

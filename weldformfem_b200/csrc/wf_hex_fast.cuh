@@ -463,7 +463,16 @@ __global__ void __launch_bounds__(TPB, MINB) k_elem_main_hex_tile(WfDev d, WfPar
   const bool active = e0 < d.ne;
   const int e = active ? e0 : d.ne - 1;
   const unsigned amask = __ballot_sync(0xffffffffu, active);
-  // everything that does not depend on the node tables goes in flight first
+  // node ids of the CTA's unique nodes (fixed-pitch list, -1 padded): the only loads the gathers depend on go first
+  constexpr int NQ = 5;
+  const int *__restrict__ ids = d.blk_pad + (long long)b * stride;
+  int gid[NQ];
+#pragma unroll
+  for (int q = 0; q < NQ; q++) {
+    const int i = q * TPB + t;
+    gid[q] = (i < stride) ? __ldg(ids + i) : -1;
+  }
+  // streaming state and index loads, independent of the node tables
   StagedSrc src;
   src.s = sm; src.stride = stride;
 #pragma unroll
@@ -479,27 +488,19 @@ __global__ void __launch_bounds__(TPB, MINB) k_elem_main_hex_tile(WfDev d, WfPar
   const double sy = d.sigma_y[e];
   double p_prev = 0.0;
   if (P.press == 1) p_prev = d.p[e];
-  // stage the CTA's unique nodes: node ids of four rounds at a time, then their 7 values each
-  const int u0 = __ldg(d.blk_off + b), U = __ldg(d.blk_off + b + 1) - u0;
-  for (int i0 = 0; i0 < U; i0 += 4 * TPB) {
-    int g[4];
+  // stage x, v and the nodal ratio of every unique node
+  auto stage = [&](int i, int gq) {
+    if (gq >= 0) {
 #pragma unroll
-    for (int q = 0; q < 4; q++) {
-      const int i = i0 + q * TPB + t;
-      g[q] = (i < U) ? __ldg(d.blk_nodes + u0 + i) : -1;
+      for (int c = 0; c < 3; c++) cp_async8(sm + c * stride + i, d.x + (long long)c * d.np + gq);
+#pragma unroll
+      for (int c = 0; c < 3; c++) cp_async8(sm + (3 + c) * stride + i, d.v + (long long)c * d.np + gq);
+      cp_async8(sm + 6 * stride + i, d.nodal_p + gq);
     }
+  };
 #pragma unroll
-    for (int q = 0; q < 4; q++) {
-      const int i = i0 + q * TPB + t;
-      if (g[q] >= 0) {
-#pragma unroll
-        for (int c = 0; c < 3; c++) cp_async8(sm + c * stride + i, d.x + (long long)c * d.np + g[q]);
-#pragma unroll
-        for (int c = 0; c < 3; c++) cp_async8(sm + (3 + c) * stride + i, d.v + (long long)c * d.np + g[q]);
-        cp_async8(sm + 6 * stride + i, d.nodal_p + g[q]);
-      }
-    }
-  }
+  for (int q = 0; q < NQ; q++) stage(q * TPB + t, gid[q]);
+  for (int i = NQ * TPB + t; i < stride; i += TPB) stage(i, __ldg(ids + i)); // lists longer than NQ * TPB
   cp_async_commit();
   // this warp's accumulators
   const int ws = d.tf_stride, lane = t & 31, warp = t >> 5;
