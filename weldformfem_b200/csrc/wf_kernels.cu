@@ -546,35 +546,6 @@ __global__ void __launch_bounds__(TPB_N) k_node_update(WfDev d, WfPar P, int fus
   double fi[D];
 #pragma unroll
   for (int c = 0; c < D; c++) fi[c] = 0.0;
-  // the node's own state does not depend on the force sum: put those loads in flight before the gathers
-  const bool integrate = phase != 1 && n < d.nn;
-  double mass = 1.0, s_fe[D], s_cf[D], s_pa[D], s_v[D], s_udt[D], s_x[D], s_u[D], s_bc[D];
-  int bi = -1;
-  unsigned bm = 0u;
-  double xmin = 0.0;
-#pragma unroll
-  for (int c = 0; c < D; c++) s_fe[c] = s_cf[c] = s_pa[c] = s_v[c] = s_udt[c] = s_x[c] = s_u[c] = s_bc[c] = 0.0;
-  if (integrate) {
-    mass = d.mdiag[n];
-    bi = d.bc_index[n];
-#pragma unroll
-    for (int c = 0; c < D; c++) {
-      const long long i = (long long)c * d.np + n;
-      if (d.fe) s_fe[c] = d.fe[i];
-      if (d.contforce) s_cf[c] = d.contforce[i];
-      s_pa[c] = d.prev_a[i];
-      s_v[c] = d.v[i];
-      s_udt[c] = d.u_dt[i];
-      s_x[c] = d.x[i];
-      s_u[c] = d.u[i];
-    }
-    if (bi >= 0) {
-      bm = d.bc_mask[bi];
-#pragma unroll
-      for (int c = 0; c < D; c++) s_bc[c] = d.bc_vals[3 * bi + c];
-    }
-    if (d.domtype == 2) xmin = key_dbl(d.xmin_key[P.xmin_cur]);
-  }
   if (TILE_F && phase != 2) {
     // tile-reduced forces: one partial per tile that touches the node, gathered through the tile-entry table
     const long long base = d.tf_ptr[slice];
@@ -635,39 +606,46 @@ __global__ void __launch_bounds__(TPB_N) k_node_update(WfDev d, WfPar P, int fus
 #pragma unroll
     for (int c = 0; c < D; c++) fi[c] = d.fi[(long long)c * d.np + n];
   }
+  const double mass = d.mdiag[n];
   // non-finite scrub (Solver_explicit.C:779-784)
 #pragma unroll
   for (int c = 0; c < D; c++)
     if (!isfinite(fi[c])) { fi[c] = 0.0; *d.nonfinite = 1; }
 
+  int bi = d.bc_index[n];
+  unsigned bm = (bi >= 0) ? d.bc_mask[bi] : 0u;
   const double f = 1.0 / (1.0 - P.alpha);
   double a[D], v[D];
 #pragma unroll
   for (int c = 0; c < D; c++) {
-    a[c] = (s_fe[c] - fi[c]) / mass;
-    if (d.contforce) a[c] += s_cf[c] / mass; // calcAccel with contact, Mechanical.C:330-335
+    long long i = (long long)c * d.np + n;
+    double fe = d.fe ? d.fe[i] : 0.0;
+    a[c] = (fe - fi[c]) / mass;
+    if (d.contforce) a[c] += d.contforce[i] / mass; // calcAccel with contact, Mechanical.C:330-335
     if (bm & (1u << c)) a[c] = 0.0;
-    a[c] = f * (a[c] - P.alpha * s_pa[c]);
-    v[c] = s_v[c] + P.gamma * P.dt * a[c];
-    if (bm & (1u << c)) v[c] = s_bc[c];
+    double pa = d.prev_a[i];
+    a[c] = f * (a[c] - P.alpha * pa);
+    v[c] = d.v[i] + P.gamma * P.dt * a[c];
+    if (bm & (1u << c)) v[c] = d.bc_vals[3 * bi + c];
   }
-  double xr = s_x[0];
+  double xr = d.x[n];
   if (d.domtype == 2) {
+    double xmin = key_dbl(d.xmin_key[P.xmin_cur]);
     if (xr <= xmin + 1.e-6) { a[0] = 0.0; v[0] = 0.0; }
   }
 #pragma unroll
   for (int c = 0; c < D; c++) {
     long long i = (long long)c * d.np + n;
-    double udt = s_udt[c] + P.beta * P.dt * P.dt * a[c];
-    double xn = s_x[c] + udt;
+    double udt = d.u_dt[i] + P.beta * P.dt * P.dt * a[c];
+    double xn = d.x[i] + udt;
     d.x[i] = xn;
     if (c == 0) xr = xn;
     d.prev_a[i] = a[c];
-    d.u[i] = s_u[c] + udt;
+    d.u[i] = d.u[i] + udt;
     if (fuse_predictor) {
       d.u_dt[i] = P.dt * (v[c] + (0.5 - P.beta) * P.dt * a[c]);
       v[c] = v[c] + (1.0 - P.gamma) * P.dt * a[c];
-      if (bm & (1u << c)) v[c] = s_bc[c];
+      if (bm & (1u << c)) v[c] = d.bc_vals[3 * bi + c];
     } else {
       d.u_dt[i] = udt;
     }
