@@ -690,6 +690,18 @@ extern "C" int wf_init_phase(wf_engine *E, int phase, double dt) {
   return 0;
 }
 
+// flags of the node pass: bit 0 = also run the next step's predictor (every step of a batch but the last);
+// WF_FAST only: bit 1 = this step's u_dt was not stored by the previous (fused) step and is recomputed from v and
+// prev_a, bit 2 = do not store u_dt because the next step recomputes it (saves 48 B per node and step)
+static int fuse_flags(const wf_engine *E, bool last) {
+  int f = last ? 0 : 1;
+  if (!E->strict) {
+    if (E->predicted) f |= 2;
+    if (!last) f |= 4;
+  }
+  return f;
+}
+
 // one explicit step = stages 0..2 (Solver_explicit.C:524-978, rows 1-22)
 static int step_stage(wf_engine *E, int stage, bool last) {
   WfDev &d = E->d;
@@ -707,7 +719,7 @@ static int step_stage(wf_engine *E, int stage, bool last) {
     if (E->distributed) halo_send(E, 2);
   } else {
     if (wf_contact_forces(E)) return 1;          // CalcContactForces (Solver_explicit.C:769-770)
-    E->L->node_update(d, P, sep, last ? 0 : 1, 0, E->stream);
+    E->L->node_update(d, P, sep, fuse_flags(E, last), 0, E->stream);
     if (wf_contact_step_end(E)) return 1;        // rigid surfaces: ramp, Move, normals, plane coefficients (:981-1005)
     if (P.thermal) { E->L->node_thermal(d, P, E->stream); P.dtedt_cur ^= 1; }  // ThermalCalcs, node part (:1008-1012)
     E->predicted = !last;
@@ -787,7 +799,7 @@ extern "C" int wf_step_timed(wf_engine *E, int nsteps, float *ms) {
     E->L->node_vol(d, P, 1, E->stream); mark(2);
     E->L->elem_main(d, P, E->et, sep, E->stream); mark(3);
     if (wf_contact_forces(E)) return 1;
-    E->L->node_update(d, P, sep, last ? 0 : 1, 0, E->stream);
+    E->L->node_update(d, P, sep, fuse_flags(E, last), 0, E->stream);
     if (wf_contact_step_end(E)) return 1;
     if (P.thermal) { E->L->node_thermal(d, P, E->stream); P.dtedt_cur ^= 1; }
     mark(4);

@@ -454,8 +454,7 @@ struct EmitTile {
   }
 };
 
-template <int MINB>
-__global__ void __launch_bounds__(TPB, MINB) k_elem_main_hex_tile(WfDev d, WfPar P, int stride) {
+__global__ void __launch_bounds__(TPB, 4) k_elem_main_hex_tile(WfDev d, WfPar P, int stride) {
   extern __shared__ double sm[];
   const int t = threadIdx.x;
   const int b = blockIdx.x;

@@ -537,8 +537,10 @@ WF_DI double halo_total(const WfDev &d, int u, int comp, int parity, double own)
 //   phase 0 = everything;  phase 1 = sums only, to d.fi (lazy m_fi);  phase 2 = integrate from d.fi.
 // On a partitioned mesh the sums of shared nodes are completed with the neighbours' partials (halo_total).
 // ---------------------------------------------------------------------------------------------
-template <int D, bool SEPARATE_HG, int UNROLL, bool TILE_F = false>
-__global__ void __launch_bounds__(TPB_N) k_node_update(WfDev d, WfPar P, int fuse_predictor, int phase) {
+WF_DI void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+template <int D, bool SEPARATE_HG, int UNROLL, bool TILE_F = false, bool PREFETCH = false, int MINB = 1>
+__global__ void __launch_bounds__(TPB_N, MINB) k_node_update(WfDev d, WfPar P, int fuse_flags, int phase) {
+  const bool fuse_predictor = fuse_flags & 1, udt_recompute = fuse_flags & 2, udt_skip_store = fuse_flags & 4;
   int n = blockIdx.x * blockDim.x + threadIdx.x;
   int slice = n >> 5;
   if (slice >= d.nslices) return;
@@ -546,6 +548,17 @@ __global__ void __launch_bounds__(TPB_N) k_node_update(WfDev d, WfPar P, int fus
   double fi[D];
 #pragma unroll
   for (int c = 0; c < D; c++) fi[c] = 0.0;
+  if (PREFETCH && phase != 1 && n < d.nn) {
+    // the node's own state is needed only after the force sum: ask L2 for it now, without holding registers
+    // (loading it early instead costs 32 registers and a third of the occupancy: measured slower)
+    prefetch_l2(d.mdiag + n);
+#pragma unroll
+    for (int c = 0; c < D; c++) {
+      const long long i = (long long)c * d.np + n;
+      prefetch_l2(d.prev_a + i); prefetch_l2(d.v + i); prefetch_l2(d.x + i); prefetch_l2(d.u + i);
+      if (!udt_recompute) prefetch_l2(d.u_dt + i);
+    }
+  }
   if (TILE_F && phase != 2) {
     // tile-reduced forces: one partial per tile that touches the node, gathered through the tile-entry table
     const long long base = d.tf_ptr[slice];
@@ -615,7 +628,7 @@ __global__ void __launch_bounds__(TPB_N) k_node_update(WfDev d, WfPar P, int fus
   int bi = d.bc_index[n];
   unsigned bm = (bi >= 0) ? d.bc_mask[bi] : 0u;
   const double f = 1.0 / (1.0 - P.alpha);
-  double a[D], v[D];
+  double a[D], v[D], udt0[D];
 #pragma unroll
   for (int c = 0; c < D; c++) {
     long long i = (long long)c * d.np + n;
@@ -624,8 +637,12 @@ __global__ void __launch_bounds__(TPB_N) k_node_update(WfDev d, WfPar P, int fus
     if (d.contforce) a[c] += d.contforce[i] / mass; // calcAccel with contact, Mechanical.C:330-335
     if (bm & (1u << c)) a[c] = 0.0;
     double pa = d.prev_a[i];
+    const double vp = d.v[i];
+    // the fused predictor of the previous step formed u_dt = dt (v_c + (1/2 - beta) dt a) and v_p = v_c + (1 - gamma) dt a
+    // (a = 0 and v_p = v_c = the prescribed value on constrained components), hence u_dt = dt (v_p + (gamma - 1/2 - beta) dt a)
+    udt0[c] = udt_recompute ? P.dt * (vp + (P.gamma - 0.5 - P.beta) * P.dt * pa) : d.u_dt[i];
     a[c] = f * (a[c] - P.alpha * pa);
-    v[c] = d.v[i] + P.gamma * P.dt * a[c];
+    v[c] = vp + P.gamma * P.dt * a[c];
     if (bm & (1u << c)) v[c] = d.bc_vals[3 * bi + c];
   }
   double xr = d.x[n];
@@ -636,14 +653,14 @@ __global__ void __launch_bounds__(TPB_N) k_node_update(WfDev d, WfPar P, int fus
 #pragma unroll
   for (int c = 0; c < D; c++) {
     long long i = (long long)c * d.np + n;
-    double udt = d.u_dt[i] + P.beta * P.dt * P.dt * a[c];
+    double udt = udt0[c] + P.beta * P.dt * P.dt * a[c];
     double xn = d.x[i] + udt;
     d.x[i] = xn;
     if (c == 0) xr = xn;
     d.prev_a[i] = a[c];
     d.u[i] = d.u[i] + udt;
     if (fuse_predictor) {
-      d.u_dt[i] = P.dt * (v[c] + (0.5 - P.beta) * P.dt * a[c]);
+      if (!udt_skip_store) d.u_dt[i] = P.dt * (v[c] + (0.5 - P.beta) * P.dt * a[c]);
       v[c] = v[c] + (1.0 - P.gamma) * P.dt * a[c];
       if (bm & (1u << c)) v[c] = d.bc_vals[3 * bi + c];
     } else {
@@ -1271,15 +1288,13 @@ static void l_node_vol(const WfDev &d, const WfPar &P, int mode, cudaStream_t s)
 // the tile-reduced force path (WfDev::ftile): same eligibility as the regrouped hexa kernel, default variant only
 static int l_tile_forces(const WfDev &d, const WfPar &P, int separate_hg) {
   return d.ftile && !separate_hg && d.k == 8 && d.dim == 3 && !P.strict && P.model < 2 && !P.thermal &&
-         (P.variant[2] == 0 || P.variant[2] == 5 || P.variant[2] == 6);
+         P.variant[2] == 0;
 }
 static void l_elem_main(const WfDev &d, const WfPar &P, int et, int separate_hg, cudaStream_t s) {
   if (et == ET_HEX8 && l_tile_forces(d, P, separate_hg)) {
     const int stride = (d.blk_umax + 31) / 32 * 32, g = cdiv(d.ne, hexfast::TPB);
     const size_t smem = ((size_t)7 * stride + (size_t)(hexfast::TPB / 32) * 3 * d.tf_stride) * 8;
-    if (P.variant[2] == 5) hexfast::k_elem_main_hex_tile<5><<<g, hexfast::TPB, smem, s>>>(d, P, stride);
-    else if (P.variant[2] == 6) hexfast::k_elem_main_hex_tile<6><<<g, hexfast::TPB, smem, s>>>(d, P, stride);
-    else hexfast::k_elem_main_hex_tile<4><<<g, hexfast::TPB, smem, s>>>(d, P, stride);
+    hexfast::k_elem_main_hex_tile<<<g, hexfast::TPB, smem, s>>>(d, P, stride);
     return;
   }
   // the regrouped hexa kernel inlines Bilinear / Hollomon; the rate-dependent laws (Johnson-Cook, GMT) take the generic kernel
@@ -1327,24 +1342,27 @@ static void l_elem_main(const WfDev &d, const WfPar &P, int et, int separate_hg,
     else { ELEM_DISPATCH(et, k_elem_main<ET, false, false><<<cdiv(d.ne, TPB_E), TPB_E, 0, s>>>(d, P, 0)); }
   }
 }
-template <bool SEP, int U>
+template <bool SEP, int U, int MINB = 1>
 static void node_update_t(const WfDev &d, const WfPar &P, int fuse, int phase, cudaStream_t s) {
   int g = cdiv((long long)d.nslices * 32, TPB_N);
-  if (d.dim == 3) k_node_update<3, SEP, U><<<g, TPB_N, 0, s>>>(d, P, fuse, phase);
-  else k_node_update<2, SEP, U><<<g, TPB_N, 0, s>>>(d, P, fuse, phase);
+  if (d.dim == 3) k_node_update<3, SEP, U, false, false, MINB><<<g, TPB_N, 0, s>>>(d, P, fuse, phase);
+  else k_node_update<2, SEP, U, false, false, MINB><<<g, TPB_N, 0, s>>>(d, P, fuse, phase);
 }
 static void l_node_update(const WfDev &d, const WfPar &P, int separate_hg, int fuse, int phase, cudaStream_t s) {
   if (l_tile_forces(d, P, separate_hg)) {
     const int g = cdiv((long long)d.nslices * 32, TPB_N);
-    if (P.variant[3] == 1) k_node_update<3, false, 2, true><<<g, TPB_N, 0, s>>>(d, P, fuse, phase);
-    else if (P.variant[3] == 2) k_node_update<3, false, 8, true><<<g, TPB_N, 0, s>>>(d, P, fuse, phase);
-    else k_node_update<3, false, 4, true><<<g, TPB_N, 0, s>>>(d, P, fuse, phase);
+    // measured on 10M hexes (tools/kbench.py): 5 resident CTAs (48 registers) + L2 prefetch of the state rows 0.60 ms;
+    // 3 CTAs (67 registers) 0.66-0.75 ms; 6 CTAs (40 registers, spills) 0.61 ms; no prefetch 0.71 ms
+    if (P.variant[3] == 5) k_node_update<3, false, 4, true, false, 5><<<g, TPB_N, 0, s>>>(d, P, fuse, phase);
+    else if (P.variant[3] == 7) k_node_update<3, false, 4, true, true, 6><<<g, TPB_N, 0, s>>>(d, P, fuse, phase);
+    else k_node_update<3, false, 4, true, true, 5><<<g, TPB_N, 0, s>>>(d, P, fuse, phase);
     return;
   }
   if (separate_hg) node_update_t<true, 4>(d, P, fuse, phase, s);
   else if (P.variant[3] == 1) node_update_t<false, 2>(d, P, fuse, phase, s);
   else if (P.variant[3] == 2) node_update_t<false, 8>(d, P, fuse, phase, s);
-  else node_update_t<false, 4>(d, P, fuse, phase, s);
+  else if (P.variant[3] == 5) node_update_t<false, 4>(d, P, fuse, phase, s);
+  else node_update_t<false, 4, 5>(d, P, fuse, phase, s); // 48 registers: 5 resident CTAs
 }
 static void l_node_thermal(const WfDev &d, const WfPar &P, cudaStream_t s) {
   k_node_thermal<<<cdiv((long long)d.nslices * 32, TPB_N), TPB_N, 0, s>>>(d, P);
@@ -1462,11 +1480,9 @@ static void l_preload(int et, int dim, int k) {
   // staged hexa kernel: up to 7 arrays x (128 elements x 8 nodes) doubles of shared memory
   cudaFuncSetAttribute(hexfast::k_elem_main_hex_staged, cudaFuncAttributeMaxDynamicSharedMemorySize, 7 * 1024 * 8);
   touch(hexfast::k_elem_main_hex_staged);
-  cudaFuncSetAttribute(hexfast::k_elem_main_hex_tile<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (7 * 1024 + 12 * 256) * 8);
-  cudaFuncSetAttribute(hexfast::k_elem_main_hex_tile<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (7 * 1024 + 12 * 256) * 8);
-  cudaFuncSetAttribute(hexfast::k_elem_main_hex_tile<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (7 * 1024 + 12 * 256) * 8);
-  touch(hexfast::k_elem_main_hex_tile<4>); touch(hexfast::k_elem_main_hex_tile<5>); touch(hexfast::k_elem_main_hex_tile<6>);
-  touch(k_node_update<3, false, 2, true>); touch(k_node_update<3, false, 4, true>); touch(k_node_update<3, false, 8, true>);
+  cudaFuncSetAttribute(hexfast::k_elem_main_hex_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, (7 * 1024 + 12 * 256) * 8);
+  touch(hexfast::k_elem_main_hex_tile);
+  touch(k_node_update<3, false, 4, true, false, 5>); touch(k_node_update<3, false, 4, true, true, 6>); touch(k_node_update<3, false, 4, true, true, 5>);
   touch(k_predict<2>); touch(k_predict<3>); touch(k_impose_bc);
   ELEM_DISPATCH(et, touch(k_elem_vol<ET>); touch(k_elem_main<ET, true, false>); touch(k_elem_main<ET, false, false>);
                 cudaFuncSetAttribute(k_elem_main<ET, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 7 * 1024 * 8);
@@ -1480,8 +1496,8 @@ static void l_preload(int et, int dim, int k) {
   cudaFuncSetAttribute(hexfast::k_elem_main_hex_pipe, cudaFuncAttributeMaxDynamicSharedMemorySize, hexfast::PIPE_SMEM_BYTES);
   cudaFuncSetAttribute(hexfast::k_elem_main_hex_pipe, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
   touch(hexfast::k_elem_main_hex_pipe);
-  touch(k_node_update<3, true, 4>); touch(k_node_update<3, false, 4>); touch(k_node_update<3, false, 2>); touch(k_node_update<3, false, 8>);
-  touch(k_node_update<2, true, 4>); touch(k_node_update<2, false, 4>); touch(k_node_update<2, false, 2>); touch(k_node_update<2, false, 8>);
+  touch(k_node_update<3, true, 4>); touch(k_node_update<3, false, 4>); touch(k_node_update<3, false, 4, false, false, 5>); touch(k_node_update<3, false, 2>); touch(k_node_update<3, false, 8>);
+  touch(k_node_update<2, true, 4>); touch(k_node_update<2, false, 4>); touch(k_node_update<2, false, 4, false, false, 5>); touch(k_node_update<2, false, 2>); touch(k_node_update<2, false, 8>);
   touch(k_halo_send<0>); touch(k_halo_send<1>); touch(k_halo_send<2>); touch(k_halo_wait);
   touch(k_halo_finish<0>); touch(k_halo_finish<1>);
   touch(k_init_elem); touch(k_vol0_density); touch(k_xmin); touch(k_energy_kin<2>); touch(k_energy_kin<3>);
