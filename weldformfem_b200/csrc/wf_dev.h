@@ -86,7 +86,13 @@ struct WfDev {
   double *ftile;
   const long long *tf_ptr;           /* [nslices+1] */
   const unsigned *tf_slots;
-  const unsigned char *tf_idx;       /* [k][ep] */
+  const unsigned char *tf_idx;       /* [k][ep] (hexahedra) */
+  /* tetrahedra: corners of different elements of a tile DO share nodes, so the tile sum is pulled instead: every
+   * element drops its k*dim force values in shared memory and lane u adds up the entries of unique node u listed in
+   * the tile's incidence table (ascending element, then corner: a fixed order).  Table of tile w at
+   * tf_tab + w * tf_tpitch: ptr[tf_stride + 1] then inc[32 * k], all uint8; inc = local element * k + corner. */
+  const unsigned char *tf_tab;
+  int tf_tpitch;
   int tf_stride;                     /* longest unique list of a force tile, rounded up to a multiple of 4 */
   double *f_elem;                    /* [k*dim][ep]  (unfused path only) */
   double *f_elem_hg;                 /* [k*dim][ep]  (unfused path only) */

@@ -218,12 +218,13 @@ static int upload_mesh(wf_engine *E, int nn, int ne, const double *x, const unsi
     // Usable when inside every tile no two elements reference the same node through the same local corner, so
     // that the accumulation rounds of the main pass are conflict-free.  Node n owns one entry per tile that
     // references it, in ascending tile order.
-    d.ftile = nullptr; d.tf_ptr = nullptr; d.tf_slots = nullptr; d.tf_idx = nullptr; d.tf_stride = 0;
-    if (k == 8 && dim == 3) {
+    d.ftile = nullptr; d.tf_ptr = nullptr; d.tf_slots = nullptr; d.tf_idx = nullptr; d.tf_tab = nullptr;
+    d.tf_stride = 0; d.tf_tpitch = 0;
+    if ((k == 8 || k == 4) && dim == 3) {
       const int ntile = (ne + 31) / 32;
       std::vector<unsigned char> tidx((size_t)k * d.ep, 0);
       std::vector<int> toff((size_t)ntile + 1, 0), tnodes;
-      tnodes.reserve((size_t)ne * 5);
+      tnodes.reserve((size_t)ne * (k == 8 ? 5 : 1));
       int wmax = 0;
       bool ok = true;
       std::vector<int> stamp(256, -1);
@@ -235,8 +236,10 @@ static int upload_mesh(wf_engine *E, int nn, int ne, const double *x, const unsi
         for (int n = 0; n < k && ok; n++)
           for (int e = e0; e < e1; e++) {
             const int u = (int)(std::lower_bound(tmp.begin(), tmp.end(), (int)elnod[(size_t)e * k + n]) - tmp.begin());
-            if (stamp[u] == w * k + n) { ok = false; break; }
-            stamp[u] = w * k + n;
+            if (k == 8) { // hexahedra: conflict-free accumulation rounds required
+              if (stamp[u] == w * k + n) { ok = false; break; }
+              stamp[u] = w * k + n;
+            }
             tidx[(size_t)n * d.ep + e] = (unsigned char)u;
           }
         tnodes.insert(tnodes.end(), tmp.begin(), tmp.end());
@@ -263,15 +266,42 @@ static int upload_mesh(wf_engine *E, int nn, int ne, const double *x, const unsi
             tslots[(size_t)(tptr[g >> 5] + 32LL * cnt[g] + (g & 31))] = (unsigned)((long long)w * 3 * stride + (i - toff[w]));
             cnt[g]++;
           }
-        long long *dtp; unsigned *dts; unsigned char *dti;
-        if (dalloc(E, &dtp, tptr.size()) || dalloc(E, &dts, std::max<size_t>(tslots.size(), 1)) || dalloc(E, &dti, tidx.size()) ||
+        long long *dtp; unsigned *dts;
+        if (dalloc(E, &dtp, tptr.size()) || dalloc(E, &dts, std::max<size_t>(tslots.size(), 1)) ||
             dalloc(E, &d.ftile, (size_t)ntile * 3 * stride))
           return 1;
         CK(cudaMemcpyAsync(dtp, tptr.data(), tptr.size() * sizeof(long long), cudaMemcpyHostToDevice, E->stream));
         CK(cudaMemcpyAsync(dts, tslots.data(), tslots.size() * sizeof(unsigned), cudaMemcpyHostToDevice, E->stream));
-        CK(cudaMemcpyAsync(dti, tidx.data(), tidx.size(), cudaMemcpyHostToDevice, E->stream));
+        if (k == 8) {
+          unsigned char *dti;
+          if (dalloc(E, &dti, tidx.size())) return 1;
+          CK(cudaMemcpyAsync(dti, tidx.data(), tidx.size(), cudaMemcpyHostToDevice, E->stream));
+          d.tf_idx = dti;
+        } else { // incidence tables: ptr[stride + 1], inc[32 * k]
+          const int tpitch = (stride + 1 + 32 * k + 3) / 4 * 4;
+          std::vector<unsigned char> tab((size_t)ntile * tpitch, 0);
+          std::vector<int> c2((size_t)stride + 1);
+          for (int w = 0; w < ntile; w++) {
+            const int e0 = w * 32, e1 = std::min(ne, e0 + 32);
+            unsigned char *T = tab.data() + (size_t)w * tpitch;
+            std::fill(c2.begin(), c2.end(), 0);
+            for (int e = e0; e < e1; e++)
+              for (int n = 0; n < k; n++) c2[tidx[(size_t)n * d.ep + e] + 1]++;
+            for (int u = 0; u < stride; u++) c2[u + 1] += c2[u];
+            for (int u = 0; u <= stride; u++) T[u] = (unsigned char)c2[u];
+            for (int e = e0; e < e1; e++)      // ascending element, then corner
+              for (int n = 0; n < k; n++) {
+                const int u = tidx[(size_t)n * d.ep + e];
+                T[stride + 1 + c2[u]++] = (unsigned char)((e - e0) * k + n);
+              }
+          }
+          unsigned char *dtab;
+          if (dalloc(E, &dtab, tab.size())) return 1;
+          CK(cudaMemcpyAsync(dtab, tab.data(), tab.size(), cudaMemcpyHostToDevice, E->stream));
+          d.tf_tab = dtab; d.tf_tpitch = tpitch;
+        }
         CK(cudaStreamSynchronize(E->stream));
-        d.tf_ptr = dtp; d.tf_slots = dts; d.tf_idx = dti; d.tf_stride = stride;
+        d.tf_ptr = dtp; d.tf_slots = dts; d.tf_stride = stride;
       }
     }
   }

@@ -92,6 +92,8 @@ __global__ void k_impose_bc(WfDev d, int dim, int is_acc, double *a_or_v) {
 // ---------------------------------------------------------------------------------------------
 // E1: element volume from current coordinates
 // ---------------------------------------------------------------------------------------------
+WF_DI void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
 template <int ET>
 __global__ void __launch_bounds__(TPB_E) k_elem_vol(WfDev d, WfPar P, int store_jac) {
   constexpr int K = Elem<ET>::K, D = Elem<ET>::D;
@@ -295,7 +297,8 @@ WF_DI void gather_nodal_p(const WfDev &d, const int (&nid)[Elem<ET>::K], double 
 // mode bits: 1 = hourglass force kept separate in f_elem_hg (strict two-pass assembly)
 // STAGED: the CTA first loads x, v and the nodal ratio of its UNIQUE nodes into shared memory (WfDev::blk_off),
 // then every element reads its nodes through 16-bit block-local indices; otherwise every element gathers its own.
-template <int ET, bool SEPARATE_HG, bool STAGED, bool THERMAL = false>
+// TILE: tile-reduced forces (WfDev::ftile, pull form: see WfDev::tf_tab) instead of one record per element node
+template <int ET, bool SEPARATE_HG, bool STAGED, bool THERMAL = false, bool TILE = false>
 __global__ void __launch_bounds__(TPB_E) k_elem_main(WfDev d, WfPar P, int stride) {
   constexpr int K = Elem<ET>::K, D = Elem<ET>::D;
   static_assert(!(STAGED && THERMAL), "the thermal terms gather by global node id");
@@ -333,6 +336,10 @@ __global__ void __launch_bounds__(TPB_E) k_elem_main(WfDev d, WfPar P, int strid
     }
   } else {
     if (e >= d.ne) return;
+    if constexpr (TILE) { // the tile's incidence table is read at the very end: ask L2 for it now (one lane per 32 B sector)
+      const int lane = threadIdx.x & 31;
+      if (lane * 32 < d.tf_tpitch) prefetch_l2(d.tf_tab + (long long)(e >> 5) * d.tf_tpitch + lane * 32);
+    }
     load_conn<ET>(d, e, nid);
     gather_nodal<ET>(d.x, d.np, nid, xl);
     gather_nodal<ET>(d.v, d.np, nid, vl);
@@ -441,6 +448,41 @@ __global__ void __launch_bounds__(TPB_E) k_elem_main(WfDev d, WfPar P, int strid
 #pragma unroll
       for (int c = 0; c < D; c++) f[n][c] -= fh[n][c];
   }
+  if constexpr (TILE) {
+    static_assert(!SEPARATE_HG && !STAGED && !THERMAL, "tile-reduced forces: fused hourglass, per-element gathers only");
+    // the warp's 32 elements drop their nodal forces in shared memory; lane u then adds up, in the fixed order of
+    // the tile's incidence table, the entries of unique node u and writes ONE partial per (tile, node)
+    constexpr int KD = K * D;
+    const unsigned amask = __activemask(); // a tail tile has fewer than 32 elements (lanes 0 .. nact-1)
+    const int nact = __popc(amask), lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int ws = d.tf_stride, tp = d.tf_tpitch;
+    double *fb = sm + warp * (KD * 32 + (tp + 7) / 8);
+    unsigned char *tab = reinterpret_cast<unsigned char *>(fb + KD * 32);
+    const long long tile = e >> 5;
+    const unsigned *__restrict__ gt = reinterpret_cast<const unsigned *>(d.tf_tab + tile * tp);
+    for (int i = lane; i < tp / 4; i += nact) reinterpret_cast<unsigned *>(tab)[i] = __ldg(gt + i);
+#pragma unroll
+    for (int n = 0; n < K; n++)
+#pragma unroll
+      for (int c = 0; c < D; c++) fb[(n * D + c) * 32 + lane] = f[n][c];
+    __syncwarp(amask);
+    double *__restrict__ out = d.ftile + tile * D * ws;
+    for (int u = lane; u < ws; u += nact) {
+      const int q0 = tab[u], q1 = tab[u + 1];
+      double sacc[D];
+#pragma unroll
+      for (int c = 0; c < D; c++) sacc[c] = 0.0;
+      for (int q = q0; q < q1; q++) {
+        const int slot = tab[ws + 1 + q];
+        const double *src = fb + (slot % K) * D * 32 + slot / K;
+#pragma unroll
+        for (int c = 0; c < D; c++) sacc[c] += src[c * 32];
+      }
+#pragma unroll
+      for (int c = 0; c < D; c++) out[(long long)c * ws + u] = sacc[c];
+    }
+    return;
+  }
   // node-ordered stores: entry of (e, n) in the nodel list of its node
 #pragma unroll
   for (int n = 0; n < K; n++) {
@@ -537,7 +579,6 @@ WF_DI double halo_total(const WfDev &d, int u, int comp, int parity, double own)
 //   phase 0 = everything;  phase 1 = sums only, to d.fi (lazy m_fi);  phase 2 = integrate from d.fi.
 // On a partitioned mesh the sums of shared nodes are completed with the neighbours' partials (halo_total).
 // ---------------------------------------------------------------------------------------------
-WF_DI void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 template <int D, bool SEPARATE_HG, int UNROLL, bool TILE_F = false, bool PREFETCH = false, int MINB = 1>
 __global__ void __launch_bounds__(TPB_N, MINB) k_node_update(WfDev d, WfPar P, int fuse_flags, int phase) {
   const bool fuse_predictor = fuse_flags & 1, udt_recompute = fuse_flags & 2, udt_skip_store = fuse_flags & 4;
@@ -1287,8 +1328,8 @@ static void l_node_vol(const WfDev &d, const WfPar &P, int mode, cudaStream_t s)
 }
 // the tile-reduced force path (WfDev::ftile): same eligibility as the regrouped hexa kernel, default variant only
 static int l_tile_forces(const WfDev &d, const WfPar &P, int separate_hg) {
-  return d.ftile && !separate_hg && d.k == 8 && d.dim == 3 && !P.strict && P.model < 2 && !P.thermal &&
-         P.variant[2] == 0;
+  return d.ftile && !separate_hg && d.dim == 3 && !P.strict && !P.thermal && P.variant[2] == 0 &&
+         ((d.k == 8 && P.model < 2) || (d.k == 4 && d.tf_tab));
 }
 static void l_elem_main(const WfDev &d, const WfPar &P, int et, int separate_hg, cudaStream_t s) {
   if (et == ET_HEX8 && l_tile_forces(d, P, separate_hg)) {
@@ -1325,6 +1366,11 @@ static void l_elem_main(const WfDev &d, const WfPar &P, int et, int separate_hg,
     }
     // variant 1 is the strict-order generic kernel (below); anything else: per-thread cp.async columns
     hexfast::k_elem_main_hex_fast<<<cdiv(d.ne, hexfast::TPB), hexfast::TPB, hexfast::SMEM_BYTES, s>>>(d, P);
+    return;
+  }
+  if (et == ET_TET4 && l_tile_forces(d, P, separate_hg)) {
+    const size_t smem = (size_t)(TPB_E / 32) * (12 * 32 + (d.tf_tpitch + 7) / 8) * 8;
+    k_elem_main<ET_TET4, false, false, false, true><<<cdiv(d.ne, TPB_E), TPB_E, smem, s>>>(d, P, 0);
     return;
   }
   const int stride = (d.blk_umax + 31) / 32 * 32;
@@ -1481,7 +1527,7 @@ static void l_preload(int et, int dim, int k) {
   cudaFuncSetAttribute(hexfast::k_elem_main_hex_staged, cudaFuncAttributeMaxDynamicSharedMemorySize, 7 * 1024 * 8);
   touch(hexfast::k_elem_main_hex_staged);
   cudaFuncSetAttribute(hexfast::k_elem_main_hex_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, (7 * 1024 + 12 * 256) * 8);
-  touch(hexfast::k_elem_main_hex_tile);
+  touch(hexfast::k_elem_main_hex_tile); touch(k_elem_main<ET_TET4, false, false, false, true>);
   touch(k_node_update<3, false, 4, true, false, 5>); touch(k_node_update<3, false, 4, true, true, 6>); touch(k_node_update<3, false, 4, true, true, 5>);
   touch(k_predict<2>); touch(k_predict<3>); touch(k_impose_bc);
   ELEM_DISPATCH(et, touch(k_elem_vol<ET>); touch(k_elem_main<ET, true, false>); touch(k_elem_main<ET, false, false>);
