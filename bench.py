@@ -371,7 +371,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--kind", default="hex", choices=["hex", "tet", "quad"])
-    ap.add_argument("--n", type=int, default=215)
+    ap.add_argument("--n", "--size", dest="n", type=int, default=215,
+                    help="elements per side (use --size under torchrun, whose own parser grabs --n as a prefix of --nnodes)")
     ap.add_argument("--cpu-n", type=int, default=64)
     ap.add_argument("--preload", type=int, default=1200)
     ap.add_argument("--strict", action="store_true")
