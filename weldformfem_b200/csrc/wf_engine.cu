@@ -721,11 +721,13 @@ extern "C" int wf_init_phase(wf_engine *E, int phase, double dt) {
 }
 
 // flags of the node pass: bit 0 = also run the next step's predictor (every step of a batch but the last);
-// WF_FAST only: bit 1 = this step's u_dt was not stored by the previous (fused) step and is recomputed from v and
-// prev_a, bit 2 = do not store u_dt because the next step recomputes it (saves 48 B per node and step)
+// WF_FAST only: bit 1 = this step's u_dt was not stored by the previous (fused) step and is recomputed from v and prev_a,
+// bit 2 = do not store u_dt because the next step recomputes it (saves 48 B per node and step)
 static int fuse_flags(const wf_engine *E, bool last) {
   int f = last ? 0 : 1;
   if (!E->strict) {
+    // only a predictor fused into the PREVIOUS node pass may drop u_dt: the first predictor of a batch must store it,
+    // because prescribed velocities can change between batches (u_dt of a constrained component is dt * OLD value)
     if (E->predicted) f |= 2;
     if (!last) f |= 4;
   }
@@ -739,9 +741,11 @@ static int step_stage(wf_engine *E, int stage, bool last) {
   const int sep = E->strict ? 1 : 0;
   if (stage == 0) {
     if (wf_contact_step_begin(E)) return 1;      // CalcExtFaceAreas every 10th step (Solver_explicit.C:445-450)
-    if (!E->predicted) E->L->predict(d, P, 1, E->stream);
+    // the batch's first predictor: its own kernel (strict) or folded into the nodal-sum pass (fast)
+    const bool fold = !E->predicted && !E->strict;
+    if (!E->predicted && E->strict) E->L->predict(d, P, 1, E->stream);
     E->L->elem_vol(d, P, E->et, 0, E->stream);
-    E->L->node_vol(d, P, 1, E->stream);
+    E->L->node_vol(d, P, fold ? 3 : 1, E->stream);
     if (E->distributed) halo_send(E, 1);
   } else if (stage == 1) {
     if (E->distributed) E->L->halo_finish(d, P, 1, P.halo_parity, E->stream);
@@ -824,9 +828,10 @@ extern "C" int wf_step_timed(wf_engine *E, int nsteps, float *ms) {
   for (int s = 0; s < nsteps; s++) {
     const bool last = (s == nsteps - 1);
     if (wf_contact_step_begin(E)) return 1;
-    if (!E->predicted) { E->L->predict(d, P, 1, E->stream); mark(0); }
+    const bool fold = !E->predicted && !E->strict;
+    if (!E->predicted && E->strict) { E->L->predict(d, P, 1, E->stream); mark(0); }
     E->L->elem_vol(d, P, E->et, 0, E->stream); mark(1);
-    E->L->node_vol(d, P, 1, E->stream); mark(2);
+    E->L->node_vol(d, P, fold ? 3 : 1, E->stream); mark(2);
     E->L->elem_main(d, P, E->et, sep, E->stream); mark(3);
     if (wf_contact_forces(E)) return 1;
     E->L->node_update(d, P, sep, fuse_flags(E, last), 0, E->stream);

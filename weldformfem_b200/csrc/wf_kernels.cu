@@ -63,6 +63,22 @@ WF_DI void apply_bcv(const WfDev &d, int n, double (&v)[D]) {
   }
 }
 
+// UpdatePrediction + ImposeBCV of one node (same arithmetic as k_predict)
+template <int D>
+WF_DI void predict_node(const WfDev &d, const WfPar &P, int n) {
+  double v[D];
+#pragma unroll
+  for (int c = 0; c < D; c++) {
+    const long long i = (long long)c * d.np + n;
+    const double pa = d.prev_a[i], vv = d.v[i];
+    d.u_dt[i] = P.dt * (vv + (0.5 - P.beta) * P.dt * pa);
+    v[c] = vv + (1.0 - P.gamma) * P.dt * pa;
+  }
+  apply_bcv<D>(d, n, v);
+#pragma unroll
+  for (int c = 0; c < D; c++) d.v[(long long)c * d.np + n] = v[c];
+}
+
 template <int D>
 __global__ void __launch_bounds__(TPB_N) k_predict(WfDev d, WfPar P, int with_bc) {
   int n = blockIdx.x * blockDim.x + threadIdx.x;
@@ -166,8 +182,12 @@ __global__ void k_vol_from_detj(WfDev d) {
 // CalcNodalVol (Mechanical.C:1555-1572) and the node loops of calcElemPressure (:697-705),
 // calcElemPressureANP (:1228-1240), calcElemPressureANP_Nodal (:1262-1284).
 // ---------------------------------------------------------------------------------------------
+//   mode 3 (step)  : mode 1 + UpdatePrediction and ImposeBCV of the node (Domain_d.C:961-974): the first step of a
+//                    batch has no previous node pass to carry its predictor (WF_FAST; strict runs k_predict)
 template <int K>
-__global__ void __launch_bounds__(TPB_N) k_node_vol(WfDev d, WfPar P, int mode) {
+__global__ void __launch_bounds__(TPB_N) k_node_vol(WfDev d, WfPar P, int mode_in) {
+  const bool with_predict = mode_in == 3;
+  const int mode = with_predict ? 1 : mode_in;
   int n = blockIdx.x * blockDim.x + threadIdx.x;
   if (n == 0 && mode == 1 && d.xmin_key) d.xmin_key[P.xmin_cur ^ 1] = dbl_key(1000.0);
   int slice = n >> 5;
@@ -216,6 +236,9 @@ __global__ void __launch_bounds__(TPB_N) k_node_vol(WfDev d, WfPar P, int mode) 
     double v0 = v0n, pn = 0.0;
     if (v0 > 1e-12) { double Jn = sq / v0; pn = P.Kbulk * (1.0 - Jn); }
     d.nodal_p[n] = pn;
+  }
+  if (with_predict) {
+    if (d.dim == 3) predict_node<3>(d, P, n); else predict_node<2>(d, P, n);
   }
   // CalcNodalMassFromVol (Mechanical.C:1576-1601): mass = sum_e rho[e] * voln / count, voln = sum/k
   const double voln = s / (double)K;
