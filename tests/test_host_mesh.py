@@ -261,3 +261,111 @@ def test_axis_plane_mesh_matches_compiled_reference(oracle_ref):
     assert np.array_equal(np.concatenate(els).reshape(-1), r.get("trimesh.elnode"))
     assert np.array_equal(np.concatenate(ids), r.get("trimesh.ele_mesh_id"))
     assert np.array_equal(np.concatenate(vels).reshape(-1), r.get("trimesh.node_v"))
+
+
+# ---- force tiles of the tile-reduced force path (csrc/wf_mesh.cpp: wf_force_tiles_build) ----------------
+def _force_tiles_lib(nn, el):
+    import ctypes as C
+    from weldformfem_b200 import _lib
+    lib = _lib.load()
+    ne, k = el.shape
+    elc = np.ascontiguousarray(el, dtype=np.uint32)
+    up = elc.ctypes.data_as(C.POINTER(C.c_uint))
+    info = (C.c_longlong * 6)()
+    assert lib.wf_host_force_tiles(nn, ne, k, up, info, None, None, None, None) == 0
+    usable, ntile, stride, tpitch, nsl, nslots = list(info)
+    out = {"usable": bool(usable), "n_tiles": ntile, "stride": stride, "tpitch": tpitch}
+    if not usable:
+        return out
+    tidx = np.zeros(ne * k, dtype=np.uint8)
+    ptr = np.zeros(nsl + 1, dtype=np.int64)
+    slots = np.zeros(max(nslots, 1), dtype=np.uint32)
+    tab = np.zeros(max(ntile * tpitch, 1), dtype=np.uint8)
+    assert lib.wf_host_force_tiles(nn, ne, k, up, info, tidx.ctypes.data_as(C.POINTER(C.c_ubyte)),
+                                   ptr.ctypes.data_as(C.POINTER(C.c_longlong)), slots.ctypes.data_as(C.POINTER(C.c_uint)),
+                                   tab.ctypes.data_as(C.POINTER(C.c_ubyte)) if tpitch else None) == 0
+    out.update(tidx=tidx.reshape(ne, k), ptr=ptr, slots=slots[:nslots], tab=tab[:ntile * tpitch].reshape(ntile, -1) if tpitch else None)
+    return out
+
+
+def _force_tiles_numpy(nn, el):
+    """Restatement: tile w = elements [32w, 32w+32); unique nodes ascending; hexahedra need distinct nodes per corner
+    within a tile; node entries in ascending tile order, sliced-ELL over 32-node slices; tet incidence CSR."""
+    ne, k = el.shape
+    ntile = (ne + 31) // 32
+    uniq = [np.unique(el[32 * w:32 * w + 32]) for w in range(ntile)]
+    if k == 8:
+        for w in range(ntile):
+            blk = el[32 * w:32 * w + 32]
+            if any(len(np.unique(blk[:, n])) != len(blk) for n in range(k)):
+                return {"usable": False}
+    stride = (max(len(u) for u in uniq) + 3) // 4 * 4
+    tidx = np.vstack([np.searchsorted(uniq[w], el[32 * w:32 * w + 32]) for w in range(ntile)]).astype(np.uint8)
+    entries = [[] for _ in range(nn)]
+    for w in range(ntile):
+        for i, g in enumerate(uniq[w]):
+            entries[g].append(w * 3 * stride + i)
+    nsl = (nn + 31) // 32
+    ptr = np.zeros(nsl + 1, dtype=np.int64)
+    for s in range(nsl):
+        ptr[s + 1] = ptr[s] + 32 * max(len(entries[n]) for n in range(32 * s, min(nn, 32 * s + 32)))
+    slots = np.full(ptr[-1], 0xFFFFFFFF, dtype=np.uint32)
+    for n in range(nn):
+        for j, off in enumerate(entries[n]):
+            slots[ptr[n >> 5] + 32 * j + (n & 31)] = off
+    out = {"usable": True, "n_tiles": ntile, "stride": stride, "tidx": tidx, "ptr": ptr, "slots": slots, "tpitch": 0, "tab": None}
+    if k == 4:
+        tpitch = (stride + 1 + 32 * k + 3) // 4 * 4
+        tab = np.zeros((ntile, tpitch), dtype=np.uint8)
+        for w in range(ntile):
+            t = tidx[32 * w:32 * w + 32].ravel()                 # order: ascending element, then corner
+            order = np.argsort(t, kind="stable")
+            cnt = np.bincount(t, minlength=stride)
+            tab[w, 1:stride + 1] = np.cumsum(cnt)[:stride]
+            tab[w, stride + 1:stride + 1 + len(t)] = order
+        out.update(tpitch=tpitch, tab=tab)
+    return out
+
+
+@pytest.mark.parametrize("kind,n,shuffle", [("hex", (5, 4, 7), False), ("hex", (33, 2, 2), False), ("hex", (4, 4, 4), True),
+                                            ("tet", (3, 4, 5), False), ("tet", (4, 3, 3), True)])
+def test_force_tile_tables_bit_exact(kind, n, shuffle):
+    h = 0.01
+    L = [(q + 1e-6) * h for q in n]
+    dim, k, x, el = host_box((0.0, 0.0, 0.0), L, 0.5 * h, kind == "tet")
+    nn = len(x) // dim
+    el = el.reshape(-1, k).astype(np.int64)
+    if shuffle:
+        rng = np.random.default_rng(7)
+        el = rng.permutation(nn)[el][rng.permutation(len(el))]
+    got = _force_tiles_lib(nn, el)
+    want = _force_tiles_numpy(nn, el)
+    assert got["usable"] == want["usable"]
+    if kind == "hex":
+        # in a box mesh every node is corner n of exactly ONE element, so any element order is conflict-free ...
+        assert got["usable"]
+        # ... until elements are relabelled: the same hexahedra with every other one rotated about its axis
+        el2 = el.copy()
+        el2[1::2] = el2[1::2][:, [1, 2, 3, 0, 5, 6, 7, 4]]
+        g2, w2 = _force_tiles_lib(nn, el2), _force_tiles_numpy(nn, el2)
+        assert g2["usable"] == w2["usable"] and not g2["usable"]
+    if not want["usable"]:
+        return
+    assert (got["n_tiles"], got["stride"], got["tpitch"]) == (want["n_tiles"], want["stride"], want["tpitch"])
+    for nm in ("tidx", "ptr", "slots"):
+        assert np.array_equal(got[nm], want[nm]), nm
+    if kind == "tet":
+        assert np.array_equal(got["tab"], want["tab"])
+    # every element node is reachable: slot -> (tile, position) -> unique list -> node
+    ne, k = el.shape
+    cover = np.zeros(nn, dtype=np.int64)
+    valid = got["slots"][got["slots"] != 0xFFFFFFFF]
+    assert len(valid) == len(set(valid.tolist()))
+    for w in range(got["n_tiles"]):
+        cover[np.unique(el[32 * w:32 * w + 32])] += 1
+    per_node = np.zeros(nn, dtype=np.int64)
+    for n_ in range(nn):
+        base = got["ptr"][n_ >> 5]
+        width = (got["ptr"][(n_ >> 5) + 1] - base) // 32
+        per_node[n_] = sum(got["slots"][base + 32 * j + (n_ & 31)] != 0xFFFFFFFF for j in range(width))
+    assert np.array_equal(per_node, cover)

@@ -261,6 +261,8 @@ def test_renumbered_mesh_through_set_mesh(key, shuffle_elems, oracle_port):
     el1 = nperm[el]
     if shuffle_elems:
         el1 = el1[rng.permutation(len(el1))]
+        if key == "hex":   # rotate every other hexahedron about its zeta axis: corners now collide inside a tile
+            el1[1::2] = el1[1::2][:, [1, 2, 3, 0, 5, 6, 7, 4]]
     nodes, dims, vals = case.bc_arrays()
     nodes1 = nperm[nodes]
 
@@ -286,4 +288,4 @@ def test_renumbered_mesh_through_set_mesh(key, shuffle_elems, oracle_port):
     # and the renumbered run is the original run, renumbered (the physics does not depend on numbering)
     base, _ = run_pair(case, oracle_port, 60, False)
     xb = base.get("x").reshape(-1, 3)
-    assert relerr(eng.get("x").reshape(-1, 3)[nperm], xb) <= 1e-9
+    assert relerr(eng.get("x").reshape(-1, 3)[nperm], xb) <= 1e-8

@@ -43,7 +43,8 @@ DECLARED = (["wf_create", "wf_destroy", "wf_last_error", "wf_set_stream", "wf_ge
              "wf_halo_status", "wf_connect_all", "wf_init_all", "wf_step_all", "wf_halo_set_transport", "wf_halo_exchange_ptrs",
              "wf_host_box_counts", "wf_host_gen_box", "wf_host_nodel", "wf_version",
              "wf_set_trimesh", "wf_set_contact", "wf_get_trimesh_counts", "wf_host_ext_faces",
-             "wf_host_axis_plane_counts", "wf_host_axis_plane_mesh", "wf_set_thermal", "wf_set_contact_heat"]
+             "wf_host_axis_plane_counts", "wf_host_axis_plane_mesh", "wf_set_thermal", "wf_set_contact_heat",
+             "wf_host_force_tiles"]
             + ["wf_" + n for n in UNFUSED])
 
 
@@ -132,6 +133,8 @@ def load():
         "wf_set_contact_heat": (C.c_int, [vp, C.c_double, C.c_double]),
         "wf_host_ext_faces": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, up, C.POINTER(C.c_ubyte), ip, ip, ip, ip]),
         "wf_host_axis_plane_counts": (C.c_int, [C.c_int, C.c_int, ip, ip]),
+        "wf_host_force_tiles": (C.c_int, [C.c_int, C.c_int, C.c_int, up, C.POINTER(C.c_longlong), C.POINTER(C.c_ubyte),
+                                          C.POINTER(C.c_longlong), up, C.POINTER(C.c_ubyte)]),
         "wf_host_axis_plane_mesh": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, dp, dp, C.c_int, dp, ip, dp, ip]),
     }
     for n in UNFUSED:

@@ -214,94 +214,32 @@ static int upload_mesh(wf_engine *E, int nn, int ne, const double *x, const unsi
       CK(cudaStreamSynchronize(E->stream));
       d.blk_pad = dpad;
     }
-    // tile-reduced force path (WfDev::ftile; hexahedra): force tile = the 32 consecutive elements of one warp.
-    // Usable when inside every tile no two elements reference the same node through the same local corner, so
-    // that the accumulation rounds of the main pass are conflict-free.  Node n owns one entry per tile that
-    // references it, in ascending tile order.
+    // tile-reduced force path (WfDev::ftile): tables built on the host (wf_force_tiles_build, wf_mesh.cpp)
     d.ftile = nullptr; d.tf_ptr = nullptr; d.tf_slots = nullptr; d.tf_idx = nullptr; d.tf_tab = nullptr;
     d.tf_stride = 0; d.tf_tpitch = 0;
     if ((k == 8 || k == 4) && dim == 3) {
-      const int ntile = (ne + 31) / 32;
-      std::vector<unsigned char> tidx((size_t)k * d.ep, 0);
-      std::vector<int> toff((size_t)ntile + 1, 0), tnodes;
-      tnodes.reserve((size_t)ne * (k == 8 ? 5 : 1));
-      int wmax = 0;
-      bool ok = true;
-      std::vector<int> stamp(256, -1);
-      for (int w = 0; w < ntile && ok; w++) {
-        const int e0 = w * 32, e1 = std::min(ne, e0 + 32);
-        tmp.assign(elnod + (size_t)e0 * k, elnod + (size_t)e1 * k);
-        std::sort(tmp.begin(), tmp.end());
-        tmp.erase(std::unique(tmp.begin(), tmp.end()), tmp.end());
-        for (int n = 0; n < k && ok; n++)
-          for (int e = e0; e < e1; e++) {
-            const int u = (int)(std::lower_bound(tmp.begin(), tmp.end(), (int)elnod[(size_t)e * k + n]) - tmp.begin());
-            if (k == 8) { // hexahedra: conflict-free accumulation rounds required
-              if (stamp[u] == w * k + n) { ok = false; break; }
-              stamp[u] = w * k + n;
-            }
-            tidx[(size_t)n * d.ep + e] = (unsigned char)u;
-          }
-        tnodes.insert(tnodes.end(), tmp.begin(), tmp.end());
-        toff[w + 1] = (int)tnodes.size();
-        wmax = std::max(wmax, (int)tmp.size());
-      }
-      const int stride = (wmax + 3) / 4 * 4;
-      ok = ok && (long long)ntile * 3 * stride < 4294967295LL;
-      if (ok) {
-        std::vector<int> cnt((size_t)nn, 0);
-        for (int g : tnodes) cnt[g]++;
-        const int nsl = d.nslices;
-        std::vector<long long> tptr((size_t)nsl + 1, 0);
-        for (int sl = 0; sl < nsl; sl++) {
-          int wd = 0;
-          for (int n = sl * 32; n < std::min(nn, sl * 32 + 32); n++) wd = std::max(wd, cnt[n]);
-          tptr[sl + 1] = tptr[sl] + 32LL * wd;
-        }
-        std::vector<unsigned> tslots((size_t)tptr[nsl], 0xFFFFFFFFu);
-        std::fill(cnt.begin(), cnt.end(), 0);
-        for (int w = 0; w < ntile; w++)
-          for (int i = toff[w]; i < toff[w + 1]; i++) {
-            const int g = tnodes[i];
-            tslots[(size_t)(tptr[g >> 5] + 32LL * cnt[g] + (g & 31))] = (unsigned)((long long)w * 3 * stride + (i - toff[w]));
-            cnt[g]++;
-          }
+      WfForceTiles T;
+      wf_force_tiles_build(nn, ne, k, d.ep, elnod, T);
+      if (T.usable) {
         long long *dtp; unsigned *dts;
-        if (dalloc(E, &dtp, tptr.size()) || dalloc(E, &dts, std::max<size_t>(tslots.size(), 1)) ||
-            dalloc(E, &d.ftile, (size_t)ntile * 3 * stride))
+        if (dalloc(E, &dtp, T.ptr.size()) || dalloc(E, &dts, std::max<size_t>(T.slots.size(), 1)) ||
+            dalloc(E, &d.ftile, (size_t)T.n_tiles * 3 * T.stride))
           return 1;
-        CK(cudaMemcpyAsync(dtp, tptr.data(), tptr.size() * sizeof(long long), cudaMemcpyHostToDevice, E->stream));
-        CK(cudaMemcpyAsync(dts, tslots.data(), tslots.size() * sizeof(unsigned), cudaMemcpyHostToDevice, E->stream));
+        CK(cudaMemcpyAsync(dtp, T.ptr.data(), T.ptr.size() * sizeof(long long), cudaMemcpyHostToDevice, E->stream));
+        CK(cudaMemcpyAsync(dts, T.slots.data(), T.slots.size() * sizeof(unsigned), cudaMemcpyHostToDevice, E->stream));
         if (k == 8) {
           unsigned char *dti;
-          if (dalloc(E, &dti, tidx.size())) return 1;
-          CK(cudaMemcpyAsync(dti, tidx.data(), tidx.size(), cudaMemcpyHostToDevice, E->stream));
+          if (dalloc(E, &dti, T.tidx.size())) return 1;
+          CK(cudaMemcpyAsync(dti, T.tidx.data(), T.tidx.size(), cudaMemcpyHostToDevice, E->stream));
           d.tf_idx = dti;
-        } else { // incidence tables: ptr[stride + 1], inc[32 * k]
-          const int tpitch = (stride + 1 + 32 * k + 3) / 4 * 4;
-          std::vector<unsigned char> tab((size_t)ntile * tpitch, 0);
-          std::vector<int> c2((size_t)stride + 1);
-          for (int w = 0; w < ntile; w++) {
-            const int e0 = w * 32, e1 = std::min(ne, e0 + 32);
-            unsigned char *T = tab.data() + (size_t)w * tpitch;
-            std::fill(c2.begin(), c2.end(), 0);
-            for (int e = e0; e < e1; e++)
-              for (int n = 0; n < k; n++) c2[tidx[(size_t)n * d.ep + e] + 1]++;
-            for (int u = 0; u < stride; u++) c2[u + 1] += c2[u];
-            for (int u = 0; u <= stride; u++) T[u] = (unsigned char)c2[u];
-            for (int e = e0; e < e1; e++)      // ascending element, then corner
-              for (int n = 0; n < k; n++) {
-                const int u = tidx[(size_t)n * d.ep + e];
-                T[stride + 1 + c2[u]++] = (unsigned char)((e - e0) * k + n);
-              }
-          }
+        } else {
           unsigned char *dtab;
-          if (dalloc(E, &dtab, tab.size())) return 1;
-          CK(cudaMemcpyAsync(dtab, tab.data(), tab.size(), cudaMemcpyHostToDevice, E->stream));
-          d.tf_tab = dtab; d.tf_tpitch = tpitch;
+          if (dalloc(E, &dtab, T.tab.size())) return 1;
+          CK(cudaMemcpyAsync(dtab, T.tab.data(), T.tab.size(), cudaMemcpyHostToDevice, E->stream));
+          d.tf_tab = dtab; d.tf_tpitch = T.tpitch;
         }
         CK(cudaStreamSynchronize(E->stream));
-        d.tf_ptr = dtp; d.tf_slots = dts; d.tf_stride = stride;
+        d.tf_ptr = dtp; d.tf_slots = dts; d.tf_stride = T.stride;
       }
     }
   }

@@ -114,6 +114,106 @@ extern "C" int wf_host_nodel(int n_nodes, int n_elems, int k, const unsigned *el
   return 0;
 }
 
+// ---- force tiles of the tile-reduced force path (WfDev::ftile) ------------------------------------------------
+// Tile w = elements [32w, 32w+32) (one warp of the main element pass).  Per tile: the ascending list of its unique
+// nodes; tidx = position of every element node in that list.  Hexahedra accumulate in conflict-free rounds (one
+// per local corner), which requires that no two elements of a tile reference the same node through the same
+// corner; tetrahedra pull through an incidence table (CSR by unique node, entries ascending element then corner).
+// Node n owns one entry per tile that references it, ascending tile order: slots = tile*3*stride + position.
+void wf_force_tiles_build(int nn, int ne, int k, long long ep, const unsigned *elnod, WfForceTiles &T) {
+  T = WfForceTiles();
+  T.k = k;
+  if ((k != 8 && k != 4) || ne <= 0) return;
+  const int ntile = (ne + 31) / 32;
+  T.n_tiles = ntile;
+  T.tidx.assign((size_t)k * ep, 0);
+  std::vector<int> toff((size_t)ntile + 1, 0), tnodes, tmp;
+  tnodes.reserve((size_t)ne * (k == 8 ? 5 : 1));
+  int wmax = 0;
+  bool ok = true;
+  std::vector<int> stamp(256, -1);
+  for (int w = 0; w < ntile && ok; w++) {
+    const int e0 = w * 32, e1 = std::min(ne, e0 + 32);
+    tmp.assign(elnod + (size_t)e0 * k, elnod + (size_t)e1 * k);
+    std::sort(tmp.begin(), tmp.end());
+    tmp.erase(std::unique(tmp.begin(), tmp.end()), tmp.end());
+    for (int n = 0; n < k && ok; n++)
+      for (int e = e0; e < e1; e++) {
+        const int u = (int)(std::lower_bound(tmp.begin(), tmp.end(), (int)elnod[(size_t)e * k + n]) - tmp.begin());
+        if (k == 8) {
+          if (stamp[u] == w * k + n) { ok = false; break; }
+          stamp[u] = w * k + n;
+        }
+        T.tidx[(size_t)n * ep + e] = (unsigned char)u;
+      }
+    tnodes.insert(tnodes.end(), tmp.begin(), tmp.end());
+    toff[w + 1] = (int)tnodes.size();
+    wmax = std::max(wmax, (int)tmp.size());
+  }
+  const int stride = (wmax + 3) / 4 * 4;
+  ok = ok && (long long)ntile * 3 * stride < 4294967295LL;
+  if (!ok) return;
+  T.stride = stride;
+  std::vector<int> cnt((size_t)nn, 0);
+  for (int g : tnodes) cnt[g]++;
+  const int nsl = (nn + 31) / 32;
+  T.ptr.assign((size_t)nsl + 1, 0);
+  for (int sl = 0; sl < nsl; sl++) {
+    int wd = 0;
+    for (int n = sl * 32; n < std::min(nn, sl * 32 + 32); n++) wd = std::max(wd, cnt[n]);
+    T.ptr[sl + 1] = T.ptr[sl] + 32LL * wd;
+  }
+  T.slots.assign((size_t)T.ptr[nsl], 0xFFFFFFFFu);
+  std::fill(cnt.begin(), cnt.end(), 0);
+  for (int w = 0; w < ntile; w++)
+    for (int i = toff[w]; i < toff[w + 1]; i++) {
+      const int g = tnodes[i];
+      T.slots[(size_t)(T.ptr[g >> 5] + 32LL * cnt[g] + (g & 31))] = (unsigned)((long long)w * 3 * stride + (i - toff[w]));
+      cnt[g]++;
+    }
+  if (k == 4) {
+    const int tpitch = (stride + 1 + 32 * k + 3) / 4 * 4;
+    T.tpitch = tpitch;
+    T.tab.assign((size_t)ntile * tpitch, 0);
+    std::vector<int> c2((size_t)stride + 1);
+    for (int w = 0; w < ntile; w++) {
+      const int e0 = w * 32, e1 = std::min(ne, e0 + 32);
+      unsigned char *tb = T.tab.data() + (size_t)w * tpitch;
+      std::fill(c2.begin(), c2.end(), 0);
+      for (int e = e0; e < e1; e++)
+        for (int n = 0; n < k; n++) c2[T.tidx[(size_t)n * ep + e] + 1]++;
+      for (int u = 0; u < stride; u++) c2[u + 1] += c2[u];
+      for (int u = 0; u <= stride; u++) tb[u] = (unsigned char)c2[u];
+      for (int e = e0; e < e1; e++)
+        for (int n = 0; n < k; n++) {
+          const int u = T.tidx[(size_t)n * ep + e];
+          tb[stride + 1 + c2[u]++] = (unsigned char)((e - e0) * k + n);
+        }
+    }
+  }
+  T.usable = true;
+}
+
+// test-facing copy of the tables (no GPU needed).  First call with NULL buffers for the sizes:
+// info = {usable, n_tiles, stride, tpitch, n_slices, n_slot_entries}; tidx comes back as [e*k + ln].
+extern "C" int wf_host_force_tiles(int n_nodes, int n_elems, int k, const unsigned *elnod, long long *info,
+                                   unsigned char *tidx, long long *ptr, unsigned *slots, unsigned char *tab) {
+  for (long long i = 0; i < (long long)n_elems * k; i++)
+    if (elnod[i] >= (unsigned)n_nodes) return 1;
+  WfForceTiles T;
+  wf_force_tiles_build(n_nodes, n_elems, k, n_elems, elnod, T);
+  info[0] = T.usable ? 1 : 0; info[1] = T.n_tiles; info[2] = T.stride; info[3] = T.tpitch;
+  info[4] = (n_nodes + 31) / 32; info[5] = (long long)T.slots.size();
+  if (!T.usable) return 0;
+  if (tidx)
+    for (int e = 0; e < n_elems; e++)
+      for (int n = 0; n < k; n++) tidx[(size_t)e * k + n] = T.tidx[(size_t)n * n_elems + e];
+  if (ptr) std::copy(T.ptr.begin(), T.ptr.end(), ptr);
+  if (slots) std::copy(T.slots.begin(), T.slots.end(), slots);
+  if (tab) std::copy(T.tab.begin(), T.tab.end(), tab);
+  return 0;
+}
+
 // ---- canonical element-block partition + halo lists (the reference has none) ---------
 struct wf_partition {
   int nranks, rank, k;
