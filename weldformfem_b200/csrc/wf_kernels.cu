@@ -321,8 +321,8 @@ WF_DI void gather_nodal_p(const WfDev &d, const int (&nid)[Elem<ET>::K], double 
 // STAGED: the CTA first loads x, v and the nodal ratio of its UNIQUE nodes into shared memory (WfDev::blk_off),
 // then every element reads its nodes through 16-bit block-local indices; otherwise every element gathers its own.
 // TILE: tile-reduced forces (WfDev::ftile, pull form: see WfDev::tf_tab) instead of one record per element node
-template <int ET, bool SEPARATE_HG, bool STAGED, bool THERMAL = false, bool TILE = false>
-__global__ void __launch_bounds__(TPB_E) k_elem_main(WfDev d, WfPar P, int stride) {
+template <int ET, bool SEPARATE_HG, bool STAGED, bool THERMAL = false, bool TILE = false, int MINB = 1>
+__global__ void __launch_bounds__(TPB_E, MINB) k_elem_main(WfDev d, WfPar P, int stride) {
   constexpr int K = Elem<ET>::K, D = Elem<ET>::D;
   static_assert(!(STAGED && THERMAL), "the thermal terms gather by global node id");
   extern __shared__ double sm[];
@@ -1351,7 +1351,7 @@ static void l_node_vol(const WfDev &d, const WfPar &P, int mode, cudaStream_t s)
 }
 // the tile-reduced force path (WfDev::ftile): same eligibility as the regrouped hexa kernel, default variant only
 static int l_tile_forces(const WfDev &d, const WfPar &P, int separate_hg) {
-  return d.ftile && !separate_hg && d.dim == 3 && !P.strict && !P.thermal && P.variant[2] == 0 &&
+  return d.ftile && !separate_hg && d.dim == 3 && !P.strict && !P.thermal && (P.variant[2] == 0 || P.variant[2] == 6 || P.variant[2] == 7) &&
          ((d.k == 8 && P.model < 2) || (d.k == 4 && d.tf_tab));
 }
 static void l_elem_main(const WfDev &d, const WfPar &P, int et, int separate_hg, cudaStream_t s) {
@@ -1393,7 +1393,9 @@ static void l_elem_main(const WfDev &d, const WfPar &P, int et, int separate_hg,
   }
   if (et == ET_TET4 && l_tile_forces(d, P, separate_hg)) {
     const size_t smem = (size_t)(TPB_E / 32) * (12 * 32 + (d.tf_tpitch + 7) / 8) * 8;
-    k_elem_main<ET_TET4, false, false, false, true><<<cdiv(d.ne, TPB_E), TPB_E, smem, s>>>(d, P, 0);
+    if (P.variant[2] == 7) k_elem_main<ET_TET4, false, false, false, true><<<cdiv(d.ne, TPB_E), TPB_E, smem, s>>>(d, P, 0);
+    else if (P.variant[2] == 6) k_elem_main<ET_TET4, false, false, false, true, 6><<<cdiv(d.ne, TPB_E), TPB_E, smem, s>>>(d, P, 0);
+    else k_elem_main<ET_TET4, false, false, false, true, 5><<<cdiv(d.ne, TPB_E), TPB_E, smem, s>>>(d, P, 0);
     return;
   }
   const int stride = (d.blk_umax + 31) / 32 * 32;
@@ -1550,7 +1552,7 @@ static void l_preload(int et, int dim, int k) {
   cudaFuncSetAttribute(hexfast::k_elem_main_hex_staged, cudaFuncAttributeMaxDynamicSharedMemorySize, 7 * 1024 * 8);
   touch(hexfast::k_elem_main_hex_staged);
   cudaFuncSetAttribute(hexfast::k_elem_main_hex_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, (7 * 1024 + 12 * 256) * 8);
-  touch(hexfast::k_elem_main_hex_tile); touch(k_elem_main<ET_TET4, false, false, false, true>);
+  touch(hexfast::k_elem_main_hex_tile); touch(k_elem_main<ET_TET4, false, false, false, true>); touch(k_elem_main<ET_TET4, false, false, false, true, 5>); touch(k_elem_main<ET_TET4, false, false, false, true, 6>);
   touch(k_node_update<3, false, 4, true, false, 5>); touch(k_node_update<3, false, 4, true, true, 6>); touch(k_node_update<3, false, 4, true, true, 5>);
   touch(k_predict<2>); touch(k_predict<3>); touch(k_impose_bc);
   ELEM_DISPATCH(et, touch(k_elem_vol<ET>); touch(k_elem_main<ET, true, false>); touch(k_elem_main<ET, false, false>);
