@@ -162,6 +162,21 @@ class Domain_d {
     ck(wf_set_mesh(eng_, n_nodes, n_elems, x, elnod));
     fetchCounts();
   }
+  // Remesh hand-off (the engine-side half of ReMesher::WriteDomain, ReMesher.C:339): the current engine is dropped and
+  // a new one is created on the new mesh; material, stabilisation, options, contact surfaces and the clock carry
+  // over.  The caller then adds the boundary conditions of the new mesh (AddBCVelNode / AllocateBCs, SearchExtNodes
+  // when contact is on), calls InitSolve() and uploads the mapped fields with set(): "u" "v" "prev_a" ("T"),
+  // "m_tau" "pl_strain" "p" "sigma_y" "rho" "vol_0" — the arrays WriteDomain maps.  Uploading vol_0 / rho refreshes
+  // the nodal reference sums on the device.
+  void ReplaceMesh(int n_nodes, int n_elems, const double *x, const unsigned *elnod) {
+    if (!eng_) throw std::runtime_error("ReplaceMesh: no mesh to replace");
+    const int dim = dim_, k = nodxelem_;
+    carry_clock_ = true;  // InitSolve() hands Time / step_count to the new engine
+    wf_destroy(eng_);
+    eng_ = nullptr;
+    inited_ = false;
+    SetMesh(dim, k, n_nodes, n_elems, x, elnod);
+  }
   void setDensity(double rho) { rho0_ = rho; }  // Domain_d.C:951
   void setTemp(double T) { temp_ = T; }         // Domain_d::setTemp (uniform initial temperature, main.C:441)
   void setThermalOn() { m_thermal = true; }     // Domain_d.h:676
@@ -211,6 +226,7 @@ class Domain_d {
       ck(wf_calcMinEdgeLength(eng_, &ml, &mh));
     }
     ck(wf_init(eng_, dt_));
+    if (carry_clock_) { ck(wf_set_time(eng_, Time, step_count)); carry_clock_ = false; }
     inited_ = true;
   }
   // n fused steps (loop body, Solver_explicit.C:524-978)
@@ -325,6 +341,7 @@ class Domain_d {
   dom_type domtype_ = _3D_;
   bool vol_weight_ = false, strict_ = false, have_mat_ = false, inited_ = false;
   double rho0_ = 0.0, dt_ = 0.0, end_t_ = 0.0, hexa_hg_ = 0.0, temp_ = 20.0;
+  bool carry_clock_ = false;
   Material_ mat_;
 };
 

@@ -133,6 +133,9 @@ int wf_step(wf_engine *, int nsteps); /* fused rows 1-22 of the step, Solver_exp
 int wf_nonfinite_flag(wf_engine *, int *flag);
 int wf_energies(wf_engine *, double *Ekin, double *dEint); /* computeEnergies, Mechanical.C:2145 */
 int wf_get_time(wf_engine *, double *time, long *step_count);
+/* restart / remesh hand-off: continue the clock of a previous engine (Domain_d::Time, step_count; the velocity ramp of
+ * the rigid surfaces and the CalcExtFaceAreas cadence depend on them, Solver_explicit.C:309, :445-450) */
+int wf_set_time(wf_engine *, double time, long step_count);
 /* diagnostics computed on the device: calcMinEdgeLength (Domain_d.C:2224; also fills "m_elem_length"), max |v| and the
  * variable step of the explicit loop dt = cfl * min_length / (cs + max|v|) (Solver_explicit.C:579-598); wf_set_dt
  * applies a new step between batches ("p_node", calcNodalPressureFromElemental Mechanical.C:1187, is produced by

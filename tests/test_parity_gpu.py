@@ -289,3 +289,50 @@ def test_renumbered_mesh_through_set_mesh(key, shuffle_elems, oracle_port):
     base, _ = run_pair(case, oracle_port, 60, False)
     xb = base.get("x").reshape(-1, 3)
     assert relerr(eng.get("x").reshape(-1, 3)[nperm], xb) <= 1e-8
+
+
+@pytest.mark.parametrize("key", ["tet", "hex"])
+def test_remesh_handoff_new_engine_with_mapped_fields(key, oracle_port):
+    """SURVEY §8f-4, second half: after a remesh the reference swaps in a new mesh and the fields mapped onto it
+    (ReMesher::WriteDomain, ReMesher.C:339: u v prev_a, T; pl_strain p sigma_y tau rho vol_0) and goes on stepping.
+    Here the hand-off is a fresh engine + wf_set_array of the same fields.  The 'remesh' is a renumbering of nodes and
+    elements, for which the mapping is exact, so the continued run must follow the uninterrupted one."""
+    from weldformfem_b200.domain import Domain_d
+    case = SMALL[key]
+    a, _ = run_pair(case, oracle_port, 0, False)
+    a.step(40)
+    k = case.nodxelem
+    el = a.get("m_elnod").reshape(-1, k).astype(np.int64)
+    rng = np.random.default_rng(99)
+    nperm = rng.permutation(case.n_nodes)        # new id of old node i
+    eperm = rng.permutation(len(el))             # new element j = old element eperm[j]
+
+    def nodal(arr, c):
+        out = np.empty_like(arr.reshape(-1, c))
+        out[nperm] = arr.reshape(-1, c)
+        return out.ravel()
+
+    def elem(arr, c):
+        return arr.reshape(-1, c)[eperm].ravel()
+
+    b = Domain_d(strict=False)
+    b.set_mesh(3, k, nodal(a.get("x"), 3), nperm[el][eperm].ravel().astype(np.int32))   # the CURRENT configuration
+    b.set_material(case.E, case.nu, case.rho0, case.model, case.sy0, case.K, case.m)
+    b.set_stab(**case.stab)
+    b.set_options(case.press, case.av[0], case.av[1], case.hexa_hg)
+    nodes, dims, vals = case.bc_arrays()
+    b.add_bcs(nperm[nodes].astype(np.int32), dims, vals)
+    b.allocate_bcs()
+    b.init(case.timestep)
+    b.set_time(*a.time())
+    for nm, c in (("u", 3), ("v", 3), ("prev_a", 3)):
+        b.set(nm, nodal(a.get(nm), c))
+    for nm, c in (("m_tau", 6), ("pl_strain", 1), ("p", 1), ("sigma_y", 1), ("rho", 1), ("vol_0", 1)):
+        b.set(nm, elem(a.get(nm), c))
+    a.step(30)
+    b.step(30)
+    assert b.time()[1] == a.time()[1] == 70 and abs(b.time()[0] - a.time()[0]) <= 1e-15
+    for nm, c in (("x", 3), ("v", 3), ("u", 3)):
+        assert relerr(b.get(nm).reshape(-1, c)[nperm], a.get(nm).reshape(-1, c)) <= 1e-9, nm
+    for nm, c in (("m_tau", 6), ("pl_strain", 1), ("p", 1)):
+        assert relerr(b.get(nm).reshape(-1, c), a.get(nm).reshape(-1, c)[eperm]) <= 1e-8, nm

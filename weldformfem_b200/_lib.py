@@ -34,7 +34,7 @@ UNFUSED = ("UpdatePrediction calcElemJAndDerivatives Calc_Element_Radius CalcEle
 DECLARED = (["wf_create", "wf_destroy", "wf_last_error", "wf_set_stream", "wf_get_stream", "wf_synchronize", "wf_set_mesh", "wf_gen_box",
              "wf_get_counts", "wf_set_axisymm_vol_weight", "wf_set_material", "wf_set_stab", "wf_set_options",
              "wf_set_tracking", "wf_add_bc_vel", "wf_add_bc_vel_array", "wf_allocate_bcs", "wf_set_bc_values", "wf_init", "wf_step",
-             "wf_nonfinite_flag", "wf_energies", "wf_monitor_async", "wf_monitor_wait", "wf_calcMinEdgeLength", "wf_max_velocity", "wf_cfl_dt", "wf_set_dt", "wf_get_time", "wf_step_timed", "wf_set_variant", "wf_ImposeBCV", "wf_ImposeBCA", "wf_CalcStressStrain",
+             "wf_nonfinite_flag", "wf_energies", "wf_monitor_async", "wf_monitor_wait", "wf_calcMinEdgeLength", "wf_max_velocity", "wf_cfl_dt", "wf_set_dt", "wf_get_time", "wf_set_time", "wf_step_timed", "wf_set_variant", "wf_ImposeBCV", "wf_ImposeBCA", "wf_CalcStressStrain",
              "wf_get_array", "wf_set_array", "wf_array_bytes", "wf_device_ptr", "wf_partition_build",
              "wf_partition_build_box", "wf_partition_free", "wf_partition_info", "wf_partition_node_l2g",
              "wf_partition_local_elnod", "wf_partition_neigh_ranks", "wf_partition_halo_offset",
@@ -93,6 +93,7 @@ def load():
         "wf_monitor_async": (C.c_int, [vp]),
         "wf_monitor_wait": (C.c_int, [vp, dp, ip]),
         "wf_get_time": (C.c_int, [vp, dp, C.POINTER(C.c_long)]),
+        "wf_set_time": (C.c_int, [vp, C.c_double, C.c_long]),
         "wf_ImposeBCV": (C.c_int, [vp, C.c_int]),
         "wf_ImposeBCA": (C.c_int, [vp, C.c_int]),
         "wf_CalcStressStrain": (C.c_int, [vp, C.c_double]),

@@ -1061,6 +1061,15 @@ extern "C" int wf_nonfinite_flag(wf_engine *E, int *flag) {
   return 0;
 }
 
+extern "C" int wf_set_time(wf_engine *E, double t, long steps) {
+  NEED(E->inited, "wf_set_time after wf_init");
+  NEED(!E->predicted, "engine is mid-batch");
+  NEED(t >= 0.0 && steps >= 0, "negative time or step count");
+  E->time = t;
+  E->step_count = steps;
+  return 0;
+}
+
 extern "C" int wf_get_time(wf_engine *E, double *t, long *steps) {
   if (t) *t = E->time;
   if (steps) *steps = E->step_count;
@@ -1381,6 +1390,14 @@ extern "C" int wf_set_array(wf_engine *E, const char *name, const void *src, siz
     if (check_launch(E, "wf_set_array")) return 1;
   }
   if (wf_contact_after_set(E, nm)) return 1;
+  if ((nm == "vol_0" || nm == "rho") && E->inited) {
+    // remesh hand-off (ReMesher::WriteDomain maps vol_0 and rho onto the new mesh): the nodal reference sums
+    // (sum vol_0, mean rho, Solver_explicit.C:262) follow the uploaded element values
+    NEED(!E->distributed, "vol_0 / rho can only be replaced on a single-GPU engine");
+    E->L->node_vol(d, E->P, 0, E->stream);
+    CK(cudaStreamSynchronize(E->stream));
+    if (check_launch(E, "nodal reference sums")) return 1;
+  }
   if (nm == "x" && E->domtype == WF_AXISYMM && E->inited) {
     if (reset_xmin(E, E->P.xmin_cur)) return 1;
     E->L->xmin(d, E->P.xmin_cur, E->stream);

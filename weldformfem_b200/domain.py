@@ -336,6 +336,10 @@ class Domain_d:
         self._ck(self._lib.wf_get_time(self._h, C.byref(t), C.byref(n)))
         return t.value, n.value
 
+    def set_time(self, time, step_count):
+        """Continue the clock of a previous engine (restart / remesh hand-off)."""
+        self._ck(self._lib.wf_set_time(self._h, float(time), int(step_count)))
+
     # ---- state ------------------------------------------------------------------------------------
     def counts(self):
         a, b, c = C.c_int(), C.c_int(), C.c_int()
