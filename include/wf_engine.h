@@ -251,13 +251,13 @@ int wf_host_ext_faces(int dim, int nodxelem, int n_nodes, int n_elems, const uns
 int wf_host_axis_plane_counts(int dimension, int dens, int *n_nodes, int *n_elems);
 int wf_host_axis_plane_mesh(int dimension, int mesh_id, int axis, int positaxisorent, const double p1[3], const double p2[3],
                             int dens, double *node, int *elnode, double *normal, int *ele_mesh_id);
-/* Tables of the tile-reduced force path (tile = 32 consecutive elements, hexahedra / tetrahedra): call
- * with NULL buffers for info = {usable, n_tiles, stride, tpitch, n_slices, n_slot_entries}, then with buffers
+/* Tables of the tile-reduced force path (tile = 32 consecutive elements): call
+ * with NULL buffers for info[7] = {usable, n_tiles, stride, tpitch, n_slices, n_slot_entries, rounds}, then with buffers
  * tidx[n_elems*k] (position of (e, ln) in its tile's ascending unique-node list), ptr[n_slices+1] / slots[n_slot_entries]
- * (sliced-ELL of the tile entries of every node: tile*3*stride + position, ascending tile, ~0u padding) and, for
- * tetrahedra, tab[n_tiles*tpitch] (per-tile incidence: ptr[stride+1] then inc[32k], uint8).  Integer artefacts: the
+ * (sliced-ELL of the tile entries of every node: tile*dim*stride + position, ascending tile, ~0u padding) and, for
+ * every element type but the hexahedron, tab[n_tiles*tpitch] (per-tile incidence: ptr[stride+1] then inc[32k], uint8).  Integer artefacts: the
  * tests compare them bit for bit with a numpy restatement. */
-int wf_host_force_tiles(int n_nodes, int n_elems, int nodxelem, const unsigned *elnod, long long *info,
+int wf_host_force_tiles(int n_nodes, int n_elems, int nodxelem, int dim, const unsigned *elnod, long long *info,
                         unsigned char *tidx, long long *ptr, unsigned *slots, unsigned char *tab);
 const char *wf_version(void);
 

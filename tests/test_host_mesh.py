@@ -264,47 +264,46 @@ def test_axis_plane_mesh_matches_compiled_reference(oracle_ref):
 
 
 # ---- force tiles of the tile-reduced force path (csrc/wf_mesh.cpp: wf_force_tiles_build) ----------------
-def _force_tiles_lib(nn, el):
+def _force_tiles_lib(nn, el, dim=3):
     import ctypes as C
     from weldformfem_b200 import _lib
     lib = _lib.load()
     ne, k = el.shape
     elc = np.ascontiguousarray(el, dtype=np.uint32)
     up = elc.ctypes.data_as(C.POINTER(C.c_uint))
-    info = (C.c_longlong * 6)()
-    assert lib.wf_host_force_tiles(nn, ne, k, up, info, None, None, None, None) == 0
-    usable, ntile, stride, tpitch, nsl, nslots = list(info)
-    out = {"usable": bool(usable), "n_tiles": ntile, "stride": stride, "tpitch": tpitch}
+    info = (C.c_longlong * 7)()
+    assert lib.wf_host_force_tiles(nn, ne, k, dim, up, info, None, None, None, None) == 0
+    usable, ntile, stride, tpitch, nsl, nslots, rounds = list(info)
+    out = {"usable": bool(usable), "n_tiles": ntile, "stride": stride, "tpitch": tpitch, "rounds": bool(rounds)}
     if not usable:
         return out
     tidx = np.zeros(ne * k, dtype=np.uint8)
     ptr = np.zeros(nsl + 1, dtype=np.int64)
     slots = np.zeros(max(nslots, 1), dtype=np.uint32)
     tab = np.zeros(max(ntile * tpitch, 1), dtype=np.uint8)
-    assert lib.wf_host_force_tiles(nn, ne, k, up, info, tidx.ctypes.data_as(C.POINTER(C.c_ubyte)),
+    assert lib.wf_host_force_tiles(nn, ne, k, dim, up, info, tidx.ctypes.data_as(C.POINTER(C.c_ubyte)),
                                    ptr.ctypes.data_as(C.POINTER(C.c_longlong)), slots.ctypes.data_as(C.POINTER(C.c_uint)),
                                    tab.ctypes.data_as(C.POINTER(C.c_ubyte)) if tpitch else None) == 0
     out.update(tidx=tidx.reshape(ne, k), ptr=ptr, slots=slots[:nslots], tab=tab[:ntile * tpitch].reshape(ntile, -1) if tpitch else None)
     return out
 
 
-def _force_tiles_numpy(nn, el):
+def _force_tiles_numpy(nn, el, dim=3):
     """Restatement: tile w = elements [32w, 32w+32); unique nodes ascending; hexahedra need distinct nodes per corner
     within a tile; node entries in ascending tile order, sliced-ELL over 32-node slices; tet incidence CSR."""
     ne, k = el.shape
     ntile = (ne + 31) // 32
     uniq = [np.unique(el[32 * w:32 * w + 32]) for w in range(ntile)]
-    if k == 8:
-        for w in range(ntile):
-            blk = el[32 * w:32 * w + 32]
-            if any(len(np.unique(blk[:, n])) != len(blk) for n in range(k)):
-                return {"usable": False}
+    hexa = k == 8
+    rounds = all(len(np.unique(el[32 * w:32 * w + 32][:, n])) == len(el[32 * w:32 * w + 32]) for w in range(ntile) for n in range(k))
+    if hexa and not rounds:
+        return {"usable": False}
     stride = (max(len(u) for u in uniq) + 3) // 4 * 4
     tidx = np.vstack([np.searchsorted(uniq[w], el[32 * w:32 * w + 32]) for w in range(ntile)]).astype(np.uint8)
     entries = [[] for _ in range(nn)]
     for w in range(ntile):
         for i, g in enumerate(uniq[w]):
-            entries[g].append(w * 3 * stride + i)
+            entries[g].append(w * dim * stride + i)
     nsl = (nn + 31) // 32
     ptr = np.zeros(nsl + 1, dtype=np.int64)
     for s in range(nsl):
@@ -313,8 +312,9 @@ def _force_tiles_numpy(nn, el):
     for n in range(nn):
         for j, off in enumerate(entries[n]):
             slots[ptr[n >> 5] + 32 * j + (n & 31)] = off
-    out = {"usable": True, "n_tiles": ntile, "stride": stride, "tidx": tidx, "ptr": ptr, "slots": slots, "tpitch": 0, "tab": None}
-    if k == 4:
+    out = {"usable": True, "n_tiles": ntile, "stride": stride, "tidx": tidx, "ptr": ptr, "slots": slots, "tpitch": 0, "tab": None,
+           "rounds": rounds}
+    if not hexa:
         tpitch = (stride + 1 + 32 * k + 3) // 4 * 4
         tab = np.zeros((ntile, tpitch), dtype=np.uint8)
         for w in range(ntile):
@@ -328,18 +328,19 @@ def _force_tiles_numpy(nn, el):
 
 
 @pytest.mark.parametrize("kind,n,shuffle", [("hex", (5, 4, 7), False), ("hex", (33, 2, 2), False), ("hex", (4, 4, 4), True),
-                                            ("tet", (3, 4, 5), False), ("tet", (4, 3, 3), True)])
+                                            ("tet", (3, 4, 5), False), ("tet", (4, 3, 3), True),
+                                            ("quad", (37, 9), False), ("quad", (8, 8), True), ("tri", (9, 7), False)])
 def test_force_tile_tables_bit_exact(kind, n, shuffle):
     h = 0.01
-    L = [(q + 1e-6) * h for q in n]
-    dim, k, x, el = host_box((0.0, 0.0, 0.0), L, 0.5 * h, kind == "tet")
+    L = [(q + 1e-6) * h for q in n] + [0.0] * (3 - len(n))
+    dim, k, x, el = host_box((0.0, 0.0, 0.0), L, 0.5 * h, kind in ("tet", "tri"))
     nn = len(x) // dim
     el = el.reshape(-1, k).astype(np.int64)
     if shuffle:
         rng = np.random.default_rng(7)
         el = rng.permutation(nn)[el][rng.permutation(len(el))]
-    got = _force_tiles_lib(nn, el)
-    want = _force_tiles_numpy(nn, el)
+    got = _force_tiles_lib(nn, el, dim)
+    want = _force_tiles_numpy(nn, el, dim)
     assert got["usable"] == want["usable"]
     if kind == "hex":
         # in a box mesh every node is corner n of exactly ONE element, so any element order is conflict-free ...
@@ -351,10 +352,11 @@ def test_force_tile_tables_bit_exact(kind, n, shuffle):
         assert g2["usable"] == w2["usable"] and not g2["usable"]
     if not want["usable"]:
         return
-    assert (got["n_tiles"], got["stride"], got["tpitch"]) == (want["n_tiles"], want["stride"], want["tpitch"])
+    assert (got["n_tiles"], got["stride"], got["tpitch"], got["rounds"]) == (want["n_tiles"], want["stride"], want["tpitch"], want["rounds"])
+    assert got["rounds"] == (kind in ("hex", "quad"))   # box meshes: one element per (node, corner) for hexes / quads only
     for nm in ("tidx", "ptr", "slots"):
         assert np.array_equal(got[nm], want[nm]), nm
-    if kind == "tet":
+    if kind != "hex":
         assert np.array_equal(got["tab"], want["tab"])
     # every element node is reachable: slot -> (tile, position) -> unique list -> node
     ne, k = el.shape

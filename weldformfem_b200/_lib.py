@@ -134,7 +134,7 @@ def load():
         "wf_set_contact_heat": (C.c_int, [vp, C.c_double, C.c_double]),
         "wf_host_ext_faces": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, up, C.POINTER(C.c_ubyte), ip, ip, ip, ip]),
         "wf_host_axis_plane_counts": (C.c_int, [C.c_int, C.c_int, ip, ip]),
-        "wf_host_force_tiles": (C.c_int, [C.c_int, C.c_int, C.c_int, up, C.POINTER(C.c_longlong), C.POINTER(C.c_ubyte),
+        "wf_host_force_tiles": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, up, C.POINTER(C.c_longlong), C.POINTER(C.c_ubyte),
                                           C.POINTER(C.c_longlong), up, C.POINTER(C.c_ubyte)]),
         "wf_host_axis_plane_mesh": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, dp, dp, C.c_int, dp, ip, dp, ip]),
     }

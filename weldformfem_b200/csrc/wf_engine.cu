@@ -217,13 +217,13 @@ static int upload_mesh(wf_engine *E, int nn, int ne, const double *x, const unsi
     // tile-reduced force path (WfDev::ftile): tables built on the host (wf_force_tiles_build, wf_mesh.cpp)
     d.ftile = nullptr; d.tf_ptr = nullptr; d.tf_slots = nullptr; d.tf_idx = nullptr; d.tf_tab = nullptr;
     d.tf_stride = 0; d.tf_tpitch = 0;
-    if ((k == 8 || k == 4) && dim == 3) {
+    if (dim == 3) { // 2D (1M quads, measured): rounds form E2 0.080 -> 0.099 ms, pull form 0.105 ms, N2 unchanged: not used
       WfForceTiles T;
-      wf_force_tiles_build(nn, ne, k, d.ep, elnod, T);
+      wf_force_tiles_build(nn, ne, k, dim, d.ep, elnod, T);
       if (T.usable) {
         long long *dtp; unsigned *dts;
         if (dalloc(E, &dtp, T.ptr.size()) || dalloc(E, &dts, std::max<size_t>(T.slots.size(), 1)) ||
-            dalloc(E, &d.ftile, (size_t)T.n_tiles * 3 * T.stride))
+            dalloc(E, &d.ftile, (size_t)T.n_tiles * dim * T.stride))
           return 1;
         CK(cudaMemcpyAsync(dtp, T.ptr.data(), T.ptr.size() * sizeof(long long), cudaMemcpyHostToDevice, E->stream));
         CK(cudaMemcpyAsync(dts, T.slots.data(), T.slots.size() * sizeof(unsigned), cudaMemcpyHostToDevice, E->stream));

@@ -479,9 +479,9 @@ __global__ void __launch_bounds__(TPB_E, MINB) k_elem_main(WfDev d, WfPar P, int
     const unsigned amask = __activemask(); // a tail tile has fewer than 32 elements (lanes 0 .. nact-1)
     const int nact = __popc(amask), lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int ws = d.tf_stride, tp = d.tf_tpitch;
+    const long long tile = e >> 5;
     double *fb = sm + warp * (KD * 32 + (tp + 7) / 8);
     unsigned char *tab = reinterpret_cast<unsigned char *>(fb + KD * 32);
-    const long long tile = e >> 5;
     const unsigned *__restrict__ gt = reinterpret_cast<const unsigned *>(d.tf_tab + tile * tp);
     for (int i = lane; i < tp / 4; i += nact) reinterpret_cast<unsigned *>(tab)[i] = __ldg(gt + i);
 #pragma unroll
@@ -562,8 +562,7 @@ WF_DI void tile_node_force(const WfDev &d, int n, double (&fi)[3]) {
   for (int j = 0; j < width; j++) {
     const unsigned o = __ldg(d.tf_slots + base + ((long long)j << 5) + (n & 31));
     if (o == 0xFFFFFFFFu) continue;
-#pragma unroll
-    for (int c = 0; c < 3; c++) fi[c] += d.ftile[(long long)o + (long long)c * d.tf_stride];
+    for (int c = 0; c < d.dim; c++) fi[c] += d.ftile[(long long)o + (long long)c * d.tf_stride];
   }
 }
 WF_DI void halo_node_force(const WfDev &d, int n, int sep, double (&fi)[3]) {
@@ -1351,6 +1350,7 @@ static void l_node_vol(const WfDev &d, const WfPar &P, int mode, cudaStream_t s)
 }
 // the tile-reduced force path (WfDev::ftile): same eligibility as the regrouped hexa kernel, default variant only
 static int l_tile_forces(const WfDev &d, const WfPar &P, int separate_hg) {
+  // 3D only: in 2D (1M quads) neither form of the tile reduction pays for itself (wf_engine.cu does not upload the tables)
   return d.ftile && !separate_hg && d.dim == 3 && !P.strict && !P.thermal && (P.variant[2] == 0 || P.variant[2] == 6 || P.variant[2] == 7) &&
          ((d.k == 8 && P.model < 2) || (d.k == 4 && d.tf_tab));
 }

@@ -120,17 +120,17 @@ extern "C" int wf_host_nodel(int n_nodes, int n_elems, int k, const unsigned *el
 // per local corner), which requires that no two elements of a tile reference the same node through the same
 // corner; tetrahedra pull through an incidence table (CSR by unique node, entries ascending element then corner).
 // Node n owns one entry per tile that references it, ascending tile order: slots = tile*3*stride + position.
-void wf_force_tiles_build(int nn, int ne, int k, long long ep, const unsigned *elnod, WfForceTiles &T) {
+void wf_force_tiles_build(int nn, int ne, int k, int dim, long long ep, const unsigned *elnod, WfForceTiles &T) {
   T = WfForceTiles();
   T.k = k;
-  if ((k != 8 && k != 4) || ne <= 0) return;
+  if (!((dim == 3 && (k == 8 || k == 4)) || (dim == 2 && (k == 4 || k == 3))) || ne <= 0) return;
   const int ntile = (ne + 31) / 32;
   T.n_tiles = ntile;
   T.tidx.assign((size_t)k * ep, 0);
   std::vector<int> toff((size_t)ntile + 1, 0), tnodes, tmp;
   tnodes.reserve((size_t)ne * (k == 8 ? 5 : 1));
   int wmax = 0;
-  bool ok = true;
+  bool ok = true, conflict = false;
   std::vector<int> stamp(256, -1);
   for (int w = 0; w < ntile && ok; w++) {
     const int e0 = w * 32, e1 = std::min(ne, e0 + 32);
@@ -140,10 +140,11 @@ void wf_force_tiles_build(int nn, int ne, int k, long long ep, const unsigned *e
     for (int n = 0; n < k && ok; n++)
       for (int e = e0; e < e1; e++) {
         const int u = (int)(std::lower_bound(tmp.begin(), tmp.end(), (int)elnod[(size_t)e * k + n]) - tmp.begin());
-        if (k == 8) {
-          if (stamp[u] == w * k + n) { ok = false; break; }
-          stamp[u] = w * k + n;
+        if (stamp[u] == w * k + n) {
+          conflict = true;
+          if (k == 8) { ok = false; break; } // hexahedra have no pull form
         }
+        stamp[u] = w * k + n;
         T.tidx[(size_t)n * ep + e] = (unsigned char)u;
       }
     tnodes.insert(tnodes.end(), tmp.begin(), tmp.end());
@@ -151,7 +152,7 @@ void wf_force_tiles_build(int nn, int ne, int k, long long ep, const unsigned *e
     wmax = std::max(wmax, (int)tmp.size());
   }
   const int stride = (wmax + 3) / 4 * 4;
-  ok = ok && (long long)ntile * 3 * stride < 4294967295LL;
+  ok = ok && (long long)ntile * dim * stride < 4294967295LL;
   if (!ok) return;
   T.stride = stride;
   std::vector<int> cnt((size_t)nn, 0);
@@ -168,10 +169,10 @@ void wf_force_tiles_build(int nn, int ne, int k, long long ep, const unsigned *e
   for (int w = 0; w < ntile; w++)
     for (int i = toff[w]; i < toff[w + 1]; i++) {
       const int g = tnodes[i];
-      T.slots[(size_t)(T.ptr[g >> 5] + 32LL * cnt[g] + (g & 31))] = (unsigned)((long long)w * 3 * stride + (i - toff[w]));
+      T.slots[(size_t)(T.ptr[g >> 5] + 32LL * cnt[g] + (g & 31))] = (unsigned)((long long)w * dim * stride + (i - toff[w]));
       cnt[g]++;
     }
-  if (k == 4) {
+  if (k != 8) {
     const int tpitch = (stride + 1 + 32 * k + 3) / 4 * 4;
     T.tpitch = tpitch;
     T.tab.assign((size_t)ntile * tpitch, 0);
@@ -191,19 +192,20 @@ void wf_force_tiles_build(int nn, int ne, int k, long long ep, const unsigned *e
         }
     }
   }
+  T.rounds = !conflict;
   T.usable = true;
 }
 
 // test-facing copy of the tables (no GPU needed).  First call with NULL buffers for the sizes:
-// info = {usable, n_tiles, stride, tpitch, n_slices, n_slot_entries}; tidx comes back as [e*k + ln].
-extern "C" int wf_host_force_tiles(int n_nodes, int n_elems, int k, const unsigned *elnod, long long *info,
+// info[7] = {usable, n_tiles, stride, tpitch, n_slices, n_slot_entries, conflict-free rounds}; tidx comes back as [e*k + ln].
+extern "C" int wf_host_force_tiles(int n_nodes, int n_elems, int k, int dim, const unsigned *elnod, long long *info,
                                    unsigned char *tidx, long long *ptr, unsigned *slots, unsigned char *tab) {
   for (long long i = 0; i < (long long)n_elems * k; i++)
     if (elnod[i] >= (unsigned)n_nodes) return 1;
   WfForceTiles T;
-  wf_force_tiles_build(n_nodes, n_elems, k, n_elems, elnod, T);
+  wf_force_tiles_build(n_nodes, n_elems, k, dim, n_elems, elnod, T);
   info[0] = T.usable ? 1 : 0; info[1] = T.n_tiles; info[2] = T.stride; info[3] = T.tpitch;
-  info[4] = (n_nodes + 31) / 32; info[5] = (long long)T.slots.size();
+  info[4] = (n_nodes + 31) / 32; info[5] = (long long)T.slots.size(); info[6] = T.rounds ? 1 : 0;
   if (!T.usable) return 0;
   if (tidx)
     for (int e = 0; e < n_elems; e++)
