@@ -456,6 +456,7 @@ struct EmitTile {
 
 __global__ void __launch_bounds__(TPB, 4) k_elem_main_hex_tile(WfDev d, WfPar P, int stride) {
   extern __shared__ double sm[];
+  pdl_trigger();
   const int t = threadIdx.x;
   const int b = blockIdx.x;
   const int e0 = b * TPB + t;
@@ -479,6 +480,7 @@ __global__ void __launch_bounds__(TPB, 4) k_elem_main_hex_tile(WfDev d, WfPar P,
   unsigned ri[8];
 #pragma unroll
   for (int n = 0; n < 8; n++) ri[n] = d.tf_idx[(long long)n * d.ep + e];
+  pdl_wait(); // everything above reads constant mesh tables only
   double tau[6];
 #pragma unroll
   for (int i = 0; i < 6; i++) tau[i] = d.tau[(long long)i * d.ep + e];

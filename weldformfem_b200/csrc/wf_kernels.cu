@@ -27,6 +27,17 @@
 
 namespace WF_NS {
 
+WF_DI void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
+// Programmatic dependent launch (sm_90+): the four kernels of the step are launched with
+// cudaLaunchAttributeProgrammaticStreamSerialization, so the CTAs of the next pass become resident while the last wave
+// of the current one drains, and do their CONSTANT-table loads (connectivity, slot tables, node lists) meanwhile.
+// Rule kept by every kernel below: pdl_trigger() first; nothing a previous kernel may have written is read, and nothing
+// is written, before pdl_wait() (= the prerequisite grids have completed and their memory operations are visible).
+// L2 prefetches are allowed earlier (L2 is the coherence point).  Launched without the attribute both are no-ops.
+WF_DI void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::); }
+WF_DI void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 #include "wf_hex_fast.cuh"
 
 constexpr int TPB_E = 128; // element kernels: register-heavy
@@ -108,15 +119,15 @@ __global__ void k_impose_bc(WfDev d, int dim, int is_acc, double *a_or_v) {
 // ---------------------------------------------------------------------------------------------
 // E1: element volume from current coordinates
 // ---------------------------------------------------------------------------------------------
-WF_DI void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
-
 template <int ET>
 __global__ void __launch_bounds__(TPB_E) k_elem_vol(WfDev d, WfPar P, int store_jac) {
   constexpr int K = Elem<ET>::K, D = Elem<ET>::D;
+  pdl_trigger();
   int e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= d.ne) return;
   int nid[K];
   load_conn<ET>(d, e, nid);
+  pdl_wait();
   double xl[K][D], A[D][D], detJ;
   gather_nodal<ET>(d.x, d.np, nid, xl);
   jac_adj_det<ET>(xl, A, detJ);
@@ -188,13 +199,15 @@ template <int K>
 __global__ void __launch_bounds__(TPB_N) k_node_vol(WfDev d, WfPar P, int mode_in) {
   const bool with_predict = mode_in == 3;
   const int mode = with_predict ? 1 : mode_in;
+  pdl_trigger();
   int n = blockIdx.x * blockDim.x + threadIdx.x;
-  if (n == 0 && mode == 1 && d.xmin_key) d.xmin_key[P.xmin_cur ^ 1] = dbl_key(1000.0);
   int slice = n >> 5;
-  if (slice >= d.nslices) return;
+  if (slice >= d.nslices) { if (n == 0) pdl_wait(); return; }
   const long long base = d.sell_ptr[slice];
   const int width = (int)((d.sell_ptr[slice + 1] - base) >> 5);
   const int lane = n & 31;
+  pdl_wait();
+  if (n == 0 && mode == 1 && d.xmin_key) d.xmin_key[P.xmin_cur ^ 1] = dbl_key(1000.0);
   double s = 0.0, sq = 0.0;
   const double *src = (mode == 0) ? d.vol_0 : d.vol;
   const bool quarter = (P.press == 3);
@@ -326,9 +339,11 @@ __global__ void __launch_bounds__(TPB_E, MINB) k_elem_main(WfDev d, WfPar P, int
   constexpr int K = Elem<ET>::K, D = Elem<ET>::D;
   static_assert(!(STAGED && THERMAL), "the thermal terms gather by global node id");
   extern __shared__ double sm[];
+  pdl_trigger();
   int e = blockIdx.x * blockDim.x + threadIdx.x;
   double xl[K][D], vl[K][D], npn[K], A[D][D], dH[D][K], detJ;
   int nid[K];
+  if constexpr (STAGED) pdl_wait();
   if constexpr (STAGED) {
     static_assert(TPB_E == WF_EBLK, "block node tables are built for WF_EBLK elements per CTA");
     const int b = blockIdx.x;
@@ -364,6 +379,7 @@ __global__ void __launch_bounds__(TPB_E, MINB) k_elem_main(WfDev d, WfPar P, int
       if (lane * 32 < d.tf_tpitch) prefetch_l2(d.tf_tab + (long long)(e >> 5) * d.tf_tpitch + lane * 32);
     }
     load_conn<ET>(d, e, nid);
+    pdl_wait();
     gather_nodal<ET>(d.x, d.np, nid, xl);
     gather_nodal<ET>(d.v, d.np, nid, vl);
     gather_nodal_p<ET>(d, nid, npn);
@@ -604,6 +620,7 @@ WF_DI double halo_total(const WfDev &d, int u, int comp, int parity, double own)
 template <int D, bool SEPARATE_HG, int UNROLL, bool TILE_F = false, bool PREFETCH = false, int MINB = 1>
 __global__ void __launch_bounds__(TPB_N, MINB) k_node_update(WfDev d, WfPar P, int fuse_flags, int phase) {
   const bool fuse_predictor = fuse_flags & 1, udt_recompute = fuse_flags & 2, udt_skip_store = fuse_flags & 4;
+  pdl_trigger();
   int n = blockIdx.x * blockDim.x + threadIdx.x;
   int slice = n >> 5;
   if (slice >= d.nslices) return;
@@ -622,6 +639,7 @@ __global__ void __launch_bounds__(TPB_N, MINB) k_node_update(WfDev d, WfPar P, i
       if (!udt_recompute) prefetch_l2(d.u_dt + i);
     }
   }
+  pdl_wait();
   if (TILE_F && phase != 2) {
     // tile-reduced forces: one partial per tile that touches the node, gathered through the tile-entry table
     const long long base = d.tf_ptr[slice];
@@ -1314,6 +1332,24 @@ __global__ void __launch_bounds__(128) k_halo_finish(WfDev d, WfPar P, int parit
 // launchers
 // ---------------------------------------------------------------------------------------------
 static inline int cdiv(long long a, int b) { return (int)((a + b - 1) / b); }
+
+// launch with programmatic stream serialisation (see pdl_trigger / pdl_wait); WF_PDL=0 in the environment falls back
+// to ordinary launches (A/B measurements)
+static bool pdl_enabled() {
+  static int on = -1;
+  if (on < 0) { const char *e = getenv("WF_PDL"); on = (e && e[0] == '0') ? 0 : 1; }
+  return on != 0;
+}
+template <class... KArgs, class... Args>
+static void launch_pdl(void (*kern)(KArgs...), int grid, int block, size_t smem, cudaStream_t s, Args &&...args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3((unsigned)block); cfg.dynamicSmemBytes = smem; cfg.stream = s;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at; cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  cudaLaunchKernelEx(&cfg, kern, std::forward<Args>(args)...);
+}
 #define ELEM_DISPATCH(et, ...)                                          \
   switch (et) {                                                         \
     case ET_HEX8: { constexpr int ET = ET_HEX8; __VA_ARGS__; } break;   \
@@ -1335,7 +1371,7 @@ static void l_elem_vol(const WfDev &d, const WfPar &P, int et, int store_jac, cu
     ELEM_DISPATCH(et, k_elem_vol_staged<ET><<<cdiv(d.ne, WF_EBLK), WF_EBLK, Elem<ET>::D * stride * 8, s>>>(d, P, stride));
     return;
   }
-  ELEM_DISPATCH(et, k_elem_vol<ET><<<cdiv(d.ne, TPB_E), TPB_E, 0, s>>>(d, P, store_jac));
+  ELEM_DISPATCH(et, launch_pdl(k_elem_vol<ET>, cdiv(d.ne, TPB_E), TPB_E, 0, s, d, P, store_jac));
 }
 static void l_vol_from_detj(const WfDev &d, int et, cudaStream_t s) {
   ELEM_DISPATCH(et, k_vol_from_detj<ET><<<cdiv(d.ne, 256), 256, 0, s>>>(d));
@@ -1343,9 +1379,9 @@ static void l_vol_from_detj(const WfDev &d, int et, cudaStream_t s) {
 static void l_node_vol(const WfDev &d, const WfPar &P, int mode, cudaStream_t s) {
   int g = cdiv((long long)d.nslices * 32, TPB_N);
   switch (d.k) {
-    case 8: k_node_vol<8><<<g, TPB_N, 0, s>>>(d, P, mode); break;
-    case 4: k_node_vol<4><<<g, TPB_N, 0, s>>>(d, P, mode); break;
-    default: k_node_vol<3><<<g, TPB_N, 0, s>>>(d, P, mode); break;
+    case 8: launch_pdl(k_node_vol<8>, g, TPB_N, 0, s, d, P, mode); break;
+    case 4: launch_pdl(k_node_vol<4>, g, TPB_N, 0, s, d, P, mode); break;
+    default: launch_pdl(k_node_vol<3>, g, TPB_N, 0, s, d, P, mode); break;
   }
 }
 // the tile-reduced force path (WfDev::ftile): same eligibility as the regrouped hexa kernel, default variant only
@@ -1358,7 +1394,7 @@ static void l_elem_main(const WfDev &d, const WfPar &P, int et, int separate_hg,
   if (et == ET_HEX8 && l_tile_forces(d, P, separate_hg)) {
     const int stride = (d.blk_umax + 31) / 32 * 32, g = cdiv(d.ne, hexfast::TPB);
     const size_t smem = ((size_t)7 * stride + (size_t)(hexfast::TPB / 32) * 3 * d.tf_stride) * 8;
-    hexfast::k_elem_main_hex_tile<<<g, hexfast::TPB, smem, s>>>(d, P, stride);
+    launch_pdl(hexfast::k_elem_main_hex_tile, g, hexfast::TPB, smem, s, d, P, stride);
     return;
   }
   // the regrouped hexa kernel inlines Bilinear / Hollomon; the rate-dependent laws (Johnson-Cook, GMT) take the generic kernel
@@ -1395,7 +1431,7 @@ static void l_elem_main(const WfDev &d, const WfPar &P, int et, int separate_hg,
     const size_t smem = (size_t)(TPB_E / 32) * (12 * 32 + (d.tf_tpitch + 7) / 8) * 8;
     if (P.variant[2] == 7) k_elem_main<ET_TET4, false, false, false, true><<<cdiv(d.ne, TPB_E), TPB_E, smem, s>>>(d, P, 0);
     else if (P.variant[2] == 6) k_elem_main<ET_TET4, false, false, false, true, 6><<<cdiv(d.ne, TPB_E), TPB_E, smem, s>>>(d, P, 0);
-    else k_elem_main<ET_TET4, false, false, false, true, 5><<<cdiv(d.ne, TPB_E), TPB_E, smem, s>>>(d, P, 0);
+    else launch_pdl(k_elem_main<ET_TET4, false, false, false, true, 5>, cdiv(d.ne, TPB_E), TPB_E, smem, s, d, P, 0);
     return;
   }
   const int stride = (d.blk_umax + 31) / 32 * 32;
@@ -1410,14 +1446,14 @@ static void l_elem_main(const WfDev &d, const WfPar &P, int et, int separate_hg,
     else { ELEM_DISPATCH(et, k_elem_main<ET, false, false, true><<<cdiv(d.ne, TPB_E), TPB_E, 0, s>>>(d, P, 0)); }
   } else {
     if (separate_hg) { ELEM_DISPATCH(et, k_elem_main<ET, true, false><<<cdiv(d.ne, TPB_E), TPB_E, 0, s>>>(d, P, 0)); }
-    else { ELEM_DISPATCH(et, k_elem_main<ET, false, false><<<cdiv(d.ne, TPB_E), TPB_E, 0, s>>>(d, P, 0)); }
+    else { ELEM_DISPATCH(et, launch_pdl(k_elem_main<ET, false, false>, cdiv(d.ne, TPB_E), TPB_E, 0, s, d, P, 0)); }
   }
 }
 template <bool SEP, int U, int MINB = 1>
 static void node_update_t(const WfDev &d, const WfPar &P, int fuse, int phase, cudaStream_t s) {
   int g = cdiv((long long)d.nslices * 32, TPB_N);
-  if (d.dim == 3) k_node_update<3, SEP, U, false, false, MINB><<<g, TPB_N, 0, s>>>(d, P, fuse, phase);
-  else k_node_update<2, SEP, U, false, false, MINB><<<g, TPB_N, 0, s>>>(d, P, fuse, phase);
+  if (d.dim == 3) launch_pdl(k_node_update<3, SEP, U, false, false, MINB>, g, TPB_N, 0, s, d, P, fuse, phase);
+  else launch_pdl(k_node_update<2, SEP, U, false, false, MINB>, g, TPB_N, 0, s, d, P, fuse, phase);
 }
 static void l_node_update(const WfDev &d, const WfPar &P, int separate_hg, int fuse, int phase, cudaStream_t s) {
   if (l_tile_forces(d, P, separate_hg)) {
