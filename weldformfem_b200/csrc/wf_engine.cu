@@ -683,15 +683,25 @@ static int step_stage(wf_engine *E, int stage, bool last) {
     const bool fold = !E->predicted && !E->strict;
     if (!E->predicted && E->strict) E->L->predict(d, P, 1, E->stream);
     E->L->elem_vol(d, P, E->et, 0, E->stream);
-    E->L->node_vol(d, P, fold ? 3 : 1, E->stream);
+    // the partial volume sums of the shared nodes depend on E1 only (k_halo_send gathers them itself): send them
+    // BEFORE the nodal-sum pass, so the transfer and the neighbours' flags travel while N1 runs
     if (E->distributed) halo_send(E, 1);
+    E->L->node_vol(d, P, fold ? 3 : 1, E->stream);
   } else if (stage == 1) {
     if (E->distributed) E->L->halo_finish(d, P, 1, P.halo_parity, E->stream);
     E->L->elem_main(d, P, E->et, sep, E->stream);
     if (E->distributed) halo_send(E, 2);
   } else {
     if (wf_contact_forces(E)) return 1;          // CalcContactForces (Solver_explicit.C:769-770)
-    E->L->node_update(d, P, sep, fuse_flags(E, last), 0, E->stream);
+    if (E->distributed && E->transport == 0) {
+      // peer transport: the nodes this rank does not share are integrated while the neighbours' force partials are
+      // still travelling; the shared ones follow after the wait (step_once skips its own wait before this stage)
+      E->L->node_update(d, P, sep, fuse_flags(E, last), 3, E->stream);
+      halo_wait(E);
+      E->L->node_update(d, P, sep, fuse_flags(E, last), 4, E->stream);
+    } else {
+      E->L->node_update(d, P, sep, fuse_flags(E, last), 0, E->stream);
+    }
     if (wf_contact_step_end(E)) return 1;        // rigid surfaces: ramp, Move, normals, plane coefficients (:981-1005)
     if (P.thermal) { E->L->node_thermal(d, P, E->stream); P.dtedt_cur ^= 1; }  // ThermalCalcs, node part (:1008-1012)
     E->predicted = !last;
@@ -705,7 +715,7 @@ static int step_stage(wf_engine *E, int stage, bool last) {
 static int step_once(wf_engine *E, bool last) {
   for (int st = 0; st < 3; st++) {
     if (step_stage(E, st, last)) return 1;
-    if (E->distributed && st < 2) halo_wait(E);
+    if (E->distributed && st < 2 && !(st == 1 && E->transport == 0)) halo_wait(E); // stage 2 waits for the forces itself
   }
   return 0;
 }

@@ -614,7 +614,9 @@ WF_DI double halo_total(const WfDev &d, int u, int comp, int parity, double own)
 // (Solver_explicit.C:953-969), UpdateCorrectionPos (Domain_d.C:1005-1025) and, unless this is the
 // last step of the batch, the next step's UpdatePrediction + ImposeBCV.  The nodal mass was formed
 // by N1.  One warp == one slice of 32 nodes; every load is a contiguous 256 B row.
-//   phase 0 = everything;  phase 1 = sums only, to d.fi (lazy m_fi);  phase 2 = integrate from d.fi.
+//   phase 0 = everything;  phase 1 = sums only, to d.fi (lazy m_fi);  phase 2 = integrate from d.fi;
+//   phase 3 = everything, nodes shared with another rank skipped;  phase 4 = everything, shared nodes only (multi-GPU:
+//   the bulk of the pass runs while the force partials of the neighbours are still in flight).
 // On a partitioned mesh the sums of shared nodes are completed with the neighbours' partials (halo_total).
 // ---------------------------------------------------------------------------------------------
 template <int D, bool SEPARATE_HG, int UNROLL, bool TILE_F = false, bool PREFETCH = false, int MINB = 1>
@@ -622,8 +624,13 @@ __global__ void __launch_bounds__(TPB_N, MINB) k_node_update(WfDev d, WfPar P, i
   const bool fuse_predictor = fuse_flags & 1, udt_recompute = fuse_flags & 2, udt_skip_store = fuse_flags & 4;
   pdl_trigger();
   int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (phase == 4) { // shared nodes only, one thread per unique shared node (after the halo wait)
+    if (n >= d.n_uniq) return;
+    n = d.hu_node[n];
+  }
   int slice = n >> 5;
   if (slice >= d.nslices) return;
+  if (phase == 3 && d.halo_slot && n < d.nn && d.halo_slot[n] >= 0) return; // shared nodes wait for phase 4
   const int lane = n & 31;
   double fi[D];
 #pragma unroll
@@ -1451,13 +1458,13 @@ static void l_elem_main(const WfDev &d, const WfPar &P, int et, int separate_hg,
 }
 template <bool SEP, int U, int MINB = 1>
 static void node_update_t(const WfDev &d, const WfPar &P, int fuse, int phase, cudaStream_t s) {
-  int g = cdiv((long long)d.nslices * 32, TPB_N);
+  int g = phase == 4 ? cdiv(std::max(d.n_uniq, 1), TPB_N) : cdiv((long long)d.nslices * 32, TPB_N);
   if (d.dim == 3) launch_pdl(k_node_update<3, SEP, U, false, false, MINB>, g, TPB_N, 0, s, d, P, fuse, phase);
   else launch_pdl(k_node_update<2, SEP, U, false, false, MINB>, g, TPB_N, 0, s, d, P, fuse, phase);
 }
 static void l_node_update(const WfDev &d, const WfPar &P, int separate_hg, int fuse, int phase, cudaStream_t s) {
   if (l_tile_forces(d, P, separate_hg)) {
-    const int g = cdiv((long long)d.nslices * 32, TPB_N);
+    const int g = phase == 4 ? cdiv(std::max(d.n_uniq, 1), TPB_N) : cdiv((long long)d.nslices * 32, TPB_N);
     // measured on 10M hexes (tools/kbench.py): 5 resident CTAs (48 registers) + L2 prefetch of the state rows 0.60 ms;
     // 3 CTAs (67 registers) 0.66-0.75 ms; 6 CTAs (40 registers, spills) 0.61 ms; no prefetch 0.71 ms
     if (P.variant[3] == 5) k_node_update<3, false, 4, true, false, 5><<<g, TPB_N, 0, s>>>(d, P, fuse, phase);
