@@ -11,10 +11,15 @@
 //       f(n,i)  = w sum_c dH(c,n) sigma(c,i)     = sum_r s_r(n) B(r,i),   B(r,i) = w sum_c A'(c,r) sigma(c,i)
 //       f_hg(n,i) = -c_h sum_j h_j(v_i) Sig_j(n)
 //     and the 24 nodal force components come out of one inverse butterfly per component.
-// Element-local node data (x, v of the 8 nodes) is staged in shared memory with cp.async, one private
-// column per thread ([item][thread], conflict-free), so the 48 gathers are in flight together without
-// holding 96 registers; no block-level synchronisation is needed because a thread only reads back
-// what it requested itself.
+// Kernels in this file, all one element per thread, 128 threads per CTA:
+//   k_elem_main_hex_tile   DEFAULT.  The CTA stages x, v and the nodal ratio of its UNIQUE nodes once (cp.async through
+//                          the fixed-pitch node list WfDev::blk_pad); nodal forces are summed per warp tile in shared
+//                          memory and one partial per (tile, unique node) goes to HBM (WfDev::ftile).
+//   k_elem_main_hex_staged same staging, one force record per element node into the node-ordered buffer (variant 9;
+//                          also the fallback when the tile tables are unusable).
+//   k_elem_main_hex_fast   per-thread cp.async columns ([item][thread], conflict-free, no block barrier): the first
+//                          working form, kept as a tuning aid together with the persistent pipelined variant and the
+//                          memory skeletons (wf_set_variant(2, ...); tools/kbench.py).
 // (included inside the flavour namespace of wf_kernels.cu, after wf_math.cuh)
 
 namespace hexfast {

@@ -10,11 +10,13 @@
 //   N1 k_node_vol    : vol gather -> nodal sums / ratios         (CalcNodalVol, node part of calcElemPressure*)
 //   E2 k_elem_main   : J, dH, D, W, pressure, Jaumann + J2 return, element + hourglass forces
 //   N2 k_node_update : per-node force sum, accel, BCs, corrector, position, next-step predictor
-// Element forces travel from E2 to N2 through the node-ordered buffer fsell: the contribution of
-// (element e, local node ln) is written straight into the entry of node n's nodel list that the
-// reference's assemblyForces would read for it (pos[ln][e]), so N2 streams its list with coalesced
-// loads and sums it in nodel order — a deterministic gather with the indirection resolved on the
-// write side, no atomics.
+// Element forces travel from E2 to N2 in one of two ways, both deterministic gathers without atomics:
+//   * strict flavour and 2D: the node-ordered buffer fsell — the contribution of (element e, local node ln) is written
+//     straight into the entry of node n's nodel list that the reference's assemblyForces would read for it
+//     (pos[ln][e]), so N2 streams its list with coalesced loads and sums it in nodel order;
+//   * fast flavour, hexahedra / tetrahedra: tile partials ftile — the forces of the 32 elements of a warp are summed
+//     per unique node in shared memory (fixed order) and one partial per (tile, node) is written; N2 gathers the
+//     partials of a node in ascending tile order (WfDev::ftile, wf_dev.h).
 #include <cuda_runtime.h>
 #include <math.h>
 
