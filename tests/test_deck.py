@@ -107,3 +107,26 @@ def test_deck_run_matches_reference_front_end(host_bins, tmp_path, name):
         worst[nm] = relerr(got[nm], gold[key])
     bad = {k: v for k, v in worst.items() if not v <= 1e-8}
     assert not bad, (name, bad, worst)
+
+
+def test_deck_k_reader_free_format_and_two_line_solids(host_bins, tmp_path):
+    """Comma-separated cards, CRLF line ends, comment lines, and the '*ELEMENT_SOLID' form that puts eid/pid on one
+    line and the nodes on the next (both appear in LS-PrePost output)."""
+    k = tmp_path / "m.k"
+    k.write_bytes(("*KEYWORD\r\n*NODE\r\n$ comment\r\n"
+                   "10,0.0,0.0,0.0\r\n20,1.0,0.0,0.0\r\n30,0.0,1.0,0.0\r\n40,0.0,0.0,1.0\r\n50,1.0,1.0,1.0\r\n"
+                   "*ELEMENT_SOLID\r\n"
+                   "1,1\r\n10,20,30,40,40,40,40,40\r\n"
+                   "2,1\r\n20,30,40,50,50,50,50,50\r\n*END\r\n").encode())
+    deck = tmp_path / "d.json"
+    deck.write_text(json.dumps({
+        "Configuration": {"simTime": 1e-5},
+        "Materials": [{"type": "Hollomon", "const": [386.796e6, 0.154], "density0": 2700.0, "youngsModulus": 68.9e9,
+                       "poissonsRatio": 0.3, "yieldStress0": 190.4e6}],
+        "DomainBlocks": [{"type": "File", "fileName": "m.k"}],
+        "BoundaryConditions": [{"zoneId": 1, "valueType": 0, "value": [0, 0, 0], "start": [-1, -1, -0.1], "end": [2, 2, 0.1]}]}))
+    r = subprocess.run([os.path.join(host_bins, "wf_weldform"), str(deck), "--parse-only"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    s = json.loads(r.stdout.strip().splitlines()[-1])
+    assert (s["nodxelem"], s["nodes"], s["elements"]) == (4, 5, 2)
+    assert s["bc_count"] == [3, 3, 3]          # the three nodes with z = 0
