@@ -197,8 +197,8 @@ __global__ void k_vol_from_detj(WfDev d) {
 // ---------------------------------------------------------------------------------------------
 //   mode 3 (step)  : mode 1 + UpdatePrediction and ImposeBCV of the node (Domain_d.C:961-974): the first step of a
 //                    batch has no previous node pass to carry its predictor (WF_FAST; strict runs k_predict)
-template <int K>
-__global__ void __launch_bounds__(TPB_N) k_node_vol(WfDev d, WfPar P, int mode_in) {
+template <int K, int MINB = 1>
+__global__ void __launch_bounds__(TPB_N, MINB) k_node_vol(WfDev d, WfPar P, int mode_in) {
   const bool with_predict = mode_in == 3;
   const int mode = with_predict ? 1 : mode_in;
   pdl_trigger();
@@ -1388,9 +1388,13 @@ static void l_vol_from_detj(const WfDev &d, int et, cudaStream_t s) {
 static void l_node_vol(const WfDev &d, const WfPar &P, int mode, cudaStream_t s) {
   int g = cdiv((long long)d.nslices * 32, TPB_N);
   switch (d.k) {
-    case 8: launch_pdl(k_node_vol<8>, g, TPB_N, 0, s, d, P, mode); break;
-    case 4: launch_pdl(k_node_vol<4>, g, TPB_N, 0, s, d, P, mode); break;
-    default: launch_pdl(k_node_vol<3>, g, TPB_N, 0, s, d, P, mode); break;
+    // register cap for 5 resident CTAs (48 registers): 0.235 -> 0.192 ms on 10M hexes; 6 and 8 CTAs (spills) 0.214 ms
+    case 8:
+      if (P.variant[1] == 5) launch_pdl(k_node_vol<8>, g, TPB_N, 0, s, d, P, mode);
+      else launch_pdl(k_node_vol<8, 5>, g, TPB_N, 0, s, d, P, mode);
+      break;
+    case 4: launch_pdl(k_node_vol<4, 5>, g, TPB_N, 0, s, d, P, mode); break;
+    default: launch_pdl(k_node_vol<3, 5>, g, TPB_N, 0, s, d, P, mode); break;
   }
 }
 // the tile-reduced force path (WfDev::ftile): same eligibility as the regrouped hexa kernel, default variant only
@@ -1604,7 +1608,7 @@ static void l_preload(int et, int dim, int k) {
                 cudaFuncSetAttribute(k_elem_main<ET, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 7 * 1024 * 8);
                 cudaFuncSetAttribute(k_elem_main<ET, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 7 * 1024 * 8);
                 touch(k_elem_main<ET, true, true>); touch(k_elem_main<ET, false, true>));
-  touch(k_node_vol<8>); touch(k_node_vol<4>); touch(k_node_vol<3>);
+  touch(k_node_vol<8>); touch(k_node_vol<8, 5>); touch(k_node_vol<4, 5>); touch(k_node_vol<3, 5>);
   // per device: the regrouped hexa kernel stages 48 KB of node data per CTA
   cudaFuncSetAttribute(hexfast::k_elem_main_hex_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, hexfast::SMEM_BYTES);
   cudaFuncSetAttribute(hexfast::k_elem_main_hex_fast, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
