@@ -124,6 +124,7 @@ struct WfDev {
   int *nonfinite;                    /* [1] */
   unsigned long long *xmin_key;      /* [2] ordered-key of min x_r (axisymmetric axis constraint) */
   double *red;                       /* [8] energy reductions */
+  double *ekin_acc;                  /* NULL, or where this step's node pass adds 1/2 m |v|^2 of the corrected velocities (step monitor) */
 };
 
 struct WfPar {

@@ -492,11 +492,16 @@ extern "C" int wf_monitor_async(wf_engine *E) {
   const int b = (E->mon_head + E->mon_pending) & 1;
   WfDev d2 = E->d;
   d2.ne = 0;                       // kinetic part only
-  d2.red = E->mon_red + 8 * b;
-  CK(cudaMemsetAsync(d2.red, 0, 2 * sizeof(double), E->stream));
-  E->L->energy(d2, nullptr, E->stream);
+  d2.red = E->mon_red + wf_engine::MON_NACC * b;
+  const bool fused = E->ekin_step == E->step_count && E->ekin_slot == b; // formed by the last node pass already
+  if (!fused) {
+    CK(cudaMemsetAsync(d2.red, 0, wf_engine::MON_NACC * sizeof(double), E->stream));
+    E->L->energy(d2, nullptr, E->stream);   // adds into d2.red[0]
+  }
+  E->mon_seen = true;
+  E->ekin_step = -1;
   wf_engine::MonSlot *h = E->mon_host + b;
-  CK(cudaMemcpyAsync(&h->ekin, d2.red, sizeof(double), cudaMemcpyDeviceToHost, E->stream));
+  CK(cudaMemcpyAsync(h->part, d2.red, wf_engine::MON_NACC * sizeof(double), cudaMemcpyDeviceToHost, E->stream));
   CK(cudaMemcpyAsync(&h->nonfinite, E->d.nonfinite, sizeof(int), cudaMemcpyDeviceToHost, E->stream));
   if (E->distributed) CK(cudaMemcpyAsync(&h->halo_error, E->d.comm_error, sizeof(int), cudaMemcpyDeviceToHost, E->stream));
   else h->halo_error = 0;
@@ -510,10 +515,12 @@ extern "C" int wf_monitor_wait(wf_engine *E, double *Ekin, int *nonfinite) {
   CK(cudaSetDevice(E->device));
   const int b = E->mon_head;
   CK(cudaEventSynchronize(E->mon_ev[b]));
-  const wf_engine::MonSlot h = E->mon_host[b];
+  const wf_engine::MonSlot &h = E->mon_host[b];
   E->mon_head ^= 1;
   E->mon_pending--;
-  if (Ekin) *Ekin = h.ekin;
+  double ek = 0.0;
+  for (int i = 0; i < wf_engine::MON_NACC; i++) ek += h.part[i];
+  if (Ekin) *Ekin = ek;
   if (nonfinite) *nonfinite = h.nonfinite;
   if (h.halo_error) FAIL("halo exchange timed out waiting for neighbour index " + std::to_string(h.halo_error - 1));
   return 0;
@@ -627,7 +634,7 @@ static int init_prologue(wf_engine *E) {
   }
   if (!E->mon_host) { // pinned result ring of wf_monitor_async (page pinning can take milliseconds: do it here)
     CK(cudaMallocHost((void **)&E->mon_host, 2 * sizeof(wf_engine::MonSlot)));
-    if (dalloc(E, &E->mon_red, 16)) return 1;
+    if (dalloc(E, &E->mon_red, 2 * wf_engine::MON_NACC)) return 1;
     for (int b = 0; b < 2; b++) CK(cudaEventCreateWithFlags(&E->mon_ev[b], cudaEventDisableTiming));
   }
   E->L->preload(E->et, E->dim, E->k);
@@ -693,6 +700,14 @@ static int step_stage(wf_engine *E, int stage, bool last) {
     if (E->distributed) halo_send(E, 2);
   } else {
     if (wf_contact_forces(E)) return 1;          // CalcContactForces (Solver_explicit.C:769-770)
+    const bool fuse_ekin = last && E->mon_seen && E->mon_red && E->mon_pending < 2;
+    if (fuse_ekin) { // the node pass of the call's last step also forms the kinetic energy for wf_monitor_async
+      const int b = (E->mon_head + E->mon_pending) & 1;
+      d.ekin_acc = E->mon_red + wf_engine::MON_NACC * b;
+      CK(cudaMemsetAsync(d.ekin_acc, 0, wf_engine::MON_NACC * sizeof(double), E->stream));
+      E->ekin_step = E->step_count + 1;
+      E->ekin_slot = b;
+    }
     if (E->distributed && E->transport == 0) {
       // peer transport: the nodes this rank does not share are integrated while the neighbours' force partials are
       // still travelling; the shared ones follow after the wait (step_once skips its own wait before this stage)
@@ -702,6 +717,7 @@ static int step_stage(wf_engine *E, int stage, bool last) {
     } else {
       E->L->node_update(d, P, sep, fuse_flags(E, last), 0, E->stream);
     }
+    d.ekin_acc = nullptr;
     if (wf_contact_step_end(E)) return 1;        // rigid surfaces: ramp, Move, normals, plane coefficients (:981-1005)
     if (P.thermal) { E->L->node_thermal(d, P, E->stream); P.dtedt_cur ^= 1; }  // ThermalCalcs, node part (:1008-1012)
     E->predicted = !last;
@@ -1093,6 +1109,7 @@ extern "C" int wf_get_time(wf_engine *E, double *t, long *steps) {
   NEED(E->inited, "call wf_init first");                          \
   NEED(!E->predicted, "engine is mid-batch");                     \
   NEED(!E->P.thermal, "the unfused entry points do not cover thermal coupling: step with wf_step"); \
+  E->ekin_step = -1;                                              \
   CK(cudaSetDevice(E->device));                                   \
   if (ensure_dbg(E)) return 1;                                    \
   WfDev &d = E->d; WfPar &P = E->P; (void)d; (void)P;
@@ -1361,6 +1378,7 @@ extern "C" int wf_set_array(wf_engine *E, const char *name, const void *src, siz
   NEED(E->meshed, "no mesh");
   NEED(name && src, "null argument");
   NEED(!E->predicted, "engine is mid-batch");
+  E->ekin_step = -1; // the state may change: a later monitor recomputes
   CK(cudaSetDevice(E->device));
   WfDev &d = E->d;
   const int nn = E->nn, ne = E->ne, k = E->k, dim = E->dim;

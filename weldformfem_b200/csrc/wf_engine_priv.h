@@ -50,11 +50,17 @@ struct wf_engine {
   std::vector<double> bc_master;           // host copy of bc_vals
   int bc_version[3] = {0, 0, 0}, bc_stage_version[2][3] = {{0, 0, 0}, {0, 0, 0}};
   // asynchronous step monitor (wf_monitor_async / wf_monitor_wait): 2-deep ring of pinned results
-  struct MonSlot { double ekin; double pad; int nonfinite; int halo_error; };
+  static constexpr int MON_NACC = 256;      // kinetic-energy accumulators per monitor slot (spreads the atomics of the node pass)
+  struct MonSlot { double part[MON_NACC]; int nonfinite; int halo_error; };
   MonSlot *mon_host = nullptr;
-  double *mon_red = nullptr;               // [2][2] device partial sums
+  double *mon_red = nullptr;               // [2][MON_NACC] device partial sums
   cudaEvent_t mon_ev[2] = {nullptr, nullptr};
   int mon_head = 0, mon_pending = 0;
+  // once the caller has asked for a monitor, the last node pass of every wf_step call accumulates the kinetic
+  // energy itself (WfDev::ekin_acc) and wf_monitor_async only copies it; ekin_step = step count that sum belongs to
+  bool mon_seen = false;
+  long ekin_step = -1;
+  int ekin_slot = -1;
   // partition / halo (multi-GPU); see wf_set_mesh_partition
   bool distributed = false, own_stream = false;
   int rank = 0, nranks = 1;

@@ -621,6 +621,21 @@ WF_DI double halo_total(const WfDev &d, int u, int comp, int parity, double own)
 //   the bulk of the pass runs while the force partials of the neighbours are still in flight).
 // On a partitioned mesh the sums of shared nodes are completed with the neighbours' partials (halo_total).
 // ---------------------------------------------------------------------------------------------
+// sum of x over the threads of the warp that are executing this call (any subset: the node pass retires lanes early),
+// added to *dst with one atomic; the order of the atomics is not fixed, the value feeds the step monitor only
+WF_DI void warp_add(double *dst, double x) {
+  const unsigned mask = __activemask();
+  const int lane = threadIdx.x & 31;
+  double t;
+  if (mask == 0xffffffffu) {
+    t = x;
+    for (int o = 16; o > 0; o >>= 1) t += __shfl_down_sync(mask, t, o);
+  } else {
+    t = 0.0;
+    for (unsigned m = mask; m; m &= m - 1) t += __shfl_sync(mask, x, __ffs(m) - 1);
+  }
+  if (lane == __ffs(mask) - 1) atomicAdd(dst, t);
+}
 template <int D, bool SEPARATE_HG, int UNROLL, bool TILE_F = false, bool PREFETCH = false, int MINB = 1>
 __global__ void __launch_bounds__(TPB_N, MINB) k_node_update(WfDev d, WfPar P, int fuse_flags, int phase) {
   const bool fuse_predictor = fuse_flags & 1, udt_recompute = fuse_flags & 2, udt_skip_store = fuse_flags & 4;
@@ -739,6 +754,12 @@ __global__ void __launch_bounds__(TPB_N, MINB) k_node_update(WfDev d, WfPar P, i
   if (d.domtype == 2) {
     double xmin = key_dbl(d.xmin_key[P.xmin_cur]);
     if (xr <= xmin + 1.e-6) { a[0] = 0.0; v[0] = 0.0; }
+  }
+  if (d.ekin_acc) { // step monitor: kinetic energy of the corrected velocities (computeEnergies, Mechanical.C:2145)
+    double s2 = 0.0;
+#pragma unroll
+    for (int c = 0; c < D; c++) s2 += v[c] * v[c];
+    warp_add(d.ekin_acc + (blockIdx.x & 255), 0.5 * mass * s2); // 256 accumulators (wf_engine::MON_NACC), summed by the host
   }
 #pragma unroll
   for (int c = 0; c < D; c++) {
