@@ -335,7 +335,8 @@ def ours(args):
             cpu = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
         except Exception as ex:  # the checker is optional for the bench line
             cpu = {"value": None, "unit": "element-steps/s", "cores": 0, "kind": "port", "sample": f"unavailable: {ex}"}
-    launches_per_step = 4 if world == 1 else 9
+    # N = 1: E1, N1, E2, N2.  N > 1: + halo send / wait / finish after E1, send after E2, wait, node pass of the shared nodes
+    launches_per_step = 4 if world == 1 else 10
     line = {
         "metric": "element-steps/s", "value": value, "unit": "element-steps/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong" if (world > 1 and args.cube) else "weak",
