@@ -323,7 +323,7 @@ def ours(args):
                                            "dram_frac": b / (kms[1 + i] * 1e-3) / 1e9 / peak})
             roof["dram"] = {"bytes_per_step": tot_b, "bytes_per_element_step": tot_b / ne,
                             "GB/s": tot_b / (sum(kms[1:5]) * 1e-3) / 1e9, "frac": tot_b / (sum(kms[1:5]) * 1e-3) / 1e9 / peak,
-                            "note": "ncu dram__bytes_read+write per launch (profiles/r01c_*) / CUDA-event time of this run"}
+                            "note": "ncu dram__bytes_read+write per launch (profiles/r01c_*, r01d_*) / CUDA-event time of this run"}
     if kms is None:  # N > 1: no per-kernel timing hook; the whole fused step per GPU
         roof.update({"achieved": step_gbs, "frac": step_gbs / peak, "kernel": "whole step (E1+N1+E2+N2 + halo kernels)"})
     roof["whole_step"] = {"bytes_per_element_step": alg, "achieved": step_gbs, "frac": step_gbs / peak,
