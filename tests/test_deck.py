@@ -130,3 +130,52 @@ def test_deck_k_reader_free_format_and_two_line_solids(host_bins, tmp_path):
     s = json.loads(r.stdout.strip().splitlines()[-1])
     assert (s["nodxelem"], s["nodes"], s["elements"]) == (4, 5, 2)
     assert s["bc_count"] == [3, 3, 3]          # the three nodes with z = 0
+
+
+# ---- the Python deck loader (weldformfem_b200/deck.py), same checker -----------------------------------------------------
+@pytest.mark.parametrize("name", PINNED)
+def test_python_deck_loader_reproduces_reference_front_end_on_the_oracle(oracle_port, name):
+    """deck.load + DeckSetup.apply drive the plain-C oracle to the state the reference's own main.C + step loop produce:
+    bit for bit, including dt, the BC lists, the rigid surfaces and the thermal settings (CPU only)."""
+    from weldformfem_b200 import deck
+    gold = _gold(name)
+    S = deck.load(os.path.join(DECKS, name + ".json"))
+    o = oracle_port()
+    S.apply(o)
+    assert S.dt == float(gold["dt"][0]) and S.sim_time == float(gold["end_t"][0])
+    info = o.info()
+    assert [info[k] for k in "dim nodxelem n_nodes n_elems bcx bcy bcz".split()] == [int(v) for v in gold["info"][:7]]
+    assert np.array_equal(o.get("m_elnod"), gold["m_elnod"]) and np.array_equal(o.get("x"), gold["x0"])
+    o.step(int(gold["steps"][0]))
+    for key in gold.files:
+        if key.startswith("sN_"):
+            assert np.array_equal(o.get(key[3:]), gold[key]), key
+
+
+def test_python_k_reader_matches_cpp_reader(host_bins, tmp_path):
+    from weldformfem_b200 import deck
+    x, el = deck.read_k(os.path.join(DECKS, "tet_block.k"))
+    s = _summary(host_bins, "file_tet_zones", "--parse-only")
+    assert (el.shape[1], len(x), len(el)) == (s["nodxelem"], s["nodes"], s["elements"])
+    k = tmp_path / "m.k"
+    k.write_text("*NODE\n1,0,0,0\n2,1,0,0\n3,0,1,0\n4,0,0,1\n*ELEMENT_SOLID\n1,1\n1,2,3,4,4,4,4,4\n")
+    x, el = deck.read_k(str(k))
+    assert el.tolist() == [[0, 1, 2, 3]] and x.shape == (4, 3)
+    with pytest.raises(ValueError):
+        k.write_text("*NODE\n1,0,0,0\n*ELEMENT_SOLID\n1,1,1,2,3,4,4,4,4,4\n")
+        deck.read_k(str(k))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["file_tet_contact", "box_axiquad"])
+def test_python_deck_loader_on_the_engine(name):
+    from weldformfem_b200 import deck
+    from weldformfem_b200.domain import Domain_d
+    gold = _gold(name)
+    S = deck.load(os.path.join(DECKS, name + ".json"))
+    eng = S.apply(Domain_d(strict=True))
+    assert abs(S.dt - float(gold["dt"][0])) <= 4e-16 * S.dt
+    eng.step(int(gold["steps"][0]))
+    for key in gold.files:
+        if key.startswith("sN_") and key[3:] not in ("trimesh.node",):
+            assert relerr(eng.get(key[3:]), gold[key]) <= 1e-8, key
