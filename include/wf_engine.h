@@ -83,6 +83,11 @@ int wf_set_mesh(wf_engine *, int n_nodes, int n_elems, const double *x /*N_n*dim
 /* Domain_d::AddBoxLength (Domain_d.C:1136-1504): same nel, numbering, coordinates by accumulation, tet/tri split */
 int wf_gen_box(wf_engine *, const double V[3], const double L[3], double r, int tritet);
 int wf_get_counts(wf_engine *, int *n_nodes, int *n_elems, int *nodel_total);
+/* Internal element order used by the NEXT wf_set_mesh / wf_gen_box / wf_set_mesh_partition (see wf_host_elem_order):
+ * 0 = the caller's numbering, 1 = Morton order (default; the environment variable WF_ELEM_ORDER overrides the
+ * default).  Every array that crosses this ABI stays in the caller's numbering whatever the mode; wf_device_ptr
+ * of an element array exposes the internal order ("elem_perm" via wf_get_array gives perm[internal] = user). */
+int wf_set_elem_order(wf_engine *, int mode);
 int wf_set_axisymm_vol_weight(wf_engine *, int on); /* setAxiSymm(vol_weight), Domain_d.h:666 */
 
 /* ---- material / options / boundary conditions -------------------------------------------------- */
@@ -259,6 +264,11 @@ int wf_host_axis_plane_mesh(int dimension, int mesh_id, int axis, int positaxiso
  * tests compare them bit for bit with a numpy restatement. */
 int wf_host_force_tiles(int n_nodes, int n_elems, int nodxelem, int dim, const unsigned *elnod, long long *info,
                         unsigned char *tidx, long long *ptr, unsigned *slots, unsigned char *tab);
+/* Internal element order of the engine: perm[internal] = user element id.  mode 0 = identity,
+ * 1 = Morton order of the quantised element centroids (ascending (key, user id)).  Integer artefact, bit-exact
+ * against the numpy restatement in tests/test_host_mesh.py. */
+int wf_host_elem_order(int dim, int nodxelem, int n_nodes, int n_elems, const double *x, const unsigned *elnod, int mode,
+                       int *perm);
 const char *wf_version(void);
 
 #ifdef __cplusplus

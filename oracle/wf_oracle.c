@@ -617,7 +617,23 @@ static void calcElemPressureANP_Nodal(wfo_domain *d) {
   free(pn);
 }
 
+/* TEST-ONLY (press_variant 2): the historical incremental pressure law the validation/ files were printed with,
+ * p = -tr(sigma_prev)/3 - K tr(D) dt  — the commented-out Domain_d::calcElemPressure_Hex (Mechanical.C:576-603) =
+ * calc_elem_pressure_from_strain (f90_ver/src/Mechanical.f90:525-547), one Gauss point.  It exists so that the
+ * restated hexa hourglass can be pinned against every printed digit of validation/1elem_3d_red_int_f_0.06.txt;
+ * neither the engine nor the reference's current solver has it. */
+static void calcElemPressure_Historical(wfo_domain *d) {
+  for (int e = 0; e < d->ne; e++) {
+    const double *D = d->m_str_rate + (size_t)6 * e, *sg = d->m_sigma + (size_t)6 * e;
+    double press_inc = (D[0] + D[1] + D[2]) * d->dt;
+    press_inc = -press_inc / 1.0;
+    const double trace = sg[0] + sg[1] + sg[2];
+    d->p[e] = -1.0 / 3.0 * trace + d->Kbulk * press_inc;
+  }
+}
+
 static void pressure(wfo_domain *d) { /* Solver_explicit.C:735-746 */
+  if (d->press_variant == 2) { calcElemPressure_Historical(d); return; }
   if (d->press_variant == 0) { if (d->dim == 3) calcElemPressure(d); else calcElemPressureLocal(d); }
   else if (d->press_variant == 1) calcElemPressureANP(d);
   else if (d->press_variant == 3) calcElemPressureANP_Nodal(d);

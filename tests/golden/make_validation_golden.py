@@ -1,0 +1,64 @@
+"""Transcribe the numbers of /root/reference/validation/*.txt that pin the hexa hourglass + step sequence into
+tests/golden/validation_pins.json (the reference tree is absent on the GPU box and in CI).
+
+    python tests/golden/make_validation_golden.py
+
+Blocks taken (file:lines):
+  1elem_3d_red_int_f_0.06.txt:5-42    "C++" block, hourglass 0.06: DISPLACEMENTS / VELOCITIES / ACCEL / FORCES, 8 nodes
+  1elem_3d_red_int_f_0.06.txt:73-108  "NO HG" block, same four tables
+  1elem_3d_red_int_f_0.06.txt:44-68   F90 block after 126 steps (Disp / Vel)
+  several dts.txt:1-9, 30-38          F90 blocks after 10 and 100 steps (Disp)
+  4elem_red_0.06_f90_1step.txt        F90, 2x2x2 elements, one step of dt = 2e-6: sigma / shear_stress of a loaded element
+  1step_red_int_cube3D_hf_c_0.06.txt:6-9  initial dHdx*detJ matrix
+"""
+import json
+import os
+import re
+
+REF = "/root/reference/validation"
+OUT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "validation_pins.json")
+
+
+def table(lines, start, n=8):
+    return [[float(t) for t in lines[start + i].split()] for i in range(n)]
+
+
+def f90_nodes(text, kind, n=8):
+    out = {}
+    for m in re.finditer(r"nod\s+(\d+)\s+%s\s+(\S+)\s+(\S+)\s+(\S+)" % kind, text):
+        out.setdefault(int(m.group(1)) - 1, [float(m.group(i)) for i in (2, 3, 4)])
+    return [out[i] for i in range(n)]
+
+
+def main():
+    pins = {}
+    L = open(os.path.join(REF, "1elem_3d_red_int_f_0.06.txt")).read().split("\n")
+    idx = [i for i, s in enumerate(L) if s.strip() == "DISPLACEMENTS"]
+    for name, i0 in (("cxx_hg_0.06", idx[0]), ("cxx_no_hg", idx[1])):
+        blk = {}
+        j = i0
+        for key in ("DISPLACEMENTS", "VELOCITIES", "ACCEL", "FORCES"):
+            while L[j].strip() != key:
+                j += 1
+            blk[key] = table(L, j + 1)
+        pins[name] = blk
+    txt = "\n".join(L)
+    f90 = txt[txt.index("F90"):txt.index("NO HG")]
+    pins["f90_126_steps"] = {"Disp": f90_nodes(f90, "Disp"), "Vel": f90_nodes(f90, "Vel")}
+    sd = open(os.path.join(REF, "several dts.txt")).read()
+    pins["f90_10_steps"] = {"Disp": f90_nodes(sd[:sd.index("C++")], "Disp")}
+    rest = sd[sd.index("100 dt"):]
+    pins["f90_100_steps"] = {"Disp": f90_nodes(rest[:rest.index("Correction")], "Disp")}
+    one = open(os.path.join(REF, "4elem_red_0.06_f90_1step.txt")).read()
+    m = re.search(r"shear_stress\s+(2112820\S+)(?:\s+\S+){7}\s+(-4225640\S+)\s+elem\s+7 , sigma\s+(\S+)(?:\s+\S+){7}\s+(\S+)", one)
+    pins["f90_8elem_1step"] = {"tau_xx": float(m.group(1)), "tau_zz": float(m.group(2)), "sigma_xx": float(m.group(3)),
+                               "sigma_zz": float(m.group(4))}
+    dh = open(os.path.join(REF, "1step_red_int_cube3D_hf_c_0.06.txt")).read().split("\n")
+    k = [i for i, s in enumerate(dh) if "INITIAL DERIVATIVE MATRIX" in s][0]
+    pins["dHdx_detJ"] = table(dh, k + 1, 3)
+    json.dump(pins, open(OUT, "w"), indent=1)
+    print("wrote", OUT)
+
+
+if __name__ == "__main__":
+    main()

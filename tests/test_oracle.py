@@ -12,6 +12,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.join(HERE, "golden"))
 from cases_golden import CONTACT_ARRAYS, FLOAT_ARRAYS, GOLDEN, INT_ARRAYS, THERMAL_ARRAYS  # noqa: E402
 
+from parity_util import relerr  # noqa: E402
 from weldformfem_b200 import cases  # noqa: E402
 
 
@@ -76,27 +77,141 @@ def test_oracle_matches_compiled_reference_live(case, oracle_port, oracle_ref):
         assert np.array_equal(a.get(nm), b.get(nm)), nm
 
 
-def test_validation_file_pins(oracle_port):
-    """validation/1elem_3d_red_int_f_0.06.txt (C++ block :5-42, "NO HG" block :73-83) were printed by older
-    code (incremental pressure law); the current algorithm agrees to ~1 %."""
+def _validation_pins():
+    import json
+    return json.load(open(os.path.join(HERE, "golden", "validation_pins.json")))
+
+
+def _historical_run(oracle_port, nsteps, hexa_hg=0.06, case=None):
+    """The step sequence the validation/ files were printed with, driven member by member: the historical
+    incremental pressure law (test-only press_algorithm 2 of the port = the commented-out calcElemPressure_Hex,
+    Mechanical.C:576-603 = f90_ver/src/Mechanical.f90:525-547) and calcElemDensity EVERY step (the sequence of the
+    reference's CUDA branch, Solver_explicit.C:601-608; its CPU branch freezes rho after init), everything else the
+    current functions in the order of SolveChungHulbert."""
+    case = case or dataclasses.replace(cases.c1_one_hex(hexa_hg=hexa_hg), press=2)
+    d = oracle_port()
+    case.apply(d)
+    for _ in range(nsteps):
+        d.call("UpdatePrediction"); d.call("ImposeBCVAllDim")
+        d.call("calcElemJAndDerivatives"); d.call("CalcElemVol"); d.call("calcElemDensity")
+        d.call("CalcNodalVol"); d.call("CalcNodalMassFromVol")
+        d.call("calcElemStrainRates"); d.call("calcElemPressure"); d.call("CalcStressStrain", case.timestep)
+        d.call("calcElemForces"); d.call("calcElemHourglassForces"); d.call("assemblyForces")
+        d.call("calcAccel"); d.call("ImposeBCAAllDim"); d.call("UpdateCorrectionAccVel"); d.call("ImposeBCVAllDim")
+        d.call("UpdateCorrectionPos")
+    return d
+
+
+def _printed_equal(got, printed, digits=7):
+    """every number equals the printed one after rounding to the printed number of significant digits (%.6e)"""
+    got, printed = np.asarray(got, dtype=np.float64), np.asarray(printed, dtype=np.float64)
+    assert got.shape == printed.shape
+    for g, w in zip(got.ravel(), printed.ravel()):
+        if abs(w) < 1e-300:
+            assert abs(g) < 1e-300, (g, w)
+        else:
+            assert float(f"{g:.{digits - 1}e}") == w or abs(g - w) <= 1.0000001 * 10.0 ** (np.floor(np.log10(abs(w))) - digits + 1), (g, w)
+
+
+@pytest.mark.parametrize("block,hexa_hg", [("cxx_hg_0.06", 0.06), ("cxx_no_hg", 0.0)])
+def test_validation_1elem_every_printed_digit(block, hexa_hg, oracle_port):
+    """validation/1elem_3d_red_int_f_0.06.txt, C++ blocks (:5-42 with hourglass 0.06, :73-108 without), 126 steps
+    of dt = 0.8e-5: displacements, velocities, accelerations AND forces agree with every printed digit (7 significant:
+    <= 5e-7 relative per entry; the accelerations are differences of forces 1e6 times larger).  This pins the restated
+    hexa viscous hourglass (f90_ver/src/Mechanical.f90:241-344: sign table, vol^0.6666666, rho, 0.25, cs0, the
+    subtraction in assemblyForces) and the step sequence; a15b of SURVEY.md 8(a)."""
+    pins = _validation_pins()[block]
+    d = _historical_run(oracle_port, 126, hexa_hg)
+    _printed_equal(d.get("u").reshape(-1, 3), pins["DISPLACEMENTS"])
+    _printed_equal(d.get("v").reshape(-1, 3), pins["VELOCITIES"])
+    acc = np.array(pins["ACCEL"])
+    acc[np.abs(acc) < 1e-300] = 0.0          # node 0 prints denormal garbage (9.88e-324) on its constrained components
+    _printed_equal(d.get("a").reshape(-1, 3), acc)
+    _printed_equal(d.get("m_fi").reshape(-1, 3), pins["FORCES"])
+    # a wrong exponent (2/3 instead of 0.6666666) or coefficient would not survive: the lateral displacement of the
+    # top nodes exists only through the hourglass force
+    if hexa_hg:
+        assert abs(d.get("u").reshape(-1, 3)[4, 0] / -6.768332e-06 - 1) < 1e-6
+
+
+def test_validation_f90_blocks(oracle_port):
+    """The F90 program's own output (1elem_3d_red_int_f_0.06.txt:44-68, 'several dts.txt'): it carries single-precision
+    contamination of its constants (M diag 0.98125004386 for 0.98125), so it agrees to ~1e-6 of the array maximum, not
+    to the last digit.  Tolerance 1e-5 relative to max |array| (the metric of BASELINE.json)."""
+    pins = _validation_pins()
+    for key, nsteps in (("f90_10_steps", 10), ("f90_100_steps", 100), ("f90_126_steps", 126)):
+        d = _historical_run(oracle_port, nsteps)
+        want = np.array(pins[key]["Disp"])
+        assert relerr(d.get("u").reshape(-1, 3), want) < 1e-5, (key, relerr(d.get("u").reshape(-1, 3), want))
+        if "Vel" in pins[key]:
+            assert relerr(d.get("v").reshape(-1, 3), np.array(pins[key]["Vel"])) < 1e-5
+
+
+def test_validation_f90_8_elements_one_step(oracle_port):
+    """validation/4elem_red_0.06_f90_1step.txt: 2x2x2 hexes of 0.05, bottom clamped, top v_z = -1, one step of
+    dt = 0.8e-5/4: stress of the loaded elements (the F90 nodal mass is total mass / node count, so its accelerations
+    are not this algorithm's; stress does not depend on the mass in the first step)."""
+    pins = _validation_pins()["f90_8elem_1step"]
+
+    class C8(cases.Case):
+        def bc_nodes(self):
+            out = []
+            for n in range(27):
+                if n // 9 == 0:
+                    out += [(n, 0, 0.0), (n, 1, 0.0), (n, 2, 0.0)]
+                if n // 9 == 2:
+                    out.append((n, 2, -1.0))
+            return out
+    c = C8("c8", 3, (2, 2, 2), 0.05, E=206e9, nu=0.3, rho0=7850.0, model=cases.BILINEAR, sy0=1e10, K=0.0, m=1.0,
+           dt=2e-6, hexa_hg=0.06, press=2)
+    d = _historical_run(oracle_port, 1, case=c)
+    sig = d.get("m_sigma").reshape(-1, 6)[4:]     # the four elements under the moving face
+    tau = d.get("m_tau").reshape(-1, 6)[4:]
+    assert np.allclose(sig[:, 0], pins["sigma_xx"], rtol=1e-7) and np.allclose(sig[:, 2], pins["sigma_zz"], rtol=1e-7)
+    assert np.allclose(tau[:, 0], pins["tau_xx"], rtol=1e-7) and np.allclose(tau[:, 2], pins["tau_zz"], rtol=1e-7)
+
+
+def test_validation_shape_derivative_matrix(oracle_port):
+    """validation/1step_red_int_cube3D_hf_c_0.06.txt:6-9: dHdx * detJ of the 0.1 cube (+-3.125e-4, signs per node)."""
+    want = np.array(_validation_pins()["dHdx_detJ"])
+    d = oracle_port()
+    cases.c1_one_hex().apply(d)
+    d.call("calcElemJAndDerivatives")
+    got = np.stack([d.get(f"m_dH_detJ_d{c}").reshape(-1, 8)[0] for c in "xyz"])
+    assert np.array_equal(np.sign(got), np.sign(want))
+    assert np.abs(got / want - 1).max() < 1e-6      # the box is padded by 1e-6 (cases.Case.apply); F90 prints ...0006E-004
+
+
+def test_validation_fixture_is_the_reference_file():
+    """the committed pins are a transcription of the reference's files (checked whenever the reference tree is here)"""
+    if not os.path.isdir("/root/reference/validation"):
+        pytest.skip("reference tree not present")
+    import json, subprocess, sys, tempfile
+    before = _validation_pins()
+    sys.path.insert(0, os.path.join(HERE, "golden"))
+    import make_validation_golden as mk
+    out = mk.OUT
+    try:
+        with tempfile.TemporaryDirectory() as td:
+            mk.OUT = os.path.join(td, "pins.json")
+            mk.main()
+            assert json.load(open(mk.OUT)) == before
+    finally:
+        mk.OUT = out
+
+
+def test_current_pressure_law_differs_from_the_validation_files(oracle_port):
+    """With the pressure law the reference ships today the same run is ~1 % off the printed numbers:
+    documents why the tight pin needs the historical law."""
     d = oracle_port()
     cases.c1_one_hex().apply(d)
     d.step(126)
     u = d.get("u").reshape(-1, 3)
-    assert abs(u[4, 2] - (-1.008000e-03)) < 1e-12                    # prescribed top displacement, exact
-    assert abs(u[1, 0] / 2.991992e-04 - 1) < 0.015                   # :7
-    assert abs(u[4, 0] / -6.768332e-06 - 1) < 0.015                  # :10
-    v = d.get("v").reshape(-1, 3)
-    assert abs(v[1, 0] / 3.039238e-01 - 1) < 0.015                   # :16
-    f = d.get("m_fi").reshape(-1, 3)
-    assert abs(f[0, 2] / 5.249056e+06 - 1) < 0.015                   # :34
+    assert abs(u[4, 2] - (-1.008000e-03)) < 1e-12
+    assert 1e-3 < abs(u[1, 0] / 2.991992e-04 - 1) < 0.015
     c = d.consts()                                                   # :112-114
     assert abs(c["alpha"] - 0.35001649984) < 1e-10 and abs(c["beta"] - 0.65152149311) < 1e-10
     assert abs(c["gamma"] - 1.1499835002) < 1e-9
-    d2 = oracle_port()
-    cases.c1_one_hex(hexa_hg=0.0).apply(d2)
-    d2.step(126)
-    assert abs(d2.get("u").reshape(-1, 3)[1, 0] / 1.530002e-04 - 1) < 0.015   # :77
 
 
 def test_hourglass_orthogonal_to_rigid_and_linear_fields(oracle_port):

@@ -336,3 +336,42 @@ def test_remesh_handoff_new_engine_with_mapped_fields(key, oracle_port):
         assert relerr(b.get(nm).reshape(-1, c)[nperm], a.get(nm).reshape(-1, c)) <= 1e-9, nm
     for nm, c in (("m_tau", 6), ("pl_strain", 1), ("p", 1)):
         assert relerr(b.get(nm).reshape(-1, c), a.get(nm).reshape(-1, c)[eperm]) <= 1e-8, nm
+
+
+# ---- internal element order (Morton bricks) is invisible at the ABI ------------------------------
+@pytest.mark.parametrize("key", ["hex", "tet", "axiquad", "pstri", "hex_stab"])
+@pytest.mark.parametrize("strict", [True, False], ids=["strict", "fast"])
+def test_elem_order_is_invisible(key, strict, oracle_port):
+    """The engine keeps its element arrays in Morton order; every array crosses the ABI in the caller's numbering and
+    every nodal sum keeps the caller's (= reference's) element order, so the strict flavour is BIT-identical with and
+    without the reordering, and the fast flavour differs only by the association of its per-tile partial sums."""
+    from weldformfem_b200.domain import Domain_d
+    case = SMALL[key]
+    engs = []
+    for mode in (0, 1):
+        e = Domain_d(strict=strict, elem_order=mode)
+        case.apply(e)
+        e.step(20)
+        engs.append(e)
+    perm0, perm1 = engs[0].get("elem_perm"), engs[1].get("elem_perm")
+    assert np.array_equal(perm0, np.arange(perm0.size))
+    assert np.array_equal(np.sort(perm1), np.arange(perm1.size)) and not np.array_equal(perm1, perm0)
+    for nm in _names(case):
+        a, b = engs[0].get(nm), engs[1].get(nm)
+        if strict:
+            assert np.array_equal(a, b), nm
+        else:
+            assert relerr(b, a) < 1e-12, (nm, relerr(b, a))
+    ref = oracle_port()
+    case.apply(ref)
+    ref.step(20)
+    compare(engs[1], ref, _names(case), 1e-11 if strict else 1e-9, f"{key} reordered vs oracle")
+    # element arrays written through the ABI land on the caller's element
+    tau = np.arange(perm1.size * 6, dtype=np.float64).reshape(-1, 6)
+    engs[1].set("m_tau", tau.ravel())
+    assert np.array_equal(engs[1].get("m_tau").reshape(-1, 6), tau)
+    pl = np.arange(perm1.size, dtype=np.float64)
+    engs[1].set("pl_strain", pl)
+    assert np.array_equal(engs[1].get("pl_strain"), pl)
+    for e in engs:
+        e.close()

@@ -6,7 +6,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 from weldformfem_b200 import cases
 from weldformfem_b200.domain import Domain_d
-from bench import linear_velocity, ALG_BYTES
+from bench import linear_velocity
 
 ap = argparse.ArgumentParser()
 ap.add_argument("--n", type=int, default=215)
@@ -20,7 +20,7 @@ case = {"hex": cases.c3_hexes, "tet": cases.c2_tets, "quad": cases.c4_axisymm_qu
 base = None
 for cfg in a.configs:
     kv = dict(x.split("=") for x in cfg.split(",") if x)
-    d = Domain_d(strict=a.strict)
+    d = Domain_d(strict=a.strict, elem_order=int(kv["order"]) if "order" in kv else None)
     case.apply(d)
     for name, idx in (("e1", 0), ("n1", 1), ("e2", 2), ("n2", 3)):
         if name in kv:
@@ -40,6 +40,6 @@ for cfg in a.configs:
         for nm in st:
             diff[nm] = float(np.abs(st[nm] - base[nm]).max() / max(np.abs(base[nm]).max(), 1e-300))
     print(json.dumps({"cfg": cfg, "preload": a.preload, "ms_per_step": {k: round(v / a.steps, 4) for k, v in zip(["pred", "E1", "N1", "E2", "N2"], ms)},
-                      "total_ms": round(tot / a.steps, 4), "rate": rate, "frac_roofline": rate * ALG_BYTES[a.kind] / 6556.8e9,
+                      "total_ms": round(tot / a.steps, 4), "rate": rate, 
                       "plastic": float((st["pl_strain"] > 0).mean()), "diff_vs_first": diff}), flush=True)
     d.close()

@@ -495,6 +495,8 @@ extern "C" int wf_SearchExtNodes(wf_engine *E) {
     if (E->h_ext[n]) { ext_index[n] = (int)ext_list.size(); ext_list.push_back(n); }
   C.n_ext = (int)ext_list.size();
   std::vector<int> xf_soa((size_t)facenod * n_xf), xf_elem(felem.begin(), felem.begin() + n_xf);
+  if (!E->iperm.empty()) // device element arrays are in the internal element order
+    for (int f = 0; f < n_xf; f++) xf_elem[f] = E->iperm[xf_elem[f]];
   std::vector<int> ptr(C.n_ext + 1, 0);
   for (int f = 0; f < n_xf; f++)
     for (int q = 0; q < facenod; q++) {

@@ -14,6 +14,7 @@
 //     element id), so gathers sum in exactly the reference's order and a warp reads 128 B rows.
 #pragma once
 #include <stdint.h>
+#include <vector_types.h>
 
 #define WF_MAXK 8
 #define WF_EBLK 128 /* elements per CTA of the element passes */
@@ -59,8 +60,10 @@ struct WfDev {
   int *comm_error;                   /* [1] set when a wait timed out */
   int n_halo, n_uniq, n_neigh;
 
-  /* elements */
+  /* elements (arrays in the engine's INTERNAL element order, see wf_host_elem_order) */
   const int *elnod;                  /* [k][ep] */
+  const int *e_user;                 /* [ep] user id of internal element e, NULL = identity (only the reference quirks
+                                      * that index a NODAL array with an element id read it) */
   double *tau;                       /* [6][ep] */
   double *sigma;                     /* [6][ep] (optional per step) */
   double *eps;                       /* [6][ep] (optional) */
@@ -73,7 +76,9 @@ struct WfDev {
   const int *blk_nodes;
   const unsigned short *lidx;        /* [k][ep] */
   int blk_umax;                      /* longest unique list */
-  const int *blk_pad;                /* [nblk][round32(blk_umax)] the same lists at a fixed pitch, -1 padded (no blk_off round trip) */
+  int blk_pitch;                     /* pitch of blk_pad and of the staged copies in shared memory: blk_umax rounded up to 32;
+                                      * hexahedra with blk_umax <= 288: exactly 288 (compile-time pitch of k_elem_main_hex_brick) */
+  const int *blk_pad;                /* [nblk][blk_pitch] the same lists at a fixed pitch, -1 padded (no blk_off round trip) */
   const int *pos;                    /* [k][ep] offset of (e, ln) in fsell: dim*q - (dim-1)*(n&31), q = sell index */
   double *fsell, *fsell_hg;          /* [slice][j][dim][32] node-ordered element (and hourglass) forces */
   /* tile-reduced forces (hexa, WF_FAST only; NULL when the mesh does not qualify): instead of one force record per
@@ -87,6 +92,8 @@ struct WfDev {
   const long long *tf_ptr;           /* [nslices+1] */
   const unsigned *tf_slots;
   const unsigned char *tf_idx;       /* [k][ep] (hexahedra) */
+  const uint4 *lidx_pk;              /* [ep] hexahedra: the eight lidx values of an element in one 16 B record */
+  const uint2 *tf_idx_pk;            /* [ep] hexahedra: the eight tf_idx values of an element in one 8 B record */
   /* tetrahedra: corners of different elements of a tile DO share nodes, so the tile sum is pulled instead: every
    * element drops its k*dim force values in shared memory and lane u adds up the entries of unique node u listed in
    * the tile's incidence table (ascending element, then corner: a fixed order).  Table of tile w at

@@ -67,6 +67,7 @@ extern "C" int wf_create(wf_engine **out, int dim, int nodxelem, int domtype, in
   E->P.w = (et == ET_HEX8) ? 8.0 : (et == ET_TET4 ? 1.0 / 6.0 : (et == ET_QUAD4 ? 4.0 : 0.5));
   E->P.stab_simple = 1;
   E->P.hg_stiff = 0.1;
+  if (const char *t = getenv("WF_ELEM_ORDER")) E->order_mode = atoi(t) != 0 ? 1 : 0;
   select_flavour(E);
   *out = E;
   return 0;
@@ -126,7 +127,26 @@ static int upload_mesh(wf_engine *E, int nn, int ne, const double *x, const unsi
   E->h_nodel.resize((size_t)ne * k); E->h_nodel_loc.resize((size_t)ne * k);
   if (wf_host_nodel(nn, ne, k, elnod, E->h_offset.data(), E->h_count.data(), E->h_nodel.data(), E->h_nodel_loc.data()))
     FAIL("connectivity entry out of range");
-  // sliced-ELL packing of slot = e*k + ln
+  // internal element order (wf_host_elem_order): the device arrays, the CTA / tile tables and the slot ids below use
+  // it; the node->element LISTS keep the order of setNodElem (ascending user element id)
+  E->perm.clear(); E->iperm.clear();
+  std::vector<unsigned> el_int;
+  const unsigned *eli = elnod; // connectivity in internal order, reference layout [e*k + ln]
+  if (E->order_mode != 0 && ne > 1) {
+    E->perm.resize(ne); E->iperm.resize(ne);
+    if (wf_host_elem_order(dim, k, nn, ne, x, elnod, E->order_mode, E->perm.data())) FAIL("element ordering failed");
+    bool ident = true;
+    for (int e = 0; e < ne; e++) { E->iperm[E->perm[e]] = e; ident = ident && E->perm[e] == e; }
+    if (ident) { E->perm.clear(); E->iperm.clear(); }
+    else {
+      el_int.resize((size_t)ne * k);
+      for (int e = 0; e < ne; e++) memcpy(&el_int[(size_t)e * k], elnod + (size_t)E->perm[e] * k, sizeof(unsigned) * k);
+      eli = el_int.data();
+    }
+  }
+  const int *ip = E->iperm.empty() ? nullptr : E->iperm.data();
+  auto internal = [&](int e_user) { return ip ? ip[e_user] : e_user; };
+  // sliced-ELL packing of slot = e*k + ln (e = internal id)
   std::vector<long long> sell_ptr(d.nslices + 1);
   long long tot = 0;
   for (int s = 0; s < d.nslices; s++) {
@@ -141,7 +161,7 @@ static int upload_mesh(wf_engine *E, int nn, int ne, const double *x, const unsi
     const long long base = sell_ptr[n >> 5];
     const int off = E->h_offset[n];
     for (int j = 0; j < E->h_count[n]; j++)
-      slots[(size_t)(base + (long long)j * 32 + (n & 31))] = E->h_nodel[off + j] * k + E->h_nodel_loc[off + j];
+      slots[(size_t)(base + (long long)j * 32 + (n & 31))] = internal(E->h_nodel[off + j]) * k + E->h_nodel_loc[off + j];
   }
   // offset of (e, ln) in the node-ordered force buffer [slice][j][dim][32]: dim*q - (dim-1)*lane
   NEED((long long)dim * tot < 4294967295LL, "node-ordered force buffer exceeds 32-bit offsets");
@@ -160,7 +180,21 @@ static int upload_mesh(wf_engine *E, int nn, int ne, const double *x, const unsi
   if (dalloc(E, &dptr, sell_ptr.size()) || dalloc(E, &dslots, slots.size()) || dalloc(E, &dpos, E->h_pos.size()) ||
       dalloc(E, &d.fsell, (size_t)dim * tot))
     return 1;
-  CK(cudaMemcpyAsync(dpos, E->h_pos.data(), E->h_pos.size() * sizeof(int), cudaMemcpyHostToDevice, E->stream));
+  if (ip) { // device copy indexed by internal id
+    std::vector<unsigned> pos_int(E->h_pos.size(), 0u);
+    for (int n = 0; n < k; n++)
+      for (int e = 0; e < ne; e++) pos_int[(size_t)n * ep_ + e] = E->h_pos[(size_t)n * ep_ + E->perm[e]];
+    CK(cudaMemcpyAsync(dpos, pos_int.data(), pos_int.size() * sizeof(int), cudaMemcpyHostToDevice, E->stream));
+    CK(cudaStreamSynchronize(E->stream));
+    int *dperm;
+    if (dalloc(E, &dperm, (size_t)ep_) || dalloc(E, &E->iperm_d, (size_t)ep_)) return 1;
+    CK(cudaMemcpyAsync(dperm, E->perm.data(), sizeof(int) * ne, cudaMemcpyHostToDevice, E->stream));
+    CK(cudaMemcpyAsync(E->iperm_d, E->iperm.data(), sizeof(int) * ne, cudaMemcpyHostToDevice, E->stream));
+    d.e_user = dperm;
+  } else {
+    CK(cudaMemcpyAsync(dpos, E->h_pos.data(), E->h_pos.size() * sizeof(int), cudaMemcpyHostToDevice, E->stream));
+    d.e_user = nullptr; E->iperm_d = nullptr;
+  }
   d.pos = dpos;
   CK(cudaMemcpyAsync(dptr, sell_ptr.data(), sell_ptr.size() * sizeof(long long), cudaMemcpyHostToDevice, E->stream));
   CK(cudaMemcpyAsync(dslots, slots.data(), slots.size() * sizeof(int), cudaMemcpyHostToDevice, E->stream));
@@ -169,7 +203,7 @@ static int upload_mesh(wf_engine *E, int nn, int ne, const double *x, const unsi
   {
     std::vector<int> el((size_t)k * d.ep, 0);
     for (int e = 0; e < ne; e++)
-      for (int n = 0; n < k; n++) el[(size_t)n * d.ep + e] = (int)elnod[(size_t)e * k + n];
+      for (int n = 0; n < k; n++) el[(size_t)n * d.ep + e] = (int)eli[(size_t)e * k + n];
     int *del;
     if (dalloc(E, &del, el.size())) return 1;
     CK(cudaMemcpyAsync(del, el.data(), el.size() * sizeof(int), cudaMemcpyHostToDevice, E->stream));
@@ -186,13 +220,13 @@ static int upload_mesh(wf_engine *E, int nn, int ne, const double *x, const unsi
     int umax = 0;
     for (int b = 0; b < nblk; b++) {
       const int e0 = b * WF_EBLK, e1 = std::min(ne, e0 + WF_EBLK);
-      tmp.assign(elnod + (size_t)e0 * k, elnod + (size_t)e1 * k);
+      tmp.assign(eli + (size_t)e0 * k, eli + (size_t)e1 * k);
       std::sort(tmp.begin(), tmp.end());
       tmp.erase(std::unique(tmp.begin(), tmp.end()), tmp.end());
       for (int e = e0; e < e1; e++)
         for (int n = 0; n < k; n++)
           lidx[(size_t)n * d.ep + e] =
-              (unsigned short)(std::lower_bound(tmp.begin(), tmp.end(), (int)elnod[(size_t)e * k + n]) - tmp.begin());
+              (unsigned short)(std::lower_bound(tmp.begin(), tmp.end(), (int)eli[(size_t)e * k + n]) - tmp.begin());
       bnodes.insert(bnodes.end(), tmp.begin(), tmp.end());
       boff[b + 1] = (int)bnodes.size();
       umax = std::max(umax, (int)tmp.size());
@@ -205,7 +239,8 @@ static int upload_mesh(wf_engine *E, int nn, int ne, const double *x, const unsi
     CK(cudaStreamSynchronize(E->stream));
     d.blk_off = doff; d.blk_nodes = dnodes; d.lidx = dl; d.blk_umax = umax;
     {
-      const int pitch = (umax + 31) / 32 * 32;
+      const int pitch = (k == 8 && umax <= 288) ? 288 : (umax + 31) / 32 * 32; // 288: see WfDev::blk_pitch
+      d.blk_pitch = pitch;
       std::vector<int> pad((size_t)nblk * pitch, -1);
       for (int b = 0; b < nblk; b++) std::copy(bnodes.begin() + boff[b], bnodes.begin() + boff[b + 1], pad.begin() + (size_t)b * pitch);
       int *dpad;
@@ -216,10 +251,11 @@ static int upload_mesh(wf_engine *E, int nn, int ne, const double *x, const unsi
     }
     // tile-reduced force path (WfDev::ftile): tables built on the host (wf_force_tiles_build, wf_mesh.cpp)
     d.ftile = nullptr; d.tf_ptr = nullptr; d.tf_slots = nullptr; d.tf_idx = nullptr; d.tf_tab = nullptr;
+    d.lidx_pk = nullptr; d.tf_idx_pk = nullptr;
     d.tf_stride = 0; d.tf_tpitch = 0;
     if (dim == 3) { // 2D (1M quads, measured): rounds form E2 0.080 -> 0.099 ms, pull form 0.105 ms, N2 unchanged: not used
       WfForceTiles T;
-      wf_force_tiles_build(nn, ne, k, dim, d.ep, elnod, T);
+      wf_force_tiles_build(nn, ne, k, dim, d.ep, eli, T);
       if (T.usable) {
         long long *dtp; unsigned *dts;
         if (dalloc(E, &dtp, T.ptr.size()) || dalloc(E, &dts, std::max<size_t>(T.slots.size(), 1)) ||
@@ -232,6 +268,20 @@ static int upload_mesh(wf_engine *E, int nn, int ne, const double *x, const unsi
           if (dalloc(E, &dti, T.tidx.size())) return 1;
           CK(cudaMemcpyAsync(dti, T.tidx.data(), T.tidx.size(), cudaMemcpyHostToDevice, E->stream));
           d.tf_idx = dti;
+          // the same local indices as one record per element (k_elem_main_hex_brick)
+          std::vector<unsigned short> lpk((size_t)8 * d.ep, 0);
+          std::vector<unsigned char> tpk((size_t)8 * d.ep, 0);
+          for (int e = 0; e < ne; e++)
+            for (int n = 0; n < 8; n++) {
+              lpk[(size_t)e * 8 + n] = lidx[(size_t)n * d.ep + e];
+              tpk[(size_t)e * 8 + n] = T.tidx[(size_t)n * d.ep + e];
+            }
+          uint4 *dl4; uint2 *dt2;
+          if (dalloc(E, &dl4, (size_t)d.ep) || dalloc(E, &dt2, (size_t)d.ep)) return 1;
+          CK(cudaMemcpyAsync(dl4, lpk.data(), lpk.size() * sizeof(unsigned short), cudaMemcpyHostToDevice, E->stream));
+          CK(cudaMemcpyAsync(dt2, tpk.data(), tpk.size(), cudaMemcpyHostToDevice, E->stream));
+          CK(cudaStreamSynchronize(E->stream));
+          d.lidx_pk = dl4; d.tf_idx_pk = dt2;
         } else {
           unsigned char *dtab;
           if (dalloc(E, &dtab, T.tab.size())) return 1;
@@ -289,6 +339,13 @@ extern "C" int wf_gen_box(wf_engine *E, const double V[3], const double L[3], do
   std::vector<unsigned> el((size_t)b.ne * b.k);
   wf_host_gen_box(V, L, r, tritet, x.data(), el.data());
   return upload_mesh(E, (int)b.nn, (int)b.ne, x.data(), el.data());
+}
+
+extern "C" int wf_set_elem_order(wf_engine *E, int mode) {
+  NEED(!E->meshed, "wf_set_elem_order before the mesh is set");
+  NEED(mode == 0 || mode == 1, "element order mode must be 0 (caller's numbering) or 1 (Morton)");
+  E->order_mode = mode;
+  return 0;
 }
 
 extern "C" int wf_get_counts(wf_engine *E, int *nn, int *ne, int *ntot) {
@@ -1237,6 +1294,13 @@ static bool lookup(wf_engine *E, const std::string &nm, ArrayRef &r, bool for_wr
   }
   auto hosti = [&](const void *p, size_t b) { r.kind = K_INT_HOST; r.host = p; r.bytes = b; return !for_write; };
   if (nm == "m_elnod") return hosti(E->h_elnod.data(), E->h_elnod.size() * sizeof(unsigned));
+  if (nm == "elem_perm") { // perm[internal] = user (identity when the mesh was not reordered)
+    if (E->perm_out.size() != (size_t)E->ne) {
+      E->perm_out.resize(E->ne);
+      for (int e = 0; e < E->ne; e++) E->perm_out[e] = E->perm.empty() ? e : E->perm[e];
+    }
+    return hosti(E->perm_out.data(), E->perm_out.size() * sizeof(int));
+  }
   if (nm == "m_nodel") return hosti(E->h_nodel.data(), E->h_nodel.size() * sizeof(int));
   if (nm == "m_nodel_loc") return hosti(E->h_nodel_loc.data(), E->h_nodel_loc.size() * sizeof(int));
   if (nm == "m_nodel_offset") return hosti(E->h_offset.data(), E->h_offset.size() * sizeof(int));
@@ -1288,7 +1352,7 @@ extern "C" int wf_get_array(wf_engine *E, const char *name, void *dst, size_t by
     const size_t c6 = (size_t)6 * d.ep;
     if (need_scratch(E, 2 * c6)) return 1;
     E->L->rebuild_sigma(d, E->scratch, E->stream);
-    E->L->soa_to_aos(E->scratch, d.ep, 6, ne, 1.0, E->scratch + c6, E->stream);
+    E->L->soa_to_aos(E->scratch, d.ep, 6, ne, 1.0, E->scratch + c6, E->iperm_d, E->stream);
     CK(cudaMemcpyAsync(dst, E->scratch + c6, bytes, cudaMemcpyDeviceToHost, E->stream));
     CK(cudaStreamSynchronize(E->stream));
     return check_launch(E, "m_sigma");
@@ -1322,7 +1386,7 @@ extern "C" int wf_get_array(wf_engine *E, const char *name, void *dst, size_t by
     d.fi = E->scratch;
     E->L->node_update(d, E->P, E->strict ? 1 : 0, 0, 1, E->stream); // sums only, exactly as the step forms them
     d.fi = save_fi;
-    E->L->soa_to_aos(E->scratch, d.np, dim, nn, 1.0, E->scratch + cv, E->stream);
+    E->L->soa_to_aos(E->scratch, d.np, dim, nn, 1.0, E->scratch + cv, nullptr, E->stream);
     CK(cudaMemcpyAsync(dst, E->scratch + cv, bytes, cudaMemcpyDeviceToHost, E->stream));
     CK(cudaStreamSynchronize(E->stream));
     return check_launch(E, "m_fi");
@@ -1331,21 +1395,22 @@ extern "C" int wf_get_array(wf_engine *E, const char *name, void *dst, size_t by
     if (r.kind != K_HGQ) {
       // convert to the reference layout on the device, then ONE device->host copy straight into the caller's buffer
       long long cnt = 0, pitch = 0; int nc = 1; const double *src = r.dev; double scale = 1.0;
+      const int *map = nullptr; // element arrays live in the internal element order
       switch (r.kind) {
         case K_NODEVEC: cnt = nn; pitch = d.np; nc = dim; break;
         case K_NODESCAL: cnt = nn; pitch = d.np; nc = 1; if (r.lazy_voln) scale = 1.0 / (double)k; break;
-        case K_ELEMSCAL: cnt = ne; pitch = d.ep; nc = 1; break;
-        case K_ELEM6: cnt = ne; pitch = d.ep; nc = 6; break;
-        case K_ELEMNODE: cnt = ne; pitch = d.ep; nc = k; src = r.dev + (size_t)r.comp * k * d.ep; break;
-        case K_ELEMNODEVEC: cnt = ne; pitch = d.ep; nc = k * dim; break;
+        case K_ELEMSCAL: cnt = ne; pitch = d.ep; nc = 1; map = E->iperm_d; break;
+        case K_ELEM6: cnt = ne; pitch = d.ep; nc = 6; map = E->iperm_d; break;
+        case K_ELEMNODE: cnt = ne; pitch = d.ep; nc = k; src = r.dev + (size_t)r.comp * k * d.ep; map = E->iperm_d; break;
+        case K_ELEMNODEVEC: cnt = ne; pitch = d.ep; nc = k * dim; map = E->iperm_d; break;
         default: break;
       }
-      if (nc == 1 && scale == 1.0) {
+      if (nc == 1 && scale == 1.0 && !map) {
         CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, E->stream));
       } else {
         if (need_scratch(E, (size_t)cnt * nc)) return 1;
-        if (r.lazy_voln) E->L->soa_to_aos(src, pitch, nc, cnt, 1.0, E->scratch, E->stream); // then divide exactly like the host did
-        else E->L->soa_to_aos(src, pitch, nc, cnt, scale, E->scratch, E->stream);
+        if (r.lazy_voln) E->L->soa_to_aos(src, pitch, nc, cnt, 1.0, E->scratch, map, E->stream); // then divide exactly like the host did
+        else E->L->soa_to_aos(src, pitch, nc, cnt, scale, E->scratch, map, E->stream);
         CK(cudaMemcpyAsync(dst, E->scratch, bytes, cudaMemcpyDeviceToHost, E->stream));
       }
       CK(cudaStreamSynchronize(E->stream));
@@ -1367,7 +1432,7 @@ extern "C" int wf_get_array(wf_engine *E, const char *name, void *dst, size_t by
     case K_HGQ:
       memset(out, 0, bytes);
       for (int e = 0; e < ne; e++)
-        for (int c = 0; c < 2; c++) out[(size_t)e * 2 + c] = h[(size_t)c * d.ep + e];
+        for (int c = 0; c < 2; c++) out[(size_t)e * 2 + c] = h[(size_t)c * d.ep + (E->iperm.empty() ? e : E->iperm[e])];
       break;
     default: break;
   }
@@ -1394,25 +1459,26 @@ extern "C" int wf_set_array(wf_engine *E, const char *name, const void *src, siz
   if (r.kind == K_HGQ) {
     std::vector<double> h((size_t)2 * d.ep, 0.0);
     for (int e = 0; e < ne; e++)
-      for (int c = 0; c < 2; c++) h[(size_t)c * d.ep + e] = in[(size_t)e * 2 + c];
+      for (int c = 0; c < 2; c++) h[(size_t)c * d.ep + (E->iperm.empty() ? e : E->iperm[e])] = in[(size_t)e * 2 + c];
     CK(cudaMemcpyAsync(r.dev, h.data(), h.size() * sizeof(double), cudaMemcpyHostToDevice, E->stream));
     CK(cudaStreamSynchronize(E->stream));
   } else {
     long long cnt = 0, pitch = 0; int nc = 1;
+    const int *map = nullptr;
     switch (r.kind) {
       case K_NODEVEC: cnt = nn; pitch = d.np; nc = dim; break;
       case K_NODESCAL: cnt = nn; pitch = d.np; nc = 1; break;
-      case K_ELEMSCAL: cnt = ne; pitch = d.ep; nc = 1; break;
-      case K_ELEM6: cnt = ne; pitch = d.ep; nc = 6; break;
-      case K_ELEMNODEVEC: cnt = ne; pitch = d.ep; nc = k * dim; break;
+      case K_ELEMSCAL: cnt = ne; pitch = d.ep; nc = 1; map = E->iperm_d; break;
+      case K_ELEM6: cnt = ne; pitch = d.ep; nc = 6; map = E->iperm_d; break;
+      case K_ELEMNODEVEC: cnt = ne; pitch = d.ep; nc = k * dim; map = E->iperm_d; break;
       default: FAIL(std::string("array '") + name + "' cannot be set");
     }
-    if (nc == 1) {
+    if (nc == 1 && !map) {
       CK(cudaMemcpyAsync(r.dev, in, bytes, cudaMemcpyHostToDevice, E->stream));
     } else { // one host->device copy of the caller's buffer, layout conversion on the device
       if (need_scratch(E, (size_t)cnt * nc)) return 1;
       CK(cudaMemcpyAsync(E->scratch, in, bytes, cudaMemcpyHostToDevice, E->stream));
-      E->L->aos_to_soa(E->scratch, pitch, nc, cnt, r.dev, E->stream);
+      E->L->aos_to_soa(E->scratch, pitch, nc, cnt, r.dev, map, E->stream);
     }
     CK(cudaStreamSynchronize(E->stream));
     if (check_launch(E, "wf_set_array")) return 1;
@@ -1501,7 +1567,7 @@ extern "C" int wf_cfl_dt(wf_engine *E, double cfl_factor, double *dt) {
   double o[3], rho0 = E->mat.rho0;
   if (diag_reduce(E, true, true, o)) return 1;
   if (E->inited) {
-    CK(cudaMemcpyAsync(&rho0, E->d.rho, sizeof(double), cudaMemcpyDeviceToHost, E->stream));
+    CK(cudaMemcpyAsync(&rho0, E->d.rho + (E->iperm.empty() ? 0 : E->iperm[0]), sizeof(double), cudaMemcpyDeviceToHost, E->stream)); // rho[0] of the caller's numbering
     CK(cudaStreamSynchronize(E->stream));
   }
   const double cs = sqrt(E->P.Kbulk / rho0);

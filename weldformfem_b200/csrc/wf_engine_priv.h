@@ -37,7 +37,11 @@ struct wf_engine {
   // host copies of integer artefacts (reference layouts)
   std::vector<unsigned> h_elnod;
   std::vector<int> h_nodel, h_nodel_loc, h_offset, h_count;
-  std::vector<unsigned> h_pos; // [k][ep], see WfDev::pos
+  std::vector<unsigned> h_pos; // [k][ep], see WfDev::pos; indexed by USER element id
+  // internal element order (wf_host_elem_order): perm[internal] = user, iperm[user] = internal; empty = identity
+  int order_mode = 1;
+  std::vector<int> perm, iperm, perm_out;
+  int *iperm_d = nullptr;
   long long sell_total = 0;
   std::vector<int> bc_nod[3];
   std::vector<double> bc_val[3];

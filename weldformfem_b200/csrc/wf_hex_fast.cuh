@@ -12,14 +12,18 @@
 //       f_hg(n,i) = -c_h sum_j h_j(v_i) Sig_j(n)
 //     and the 24 nodal force components come out of one inverse butterfly per component.
 // Kernels in this file, all one element per thread, 128 threads per CTA:
-//   k_elem_main_hex_tile   DEFAULT.  The CTA stages x, v and the nodal ratio of its UNIQUE nodes once (cp.async through
-//                          the fixed-pitch node list WfDev::blk_pad); nodal forces are summed per warp tile in shared
-//                          memory and one partial per (tile, unique node) goes to HBM (WfDev::ftile).
+//   k_elem_main_hex_brick  DEFAULT on meshes whose CTA / tile node lists fit its compile-time pitches (every structured
+//                          mesh in the engine's Morton element order: 128 elements = 8x4x4 brick, <= 288 unique nodes;
+//                          32 elements = 4x4x2 brick, <= 104).  Same data flow as k_elem_main_hex_tile with
+//                          shared-memory strides known at compile time (no address arithmetic per access), the 16-bit
+//                          / 8-bit local indices of an element fetched with one 16 B and one 8 B load, and only the
+//                          tile's actual number of partial sums written.
+//   k_elem_main_hex_tile   same with run-time pitches (any mesh whose force tiles are conflict-free).  The CTA stages x,
+//                          v and the nodal ratio of its UNIQUE nodes once (cp.async through the fixed-pitch node list
+//                          WfDev::blk_pad); nodal forces are summed per warp tile in shared memory and one partial per
+//                          (tile, unique node) goes to HBM (WfDev::ftile).
 //   k_elem_main_hex_staged same staging, one force record per element node into the node-ordered buffer (variant 9;
 //                          also the fallback when the tile tables are unusable).
-//   k_elem_main_hex_fast   per-thread cp.async columns ([item][thread], conflict-free, no block barrier): the first
-//                          working form, kept as a tuning aid together with the persistent pipelined variant and the
-//                          memory skeletons (wf_set_variant(2, ...); tools/kbench.py).
 // (included inside the flavour namespace of wf_kernels.cu, after wf_math.cuh)
 
 namespace hexfast {
@@ -55,11 +59,6 @@ WF_DI void wht_fwd8(double q0, double q1, double q2, double q3, double q4, doubl
     h[3] = dd2 - dd1;
   }
 }
-// node data staged as one private column per thread: value n of a component at col[n * TPB]
-struct ColSrc {
-  const double *col;
-  WF_DI double operator()(int comp, int n) const { return col[(comp * 8 + n) * TPB]; }
-};
 // node data staged once per CTA: value of node n of this element at s[comp * stride + li[n]]
 struct StagedSrc {
   const double *s;
@@ -266,127 +265,6 @@ WF_DI void hex_back(const WfDev &d, const WfPar &P, int e, bool active, const He
   }
 }
 
-// one element per thread, one tile per CTA
-__global__ void __launch_bounds__(TPB, 4) k_elem_main_hex_fast(WfDev d, WfPar P) {
-  extern __shared__ double sm[];
-  const int t = threadIdx.x;
-  const int e0 = blockIdx.x * TPB + t;
-  const bool active = e0 < d.ne;
-  const int e = active ? e0 : d.ne - 1; // tail threads shadow the last element and do not store
-  double *col = sm + t;
-
-  int nid[8];
-#pragma unroll
-  for (int n = 0; n < 8; n++) nid[n] = __ldg(d.elnod + (long long)n * d.ep + e);
-#pragma unroll
-  for (int c = 0; c < 3; c++)
-#pragma unroll
-    for (int n = 0; n < 8; n++) cp_async8(col + (c * 8 + n) * TPB, d.x + (long long)c * d.np + nid[n]);
-#pragma unroll
-  for (int c = 0; c < 3; c++)
-#pragma unroll
-    for (int n = 0; n < 8; n++) cp_async8(col + (24 + c * 8 + n) * TPB, d.v + (long long)c * d.np + nid[n]);
-  cp_async_commit();
-
-  // independent streaming loads
-  double tau[6];
-#pragma unroll
-  for (int i = 0; i < 6; i++) tau[i] = d.tau[(long long)i * d.ep + e];
-  const double pl = d.pl_strain[e];
-  const double rho_e = d.rho[e];
-  const double sy = d.sigma_y[e];
-  double J_sum = 0.0, p_prev = 0.0;
-  if (P.press == 1) p_prev = d.p[e];
-#pragma unroll
-  for (int a = 0; a < 8; a++) J_sum += d.nodal_p[nid[a]];
-
-  cp_async_wait_all();
-  HexFront g;
-  hex_front(ColSrc{col}, g);
-  auto off = [&](int n) { return (unsigned)__ldg(d.pos + (long long)n * d.ep + e); };
-  hex_back(d, P, e, active, g, tau, pl, rho_e, sy, J_sum, p_prev, EmitScatter<decltype(off)>{d.fsell, off});
-}
-
-// Persistent, software-pipelined variant: every CTA walks tiles blockIdx.x, += gridDim.x.  While a tile's
-// stress update / force stores run, the node data (x, v), the force-buffer offsets of the NEXT tile are already
-// in flight (cp.async into the staging columns the front half has just drained), and the connectivity of the
-// tile after that is being loaded — the three dependent memory round trips of the one-shot kernel
-// (connectivity -> gathers -> offsets) overlap with arithmetic instead of adding up.
-constexpr int PIPE_SMEM_BYTES = SMEM_BYTES + 2 * 8 * TPB * 4;
-
-WF_DI void cp_async4(unsigned *smem_dst, const int *gsrc) {
-  unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(s), "l"(gsrc));
-}
-
-__global__ void __launch_bounds__(TPB, 4) k_elem_main_hex_pipe(WfDev d, WfPar P) {
-  extern __shared__ double sm[];
-  const int t = threadIdx.x;
-  double *col = sm + t;
-  unsigned *posbuf = reinterpret_cast<unsigned *>(sm + ITEMS * TPB) + t; // [2][8][TPB]
-  const int ntiles = (d.ne + TPB - 1) / TPB;
-  int tile = blockIdx.x;
-  if (tile >= ntiles) return;
-  const int last = d.ne - 1;
-
-  auto issue = [&](const int (&nid)[8], int e, int buf) {
-#pragma unroll
-    for (int c = 0; c < 3; c++)
-#pragma unroll
-      for (int n = 0; n < 8; n++) cp_async8(col + (c * 8 + n) * TPB, d.x + (long long)c * d.np + nid[n]);
-#pragma unroll
-    for (int c = 0; c < 3; c++)
-#pragma unroll
-      for (int n = 0; n < 8; n++) cp_async8(col + (24 + c * 8 + n) * TPB, d.v + (long long)c * d.np + nid[n]);
-#pragma unroll
-    for (int n = 0; n < 8; n++) cp_async4(posbuf + (buf * 8 + n) * TPB, d.pos + (long long)n * d.ep + e);
-    cp_async_commit();
-  };
-
-  int nid[8];
-  int e = min(tile * TPB + t, last);
-#pragma unroll
-  for (int n = 0; n < 8; n++) nid[n] = __ldg(d.elnod + (long long)n * d.ep + e);
-  issue(nid, e, 0);
-  int buf = 0;
-  for (; tile < ntiles; tile += gridDim.x, buf ^= 1) {
-    const int e0 = tile * TPB + t;
-    const bool active = e0 < d.ne;
-    e = active ? e0 : last;
-    // streaming state of this tile (consumed by the back half) and the nodal ratios of its nodes
-    double tau[6];
-#pragma unroll
-    for (int i = 0; i < 6; i++) tau[i] = d.tau[(long long)i * d.ep + e];
-    const double pl = d.pl_strain[e];
-    const double rho_e = d.rho[e];
-    const double sy = d.sigma_y[e];
-    double p_prev = 0.0;
-    if (P.press == 1) p_prev = d.p[e];
-    double jn[8];
-#pragma unroll
-    for (int a = 0; a < 8; a++) jn[a] = d.nodal_p[nid[a]];
-    // connectivity of the next tile of this CTA
-    const int tnext = tile + gridDim.x;
-    const bool more = tnext < ntiles;
-    const int en = min((more ? tnext : tile) * TPB + t, last);
-#pragma unroll
-    for (int n = 0; n < 8; n++) nid[n] = __ldg(d.elnod + (long long)n * d.ep + en);
-
-    cp_async_wait_all();
-    HexFront g;
-    hex_front(ColSrc{col}, g);
-    if (more) issue(nid, en, buf ^ 1); // staging columns are drained: refill them for the next tile
-    double J_sum = 0.0;
-#pragma unroll
-    for (int a = 0; a < 8; a++) J_sum += jn[a];
-    const unsigned *pb = posbuf + buf * 8 * TPB;
-    auto off = [&](int n) { return pb[n * TPB]; };
-    hex_back(d, P, e, active, g, tau, pl, rho_e, sy, J_sum, p_prev, EmitScatter<decltype(off)>{d.fsell, off});
-  }
-}
-
-
-
 // Block-staged variant: the CTA loads the data of its UNIQUE nodes (x, v, nodal ratio: 7 doubles per node) into
 // shared memory once, coalesced along the ascending node list, instead of every element gathering its eight
 // nodes separately (a structured 128-element tile has ~520 unique nodes for 1024 element-nodes).  Element-nodes
@@ -522,74 +400,114 @@ __global__ void __launch_bounds__(TPB, 4) k_elem_main_hex_tile(WfDev d, WfPar P,
   hex_back(d, P, e, active, g, tau, pl, rho_e, sy, J_sum, p_prev, EmitTile{acc, ws, ri, amask});
   __syncwarp();
   const long long tile = (long long)b * (TPB / 32) + warp;
+  // number of unique nodes of this tile = largest tile-local index + 1: only that many partials are written
+  unsigned m = max(max(ri[0], ri[1]), max(ri[2], ri[3]));
+  m = max(m, max(max(ri[4], ri[5]), max(ri[6], ri[7])));
+  const int cnt = (int)__reduce_max_sync(0xffffffffu, m) + 1;
   if (tile * 32 < d.ne) {
     double *__restrict__ out = d.ftile + tile * 3 * ws;
-    for (int i = lane; i < 3 * ws; i += 32) out[i] = acc[i];
+#pragma unroll
+    for (int c = 0; c < 3; c++)
+      for (int i = lane; i < cnt; i += 32) out[c * ws + i] = acc[c * ws + i];
   }
 }
 
-// ---- memory skeleton of the hexa main pass (tuning aid only: same loads / stores, trivial arithmetic, results are
-// garbage).  MODE bit0: force records scattered through pos (1) or stored element-ordered (0); bit1: node data
-// staged with cp.async (1) or loaded straight to registers (0); bit2: skip the x/v gathers; bit3: skip force stores.
-template <int MODE>
-__global__ void __launch_bounds__(TPB, 4) k_elem_main_hex_skel(WfDev d, WfPar P) {
-  extern __shared__ double sm[];
-  const int t = threadIdx.x;
-  const int e0 = blockIdx.x * TPB + t;
-  if (e0 >= d.ne) return;
-  const int e = e0;
-  double *col = sm + t;
-  int nid[8];
+// ---- brick form: compile-time pitches, packed local indices ------------------------------------------------------
+// WfDev::lidx_pk[e] = the eight 16-bit CTA-local node indices of element e (one uint4), WfDev::tf_idx_pk[e] = its eight
+// 8-bit tile-local indices (one uint2); both are plain repackings of lidx / tf_idx made at mesh upload.
+template <int STRIDE>
+struct StagedSrcC {
+  const double *s;
+  unsigned li[8];
+  WF_DI double operator()(int comp, int n) const { return s[comp * STRIDE + li[n]]; }
+};
+template <int WS>
+struct EmitTileC {
+  double *acc;       // [3][WS] accumulators of this warp
+  uint2 pk;          // eight 8-bit tile-local indices
+  unsigned amask;
+  WF_DI unsigned idx(int n) const { return ((n < 4 ? pk.x : pk.y) >> (8 * (n & 3))) & 0xffu; }
+  WF_DI void operator()(int i, const double (&B)[3], const double (&c)[4]) {
+    double q[8];
+    wht_inv8(B, c, q);
+    double *a = acc + i * WS;
 #pragma unroll
-  for (int n = 0; n < 8; n++) nid[n] = __ldg(d.elnod + (long long)n * d.ep + e);
-  double acc = 0.0;
-  if (!(MODE & 4)) {
-    if (MODE & 2) {
-#pragma unroll
-      for (int c = 0; c < 3; c++)
-#pragma unroll
-        for (int n = 0; n < 8; n++) cp_async8(col + (c * 8 + n) * TPB, d.x + (long long)c * d.np + nid[n]);
-#pragma unroll
-      for (int c = 0; c < 3; c++)
-#pragma unroll
-        for (int n = 0; n < 8; n++) cp_async8(col + (24 + c * 8 + n) * TPB, d.v + (long long)c * d.np + nid[n]);
-      cp_async_commit();
-    } else {
-#pragma unroll
-      for (int c = 0; c < 3; c++)
-#pragma unroll
-        for (int n = 0; n < 8; n++) acc += d.x[(long long)c * d.np + nid[n]] + d.v[(long long)c * d.np + nid[n]];
+    for (int n = 0; n < 8; n++) {
+      a[idx(n)] += q[n];
+      __syncwarp(amask);
     }
   }
+};
+
+template <int STRIDE, int WS, int MINB>
+__global__ void __launch_bounds__(TPB, MINB) k_elem_main_hex_brick(WfDev d, WfPar P) {
+  extern __shared__ double sm[];
+  pdl_trigger();
+  const int t = threadIdx.x;
+  const int b = blockIdx.x;
+  const int e0 = b * TPB + t;
+  const bool active = e0 < d.ne;
+  const int e = active ? e0 : d.ne - 1;
+  const unsigned amask = __ballot_sync(0xffffffffu, active);
+  constexpr int NQ = (STRIDE + TPB - 1) / TPB;
+  const int *__restrict__ ids = d.blk_pad + (long long)b * STRIDE;
+  int gid[NQ];
+#pragma unroll
+  for (int q = 0; q < NQ; q++) {
+    const int i = q * TPB + t;
+    gid[q] = (i < STRIDE) ? __ldg(ids + i) : -1;
+  }
+  const uint4 lpk = __ldg(d.lidx_pk + e);
+  const uint2 rpk = __ldg(d.tf_idx_pk + e);
+  pdl_wait(); // everything above reads constant mesh tables only
   double tau[6];
 #pragma unroll
   for (int i = 0; i < 6; i++) tau[i] = d.tau[(long long)i * d.ep + e];
-  acc += d.pl_strain[e] + d.rho[e] + d.sigma_y[e];
+  const double pl = d.pl_strain[e];
+  const double rho_e = d.rho[e];
+  const double sy = d.sigma_y[e];
+  double p_prev = 0.0;
+  if (P.press == 1) p_prev = d.p[e];
 #pragma unroll
-  for (int a = 0; a < 8; a++) acc += d.nodal_p[nid[a]];
-  if ((MODE & 2) && !(MODE & 4)) {
-    cp_async_wait_all();
+  for (int q = 0; q < NQ; q++) {
+    const int i = q * TPB + t, gq = gid[q];
+    if (gq >= 0) {
 #pragma unroll
-    for (int i = 0; i < ITEMS; i++) acc += col[i * TPB];
-  }
+      for (int c = 0; c < 3; c++) cp_async8(sm + c * STRIDE + i, d.x + (long long)c * d.np + gq);
 #pragma unroll
-  for (int i = 0; i < 6; i++) d.tau[(long long)i * d.ep + e] = tau[i] + acc;
-  d.pl_strain[e] = acc;
-  d.sigma_y[e] = acc + 1.0;
-  d.p[e] = acc + 2.0;
-  if (MODE & 8) return;
-  if (MODE & 1) {
-#pragma unroll
-    for (int n = 0; n < 8; n++) {
-      const long long o = (long long)(unsigned)__ldg(d.pos + (long long)n * d.ep + e);
-#pragma unroll
-      for (int c = 0; c < 3; c++) d.fsell[o + 32 * c] = acc + n + c;
+      for (int c = 0; c < 3; c++) cp_async8(sm + (3 + c) * STRIDE + i, d.v + (long long)c * d.np + gq);
+      cp_async8(sm + 6 * STRIDE + i, d.nodal_p + gq);
     }
-  } else {
+  }
+  cp_async_commit();
+  const int lane = t & 31, warp = t >> 5;
+  double *acc = sm + 7 * STRIDE + warp * 3 * WS;
 #pragma unroll
-    for (int n = 0; n < 8; n++)
+  for (int i = lane; i < 3 * WS; i += 32) acc[i] = 0.0;
+  StagedSrcC<STRIDE> src;
+  src.s = sm;
+  src.li[0] = lpk.x & 0xffffu; src.li[1] = lpk.x >> 16; src.li[2] = lpk.y & 0xffffu; src.li[3] = lpk.y >> 16;
+  src.li[4] = lpk.z & 0xffffu; src.li[5] = lpk.z >> 16; src.li[6] = lpk.w & 0xffffu; src.li[7] = lpk.w >> 16;
+  cp_async_wait_all();
+  __syncthreads();
+  HexFront g;
+  hex_front(src, g);
+  double J_sum = 0.0;
 #pragma unroll
-      for (int c = 0; c < 3; c++) d.fsell[(long long)(n * 3 + c) * d.ep + e] = acc + n + c;
+  for (int a = 0; a < 8; a++) J_sum += sm[6 * STRIDE + src.li[a]];
+  EmitTileC<WS> emit{acc, rpk, amask};
+  hex_back(d, P, e, active, g, tau, pl, rho_e, sy, J_sum, p_prev, emit);
+  __syncwarp();
+  // number of unique nodes of this tile = largest tile-local index + 1 (inactive lanes shadow the last element)
+  unsigned m = max(max(emit.idx(0), emit.idx(1)), max(emit.idx(2), emit.idx(3)));
+  m = max(m, max(max(emit.idx(4), emit.idx(5)), max(emit.idx(6), emit.idx(7))));
+  const int cnt = (int)__reduce_max_sync(0xffffffffu, m) + 1;
+  const long long tile = (long long)b * (TPB / 32) + warp;
+  if (tile * 32 < d.ne) {
+    double *__restrict__ out = d.ftile + tile * 3 * d.tf_stride;
+#pragma unroll
+    for (int c = 0; c < 3; c++)
+      for (int i = lane; i < cnt; i += 32) out[c * d.tf_stride + i] = acc[c * WS + i];
   }
 }
 

@@ -413,7 +413,8 @@ __global__ void __launch_bounds__(TPB_E, MINB) k_elem_main(WfDev d, WfPar P, int
     const double f = P.exp_T * dTdt_gp;
     Dr[0] = Dr[0] - f * 1.; Dr[1] = Dr[1] - f * 1.; Dr[2] = Dr[2] - f * 1.;
     Dr[3] = Dr[3] - f * 0.; Dr[4] = Dr[4] - f * 0.; Dr[5] = Dr[5] - f * 0.;
-    if (e < d.nn) temp_e = d.T[e]; // T[e]: nodal array read with the element id (Mechanical.C:1731)
+    const int eu = d.e_user ? d.e_user[e] : e; // the reference's element id
+    if (eu < d.nn) temp_e = d.T[eu]; // T[e]: nodal array read with the element id (Mechanical.C:1731)
   }
   const double p = elem_pressure<ET>(d, P, e, npn, vol, vol0, rho_e, dH, vl, elem_in_contact<ET>(d, e));
   StressOut so;
@@ -447,7 +448,7 @@ __global__ void __launch_bounds__(TPB_E, MINB) k_elem_main(WfDev d, WfPar P, int
       const long long o = (long long)__ldg(d.pos + (long long)i * d.ep + e);
       const long long lane = o & 31;
       d.tsell[(o + (D - 1) * lane) / D] = val; // fsell offset D*q - (D-1)*lane  ->  q
-      const long long flat = (long long)e * K + i;
+      const long long flat = (long long)(d.e_user ? d.e_user[e] : e) * K + i; // index in the reference's flat m_dTedt
       if (flat < d.nn) cur[flat] = val;
     }
   }
@@ -1022,20 +1023,25 @@ __global__ void __launch_bounds__(256) k_max_vel(WfDev d, unsigned long long *ke
 }
 
 // layout conversion between the private component-major arrays and the reference's interleaved records:
-//   aos[i * nc + c] <-> soa[c * pitch + i]   (scale: m_voln = sum / k)
-__global__ void k_soa_to_aos(const double *__restrict__ soa, long long pitch, int nc, long long n, double scale, double *__restrict__ aos) {
+//   aos[i * nc + c] <-> soa[c * pitch + map(i)]   (scale: m_voln = sum / k)
+// map = NULL for nodal arrays; for element arrays map[user element] = internal element (wf_host_elem_order)
+__global__ void k_soa_to_aos(const double *__restrict__ soa, long long pitch, int nc, long long n, double scale, double *__restrict__ aos,
+                             const int *__restrict__ map) {
   const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= n * nc) return;
   const long long i = j / nc;
   const int c = (int)(j - i * nc);
-  aos[j] = soa[(long long)c * pitch + i] * scale;
+  const long long is = map ? (long long)map[i] : i;
+  aos[j] = soa[(long long)c * pitch + is] * scale;
 }
-__global__ void k_aos_to_soa(const double *__restrict__ aos, long long pitch, int nc, long long n, double *__restrict__ soa) {
+__global__ void k_aos_to_soa(const double *__restrict__ aos, long long pitch, int nc, long long n, double *__restrict__ soa,
+                             const int *__restrict__ map) {
   const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= n * nc) return;
   const long long i = j / nc;
   const int c = (int)(j - i * nc);
-  soa[(long long)c * pitch + i] = aos[j];
+  const long long is = map ? (long long)map[i] : i;
+  soa[(long long)c * pitch + is] = aos[j];
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1397,7 +1403,7 @@ static void l_impose_bc(const WfDev &d, int dim, int is_acc, double *arr, cudaSt
 }
 static void l_elem_vol(const WfDev &d, const WfPar &P, int et, int store_jac, cudaStream_t s) {
   if (!store_jac && P.variant[0] == 1) {
-    const int stride = (d.blk_umax + 31) / 32 * 32;
+    const int stride = d.blk_pitch;
     ELEM_DISPATCH(et, k_elem_vol_staged<ET><<<cdiv(d.ne, WF_EBLK), WF_EBLK, Elem<ET>::D * stride * 8, s>>>(d, P, stride));
     return;
   }
@@ -1424,41 +1430,28 @@ static int l_tile_forces(const WfDev &d, const WfPar &P, int separate_hg) {
   return d.ftile && !separate_hg && d.dim == 3 && !P.strict && !P.thermal && (P.variant[2] == 0 || P.variant[2] == 6 || P.variant[2] == 7) &&
          ((d.k == 8 && P.model < 2) || (d.k == 4 && d.tf_tab));
 }
+// compile-time pitches of k_elem_main_hex_brick: unique nodes of a 128-element CTA / of a 32-element tile (Morton order
+// of a structured mesh: <= 277 / <= 97 at 215^3)
+constexpr int BRICK_STRIDE = 288, BRICK_WS = 104;
 static void l_elem_main(const WfDev &d, const WfPar &P, int et, int separate_hg, cudaStream_t s) {
   if (et == ET_HEX8 && l_tile_forces(d, P, separate_hg)) {
-    const int stride = (d.blk_umax + 31) / 32 * 32, g = cdiv(d.ne, hexfast::TPB);
+    const int stride = d.blk_pitch, g = cdiv(d.ne, hexfast::TPB);
+    if (d.lidx_pk && stride == BRICK_STRIDE && d.tf_stride <= BRICK_WS && P.variant[2] != 7) {
+      constexpr size_t smem = ((size_t)7 * BRICK_STRIDE + (size_t)(hexfast::TPB / 32) * 3 * BRICK_WS) * 8;
+      if (P.variant[2] == 6) launch_pdl(hexfast::k_elem_main_hex_brick<BRICK_STRIDE, BRICK_WS, 4>, g, hexfast::TPB, smem, s, d, P);
+      else launch_pdl(hexfast::k_elem_main_hex_brick<BRICK_STRIDE, BRICK_WS, 5>, g, hexfast::TPB, smem, s, d, P);
+      return;
+    }
     const size_t smem = ((size_t)7 * stride + (size_t)(hexfast::TPB / 32) * 3 * d.tf_stride) * 8;
     launch_pdl(hexfast::k_elem_main_hex_tile, g, hexfast::TPB, smem, s, d, P, stride);
     return;
   }
   // the regrouped hexa kernel inlines Bilinear / Hollomon; the rate-dependent laws (Johnson-Cook, GMT) take the generic kernel
   if (!separate_hg && et == ET_HEX8 && !P.strict && P.variant[2] != 1 && P.model < 2 && !P.thermal) {
-    if (P.variant[2] >= 100) { // memory skeletons (tuning aid, garbage results)
-      const int g = cdiv(d.ne, hexfast::TPB);
-      switch (P.variant[2] - 100) {
-#define WF_SKEL(M) case M: cudaFuncSetAttribute(hexfast::k_elem_main_hex_skel<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, hexfast::SMEM_BYTES); \
-                   hexfast::k_elem_main_hex_skel<M><<<g, hexfast::TPB, (M & 2) ? hexfast::SMEM_BYTES : 0, s>>>(d, P); break;
-        WF_SKEL(0) WF_SKEL(1) WF_SKEL(2) WF_SKEL(3) WF_SKEL(4) WF_SKEL(5) WF_SKEL(8) WF_SKEL(10) WF_SKEL(12)
-#undef WF_SKEL
-        default: break;
-      }
-      return;
-    }
-    if (P.variant[2] == 0 || P.variant[2] == 9) { // unique nodes of the CTA staged once in shared memory (9: without the tile reduction)
-      const int stride = (d.blk_umax + 31) / 32 * 32;
-      hexfast::k_elem_main_hex_staged<<<cdiv(d.ne, hexfast::TPB), hexfast::TPB, 7 * stride * 8, s>>>(d, P, stride);
-      return;
-    }
-    if (P.variant[2] >= 2 && P.variant[2] <= 4) { // persistent pipelined variant; variant = CTAs per SM
-      static int sms = 0;
-      if (!sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); }
-      const int per_sm = P.variant[2];
-      const int g = min(cdiv(d.ne, hexfast::TPB), sms * per_sm);
-      hexfast::k_elem_main_hex_pipe<<<g, hexfast::TPB, hexfast::PIPE_SMEM_BYTES, s>>>(d, P);
-      return;
-    }
-    // variant 1 is the strict-order generic kernel (below); anything else: per-thread cp.async columns
-    hexfast::k_elem_main_hex_fast<<<cdiv(d.ne, hexfast::TPB), hexfast::TPB, hexfast::SMEM_BYTES, s>>>(d, P);
+    // unique nodes of the CTA staged once in shared memory, one force record per element node (variant 9, and the
+    // fallback when the force tiles of the mesh are not conflict-free)
+    const int stride = d.blk_pitch;
+    hexfast::k_elem_main_hex_staged<<<cdiv(d.ne, hexfast::TPB), hexfast::TPB, 7 * stride * 8, s>>>(d, P, stride);
     return;
   }
   if (et == ET_TET4 && l_tile_forces(d, P, separate_hg)) {
@@ -1468,7 +1461,7 @@ static void l_elem_main(const WfDev &d, const WfPar &P, int et, int separate_hg,
     else launch_pdl(k_elem_main<ET_TET4, false, false, false, true, 5>, cdiv(d.ne, TPB_E), TPB_E, smem, s, d, P, 0);
     return;
   }
-  const int stride = (d.blk_umax + 31) / 32 * 32;
+  const int stride = d.blk_pitch;
   // measured (tools/kbench.py): per-element gathers beat block staging for tets, quads and the strict hexa kernel
   // (0.71 vs 0.78 ms at 10M tets); the staged form is kept as variant 8
   const bool staged = P.variant[2] == 8 && !P.thermal;
@@ -1601,11 +1594,11 @@ static void l_max_vel(const WfDev &d, unsigned long long *keys, cudaStream_t s) 
   if (d.dim == 3) k_max_vel<3><<<cdiv(d.nn, 256), 256, 0, s>>>(d, keys);
   else k_max_vel<2><<<cdiv(d.nn, 256), 256, 0, s>>>(d, keys);
 }
-static void l_soa_to_aos(const double *soa, long long pitch, int nc, long long n, double scale, double *aos, cudaStream_t s) {
-  if (n > 0) k_soa_to_aos<<<(unsigned)((n * nc + 255) / 256), 256, 0, s>>>(soa, pitch, nc, n, scale, aos);
+static void l_soa_to_aos(const double *soa, long long pitch, int nc, long long n, double scale, double *aos, const int *map, cudaStream_t s) {
+  if (n > 0) k_soa_to_aos<<<(unsigned)((n * nc + 255) / 256), 256, 0, s>>>(soa, pitch, nc, n, scale, aos, map);
 }
-static void l_aos_to_soa(const double *aos, long long pitch, int nc, long long n, double *soa, cudaStream_t s) {
-  if (n > 0) k_aos_to_soa<<<(unsigned)((n * nc + 255) / 256), 256, 0, s>>>(aos, pitch, nc, n, soa);
+static void l_aos_to_soa(const double *aos, long long pitch, int nc, long long n, double *soa, const int *map, cudaStream_t s) {
+  if (n > 0) k_aos_to_soa<<<(unsigned)((n * nc + 255) / 256), 256, 0, s>>>(aos, pitch, nc, n, soa, map);
 }
 
 // Force-load every kernel of the step (CUDA loads kernels lazily, and loading one synchronises the context:
@@ -1630,13 +1623,7 @@ static void l_preload(int et, int dim, int k) {
                 cudaFuncSetAttribute(k_elem_main<ET, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 7 * 1024 * 8);
                 touch(k_elem_main<ET, true, true>); touch(k_elem_main<ET, false, true>));
   touch(k_node_vol<8>); touch(k_node_vol<8, 5>); touch(k_node_vol<4, 5>); touch(k_node_vol<3, 5>);
-  // per device: the regrouped hexa kernel stages 48 KB of node data per CTA
-  cudaFuncSetAttribute(hexfast::k_elem_main_hex_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, hexfast::SMEM_BYTES);
-  cudaFuncSetAttribute(hexfast::k_elem_main_hex_fast, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
-  touch(hexfast::k_elem_main_hex_fast);
-  cudaFuncSetAttribute(hexfast::k_elem_main_hex_pipe, cudaFuncAttributeMaxDynamicSharedMemorySize, hexfast::PIPE_SMEM_BYTES);
-  cudaFuncSetAttribute(hexfast::k_elem_main_hex_pipe, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
-  touch(hexfast::k_elem_main_hex_pipe);
+  touch(hexfast::k_elem_main_hex_brick<BRICK_STRIDE, BRICK_WS, 4>); touch(hexfast::k_elem_main_hex_brick<BRICK_STRIDE, BRICK_WS, 5>);
   touch(k_node_update<3, true, 4>); touch(k_node_update<3, false, 4>); touch(k_node_update<3, false, 4, false, false, 5>); touch(k_node_update<3, false, 2>); touch(k_node_update<3, false, 8>);
   touch(k_node_update<2, true, 4>); touch(k_node_update<2, false, 4>); touch(k_node_update<2, false, 4, false, false, 5>); touch(k_node_update<2, false, 2>); touch(k_node_update<2, false, 8>);
   touch(k_halo_send<0>); touch(k_halo_send<1>); touch(k_halo_send<2>); touch(k_halo_wait);

@@ -37,8 +37,8 @@ struct WfLaunch {
   void (*p_node)(const WfDev &, double *out, cudaStream_t);
   void (*min_edge)(const WfDev &, double *elem_length, unsigned long long *keys3, cudaStream_t);
   void (*max_vel)(const WfDev &, unsigned long long *keys3, cudaStream_t);
-  void (*soa_to_aos)(const double *soa, long long pitch, int nc, long long n, double scale, double *aos, cudaStream_t);
-  void (*aos_to_soa)(const double *aos, long long pitch, int nc, long long n, double *soa, cudaStream_t);
+  void (*soa_to_aos)(const double *soa, long long pitch, int nc, long long n, double scale, double *aos, const int *map, cudaStream_t);
+  void (*aos_to_soa)(const double *aos, long long pitch, int nc, long long n, double *soa, const int *map, cudaStream_t);
   void (*node_thermal)(const WfDev &, const WfPar &, cudaStream_t);
   int (*tile_forces)(const WfDev &, const WfPar &, int separate_hg); /* does the step use WfDev::ftile instead of fsell? */
 };

@@ -2,6 +2,8 @@
 // element-block partition and halo lists.  No CUDA here, so the CPU test-suite can check every
 // integer artefact bit-exactly against the oracle without a GPU.
 #include <algorithm>
+#include <cmath>
+#include <cstdint>
 #include <cstdlib>
 #include <cstring>
 #include <vector>
@@ -111,6 +113,82 @@ extern "C" int wf_host_nodel(int n_nodes, int n_elems, int k, const unsigned *el
       nodel_loc[offset[n] + count[n]] = ln;
       count[n]++;
     }
+  return 0;
+}
+
+// ---- internal element order ("element order") ---------------------------------------------------
+// The element passes give one CTA 128 consecutive elements and one warp 32 (a force tile); how many DISTINCT nodes
+// such a run touches decides the staging traffic of E1/E2 and the number of force partials N2 gathers.  In the
+// reference's numbering (AddBoxLength: x fastest) a 32-element run is a 1-D row segment with 132 distinct nodes; along
+// a Morton (Z-order) curve of the element centroids it is a 4x4x2 brick with 75, and 128 elements are an 8x4x4 brick
+// with 225 instead of ~516.  The engine therefore keeps its element arrays in Morton order internally and converts
+// at the ABI (wf_get_array / wf_set_array); node->element lists stay in ascending USER element id, so every nodal
+// sum keeps the reference's order.  Integer work, restated in numpy by the CPU tests:
+//   box = bounding box of the nodes, ext_c = hi_c - lo_c; active dims = those with ext_c > 0 (na of them);
+//   cells = max(1, n_elems / per_cell), per_cell = 1 (hexa, quad), 6 (tetra), 2 (triangle);
+//   h = pow(prod ext_c / cells, 1/na); n_c = max(1, (int)(ext_c / h + 0.5));
+//   q_c = min(n_c - 1, (int)((centroid_c - lo_c) / ext_c * n_c)), centroid = (sum of the k node coordinates) / k;
+//   key = bit-interleave(q_0, q_1[, q_2]) with q_0 in the lowest bit; order = ascending (key, user id).
+// mode 0 = identity.  perm[internal] = user.
+static inline uint64_t spread_bits(uint32_t v, int ndim) {
+  uint64_t r = 0;
+  for (int b = 0; b < (ndim == 3 ? 21 : 31); b++) r |= (uint64_t)((v >> b) & 1u) << (ndim * b);
+  return r;
+}
+extern "C" int wf_host_elem_order(int dim, int k, int n_nodes, int n_elems, const double *x, const unsigned *elnod, int mode,
+                                  int *perm) {
+  if (n_elems <= 0 || n_nodes <= 0 || !x || !elnod || !perm || (dim != 2 && dim != 3)) return 1;
+  if (mode == 0) {
+    for (int e = 0; e < n_elems; e++) perm[e] = e;
+    return 0;
+  }
+  double lo[3] = {0, 0, 0}, hi[3] = {0, 0, 0};
+  for (int c = 0; c < dim; c++) lo[c] = hi[c] = x[c];
+  for (long long n = 1; n < n_nodes; n++)
+    for (int c = 0; c < dim; c++) {
+      const double v = x[n * dim + c];
+      if (v < lo[c]) lo[c] = v;
+      if (v > hi[c]) hi[c] = v;
+    }
+  const int per_cell = (k == 8) ? 1 : (dim == 3 ? 6 : (k == 4 ? 1 : 2));
+  const long long cells = std::max<long long>(1, n_elems / per_cell);
+  double ext[3] = {0, 0, 0}, vol = 1.0;
+  int na = 0;
+  for (int c = 0; c < dim; c++) {
+    ext[c] = hi[c] - lo[c];
+    if (ext[c] > 0.0) { vol *= ext[c]; na++; }
+  }
+  int ncell[3] = {1, 1, 1};
+  if (na > 0) {
+    const double h = pow(vol / (double)cells, 1.0 / (double)na);
+    const int cap = dim == 3 ? (1 << 21) : (1 << 30);
+    for (int c = 0; c < dim; c++)
+      if (ext[c] > 0.0) {
+        const double r = ext[c] / h + 0.5;
+        ncell[c] = r >= (double)cap ? cap : std::max(1, (int)r);
+      }
+  }
+  for (size_t i = 0; i < (size_t)n_elems * k; i++)
+    if (elnod[i] >= (unsigned)n_nodes) return 2;
+  std::vector<std::pair<uint64_t, int>> keys((size_t)n_elems);
+  for (int e = 0; e < n_elems; e++) {
+    uint32_t q[3] = {0, 0, 0};
+    for (int c = 0; c < dim; c++) {
+      if (!(ext[c] > 0.0)) continue;
+      double s = 0.0;
+      for (int a = 0; a < k; a++) s += x[(size_t)elnod[(size_t)e * k + a] * dim + c];
+      const double t = (s / (double)k - lo[c]) / ext[c] * (double)ncell[c];
+      int qi = (int)t;
+      if (qi < 0) qi = 0;
+      if (qi > ncell[c] - 1) qi = ncell[c] - 1;
+      q[c] = (uint32_t)qi;
+    }
+    uint64_t key = spread_bits(q[0], dim) | (spread_bits(q[1], dim) << 1);
+    if (dim == 3) key |= spread_bits(q[2], dim) << 2;
+    keys[(size_t)e] = std::make_pair(key, e);
+  }
+  std::sort(keys.begin(), keys.end());
+  for (int e = 0; e < n_elems; e++) perm[e] = keys[(size_t)e].second;
   return 0;
 }
 

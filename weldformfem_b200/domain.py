@@ -19,7 +19,7 @@ BILINEAR, HOLLOMON, JOHNSON_COOK, GMT = 0, 1, 2, 3
 STRICT, FAST = 1, 0
 
 _INT_ARRAYS = {"m_nodel": np.int32, "m_nodel_loc": np.int32, "m_nodel_offset": np.int32, "m_nodel_count": np.int32,
-               "m_elnod": np.uint32, "ext_nodes": np.uint8, "m_mesh_in_contact": np.int32}
+               "m_elnod": np.uint32, "ext_nodes": np.uint8, "m_mesh_in_contact": np.int32, "elem_perm": np.int32}
 
 
 def axis_plane_mesh(dimension, mesh_id, axis, positaxisorent, p1, p2, dens):
@@ -48,7 +48,10 @@ class WfError(RuntimeError):
 class Domain_d:
     """One explicit-dynamics domain on one GPU."""
 
-    def __init__(self, device: int = 0, strict: bool = False):
+    def __init__(self, device: int = 0, strict: bool = False, elem_order: int | None = None):
+        """elem_order: internal element order of the engine (None = default = Morton, 0 = the caller's numbering);
+        arrays always cross the ABI in the caller's numbering."""
+        self._elem_order = elem_order
         self._lib = _lib.load()
         self._h = C.c_void_p()
         self._device = device
@@ -78,6 +81,8 @@ class Domain_d:
         if rc != 0:
             raise WfError(self._lib.wf_last_error(None).decode())
         self._h = h
+        if self._elem_order is not None:
+            self._ck(self._lib.wf_set_elem_order(self._h, int(self._elem_order)))
         self.dim, self.nodxelem, self._domtype = dim, k, domtype
         if domtype == AXISYMM and self._vol_weight:
             self._ck(self._lib.wf_set_axisymm_vol_weight(self._h, 1))
