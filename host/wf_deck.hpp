@@ -148,8 +148,11 @@ inline DeckSummary setup_from_deck(const std::string &deck_path, Domain_d &dom, 
   std::string dir = deck_path.substr(0, deck_path.find_last_of("/\\") + 1);
   DeckSummary S;
 
-  // loadStabilizationParams, main.C:84-120: with a "Stabilization" block EVERY field is overwritten (absent keys -> 0;
-  // pspg_scale is never read), without one the constructor defaults stay (all 0, hg_stiff 0.1; Domain_d.h:283-296)
+  // loadStabilizationParams, main.C:84-120: with a "Stabilization" block EVERY field is overwritten (absent keys -> 0),
+  // without one the constructor defaults stay (all 0, hg_stiff 0.1; Domain_d.h:283-296).  pspg_scale is the exception:
+  // main.C never assigns it in its local struct, so the reference passes an INDETERMINATE value on to
+  // calcElemPressure (Mechanical.C:796 reads it on the 3D path when div v < 0).  Deliberate deviation: this
+  // front-end pins it to 0 unless the deck carries an explicit "pspg_scale" key.
   if (j.contains("Stabilization") && !j["Stabilization"].is_null()) {
     const Json &st = j["Stabilization"];
     StabilizationParams p;
@@ -158,6 +161,7 @@ inline DeckSummary setup_from_deck(const std::string &deck_path, Domain_d &dom, 
     p.av_coeff_div = st.value("av_coeff_div", 0.0); p.av_coeff_bulk = st.value("av_coeff_bulk", 0.0);
     p.log_factor = st.value("log_factor", 0.0); p.p_pspg_bulkfac = st.value("p_pspg_bulkfac", 0.0);
     p.J_min = st.value("J_min", 0.0); p.hg_visc = st.value("hg_visc", 0.0); p.hg_stiff = st.value("hg_stiff", 0.0);
+    p.pspg_scale = st.value("pspg_scale", 0.0);
     dom.m_stab = p;
   } else {
     dom.m_stab.hg_stiff = 0.1;
@@ -190,6 +194,11 @@ inline DeckSummary setup_from_deck(const std::string &deck_path, Domain_d &dom, 
   }
   int press_alg = 0;
   readValue(config["pressAlgorithm"], press_alg);
+  // Solver_explicit.C:733-743 dispatches on 0 and 1 only (any other value would skip the pressure update altogether)
+  if (press_alg != 0 && press_alg != 1) throw std::runtime_error("pressAlgorithm must be 0 or 1");
+  bool dev_elastic = true;
+  readValue(config["devElastic"], dev_elastic);
+  if (!dev_elastic) throw std::runtime_error("devElastic = false (calcElemPressureRigid) is not supported");
   if (press_alg > 0) dom.m_press_algorithm = press_alg;
   dom.setHexaHourglass(hexa_hg);
   dom.setStrict(strict);

@@ -269,6 +269,9 @@ int wf_host_force_tiles(int n_nodes, int n_elems, int nodxelem, int dim, const u
  * against the numpy restatement in tests/test_host_mesh.py. */
 int wf_host_elem_order(int dim, int nodxelem, int n_nodes, int n_elems, const double *x, const unsigned *elnod, int mode,
                        int *perm);
+/* Shared-memory slots of a sorted node list for the brick form of the hexa main pass (csrc/wf_mesh.cpp): run r of
+ * consecutive ids starts at the first free slot congruent to 12 r (mod 16).  Returns the slot count. */
+int wf_host_run_slots(int n, const int *sorted_ids, int *slots);
 const char *wf_version(void);
 
 #ifdef __cplusplus

@@ -130,3 +130,33 @@ def test_global_mesh_entry_point_matches_box(oracle_port):
     for nm in ("x", "m_tau"):
         assert np.array_equal(cl.get(nm), a.get(nm))
     a.close(); cl.close()
+
+
+def test_halo_timeout_is_sticky_and_surfaces_everywhere(monkeypatch):
+    """A neighbour that never sends: the wait kernel gives up after WF_HALO_TIMEOUT_S, and from then on every entry point
+    that reads the engine fails loudly (wf_get_array, wf_synchronize, wf_nonfinite_flag, wf_halo_status) instead of
+    handing back shared-node state summed from stale partials."""
+    from weldformfem_b200.distributed import LocalCluster
+    from weldformfem_b200.domain import WfError
+    monkeypatch.setenv("WF_HALO_TIMEOUT_S", "0.3")
+    cl = LocalCluster(2, devices_for(2))
+    CASES["hex"].apply(cl)              # init runs on both ranks: the exchanges of wf_init complete
+    cl.step(2)
+    cl.synchronize()
+    r0 = cl.ranks[0]
+    r0.step(1)                          # rank 1 does not step: its partials never arrive
+    with pytest.raises(WfError, match="halo exchange timed out"):
+        r0.synchronize()
+    with pytest.raises(WfError, match="halo exchange timed out"):
+        r0.get("x")
+    with pytest.raises(WfError, match="halo exchange timed out"):
+        r0.nonfinite_flag()
+    with pytest.raises(WfError, match="halo exchange timed out"):
+        r0.halo_status()
+    r0.step(3)                          # sticky: later waits return at once instead of spinning 3 x timeout
+    import time
+    t0 = time.time()
+    with pytest.raises(WfError):
+        r0.synchronize()
+    assert time.time() - t0 < 0.25
+    cl.close()

@@ -404,15 +404,27 @@ def numpy_elem_order(dim, k, x, el):
         h = math.pow(vol / float(cells), 1.0 / float(len(act)))
         for c in act:
             ncell[c] = max(1, int(ext[c] / h + 0.5))
-    key = np.zeros(ne, np.uint64)
+    q = np.zeros((dim, ne), np.uint64)
     for c in act:
         s = np.zeros(ne)
         for a in range(k):                       # same summation order as the C loop
             s = s + X[EL[:, a], c]
         t = (s / float(k) - lo[c]) / ext[c] * float(ncell[c])
-        q = np.clip(t.astype(np.int64), 0, ncell[c] - 1).astype(np.uint64)
-        for b in range(21 if dim == 3 else 31):
-            key |= ((q >> np.uint64(b)) & np.uint64(1)) << np.uint64(dim * b + c)
+        q[c] = np.clip(t.astype(np.int64), 0, ncell[c] - 1).astype(np.uint64)
+
+    def interleave(vals, bits):
+        key = np.zeros(ne, np.uint64)
+        nd = len(vals)
+        for c, v in enumerate(vals):
+            for b in range(bits):
+                key |= ((v >> np.uint64(b)) & np.uint64(1)) << np.uint64(nd * b + c)
+        return key
+    if k == 8 and dim == 3:     # tiles of 4x4x2 in Morton order (z lowest), inside a tile layer / row / column
+        U = np.uint64
+        tkey = interleave([q[2] >> U(1), q[0] >> U(2), q[1] >> U(2)], 21)
+        key = (tkey << U(5)) | ((q[2] & U(1)) << U(4)) | ((q[1] & U(3)) << U(2)) | (q[0] & U(3))
+    else:
+        key = interleave([q[c] for c in range(dim)], 21 if dim == 3 else 31)
     return np.lexsort((np.arange(ne), key)).astype(np.int32)
 
 
@@ -448,3 +460,56 @@ def test_elem_order_rejects_bad_connectivity():
     el = np.array([0, 1, 7], np.uint32)
     rc, _ = host_elem_order(3, 3, x, el)   # dim 3 / k 3 is not an element type, but only the range check matters here
     assert rc != 0
+
+
+def host_run_slots(ids):
+    from weldformfem_b200 import _lib
+    lib = _lib.load()
+    ids = np.ascontiguousarray(ids, np.int32)
+    out = np.empty(ids.size, np.int32)
+    n = lib.wf_host_run_slots(ids.size, ids.ctypes.data_as(C.POINTER(C.c_int)), out.ctypes.data_as(C.POINTER(C.c_int)))
+    return n, out
+
+
+def numpy_run_slots(ids):
+    slots, cur, r, a = [], 0, 0, 0
+    while a < len(ids):
+        b = a
+        while b + 1 < len(ids) and ids[b + 1] == ids[b] + 1:
+            b += 1
+        while cur % 16 != (12 * r) % 16:
+            cur += 1
+        slots += list(range(cur, cur + b - a + 1))
+        cur += b - a + 1
+        r += 1
+        a = b + 1
+    return cur, np.array(slots, np.int32)
+
+
+def test_run_slots_bit_exact_and_conflict_free_on_bricks():
+    """wf_host_run_slots against its restatement, and the property it exists for: in the engine's hexa element order
+    the 16 lanes of a half-warp (one 4x4 layer of a tile) read, for each of the eight corners, 16 nodes whose slots
+    fall into 16 different 8-byte bank pairs — for the CTA copy (128 elements) and the tile accumulators (32)."""
+    rng = np.random.default_rng(5)
+    for _ in range(20):
+        ids = np.unique(rng.integers(0, 400, rng.integers(1, 300)))
+        n, sl = host_run_slots(ids)
+        n2, sl2 = numpy_run_slots(list(ids))
+        assert n == n2 and np.array_equal(sl, sl2)
+        assert np.all(np.diff(sl) > 0)
+    dim, k, x, el = host_box((0, 0, 0), (2.4001, 2.4001, 2.4001), 0.05, False)   # 24^3 hexes
+    assert el.size == 8 * 24 ** 3
+    EL = el.reshape(-1, 8).astype(np.int64)
+    rc, perm = host_elem_order(dim, k, x, el)
+    assert rc == 0
+    ELi = EL[perm]
+    for chunk, limit in ((128, 304), (32, 176)):
+        for c0 in range(0, ELi.shape[0], chunk):
+            ids = np.unique(ELi[c0:c0 + chunk])
+            n, sl = host_run_slots(ids)
+            assert n <= limit
+            slot = dict(zip(ids.tolist(), sl.tolist()))
+            for h0 in range(c0, c0 + chunk, 16):
+                for c in range(8):
+                    banks = [slot[g] % 16 for g in ELi[h0:h0 + 16, c]]
+                    assert len(set(banks)) == 16

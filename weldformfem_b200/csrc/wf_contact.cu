@@ -472,7 +472,7 @@ static int calc_ext_face_areas(wf_engine *E) {
 }
 
 // Domain_d::SearchExtNodes (Domain_d.C:110-205): external faces / nodes, then CalcExtFaceAreas
-extern "C" int wf_SearchExtNodes(wf_engine *E) {
+extern "C" int wf_SearchExtNodes(wf_engine *E) { WF_NULLCHK(E);
   NEED(E->meshed, "SearchExtNodes needs the mesh");
   NEED(!E->distributed, "contact is not available on a partitioned mesh");
   NEED((E->dim == 3 && E->k == 4) || (E->dim == 2 && E->k == 4),
@@ -526,7 +526,7 @@ extern "C" int wf_SearchExtNodes(wf_engine *E) {
   return wf_check_launch(E, "wf_SearchExtNodes");
 }
 
-extern "C" int wf_CalcExtFaceAreas(wf_engine *E) {
+extern "C" int wf_CalcExtFaceAreas(wf_engine *E) { WF_NULLCHK(E);
   NEED(E->ext_searched, "CalcExtFaceAreas needs wf_SearchExtNodes");
   NEED(!E->predicted, "engine is mid-batch");
   CK(cudaSetDevice(E->device));
@@ -538,7 +538,7 @@ extern "C" int wf_CalcExtFaceAreas(wf_engine *E) {
 // (main.C:672-708, 775-828): node / node_v as xyz triples, elnode with 3 (3D) or 2 (2D) ids per facet, the
 // initial facet normals and ele_mesh_id.
 extern "C" int wf_set_trimesh(wf_engine *E, int dimension, int n_nodes, int n_elems, const double *node, const double *node_v,
-                              const int *elnode, const double *normal, const int *ele_mesh_id) {
+                              const int *elnode, const double *normal, const int *ele_mesh_id) { WF_NULLCHK(E);
   NEED(E->ext_searched, "wf_set_trimesh needs wf_SearchExtNodes (main.C:650 comes first)");
   NEED(!E->trimesh_set, "rigid surfaces already set");
   NEED(dimension == E->dim, "TriMesh_d::dimension must equal the domain's dimension");
@@ -561,7 +561,7 @@ extern "C" int wf_set_trimesh(wf_engine *E, int dimension, int n_nodes, int n_el
 }
 
 // friction + penalty factor (main.C:716-725), CalcSpheres + setContactOn (main.C:842-847), SetEndTime (Domain_d.h:636)
-extern "C" int wf_set_contact(wf_engine *E, double mu_sta, double mu_dyn, double penalty_factor, double end_time) {
+extern "C" int wf_set_contact(wf_engine *E, double mu_sta, double mu_dyn, double penalty_factor, double end_time) { WF_NULLCHK(E);
   NEED(E->trimesh_set, "wf_set_contact needs wf_set_trimesh");
   NEED(E->material_set, "wf_set_contact needs the material (contact stiffness uses E)");
   NEED(!E->inited, "contact must be switched on before wf_init");
@@ -581,7 +581,7 @@ extern "C" int wf_set_contact(wf_engine *E, double mu_sta, double mu_dyn, double
 }
 
 // heatCondCoeff / dieTemp of the rigid surfaces (main.C:718-719): contact heat flow into the nodal temperature
-extern "C" int wf_set_contact_heat(wf_engine *E, double heat_cond, double T_const) {
+extern "C" int wf_set_contact_heat(wf_engine *E, double heat_cond, double T_const) { WF_NULLCHK(E);
   NEED(E->contact, "wf_set_contact_heat needs wf_set_contact");
   NEED(E->d.T, "wf_set_contact_heat needs wf_set_thermal");
   NEED(!E->inited, "contact heat must be set before wf_init");
@@ -640,20 +640,20 @@ int wf_contact_step_end(wf_engine *E) {
 }
 
 // unfused entry points
-extern "C" int wf_CalcContactForces(wf_engine *E) {
+extern "C" int wf_CalcContactForces(wf_engine *E) { WF_NULLCHK(E);
   NEED(E->contact && E->inited, "CalcContactForces needs wf_set_contact and wf_init");
   NEED(!E->predicted, "engine is mid-batch");
   CK(cudaSetDevice(E->device));
   if (contact_forces(E, (E->a_in_dbg && E->d.a) ? E->d.a : E->d.prev_a)) return 1;
   return wf_check_launch(E, "wf_CalcContactForces");
 }
-extern "C" int wf_MoveTriMesh(wf_engine *E) {
+extern "C" int wf_MoveTriMesh(wf_engine *E) { WF_NULLCHK(E);
   NEED(E->contact && E->inited, "MoveTriMesh needs wf_set_contact and wf_init");
   CK(cudaSetDevice(E->device));
   if (wf_contact_step_end(E)) return 1;
   return wf_check_launch(E, "wf_MoveTriMesh");
 }
-extern "C" int wf_get_trimesh_counts(wf_engine *E, int *dimension, int *n_nodes, int *n_elems) {
+extern "C" int wf_get_trimesh_counts(wf_engine *E, int *dimension, int *n_nodes, int *n_elems) { WF_NULLCHK(E);
   if (dimension) *dimension = E->C.tm_dim;
   if (n_nodes) *n_nodes = E->trimesh_set ? E->C.tm_nn : 0;
   if (n_elems) *n_elems = E->trimesh_set ? E->C.tm_ne : 0;

@@ -18,6 +18,8 @@
 
 #define WF_MAXK 8
 #define WF_EBLK 128 /* elements per CTA of the element passes */
+#define WF_BRICK_STRIDE 304 /* compile-time pitches of k_elem_main_hex_brick: slots of a CTA's node copy (8x4x4 brick of a */
+#define WF_BRICK_WS 176     /* structured mesh: 297) and of a tile's accumulators (4x4x2 brick: 173) */
 #define WF_HALO_NC 3 /* doubles per shared node and exchange (max: dim force components / init triple) */
 
 struct WfHaloNb {
@@ -76,8 +78,7 @@ struct WfDev {
   const int *blk_nodes;
   const unsigned short *lidx;        /* [k][ep] */
   int blk_umax;                      /* longest unique list */
-  int blk_pitch;                     /* pitch of blk_pad and of the staged copies in shared memory: blk_umax rounded up to 32;
-                                      * hexahedra with blk_umax <= 288: exactly 288 (compile-time pitch of k_elem_main_hex_brick) */
+  int blk_pitch;                     /* pitch of blk_pad and of the staged copies in shared memory: blk_umax rounded up to 32 */
   const int *blk_pad;                /* [nblk][blk_pitch] the same lists at a fixed pitch, -1 padded (no blk_off round trip) */
   const int *pos;                    /* [k][ep] offset of (e, ln) in fsell: dim*q - (dim-1)*(n&31), q = sell index */
   double *fsell, *fsell_hg;          /* [slice][j][dim][32] node-ordered element (and hourglass) forces */
@@ -92,8 +93,15 @@ struct WfDev {
   const long long *tf_ptr;           /* [nslices+1] */
   const unsigned *tf_slots;
   const unsigned char *tf_idx;       /* [k][ep] (hexahedra) */
-  const uint4 *lidx_pk;              /* [ep] hexahedra: the eight lidx values of an element in one 16 B record */
-  const uint2 *tf_idx_pk;            /* [ep] hexahedra: the eight tf_idx values of an element in one 8 B record */
+  /* brick form of the hexa main pass (NULL when the bank-aware layouts do not fit its compile-time pitches): node list
+   * of CTA b at blk_pad_b + b * WF_BRICK_STRIDE indexed by shared-memory SLOT (wf_host_run_slots, -1 = hole); the slots
+   * of an element's eight nodes in the CTA copy (16 bit each) and in its tile's accumulators (8 bit each) as one
+   * record per element; per tile tf_r2s[tile * tf_r2s_pitch] = number of unique nodes, then the slot of rank 0, 1, ... */
+  const int *blk_pad_b;
+  const uint4 *lidx_pk;              /* [ep] */
+  const uint2 *tf_idx_pk;            /* [ep] */
+  const unsigned char *tf_r2s;
+  int tf_r2s_pitch;
   /* tetrahedra: corners of different elements of a tile DO share nodes, so the tile sum is pulled instead: every
    * element drops its k*dim force values in shared memory and lane u adds up the entries of unique node u listed in
    * the tile's incidence table (ascending element, then corner: a fixed order).  Table of tile w at

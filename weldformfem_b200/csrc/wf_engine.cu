@@ -23,6 +23,7 @@ static std::string g_create_error;
 #include "wf_engine_priv.h"
 
 static int check_launch(wf_engine *E, const char *what) { return wf_check_launch(E, what); }
+int wf_null_engine(void) { g_create_error = "null engine handle (create the mesh first)"; return 1; }
 
 static int select_flavour(wf_engine *E) {
   E->L = E->strict ? wf_strict_table() : wf_fast_table();
@@ -91,17 +92,30 @@ extern "C" void wf_destroy(wf_engine *E) {
   delete E;
 }
 
-extern "C" int wf_set_stream(wf_engine *E, void *s) {
+extern "C" int wf_set_stream(wf_engine *E, void *s) { WF_NULLCHK(E);
   CK(cudaSetDevice(E->device));
   CK(cudaStreamSynchronize(E->stream));
   if (E->own_stream) { cudaStreamDestroy(E->stream); E->own_stream = false; }
   E->stream = (cudaStream_t)s;
   return 0;
 }
-extern "C" int wf_get_stream(wf_engine *E, void **s) { if (s) *s = (void *)E->stream; return 0; }
-extern "C" int wf_synchronize(wf_engine *E) { CK(cudaSetDevice(E->device)); CK(cudaStreamSynchronize(E->stream)); return 0; }
+extern "C" int wf_get_stream(wf_engine *E, void **s) { WF_NULLCHK(E); if (s) *s = (void *)E->stream; return 0; }
+// multi-GPU: a halo wait that timed out leaves comm_error set (k_halo_wait); surfaced by every entry point that reads
+static int check_halo_error(wf_engine *E) {
+  if (!E->distributed || !E->d.comm_error) return 0;
+  int e = 0;
+  CK(cudaMemcpyAsync(&e, E->d.comm_error, sizeof(int), cudaMemcpyDeviceToHost, E->stream));
+  CK(cudaStreamSynchronize(E->stream));
+  if (e) FAIL("halo exchange timed out waiting for neighbour index " + std::to_string(e - 1) + " (shared-node state is stale)");
+  return 0;
+}
+extern "C" int wf_synchronize(wf_engine *E) { WF_NULLCHK(E);
+  CK(cudaSetDevice(E->device));
+  CK(cudaStreamSynchronize(E->stream));
+  return check_halo_error(E);
+}
 
-extern "C" int wf_set_axisymm_vol_weight(wf_engine *E, int on) {
+extern "C" int wf_set_axisymm_vol_weight(wf_engine *E, int on) { WF_NULLCHK(E);
   NEED(E->domtype == WF_AXISYMM, "vol_weight only applies to axisymmetric domains");
   E->d.vol_weight = on ? 1 : 0;
   return 0;
@@ -239,7 +253,7 @@ static int upload_mesh(wf_engine *E, int nn, int ne, const double *x, const unsi
     CK(cudaStreamSynchronize(E->stream));
     d.blk_off = doff; d.blk_nodes = dnodes; d.lidx = dl; d.blk_umax = umax;
     {
-      const int pitch = (k == 8 && umax <= 288) ? 288 : (umax + 31) / 32 * 32; // 288: see WfDev::blk_pitch
+      const int pitch = (umax + 31) / 32 * 32;
       d.blk_pitch = pitch;
       std::vector<int> pad((size_t)nblk * pitch, -1);
       for (int b = 0; b < nblk; b++) std::copy(bnodes.begin() + boff[b], bnodes.begin() + boff[b + 1], pad.begin() + (size_t)b * pitch);
@@ -251,7 +265,7 @@ static int upload_mesh(wf_engine *E, int nn, int ne, const double *x, const unsi
     }
     // tile-reduced force path (WfDev::ftile): tables built on the host (wf_force_tiles_build, wf_mesh.cpp)
     d.ftile = nullptr; d.tf_ptr = nullptr; d.tf_slots = nullptr; d.tf_idx = nullptr; d.tf_tab = nullptr;
-    d.lidx_pk = nullptr; d.tf_idx_pk = nullptr;
+    d.lidx_pk = nullptr; d.tf_idx_pk = nullptr; d.blk_pad_b = nullptr; d.tf_r2s = nullptr; d.tf_r2s_pitch = 0;
     d.tf_stride = 0; d.tf_tpitch = 0;
     if (dim == 3) { // 2D (1M quads, measured): rounds form E2 0.080 -> 0.099 ms, pull form 0.105 ms, N2 unchanged: not used
       WfForceTiles T;
@@ -268,20 +282,55 @@ static int upload_mesh(wf_engine *E, int nn, int ne, const double *x, const unsi
           if (dalloc(E, &dti, T.tidx.size())) return 1;
           CK(cudaMemcpyAsync(dti, T.tidx.data(), T.tidx.size(), cudaMemcpyHostToDevice, E->stream));
           d.tf_idx = dti;
-          // the same local indices as one record per element (k_elem_main_hex_brick)
-          std::vector<unsigned short> lpk((size_t)8 * d.ep, 0);
-          std::vector<unsigned char> tpk((size_t)8 * d.ep, 0);
-          for (int e = 0; e < ne; e++)
-            for (int n = 0; n < 8; n++) {
-              lpk[(size_t)e * 8 + n] = lidx[(size_t)n * d.ep + e];
-              tpk[(size_t)e * 8 + n] = T.tidx[(size_t)n * d.ep + e];
+          // brick form of the main pass (k_elem_main_hex_brick): bank-aware shared-memory slots (wf_host_run_slots) of
+          // the CTA's node list and of every tile's node list, the slots of an element's eight nodes packed into one
+          // record each, and per tile the table rank -> slot used when the partial sums are written out
+          if (T.rounds) {
+            constexpr int BS = WF_BRICK_STRIDE, BW = WF_BRICK_WS;
+            const int ntile = T.n_tiles, rp = (T.stride + 1 + 3) / 4 * 4;
+            std::vector<int> bpad((size_t)nblk * BS, -1), sl, ids;
+            std::vector<unsigned short> lpk((size_t)8 * d.ep, 0);
+            std::vector<unsigned char> tpk((size_t)8 * d.ep, 0), r2s((size_t)ntile * rp, 0);
+            bool fits = true;
+            for (int b = 0; b < nblk && fits; b++) {
+              const int u0 = boff[b], U = boff[b + 1] - u0;
+              sl.resize(U);
+              if (U > BS) { fits = false; break; }
+              // ragged CTAs (not a whole brick: more, shorter runs) keep the plain ascending layout
+              if (wf_host_run_slots(U, bnodes.data() + u0, sl.data()) > BS)
+                for (int i = 0; i < U; i++) sl[i] = i;
+              for (int i = 0; i < U; i++) bpad[(size_t)b * BS + sl[i]] = bnodes[u0 + i];
+              const int e0 = b * WF_EBLK, e1 = std::min(ne, e0 + WF_EBLK);
+              for (int e = e0; e < e1; e++)
+                for (int n = 0; n < 8; n++) lpk[(size_t)e * 8 + n] = (unsigned short)sl[lidx[(size_t)n * d.ep + e]];
             }
-          uint4 *dl4; uint2 *dt2;
-          if (dalloc(E, &dl4, (size_t)d.ep) || dalloc(E, &dt2, (size_t)d.ep)) return 1;
-          CK(cudaMemcpyAsync(dl4, lpk.data(), lpk.size() * sizeof(unsigned short), cudaMemcpyHostToDevice, E->stream));
-          CK(cudaMemcpyAsync(dt2, tpk.data(), tpk.size(), cudaMemcpyHostToDevice, E->stream));
-          CK(cudaStreamSynchronize(E->stream));
-          d.lidx_pk = dl4; d.tf_idx_pk = dt2;
+            for (int w = 0; w < ntile && fits; w++) {
+              const int e0 = w * 32, e1 = std::min(ne, e0 + 32);
+              ids.assign(eli + (size_t)e0 * 8, eli + (size_t)e1 * 8);
+              std::sort(ids.begin(), ids.end());
+              ids.erase(std::unique(ids.begin(), ids.end()), ids.end());
+              const int U = (int)ids.size();
+              sl.resize(U);
+              if (U > BW || U + 1 > rp) { fits = false; break; }
+              if (wf_host_run_slots(U, ids.data(), sl.data()) > BW)
+                for (int i = 0; i < U; i++) sl[i] = i;
+              r2s[(size_t)w * rp] = (unsigned char)U;
+              for (int i = 0; i < U; i++) r2s[(size_t)w * rp + 1 + i] = (unsigned char)sl[i];
+              for (int e = e0; e < e1; e++)
+                for (int n = 0; n < 8; n++) tpk[(size_t)e * 8 + n] = (unsigned char)sl[T.tidx[(size_t)n * d.ep + e]];
+            }
+            if (fits) {
+              uint4 *dl4; uint2 *dt2; int *dbp; unsigned char *dr;
+              if (dalloc(E, &dl4, (size_t)d.ep) || dalloc(E, &dt2, (size_t)d.ep) || dalloc(E, &dbp, bpad.size()) || dalloc(E, &dr, r2s.size()))
+                return 1;
+              CK(cudaMemcpyAsync(dl4, lpk.data(), lpk.size() * sizeof(unsigned short), cudaMemcpyHostToDevice, E->stream));
+              CK(cudaMemcpyAsync(dt2, tpk.data(), tpk.size(), cudaMemcpyHostToDevice, E->stream));
+              CK(cudaMemcpyAsync(dbp, bpad.data(), bpad.size() * sizeof(int), cudaMemcpyHostToDevice, E->stream));
+              CK(cudaMemcpyAsync(dr, r2s.data(), r2s.size(), cudaMemcpyHostToDevice, E->stream));
+              CK(cudaStreamSynchronize(E->stream));
+              d.lidx_pk = dl4; d.tf_idx_pk = dt2; d.blk_pad_b = dbp; d.tf_r2s = dr; d.tf_r2s_pitch = rp;
+            }
+          }
         } else {
           unsigned char *dtab;
           if (dalloc(E, &dtab, T.tab.size())) return 1;
@@ -324,12 +373,12 @@ static int upload_mesh(wf_engine *E, int nn, int ne, const double *x, const unsi
   return 0;
 }
 
-extern "C" int wf_set_mesh(wf_engine *E, int nn, int ne, const double *x, const unsigned *elnod) {
+extern "C" int wf_set_mesh(wf_engine *E, int nn, int ne, const double *x, const unsigned *elnod) { WF_NULLCHK(E);
   NEED(x && elnod, "null mesh arrays");
   return upload_mesh(E, nn, ne, x, elnod);
 }
 
-extern "C" int wf_gen_box(wf_engine *E, const double V[3], const double L[3], double r, int tritet) {
+extern "C" int wf_gen_box(wf_engine *E, const double V[3], const double L[3], double r, int tritet) { WF_NULLCHK(E);
   WfBox b;
   wf_box_dims(L, r, tritet, &b);
   NEED(b.dim == E->dim && b.k == E->k, "box element type does not match the engine's dim/nodxelem");
@@ -341,14 +390,14 @@ extern "C" int wf_gen_box(wf_engine *E, const double V[3], const double L[3], do
   return upload_mesh(E, (int)b.nn, (int)b.ne, x.data(), el.data());
 }
 
-extern "C" int wf_set_elem_order(wf_engine *E, int mode) {
+extern "C" int wf_set_elem_order(wf_engine *E, int mode) { WF_NULLCHK(E);
   NEED(!E->meshed, "wf_set_elem_order before the mesh is set");
   NEED(mode == 0 || mode == 1, "element order mode must be 0 (caller's numbering) or 1 (Morton)");
   E->order_mode = mode;
   return 0;
 }
 
-extern "C" int wf_get_counts(wf_engine *E, int *nn, int *ne, int *ntot) {
+extern "C" int wf_get_counts(wf_engine *E, int *nn, int *ne, int *ntot) { WF_NULLCHK(E);
   NEED(E->meshed, "no mesh");
   if (nn) *nn = E->nn;
   if (ne) *ne = E->ne;
@@ -359,7 +408,7 @@ extern "C" int wf_get_counts(wf_engine *E, int *nn, int *ne, int *ntot) {
 // ---------------------------------------------------------------------------------------------------
 // material / options / BCs
 // ---------------------------------------------------------------------------------------------------
-extern "C" int wf_set_material(wf_engine *E, const wf_material *m) {
+extern "C" int wf_set_material(wf_engine *E, const wf_material *m) { WF_NULLCHK(E);
   NEED(m, "null material");
   NEED(m->model >= WF_BILINEAR && m->model <= WF_GMT, "material model must be Bilinear, Hollomon, JohnsonCook or GMT");
   E->mat = *m;
@@ -393,7 +442,7 @@ static void refresh_stab_simple(wf_engine *E) {
                       s.log_factor == 0.0 && s.pspg_scale == 0.0 && s.p_pspg_bulkfac == 0.0) ? 1 : 0;
 }
 
-extern "C" int wf_set_stab(wf_engine *E, const wf_stab *s) {
+extern "C" int wf_set_stab(wf_engine *E, const wf_stab *s) { WF_NULLCHK(E);
   NEED(s, "null stab");
   E->stab = *s;
   WfPar &P = E->P;
@@ -406,7 +455,7 @@ extern "C" int wf_set_stab(wf_engine *E, const wf_stab *s) {
   return 0;
 }
 
-extern "C" int wf_set_options(wf_engine *E, int press, double av_alpha, double av_beta, int strict) {
+extern "C" int wf_set_options(wf_engine *E, int press, double av_alpha, double av_beta, int strict) { WF_NULLCHK(E);
   NEED(press == WF_PRESS_DEFAULT || press == WF_PRESS_ANP_SHIPPED || press == WF_PRESS_ANP_NODAL, "bad pressure algorithm");
   NEED(!E->inited, "options must be set before wf_init");
   E->P.press = press; E->P.av_alpha = av_alpha; E->P.av_beta = av_beta;
@@ -415,7 +464,7 @@ extern "C" int wf_set_options(wf_engine *E, int press, double av_alpha, double a
   return 0;
 }
 
-extern "C" int wf_set_tracking(wf_engine *E, int flags) {
+extern "C" int wf_set_tracking(wf_engine *E, int flags) { WF_NULLCHK(E);
   NEED(!E->inited, "tracking must be set before wf_init");
   E->tracking = flags;
   return 0;
@@ -423,7 +472,7 @@ extern "C" int wf_set_tracking(wf_engine *E, int flags) {
 
 // thermal coupling: setThermalOn + setTemp(T0) + thermalCond / thermalHeatCap / thermalExp + plHeatFrac
 // (main.C:218, 436-441, 567-570; Thermal.C)
-extern "C" int wf_set_thermal(wf_engine *E, double k_T, double cp_T, double exp_T, double plheatfrac, double T0) {
+extern "C" int wf_set_thermal(wf_engine *E, double k_T, double cp_T, double exp_T, double plheatfrac, double T0) { WF_NULLCHK(E);
   NEED(E->meshed, "wf_set_thermal needs the mesh");
   NEED(!E->inited, "thermal coupling must be switched on before wf_init");
   NEED(!E->distributed, "thermal coupling is not available on a partitioned mesh");
@@ -440,20 +489,20 @@ extern "C" int wf_set_thermal(wf_engine *E, double k_T, double cp_T, double exp_
   return 0;
 }
 
-extern "C" int wf_add_bc_vel(wf_engine *E, int node, int dim, double val) {
+extern "C" int wf_add_bc_vel(wf_engine *E, int node, int dim, double val) { WF_NULLCHK(E);
   NEED(dim >= 0 && dim < 3, "bad BC dim");
   E->bc_nod[dim].push_back(node);
   E->bc_val[dim].push_back(val);
   E->bcs_ready = false;
   return 0;
 }
-extern "C" int wf_add_bc_vel_array(wf_engine *E, int count, const int *node, const int *dim, const double *val) {
+extern "C" int wf_add_bc_vel_array(wf_engine *E, int count, const int *node, const int *dim, const double *val) { WF_NULLCHK(E);
   for (int i = 0; i < count; i++)
     if (wf_add_bc_vel(E, node[i], dim[i], val[i])) return 1;
   return 0;
 }
 
-extern "C" int wf_allocate_bcs(wf_engine *E) {
+extern "C" int wf_allocate_bcs(wf_engine *E) { WF_NULLCHK(E);
   NEED(E->meshed, "AllocateBCs needs the mesh");
   CK(cudaSetDevice(E->device));
   // per node: mask of prescribed dims + values; a later AddBCVelNode on the same (node, dim) wins, which is
@@ -513,7 +562,7 @@ extern "C" int wf_allocate_bcs(wf_engine *E) {
 // New prescribed values for the BCs of one dimension, in insertion order — the engine-side equivalent of writing
 // into Domain_d::bcx_val / bcy_val / bcz_val (Domain_d.h:901) between steps (time-dependent velocity BCs).
 // Host values are staged in pinned memory and uploaded asynchronously on the engine's stream.
-extern "C" int wf_set_bc_values(wf_engine *E, int dim, int count, const double *vals) {
+extern "C" int wf_set_bc_values(wf_engine *E, int dim, int count, const double *vals) { WF_NULLCHK(E);
   NEED(E->bcs_ready, "wf_set_bc_values needs wf_allocate_bcs");
   NEED(dim >= 0 && dim < E->dim, "bad BC dim");
   NEED(count == (int)E->bc_slot[dim].size(), "count must equal the number of BCs of this dimension");
@@ -542,7 +591,7 @@ extern "C" int wf_set_bc_values(wf_engine *E, int dim, int count, const double *
 // (computeEnergies, Mechanical.C:2145) and a copy of {Ekin, non-finite flag (Solver_explicit.C:779), halo error}
 // into pinned host memory; wf_monitor_wait returns the OLDEST pending result.  Up to two may be pending, so a
 // host loop can read step i's monitor while step i+1 is already running.
-extern "C" int wf_monitor_async(wf_engine *E) {
+extern "C" int wf_monitor_async(wf_engine *E) { WF_NULLCHK(E);
   NEED(E->inited, "wf_monitor_async before wf_init");
   NEED(E->mon_pending < 2, "two monitors already pending: call wf_monitor_wait");
   CK(cudaSetDevice(E->device));
@@ -567,7 +616,7 @@ extern "C" int wf_monitor_async(wf_engine *E) {
   return check_launch(E, "wf_monitor_async");
 }
 
-extern "C" int wf_monitor_wait(wf_engine *E, double *Ekin, int *nonfinite) {
+extern "C" int wf_monitor_wait(wf_engine *E, double *Ekin, int *nonfinite) { WF_NULLCHK(E);
   NEED(E->mon_pending > 0, "no monitor pending");
   CK(cudaSetDevice(E->device));
   const int b = E->mon_head;
@@ -699,7 +748,7 @@ static int init_prologue(wf_engine *E) {
   return check_launch(E, "kernel preload");
 }
 
-extern "C" int wf_init(wf_engine *E, double dt) {
+extern "C" int wf_init(wf_engine *E, double dt) { WF_NULLCHK(E);
   if (init_prologue(E)) return 1;
   if (E->distributed) {
     NEED(E->transport == 0, "host-driven halo transport: initialise with wf_init_phase");
@@ -712,7 +761,7 @@ extern "C" int wf_init(wf_engine *E, double dt) {
   return 0;
 }
 
-extern "C" int wf_init_phase(wf_engine *E, int phase, double dt) {
+extern "C" int wf_init_phase(wf_engine *E, int phase, double dt) { WF_NULLCHK(E);
   NEED(phase >= 0 && phase < 3, "init phase must be 0, 1 or 2");
   NEED(phase == E->init_stage, "init phases must be called in order 0, 1, 2");
   if (phase == 0 && init_prologue(E)) return 1;
@@ -804,14 +853,14 @@ static int step_epilogue(wf_engine *E, const char *what) {
   return check_launch(E, what);
 }
 
-extern "C" int wf_step(wf_engine *E, int nsteps) {
+extern "C" int wf_step(wf_engine *E, int nsteps) { WF_NULLCHK(E);
   if (step_prologue(E)) return 1;
   for (int s = 0; s < nsteps; s++)
     if (step_once(E, s == nsteps - 1)) return 1;
   return step_epilogue(E, "wf_step");
 }
 
-extern "C" int wf_step_phase(wf_engine *E, int phase, int last_step) {
+extern "C" int wf_step_phase(wf_engine *E, int phase, int last_step) { WF_NULLCHK(E);
   NEED(E->inited, "wf_step_phase before wf_init");
   NEED(phase >= 0 && phase < 3, "step phase must be 0, 1 or 2");
   NEED(phase == E->step_stage, "step phases must be called in order 0, 1, 2");
@@ -822,14 +871,14 @@ extern "C" int wf_step_phase(wf_engine *E, int phase, int last_step) {
 }
 
 // tuning / profiling hooks -----------------------------------------------------------------------------
-extern "C" int wf_set_variant(wf_engine *E, int kernel, int variant) {
+extern "C" int wf_set_variant(wf_engine *E, int kernel, int variant) { WF_NULLCHK(E);
   NEED(kernel >= 0 && kernel < 4, "kernel id must be 0..3 (E1, N1, E2, N2)");
   E->P.variant[kernel] = variant;
   return 0;
 }
 
 // same as wf_step on one GPU, with CUDA events around every launch; ms[0..4] += time of predictor, E1, N1, E2, N2
-extern "C" int wf_step_timed(wf_engine *E, int nsteps, float *ms) {
+extern "C" int wf_step_timed(wf_engine *E, int nsteps, float *ms) { WF_NULLCHK(E);
   if (step_prologue(E)) return 1;
   NEED(!E->distributed, "wf_step_timed is a single-GPU profiling hook");
   NEED(ms, "null output");
@@ -877,7 +926,7 @@ extern "C" int wf_step_timed(wf_engine *E, int nsteps, float *ms) {
 // ---------------------------------------------------------------------------------------------------
 // multi-GPU: local part of a partitioned mesh + halo plumbing
 // ---------------------------------------------------------------------------------------------------
-extern "C" int wf_set_mesh_partition(wf_engine *E, const wf_partition *p, const double *x_local) {
+extern "C" int wf_set_mesh_partition(wf_engine *E, const wf_partition *p, const double *x_local) { WF_NULLCHK(E);
   NEED(p, "null partition");
   NEED(wf_partition_k(p) == E->k, "partition nodxelem does not match the engine");
   NEED(E->domtype != WF_AXISYMM, "axisymmetric domains are not partitioned (the axis constraint needs a global min over x_r)");
@@ -969,7 +1018,7 @@ extern "C" int wf_set_mesh_partition(wf_engine *E, const wf_partition *p, const 
 }
 
 extern "C" int wf_halo_info(wf_engine *E, int *rank, int *nranks, int *n_neigh, const int **neigh_ranks, const int **halo_offset,
-                            const int **node_l2g) {
+                            const int **node_l2g) { WF_NULLCHK(E);
   NEED(E->distributed, "not a partitioned engine");
   if (rank) *rank = E->rank;
   if (nranks) *nranks = E->nranks;
@@ -980,14 +1029,14 @@ extern "C" int wf_halo_info(wf_engine *E, int *rank, int *nranks, int *n_neigh, 
   return 0;
 }
 
-extern "C" int wf_halo_comm_block(wf_engine *E, void **base, size_t *bytes) {
+extern "C" int wf_halo_comm_block(wf_engine *E, void **base, size_t *bytes) { WF_NULLCHK(E);
   NEED(E->distributed, "not a partitioned engine");
   if (base) *base = E->comm;
   if (bytes) *bytes = E->comm_bytes;
   return 0;
 }
 
-extern "C" int wf_halo_slot_offsets(wf_engine *E, int i, size_t *flag_off, size_t *region_off, size_t *region_bytes) {
+extern "C" int wf_halo_slot_offsets(wf_engine *E, int i, size_t *flag_off, size_t *region_off, size_t *region_bytes) { WF_NULLCHK(E);
   NEED(E->distributed, "not a partitioned engine");
   NEED(i >= 0 && i < (int)E->neigh.size(), "bad neighbour index");
   if (flag_off) *flag_off = 8 * (size_t)i;
@@ -1003,7 +1052,7 @@ static int push_nb(wf_engine *E) {
   return 0;
 }
 
-extern "C" int wf_halo_connect(wf_engine *E, int i, void *peer_base, size_t flag_off, size_t region_off) {
+extern "C" int wf_halo_connect(wf_engine *E, int i, void *peer_base, size_t flag_off, size_t region_off) { WF_NULLCHK(E);
   NEED(E->distributed, "not a partitioned engine");
   NEED(E->transport == 0, "wf_halo_connect belongs to the peer-memory transport");
   NEED(i >= 0 && i < (int)E->neigh.size(), "bad neighbour index");
@@ -1014,7 +1063,7 @@ extern "C" int wf_halo_connect(wf_engine *E, int i, void *peer_base, size_t flag
   return push_nb(E);
 }
 
-extern "C" int wf_halo_set_transport(wf_engine *E, int host_driven) {
+extern "C" int wf_halo_set_transport(wf_engine *E, int host_driven) { WF_NULLCHK(E);
   NEED(E->distributed, "not a partitioned engine");
   NEED(!E->inited, "choose the halo transport before wf_init");
   E->transport = host_driven ? 1 : 0;
@@ -1032,7 +1081,7 @@ extern "C" int wf_halo_set_transport(wf_engine *E, int host_driven) {
 }
 
 // host-driven transport: what to send to / receive from neighbour i for the exchange just packed
-extern "C" int wf_halo_exchange_ptrs(wf_engine *E, int i, void **send_ptr, void **recv_ptr, size_t *n_doubles) {
+extern "C" int wf_halo_exchange_ptrs(wf_engine *E, int i, void **send_ptr, void **recv_ptr, size_t *n_doubles) { WF_NULLCHK(E);
   NEED(E->distributed && E->transport == 1, "host-driven halo transport is not selected");
   NEED(i >= 0 && i < (int)E->neigh.size(), "bad neighbour index");
   const size_t cnt = (size_t)(E->halo_offset[i + 1] - E->halo_offset[i]);
@@ -1043,7 +1092,7 @@ extern "C" int wf_halo_exchange_ptrs(wf_engine *E, int i, void **send_ptr, void 
   return 0;
 }
 
-extern "C" int wf_halo_ipc_export(wf_engine *E, void *handle64) {
+extern "C" int wf_halo_ipc_export(wf_engine *E, void *handle64) { WF_NULLCHK(E);
   NEED(E->distributed && E->comm, "not a partitioned engine");
   static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
   CK(cudaSetDevice(E->device));
@@ -1053,7 +1102,7 @@ extern "C" int wf_halo_ipc_export(wf_engine *E, void *handle64) {
   return 0;
 }
 
-extern "C" int wf_halo_ipc_open(wf_engine *E, const void *handle64, void **mapped) {
+extern "C" int wf_halo_ipc_open(wf_engine *E, const void *handle64, void **mapped) { WF_NULLCHK(E);
   NEED(handle64 && mapped, "null argument");
   CK(cudaSetDevice(E->device));
   cudaIpcMemHandle_t h;
@@ -1065,7 +1114,7 @@ extern "C" int wf_halo_ipc_open(wf_engine *E, const void *handle64, void **mappe
   return 0;
 }
 
-extern "C" int wf_halo_status(wf_engine *E, int *error) {
+extern "C" int wf_halo_status(wf_engine *E, int *error) { WF_NULLCHK(E);
   int e = 0;
   if (E->distributed) {
     CK(cudaSetDevice(E->device));
@@ -1134,17 +1183,17 @@ extern "C" int wf_step_all(wf_engine **R, int n, int nsteps) {
   return 0;
 }
 
-extern "C" int wf_nonfinite_flag(wf_engine *E, int *flag) {
+extern "C" int wf_nonfinite_flag(wf_engine *E, int *flag) { WF_NULLCHK(E);
   CK(cudaSetDevice(E->device));
   int f = 0;
   CK(cudaMemcpyAsync(&f, E->d.nonfinite, sizeof(int), cudaMemcpyDeviceToHost, E->stream));
   CK(cudaStreamSynchronize(E->stream));
   if (f) CK(cudaMemsetAsync(E->d.nonfinite, 0, sizeof(int), E->stream));
   if (flag) *flag = f;
-  return 0;
+  return check_halo_error(E);
 }
 
-extern "C" int wf_set_time(wf_engine *E, double t, long steps) {
+extern "C" int wf_set_time(wf_engine *E, double t, long steps) { WF_NULLCHK(E);
   NEED(E->inited, "wf_set_time after wf_init");
   NEED(!E->predicted, "engine is mid-batch");
   NEED(t >= 0.0 && steps >= 0, "negative time or step count");
@@ -1153,7 +1202,7 @@ extern "C" int wf_set_time(wf_engine *E, double t, long steps) {
   return 0;
 }
 
-extern "C" int wf_get_time(wf_engine *E, double *t, long *steps) {
+extern "C" int wf_get_time(wf_engine *E, double *t, long *steps) { WF_NULLCHK(E);
   if (t) *t = E->time;
   if (steps) *steps = E->step_count;
   return 0;
@@ -1171,29 +1220,29 @@ extern "C" int wf_get_time(wf_engine *E, double *t, long *steps) {
   if (ensure_dbg(E)) return 1;                                    \
   WfDev &d = E->d; WfPar &P = E->P; (void)d; (void)P;
 
-extern "C" int wf_UpdatePrediction(wf_engine *E) { UNFUSED_PROLOGUE(); E->L->predict(d, P, 0, E->stream); return check_launch(E, __func__); }
-extern "C" int wf_ImposeBCV(wf_engine *E, int dd) { UNFUSED_PROLOGUE(); NEED(dd >= 0 && dd < E->dim, "bad dim"); E->L->impose_bc(d, dd, 0, d.v, E->stream); return check_launch(E, __func__); }
-extern "C" int wf_ImposeBCA(wf_engine *E, int dd) { UNFUSED_PROLOGUE(); NEED(dd >= 0 && dd < E->dim, "bad dim"); E->L->impose_bc(d, dd, 1, d.a, E->stream); return check_launch(E, __func__); }
-extern "C" int wf_calcElemJAndDerivatives(wf_engine *E) { UNFUSED_PROLOGUE(); E->L->elem_vol(d, P, E->et, 1, E->stream); return check_launch(E, __func__); }
-extern "C" int wf_Calc_Element_Radius(wf_engine *E) { UNFUSED_PROLOGUE(); E->L->elem_vol(d, P, E->et, 2, E->stream); return check_launch(E, __func__); }
-extern "C" int wf_CalcElemVol(wf_engine *E) { UNFUSED_PROLOGUE(); E->L->vol_from_detj(d, E->et, E->stream); return check_launch(E, __func__); }
-extern "C" int wf_CalcNodalVol(wf_engine *E) { UNFUSED_PROLOGUE(); E->L->u_nodal_vol(d, E->stream); return check_launch(E, __func__); }
-extern "C" int wf_CalcNodalMassFromVol(wf_engine *E) { UNFUSED_PROLOGUE(); E->L->node_mass(d, P, 1, E->stream); return check_launch(E, __func__); }
-extern "C" int wf_calcElemStrainRates(wf_engine *E) { UNFUSED_PROLOGUE(); E->L->u_strain_rates(d, P, E->et, E->stream); E->rates_in_dbg = true; return check_launch(E, __func__); }
-extern "C" int wf_calcElemPressure(wf_engine *E) {
+extern "C" int wf_UpdatePrediction(wf_engine *E) { WF_NULLCHK(E); UNFUSED_PROLOGUE(); E->L->predict(d, P, 0, E->stream); return check_launch(E, __func__); }
+extern "C" int wf_ImposeBCV(wf_engine *E, int dd) { WF_NULLCHK(E); UNFUSED_PROLOGUE(); NEED(dd >= 0 && dd < E->dim, "bad dim"); E->L->impose_bc(d, dd, 0, d.v, E->stream); return check_launch(E, __func__); }
+extern "C" int wf_ImposeBCA(wf_engine *E, int dd) { WF_NULLCHK(E); UNFUSED_PROLOGUE(); NEED(dd >= 0 && dd < E->dim, "bad dim"); E->L->impose_bc(d, dd, 1, d.a, E->stream); return check_launch(E, __func__); }
+extern "C" int wf_calcElemJAndDerivatives(wf_engine *E) { WF_NULLCHK(E); UNFUSED_PROLOGUE(); E->L->elem_vol(d, P, E->et, 1, E->stream); return check_launch(E, __func__); }
+extern "C" int wf_Calc_Element_Radius(wf_engine *E) { WF_NULLCHK(E); UNFUSED_PROLOGUE(); E->L->elem_vol(d, P, E->et, 2, E->stream); return check_launch(E, __func__); }
+extern "C" int wf_CalcElemVol(wf_engine *E) { WF_NULLCHK(E); UNFUSED_PROLOGUE(); E->L->vol_from_detj(d, E->et, E->stream); return check_launch(E, __func__); }
+extern "C" int wf_CalcNodalVol(wf_engine *E) { WF_NULLCHK(E); UNFUSED_PROLOGUE(); E->L->u_nodal_vol(d, E->stream); return check_launch(E, __func__); }
+extern "C" int wf_CalcNodalMassFromVol(wf_engine *E) { WF_NULLCHK(E); UNFUSED_PROLOGUE(); E->L->node_mass(d, P, 1, E->stream); return check_launch(E, __func__); }
+extern "C" int wf_calcElemStrainRates(wf_engine *E) { WF_NULLCHK(E); UNFUSED_PROLOGUE(); E->L->u_strain_rates(d, P, E->et, E->stream); E->rates_in_dbg = true; return check_launch(E, __func__); }
+extern "C" int wf_calcElemPressure(wf_engine *E) { WF_NULLCHK(E);
   UNFUSED_PROLOGUE();
   E->L->node_vol(d, P, 1, E->stream);
   E->L->u_pressure(d, P, E->et, E->stream);
   return check_launch(E, __func__);
 }
-extern "C" int wf_CalcStressStrain(wf_engine *E, double dt) { UNFUSED_PROLOGUE(); E->L->u_stress(d, P, dt, E->stream); E->sigma_in_dbg = true; return check_launch(E, __func__); }
-extern "C" int wf_calcArtificialViscosity(wf_engine *E) { UNFUSED_PROLOGUE(); E->L->u_artvisc(d, P, E->stream); return check_launch(E, __func__); }
-extern "C" int wf_calcElemForces(wf_engine *E) { UNFUSED_PROLOGUE(); E->L->u_forces(d, P, E->et, E->stream); E->felem_in_dbg = true; return check_launch(E, __func__); }
-extern "C" int wf_calcElemHourglassForces(wf_engine *E) { UNFUSED_PROLOGUE(); E->L->u_hourglass(d, P, E->et, E->stream); return check_launch(E, __func__); }
-extern "C" int wf_assemblyForces(wf_engine *E) { UNFUSED_PROLOGUE(); E->L->u_assembly(d, E->stream); E->fi_in_dbg = true; return check_launch(E, __func__); }
-extern "C" int wf_calcAccel(wf_engine *E) { UNFUSED_PROLOGUE(); E->L->u_accel(d, E->stream); E->a_in_dbg = true; return check_launch(E, __func__); }
-extern "C" int wf_UpdateCorrectionAccVel(wf_engine *E) { UNFUSED_PROLOGUE(); E->L->u_corr_accvel(d, P, E->stream); return check_launch(E, __func__); }
-extern "C" int wf_AxisConstraint(wf_engine *E) {
+extern "C" int wf_CalcStressStrain(wf_engine *E, double dt) { WF_NULLCHK(E); UNFUSED_PROLOGUE(); E->L->u_stress(d, P, dt, E->stream); E->sigma_in_dbg = true; return check_launch(E, __func__); }
+extern "C" int wf_calcArtificialViscosity(wf_engine *E) { WF_NULLCHK(E); UNFUSED_PROLOGUE(); E->L->u_artvisc(d, P, E->stream); return check_launch(E, __func__); }
+extern "C" int wf_calcElemForces(wf_engine *E) { WF_NULLCHK(E); UNFUSED_PROLOGUE(); E->L->u_forces(d, P, E->et, E->stream); E->felem_in_dbg = true; return check_launch(E, __func__); }
+extern "C" int wf_calcElemHourglassForces(wf_engine *E) { WF_NULLCHK(E); UNFUSED_PROLOGUE(); E->L->u_hourglass(d, P, E->et, E->stream); return check_launch(E, __func__); }
+extern "C" int wf_assemblyForces(wf_engine *E) { WF_NULLCHK(E); UNFUSED_PROLOGUE(); E->L->u_assembly(d, E->stream); E->fi_in_dbg = true; return check_launch(E, __func__); }
+extern "C" int wf_calcAccel(wf_engine *E) { WF_NULLCHK(E); UNFUSED_PROLOGUE(); E->L->u_accel(d, E->stream); E->a_in_dbg = true; return check_launch(E, __func__); }
+extern "C" int wf_UpdateCorrectionAccVel(wf_engine *E) { WF_NULLCHK(E); UNFUSED_PROLOGUE(); E->L->u_corr_accvel(d, P, E->stream); return check_launch(E, __func__); }
+extern "C" int wf_AxisConstraint(wf_engine *E) { WF_NULLCHK(E);
   UNFUSED_PROLOGUE();
   if (E->domtype != WF_AXISYMM) return 0;
   if (reset_xmin(E, P.xmin_cur)) return 1;
@@ -1201,7 +1250,7 @@ extern "C" int wf_AxisConstraint(wf_engine *E) {
   E->L->u_axis(d, P, E->stream);
   return check_launch(E, __func__);
 }
-extern "C" int wf_UpdateCorrectionPos(wf_engine *E) {
+extern "C" int wf_UpdateCorrectionPos(wf_engine *E) { WF_NULLCHK(E);
   UNFUSED_PROLOGUE();
   E->L->u_corr_pos(d, P, E->stream);
   E->time += P.dt; E->step_count++;
@@ -1322,11 +1371,12 @@ static int download(wf_engine *E, const double *dev, size_t count, std::vector<d
   return 0;
 }
 
-extern "C" int wf_get_array(wf_engine *E, const char *name, void *dst, size_t bytes) {
+extern "C" int wf_get_array(wf_engine *E, const char *name, void *dst, size_t bytes) { WF_NULLCHK(E);
   NEED(E->meshed, "no mesh");
   NEED(name && dst, "null argument");
   NEED(!E->predicted, "engine is mid-batch");
   CK(cudaSetDevice(E->device));
+  if (check_halo_error(E)) return 1;
   ArrayRef r;
   if (!lookup(E, name, r, false))
     FAIL(std::string("array '") + name + "' is unknown or only produced by the unfused entry points / tracking options");
@@ -1439,7 +1489,7 @@ extern "C" int wf_get_array(wf_engine *E, const char *name, void *dst, size_t by
   return 0;
 }
 
-extern "C" int wf_set_array(wf_engine *E, const char *name, const void *src, size_t bytes) {
+extern "C" int wf_set_array(wf_engine *E, const char *name, const void *src, size_t bytes) { WF_NULLCHK(E);
   NEED(E->meshed, "no mesh");
   NEED(name && src, "null argument");
   NEED(!E->predicted, "engine is mid-batch");
@@ -1536,7 +1586,7 @@ static int diag_reduce(wf_engine *E, bool edges, bool vel, double out[3]) {
 }
 
 // Domain_d::calcMinEdgeLength (Domain_d.C:2224-2468): m_min_length, m_min_height, m_elem_length
-extern "C" int wf_calcMinEdgeLength(wf_engine *E, double *min_length, double *min_height) {
+extern "C" int wf_calcMinEdgeLength(wf_engine *E, double *min_length, double *min_height) { WF_NULLCHK(E);
   NEED(E->meshed, "no mesh");
   NEED(!E->predicted, "engine is mid-batch");
   NEED(E->dim == 3 || E->k == 4, "calcMinEdgeLength reads four nodes per element (Domain_d.C:2381-2384): not defined for triangles");
@@ -1549,7 +1599,7 @@ extern "C" int wf_calcMinEdgeLength(wf_engine *E, double *min_length, double *mi
 }
 
 // max |v| over the nodes (Solver_explicit.C:583-587)
-extern "C" int wf_max_velocity(wf_engine *E, double *vmax) {
+extern "C" int wf_max_velocity(wf_engine *E, double *vmax) { WF_NULLCHK(E);
   NEED(E->meshed, "no mesh");
   NEED(!E->predicted, "engine is mid-batch");
   double o[3];
@@ -1560,7 +1610,7 @@ extern "C" int wf_max_velocity(wf_engine *E, double *vmax) {
 
 // variable time step of the explicit loop (Solver_explicit.C:579-598): dt = cfl * min_length / (cs + max|v|),
 // cs = sqrt(K / rho[0])
-extern "C" int wf_cfl_dt(wf_engine *E, double cfl_factor, double *dt) {
+extern "C" int wf_cfl_dt(wf_engine *E, double cfl_factor, double *dt) { WF_NULLCHK(E);
   NEED(E->meshed && E->material_set, "wf_cfl_dt needs mesh and material");
   NEED(!E->predicted, "engine is mid-batch");
   NEED(E->dim == 3 || E->k == 4, "calcMinEdgeLength is not defined for triangles");
@@ -1576,7 +1626,7 @@ extern "C" int wf_cfl_dt(wf_engine *E, double cfl_factor, double *dt) {
 }
 
 // change the step size between batches (variable-dt loop); takes effect at the next wf_step
-extern "C" int wf_set_dt(wf_engine *E, double dt) {
+extern "C" int wf_set_dt(wf_engine *E, double dt) { WF_NULLCHK(E);
   NEED(E->inited, "wf_set_dt after wf_init");
   NEED(!E->predicted, "engine is mid-batch");
   NEED(dt > 0.0, "dt must be positive");
@@ -1586,7 +1636,7 @@ extern "C" int wf_set_dt(wf_engine *E, double dt) {
 
 // computeEnergies (Mechanical.C:2145-2185).  Ekin from the current velocities and the nodal mass of the last
 // step; dEint needs the strain rates of the last step, which only the unfused path keeps.
-extern "C" int wf_energies(wf_engine *E, double *Ekin, double *dEint) {
+extern "C" int wf_energies(wf_engine *E, double *Ekin, double *dEint) { WF_NULLCHK(E);
   NEED(E->inited, "wf_energies before wf_init");
   NEED(!E->predicted, "engine is mid-batch");
   CK(cudaSetDevice(E->device));

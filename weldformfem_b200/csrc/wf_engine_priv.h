@@ -103,6 +103,8 @@ int wf_contact_refresh_nodlen(wf_engine *E);
 int wf_contact_after_set(wf_engine *E, const std::string &nm);
 bool wf_contact_lookup(wf_engine *E, const std::string &nm, void **dev, size_t *bytes, int *kind);
 
+int wf_null_engine(void); // records "null engine handle" for wf_last_error(NULL), returns 1
+#define WF_NULLCHK(E) do { if (!(E)) return wf_null_engine(); } while (0)
 #define CK(call)                                                                          \
   do {                                                                                    \
     cudaError_t _e = (call);                                                              \

@@ -13,11 +13,11 @@
 //     and the 24 nodal force components come out of one inverse butterfly per component.
 // Kernels in this file, all one element per thread, 128 threads per CTA:
 //   k_elem_main_hex_brick  DEFAULT on meshes whose CTA / tile node lists fit its compile-time pitches (every structured
-//                          mesh in the engine's Morton element order: 128 elements = 8x4x4 brick, <= 288 unique nodes;
-//                          32 elements = 4x4x2 brick, <= 104).  Same data flow as k_elem_main_hex_tile with
-//                          shared-memory strides known at compile time (no address arithmetic per access), the 16-bit
-//                          / 8-bit local indices of an element fetched with one 16 B and one 8 B load, and only the
-//                          tile's actual number of partial sums written.
+//                          mesh in the engine's element order: 128 elements = 8x4x4 brick, 32 = 4x4x2).  Same data
+//                          flow as k_elem_main_hex_tile with shared-memory pitches known at compile time (no address
+//                          arithmetic per access), node copies and accumulators at bank-aware slots
+//                          (wf_host_run_slots: every 64-bit access of a half-warp is conflict-free on a structured mesh),
+//                          and the slots of an element's eight nodes fetched with one 16 B and one 8 B load.
 //   k_elem_main_hex_tile   same with run-time pitches (any mesh whose force tiles are conflict-free).  The CTA stages x,
 //                          v and the nodal ratio of its UNIQUE nodes once (cp.async through the fixed-pitch node list
 //                          WfDev::blk_pad); nodal forces are summed per warp tile in shared memory and one partial per
@@ -450,7 +450,7 @@ __global__ void __launch_bounds__(TPB, MINB) k_elem_main_hex_brick(WfDev d, WfPa
   const int e = active ? e0 : d.ne - 1;
   const unsigned amask = __ballot_sync(0xffffffffu, active);
   constexpr int NQ = (STRIDE + TPB - 1) / TPB;
-  const int *__restrict__ ids = d.blk_pad + (long long)b * STRIDE;
+  const int *__restrict__ ids = d.blk_pad_b + (long long)b * STRIDE;
   int gid[NQ];
 #pragma unroll
   for (int q = 0; q < NQ; q++) {
@@ -498,16 +498,17 @@ __global__ void __launch_bounds__(TPB, MINB) k_elem_main_hex_brick(WfDev d, WfPa
   EmitTileC<WS> emit{acc, rpk, amask};
   hex_back(d, P, e, active, g, tau, pl, rho_e, sy, J_sum, p_prev, emit);
   __syncwarp();
-  // number of unique nodes of this tile = largest tile-local index + 1 (inactive lanes shadow the last element)
-  unsigned m = max(max(emit.idx(0), emit.idx(1)), max(emit.idx(2), emit.idx(3)));
-  m = max(m, max(max(emit.idx(4), emit.idx(5)), max(emit.idx(6), emit.idx(7))));
-  const int cnt = (int)__reduce_max_sync(0xffffffffu, m) + 1;
+  // one partial per unique node of the tile, in rank order (the accumulators sit at bank-aware slots: tf_r2s)
   const long long tile = (long long)b * (TPB / 32) + warp;
   if (tile * 32 < d.ne) {
+    const unsigned char *__restrict__ r2s = d.tf_r2s + tile * d.tf_r2s_pitch;
+    const int cnt = __ldg(r2s);
     double *__restrict__ out = d.ftile + tile * 3 * d.tf_stride;
+    for (int r = lane; r < cnt; r += 32) {
+      const int sl = __ldg(r2s + 1 + r);
 #pragma unroll
-    for (int c = 0; c < 3; c++)
-      for (int i = lane; i < cnt; i += 32) out[c * d.tf_stride + i] = acc[c * WS + i];
+      for (int c = 0; c < 3; c++) out[c * d.tf_stride + r] = acc[c * WS + sl];
+    }
   }
 }
 

@@ -129,6 +129,8 @@ extern "C" int wf_host_nodel(int n_nodes, int n_elems, int k, const unsigned *el
 //   h = pow(prod ext_c / cells, 1/na); n_c = max(1, (int)(ext_c / h + 0.5));
 //   q_c = min(n_c - 1, (int)((centroid_c - lo_c) / ext_c * n_c)), centroid = (sum of the k node coordinates) / k;
 //   key = bit-interleave(q_0, q_1[, q_2]) with q_0 in the lowest bit; order = ascending (key, user id).
+//   Hexahedra: key = (bit-interleave(q_2 >> 1, q_0 >> 2, q_1 >> 2) << 5) | (q_2 & 1) << 4 | (q_1 & 3) << 2 | (q_0 & 3):
+//   the same bricks, with the 32 elements of a tile ordered layer by layer.
 // mode 0 = identity.  perm[internal] = user.
 static inline uint64_t spread_bits(uint32_t v, int ndim) {
   uint64_t r = 0;
@@ -183,13 +185,43 @@ extern "C" int wf_host_elem_order(int dim, int k, int n_nodes, int n_elems, cons
       if (qi > ncell[c] - 1) qi = ncell[c] - 1;
       q[c] = (uint32_t)qi;
     }
-    uint64_t key = spread_bits(q[0], dim) | (spread_bits(q[1], dim) << 1);
-    if (dim == 3) key |= spread_bits(q[2], dim) << 2;
+    uint64_t key;
+    if (k == 8 && dim == 3) {
+      // hexahedra: Morton order of the 4x4x2 tiles (z lowest, then x, y: 128 consecutive elements = 8x4x4), and inside
+      // a tile z-layer, then y, then x: lanes 0-15 / 16-31 of a warp are the two 4x4 layers (see wf_host_run_slots)
+      const uint32_t tx = q[0] >> 2, ty = q[1] >> 2, tz = q[2] >> 1;
+      const uint64_t tkey = spread_bits(tz, 3) | (spread_bits(tx, 3) << 1) | (spread_bits(ty, 3) << 2);
+      key = (tkey << 5) | ((q[2] & 1u) << 4) | ((q[1] & 3u) << 2) | (q[0] & 3u);
+    } else {
+      key = spread_bits(q[0], dim) | (spread_bits(q[1], dim) << 1);
+      if (dim == 3) key |= spread_bits(q[2], dim) << 2;
+    }
     keys[(size_t)e] = std::make_pair(key, e);
   }
   std::sort(keys.begin(), keys.end());
   for (int e = 0; e < n_elems; e++) perm[e] = keys[(size_t)e].second;
   return 0;
+}
+
+// ---- bank-aware shared-memory slots of the brick kernel (k_elem_main_hex_brick) -----------------------------------
+// A 64-bit shared-memory access of a warp is served per half-warp: 16 lanes are conflict-free when their 8-byte words
+// fall into 16 different bank pairs (word index mod 16).  In the engine's element order a half-warp is a 4x4 layer of
+// a tile, and corner c of those 16 elements are the nodes (x + dx, y + dy) of one node layer, so word index
+// x + P*y is conflict-free for every corner iff P = 4 or 12 (mod 16).  The node lists of a CTA / tile are ascending
+// node ids = runs of consecutive ids (one run per mesh row: 9 or 5 nodes); placing run r at the first free slot
+// congruent to 12 r (mod 16) gives exactly that lattice with P = 12 on a structured mesh, and some valid layout on
+// any other (only the conflict count depends on it).  Returns the number of slots used.
+extern "C" int wf_host_run_slots(int n, const int *sorted_ids, int *slots) {
+  int cur = 0, r = 0;
+  for (int a = 0; a < n;) {
+    int b = a;
+    while (b + 1 < n && sorted_ids[b + 1] == sorted_ids[b] + 1) b++;
+    while ((cur & 15) != ((12 * r) & 15)) cur++;
+    for (int q = a; q <= b; q++) slots[q] = cur++;
+    r++;
+    a = b + 1;
+  }
+  return cur;
 }
 
 // ---- force tiles of the tile-reduced force path (WfDev::ftile) ------------------------------------------------
@@ -334,7 +366,7 @@ static void build_partition(wf_partition *pt, long long n_nodes, long long n_ele
   // Only elements of q can reference a node; scan q's block and keep hits (ascending, unique).
   pt->neigh.clear(); pt->halo_offset.assign(1, 0); pt->halo_nodes.clear();
   (void)n_nodes;
-  for (int q = 0; q < P; q++) {
+  for (int q = 0; q < P && !l2g.empty(); q++) { // a rank that owns no elements has no shared nodes
     if (q == pt->rank) continue;
     const long long qb = block_begin(n_elems, P, q), qe = block_begin(n_elems, P, q + 1);
     std::vector<int> hits;

@@ -21,7 +21,9 @@ import numpy as np
 
 BILINEAR, HOLLOMON, JOHNSON_COOK, GMT = 0, 1, 2, 3
 STAB_KEYS = ("alpha_free", "alpha_contact", "hg_coeff_free", "hg_coeff_contact", "av_coeff_div", "av_coeff_bulk",
-             "log_factor", "p_pspg_bulkfac", "J_min", "hg_visc", "hg_stiff")
+             "log_factor", "p_pspg_bulkfac", "J_min", "hg_visc", "hg_stiff", "pspg_scale")
+# "pspg_scale": main.C's loadStabilizationParams never assigns it, so the reference hands an INDETERMINATE value to
+# calcElemPressure (Mechanical.C:796); deliberate deviation: 0 unless the deck carries the key
 
 
 def read_k(path, scale=1.0):
@@ -205,7 +207,12 @@ def load(path) -> DeckSetup:
     S.vol_weight = bool(cfg.get("AxiSymmVol", False))
     S.sym = (bool(cfg.get("xSymm", False)), bool(cfg.get("ySymm", False)), bool(cfg.get("zSymm", False)))
     S.symtol = float(cfg.get("symtol", 1.0e-4))
-    S.press = 1 if int(cfg.get("pressAlgorithm", 0)) > 0 else 0
+    # Solver_explicit.C:733-743 dispatches on 0 and 1 only (any other value would skip the pressure update altogether)
+    if int(cfg.get("pressAlgorithm", 0)) not in (0, 1):
+        raise ValueError("pressAlgorithm must be 0 or 1")
+    if cfg.get("devElastic", True) is False:
+        raise ValueError("devElastic = false (calcElemPressureRigid) is not supported")
+    S.press = int(cfg.get("pressAlgorithm", 0))
     blk = blocks[0]
     kind = blk.get("type", "Box")
     if kind == "File":
