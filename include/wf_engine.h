@@ -134,6 +134,14 @@ int wf_get_trimesh_counts(wf_engine *, int *dimension, int *n_nodes, int *n_elem
 /* ---- solve --------------------------------------------------------------------------------------- */
 int wf_init(wf_engine *, double dt);  /* Solver_explicit.C:115-292 incl. SetDT; CH constants rho_b = 0.8182 */
 int wf_step(wf_engine *, int nsteps); /* fused rows 1-22 of the step, Solver_explicit.C:524-978 */
+/* wf_step for a host loop that exchanges data with the engine EVERY step (the reference's loop rewrites bcx_val / reads
+ * energies per step, Solver_explicit.C:524-1170): same steps, but the engine is left in predicted state — the next
+ * step's UpdatePrediction + ImposeBCV (Solver_explicit.C:524-540) have already run inside the last node pass — so
+ * single-step calls keep the fused schedule of a batch.  In that state only wf_set_bc_values (patches the predicted
+ * velocities of the prescribed components), wf_monitor_async / wf_monitor_wait, wf_step, wf_step_open and
+ * wf_step_close may be called.  wf_step_close undoes the prediction so that every array can be read; fast flavour. */
+int wf_step_open(wf_engine *, int nsteps);
+int wf_step_close(wf_engine *);
 /* set after a step that scrubbed a non-finite internal force (Solver_explicit.C:779-784); clears the flag */
 int wf_nonfinite_flag(wf_engine *, int *flag);
 int wf_energies(wf_engine *, double *Ekin, double *dEint); /* computeEnergies, Mechanical.C:2145 */

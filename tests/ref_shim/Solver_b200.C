@@ -32,10 +32,13 @@ class Domain_b200 : public Domain_d {
 
   // call once after the deck has been read: mesh, material, BCs and options are already in *this
   void AttachB200(int device) {
-    ck(nullptr, wf_create(&eng, m_dim, m_nodxelem, (int)m_domtype, device));       // dom_type, Domain_d.h:101
+    // dom_type (Domain_d.h:101).  main.C leaves m_domtype at its 3D default for a "plStrain" deck (main.C:325-327 only
+    // prints), and the reference's 2D kernels never read it: a 2D domain that is not axisymmetric is plane strain.
+    const int domtype = (m_dim == 2 && m_domtype != _Axi_Symm_) ? WF_PLANE_STRAIN : (int)m_domtype;
+    ck(nullptr, wf_create(&eng, m_dim, m_nodxelem, domtype, device));
     ck(eng, wf_set_mesh(eng, m_node_count, m_elem_count, x, m_elnod));             // rebuilds nodel* like setNodElem
     if (m_domtype == _Axi_Symm_) ck(eng, wf_set_axisymm_vol_weight(eng, m_axisymm_vol_weight ? 1 : 0));
-    const Material_ *mt = mat[0];                                                  // AssignMaterial, Domain_d.C:903
+    const Material_ *mt = &materials[0];   // AssignMaterial (Domain_d.C:903); mat[e] is only wired by SolveChungHulbert
     wf_material wm = {};
     wm.model = mt->Material_model == HOLLOMON ? WF_HOLLOMON : WF_BILINEAR;         // Material.cuh:9-13
     wm.E = mt->Elastic().E(); wm.nu = mt->Elastic().Poisson();

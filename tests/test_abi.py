@@ -63,6 +63,21 @@ def test_product_never_imports_oracle():
                 assert "import oracle" not in txt and "from oracle" not in txt and "wf_oracle" not in txt, f
 
 
+def test_null_engine_handle_is_an_error_not_a_crash():
+    """Domain_d.set_material / set_stab before the mesh passed NULL to the C ABI, which dereferenced it."""
+    from weldformfem_b200 import _lib
+    from weldformfem_b200.domain import Domain_d, WfError
+    lib = _lib.load()
+    mat = _lib.wf_material()
+    assert lib.wf_set_material(None, C.byref(mat)) != 0
+    assert b"null engine handle" in lib.wf_last_error(None)
+    assert lib.wf_step(None, 1) != 0 and lib.wf_get_array(None, b"x", None, 0) != 0 and lib.wf_SearchExtNodes(None) != 0
+    with pytest.raises(WfError, match="null engine handle"):
+        Domain_d().set_material(1e9, 0.3, 1000.0)
+    with pytest.raises(WfError, match="null engine handle"):
+        Domain_d().set_stab(hg_visc=0.1)
+
+
 def test_bad_arguments():
     from weldformfem_b200 import _lib
     lib = _lib.load()

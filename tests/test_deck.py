@@ -89,6 +89,29 @@ def test_deck_errors_are_loud(host_bins, tmp_path):
     assert r.returncode == 1 and r.stderr.strip()
 
 
+def test_deck_options_the_engine_does_not_implement_are_refused(host_bins, tmp_path):
+    """pressAlgorithm outside {0, 1} (the reference would silently skip the pressure update,
+    Solver_explicit.C:733-743) and devElastic = false (calcElemPressureRigid) must not run a different algorithm
+    silently — both front-ends refuse them; an explicit "pspg_scale" key is honoured (main.C leaves it indeterminate)."""
+    from weldformfem_b200 import deck
+    base = json.load(open(os.path.join(DECKS, "box_psquad.json")))
+    for key, val, msg in (("pressAlgorithm", 2, "pressAlgorithm"), ("devElastic", False, "devElastic")):
+        j = json.loads(json.dumps(base))
+        j["Configuration"][key] = val
+        path = tmp_path / f"bad_{key}.json"
+        path.write_text(json.dumps(j))
+        r = subprocess.run([os.path.join(host_bins, "wf_weldform"), str(path), "--parse-only"], capture_output=True, text=True)
+        assert r.returncode == 1 and msg in r.stderr, r.stderr
+        with pytest.raises(ValueError, match=msg):
+            deck.load(str(path))
+    j = json.loads(json.dumps(base))
+    j["Stabilization"] = {"hg_visc": 0.1, "hg_stiff": 0.1, "pspg_scale": 0.25}
+    path = tmp_path / "pspg.json"
+    path.write_text(json.dumps(j))
+    assert deck.load(str(path)).stab["pspg_scale"] == 0.25
+    assert deck.load(os.path.join(DECKS, "box_axiquad.json")).stab["pspg_scale"] == 0.0
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("name", PINNED)
 def test_deck_run_matches_reference_front_end(host_bins, tmp_path, name):

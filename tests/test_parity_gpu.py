@@ -375,3 +375,43 @@ def test_elem_order_is_invisible(key, strict, oracle_port):
     assert np.array_equal(engs[1].get("pl_strain"), pl)
     for e in engs:
         e.close()
+
+
+@pytest.mark.parametrize("key", ["hex", "tet", "psquad"])
+def test_open_stepping_with_per_step_bc_values_and_monitor(key, oracle_port):
+    """wf_step_open: a host loop that talks to the engine every step (new prescribed velocities in, kinetic energy out)
+    keeps the fused schedule — the call's last node pass already runs the next predictor.  Prescribed values change
+    between calls: their u_dt must use the OLD value, their velocity the NEW one (UpdatePrediction then ImposeBCV,
+    Solver_explicit.C:524-540).  Compared with the oracle stepping one step at a time with the same values."""
+    case = SMALL[key]
+    eng, ref = run_pair(case, oracle_port, 3, False)
+    _, dims, vals = case.bc_arrays()
+    d = case.dim - 1
+    name = "bcz_val" if d == 2 else "bcy_val"
+    vd = vals[dims == d]
+    ek_ref = []
+    for i in range(8):
+        newv = vd * (1.0 + 0.15 * np.sin(1.0 + i))
+        eng.set_bc_values(d, newv)
+        ref.set(name, newv)
+        eng.step_open(1)
+        ref.step(1)
+        eng.monitor_async()
+        ek_ref.append(ref.energies()[0])
+        if i >= 1:
+            ek, bad = eng.monitor_wait()
+            assert not bad and abs(ek - ek_ref[i - 1]) <= 1e-9 * abs(ek_ref[i - 1])
+    ek, bad = eng.monitor_wait()
+    assert not bad and abs(ek - ek_ref[-1]) <= 1e-9 * abs(ek_ref[-1])
+    with pytest.raises(Exception, match="mid-batch"):
+        eng.get("v")
+    eng.step_close()
+    compare(eng, ref, [n for n in STATE], 1e-9, f"{key} open stepping")
+    with pytest.raises(Exception):
+        eng.get("u_dt")                      # the fused schedule does not keep the last increment
+    # a plain step closes too, and u_dt is back
+    eng2, ref2 = run_pair(case, oracle_port, 2, False)
+    eng2.step_open(3)
+    eng2.step(1)
+    ref2.step(4)
+    compare(eng2, ref2, STATE + ["u_dt"], 1e-9, f"{key} open then closed")

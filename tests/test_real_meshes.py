@@ -86,8 +86,8 @@ def test_port_matches_compiled_reference_on_real_meshes(name, oracle_port, oracl
     x, el, dt = case_params(name)
     oracle_ref.set_threads(1)
     hg = 0.06 if name == "cyl_hex" else 0.0
-    a = setup(oracle_port(), x, el, hg, -300.0, dt)
-    b = setup(oracle_ref(), x, el, hg, -300.0, dt)
+    a = setup(oracle_port(), x, el, hg, -40.0, dt)
+    b = setup(oracle_ref(), x, el, hg, -40.0, dt)
     a.step(30)
     b.step(30)
     for nm in STATE + ["m_nodel", "m_nodel_loc", "m_nodel_offset", "m_nodel_count"]:
@@ -105,8 +105,8 @@ def test_cylinder_meshes_match_reference(name, press, strict, oracle_port, oracl
     checker = oracle_port if hexes else oracle_ref    # the hexa hourglass of the harness is not upstream code: use the pinned port
     if not hexes:
         oracle_ref.set_threads(0)
-    ref = setup(checker(), x, el, 0.06 if hexes else 0.0, -300.0, dt, press)
-    eng = setup(Domain_d(strict=strict), x, el, 0.06 if hexes else 0.0, -300.0, dt, press)
+    ref = setup(checker(), x, el, 0.06 if hexes else 0.0, -40.0, dt, press)
+    eng = setup(Domain_d(strict=strict), x, el, 0.06 if hexes else 0.0, -40.0, dt, press)
     for nm in ("m_elnod", "m_nodel", "m_nodel_loc", "m_nodel_offset", "m_nodel_count"):
         assert np.array_equal(eng.get(nm), ref.get(nm)), nm
     perm = eng.get("elem_perm")

@@ -85,11 +85,14 @@ def test_shim_b200_arm_matches_reference_cpu_solver(shim_bin, tmp_path, deck, st
     """main.C:995 swapped: the deck runs to simTime on the B200 engine through the shim and is compared with the
     reference's own CPU solver inside the same binary (tets with the shipped ANP pressure + Hollomon; plane-strain and
     axisymmetric quads with the shipped hourglass)."""
-    cpu = run_shim(shim_bin, deck, tmp_path, "cpu", cpu=True, steps=300)
-    gpu = run_shim(shim_bin, deck, tmp_path, "gpu", cpu=False, extra_env={"WF_SHIM_STRICT": "1"} if strict else None, steps=300)
+    # the tet deck runs the pressure law the reference ships as algorithm 1, which ACCUMULATES (Mechanical.C:1243-1247):
+    # the state grows exponentially and overflows within a few hundred steps on either side, so it is compared early
+    steps = 20 if deck == "file_tet_zones" else 300
+    cpu = run_shim(shim_bin, deck, tmp_path, "cpu", cpu=True, steps=steps)
+    gpu = run_shim(shim_bin, deck, tmp_path, "gpu", cpu=False, extra_env={"WF_SHIM_STRICT": "1"} if strict else None, steps=steps)
     assert gpu["time_dt"][1] == cpu["time_dt"][1]
     assert abs(gpu["time_dt"][0] - cpu["time_dt"][0]) < 1e-9 * cpu["time_dt"][0]
-    assert abs(cpu["time_dt"][0] / cpu["time_dt"][1] - 300) < 1e-6
+    assert abs(cpu["time_dt"][0] / cpu["time_dt"][1] - steps) < 1e-6
     assert (cpu["pl_strain"] > 0).mean() > 0.2, "the run should reach plasticity"
     worst = {nm: relerr(gpu[nm], cpu[nm]) for nm in ("x", "v", "u", "m_sigma", "m_tau", "pl_strain", "p", "sigma_y", "vol")}
     assert max(worst.values()) < (1e-9 if strict else 1e-7), worst

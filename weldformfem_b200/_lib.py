@@ -44,7 +44,7 @@ DECLARED = (["wf_create", "wf_destroy", "wf_last_error", "wf_set_stream", "wf_ge
              "wf_host_box_counts", "wf_host_gen_box", "wf_host_nodel", "wf_version",
              "wf_set_trimesh", "wf_set_contact", "wf_get_trimesh_counts", "wf_host_ext_faces",
              "wf_host_axis_plane_counts", "wf_host_axis_plane_mesh", "wf_set_thermal", "wf_set_contact_heat",
-             "wf_host_force_tiles", "wf_set_elem_order", "wf_host_elem_order", "wf_host_run_slots"]
+             "wf_host_force_tiles", "wf_set_elem_order", "wf_host_elem_order", "wf_host_run_slots", "wf_step_open", "wf_step_close"]
             + ["wf_" + n for n in UNFUSED])
 
 
@@ -81,6 +81,8 @@ def load():
         "wf_init": (C.c_int, [vp, C.c_double]),
         "wf_init_phase": (C.c_int, [vp, C.c_int, C.c_double]),
         "wf_step": (C.c_int, [vp, C.c_int]),
+        "wf_step_open": (C.c_int, [vp, C.c_int]),
+        "wf_step_close": (C.c_int, [vp]),
         "wf_step_phase": (C.c_int, [vp, C.c_int, C.c_int]),
         "wf_step_timed": (C.c_int, [vp, C.c_int, C.POINTER(C.c_float)]),
         "wf_set_variant": (C.c_int, [vp, C.c_int, C.c_int]),

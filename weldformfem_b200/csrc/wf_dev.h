@@ -96,12 +96,13 @@ struct WfDev {
   /* brick form of the hexa main pass (NULL when the bank-aware layouts do not fit its compile-time pitches): node list
    * of CTA b at blk_pad_b + b * WF_BRICK_STRIDE indexed by shared-memory SLOT (wf_host_run_slots, -1 = hole); the slots
    * of an element's eight nodes in the CTA copy (16 bit each) and in its tile's accumulators (8 bit each) as one
-   * record per element; per tile tf_r2s[tile * tf_r2s_pitch] = number of unique nodes, then the slot of rank 0, 1, ... */
+   * record per element; tf_r2s[tile * 32 + lane] byte j = accumulator slot of the tile's unique node of rank
+   * lane + 32 j (0xff = none: at most 128 unique nodes), read when the partial sums are written out in rank order */
   const int *blk_pad_b;
   const uint4 *lidx_pk;              /* [ep] */
   const uint2 *tf_idx_pk;            /* [ep] */
-  const unsigned char *tf_r2s;
-  int tf_r2s_pitch;
+  const unsigned *tf_r2s;            /* [n_ctas * 128] */
+  int cta_lookahead;                 /* resident CTAs of the main element pass on the device (L2 look-ahead distance) */
   /* tetrahedra: corners of different elements of a tile DO share nodes, so the tile sum is pulled instead: every
    * element drops its k*dim force values in shared memory and lane u adds up the entries of unique node u listed in
    * the tile's incidence table (ascending element, then corner: a fixed order).  Table of tile w at
@@ -162,6 +163,12 @@ struct WfPar {
   double w; /* Gauss weight, Mechanical.C:269-282 */
   int xmin_cur; /* which xmin_key slot holds min x_r of the current coordinates */
   int halo_parity; /* multi-GPU: which half of the receive regions the current exchange uses */
+  /* multi-GPU, peer transport: halo work folded into the node passes.  send_ctas > 0: the first send_ctas CTAs of the
+   * launch send this rank's partial sums to the neighbours (send_chunks CTAs per neighbour, exchange number send_seq)
+   * instead of a separate k_halo_send launch; wait_seq > 0: every CTA of the consumer first waits until all neighbours
+   * have published exchange wait_seq (instead of a separate k_halo_wait launch). */
+  int send_ctas, send_chunks;
+  unsigned long long send_seq, wait_seq, wait_timeout_ns;
   int variant[4]; /* tuning: kernel variant for E1, N1, E2, N2 (0 = default) */
 };
 

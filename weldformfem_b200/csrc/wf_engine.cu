@@ -85,6 +85,10 @@ extern "C" void wf_destroy(wf_engine *E) {
   if (E->mon_host) cudaFreeHost(E->mon_host);
   for (int b = 0; b < 2; b++)
     if (E->mon_ev[b]) cudaEventDestroy(E->mon_ev[b]);
+  if (E->copy_stream) { cudaStreamSynchronize(E->copy_stream); cudaStreamDestroy(E->copy_stream); }
+  for (int b = 0; b < 2; b++)
+    if (E->bc_at_ev[b]) cudaEventDestroy(E->bc_at_ev[b]);
+  if (E->bc_copy_ev) cudaEventDestroy(E->bc_copy_ev);
   for (void *p : E->ipc_opened) cudaIpcCloseMemHandle(p);
   for (void *p : E->allocs) cudaFree(p);
   if (E->scratch) cudaFree(E->scratch);
@@ -265,7 +269,7 @@ static int upload_mesh(wf_engine *E, int nn, int ne, const double *x, const unsi
     }
     // tile-reduced force path (WfDev::ftile): tables built on the host (wf_force_tiles_build, wf_mesh.cpp)
     d.ftile = nullptr; d.tf_ptr = nullptr; d.tf_slots = nullptr; d.tf_idx = nullptr; d.tf_tab = nullptr;
-    d.lidx_pk = nullptr; d.tf_idx_pk = nullptr; d.blk_pad_b = nullptr; d.tf_r2s = nullptr; d.tf_r2s_pitch = 0;
+    d.lidx_pk = nullptr; d.tf_idx_pk = nullptr; d.blk_pad_b = nullptr; d.tf_r2s = nullptr; d.cta_lookahead = 0;
     d.tf_stride = 0; d.tf_tpitch = 0;
     if (dim == 3) { // 2D (1M quads, measured): rounds form E2 0.080 -> 0.099 ms, pull form 0.105 ms, N2 unchanged: not used
       WfForceTiles T;
@@ -287,10 +291,11 @@ static int upload_mesh(wf_engine *E, int nn, int ne, const double *x, const unsi
           // record each, and per tile the table rank -> slot used when the partial sums are written out
           if (T.rounds) {
             constexpr int BS = WF_BRICK_STRIDE, BW = WF_BRICK_WS;
-            const int ntile = T.n_tiles, rp = (T.stride + 1 + 3) / 4 * 4;
+            const int ntile = T.n_tiles;
             std::vector<int> bpad((size_t)nblk * BS, -1), sl, ids;
             std::vector<unsigned short> lpk((size_t)8 * d.ep, 0);
-            std::vector<unsigned char> tpk((size_t)8 * d.ep, 0), r2s((size_t)ntile * rp, 0);
+            std::vector<unsigned char> tpk((size_t)8 * d.ep, 0);
+            std::vector<unsigned> r2s((size_t)nblk * WF_EBLK, 0xFFFFFFFFu); // one word per thread of the main pass
             bool fits = true;
             for (int b = 0; b < nblk && fits; b++) {
               const int u0 = boff[b], U = boff[b + 1] - u0;
@@ -311,24 +316,29 @@ static int upload_mesh(wf_engine *E, int nn, int ne, const double *x, const unsi
               ids.erase(std::unique(ids.begin(), ids.end()), ids.end());
               const int U = (int)ids.size();
               sl.resize(U);
-              if (U > BW || U + 1 > rp) { fits = false; break; }
+              if (U > BW || U > 128) { fits = false; break; }
               if (wf_host_run_slots(U, ids.data(), sl.data()) > BW)
                 for (int i = 0; i < U; i++) sl[i] = i;
-              r2s[(size_t)w * rp] = (unsigned char)U;
-              for (int i = 0; i < U; i++) r2s[(size_t)w * rp + 1 + i] = (unsigned char)sl[i];
+              for (int i = 0; i < U; i++) {
+                unsigned &word = r2s[(size_t)w * 32 + (i & 31)];
+                word = (word & ~(0xFFu << (8 * (i >> 5)))) | ((unsigned)sl[i] << (8 * (i >> 5)));
+              }
               for (int e = e0; e < e1; e++)
                 for (int n = 0; n < 8; n++) tpk[(size_t)e * 8 + n] = (unsigned char)sl[T.tidx[(size_t)n * d.ep + e]];
             }
             if (fits) {
-              uint4 *dl4; uint2 *dt2; int *dbp; unsigned char *dr;
+              uint4 *dl4; uint2 *dt2; int *dbp; unsigned *dr;
               if (dalloc(E, &dl4, (size_t)d.ep) || dalloc(E, &dt2, (size_t)d.ep) || dalloc(E, &dbp, bpad.size()) || dalloc(E, &dr, r2s.size()))
                 return 1;
               CK(cudaMemcpyAsync(dl4, lpk.data(), lpk.size() * sizeof(unsigned short), cudaMemcpyHostToDevice, E->stream));
               CK(cudaMemcpyAsync(dt2, tpk.data(), tpk.size(), cudaMemcpyHostToDevice, E->stream));
               CK(cudaMemcpyAsync(dbp, bpad.data(), bpad.size() * sizeof(int), cudaMemcpyHostToDevice, E->stream));
-              CK(cudaMemcpyAsync(dr, r2s.data(), r2s.size(), cudaMemcpyHostToDevice, E->stream));
+              CK(cudaMemcpyAsync(dr, r2s.data(), r2s.size() * sizeof(unsigned), cudaMemcpyHostToDevice, E->stream));
               CK(cudaStreamSynchronize(E->stream));
-              d.lidx_pk = dl4; d.tf_idx_pk = dt2; d.blk_pad_b = dbp; d.tf_r2s = dr; d.tf_r2s_pitch = rp;
+              d.lidx_pk = dl4; d.tf_idx_pk = dt2; d.blk_pad_b = dbp; d.tf_r2s = dr;
+              int sms = 0;
+              CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, E->device));
+              d.cta_lookahead = 4 * sms; // four 128-register CTAs per SM
             }
           }
         } else {
@@ -545,6 +555,13 @@ extern "C" int wf_allocate_bcs(wf_engine *E) { WF_NULLCHK(E);
   E->d.bc_mask = dm; E->d.bc_vals = dv;
   E->bc_vals_d = dv;
   E->nbc_rows = (int)mask.size();
+  E->bc_vals_buf[0] = dv; E->bc_vals_buf[1] = nullptr; E->bc_vals_cur = 0; E->bc_set_calls = 0;
+  {
+    std::vector<int> row_node(std::max<size_t>(mask.size(), 1), 0);
+    for (auto &kv : row_of) row_node[kv.second] = kv.first;
+    if (dalloc(E, &E->bc_row_node_d, row_node.size())) return 1;
+    CK(cudaMemcpy(E->bc_row_node_d, row_node.data(), row_node.size() * sizeof(int), cudaMemcpyHostToDevice));
+  }
   for (int b = 0; b < 2; b++) {
     if (E->bc_stage[b]) { cudaFreeHost(E->bc_stage[b]); E->bc_stage[b] = nullptr; }
     if (!vals.empty()) {
@@ -581,9 +598,35 @@ extern "C" int wf_set_bc_values(wf_engine *E, int dim, int count, const double *
       if (slot[i] >= 0) st[slot[i]] = v[i];
     E->bc_stage_version[b][dd] = E->bc_version[dd];
   }
-  CK(cudaMemcpyAsync(E->bc_vals_d, st, (size_t)3 * E->nbc_rows * sizeof(double), cudaMemcpyHostToDevice, E->stream));
-  CK(cudaEventRecord(E->bc_ev[b], E->stream));
+  // Upload on a copy stream into the device copy the running step does NOT read (two copies, used alternately), so the
+  // transfer of step k+1's values overlaps step k.  Copy j targets the buffer last read by step j-2: it waits for the
+  // event recorded on the engine's stream at the previous call (covers every step enqueued before it).
+  const size_t nbytes = (size_t)3 * E->nbc_rows * sizeof(double);
+  if (!E->copy_stream) {
+    CK(cudaStreamCreateWithFlags(&E->copy_stream, cudaStreamNonBlocking));
+    for (int q = 0; q < 2; q++) CK(cudaEventCreateWithFlags(&E->bc_at_ev[q], cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&E->bc_copy_ev, cudaEventDisableTiming));
+  }
+  if (!E->bc_vals_buf[1] && dalloc(E, &E->bc_vals_buf[1], (size_t)3 * E->nbc_rows)) return 1;
+  const long j = E->bc_set_calls++;
+  const int tgt = E->bc_vals_cur ^ 1;
+  if (j > 0) CK(cudaStreamWaitEvent(E->copy_stream, E->bc_at_ev[(j - 1) & 1], 0));
+  else CK(cudaStreamSynchronize(E->stream)); // first call: the second copy was just allocated (memset on the engine's stream)
+  CK(cudaEventRecord(E->bc_at_ev[j & 1], E->stream));
+  CK(cudaMemcpyAsync(E->bc_vals_buf[tgt], st, nbytes, cudaMemcpyHostToDevice, E->copy_stream));
+  CK(cudaEventRecord(E->bc_ev[b], E->copy_stream));
+  CK(cudaEventRecord(E->bc_copy_ev, E->copy_stream));
+  CK(cudaStreamWaitEvent(E->stream, E->bc_copy_ev, 0));
+  E->bc_vals_cur = tgt;
+  E->bc_vals_d = E->bc_vals_buf[tgt];
+  E->d.bc_vals = E->bc_vals_d;
   E->bc_stage_cur ^= 1;
+  // engine in predicted state (wf_step_open): the velocities of the prescribed components already hold the values of
+  // the previous predictor; replace them (ImposeBCV after UpdatePrediction, Solver_explicit.C:535-540)
+  if (E->predicted) {
+    E->L->bc_patch_v(E->d, E->bc_row_node_d, E->nbc_rows, E->stream);
+    return check_launch(E, "wf_set_bc_values");
+  }
   return 0;
 }
 
@@ -600,6 +643,7 @@ extern "C" int wf_monitor_async(wf_engine *E) { WF_NULLCHK(E);
   d2.ne = 0;                       // kinetic part only
   d2.red = E->mon_red + wf_engine::MON_NACC * b;
   const bool fused = E->ekin_step == E->step_count && E->ekin_slot == b; // formed by the last node pass already
+  NEED(fused || !E->predicted, "no kinetic energy was formed for this step (two monitors were pending during wf_step_open)");
   if (!fused) {
     CK(cudaMemsetAsync(d2.red, 0, wf_engine::MON_NACC * sizeof(double), E->stream));
     E->L->energy(d2, nullptr, E->stream);   // adds into d2.red[0]
@@ -683,6 +727,25 @@ static void halo_send(wf_engine *E, int mode) {
 static void halo_wait(wf_engine *E) {
   if (E->transport == 0) E->L->halo_wait(E->d, E->seq, E->timeout_ns, E->stream);
 }
+// Peer transport inside the step: no launches of their own.  The send of an exchange rides in the first CTAs of the
+// next node pass (WfPar::send_ctas), the wait at the head of the kernel that consumes the neighbours' partials
+// (WfPar::wait_seq).  WF_HALO_FOLD=0 keeps the separate kernels (measurement).
+static bool halo_folded(const wf_engine *E) {
+  static const bool on = [] { const char *t = getenv("WF_HALO_FOLD"); return !(t && atoi(t) == 0); }();
+  return on && E->distributed && E->transport == 0;
+}
+static void halo_send_arm(wf_engine *E) {   // the NEXT node-pass launch sends
+  E->seq++;
+  E->P.halo_parity = (int)(E->seq & 1ull);
+  E->P.send_chunks = (std::max(E->max_halo_count, 1) + 255) / 256;   // 256 = threads per CTA of the node passes
+  E->P.send_ctas = (int)E->neigh.size() * E->P.send_chunks;
+  E->P.send_seq = E->seq;
+}
+static void halo_wait_arm(wf_engine *E) {   // the NEXT consumer launch waits
+  E->P.wait_seq = E->seq;
+  E->P.wait_timeout_ns = E->timeout_ns;
+}
+static void halo_disarm(wf_engine *E) { E->P.send_ctas = 0; E->P.wait_seq = 0; }
 
 static int init_stage(wf_engine *E, int stage, double dt) {
   WfDev &d = E->d;
@@ -775,6 +838,7 @@ extern "C" int wf_init_phase(wf_engine *E, int phase, double dt) { WF_NULLCHK(E)
 // WF_FAST only: bit 1 = this step's u_dt was not stored by the previous (fused) step and is recomputed from v and prev_a,
 // bit 2 = do not store u_dt because the next step recomputes it (saves 48 B per node and step)
 static int fuse_flags(const wf_engine *E, bool last) {
+  if (E->open_mode) last = false; // wf_step_open: the call's last node pass runs the next predictor too
   int f = last ? 0 : 1;
   if (!E->strict) {
     // only a predictor fused into the PREVIOUS node pass may drop u_dt: the first predictor of a batch must store it,
@@ -796,17 +860,25 @@ static int step_stage(wf_engine *E, int stage, bool last) {
     const bool fold = !E->predicted && !E->strict;
     if (!E->predicted && E->strict) E->L->predict(d, P, 1, E->stream);
     E->L->elem_vol(d, P, E->et, 0, E->stream);
-    // the partial volume sums of the shared nodes depend on E1 only (k_halo_send gathers them itself): send them
-    // BEFORE the nodal-sum pass, so the transfer and the neighbours' flags travel while N1 runs
-    if (E->distributed) halo_send(E, 1);
+    // the partial volume sums of the shared nodes depend on E1 only: they are sent BEFORE the nodal sums are formed
+    // (first CTAs of the N1 launch, or a kernel of their own), so the transfer and the neighbours' flags travel
+    // while N1 runs
+    const bool fold_halo = halo_folded(E);
+    if (fold_halo) halo_send_arm(E);
+    else if (E->distributed) halo_send(E, 1);
     E->L->node_vol(d, P, fold ? 3 : 1, E->stream);
+    halo_disarm(E);
   } else if (stage == 1) {
+    const bool fold_halo = halo_folded(E);
+    if (fold_halo) halo_wait_arm(E);
     if (E->distributed) E->L->halo_finish(d, P, 1, P.halo_parity, E->stream);
+    halo_disarm(E);
     E->L->elem_main(d, P, E->et, sep, E->stream);
-    if (E->distributed) halo_send(E, 2);
+    if (E->distributed && !fold_halo) halo_send(E, 2);
   } else {
     if (wf_contact_forces(E)) return 1;          // CalcContactForces (Solver_explicit.C:769-770)
-    const bool fuse_ekin = last && E->mon_seen && E->mon_red && E->mon_pending < 2;
+    // (wf_step_open always forms it: in predicted state the corrected velocities are gone afterwards)
+    const bool fuse_ekin = last && (E->mon_seen || E->open_mode) && E->mon_red && E->mon_pending < 2;
     if (fuse_ekin) { // the node pass of the call's last step also forms the kinetic energy for wf_monitor_async
       const int b = (E->mon_head + E->mon_pending) & 1;
       d.ekin_acc = E->mon_red + wf_engine::MON_NACC * b;
@@ -817,16 +889,26 @@ static int step_stage(wf_engine *E, int stage, bool last) {
     if (E->distributed && E->transport == 0) {
       // peer transport: the nodes this rank does not share are integrated while the neighbours' force partials are
       // still travelling; the shared ones follow after the wait (step_once skips its own wait before this stage)
-      E->L->node_update(d, P, sep, fuse_flags(E, last), 3, E->stream);
-      halo_wait(E);
-      E->L->node_update(d, P, sep, fuse_flags(E, last), 4, E->stream);
+      if (halo_folded(E)) {
+        halo_send_arm(E);                        // first CTAs of the phase-3 launch send the force partials
+        E->L->node_update(d, P, sep, fuse_flags(E, last), 3, E->stream);
+        halo_disarm(E);
+        halo_wait_arm(E);                        // phase 4 waits for the neighbours itself
+        E->L->node_update(d, P, sep, fuse_flags(E, last), 4, E->stream);
+        halo_disarm(E);
+      } else {
+        E->L->node_update(d, P, sep, fuse_flags(E, last), 3, E->stream);
+        halo_wait(E);
+        E->L->node_update(d, P, sep, fuse_flags(E, last), 4, E->stream);
+      }
     } else {
       E->L->node_update(d, P, sep, fuse_flags(E, last), 0, E->stream);
     }
     d.ekin_acc = nullptr;
     if (wf_contact_step_end(E)) return 1;        // rigid surfaces: ramp, Move, normals, plane coefficients (:981-1005)
     if (P.thermal) { E->L->node_thermal(d, P, E->stream); P.dtedt_cur ^= 1; }  // ThermalCalcs, node part (:1008-1012)
-    E->predicted = !last;
+    E->predicted = !last || E->open_mode;
+    E->udt_valid = !E->predicted;
     P.xmin_cur ^= 1;
     E->time += P.dt;
     E->step_count++;
@@ -837,7 +919,8 @@ static int step_stage(wf_engine *E, int stage, bool last) {
 static int step_once(wf_engine *E, bool last) {
   for (int st = 0; st < 3; st++) {
     if (step_stage(E, st, last)) return 1;
-    if (E->distributed && st < 2 && !(st == 1 && E->transport == 0)) halo_wait(E); // stage 2 waits for the forces itself
+    // stage 2 waits for the forces itself; with the folded exchange the consumers wait themselves
+    if (E->distributed && st < 2 && !(st == 1 && E->transport == 0) && !halo_folded(E)) halo_wait(E);
   }
   return 0;
 }
@@ -858,6 +941,35 @@ extern "C" int wf_step(wf_engine *E, int nsteps) { WF_NULLCHK(E);
   for (int s = 0; s < nsteps; s++)
     if (step_once(E, s == nsteps - 1)) return 1;
   return step_epilogue(E, "wf_step");
+}
+
+// wf_step that leaves the engine in PREDICTED state: the last node pass of the call also runs the next step's
+// UpdatePrediction + ImposeBCV (as every other step of a batch does), so a host loop that steps once per call — new
+// prescribed velocities in, a monitor value out, every step — runs the same fused schedule as one long batch.
+// Between calls only wf_set_bc_values (which patches the predicted velocities of the prescribed components),
+// wf_monitor_async / wf_monitor_wait, wf_step and wf_step_open are allowed; wf_step_close (or a plain wf_step) returns
+// to the state every other entry point expects.  Fast flavour only.
+extern "C" int wf_step_open(wf_engine *E, int nsteps) { WF_NULLCHK(E);
+  NEED(!E->strict, "wf_step_open needs the fast flavour (the strict flavour runs the reference's unfused predictor)");
+  if (step_prologue(E)) return 1;
+  E->open_mode = true;
+  int rc = 0;
+  for (int s = 0; s < nsteps && !rc; s++) rc = step_once(E, s == nsteps - 1);
+  E->open_mode = false;
+  if (rc) return 1;
+  return step_epilogue(E, "wf_step_open");
+}
+
+// leave the predicted state without stepping: v_c = v_p - (1 - gamma) dt a.  "u_dt" (the last increment, which the
+// fused schedule does not store) is not available until the next closed step.
+extern "C" int wf_step_close(wf_engine *E) { WF_NULLCHK(E);
+  NEED(E->inited, "wf_step_close before wf_init");
+  if (!E->predicted) return 0;
+  CK(cudaSetDevice(E->device));
+  E->L->unpredict(E->d, E->P, E->stream);
+  E->predicted = false;
+  E->udt_valid = false;
+  return check_launch(E, "wf_step_close");
 }
 
 extern "C" int wf_step_phase(wf_engine *E, int phase, int last_step) { WF_NULLCHK(E);
@@ -1286,7 +1398,7 @@ static bool lookup(wf_engine *E, const std::string &nm, ArrayRef &r, bool for_wr
   if (nm == "x") return nodevec(d.x);
   if (nm == "v") return nodevec(d.v);
   if (nm == "u") return nodevec(d.u);
-  if (nm == "u_dt") return nodevec(d.u_dt);
+  if (nm == "u_dt") return E->udt_valid || for_write ? nodevec(d.u_dt) : false;
   if (nm == "prev_a") return nodevec(d.prev_a);
   if (nm == "a") return nodevec((E->a_in_dbg || for_write) && d.a ? d.a : d.prev_a);
   if (nm == "m_fe") return nodevec(d.fe);

@@ -51,6 +51,16 @@ struct wf_engine {
   cudaEvent_t bc_ev[2] = {nullptr, nullptr};
   int bc_stage_cur = 0;
   double *bc_vals_d = nullptr;
+  // time-dependent prescribed values (wf_set_bc_values): two device copies of bc_vals, written alternately by a copy
+  // stream while the step that reads the other one is still running
+  double *bc_vals_buf[2] = {nullptr, nullptr};
+  int bc_vals_cur = 0;
+  cudaStream_t copy_stream = nullptr;
+  cudaEvent_t bc_at_ev[2] = {nullptr, nullptr}, bc_copy_ev = nullptr;
+  long bc_set_calls = 0;
+  int *bc_row_node_d = nullptr;            // node of every BC row (k_bc_patch_v)
+  bool open_mode = false;                  // wf_step_open: the call's last node pass also runs the next predictor
+  bool udt_valid = true;                   // "u_dt" holds the last step's increment (not after wf_step_close)
   std::vector<double> bc_master;           // host copy of bc_vals
   int bc_version[3] = {0, 0, 0}, bc_stage_version[2][3] = {{0, 0, 0}, {0, 0, 0}};
   // asynchronous step monitor (wf_monitor_async / wf_monitor_wait): 2-deep ring of pinned results

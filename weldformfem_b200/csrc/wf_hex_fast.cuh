@@ -421,25 +421,43 @@ struct StagedSrcC {
   unsigned li[8];
   WF_DI double operator()(int comp, int n) const { return s[comp * STRIDE + li[n]]; }
 };
-template <int WS>
+template <int WS, bool BATCH3>
 struct EmitTileC {
   double *acc;       // [3][WS] accumulators of this warp
-  uint2 pk;          // eight 8-bit tile-local indices
+  uint2 pk;          // eight 8-bit tile-local slots
   unsigned amask;
+  double qb[2][8];   // BATCH3: corner values of components 0 and 1, kept until component 2 arrives
   WF_DI unsigned idx(int n) const { return ((n < 4 ? pk.x : pk.y) >> (8 * (n & 3))) & 0xffu; }
   WF_DI void operator()(int i, const double (&B)[3], const double (&c)[4]) {
     double q[8];
     wht_inv8(B, c, q);
-    double *a = acc + i * WS;
+    if (!BATCH3) {
+      double *a = acc + i * WS;
 #pragma unroll
-    for (int n = 0; n < 8; n++) {
-      a[idx(n)] += q[n];
-      __syncwarp(amask);
+      for (int n = 0; n < 8; n++) {
+        a[idx(n)] += q[n];
+        __syncwarp(amask);
+      }
+    } else if (i < 2) {
+#pragma unroll
+      for (int n = 0; n < 8; n++) qb[i][n] = q[n];
+    } else {
+      // one round per corner for all three components: three independent read-modify-writes in flight per round
+      // (the rounds are a serial chain of shared-memory latencies: 8 links instead of 24)
+#pragma unroll
+      for (int n = 0; n < 8; n++) {
+        double *a = acc + idx(n);
+        const double a0 = a[0], a1 = a[WS], a2 = a[2 * WS];
+        a[0] = a0 + qb[0][n]; a[WS] = a1 + qb[1][n]; a[2 * WS] = a2 + q[n];
+        __syncwarp(amask);
+      }
     }
   }
 };
 
-template <int STRIDE, int WS, int MINB>
+// BATCH3: see EmitTileC.  LOOKAHEAD: besides the node list of the CTA that follows on this SM, ask L2 for that CTA's
+// node DATA (its list was requested one generation earlier, so reading it here is an L2 hit).
+template <int STRIDE, int WS, int MINB, bool BATCH3 = true, bool LOOKAHEAD = false>
 __global__ void __launch_bounds__(TPB, MINB) k_elem_main_hex_brick(WfDev d, WfPar P) {
   extern __shared__ double sm[];
   pdl_trigger();
@@ -459,6 +477,22 @@ __global__ void __launch_bounds__(TPB, MINB) k_elem_main_hex_brick(WfDev d, WfPa
   }
   const uint4 lpk = __ldg(d.lidx_pk + e);
   const uint2 rpk = __ldg(d.tf_idx_pk + e);
+  const unsigned r2s = __ldg(d.tf_r2s + (long long)b * TPB + t); // rank -> slot of this warp's tile, used at the very end
+  // the node list of the CTA that will follow this one on the SM: ask L2 for it now (the first thing that CTA waits for)
+  if (t < (STRIDE * 4 + 127) / 128) {
+    const long long nb = (long long)b + (LOOKAHEAD ? 2 : 1) * (long long)d.cta_lookahead;
+    if (nb * TPB < d.ne) prefetch_l2(reinterpret_cast<const char *>(d.blk_pad_b + nb * STRIDE) + t * 128);
+  }
+  int gnext[NQ];
+  if (LOOKAHEAD) {
+    const long long nb = (long long)b + d.cta_lookahead;
+    const bool have = nb * TPB < d.ne;
+#pragma unroll
+    for (int q = 0; q < NQ; q++) {
+      const int i = q * TPB + t;
+      gnext[q] = (have && i < STRIDE) ? __ldg(d.blk_pad_b + nb * STRIDE + i) : -1;
+    }
+  }
   pdl_wait(); // everything above reads constant mesh tables only
   double tau[6];
 #pragma unroll
@@ -480,6 +514,17 @@ __global__ void __launch_bounds__(TPB, MINB) k_elem_main_hex_brick(WfDev d, WfPa
     }
   }
   cp_async_commit();
+  if (LOOKAHEAD) {
+#pragma unroll
+    for (int q = 0; q < NQ; q++) {
+      const int gq = gnext[q];
+      if (gq >= 0) {
+#pragma unroll
+        for (int c = 0; c < 3; c++) { prefetch_l2(d.x + (long long)c * d.np + gq); prefetch_l2(d.v + (long long)c * d.np + gq); }
+        prefetch_l2(d.nodal_p + gq);
+      }
+    }
+  }
   const int lane = t & 31, warp = t >> 5;
   double *acc = sm + 7 * STRIDE + warp * 3 * WS;
 #pragma unroll
@@ -495,19 +540,22 @@ __global__ void __launch_bounds__(TPB, MINB) k_elem_main_hex_brick(WfDev d, WfPa
   double J_sum = 0.0;
 #pragma unroll
   for (int a = 0; a < 8; a++) J_sum += sm[6 * STRIDE + src.li[a]];
-  EmitTileC<WS> emit{acc, rpk, amask};
+  EmitTileC<WS, BATCH3> emit;
+  emit.acc = acc; emit.pk = rpk; emit.amask = amask;
   hex_back(d, P, e, active, g, tau, pl, rho_e, sy, J_sum, p_prev, emit);
   __syncwarp();
-  // one partial per unique node of the tile, in rank order (the accumulators sit at bank-aware slots: tf_r2s)
+  // one partial per unique node of the tile, in rank order (the accumulators sit at bank-aware slots; r2s was loaded in
+  // the prologue: byte j = slot of rank lane + 32 j, 0xff = none)
   const long long tile = (long long)b * (TPB / 32) + warp;
   if (tile * 32 < d.ne) {
-    const unsigned char *__restrict__ r2s = d.tf_r2s + tile * d.tf_r2s_pitch;
-    const int cnt = __ldg(r2s);
     double *__restrict__ out = d.ftile + tile * 3 * d.tf_stride;
-    for (int r = lane; r < cnt; r += 32) {
-      const int sl = __ldg(r2s + 1 + r);
 #pragma unroll
-      for (int c = 0; c < 3; c++) out[c * d.tf_stride + r] = acc[c * WS + sl];
+    for (int j = 0; j < 4; j++) {
+      const unsigned sl = (r2s >> (8 * j)) & 0xffu;
+      if (sl != 0xffu) {
+#pragma unroll
+        for (int c = 0; c < 3; c++) out[c * d.tf_stride + lane + 32 * j] = acc[c * WS + sl];
+      }
     }
   }
 }

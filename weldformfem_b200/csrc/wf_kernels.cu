@@ -118,6 +118,29 @@ __global__ void k_impose_bc(WfDev d, int dim, int is_acc, double *a_or_v) {
   if (d.bc_mask[bi] & (1u << dim)) a_or_v[(long long)dim * d.np + n] = is_acc ? 0.0 : d.bc_vals[3 * bi + dim];
 }
 
+// wf_set_bc_values on an engine that is in predicted state (wf_step_open): the velocities of the prescribed components
+// were set by the fused predictor of the previous node pass; overwrite them with the new values (= the ImposeBCV the
+// reference runs after UpdatePrediction, Solver_explicit.C:535-540).  One thread per BC row.
+__global__ void k_bc_patch_v(WfDev d, const int *__restrict__ row_node, int nrows) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= nrows) return;
+  const int n = row_node[r];
+  const unsigned m = d.bc_mask[r];
+  for (int c = 0; c < d.dim; c++)
+    if (m & (1u << c)) d.v[(long long)c * d.np + n] = d.bc_vals[3 * r + c];
+}
+// wf_step_close: undo the fused predictor, v_c = v_p - (1 - gamma) dt a (prescribed components have a = 0)
+template <int D>
+__global__ void k_unpredict(WfDev d, WfPar P) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= d.nn) return;
+#pragma unroll
+  for (int c = 0; c < D; c++) {
+    const long long i = (long long)c * d.np + n;
+    d.v[i] = d.v[i] - (1.0 - P.gamma) * P.dt * d.prev_a[i];
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // E1: element volume from current coordinates
 // ---------------------------------------------------------------------------------------------
@@ -180,12 +203,175 @@ __global__ void __launch_bounds__(WF_EBLK) k_elem_vol_staged(WfDev d, WfPar P, i
   d.vol[e] = elem_volume<ET>(detJ, radius, d.domtype, d.vol_weight);
 }
 
+// E1, brick form (hexahedra whose CTA node lists fit the bank-aware layout, WfDev::blk_pad_b): the CTA stages the
+// coordinates of its unique nodes once (coalesced runs of node ids instead of 24 scattered 8-byte loads per element:
+// in the engine's element order the per-element gathers are L1-request-bound) and every element reads its eight
+// nodes conflict-free through the packed slots.  Same arithmetic as k_elem_vol: identical volumes.
+template <int STRIDE>
+__global__ void __launch_bounds__(WF_EBLK) k_elem_vol_brick(WfDev d, WfPar P) {
+  extern __shared__ double sm[];
+  pdl_trigger();
+  const int t = threadIdx.x, b = blockIdx.x;
+  constexpr int NQ = (STRIDE + WF_EBLK - 1) / WF_EBLK;
+  const int *__restrict__ ids = d.blk_pad_b + (long long)b * STRIDE;
+  int gid[NQ];
+#pragma unroll
+  for (int q = 0; q < NQ; q++) {
+    const int i = q * WF_EBLK + t;
+    gid[q] = (i < STRIDE) ? __ldg(ids + i) : -1;
+  }
+  const int e = b * WF_EBLK + t;
+  const bool active = e < d.ne;
+  const uint4 lpk = __ldg(d.lidx_pk + (active ? e : d.ne - 1));
+  if (t < (STRIDE * 4 + 127) / 128) { // node list of the CTA that follows on this SM (see k_elem_main_hex_brick)
+    const long long nb = (long long)b + 4LL * d.cta_lookahead;
+    if (nb * WF_EBLK < d.ne) prefetch_l2(reinterpret_cast<const char *>(d.blk_pad_b + nb * STRIDE) + t * 128);
+  }
+  pdl_wait();
+#pragma unroll
+  for (int q = 0; q < NQ; q++) {
+    const int i = q * WF_EBLK + t, gq = gid[q];
+    if (gq >= 0) {
+#pragma unroll
+      for (int c = 0; c < 3; c++) hexfast::cp_async8(sm + c * STRIDE + i, d.x + (long long)c * d.np + gq);
+    }
+  }
+  hexfast::cp_async_commit();
+  unsigned li[8];
+  li[0] = lpk.x & 0xffffu; li[1] = lpk.x >> 16; li[2] = lpk.y & 0xffffu; li[3] = lpk.y >> 16;
+  li[4] = lpk.z & 0xffffu; li[5] = lpk.z >> 16; li[6] = lpk.w & 0xffffu; li[7] = lpk.w >> 16;
+  hexfast::cp_async_wait_all();
+  __syncthreads();
+  if (!active) return;
+  double xl[8][3], A[3][3], detJ;
+#pragma unroll
+  for (int n = 0; n < 8; n++)
+#pragma unroll
+    for (int c = 0; c < 3; c++) xl[n][c] = sm[c * STRIDE + li[n]];
+  jac_adj_det<ET_HEX8>(xl, A, detJ);
+  d.vol[e] = elem_volume<ET_HEX8>(detJ, 0.0, d.domtype, d.vol_weight);
+}
+
 // CalcElemVol on stored detJ / radius (unfused)
 template <int ET>
 __global__ void k_vol_from_detj(WfDev d) {
   int e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= d.ne) return;
   d.vol[e] = elem_volume<ET>(d.detJ[e], d.radius ? d.radius[e] : 0.0, d.domtype, d.vol_weight);
+}
+
+// ---------------------------------------------------------------------------------------------
+// multi-GPU halo primitives used INSIDE the node passes (peer transport; the stand-alone kernels are further below)
+// ---------------------------------------------------------------------------------------------
+WF_DI void st_release_sys(unsigned long long *p, unsigned long long v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+WF_DI unsigned long long ld_acquire_sys(const unsigned long long *p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+WF_DI unsigned long long global_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+// Every CTA of a consumer kernel: thread 0 waits (acquire, system scope) until all neighbours have published exchange
+// `seq`, the rest of the CTA waits at the barrier.  A timeout is sticky: comm_error stays set, later waits return at
+// once (the shared-node state is stale from the first missed exchange on), the non-finite flag is raised, and every
+// host entry point that reads the engine reports the error.
+WF_DI void halo_wait_cta(const WfDev &d, unsigned long long seq, unsigned long long timeout_ns) {
+  if (threadIdx.x == 0 && *(volatile int *)d.comm_error == 0) {
+    const unsigned long long t0 = global_ns();
+    for (int i = 0; i < d.n_neigh; i++)
+      while (ld_acquire_sys(d.flags + i) < seq) {
+        if (global_ns() - t0 > timeout_ns) { atomicExch(d.comm_error, 1 + i); atomicExch(d.nonfinite, 1); i = d.n_neigh; break; }
+        __nanosleep(100);
+      }
+  }
+  __syncthreads();
+}
+// partial sums over the local nodel list of node n, in list order
+WF_DI void halo_node_sums(const WfDev &d, int n, const double *__restrict__ src, double &s, double &sq, double &rs, int &cnt) {
+  const long long base = d.sell_ptr[n >> 5];
+  const int width = (int)((d.sell_ptr[(n >> 5) + 1] - base) >> 5);
+  const int lane = n & 31;
+  s = 0.0; sq = 0.0; rs = 0.0; cnt = 0;
+  for (int j = 0; j < width; j++) {
+    int slot = __ldg(d.sell_slots + base + ((long long)j << 5) + lane);
+    if (slot >= 0) {
+      const int e = slot / d.k;
+      const double ve = src[e];
+      s += ve;
+      sq += ve / 4.0;
+      rs += d.rho[e];
+      cnt++;
+    }
+  }
+}
+// sum of the tile partials of node n (tile-reduced force path, WfDev::ftile), ascending tile order
+WF_DI void tile_node_force(const WfDev &d, int n, double (&fi)[3]) {
+  const long long base = d.tf_ptr[n >> 5];
+  const int width = (int)((d.tf_ptr[(n >> 5) + 1] - base) >> 5);
+  fi[0] = fi[1] = fi[2] = 0.0;
+  for (int j = 0; j < width; j++) {
+    const unsigned o = __ldg(d.tf_slots + base + ((long long)j << 5) + (n & 31));
+    if (o == 0xFFFFFFFFu) continue;
+    for (int c = 0; c < d.dim; c++) fi[c] += d.ftile[(long long)o + (long long)c * d.tf_stride];
+  }
+}
+WF_DI void halo_node_force(const WfDev &d, int n, int sep, double (&fi)[3]) {
+  if (sep == 2) { tile_node_force(d, n, fi); return; }
+  const long long base = d.sell_ptr[n >> 5];
+  const int width = (int)((d.sell_ptr[(n >> 5) + 1] - base) >> 5);
+  const int D = d.dim;
+  const double *__restrict__ row = d.fsell + base * D + (n & 31);
+  fi[0] = fi[1] = fi[2] = 0.0;
+  for (int j = 0; j < width; j++)
+    for (int c = 0; c < D; c++) fi[c] += row[((long long)j * D + c) * 32];
+  if (sep) {
+    const double *__restrict__ rowh = d.fsell_hg + base * D + (n & 31);
+    for (int j = 0; j < width; j++)
+      for (int c = 0; c < D; c++) fi[c] -= rowh[((long long)j * D + c) * 32];
+  }
+}
+// One CTA of a halo send: chunk `chunk` of neighbour `inb` (any block size).  Recomputes this rank's partial sums for
+// its shared nodes (same list order as the node kernels, so the values are the ones those kernels form) and stores them
+// straight into the neighbour's receive region over NVLink; the last of the neighbour's `chunks` CTAs publishes the
+// exchange number in the neighbour's flag slot (system-scope release).  MODE 0 = init triple (sum vol_0, sum rho,
+// count), 1 = sum vol (+ sum vol/4 for ANP_Nodal), 2 = internal-force partial.
+template <int MODE>
+WF_DI void halo_send_cta(const WfDev &d, const WfPar &P, int sep, unsigned long long seq, int inb, int chunk, int chunks) {
+  const WfHaloNb nb = d.nb[inb];
+  const int j = chunk * blockDim.x + threadIdx.x;
+  if (j < nb.count) {
+    const int n = d.halo_nodes[nb.offset + j];
+    double vals[WF_HALO_NC] = {0.0, 0.0, 0.0};
+    int nc = WF_HALO_NC;
+    if (MODE == 2) {
+      halo_node_force(d, n, sep, vals);
+      nc = d.dim;
+    } else {
+      double s, sq, rs;
+      int cnt;
+      halo_node_sums(d, n, MODE == 0 ? d.vol_0 : d.vol, s, sq, rs, cnt);
+      if (MODE == 0) { vals[0] = (P.press == 3) ? sq : s; vals[1] = rs; vals[2] = (double)cnt; }
+      else { vals[0] = s; vals[1] = sq; nc = 2; }
+    }
+    double *dst = nb.dst + (long long)(seq & 1ull) * WF_HALO_NC * nb.count + j;
+    for (int c = 0; c < nc; c++) dst[(long long)c * nb.count] = vals[c];
+    __threadfence_system();
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    const unsigned done = atomicAdd(nb.counter, 1u);
+    if (done == (unsigned)chunks - 1u) {
+      *nb.counter = 0u;
+      __threadfence_system();
+      st_release_sys(nb.flag, seq);
+    }
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -202,7 +388,18 @@ __global__ void __launch_bounds__(TPB_N, MINB) k_node_vol(WfDev d, WfPar P, int 
   const bool with_predict = mode_in == 3;
   const int mode = with_predict ? 1 : mode_in;
   pdl_trigger();
-  int n = blockIdx.x * blockDim.x + threadIdx.x;
+  int bx = blockIdx.x;
+  if (mode == 1 && P.send_ctas > 0) {
+    // multi-GPU: the first CTAs of the launch send this rank's partial volume sums of the shared nodes (they depend on
+    // the element volumes only), so the transfer travels while the rest of the grid forms the nodal sums
+    if (bx < P.send_ctas) {
+      pdl_wait();
+      halo_send_cta<1>(d, P, 0, P.send_seq, bx / P.send_chunks, bx % P.send_chunks, P.send_chunks);
+      return;
+    }
+    bx -= P.send_ctas;
+  }
+  int n = bx * blockDim.x + threadIdx.x;
   int slice = n >> 5;
   if (slice >= d.nslices) { if (n == 0) pdl_wait(); return; }
   const long long base = d.sell_ptr[slice];
@@ -539,66 +736,8 @@ __global__ void __launch_bounds__(TPB_E, MINB) k_elem_main(WfDev d, WfPar P, int
 }
 
 // ---------------------------------------------------------------------------------------------
-// device helpers of the multi-GPU halo exchange (kernels further below)
+// device helpers of the multi-GPU halo exchange (the primitives are defined ahead of the node passes)
 // ---------------------------------------------------------------------------------------------
-WF_DI void st_release_sys(unsigned long long *p, unsigned long long v) {
-  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
-}
-WF_DI unsigned long long ld_acquire_sys(const unsigned long long *p) {
-  unsigned long long v;
-  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-  return v;
-}
-WF_DI unsigned long long global_ns() {
-  unsigned long long t;
-  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-  return t;
-}
-
-// partial sums over the local nodel list of node n, in list order
-WF_DI void halo_node_sums(const WfDev &d, int n, const double *__restrict__ src, double &s, double &sq, double &rs, int &cnt) {
-  const long long base = d.sell_ptr[n >> 5];
-  const int width = (int)((d.sell_ptr[(n >> 5) + 1] - base) >> 5);
-  const int lane = n & 31;
-  s = 0.0; sq = 0.0; rs = 0.0; cnt = 0;
-  for (int j = 0; j < width; j++) {
-    int slot = __ldg(d.sell_slots + base + ((long long)j << 5) + lane);
-    if (slot >= 0) {
-      const int e = slot / d.k;
-      const double ve = src[e];
-      s += ve;
-      sq += ve / 4.0;
-      rs += d.rho[e];
-      cnt++;
-    }
-  }
-}
-// sum of the tile partials of node n (tile-reduced force path, WfDev::ftile), ascending tile order
-WF_DI void tile_node_force(const WfDev &d, int n, double (&fi)[3]) {
-  const long long base = d.tf_ptr[n >> 5];
-  const int width = (int)((d.tf_ptr[(n >> 5) + 1] - base) >> 5);
-  fi[0] = fi[1] = fi[2] = 0.0;
-  for (int j = 0; j < width; j++) {
-    const unsigned o = __ldg(d.tf_slots + base + ((long long)j << 5) + (n & 31));
-    if (o == 0xFFFFFFFFu) continue;
-    for (int c = 0; c < d.dim; c++) fi[c] += d.ftile[(long long)o + (long long)c * d.tf_stride];
-  }
-}
-WF_DI void halo_node_force(const WfDev &d, int n, int sep, double (&fi)[3]) {
-  if (sep == 2) { tile_node_force(d, n, fi); return; }
-  const long long base = d.sell_ptr[n >> 5];
-  const int width = (int)((d.sell_ptr[(n >> 5) + 1] - base) >> 5);
-  const int D = d.dim;
-  const double *__restrict__ row = d.fsell + base * D + (n & 31);
-  fi[0] = fi[1] = fi[2] = 0.0;
-  for (int j = 0; j < width; j++)
-    for (int c = 0; c < D; c++) fi[c] += row[((long long)j * D + c) * 32];
-  if (sep) {
-    const double *__restrict__ rowh = d.fsell_hg + base * D + (n & 31);
-    for (int j = 0; j < width; j++)
-      for (int c = 0; c < D; c++) fi[c] -= rowh[((long long)j * D + c) * 32];
-  }
-}
 // sum of the sharers' partials of unique shared node u, component comp, ascending rank order
 WF_DI double halo_total(const WfDev &d, int u, int comp, int parity, double own) {
   double acc = 0.0;
@@ -641,7 +780,19 @@ template <int D, bool SEPARATE_HG, int UNROLL, bool TILE_F = false, bool PREFETC
 __global__ void __launch_bounds__(TPB_N, MINB) k_node_update(WfDev d, WfPar P, int fuse_flags, int phase) {
   const bool fuse_predictor = fuse_flags & 1, udt_recompute = fuse_flags & 2, udt_skip_store = fuse_flags & 4;
   pdl_trigger();
-  int n = blockIdx.x * blockDim.x + threadIdx.x;
+  int bx = blockIdx.x;
+  if (phase == 3 && P.send_ctas > 0) {
+    // multi-GPU: the first CTAs of the launch send this rank's partial forces of the shared nodes; the rest of the grid
+    // integrates the nodes this rank does not share while they travel
+    if (bx < P.send_ctas) {
+      pdl_wait();
+      halo_send_cta<2>(d, P, TILE_F ? 2 : (SEPARATE_HG ? 1 : 0), P.send_seq, bx / P.send_chunks, bx % P.send_chunks, P.send_chunks);
+      return;
+    }
+    bx -= P.send_ctas;
+  }
+  if (phase == 4 && P.wait_seq) halo_wait_cta(d, P.wait_seq, P.wait_timeout_ns); // folded k_halo_wait (before any early exit)
+  int n = bx * blockDim.x + threadIdx.x;
   if (phase == 4) { // shared nodes only, one thread per unique shared node (after the halo wait)
     if (n >= d.n_uniq) return;
     n = d.hu_node[n];
@@ -746,7 +897,9 @@ __global__ void __launch_bounds__(TPB_N, MINB) k_node_update(WfDev d, WfPar P, i
     const double vp = d.v[i];
     // the fused predictor of the previous step formed u_dt = dt (v_c + (1/2 - beta) dt a) and v_p = v_c + (1 - gamma) dt a
     // (a = 0 and v_p = v_c = the prescribed value on constrained components), hence u_dt = dt (v_p + (gamma - 1/2 - beta) dt a)
-    udt0[c] = udt_recompute ? P.dt * (vp + (P.gamma - 0.5 - P.beta) * P.dt * pa) : d.u_dt[i];
+    // (a prescribed component may get a NEW value between two steps, wf_set_bc_values: its u_dt = dt * OLD value is
+    // therefore always stored and read, never recomputed from the patched velocity)
+    udt0[c] = (udt_recompute && !(bm & (1u << c))) ? P.dt * (vp + (P.gamma - 0.5 - P.beta) * P.dt * pa) : d.u_dt[i];
     a[c] = f * (a[c] - P.alpha * pa);
     v[c] = vp + P.gamma * P.dt * a[c];
     if (bm & (1u << c)) v[c] = d.bc_vals[3 * bi + c];
@@ -760,7 +913,7 @@ __global__ void __launch_bounds__(TPB_N, MINB) k_node_update(WfDev d, WfPar P, i
     double s2 = 0.0;
 #pragma unroll
     for (int c = 0; c < D; c++) s2 += v[c] * v[c];
-    warp_add(d.ekin_acc + (blockIdx.x & 255), 0.5 * mass * s2); // 256 accumulators (wf_engine::MON_NACC), summed by the host
+    warp_add(d.ekin_acc + (bx & 255), 0.5 * mass * s2); // 256 accumulators (wf_engine::MON_NACC), summed by the host
   }
 #pragma unroll
   for (int c = 0; c < D; c++) {
@@ -772,7 +925,7 @@ __global__ void __launch_bounds__(TPB_N, MINB) k_node_update(WfDev d, WfPar P, i
     d.prev_a[i] = a[c];
     d.u[i] = d.u[i] + udt;
     if (fuse_predictor) {
-      if (!udt_skip_store) d.u_dt[i] = P.dt * (v[c] + (0.5 - P.beta) * P.dt * a[c]);
+      if (!udt_skip_store || (bm & (1u << c))) d.u_dt[i] = P.dt * (v[c] + (0.5 - P.beta) * P.dt * a[c]);
       v[c] = v[c] + (1.0 - P.gamma) * P.dt * a[c];
       if (bm & (1u << c)) v[c] = d.bc_vals[3 * bi + c];
     } else {
@@ -1291,54 +1444,16 @@ __global__ void k_u_corr_pos(WfDev d, WfPar P) { // UpdateCorrectionPos
 // ---------------------------------------------------------------------------------------------
 template <int MODE>
 __global__ void __launch_bounds__(128) k_halo_send(WfDev d, WfPar P, int sep, unsigned long long seq) {
-  const WfHaloNb nb = d.nb[blockIdx.y];
-  const int j = blockIdx.x * blockDim.x + threadIdx.x;
-  if (j < nb.count) {
-    const int n = d.halo_nodes[nb.offset + j];
-    double vals[WF_HALO_NC] = {0.0, 0.0, 0.0};
-    int nc = WF_HALO_NC;
-    if (MODE == 2) {
-      halo_node_force(d, n, sep, vals);
-      nc = d.dim;
-    } else {
-      double s, sq, rs;
-      int cnt;
-      halo_node_sums(d, n, MODE == 0 ? d.vol_0 : d.vol, s, sq, rs, cnt);
-      if (MODE == 0) { vals[0] = (P.press == 3) ? sq : s; vals[1] = rs; vals[2] = (double)cnt; }
-      else { vals[0] = s; vals[1] = sq; nc = 2; }
-    }
-    double *dst = nb.dst + (long long)(seq & 1ull) * WF_HALO_NC * nb.count + j;
-    for (int c = 0; c < nc; c++) dst[(long long)c * nb.count] = vals[c];
-    __threadfence_system();
-  }
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    __threadfence();
-    const unsigned done = atomicAdd(nb.counter, 1u);
-    if (done == gridDim.x - 1) {
-      *nb.counter = 0u;
-      __threadfence_system();
-      st_release_sys(nb.flag, seq);
-    }
-  }
+  halo_send_cta<MODE>(d, P, sep, seq, blockIdx.y, blockIdx.x, gridDim.x);
 }
 
 __global__ void k_halo_wait(WfDev d, unsigned long long seq, unsigned long long timeout_ns) {
-  const int i = threadIdx.x;
-  if (i >= d.n_neigh) return;
-  // a timeout is sticky: comm_error stays set, later waits return at once (the state of the shared nodes is stale from
-  // the first missed exchange on), the non-finite flag is raised, and every host entry point that reads the engine
-  // (wf_get_array, wf_synchronize, wf_nonfinite_flag, wf_monitor_wait, wf_halo_status) reports the error
-  if (*(volatile int *)d.comm_error != 0) return;
-  const unsigned long long t0 = global_ns();
-  while (ld_acquire_sys(d.flags + i) < seq) {
-    if (global_ns() - t0 > timeout_ns) { atomicExch(d.comm_error, 1 + i); atomicExch(d.nonfinite, 1); break; }
-    __nanosleep(200);
-  }
+  halo_wait_cta(d, seq, timeout_ns);
 }
 
 template <int MODE>
 __global__ void __launch_bounds__(128) k_halo_finish(WfDev d, WfPar P, int parity) {
+  if (P.wait_seq) halo_wait_cta(d, P.wait_seq, P.wait_timeout_ns); // folded k_halo_wait
   const int u = blockIdx.x * blockDim.x + threadIdx.x;
   if (u >= d.n_uniq) return;
   const int n = d.hu_node[u];
@@ -1402,10 +1517,21 @@ static void l_predict(const WfDev &d, const WfPar &P, int with_bc, cudaStream_t 
   if (d.dim == 3) k_predict<3><<<cdiv(d.nn, TPB_N), TPB_N, 0, s>>>(d, P, with_bc);
   else k_predict<2><<<cdiv(d.nn, TPB_N), TPB_N, 0, s>>>(d, P, with_bc);
 }
+static void l_bc_patch_v(const WfDev &d, const int *row_node, int nrows, cudaStream_t s) {
+  if (nrows > 0) k_bc_patch_v<<<cdiv(nrows, 256), 256, 0, s>>>(d, row_node, nrows);
+}
+static void l_unpredict(const WfDev &d, const WfPar &P, cudaStream_t s) {
+  if (d.dim == 3) k_unpredict<3><<<cdiv(d.nn, 256), 256, 0, s>>>(d, P);
+  else k_unpredict<2><<<cdiv(d.nn, 256), 256, 0, s>>>(d, P);
+}
 static void l_impose_bc(const WfDev &d, int dim, int is_acc, double *arr, cudaStream_t s) {
   k_impose_bc<<<cdiv(d.nn, 256), 256, 0, s>>>(d, dim, is_acc, arr);
 }
 static void l_elem_vol(const WfDev &d, const WfPar &P, int et, int store_jac, cudaStream_t s) {
+  if (!store_jac && et == ET_HEX8 && d.blk_pad_b && !P.strict && P.variant[0] == 0) {
+    launch_pdl(k_elem_vol_brick<WF_BRICK_STRIDE>, cdiv(d.ne, WF_EBLK), WF_EBLK, (size_t)3 * WF_BRICK_STRIDE * 8, s, d, P);
+    return;
+  }
   if (!store_jac && P.variant[0] == 1) {
     const int stride = d.blk_pitch;
     ELEM_DISPATCH(et, k_elem_vol_staged<ET><<<cdiv(d.ne, WF_EBLK), WF_EBLK, Elem<ET>::D * stride * 8, s>>>(d, P, stride));
@@ -1417,7 +1543,7 @@ static void l_vol_from_detj(const WfDev &d, int et, cudaStream_t s) {
   ELEM_DISPATCH(et, k_vol_from_detj<ET><<<cdiv(d.ne, 256), 256, 0, s>>>(d));
 }
 static void l_node_vol(const WfDev &d, const WfPar &P, int mode, cudaStream_t s) {
-  int g = cdiv((long long)d.nslices * 32, TPB_N);
+  int g = cdiv((long long)d.nslices * 32, TPB_N) + ((mode == 1 || mode == 3) ? P.send_ctas : 0);
   switch (d.k) {
     // register cap for 5 resident CTAs (48 registers): 0.235 -> 0.192 ms on 10M hexes; 6 and 8 CTAs (spills) 0.214 ms
     case 8:
@@ -1431,7 +1557,7 @@ static void l_node_vol(const WfDev &d, const WfPar &P, int mode, cudaStream_t s)
 // the tile-reduced force path (WfDev::ftile): same eligibility as the regrouped hexa kernel, default variant only
 static int l_tile_forces(const WfDev &d, const WfPar &P, int separate_hg) {
   // 3D only: in 2D (1M quads) neither form of the tile reduction pays for itself (wf_engine.cu does not upload the tables)
-  return d.ftile && !separate_hg && d.dim == 3 && !P.strict && !P.thermal && (P.variant[2] == 0 || P.variant[2] == 6 || P.variant[2] == 7) &&
+  return d.ftile && !separate_hg && d.dim == 3 && !P.strict && !P.thermal && (P.variant[2] == 0 || P.variant[2] == 6 || P.variant[2] == 7 || (P.variant[2] >= 10 && P.variant[2] <= 11)) &&
          ((d.k == 8 && P.model < 2) || (d.k == 4 && d.tf_tab));
 }
 constexpr int BRICK_STRIDE = WF_BRICK_STRIDE, BRICK_WS = WF_BRICK_WS;
@@ -1441,8 +1567,13 @@ static void l_elem_main(const WfDev &d, const WfPar &P, int et, int separate_hg,
     if (d.blk_pad_b && P.variant[2] != 7) {
       constexpr size_t smem = ((size_t)7 * BRICK_STRIDE + (size_t)(hexfast::TPB / 32) * 3 * BRICK_WS) * 8;
       // measured (10M hexes): 4 resident CTAs at 128 registers 0.847 ms, 5 at 96 registers (72 B of spills) 0.910 ms
-      if (P.variant[2] == 6) launch_pdl(hexfast::k_elem_main_hex_brick<BRICK_STRIDE, BRICK_WS, 5>, g, hexfast::TPB, smem, s, d, P);
-      else launch_pdl(hexfast::k_elem_main_hex_brick<BRICK_STRIDE, BRICK_WS, 4>, g, hexfast::TPB, smem, s, d, P);
+      using namespace hexfast;
+      switch (P.variant[2]) {
+        case 6: launch_pdl(k_elem_main_hex_brick<BRICK_STRIDE, BRICK_WS, 5>, g, TPB, smem, s, d, P); break;
+        case 10: launch_pdl(k_elem_main_hex_brick<BRICK_STRIDE, BRICK_WS, 4, false, false>, g, TPB, smem, s, d, P); break;
+        case 11: launch_pdl(k_elem_main_hex_brick<BRICK_STRIDE, BRICK_WS, 4, true, true>, g, TPB, smem, s, d, P); break;
+        default: launch_pdl(k_elem_main_hex_brick<BRICK_STRIDE, BRICK_WS, 4>, g, TPB, smem, s, d, P); break;
+      }
       return;
     }
     const size_t smem = ((size_t)7 * stride + (size_t)(hexfast::TPB / 32) * 3 * d.tf_stride) * 8;
@@ -1481,13 +1612,13 @@ static void l_elem_main(const WfDev &d, const WfPar &P, int et, int separate_hg,
 }
 template <bool SEP, int U, int MINB = 1>
 static void node_update_t(const WfDev &d, const WfPar &P, int fuse, int phase, cudaStream_t s) {
-  int g = phase == 4 ? cdiv(std::max(d.n_uniq, 1), TPB_N) : cdiv((long long)d.nslices * 32, TPB_N);
+  int g = phase == 4 ? cdiv(std::max(d.n_uniq, 1), TPB_N) : cdiv((long long)d.nslices * 32, TPB_N) + (phase == 3 ? P.send_ctas : 0);
   if (d.dim == 3) launch_pdl(k_node_update<3, SEP, U, false, false, MINB>, g, TPB_N, 0, s, d, P, fuse, phase);
   else launch_pdl(k_node_update<2, SEP, U, false, false, MINB>, g, TPB_N, 0, s, d, P, fuse, phase);
 }
 static void l_node_update(const WfDev &d, const WfPar &P, int separate_hg, int fuse, int phase, cudaStream_t s) {
   if (l_tile_forces(d, P, separate_hg)) {
-    const int g = phase == 4 ? cdiv(std::max(d.n_uniq, 1), TPB_N) : cdiv((long long)d.nslices * 32, TPB_N);
+    const int g = phase == 4 ? cdiv(std::max(d.n_uniq, 1), TPB_N) : cdiv((long long)d.nslices * 32, TPB_N) + (phase == 3 ? P.send_ctas : 0);
     // measured on 10M hexes (tools/kbench.py): 5 resident CTAs (48 registers) + L2 prefetch of the state rows 0.60 ms;
     // 3 CTAs (67 registers) 0.66-0.75 ms; 6 CTAs (40 registers, spills) 0.61 ms; no prefetch 0.71 ms
     if (P.variant[3] == 5) k_node_update<3, false, 4, true, false, 5><<<g, TPB_N, 0, s>>>(d, P, fuse, phase);
@@ -1626,7 +1757,9 @@ static void l_preload(int et, int dim, int k) {
                 cudaFuncSetAttribute(k_elem_main<ET, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 7 * 1024 * 8);
                 touch(k_elem_main<ET, true, true>); touch(k_elem_main<ET, false, true>));
   touch(k_node_vol<8>); touch(k_node_vol<8, 5>); touch(k_node_vol<4, 5>); touch(k_node_vol<3, 5>);
+  touch(k_elem_vol_brick<WF_BRICK_STRIDE>);
   touch(hexfast::k_elem_main_hex_brick<BRICK_STRIDE, BRICK_WS, 4>); touch(hexfast::k_elem_main_hex_brick<BRICK_STRIDE, BRICK_WS, 5>);
+  touch(hexfast::k_elem_main_hex_brick<BRICK_STRIDE, BRICK_WS, 4, false, false>); touch(hexfast::k_elem_main_hex_brick<BRICK_STRIDE, BRICK_WS, 4, true, true>);
   touch(k_node_update<3, true, 4>); touch(k_node_update<3, false, 4>); touch(k_node_update<3, false, 4, false, false, 5>); touch(k_node_update<3, false, 2>); touch(k_node_update<3, false, 8>);
   touch(k_node_update<2, true, 4>); touch(k_node_update<2, false, 4>); touch(k_node_update<2, false, 4, false, false, 5>); touch(k_node_update<2, false, 2>); touch(k_node_update<2, false, 8>);
   touch(k_halo_send<0>); touch(k_halo_send<1>); touch(k_halo_send<2>); touch(k_halo_wait);
@@ -1646,6 +1779,6 @@ extern "C" const WfLaunch *WF_CAT(WF_NS, _table)() {
                              l_rebuild_sigma, l_energy, l_u_strain_rates, l_u_pressure, l_u_stress, l_u_artvisc,
                              l_u_forces, l_u_hourglass, l_u_nodal_vol, l_u_assembly, l_u_accel, l_u_corr_accvel,
                              l_u_axis, l_u_corr_pos, l_halo_send, l_halo_wait, l_halo_finish, l_preload, l_p_node, l_min_edge, l_max_vel, l_soa_to_aos,
-                             l_aos_to_soa, l_node_thermal, l_tile_forces};
+                             l_aos_to_soa, l_node_thermal, l_tile_forces, l_bc_patch_v, l_unpredict};
   return &t;
 }

@@ -41,6 +41,8 @@ struct WfLaunch {
   void (*aos_to_soa)(const double *aos, long long pitch, int nc, long long n, double *soa, const int *map, cudaStream_t);
   void (*node_thermal)(const WfDev &, const WfPar &, cudaStream_t);
   int (*tile_forces)(const WfDev &, const WfPar &, int separate_hg); /* does the step use WfDev::ftile instead of fsell? */
+  void (*bc_patch_v)(const WfDev &, const int *row_node, int nrows, cudaStream_t);
+  void (*unpredict)(const WfDev &, const WfPar &, cudaStream_t);
 };
 
 extern "C" const WfLaunch *wf_strict_table();

@@ -264,6 +264,13 @@ class Domain_d:
         """n fused time steps (rows 1-22 of the loop body, Solver_explicit.C:524-978)."""
         self._ck(self._lib.wf_step(self._h, int(n)))
 
+    def step_open(self, n=1):
+        """n steps, leaving the engine in predicted state (wf_step_open): for loops that call the engine once per step."""
+        self._ck(self._lib.wf_step_open(self._h, int(n)))
+
+    def step_close(self):
+        self._ck(self._lib.wf_step_close(self._h))
+
     def step_timed(self, n=1):
         """wf_step with per-kernel CUDA-event timing; returns ms for [predictor, E1, N1, E2, N2]."""
         ms = (C.c_float * 5)()
