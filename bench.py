@@ -512,8 +512,10 @@ def ours(args):
             cpu = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample", "same_config")}
         except Exception as ex:  # the checker is optional for the bench line
             cpu = {"value": None, "unit": "element-steps/s", "cores": 0, "kind": "port", "sample": f"unavailable: {ex}"}
-    # N = 1: E1, N1, E2, N2.  N > 1: + halo send / wait / finish after E1, send after E2, wait, node pass of the shared nodes
-    launches_per_step = 4 if world == 1 else 10
+    # N = 1: E1, N1, E2, N2.  N > 1 (peer transport, sends / waits folded into the node passes): + the nodal-sum finish of
+    # the shared nodes and the node pass of the shared nodes = 6; WF_HALO_FOLD=0 keeps send / wait kernels of their own = 10
+    folded = os.environ.get("WF_HALO_FOLD", "1") != "0" and args.halo == "peer"
+    launches_per_step = 4 if world == 1 else (6 if folded else 10)
     line = {
         "metric": "element-steps/s", "value": value, "unit": "element-steps/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong" if (world > 1 and args.cube) else "weak",

@@ -455,9 +455,7 @@ struct EmitTileC {
   }
 };
 
-// BATCH3: see EmitTileC.  LOOKAHEAD: besides the node list of the CTA that follows on this SM, ask L2 for that CTA's
-// node DATA (its list was requested one generation earlier, so reading it here is an L2 hit).
-template <int STRIDE, int WS, int MINB, bool BATCH3 = true, bool LOOKAHEAD = false>
+template <int STRIDE, int WS, int MINB, bool BATCH3 = true>
 __global__ void __launch_bounds__(TPB, MINB) k_elem_main_hex_brick(WfDev d, WfPar P) {
   extern __shared__ double sm[];
   pdl_trigger();
@@ -480,18 +478,8 @@ __global__ void __launch_bounds__(TPB, MINB) k_elem_main_hex_brick(WfDev d, WfPa
   const unsigned r2s = __ldg(d.tf_r2s + (long long)b * TPB + t); // rank -> slot of this warp's tile, used at the very end
   // the node list of the CTA that will follow this one on the SM: ask L2 for it now (the first thing that CTA waits for)
   if (t < (STRIDE * 4 + 127) / 128) {
-    const long long nb = (long long)b + (LOOKAHEAD ? 2 : 1) * (long long)d.cta_lookahead;
-    if (nb * TPB < d.ne) prefetch_l2(reinterpret_cast<const char *>(d.blk_pad_b + nb * STRIDE) + t * 128);
-  }
-  int gnext[NQ];
-  if (LOOKAHEAD) {
     const long long nb = (long long)b + d.cta_lookahead;
-    const bool have = nb * TPB < d.ne;
-#pragma unroll
-    for (int q = 0; q < NQ; q++) {
-      const int i = q * TPB + t;
-      gnext[q] = (have && i < STRIDE) ? __ldg(d.blk_pad_b + nb * STRIDE + i) : -1;
-    }
+    if (nb * TPB < d.ne) prefetch_l2(reinterpret_cast<const char *>(d.blk_pad_b + nb * STRIDE) + t * 128);
   }
   pdl_wait(); // everything above reads constant mesh tables only
   double tau[6];
@@ -514,17 +502,6 @@ __global__ void __launch_bounds__(TPB, MINB) k_elem_main_hex_brick(WfDev d, WfPa
     }
   }
   cp_async_commit();
-  if (LOOKAHEAD) {
-#pragma unroll
-    for (int q = 0; q < NQ; q++) {
-      const int gq = gnext[q];
-      if (gq >= 0) {
-#pragma unroll
-        for (int c = 0; c < 3; c++) { prefetch_l2(d.x + (long long)c * d.np + gq); prefetch_l2(d.v + (long long)c * d.np + gq); }
-        prefetch_l2(d.nodal_p + gq);
-      }
-    }
-  }
   const int lane = t & 31, warp = t >> 5;
   double *acc = sm + 7 * STRIDE + warp * 3 * WS;
 #pragma unroll

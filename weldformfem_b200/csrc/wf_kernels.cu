@@ -1557,7 +1557,7 @@ static void l_node_vol(const WfDev &d, const WfPar &P, int mode, cudaStream_t s)
 // the tile-reduced force path (WfDev::ftile): same eligibility as the regrouped hexa kernel, default variant only
 static int l_tile_forces(const WfDev &d, const WfPar &P, int separate_hg) {
   // 3D only: in 2D (1M quads) neither form of the tile reduction pays for itself (wf_engine.cu does not upload the tables)
-  return d.ftile && !separate_hg && d.dim == 3 && !P.strict && !P.thermal && (P.variant[2] == 0 || P.variant[2] == 6 || P.variant[2] == 7 || (P.variant[2] >= 10 && P.variant[2] <= 11)) &&
+  return d.ftile && !separate_hg && d.dim == 3 && !P.strict && !P.thermal && (P.variant[2] == 0 || P.variant[2] == 7) &&
          ((d.k == 8 && P.model < 2) || (d.k == 4 && d.tf_tab));
 }
 constexpr int BRICK_STRIDE = WF_BRICK_STRIDE, BRICK_WS = WF_BRICK_WS;
@@ -1566,14 +1566,10 @@ static void l_elem_main(const WfDev &d, const WfPar &P, int et, int separate_hg,
     const int stride = d.blk_pitch, g = cdiv(d.ne, hexfast::TPB);
     if (d.blk_pad_b && P.variant[2] != 7) {
       constexpr size_t smem = ((size_t)7 * BRICK_STRIDE + (size_t)(hexfast::TPB / 32) * 3 * BRICK_WS) * 8;
-      // measured (10M hexes): 4 resident CTAs at 128 registers 0.847 ms, 5 at 96 registers (72 B of spills) 0.910 ms
-      using namespace hexfast;
-      switch (P.variant[2]) {
-        case 6: launch_pdl(k_elem_main_hex_brick<BRICK_STRIDE, BRICK_WS, 5>, g, TPB, smem, s, d, P); break;
-        case 10: launch_pdl(k_elem_main_hex_brick<BRICK_STRIDE, BRICK_WS, 4, false, false>, g, TPB, smem, s, d, P); break;
-        case 11: launch_pdl(k_elem_main_hex_brick<BRICK_STRIDE, BRICK_WS, 4, true, true>, g, TPB, smem, s, d, P); break;
-        default: launch_pdl(k_elem_main_hex_brick<BRICK_STRIDE, BRICK_WS, 4>, g, TPB, smem, s, d, P); break;
-      }
+      // 4 resident CTAs at 128 registers; measured alternatives: 5 CTAs at 96 registers (80 B of spills)
+      // 0.910 vs 0.847 ms, L2 look-ahead of the next CTA's node data 0.787 vs 0.791 ms, a persistent double-buffered
+      // form 1.07 vs 0.79 ms
+      launch_pdl(hexfast::k_elem_main_hex_brick<BRICK_STRIDE, BRICK_WS, 4>, g, hexfast::TPB, smem, s, d, P);
       return;
     }
     const size_t smem = ((size_t)7 * stride + (size_t)(hexfast::TPB / 32) * 3 * d.tf_stride) * 8;
@@ -1591,7 +1587,6 @@ static void l_elem_main(const WfDev &d, const WfPar &P, int et, int separate_hg,
   if (et == ET_TET4 && l_tile_forces(d, P, separate_hg)) {
     const size_t smem = (size_t)(TPB_E / 32) * (12 * 32 + (d.tf_tpitch + 7) / 8) * 8;
     if (P.variant[2] == 7) k_elem_main<ET_TET4, false, false, false, true><<<cdiv(d.ne, TPB_E), TPB_E, smem, s>>>(d, P, 0);
-    else if (P.variant[2] == 6) k_elem_main<ET_TET4, false, false, false, true, 6><<<cdiv(d.ne, TPB_E), TPB_E, smem, s>>>(d, P, 0);
     else launch_pdl(k_elem_main<ET_TET4, false, false, false, true, 5>, cdiv(d.ne, TPB_E), TPB_E, smem, s, d, P, 0);
     return;
   }
@@ -1749,7 +1744,7 @@ static void l_preload(int et, int dim, int k) {
   cudaFuncSetAttribute(hexfast::k_elem_main_hex_staged, cudaFuncAttributeMaxDynamicSharedMemorySize, 7 * 1024 * 8);
   touch(hexfast::k_elem_main_hex_staged);
   cudaFuncSetAttribute(hexfast::k_elem_main_hex_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, (7 * 1024 + 12 * 256) * 8);
-  touch(hexfast::k_elem_main_hex_tile); touch(k_elem_main<ET_TET4, false, false, false, true>); touch(k_elem_main<ET_TET4, false, false, false, true, 5>); touch(k_elem_main<ET_TET4, false, false, false, true, 6>);
+  touch(hexfast::k_elem_main_hex_tile); touch(k_elem_main<ET_TET4, false, false, false, true>); touch(k_elem_main<ET_TET4, false, false, false, true, 5>);
   touch(k_node_update<3, false, 4, true, false, 5>); touch(k_node_update<3, false, 4, true, true, 6>); touch(k_node_update<3, false, 4, true, true, 5>);
   touch(k_predict<2>); touch(k_predict<3>); touch(k_impose_bc);
   ELEM_DISPATCH(et, touch(k_elem_vol<ET>); touch(k_elem_main<ET, true, false>); touch(k_elem_main<ET, false, false>);
@@ -1758,8 +1753,7 @@ static void l_preload(int et, int dim, int k) {
                 touch(k_elem_main<ET, true, true>); touch(k_elem_main<ET, false, true>));
   touch(k_node_vol<8>); touch(k_node_vol<8, 5>); touch(k_node_vol<4, 5>); touch(k_node_vol<3, 5>);
   touch(k_elem_vol_brick<WF_BRICK_STRIDE>);
-  touch(hexfast::k_elem_main_hex_brick<BRICK_STRIDE, BRICK_WS, 4>); touch(hexfast::k_elem_main_hex_brick<BRICK_STRIDE, BRICK_WS, 5>);
-  touch(hexfast::k_elem_main_hex_brick<BRICK_STRIDE, BRICK_WS, 4, false, false>); touch(hexfast::k_elem_main_hex_brick<BRICK_STRIDE, BRICK_WS, 4, true, true>);
+  touch(hexfast::k_elem_main_hex_brick<BRICK_STRIDE, BRICK_WS, 4>);
   touch(k_node_update<3, true, 4>); touch(k_node_update<3, false, 4>); touch(k_node_update<3, false, 4, false, false, 5>); touch(k_node_update<3, false, 2>); touch(k_node_update<3, false, 8>);
   touch(k_node_update<2, true, 4>); touch(k_node_update<2, false, 4>); touch(k_node_update<2, false, 4, false, false, 5>); touch(k_node_update<2, false, 2>); touch(k_node_update<2, false, 8>);
   touch(k_halo_send<0>); touch(k_halo_send<1>); touch(k_halo_send<2>); touch(k_halo_wait);
