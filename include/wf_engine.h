@@ -84,8 +84,9 @@ int wf_set_mesh(wf_engine *, int n_nodes, int n_elems, const double *x /*N_n*dim
 int wf_gen_box(wf_engine *, const double V[3], const double L[3], double r, int tritet);
 int wf_get_counts(wf_engine *, int *n_nodes, int *n_elems, int *nodel_total);
 /* Internal element order used by the NEXT wf_set_mesh / wf_gen_box / wf_set_mesh_partition (see wf_host_elem_order):
- * 0 = the caller's numbering, 1 = Morton order (default; the environment variable WF_ELEM_ORDER overrides the
- * default).  Every array that crosses this ABI stays in the caller's numbering whatever the mode; wf_device_ptr
+ * 0 = the caller's numbering, 1 = Morton order.  Default: 1 for hexahedra, 0 for every other element type (measured:
+ * tetrahedra and quadrilaterals gather per element and lose from the reordering); the environment variable
+ * WF_ELEM_ORDER overrides the default.  Every array that crosses this ABI stays in the caller's numbering whatever the mode; wf_device_ptr
  * of an element array exposes the internal order ("elem_perm" via wf_get_array gives perm[internal] = user). */
 int wf_set_elem_order(wf_engine *, int mode);
 int wf_set_axisymm_vol_weight(wf_engine *, int on); /* setAxiSymm(vol_weight), Domain_d.h:666 */

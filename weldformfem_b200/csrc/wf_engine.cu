@@ -150,9 +150,10 @@ static int upload_mesh(wf_engine *E, int nn, int ne, const double *x, const unsi
   E->perm.clear(); E->iperm.clear();
   std::vector<unsigned> el_int;
   const unsigned *eli = elnod; // connectivity in internal order, reference layout [e*k + ln]
-  if (E->order_mode != 0 && ne > 1) {
+  const int order = E->order_mode >= 0 ? E->order_mode : (k == 8 ? 1 : 0);
+  if (order != 0 && ne > 1) {
     E->perm.resize(ne); E->iperm.resize(ne);
-    if (wf_host_elem_order(dim, k, nn, ne, x, elnod, E->order_mode, E->perm.data())) FAIL("element ordering failed");
+    if (wf_host_elem_order(dim, k, nn, ne, x, elnod, order, E->perm.data())) FAIL("element ordering failed");
     bool ident = true;
     for (int e = 0; e < ne; e++) { E->iperm[E->perm[e]] = e; ident = ident && E->perm[e] == e; }
     if (ident) { E->perm.clear(); E->iperm.clear(); }
