@@ -415,3 +415,23 @@ def test_open_stepping_with_per_step_bc_values_and_monitor(key, oracle_port):
     eng2.step(1)
     ref2.step(4)
     compare(eng2, ref2, STATE + ["u_dt"], 1e-9, f"{key} open then closed")
+
+
+@pytest.mark.parametrize("strict", [True, False], ids=["strict", "fast"])
+def test_many_cta_waves_against_the_compiled_reference(strict, oracle_ref):
+    """262 144 hexes (64^3: 2 048 CTAs of the element passes = several waves on 148 SMs, ragged Morton bricks at the mesh
+    faces, tail tiles) with hourglass 0.06, 50 steps into the plastic range, against the reference compiled from its own
+    sources (oracle/_ref, all host threads) — the brick form of E1 / E2, the tile partials and the node passes on a mesh
+    that does not fit one wave."""
+    case = R(cases.c3_hexes(64), top_vel=-200.0)
+    oracle_ref.set_threads(0)
+    eng, ref = run_pair(case, oracle_ref, 0, strict)
+    ref.step(1)
+    eng.step(1)
+    compare(eng, ref, STATE, TOL_STRICT if strict else TOL_1STEP, "64^3 hexes, 1 step")
+    ref.step(49)
+    eng.step(49)
+    assert (ref.get("pl_strain") > 0).mean() > 0.05
+    w = compare(eng, ref, STATE, 1e-9 if strict else 1e-7, "64^3 hexes, 50 steps")
+    report(f"hex64_50_steps_{'strict' if strict else 'fast'}", w)
+    assert not eng.nonfinite_flag()

@@ -383,13 +383,15 @@ WF_DI void halo_send_cta(const WfDev &d, const WfPar &P, int sep, unsigned long 
 // ---------------------------------------------------------------------------------------------
 //   mode 3 (step)  : mode 1 + UpdatePrediction and ImposeBCV of the node (Domain_d.C:961-974): the first step of a
 //                    batch has no previous node pass to carry its predictor (WF_FAST; strict runs k_predict)
-template <int K, int MINB = 1>
+// HALO: instantiation for partitioned meshes (carries the folded halo send; kept out of the single-GPU kernel, which is
+// register-capped)
+template <int K, int MINB = 1, bool HALO = false>
 __global__ void __launch_bounds__(TPB_N, MINB) k_node_vol(WfDev d, WfPar P, int mode_in) {
   const bool with_predict = mode_in == 3;
   const int mode = with_predict ? 1 : mode_in;
   pdl_trigger();
   int bx = blockIdx.x;
-  if (mode == 1 && P.send_ctas > 0) {
+  if (HALO && mode == 1 && P.send_ctas > 0) {
     // multi-GPU: the first CTAs of the launch send this rank's partial volume sums of the shared nodes (they depend on
     // the element volumes only), so the transfer travels while the rest of the grid forms the nodal sums
     if (bx < P.send_ctas) {
@@ -776,12 +778,12 @@ WF_DI void warp_add(double *dst, double x) {
   }
   if (lane == __ffs(mask) - 1) atomicAdd(dst, t);
 }
-template <int D, bool SEPARATE_HG, int UNROLL, bool TILE_F = false, bool PREFETCH = false, int MINB = 1>
+template <int D, bool SEPARATE_HG, int UNROLL, bool TILE_F = false, bool PREFETCH = false, int MINB = 1, bool HALO = false>
 __global__ void __launch_bounds__(TPB_N, MINB) k_node_update(WfDev d, WfPar P, int fuse_flags, int phase) {
   const bool fuse_predictor = fuse_flags & 1, udt_recompute = fuse_flags & 2, udt_skip_store = fuse_flags & 4;
   pdl_trigger();
   int bx = blockIdx.x;
-  if (phase == 3 && P.send_ctas > 0) {
+  if (HALO && phase == 3 && P.send_ctas > 0) {
     // multi-GPU: the first CTAs of the launch send this rank's partial forces of the shared nodes; the rest of the grid
     // integrates the nodes this rank does not share while they travel
     if (bx < P.send_ctas) {
@@ -791,7 +793,7 @@ __global__ void __launch_bounds__(TPB_N, MINB) k_node_update(WfDev d, WfPar P, i
     }
     bx -= P.send_ctas;
   }
-  if (phase == 4 && P.wait_seq) halo_wait_cta(d, P.wait_seq, P.wait_timeout_ns); // folded k_halo_wait (before any early exit)
+  if (HALO && phase == 4 && P.wait_seq) halo_wait_cta(d, P.wait_seq, P.wait_timeout_ns); // folded k_halo_wait (before any early exit)
   int n = bx * blockDim.x + threadIdx.x;
   if (phase == 4) { // shared nodes only, one thread per unique shared node (after the halo wait)
     if (n >= d.n_uniq) return;
@@ -1544,14 +1546,22 @@ static void l_vol_from_detj(const WfDev &d, int et, cudaStream_t s) {
 }
 static void l_node_vol(const WfDev &d, const WfPar &P, int mode, cudaStream_t s) {
   int g = cdiv((long long)d.nslices * 32, TPB_N) + ((mode == 1 || mode == 3) ? P.send_ctas : 0);
+  const bool halo = d.n_neigh > 0;
   switch (d.k) {
     // register cap for 5 resident CTAs (48 registers): 0.235 -> 0.192 ms on 10M hexes; 6 and 8 CTAs (spills) 0.214 ms
     case 8:
-      if (P.variant[1] == 5) launch_pdl(k_node_vol<8>, g, TPB_N, 0, s, d, P, mode);
+      if (halo) launch_pdl(k_node_vol<8, 5, true>, g, TPB_N, 0, s, d, P, mode);
+      else if (P.variant[1] == 5) launch_pdl(k_node_vol<8>, g, TPB_N, 0, s, d, P, mode);
       else launch_pdl(k_node_vol<8, 5>, g, TPB_N, 0, s, d, P, mode);
       break;
-    case 4: launch_pdl(k_node_vol<4, 5>, g, TPB_N, 0, s, d, P, mode); break;
-    default: launch_pdl(k_node_vol<3, 5>, g, TPB_N, 0, s, d, P, mode); break;
+    case 4:
+      if (halo) launch_pdl(k_node_vol<4, 5, true>, g, TPB_N, 0, s, d, P, mode);
+      else launch_pdl(k_node_vol<4, 5>, g, TPB_N, 0, s, d, P, mode);
+      break;
+    default:
+      if (halo) launch_pdl(k_node_vol<3, 5, true>, g, TPB_N, 0, s, d, P, mode);
+      else launch_pdl(k_node_vol<3, 5>, g, TPB_N, 0, s, d, P, mode);
+      break;
   }
 }
 // the tile-reduced force path (WfDev::ftile): same eligibility as the regrouped hexa kernel, default variant only
@@ -1608,6 +1618,11 @@ static void l_elem_main(const WfDev &d, const WfPar &P, int et, int separate_hg,
 template <bool SEP, int U, int MINB = 1>
 static void node_update_t(const WfDev &d, const WfPar &P, int fuse, int phase, cudaStream_t s) {
   int g = phase == 4 ? cdiv(std::max(d.n_uniq, 1), TPB_N) : cdiv((long long)d.nslices * 32, TPB_N) + (phase == 3 ? P.send_ctas : 0);
+  if (d.n_neigh > 0) { // partitioned mesh: the instantiation that carries the folded halo send / wait
+    if (d.dim == 3) launch_pdl(k_node_update<3, SEP, U, false, false, MINB, true>, g, TPB_N, 0, s, d, P, fuse, phase);
+    else launch_pdl(k_node_update<2, SEP, U, false, false, MINB, true>, g, TPB_N, 0, s, d, P, fuse, phase);
+    return;
+  }
   if (d.dim == 3) launch_pdl(k_node_update<3, SEP, U, false, false, MINB>, g, TPB_N, 0, s, d, P, fuse, phase);
   else launch_pdl(k_node_update<2, SEP, U, false, false, MINB>, g, TPB_N, 0, s, d, P, fuse, phase);
 }
@@ -1616,7 +1631,8 @@ static void l_node_update(const WfDev &d, const WfPar &P, int separate_hg, int f
     const int g = phase == 4 ? cdiv(std::max(d.n_uniq, 1), TPB_N) : cdiv((long long)d.nslices * 32, TPB_N) + (phase == 3 ? P.send_ctas : 0);
     // measured on 10M hexes (tools/kbench.py): 5 resident CTAs (48 registers) + L2 prefetch of the state rows 0.60 ms;
     // 3 CTAs (67 registers) 0.66-0.75 ms; 6 CTAs (40 registers, spills) 0.61 ms; no prefetch 0.71 ms
-    if (P.variant[3] == 5) k_node_update<3, false, 4, true, false, 5><<<g, TPB_N, 0, s>>>(d, P, fuse, phase);
+    if (d.n_neigh > 0) k_node_update<3, false, 4, true, true, 5, true><<<g, TPB_N, 0, s>>>(d, P, fuse, phase);
+    else if (P.variant[3] == 5) k_node_update<3, false, 4, true, false, 5><<<g, TPB_N, 0, s>>>(d, P, fuse, phase);
     else if (P.variant[3] == 7) k_node_update<3, false, 4, true, true, 6><<<g, TPB_N, 0, s>>>(d, P, fuse, phase);
     else k_node_update<3, false, 4, true, true, 5><<<g, TPB_N, 0, s>>>(d, P, fuse, phase);
     return;
@@ -1752,6 +1768,12 @@ static void l_preload(int et, int dim, int k) {
                 cudaFuncSetAttribute(k_elem_main<ET, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 7 * 1024 * 8);
                 touch(k_elem_main<ET, true, true>); touch(k_elem_main<ET, false, true>));
   touch(k_node_vol<8>); touch(k_node_vol<8, 5>); touch(k_node_vol<4, 5>); touch(k_node_vol<3, 5>);
+  touch(k_node_vol<8, 5, true>); touch(k_node_vol<4, 5, true>); touch(k_node_vol<3, 5, true>);
+  touch(k_node_update<3, false, 4, true, true, 5, true>);
+  touch(k_node_update<3, true, 4, false, false, 1, true>); touch(k_node_update<3, false, 4, false, false, 5, true>); touch(k_node_update<3, false, 4, false, false, 1, true>);
+  touch(k_node_update<3, false, 2, false, false, 1, true>); touch(k_node_update<3, false, 8, false, false, 1, true>);
+  touch(k_node_update<2, true, 4, false, false, 1, true>); touch(k_node_update<2, false, 4, false, false, 5, true>); touch(k_node_update<2, false, 4, false, false, 1, true>);
+  touch(k_node_update<2, false, 2, false, false, 1, true>); touch(k_node_update<2, false, 8, false, false, 1, true>);
   touch(k_elem_vol_brick<WF_BRICK_STRIDE>);
   touch(hexfast::k_elem_main_hex_brick<BRICK_STRIDE, BRICK_WS, 4>);
   touch(k_node_update<3, true, 4>); touch(k_node_update<3, false, 4>); touch(k_node_update<3, false, 4, false, false, 5>); touch(k_node_update<3, false, 2>); touch(k_node_update<3, false, 8>);
