@@ -390,10 +390,22 @@ def ours(args):
         dom.halo_status()
 
     # ---- per-kernel device times (CUDA events around every launch), single GPU ----------------------
-    kms = None
+    kms, timeline = None, None
     if world == 1:
         dom.step_timed(3)
         kms = [t / args.steps for t in dom.step_timed(args.steps)]
+    elif args.halo == "peer":
+        # where a distributed step spends its time: an event after each of its launches, max over ranks per slot.  The
+        # folded waits sit at the head of "shared-node sums" and "N2 shared nodes": a late neighbour shows up there.
+        dom.step_timed(3)
+        kt = torch.tensor(dom.step_timed(args.steps), device="cuda", dtype=torch.float64) / args.steps
+        dist.all_reduce(kt, op=dist.ReduceOp.MAX)
+        kt = [float(v) for v in kt.tolist()]
+        timeline = {"unit": "ms per step, max over ranks", "E1": kt[1], "N1 (+ volume-partial send)": kt[2],
+                    "shared-node sums (+ wait for exchange 1)": kt[5], "E2": kt[3],
+                    "N2 of the nodes not shared (+ force-partial send)": kt[4],
+                    "N2 of the shared nodes (+ wait for exchange 2)": kt[6], "halo kernels of their own": kt[7],
+                    "sum": sum(kt[1:8])}
 
     # ---- e2e: the call sequence a host solver loop makes through the C ABI with HOST buffers ----------
     # every step: new prescribed-velocity values for the moving plane (H2D from host memory via wf_set_bc_values: pinned
@@ -439,7 +451,7 @@ def ours(args):
         other = []
         for k2, n2, label, pre, tv in (("tet", 26, "configs[1] size: 105 456 constant-stress tets (structured 6-tet split of a 26^3 box)", 400, -10.0),
                                        ("tet", 118, "9.86 M tets (118^3 x 6)", 1200, -25.0),
-                                       ("quad", 1000, "configs[3]: 1 M axisymmetric quads with hourglass", 3000, -20.0)):
+                                       ("quad", 1000, "configs[3]: 1 M axisymmetric quads with hourglass", 6000, -10.0)):
             try:
                 other.append(side_config(torch, stream, local, k2, n2, label, pre, tv))
             except Exception as ex:
@@ -542,6 +554,8 @@ def ours(args):
         "gpu_launches": launches_per_step * args.steps,
         "clocks": clocks,
     }
+    if timeline is not None:
+        line["timeline"] = timeline
     if other is not None:
         line["other_configs"] = other
     if parity is not None:

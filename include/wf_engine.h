@@ -162,10 +162,13 @@ int wf_set_dt(wf_engine *, double dt);
  * wf_monitor_wait returns the oldest pending result (at most two pending) */
 int wf_monitor_async(wf_engine *);
 int wf_monitor_wait(wf_engine *, double *Ekin, int *nonfinite);
-/* profiling / tuning hooks (no reference counterpart): wf_step with CUDA events around every launch,
+/* profiling / tuning hooks (no reference counterpart): wf_step with a CUDA event after every launch,
  * ms[0..4] += device time of predictor, E1 (element volume), N1 (nodal sums), E2 (main element pass),
- * N2 (assembly + integration); and selection of an alternative implementation of one of the four kernels */
-int wf_step_timed(wf_engine *, int nsteps, float *ms5);
+ * N2 (assembly + integration; partitioned mesh: the nodes this rank does not share); partitioned mesh, peer transport:
+ * ms[5] += nodal sums of the shared nodes, ms[6] += N2 of the shared nodes (both start by waiting for the neighbours, so
+ * they show a neighbour's lateness), ms[7] += halo kernels of their own (WF_HALO_FOLD=0).  ms has 8 entries.
+ * wf_set_variant: selection of an alternative implementation of one of the four kernels */
+int wf_step_timed(wf_engine *, int nsteps, float *ms8);
 int wf_set_variant(wf_engine *, int kernel /*0..3 = E1,N1,E2,N2*/, int variant);
 
 /* 1:1 unfused entry points for parity bisecting; names = Domain_d members */

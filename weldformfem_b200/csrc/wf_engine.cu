@@ -850,6 +850,18 @@ static int fuse_flags(const wf_engine *E, bool last) {
   return f;
 }
 
+// wf_step_timed: an event after the launch(es) just enqueued; tags: 0 predictor, 1 E1, 2 N1 (+ folded halo send), 3 E2,
+// 4 N2 (single GPU: the whole node pass; partitioned: the nodes this rank does not share, + folded send), 5 nodal sums of
+// the shared nodes (+ folded wait), 6 N2 of the shared nodes (+ folded wait), 7 halo kernels of their own
+static inline void tmark(wf_engine *E, int tag) {
+  if (!E->tm_ev) return;
+  cudaEvent_t x;
+  cudaEventCreate(&x);
+  cudaEventRecord(x, E->stream);
+  E->tm_ev->push_back(x);
+  E->tm_tag->push_back(tag);
+}
+
 // one explicit step = stages 0..2 (Solver_explicit.C:524-978, rows 1-22)
 static int step_stage(wf_engine *E, int stage, bool last) {
   WfDev &d = E->d;
@@ -859,23 +871,26 @@ static int step_stage(wf_engine *E, int stage, bool last) {
     if (wf_contact_step_begin(E)) return 1;      // CalcExtFaceAreas every 10th step (Solver_explicit.C:445-450)
     // the batch's first predictor: its own kernel (strict) or folded into the nodal-sum pass (fast)
     const bool fold = !E->predicted && !E->strict;
-    if (!E->predicted && E->strict) E->L->predict(d, P, 1, E->stream);
+    if (!E->predicted && E->strict) { E->L->predict(d, P, 1, E->stream); tmark(E, 0); }
     E->L->elem_vol(d, P, E->et, 0, E->stream);
+    tmark(E, 1);
     // the partial volume sums of the shared nodes depend on E1 only: they are sent BEFORE the nodal sums are formed
     // (first CTAs of the N1 launch, or a kernel of their own), so the transfer and the neighbours' flags travel
     // while N1 runs
     const bool fold_halo = halo_folded(E);
     if (fold_halo) halo_send_arm(E);
-    else if (E->distributed) halo_send(E, 1);
+    else if (E->distributed) { halo_send(E, 1); tmark(E, 7); }
     E->L->node_vol(d, P, fold ? 3 : 1, E->stream);
+    tmark(E, 2);
     halo_disarm(E);
   } else if (stage == 1) {
     const bool fold_halo = halo_folded(E);
     if (fold_halo) halo_wait_arm(E);
-    if (E->distributed) E->L->halo_finish(d, P, 1, P.halo_parity, E->stream);
+    if (E->distributed) { E->L->halo_finish(d, P, 1, P.halo_parity, E->stream); tmark(E, 5); }
     halo_disarm(E);
     E->L->elem_main(d, P, E->et, sep, E->stream);
-    if (E->distributed && !fold_halo) halo_send(E, 2);
+    tmark(E, 3);
+    if (E->distributed && !fold_halo) { halo_send(E, 2); tmark(E, 7); }
   } else {
     if (wf_contact_forces(E)) return 1;          // CalcContactForces (Solver_explicit.C:769-770)
     // (wf_step_open always forms it: in predicted state the corrected velocities are gone afterwards)
@@ -893,14 +908,19 @@ static int step_stage(wf_engine *E, int stage, bool last) {
       if (halo_folded(E)) {
         halo_send_arm(E);                        // first CTAs of the phase-3 launch send the force partials
         E->L->node_update(d, P, sep, fuse_flags(E, last), 3, E->stream);
+        tmark(E, 4);
         halo_disarm(E);
         halo_wait_arm(E);                        // phase 4 waits for the neighbours itself
         E->L->node_update(d, P, sep, fuse_flags(E, last), 4, E->stream);
+        tmark(E, 6);
         halo_disarm(E);
       } else {
         E->L->node_update(d, P, sep, fuse_flags(E, last), 3, E->stream);
+        tmark(E, 4);
         halo_wait(E);
+        tmark(E, 7);
         E->L->node_update(d, P, sep, fuse_flags(E, last), 4, E->stream);
+        tmark(E, 6);
       }
     } else {
       E->L->node_update(d, P, sep, fuse_flags(E, last), 0, E->stream);
@@ -908,6 +928,7 @@ static int step_stage(wf_engine *E, int stage, bool last) {
     d.ekin_acc = nullptr;
     if (wf_contact_step_end(E)) return 1;        // rigid surfaces: ramp, Move, normals, plane coefficients (:981-1005)
     if (P.thermal) { E->L->node_thermal(d, P, E->stream); P.dtedt_cur ^= 1; }  // ThermalCalcs, node part (:1008-1012)
+    if (!(E->distributed && E->transport == 0)) tmark(E, 4);
     E->predicted = !last || E->open_mode;
     E->udt_valid = !E->predicted;
     P.xmin_cur ^= 1;
@@ -921,7 +942,7 @@ static int step_once(wf_engine *E, bool last) {
   for (int st = 0; st < 3; st++) {
     if (step_stage(E, st, last)) return 1;
     // stage 2 waits for the forces itself; with the folded exchange the consumers wait themselves
-    if (E->distributed && st < 2 && !(st == 1 && E->transport == 0) && !halo_folded(E)) halo_wait(E);
+    if (E->distributed && st < 2 && !(st == 1 && E->transport == 0) && !halo_folded(E)) { halo_wait(E); tmark(E, 7); }
   }
   return 0;
 }
@@ -990,49 +1011,27 @@ extern "C" int wf_set_variant(wf_engine *E, int kernel, int variant) { WF_NULLCH
   return 0;
 }
 
-// same as wf_step on one GPU, with CUDA events around every launch; ms[0..4] += time of predictor, E1, N1, E2, N2
+// wf_step with a CUDA event after every launch; ms[0..7] += predictor, E1, N1, E2, N2, and on a partitioned mesh: nodal
+// sums of the shared nodes, N2 of the shared nodes, halo kernels of their own (see tmark; folded sends / waits are part
+// of the launch that carries them, so a neighbour's lateness shows up in slots 5 and 6).  Peer transport or one GPU.
 extern "C" int wf_step_timed(wf_engine *E, int nsteps, float *ms) { WF_NULLCHK(E);
   if (step_prologue(E)) return 1;
-  NEED(!E->distributed, "wf_step_timed is a single-GPU profiling hook");
   NEED(ms, "null output");
-  WfDev &d = E->d;
-  WfPar &P = E->P;
-  const int sep = E->strict ? 1 : 0;
   std::vector<cudaEvent_t> ev;
   std::vector<int> tag;
-  auto mark = [&](int t) {
-    cudaEvent_t x;
-    cudaEventCreate(&x);
-    cudaEventRecord(x, E->stream);
-    ev.push_back(x);
-    tag.push_back(t);
-  };
-  mark(-1);
-  for (int s = 0; s < nsteps; s++) {
-    const bool last = (s == nsteps - 1);
-    if (wf_contact_step_begin(E)) return 1;
-    const bool fold = !E->predicted && !E->strict;
-    if (!E->predicted && E->strict) { E->L->predict(d, P, 1, E->stream); mark(0); }
-    E->L->elem_vol(d, P, E->et, 0, E->stream); mark(1);
-    E->L->node_vol(d, P, fold ? 3 : 1, E->stream); mark(2);
-    E->L->elem_main(d, P, E->et, sep, E->stream); mark(3);
-    if (wf_contact_forces(E)) return 1;
-    E->L->node_update(d, P, sep, fuse_flags(E, last), 0, E->stream);
-    if (wf_contact_step_end(E)) return 1;
-    if (P.thermal) { E->L->node_thermal(d, P, E->stream); P.dtedt_cur ^= 1; }
-    mark(4);
-    E->predicted = !last;
-    P.xmin_cur ^= 1;
-    E->time += P.dt;
-    E->step_count++;
-  }
-  CK(cudaStreamSynchronize(E->stream));
-  for (size_t i = 1; i < ev.size(); i++) {
+  E->tm_ev = &ev; E->tm_tag = &tag;
+  tmark(E, -1);
+  int rc = 0;
+  for (int s = 0; s < nsteps && !rc; s++) rc = step_once(E, s == nsteps - 1);
+  E->tm_ev = nullptr; E->tm_tag = nullptr;
+  if (!rc && cudaStreamSynchronize(E->stream) != cudaSuccess) rc = 1;
+  for (size_t i = 1; i < ev.size() && !rc; i++) {
     float t = 0.f;
     cudaEventElapsedTime(&t, ev[i - 1], ev[i]);
     ms[tag[i]] += t;
   }
   for (auto x : ev) cudaEventDestroy(x);
+  if (rc) { if (E->err.empty()) E->err = "wf_step_timed failed"; return 1; }
   return step_epilogue(E, "wf_step_timed");
 }
 

@@ -59,6 +59,9 @@ struct wf_engine {
   cudaEvent_t bc_at_ev[2] = {nullptr, nullptr}, bc_copy_ev = nullptr;
   long bc_set_calls = 0;
   int *bc_row_node_d = nullptr;            // node of every BC row (k_bc_patch_v)
+  // wf_step_timed: when set, step_stage records a CUDA event after every launch (tag = slot of the caller's ms array)
+  std::vector<cudaEvent_t> *tm_ev = nullptr;
+  std::vector<int> *tm_tag = nullptr;
   bool open_mode = false;                  // wf_step_open: the call's last node pass also runs the next predictor
   bool udt_valid = true;                   // "u_dt" holds the last step's increment (not after wf_step_close)
   std::vector<double> bc_master;           // host copy of bc_vals

@@ -272,8 +272,9 @@ class Domain_d:
         self._ck(self._lib.wf_step_close(self._h))
 
     def step_timed(self, n=1):
-        """wf_step with per-kernel CUDA-event timing; returns ms for [predictor, E1, N1, E2, N2]."""
-        ms = (C.c_float * 5)()
+        """wf_step with per-launch CUDA-event timing; returns ms for [predictor, E1, N1, E2, N2, shared-node sums,
+        shared-node N2, halo kernels of their own] (the last three only on a partitioned mesh)."""
+        ms = (C.c_float * 8)()
         self._ck(self._lib.wf_step_timed(self._h, int(n), ms))
         return list(ms)
 
