@@ -28,6 +28,8 @@ for cfg in a.configs:
     nn, ne, _ = d.counts()
     d.set("v", linear_velocity(case, nn))
     d.step(a.preload)
+    import torch
+    torch.cuda.synchronize(); t0 = time.perf_counter(); d.step(a.steps); d.synchronize(); wall_ms = (time.perf_counter() - t0) * 1e3 / a.steps
     d.step_timed(3)
     ms = d.step_timed(a.steps)
     tot = sum(ms)
@@ -40,6 +42,6 @@ for cfg in a.configs:
         for nm in st:
             diff[nm] = float(np.abs(st[nm] - base[nm]).max() / max(np.abs(base[nm]).max(), 1e-300))
     print(json.dumps({"cfg": cfg, "preload": a.preload, "ms_per_step": {k: round(v / a.steps, 4) for k, v in zip(["pred", "E1", "N1", "E2", "N2"], ms)},
-                      "total_ms": round(tot / a.steps, 4), "rate": rate, 
+                      "total_ms": round(tot / a.steps, 4), "batch_ms_per_step": round(wall_ms, 5), "rate": rate, 
                       "plastic": float((st["pl_strain"] > 0).mean()), "diff_vs_first": diff}), flush=True)
     d.close()

@@ -144,11 +144,14 @@ __global__ void k_unpredict(WfDev d, WfPar P) {
 // ---------------------------------------------------------------------------------------------
 // E1: element volume from current coordinates
 // ---------------------------------------------------------------------------------------------
+// (the bodies of the four step kernels are device functions of a virtual block index; the __global__ wrappers pass
+// blockIdx.x.  A persistent cooperative kernel that walked them in a loop with grid barriers was measured on the
+// 105 k-tet mesh and rejected: 42 us per step against 24.5 us for the four launches with programmatic dependent launch)
 template <int ET>
-__global__ void __launch_bounds__(TPB_E) k_elem_vol(WfDev d, WfPar P, int store_jac) {
+WF_DI void elem_vol_body(const WfDev &d, const WfPar &P, int store_jac, int vbx) {
   constexpr int K = Elem<ET>::K, D = Elem<ET>::D;
   pdl_trigger();
-  int e = blockIdx.x * blockDim.x + threadIdx.x;
+  int e = vbx * blockDim.x + threadIdx.x;
   if (e >= d.ne) return;
   int nid[K];
   load_conn<ET>(d, e, nid);
@@ -170,6 +173,10 @@ __global__ void __launch_bounds__(TPB_E) k_elem_vol(WfDev d, WfPar P, int store_
     if (store_jac == 1) return;
   }
   d.vol[e] = elem_volume<ET>(detJ, radius, d.domtype, d.vol_weight);
+}
+template <int ET>
+__global__ void __launch_bounds__(TPB_E) k_elem_vol(WfDev d, WfPar P, int store_jac) {
+  elem_vol_body<ET>(d, P, store_jac, blockIdx.x);
 }
 
 // E1 with the CTA's unique nodes staged once in shared memory (WfDev::blk_off / lidx)
@@ -385,12 +392,12 @@ WF_DI void halo_send_cta(const WfDev &d, const WfPar &P, int sep, unsigned long 
 //                    batch has no previous node pass to carry its predictor (WF_FAST; strict runs k_predict)
 // HALO: instantiation for partitioned meshes (carries the folded halo send; kept out of the single-GPU kernel, which is
 // register-capped)
-template <int K, int MINB = 1, bool HALO = false>
-__global__ void __launch_bounds__(TPB_N, MINB) k_node_vol(WfDev d, WfPar P, int mode_in) {
+template <int K, bool HALO>
+WF_DI void node_vol_body(const WfDev &d, const WfPar &P, int mode_in, int vbx) {
   const bool with_predict = mode_in == 3;
   const int mode = with_predict ? 1 : mode_in;
   pdl_trigger();
-  int bx = blockIdx.x;
+  int bx = vbx;
   if (HALO && mode == 1 && P.send_ctas > 0) {
     // multi-GPU: the first CTAs of the launch send this rank's partial volume sums of the shared nodes (they depend on
     // the element volumes only), so the transfer travels while the rest of the grid forms the nodal sums
@@ -478,6 +485,11 @@ __global__ void __launch_bounds__(TPB_N, MINB) k_node_vol(WfDev d, WfPar P, int 
   }
 }
 
+template <int K, int MINB = 1, bool HALO = false>
+__global__ void __launch_bounds__(TPB_N, MINB) k_node_vol(WfDev d, WfPar P, int mode_in) {
+  node_vol_body<K, HALO>(d, P, mode_in, blockIdx.x);
+}
+
 // ---------------------------------------------------------------------------------------------
 // E2: the main element pass
 // ---------------------------------------------------------------------------------------------
@@ -535,19 +547,19 @@ WF_DI void gather_nodal_p(const WfDev &d, const int (&nid)[Elem<ET>::K], double 
 // STAGED: the CTA first loads x, v and the nodal ratio of its UNIQUE nodes into shared memory (WfDev::blk_off),
 // then every element reads its nodes through 16-bit block-local indices; otherwise every element gathers its own.
 // TILE: tile-reduced forces (WfDev::ftile, pull form: see WfDev::tf_tab) instead of one record per element node
-template <int ET, bool SEPARATE_HG, bool STAGED, bool THERMAL = false, bool TILE = false, int MINB = 1>
-__global__ void __launch_bounds__(TPB_E, MINB) k_elem_main(WfDev d, WfPar P, int stride) {
+template <int ET, bool SEPARATE_HG, bool STAGED, bool THERMAL, bool TILE>
+WF_DI void elem_main_body(const WfDev &d, const WfPar &P, int stride, int vbx) {
   constexpr int K = Elem<ET>::K, D = Elem<ET>::D;
   static_assert(!(STAGED && THERMAL), "the thermal terms gather by global node id");
   extern __shared__ double sm[];
   pdl_trigger();
-  int e = blockIdx.x * blockDim.x + threadIdx.x;
+  int e = vbx * blockDim.x + threadIdx.x;
   double xl[K][D], vl[K][D], npn[K], A[D][D], dH[D][K], detJ;
   int nid[K];
   if constexpr (STAGED) pdl_wait();
   if constexpr (STAGED) {
     static_assert(TPB_E == WF_EBLK, "block node tables are built for WF_EBLK elements per CTA");
-    const int b = blockIdx.x;
+    const int b = vbx;
     const int u0 = __ldg(d.blk_off + b), U = __ldg(d.blk_off + b + 1) - u0;
     for (int i = threadIdx.x; i < U; i += TPB_E) {
       const int g = __ldg(d.blk_nodes + u0 + i);
@@ -737,6 +749,11 @@ __global__ void __launch_bounds__(TPB_E, MINB) k_elem_main(WfDev d, WfPar P, int
   }
 }
 
+template <int ET, bool SEPARATE_HG, bool STAGED, bool THERMAL = false, bool TILE = false, int MINB = 1>
+__global__ void __launch_bounds__(TPB_E, MINB) k_elem_main(WfDev d, WfPar P, int stride) {
+  elem_main_body<ET, SEPARATE_HG, STAGED, THERMAL, TILE>(d, P, stride, blockIdx.x);
+}
+
 // ---------------------------------------------------------------------------------------------
 // device helpers of the multi-GPU halo exchange (the primitives are defined ahead of the node passes)
 // ---------------------------------------------------------------------------------------------
@@ -778,11 +795,12 @@ WF_DI void warp_add(double *dst, double x) {
   }
   if (lane == __ffs(mask) - 1) atomicAdd(dst, t);
 }
-template <int D, bool SEPARATE_HG, int UNROLL, bool TILE_F = false, bool PREFETCH = false, int MINB = 1, bool HALO = false>
-__global__ void __launch_bounds__(TPB_N, MINB) k_node_update(WfDev d, WfPar P, int fuse_flags, int phase) {
+// ekin_acc: where the kinetic energy of the corrected velocities is accumulated (step monitor), or NULL
+template <int D, bool SEPARATE_HG, int UNROLL, bool TILE_F, bool PREFETCH, bool HALO>
+WF_DI void node_update_body(const WfDev &d, const WfPar &P, int fuse_flags, int phase, int vbx, double *ekin_acc) {
   const bool fuse_predictor = fuse_flags & 1, udt_recompute = fuse_flags & 2, udt_skip_store = fuse_flags & 4;
   pdl_trigger();
-  int bx = blockIdx.x;
+  int bx = vbx;
   if (HALO && phase == 3 && P.send_ctas > 0) {
     // multi-GPU: the first CTAs of the launch send this rank's partial forces of the shared nodes; the rest of the grid
     // integrates the nodes this rank does not share while they travel
@@ -911,11 +929,11 @@ __global__ void __launch_bounds__(TPB_N, MINB) k_node_update(WfDev d, WfPar P, i
     double xmin = key_dbl(d.xmin_key[P.xmin_cur]);
     if (xr <= xmin + 1.e-6) { a[0] = 0.0; v[0] = 0.0; }
   }
-  if (d.ekin_acc) { // step monitor: kinetic energy of the corrected velocities (computeEnergies, Mechanical.C:2145)
+  if (ekin_acc) { // step monitor: kinetic energy of the corrected velocities (computeEnergies, Mechanical.C:2145)
     double s2 = 0.0;
 #pragma unroll
     for (int c = 0; c < D; c++) s2 += v[c] * v[c];
-    warp_add(d.ekin_acc + (bx & 255), 0.5 * mass * s2); // 256 accumulators (wf_engine::MON_NACC), summed by the host
+    warp_add(ekin_acc + (bx & 255), 0.5 * mass * s2); // 256 accumulators (wf_engine::MON_NACC), summed by the host
   }
 #pragma unroll
   for (int c = 0; c < D; c++) {
@@ -945,6 +963,11 @@ __global__ void __launch_bounds__(TPB_N, MINB) k_node_update(WfDev d, WfPar P, i
     }
     if ((threadIdx.x & 31) == (__ffs(mask) - 1)) atomicMin(d.xmin_key + (P.xmin_cur ^ 1), key);
   }
+}
+
+template <int D, bool SEPARATE_HG, int UNROLL, bool TILE_F = false, bool PREFETCH = false, int MINB = 1, bool HALO = false>
+__global__ void __launch_bounds__(TPB_N, MINB) k_node_update(WfDev d, WfPar P, int fuse_flags, int phase) {
+  node_update_body<D, SEPARATE_HG, UNROLL, TILE_F, PREFETCH, HALO>(d, P, fuse_flags, phase, blockIdx.x, d.ekin_acc);
 }
 
 // ThermalCalcs, node part (Thermal.C:103-125): dTdt = sum of the element contributions in nodel order;
