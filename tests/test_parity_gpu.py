@@ -435,3 +435,49 @@ def test_many_cta_waves_against_the_compiled_reference(strict, oracle_ref):
     w = compare(eng, ref, STATE, 1e-9 if strict else 1e-7, "64^3 hexes, 50 steps")
     report(f"hex64_50_steps_{'strict' if strict else 'fast'}", w)
     assert not eng.nonfinite_flag()
+
+
+def test_full_size_properties_10m_hexes():
+    """configs[2] at its full size (215^3 = 9 938 375 hexes, ~77 600 CTAs per element pass), where the oracle cannot
+    follow: size-independent properties of the step.
+      1. the caller's element order and the engine's brick order give the same state (1e-12: association of the tile sums);
+      2. the step is deterministic: a second run in brick order is BIT-identical (gathers only, no atomics);
+      3. a rigid translation produces no internal force and moves every node by v dt.
+    (Mirror symmetries are not a property of this algorithm: the reference's tensor product in the Jaumann terms,
+    Tensor3.C:290-304, treats the axes differently, and the engine reproduces that.)"""
+    from weldformfem_b200.domain import Domain_d
+    n = 215
+    case = R(cases.c3_hexes(n), top_vel=-200.0)
+    states = []
+    for mode in (1, 0, 1):
+        e = Domain_d(elem_order=mode)
+        case.apply(e)
+        e.step(20)
+        states.append({nm: e.get(nm) for nm in ("u", "v", "m_tau", "pl_strain", "p")})
+        assert not e.nonfinite_flag()
+        e.close()
+    a, b, c = states
+    for nm in a:
+        assert relerr(a[nm], b[nm]) < 1e-12, (nm, relerr(a[nm], b[nm]))
+        assert np.array_equal(a[nm], c[nm]), nm
+    assert (a["pl_strain"] > 0).mean() > 0.01
+    del states, a, b, c
+    # rigid translation, no boundary conditions
+    e = Domain_d()
+    e.box((0.0, 0.0, 0.0), [n * case.h * (1 + 1e-6)] * 3, 0.5 * case.h, False)
+    e.set_material(case.E, case.nu, case.rho0, case.model, case.sy0, case.K, case.m)
+    e.set_stab()
+    e.set_options(0, 0.0, 0.0, case.hexa_hg)
+    e.allocate_bcs()
+    e.init(case.timestep)
+    nn = e.counts()[0]
+    x0 = e.get("x")
+    v0 = np.tile(np.array([3.0, -2.0, 5.0]), nn)
+    e.set("v", v0)
+    e.step(3)
+    f = e.get("m_fi")
+    scale = case.E * case.h * case.h                 # force scale of a unit strain on one element face
+    assert np.abs(f).max() < 1e-9 * scale, np.abs(f).max()
+    assert np.abs(e.get("x") - x0 - 3 * case.timestep * v0).max() < 1e-12
+    assert (e.get("pl_strain") == 0).all()
+    e.close()
