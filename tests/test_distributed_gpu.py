@@ -160,3 +160,33 @@ def test_halo_timeout_is_sticky_and_surfaces_everywhere(monkeypatch):
         r0.synchronize()
     assert time.time() - t0 < 0.25
     cl.close()
+
+
+def test_open_stepping_on_a_partitioned_mesh():
+    """wf_step_open + wf_set_bc_values per step on every rank (what bench.py's e2e loop does at N > 1): prescribed values
+    are given for the GLOBAL BC list on every rank, the engine keeps the rows of its own nodes; compared with the one-GPU
+    engine stepping closed with the same values."""
+    from weldformfem_b200.distributed import LocalCluster
+    case = CASES["hex"]
+    cl = LocalCluster(2, devices_for(2))
+    case.apply(cl)
+    one = run_single(case, 0)
+    _, dims, vals = case.bc_arrays()
+    vz = vals[dims == 2]
+    for i in range(7):
+        newv = vz * (1.0 + 0.1 * np.cos(i))
+        one.set_bc_values(2, newv)
+        one.step(1)
+        for r in cl.ranks:
+            r.set_bc_values(2, newv)
+        for r in cl.ranks:
+            r.step_open(1)
+            r.monitor_async()
+        ek = sum(r.monitor_wait()[0] for r in cl.ranks)
+    for r in cl.ranks:
+        r.step_close()
+    worst = {nm: relerr(cl.get(nm), one.get(nm)) for nm in NAMES}
+    assert max(worst.values()) < 1e-11, worst
+    # kinetic energy of the last step: shared nodes are counted by every sharer, so the sum over ranks is >= the global value
+    assert ek >= one.energies()[0] * (1 - 1e-12)
+    cl.close(); one.close()
