@@ -89,6 +89,10 @@ int wf_get_counts(wf_engine *, int *n_nodes, int *n_elems, int *nodel_total);
  * WF_ELEM_ORDER overrides the default.  Every array that crosses this ABI stays in the caller's numbering whatever the mode; wf_device_ptr
  * of an element array exposes the internal order ("elem_perm" via wf_get_array gives perm[internal] = user). */
 int wf_set_elem_order(wf_engine *, int mode);
+/* Thread layout of the brick form of the hexahedron passes on the current mesh: n_cta = CTAs of 128 thread slots (0: the
+ * brick form is not in use), plan = 1 when the slots follow the cells of the mesh (wf_host_brick_plan: every CTA a
+ * clipped 8x4x4 brick), 0 for the compact numbering.  The environment variable WF_BRICK_PLAN=0 forces the latter. */
+int wf_brick_info(wf_engine *, int *n_cta, int *plan);
 int wf_set_axisymm_vol_weight(wf_engine *, int on); /* setAxiSymm(vol_weight), Domain_d.h:666 */
 
 /* ---- material / options / boundary conditions -------------------------------------------------- */
@@ -281,6 +285,14 @@ int wf_host_force_tiles(int n_nodes, int n_elems, int nodxelem, int dim, const u
  * against the numpy restatement in tests/test_host_mesh.py. */
 int wf_host_elem_order(int dim, int nodxelem, int n_nodes, int n_elems, const double *x, const unsigned *elnod, int mode,
                        int *perm);
+/* Same, also returning the sort key of every element in the resulting internal order (mode 1; keys may be NULL). */
+int wf_host_elem_order_keys(int dim, int nodxelem, int n_nodes, int n_elems, const double *x, const unsigned *elnod, int mode,
+                            int *perm, unsigned long long *keys);
+/* Thread slots of the brick passes of the hexahedron path (csrc/wf_mesh.cpp): with the keys of wf_host_elem_order_keys
+ * strictly ascending (one element per cell), CTA = rank of key >> 7 (an 8x4x4 group of cells), thread = key & 127:
+ * slot_elem[cta * 128 + thread] = internal element, -1 = no such cell.  slot_elem = NULL returns n_cta only.  Returns 1
+ * when two elements share a key (the engine then keeps the compact numbering 128 cta + thread). */
+int wf_host_brick_plan(int n_elems, const unsigned long long *keys, int *n_cta, int *slot_elem);
 /* Shared-memory slots of a sorted node list for the brick form of the hexa main pass (csrc/wf_mesh.cpp): run r of
  * consecutive ids starts at the first free slot congruent to 12 r (mod 16).  Returns the slot count. */
 int wf_host_run_slots(int n, const int *sorted_ids, int *slots);

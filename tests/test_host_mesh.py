@@ -513,3 +513,90 @@ def test_run_slots_bit_exact_and_conflict_free_on_bricks():
                 for c in range(8):
                     banks = [slot[g] % 16 for g in ELi[h0:h0 + 16, c]]
                     assert len(set(banks)) == 16
+
+
+# ---- thread slots of the brick passes (wf_host_brick_plan) ----------------------------------------------------
+def host_elem_order_keys(dim, k, x, el):
+    from weldformfem_b200 import _lib
+    lib = _lib.load()
+    nn, ne = x.size // dim, el.size // k
+    perm = np.empty(ne, np.int32)
+    keys = np.empty(ne, np.uint64)
+    rc = lib.wf_host_elem_order_keys(dim, k, nn, ne, np.ascontiguousarray(x).ctypes.data_as(C.POINTER(C.c_double)),
+                                     np.ascontiguousarray(el).ctypes.data_as(C.POINTER(C.c_uint)), 1,
+                                     perm.ctypes.data_as(C.POINTER(C.c_int)), keys.ctypes.data_as(C.POINTER(C.c_ulonglong)))
+    return rc, perm, keys
+
+
+def host_brick_plan(keys):
+    from weldformfem_b200 import _lib
+    lib = _lib.load()
+    keys = np.ascontiguousarray(keys, np.uint64)
+    n = C.c_int(0)
+    kp = keys.ctypes.data_as(C.POINTER(C.c_ulonglong))
+    rc = lib.wf_host_brick_plan(keys.size, kp, C.byref(n), None)
+    if rc:
+        return rc, 0, None
+    slot = np.empty(n.value * 128, np.int32)
+    rc = lib.wf_host_brick_plan(keys.size, kp, C.byref(n), slot.ctypes.data_as(C.POINTER(C.c_int)))
+    return rc, n.value, slot
+
+
+def test_brick_plan_bit_exact_and_every_cta_is_a_clipped_brick():
+    """A box whose edge counts are no multiples of the brick (23 x 21 x 19 hexes): in the compact numbering the chunks
+    of 128 drift across brick boundaries; with the plan every CTA holds the cells of ONE 8x4x4 group, its node list
+    fits the bank-aware layout and every half-warp reads 16 different bank pairs per corner."""
+    dim, k, x, el = host_box((0, 0, 0), (1.1501, 1.0501, 0.9501), 0.025, False)
+    assert el.size == 8 * 23 * 21 * 19
+    rc, perm, keys = host_elem_order_keys(dim, k, x, el)
+    assert rc == 0 and np.array_equal(perm, numpy_elem_order(dim, k, x, el))
+    assert np.all(np.diff(keys.astype(np.int64)) > 0)
+    rc, n_cta, slot = host_brick_plan(keys)
+    assert rc == 0
+    # restatement: CTA = rank of key >> 7, thread = key & 127
+    grp = (keys >> np.uint64(7)).astype(np.int64)
+    cta = np.concatenate([[0], np.cumsum(np.diff(grp) != 0)])
+    want = np.full((cta[-1] + 1) * 128, -1, np.int32)
+    want[cta * 128 + (keys & np.uint64(127)).astype(np.int64)] = np.arange(keys.size)
+    assert n_cta == cta[-1] + 1 == 3 * 6 * 5 and np.array_equal(slot, want)
+    ELi = el.reshape(-1, 8).astype(np.int64)[perm]
+    ragged_compact = 0
+    for c0 in range(0, ELi.shape[0], 128):
+        n, _ = host_run_slots(np.unique(ELi[c0:c0 + 128]))
+        ragged_compact += n > 304
+    assert ragged_compact > 0                      # what the plan is for
+    for b in range(n_cta):
+        s = slot[b * 128:(b + 1) * 128]
+        ids = np.unique(ELi[s[s >= 0]])
+        n, sl = host_run_slots(ids)
+        assert n <= 304
+        lut = dict(zip(ids.tolist(), sl.tolist()))
+        for h0 in range(0, 128, 16):
+            lanes = s[h0:h0 + 16]
+            lanes = lanes[lanes >= 0]
+            for c in range(8):
+                banks = [lut[g] % 16 for g in ELi[lanes, c]]
+                assert len(set(banks)) == len(banks)
+        for w in range(4):                          # tile accumulators
+            lanes = s[32 * w:32 * w + 32]
+            lanes = lanes[lanes >= 0]
+            if lanes.size == 0:
+                continue
+            ids = np.unique(ELi[lanes])
+            n, sl = host_run_slots(ids)
+            assert n <= 176 and ids.size <= 75
+
+
+def test_brick_plan_refuses_two_elements_in_one_cell():
+    keys = np.array([5, 9, 9, 300], np.uint64)
+    rc, _, _ = host_brick_plan(keys)
+    assert rc != 0
+    dim, k, x, el = host_box((0, 0, 0), (0.3, 0.3, 0.3), 0.05, True)      # tets: six per cell, no hexa keys at all
+    from weldformfem_b200 import _lib
+    lib = _lib.load()
+    perm = np.empty(el.size // k, np.int32)
+    keys = np.empty(el.size // k, np.uint64)
+    assert lib.wf_host_elem_order_keys(dim, k, x.size // dim, el.size // k, x.ctypes.data_as(C.POINTER(C.c_double)),
+                                       el.ctypes.data_as(C.POINTER(C.c_uint)), 1, perm.ctypes.data_as(C.POINTER(C.c_int)),
+                                       keys.ctypes.data_as(C.POINTER(C.c_ulonglong))) == 0
+    assert host_brick_plan(keys)[0] != 0

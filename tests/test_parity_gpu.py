@@ -377,6 +377,38 @@ def test_elem_order_is_invisible(key, strict, oracle_port):
         e.close()
 
 
+@pytest.mark.parametrize("dims", [(13, 11, 9), (8, 4, 4), (5, 3, 2), (17, 6, 7)])
+def test_brick_plan_vs_compact_thread_slots(dims, oracle_port, monkeypatch):
+    """Hexa boxes whose edge counts are no multiples of the 8x4x4 brick: the brick passes give every CTA the cells of ONE
+    brick group (wf_host_brick_plan; idle threads where a cell does not exist) instead of 128 consecutive elements.  Same
+    results as the compact thread slots up to the association of the per-tile partial sums, and as the oracle."""
+    from weldformfem_b200.domain import Domain_d
+    case = R(cases.Case("hex_%dx%dx%d" % dims, 3, dims, 1.0e-3, cfl=0.3, hexa_hg=0.06), top_vel=-200.0)
+    engs = []
+    for plan in ("1", "0"):
+        monkeypatch.setenv("WF_BRICK_PLAN", plan)
+        e = Domain_d()
+        case.apply(e)
+        n_cta, is_plan = e.brick_info()
+        groups = -(-dims[0] // 8) * -(-dims[1] // 4) * -(-dims[2] // 4)
+        ne = dims[0] * dims[1] * dims[2]
+        if plan == "1":
+            assert (n_cta, is_plan) == (groups, 1)
+        else:   # compact slots: chunks of 128 consecutive elements, or (ragged chunks that do not fit) the generic tile kernel
+            assert is_plan == 0 and n_cta in (0, -(-ne // 128))
+        e.step(20)
+        engs.append(e)
+    for nm in _names(case):
+        a, b = engs[0].get(nm), engs[1].get(nm)
+        assert relerr(a, b) < 1e-12, (nm, relerr(a, b))
+    ref = oracle_port()
+    case.apply(ref)
+    ref.step(20)
+    compare(engs[0], ref, _names(case), 1e-9, "hexa brick plan vs oracle")
+    for e in engs:
+        e.close()
+
+
 @pytest.mark.parametrize("key", ["hex", "tet", "psquad"])
 def test_open_stepping_with_per_step_bc_values_and_monitor(key, oracle_port):
     """wf_step_open: a host loop that talks to the engine every step (new prescribed velocities in, kinetic energy out)

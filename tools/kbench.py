@@ -20,6 +20,10 @@ case = {"hex": cases.c3_hexes, "tet": cases.c2_tets, "quad": cases.c4_axisymm_qu
 base = None
 for cfg in a.configs:
     kv = dict(x.split("=") for x in cfg.split(",") if x)
+    if "plan" in kv:
+        os.environ["WF_BRICK_PLAN"] = kv["plan"]
+    else:
+        os.environ.pop("WF_BRICK_PLAN", None)
     d = Domain_d(strict=a.strict, elem_order=int(kv["order"]) if "order" in kv else None)
     case.apply(d)
     for name, idx in (("e1", 0), ("n1", 1), ("e2", 2), ("n2", 3)):

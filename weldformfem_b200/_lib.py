@@ -44,7 +44,7 @@ DECLARED = (["wf_create", "wf_destroy", "wf_last_error", "wf_set_stream", "wf_ge
              "wf_host_box_counts", "wf_host_gen_box", "wf_host_nodel", "wf_version",
              "wf_set_trimesh", "wf_set_contact", "wf_get_trimesh_counts", "wf_host_ext_faces",
              "wf_host_axis_plane_counts", "wf_host_axis_plane_mesh", "wf_set_thermal", "wf_set_contact_heat",
-             "wf_host_force_tiles", "wf_set_elem_order", "wf_host_elem_order", "wf_host_run_slots", "wf_step_open", "wf_step_close"]
+             "wf_host_force_tiles", "wf_set_elem_order", "wf_host_elem_order", "wf_host_elem_order_keys", "wf_host_brick_plan", "wf_brick_info", "wf_host_run_slots", "wf_step_open", "wf_step_close"]
             + ["wf_" + n for n in UNFUSED])
 
 
@@ -141,6 +141,9 @@ def load():
         "wf_set_elem_order": (C.c_int, [vp, C.c_int]),
         "wf_host_run_slots": (C.c_int, [C.c_int, ip, ip]),
         "wf_host_elem_order": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, dp, up, C.c_int, ip]),
+        "wf_host_elem_order_keys": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, dp, up, C.c_int, ip, C.POINTER(C.c_ulonglong)]),
+        "wf_brick_info": (C.c_int, [vp, ip, ip]),
+        "wf_host_brick_plan": (C.c_int, [C.c_int, C.POINTER(C.c_ulonglong), ip, ip]),
         "wf_host_axis_plane_mesh": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, dp, dp, C.c_int, dp, ip, dp, ip]),
     }
     for n in UNFUSED:

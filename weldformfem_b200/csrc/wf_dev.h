@@ -83,7 +83,7 @@ struct WfDev {
   const int *pos;                    /* [k][ep] offset of (e, ln) in fsell: dim*q - (dim-1)*(n&31), q = sell index */
   double *fsell, *fsell_hg;          /* [slice][j][dim][32] node-ordered element (and hourglass) forces */
   /* tile-reduced forces (hexa, WF_FAST only; NULL when the mesh does not qualify): instead of one force record per
-   * element node, every WARP of the main element pass (32 consecutive elements = one "force tile") sums the
+   * element node, every WARP of the main element pass (32 thread slots = one "force tile") sums the
    * contributions of its elements per UNIQUE node in shared memory — one round per local corner, each round a
    * conflict-free read-modify-write, so the order of additions is fixed — and writes one partial per (tile, unique
    * node): ftile[(tile*3 + c) * tf_stride + u], u = tf_idx[corner][e] = index of the node in the tile's ascending
@@ -93,15 +93,20 @@ struct WfDev {
   const long long *tf_ptr;           /* [nslices+1] */
   const unsigned *tf_slots;
   const unsigned char *tf_idx;       /* [k][ep] (hexahedra) */
-  /* brick form of the hexa main pass (NULL when the bank-aware layouts do not fit its compile-time pitches): node list
-   * of CTA b at blk_pad_b + b * WF_BRICK_STRIDE indexed by shared-memory SLOT (wf_host_run_slots, -1 = hole); the slots
-   * of an element's eight nodes in the CTA copy (16 bit each) and in its tile's accumulators (8 bit each) as one
-   * record per element; tf_r2s[tile * 32 + lane] byte j = accumulator slot of the tile's unique node of rank
-   * lane + 32 j (0xff = none: at most 128 unique nodes), read when the partial sums are written out in rank order */
+  /* brick form of the hexa passes (NULL when the bank-aware layouts do not fit the compile-time pitches).  The brick
+   * kernels run n_bcta CTAs of 128 THREAD SLOTS; slot s = cta * 128 + thread works on element brick_elem[s] (>= 0), or
+   * idles (< 0: ~brick_elem[s] is an element of the same CTA whose tables the idle thread reads).  brick_plan = 1: the
+   * slots follow the cells of the mesh (wf_host_brick_plan: every CTA a clipped 8x4x4 brick), 0: slot s = element s.
+   * Node list of CTA b at blk_pad_b + b * WF_BRICK_STRIDE indexed by shared-memory SLOT (wf_host_run_slots, -1 = hole);
+   * lidx_pk[s] = the slots of the element's eight nodes in the CTA copy (16 bit each); tile_pk[s] = {x, y: its eight
+   * 8-bit slots in the tile's accumulators; z: byte j = accumulator slot of the tile's unique node of rank
+   * lane + 32 j (0xff = none: at most 128 unique nodes), read when the partial sums are written out in rank order;
+   * w = brick_elem[s]} */
   const int *blk_pad_b;
-  const uint4 *lidx_pk;              /* [ep] */
-  const uint2 *tf_idx_pk;            /* [ep] */
-  const unsigned *tf_r2s;            /* [n_ctas * 128] */
+  const uint4 *lidx_pk;              /* [n_bcta * 128] */
+  const uint4 *tile_pk;              /* [n_bcta * 128] */
+  const int *brick_elem;             /* [n_bcta * 128] */
+  int n_bcta, brick_plan;
   int cta_lookahead;                 /* resident CTAs of the main element pass on the device (L2 look-ahead distance) */
   /* tetrahedra: corners of different elements of a tile DO share nodes, so the tile sum is pulled instead: every
    * element drops its k*dim force values in shared memory and lane u adds up the entries of unique node u listed in

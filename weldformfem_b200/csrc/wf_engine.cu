@@ -151,9 +151,12 @@ static int upload_mesh(wf_engine *E, int nn, int ne, const double *x, const unsi
   std::vector<unsigned> el_int;
   const unsigned *eli = elnod; // connectivity in internal order, reference layout [e*k + ln]
   const int order = E->order_mode >= 0 ? E->order_mode : (k == 8 ? 1 : 0);
+  std::vector<unsigned long long> okeys; // hexahedra: sort keys in internal order (wf_host_brick_plan)
   if (order != 0 && ne > 1) {
     E->perm.resize(ne); E->iperm.resize(ne);
-    if (wf_host_elem_order(dim, k, nn, ne, x, elnod, order, E->perm.data())) FAIL("element ordering failed");
+    if (k == 8 && dim == 3) okeys.resize(ne);
+    if (wf_host_elem_order_keys(dim, k, nn, ne, x, elnod, order, E->perm.data(), okeys.empty() ? nullptr : okeys.data()))
+      FAIL("element ordering failed");
     bool ident = true;
     for (int e = 0; e < ne; e++) { E->iperm[E->perm[e]] = e; ident = ident && E->perm[e] == e; }
     if (ident) { E->perm.clear(); E->iperm.clear(); }
@@ -270,11 +273,99 @@ static int upload_mesh(wf_engine *E, int nn, int ne, const double *x, const unsi
     }
     // tile-reduced force path (WfDev::ftile): tables built on the host (wf_force_tiles_build, wf_mesh.cpp)
     d.ftile = nullptr; d.tf_ptr = nullptr; d.tf_slots = nullptr; d.tf_idx = nullptr; d.tf_tab = nullptr;
-    d.lidx_pk = nullptr; d.tf_idx_pk = nullptr; d.blk_pad_b = nullptr; d.tf_r2s = nullptr; d.cta_lookahead = 0;
+    d.lidx_pk = nullptr; d.tile_pk = nullptr; d.blk_pad_b = nullptr; d.brick_elem = nullptr; d.cta_lookahead = 0;
+    d.n_bcta = 0; d.brick_plan = 0;
     d.tf_stride = 0; d.tf_tpitch = 0;
     if (dim == 3) { // 2D (1M quads, measured): rounds form E2 0.080 -> 0.099 ms, pull form 0.105 ms, N2 unchanged: not used
       WfForceTiles T;
-      wf_force_tiles_build(nn, ne, k, dim, d.ep, eli, T);
+      // brick form of the hexa passes (k_elem_vol_brick, k_elem_main_hex_brick): thread slots (wf_host_brick_plan, or the
+      // compact numbering), bank-aware shared-memory slots (wf_host_run_slots) of every CTA's node list and of every
+      // tile's node list, the slots of an element's eight nodes packed into one record each, and per tile the table
+      // rank -> slot used when the partial sums are written out.  All built on the host first: the plan is dropped for
+      // the compact numbering when its tables do not fit.
+      constexpr int BS = WF_BRICK_STRIDE, BW = WF_BRICK_WS;
+      std::vector<int> slot_elem, bpad, belem;
+      std::vector<unsigned short> lpk;
+      std::vector<unsigned> tpk;
+      int n_bcta = 0;
+      auto build_brick = [&](bool plan) -> bool {
+        n_bcta = nblk;
+        slot_elem.clear();
+        if (plan) {
+          if (wf_host_brick_plan(ne, okeys.data(), &n_bcta, nullptr)) return false;
+          slot_elem.resize((size_t)n_bcta * WF_EBLK);
+          if (wf_host_brick_plan(ne, okeys.data(), &n_bcta, slot_elem.data())) return false;
+        }
+        const long long ns = plan ? (long long)n_bcta * WF_EBLK : ne, sp = plan ? ns : d.ep;
+        const int *se = plan ? slot_elem.data() : nullptr;
+        auto elem = [&](long long s_) { return se ? se[s_] : (s_ < ne ? (int)s_ : -1); };
+        wf_force_tiles_build(nn, (int)ns, se, k, dim, sp, eli, T);
+        if (!T.usable) return false;
+        if (k != 8 || !T.rounds) return !plan;
+        const long long nslot = (long long)n_bcta * WF_EBLK;
+        bpad.assign((size_t)n_bcta * BS, -1);
+        lpk.assign((size_t)8 * nslot, 0);
+        tpk.assign((size_t)4 * nslot, 0u);
+        belem.assign((size_t)nslot, 0);
+        std::vector<int> sl, ids;
+        for (int b = 0; b < n_bcta; b++) {
+          const long long s0 = (long long)b * WF_EBLK;
+          ids.clear();
+          int first = -1;
+          for (int t = 0; t < WF_EBLK; t++) {
+            const int e = elem(s0 + t);
+            if (e < 0) continue;
+            if (first < 0) first = t;
+            ids.insert(ids.end(), eli + (size_t)e * 8, eli + (size_t)e * 8 + 8);
+          }
+          if (first < 0) return false;
+          std::sort(ids.begin(), ids.end());
+          ids.erase(std::unique(ids.begin(), ids.end()), ids.end());
+          const int U = (int)ids.size();
+          if (U > BS) return false;
+          sl.resize(U);
+          // ragged CTAs (not a whole brick: more, shorter runs) keep the plain ascending layout
+          if (wf_host_run_slots(U, ids.data(), sl.data()) > BS)
+            for (int i = 0; i < U; i++) sl[i] = i;
+          for (int i = 0; i < U; i++) bpad[(size_t)b * BS + sl[i]] = ids[i];
+          for (int t = 0; t < WF_EBLK; t++) {
+            const int e = elem(s0 + t), es = e >= 0 ? e : elem(s0 + first); // idle threads read the tables of a real element
+            belem[(size_t)(s0 + t)] = e >= 0 ? e : ~es;
+            for (int n = 0; n < 8; n++)
+              lpk[(size_t)(s0 + t) * 8 + n] =
+                  (unsigned short)sl[std::lower_bound(ids.begin(), ids.end(), (int)eli[(size_t)es * 8 + n]) - ids.begin()];
+          }
+        }
+        for (long long w = 0; w < (long long)n_bcta * (WF_EBLK / 32); w++) {
+          const long long s0 = w * 32;
+          ids.clear();
+          for (int t = 0; t < 32; t++)
+            if (elem(s0 + t) >= 0) ids.insert(ids.end(), eli + (size_t)elem(s0 + t) * 8, eli + (size_t)elem(s0 + t) * 8 + 8);
+          std::sort(ids.begin(), ids.end());
+          ids.erase(std::unique(ids.begin(), ids.end()), ids.end());
+          const int U = (int)ids.size();
+          if (U > BW || U > 128) return false;
+          sl.resize(U);
+          if (wf_host_run_slots(U, ids.data(), sl.data()) > BW)
+            for (int i = 0; i < U; i++) sl[i] = i;
+          unsigned r2s[32];
+          for (int t = 0; t < 32; t++) r2s[t] = 0xFFFFFFFFu;
+          for (int i = 0; i < U; i++) r2s[i & 31] = (r2s[i & 31] & ~(0xFFu << (8 * (i >> 5)))) | ((unsigned)sl[i] << (8 * (i >> 5)));
+          for (int t = 0; t < 32; t++) {
+            unsigned *rec = &tpk[(size_t)(s0 + t) * 4];
+            if (elem(s0 + t) >= 0)
+              for (int n = 0; n < 8; n++) rec[n >> 2] |= (unsigned)sl[T.tidx[(size_t)n * sp + (s0 + t)]] << (8 * (n & 3));
+            rec[2] = r2s[t];
+            rec[3] = (unsigned)belem[(size_t)(s0 + t)];
+          }
+        }
+        return true;
+      };
+      bool plan = k == 8 && !okeys.empty();
+      if (const char *t = getenv("WF_BRICK_PLAN")) plan = plan && atoi(t) != 0; // 0: compact thread slots (A/B runs, tests)
+      bool brick = build_brick(plan);
+      if (!brick && plan) { plan = false; brick = build_brick(false); }
+      brick = brick && k == 8 && T.usable && T.rounds && !bpad.empty();
       if (T.usable) {
         long long *dtp; unsigned *dts;
         if (dalloc(E, &dtp, T.ptr.size()) || dalloc(E, &dts, std::max<size_t>(T.slots.size(), 1)) ||
@@ -283,64 +374,26 @@ static int upload_mesh(wf_engine *E, int nn, int ne, const double *x, const unsi
         CK(cudaMemcpyAsync(dtp, T.ptr.data(), T.ptr.size() * sizeof(long long), cudaMemcpyHostToDevice, E->stream));
         CK(cudaMemcpyAsync(dts, T.slots.data(), T.slots.size() * sizeof(unsigned), cudaMemcpyHostToDevice, E->stream));
         if (k == 8) {
-          unsigned char *dti;
-          if (dalloc(E, &dti, T.tidx.size())) return 1;
-          CK(cudaMemcpyAsync(dti, T.tidx.data(), T.tidx.size(), cudaMemcpyHostToDevice, E->stream));
-          d.tf_idx = dti;
-          // brick form of the main pass (k_elem_main_hex_brick): bank-aware shared-memory slots (wf_host_run_slots) of
-          // the CTA's node list and of every tile's node list, the slots of an element's eight nodes packed into one
-          // record each, and per tile the table rank -> slot used when the partial sums are written out
-          if (T.rounds) {
-            constexpr int BS = WF_BRICK_STRIDE, BW = WF_BRICK_WS;
-            const int ntile = T.n_tiles;
-            std::vector<int> bpad((size_t)nblk * BS, -1), sl, ids;
-            std::vector<unsigned short> lpk((size_t)8 * d.ep, 0);
-            std::vector<unsigned char> tpk((size_t)8 * d.ep, 0);
-            std::vector<unsigned> r2s((size_t)nblk * WF_EBLK, 0xFFFFFFFFu); // one word per thread of the main pass
-            bool fits = true;
-            for (int b = 0; b < nblk && fits; b++) {
-              const int u0 = boff[b], U = boff[b + 1] - u0;
-              sl.resize(U);
-              if (U > BS) { fits = false; break; }
-              // ragged CTAs (not a whole brick: more, shorter runs) keep the plain ascending layout
-              if (wf_host_run_slots(U, bnodes.data() + u0, sl.data()) > BS)
-                for (int i = 0; i < U; i++) sl[i] = i;
-              for (int i = 0; i < U; i++) bpad[(size_t)b * BS + sl[i]] = bnodes[u0 + i];
-              const int e0 = b * WF_EBLK, e1 = std::min(ne, e0 + WF_EBLK);
-              for (int e = e0; e < e1; e++)
-                for (int n = 0; n < 8; n++) lpk[(size_t)e * 8 + n] = (unsigned short)sl[lidx[(size_t)n * d.ep + e]];
-            }
-            for (int w = 0; w < ntile && fits; w++) {
-              const int e0 = w * 32, e1 = std::min(ne, e0 + 32);
-              ids.assign(eli + (size_t)e0 * 8, eli + (size_t)e1 * 8);
-              std::sort(ids.begin(), ids.end());
-              ids.erase(std::unique(ids.begin(), ids.end()), ids.end());
-              const int U = (int)ids.size();
-              sl.resize(U);
-              if (U > BW || U > 128) { fits = false; break; }
-              if (wf_host_run_slots(U, ids.data(), sl.data()) > BW)
-                for (int i = 0; i < U; i++) sl[i] = i;
-              for (int i = 0; i < U; i++) {
-                unsigned &word = r2s[(size_t)w * 32 + (i & 31)];
-                word = (word & ~(0xFFu << (8 * (i >> 5)))) | ((unsigned)sl[i] << (8 * (i >> 5)));
-              }
-              for (int e = e0; e < e1; e++)
-                for (int n = 0; n < 8; n++) tpk[(size_t)e * 8 + n] = (unsigned char)sl[T.tidx[(size_t)n * d.ep + e]];
-            }
-            if (fits) {
-              uint4 *dl4; uint2 *dt2; int *dbp; unsigned *dr;
-              if (dalloc(E, &dl4, (size_t)d.ep) || dalloc(E, &dt2, (size_t)d.ep) || dalloc(E, &dbp, bpad.size()) || dalloc(E, &dr, r2s.size()))
-                return 1;
-              CK(cudaMemcpyAsync(dl4, lpk.data(), lpk.size() * sizeof(unsigned short), cudaMemcpyHostToDevice, E->stream));
-              CK(cudaMemcpyAsync(dt2, tpk.data(), tpk.size(), cudaMemcpyHostToDevice, E->stream));
-              CK(cudaMemcpyAsync(dbp, bpad.data(), bpad.size() * sizeof(int), cudaMemcpyHostToDevice, E->stream));
-              CK(cudaMemcpyAsync(dr, r2s.data(), r2s.size() * sizeof(unsigned), cudaMemcpyHostToDevice, E->stream));
-              CK(cudaStreamSynchronize(E->stream));
-              d.lidx_pk = dl4; d.tf_idx_pk = dt2; d.blk_pad_b = dbp; d.tf_r2s = dr;
-              int sms = 0;
-              CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, E->device));
-              d.cta_lookahead = 4 * sms; // four 128-register CTAs per SM
-            }
+          if (!plan) { // the generic tile kernel addresses tiles by the compact numbering
+            unsigned char *dti;
+            if (dalloc(E, &dti, T.tidx.size())) return 1;
+            CK(cudaMemcpyAsync(dti, T.tidx.data(), T.tidx.size(), cudaMemcpyHostToDevice, E->stream));
+            d.tf_idx = dti;
+          }
+          if (brick) {
+            uint4 *dl4, *dt4; int *dbp, *dbe;
+            if (dalloc(E, &dl4, belem.size()) || dalloc(E, &dt4, belem.size()) || dalloc(E, &dbp, bpad.size()) || dalloc(E, &dbe, belem.size()))
+              return 1;
+            CK(cudaMemcpyAsync(dl4, lpk.data(), lpk.size() * sizeof(unsigned short), cudaMemcpyHostToDevice, E->stream));
+            CK(cudaMemcpyAsync(dt4, tpk.data(), tpk.size() * sizeof(unsigned), cudaMemcpyHostToDevice, E->stream));
+            CK(cudaMemcpyAsync(dbp, bpad.data(), bpad.size() * sizeof(int), cudaMemcpyHostToDevice, E->stream));
+            CK(cudaMemcpyAsync(dbe, belem.data(), belem.size() * sizeof(int), cudaMemcpyHostToDevice, E->stream));
+            CK(cudaStreamSynchronize(E->stream));
+            d.lidx_pk = dl4; d.tile_pk = dt4; d.blk_pad_b = dbp; d.brick_elem = dbe;
+            d.n_bcta = n_bcta; d.brick_plan = plan ? 1 : 0;
+            int sms = 0;
+            CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, E->device));
+            d.cta_lookahead = 4 * sms; // four 128-register CTAs per SM
           }
         } else {
           unsigned char *dtab;
@@ -405,6 +458,13 @@ extern "C" int wf_set_elem_order(wf_engine *E, int mode) { WF_NULLCHK(E);
   NEED(!E->meshed, "wf_set_elem_order before the mesh is set");
   NEED(mode == 0 || mode == 1, "element order mode must be 0 (caller's numbering) or 1 (Morton)");
   E->order_mode = mode;
+  return 0;
+}
+
+extern "C" int wf_brick_info(wf_engine *E, int *n_cta, int *plan) { WF_NULLCHK(E);
+  NEED(E->meshed, "no mesh");
+  if (n_cta) *n_cta = E->d.n_bcta;
+  if (plan) *plan = E->d.brick_plan;
   return 0;
 }
 

@@ -413,8 +413,8 @@ __global__ void __launch_bounds__(TPB, 4) k_elem_main_hex_tile(WfDev d, WfPar P,
 }
 
 // ---- brick form: compile-time pitches, packed local indices ------------------------------------------------------
-// WfDev::lidx_pk[e] = the eight 16-bit CTA-local node indices of element e (one uint4), WfDev::tf_idx_pk[e] = its eight
-// 8-bit tile-local indices (one uint2); both are plain repackings of lidx / tf_idx made at mesh upload.
+// Per thread slot (WfDev::brick_elem): lidx_pk = the eight 16-bit CTA-local node slots of the element (one uint4),
+// tile_pk = its eight 8-bit accumulator slots, the tile's rank -> slot word and the element id (one uint4).
 template <int STRIDE>
 struct StagedSrcC {
   const double *s;
@@ -461,10 +461,6 @@ __global__ void __launch_bounds__(TPB, MINB) k_elem_main_hex_brick(WfDev d, WfPa
   pdl_trigger();
   const int t = threadIdx.x;
   const int b = blockIdx.x;
-  const int e0 = b * TPB + t;
-  const bool active = e0 < d.ne;
-  const int e = active ? e0 : d.ne - 1;
-  const unsigned amask = __ballot_sync(0xffffffffu, active);
   constexpr int NQ = (STRIDE + TPB - 1) / TPB;
   const int *__restrict__ ids = d.blk_pad_b + (long long)b * STRIDE;
   int gid[NQ];
@@ -473,13 +469,20 @@ __global__ void __launch_bounds__(TPB, MINB) k_elem_main_hex_brick(WfDev d, WfPa
     const int i = q * TPB + t;
     gid[q] = (i < STRIDE) ? __ldg(ids + i) : -1;
   }
-  const uint4 lpk = __ldg(d.lidx_pk + e);
-  const uint2 rpk = __ldg(d.tf_idx_pk + e);
-  const unsigned r2s = __ldg(d.tf_r2s + (long long)b * TPB + t); // rank -> slot of this warp's tile, used at the very end
+  // this thread slot: the element (or the element an idle thread shadows), its node slots in the CTA copy and in the
+  // tile's accumulators, and (z) the rank -> slot word of this warp's tile, used at the very end
+  const uint4 lpk = __ldg(d.lidx_pk + (long long)b * TPB + t);
+  const uint4 tpk = __ldg(d.tile_pk + (long long)b * TPB + t);
+  const int e0 = (int)tpk.w;
+  const bool active = e0 >= 0;
+  const int e = active ? e0 : ~e0;
+  const unsigned amask = __ballot_sync(0xffffffffu, active);
+  const uint2 rpk = make_uint2(tpk.x, tpk.y);
+  const unsigned r2s = tpk.z;
   // the node list of the CTA that will follow this one on the SM: ask L2 for it now (the first thing that CTA waits for)
   if (t < (STRIDE * 4 + 127) / 128) {
     const long long nb = (long long)b + d.cta_lookahead;
-    if (nb * TPB < d.ne) prefetch_l2(reinterpret_cast<const char *>(d.blk_pad_b + nb * STRIDE) + t * 128);
+    if (nb < d.n_bcta) prefetch_l2(reinterpret_cast<const char *>(d.blk_pad_b + nb * STRIDE) + t * 128);
   }
   pdl_wait(); // everything above reads constant mesh tables only
   double tau[6];
@@ -524,7 +527,7 @@ __global__ void __launch_bounds__(TPB, MINB) k_elem_main_hex_brick(WfDev d, WfPa
   // one partial per unique node of the tile, in rank order (the accumulators sit at bank-aware slots; r2s was loaded in
   // the prologue: byte j = slot of rank lane + 32 j, 0xff = none)
   const long long tile = (long long)b * (TPB / 32) + warp;
-  if (tile * 32 < d.ne) {
+  {
     double *__restrict__ out = d.ftile + tile * 3 * d.tf_stride;
 #pragma unroll
     for (int j = 0; j < 4; j++) {

@@ -22,15 +22,18 @@ bool wf_partition_is_box(const wf_partition *p);
 void wf_partition_box_coords(const wf_partition *p, std::vector<double> &x);
 int wf_partition_box_dim(const wf_partition *p);
 
-// Force tiles of the tile-reduced force path (WfDev::ftile; see wf_dev.h): tile w = elements [32w, 32w+32).
+// Force tiles of the tile-reduced force path (WfDev::ftile; see wf_dev.h): tile w = thread slots [32w, 32w+32) of the
+// main element pass; slot s holds element slot_elem[s] (-1 = idle), or element s when slot_elem is NULL.
 struct WfForceTiles {
   bool usable = false;               // hexahedra: false when two elements of a tile share a node at the same corner
   bool rounds = false;               // no tile has two elements sharing a node at the same corner (conflict-free rounds)
   int k = 0, n_tiles = 0, stride = 0, tpitch = 0;
-  std::vector<unsigned char> tidx;   // [k][ep] index of element node (e, ln) in its tile's ascending unique-node list
+  std::vector<unsigned char> tidx;   // [k][ep] index of element node (slot, ln) in its tile's ascending unique-node list
   std::vector<long long> ptr;        // [nslices+1] sliced-ELL of the tile entries of each node
   std::vector<unsigned> slots;       // offset of component 0 in ftile (tile*dim*stride + position), ascending tile order, ~0u = padding
   std::vector<unsigned char> tab;    // all but hexahedra: [n_tiles][tpitch] incidence tables (ptr[stride+1], inc[32k])
 };
-// ep = pitch of tidx (>= n_elems); elnod is the reference layout [e*k + ln]
-void wf_force_tiles_build(int n_nodes, int n_elems, int k, int dim, long long ep, const unsigned *elnod, WfForceTiles &out);
+// n_slots = thread slots (= n_elems when slot_elem is NULL); ep = pitch of tidx (>= n_slots); elnod is the reference
+// layout [e*k + ln]
+void wf_force_tiles_build(int n_nodes, int n_slots, const int *slot_elem, int k, int dim, long long ep, const unsigned *elnod,
+                          WfForceTiles &out);

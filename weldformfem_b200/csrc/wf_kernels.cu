@@ -227,12 +227,12 @@ __global__ void __launch_bounds__(WF_EBLK) k_elem_vol_brick(WfDev d, WfPar P) {
     const int i = q * WF_EBLK + t;
     gid[q] = (i < STRIDE) ? __ldg(ids + i) : -1;
   }
-  const int e = b * WF_EBLK + t;
-  const bool active = e < d.ne;
-  const uint4 lpk = __ldg(d.lidx_pk + (active ? e : d.ne - 1));
+  const int e = __ldg(d.brick_elem + (long long)b * WF_EBLK + t); // < 0: idle thread slot
+  const bool active = e >= 0;
+  const uint4 lpk = __ldg(d.lidx_pk + (long long)b * WF_EBLK + t);
   if (t < (STRIDE * 4 + 127) / 128) { // node list of the CTA that follows on this SM (see k_elem_main_hex_brick)
     const long long nb = (long long)b + 4LL * d.cta_lookahead;
-    if (nb * WF_EBLK < d.ne) prefetch_l2(reinterpret_cast<const char *>(d.blk_pad_b + nb * STRIDE) + t * 128);
+    if (nb < d.n_bcta) prefetch_l2(reinterpret_cast<const char *>(d.blk_pad_b + nb * STRIDE) + t * 128);
   }
   pdl_wait();
 #pragma unroll
@@ -1554,7 +1554,7 @@ static void l_impose_bc(const WfDev &d, int dim, int is_acc, double *arr, cudaSt
 }
 static void l_elem_vol(const WfDev &d, const WfPar &P, int et, int store_jac, cudaStream_t s) {
   if (!store_jac && et == ET_HEX8 && d.blk_pad_b && !P.strict && P.variant[0] == 0) {
-    launch_pdl(k_elem_vol_brick<WF_BRICK_STRIDE>, cdiv(d.ne, WF_EBLK), WF_EBLK, (size_t)3 * WF_BRICK_STRIDE * 8, s, d, P);
+    launch_pdl(k_elem_vol_brick<WF_BRICK_STRIDE>, d.n_bcta, WF_EBLK, (size_t)3 * WF_BRICK_STRIDE * 8, s, d, P);
     return;
   }
   if (!store_jac && P.variant[0] == 1) {
@@ -1597,12 +1597,13 @@ constexpr int BRICK_STRIDE = WF_BRICK_STRIDE, BRICK_WS = WF_BRICK_WS;
 static void l_elem_main(const WfDev &d, const WfPar &P, int et, int separate_hg, cudaStream_t s) {
   if (et == ET_HEX8 && l_tile_forces(d, P, separate_hg)) {
     const int stride = d.blk_pitch, g = cdiv(d.ne, hexfast::TPB);
-    if (d.blk_pad_b && P.variant[2] != 7) {
+    // variant 7 = the generic tile kernel; it addresses tiles by the compact numbering, so not with a brick plan
+    if (d.blk_pad_b && (P.variant[2] != 7 || d.brick_plan)) {
       constexpr size_t smem = ((size_t)7 * BRICK_STRIDE + (size_t)(hexfast::TPB / 32) * 3 * BRICK_WS) * 8;
       // 4 resident CTAs at 128 registers; measured alternatives: 5 CTAs at 96 registers (80 B of spills)
       // 0.910 vs 0.847 ms, L2 look-ahead of the next CTA's node data 0.787 vs 0.791 ms, a persistent double-buffered
       // form 1.07 vs 0.79 ms
-      launch_pdl(hexfast::k_elem_main_hex_brick<BRICK_STRIDE, BRICK_WS, 4>, g, hexfast::TPB, smem, s, d, P);
+      launch_pdl(hexfast::k_elem_main_hex_brick<BRICK_STRIDE, BRICK_WS, 4>, d.n_bcta, hexfast::TPB, smem, s, d, P);
       return;
     }
     const size_t smem = ((size_t)7 * stride + (size_t)(hexfast::TPB / 32) * 3 * d.tf_stride) * 8;

@@ -137,10 +137,12 @@ static inline uint64_t spread_bits(uint32_t v, int ndim) {
   for (int b = 0; b < (ndim == 3 ? 21 : 31); b++) r |= (uint64_t)((v >> b) & 1u) << (ndim * b);
   return r;
 }
-extern "C" int wf_host_elem_order(int dim, int k, int n_nodes, int n_elems, const double *x, const unsigned *elnod, int mode,
-                                  int *perm) {
+// keys (optional): the sort key of every element, in the resulting INTERNAL order (mode 1 only; see wf_host_brick_plan)
+extern "C" int wf_host_elem_order_keys(int dim, int k, int n_nodes, int n_elems, const double *x, const unsigned *elnod, int mode,
+                                       int *perm, unsigned long long *keys_out) {
   if (n_elems <= 0 || n_nodes <= 0 || !x || !elnod || !perm || (dim != 2 && dim != 3)) return 1;
   if (mode == 0) {
+    if (keys_out) return 1;
     for (int e = 0; e < n_elems; e++) perm[e] = e;
     return 0;
   }
@@ -200,6 +202,40 @@ extern "C" int wf_host_elem_order(int dim, int k, int n_nodes, int n_elems, cons
   }
   std::sort(keys.begin(), keys.end());
   for (int e = 0; e < n_elems; e++) perm[e] = keys[(size_t)e].second;
+  if (keys_out)
+    for (int e = 0; e < n_elems; e++) keys_out[e] = keys[(size_t)e].first;
+  return 0;
+}
+extern "C" int wf_host_elem_order(int dim, int k, int n_nodes, int n_elems, const double *x, const unsigned *elnod, int mode,
+                                  int *perm) {
+  return wf_host_elem_order_keys(dim, k, n_nodes, n_elems, x, elnod, mode, perm, nullptr);
+}
+
+// ---- thread slots of the brick passes (k_elem_vol_brick, k_elem_main_hex_brick) -------------------------------------
+// The hexahedron key of wf_host_elem_order is (tile Morton code << 5) | position in the 4x4x2 tile, and the two lowest
+// bits of the tile code are (z, x) of the tile inside its 8x4x4 group: key >> 7 names the group = one CTA, key & 127
+// the thread (warp = tile, lane = position).  When every element of the mesh has its own key (one element per cell:
+// any mapped structured mesh), giving thread key & 127 of CTA rank(key >> 7) to the element makes EVERY CTA a clipped
+// 8x4x4 brick, also along ragged mesh boundaries (the compact numbering 128 b + t shifts by the missing elements of
+// every clipped brick it has passed); threads whose cell does not exist idle.  keys: ascending, internal order.
+// slot_elem[cta * 128 + thread] = internal element or -1; call with slot_elem = NULL for n_cta.  Returns 1 when the
+// keys are not strictly ascending (two elements in one cell): the caller keeps the compact numbering.
+extern "C" int wf_host_brick_plan(int n_elems, const unsigned long long *keys, int *n_cta, int *slot_elem) {
+  if (n_elems <= 0 || !keys || !n_cta) return 1;
+  long long nc = 1;
+  for (int e = 1; e < n_elems; e++) {
+    if (keys[e] <= keys[e - 1]) return 1;
+    if ((keys[e] >> 7) != (keys[e - 1] >> 7)) nc++;
+  }
+  if (nc * 128 > 2147483647LL) return 1;
+  *n_cta = (int)nc;
+  if (!slot_elem) return 0;
+  std::fill(slot_elem, slot_elem + nc * 128, -1);
+  long long c = 0;
+  for (int e = 0; e < n_elems; e++) {
+    if (e > 0 && (keys[e] >> 7) != (keys[e - 1] >> 7)) c++;
+    slot_elem[c * 128 + (long long)(keys[e] & 127u)] = e;
+  }
   return 0;
 }
 
@@ -225,15 +261,18 @@ extern "C" int wf_host_run_slots(int n, const int *sorted_ids, int *slots) {
 }
 
 // ---- force tiles of the tile-reduced force path (WfDev::ftile) ------------------------------------------------
-// Tile w = elements [32w, 32w+32) (one warp of the main element pass).  Per tile: the ascending list of its unique
+// Tile w = thread slots [32w, 32w+32) of the main element pass (one warp); slot s holds element slot_elem[s] (-1 = idle
+// thread; slot_elem = NULL: slot s = element s, the compact numbering).  Per tile: the ascending list of its unique
 // nodes; tidx = position of every element node in that list.  Hexahedra accumulate in conflict-free rounds (one
 // per local corner), which requires that no two elements of a tile reference the same node through the same
 // corner; tetrahedra pull through an incidence table (CSR by unique node, entries ascending element then corner).
 // Node n owns one entry per tile that references it, ascending tile order: slots = tile*3*stride + position.
-void wf_force_tiles_build(int nn, int ne, int k, int dim, long long ep, const unsigned *elnod, WfForceTiles &T) {
+void wf_force_tiles_build(int nn, int ne, const int *slot_elem, int k, int dim, long long ep, const unsigned *elnod,
+                          WfForceTiles &T) {
   T = WfForceTiles();
   T.k = k;
   if (!((dim == 3 && (k == 8 || k == 4)) || (dim == 2 && (k == 4 || k == 3))) || ne <= 0) return;
+  if (slot_elem && k != 8) return; // the incidence tables of the pull form are built for the compact numbering only
   const int ntile = (ne + 31) / 32;
   T.n_tiles = ntile;
   T.tidx.assign((size_t)k * ep, 0);
@@ -242,14 +281,19 @@ void wf_force_tiles_build(int nn, int ne, int k, int dim, long long ep, const un
   int wmax = 0;
   bool ok = true, conflict = false;
   std::vector<int> stamp(256, -1);
+  auto elem = [&](int s) { return slot_elem ? slot_elem[s] : s; };
   for (int w = 0; w < ntile && ok; w++) {
     const int e0 = w * 32, e1 = std::min(ne, e0 + 32);
-    tmp.assign(elnod + (size_t)e0 * k, elnod + (size_t)e1 * k);
+    tmp.clear();
+    for (int s = e0; s < e1; s++)
+      if (elem(s) >= 0) tmp.insert(tmp.end(), elnod + (size_t)elem(s) * k, elnod + (size_t)(elem(s) + 1) * k);
     std::sort(tmp.begin(), tmp.end());
     tmp.erase(std::unique(tmp.begin(), tmp.end()), tmp.end());
+    if (tmp.size() > 256) { ok = false; break; }
     for (int n = 0; n < k && ok; n++)
       for (int e = e0; e < e1; e++) {
-        const int u = (int)(std::lower_bound(tmp.begin(), tmp.end(), (int)elnod[(size_t)e * k + n]) - tmp.begin());
+        if (elem(e) < 0) continue;
+        const int u = (int)(std::lower_bound(tmp.begin(), tmp.end(), (int)elnod[(size_t)elem(e) * k + n]) - tmp.begin());
         if (stamp[u] == w * k + n) {
           conflict = true;
           if (k == 8) { ok = false; break; } // hexahedra have no pull form
@@ -313,7 +357,7 @@ extern "C" int wf_host_force_tiles(int n_nodes, int n_elems, int k, int dim, con
   for (long long i = 0; i < (long long)n_elems * k; i++)
     if (elnod[i] >= (unsigned)n_nodes) return 1;
   WfForceTiles T;
-  wf_force_tiles_build(n_nodes, n_elems, k, dim, n_elems, elnod, T);
+  wf_force_tiles_build(n_nodes, n_elems, nullptr, k, dim, n_elems, elnod, T);
   info[0] = T.usable ? 1 : 0; info[1] = T.n_tiles; info[2] = T.stride; info[3] = T.tpitch;
   info[4] = (n_nodes + 31) / 32; info[5] = (long long)T.slots.size(); info[6] = T.rounds ? 1 : 0;
   if (!T.usable) return 0;

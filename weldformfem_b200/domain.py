@@ -359,6 +359,12 @@ class Domain_d:
         self._ck(self._lib.wf_get_counts(self._h, C.byref(a), C.byref(b), C.byref(c)))
         return a.value, b.value, c.value
 
+    def brick_info(self):
+        """(CTAs of the brick form of the hexa passes, 1 if their thread slots follow the mesh cells) — wf_brick_info."""
+        a, b = C.c_int(), C.c_int()
+        self._ck(self._lib.wf_brick_info(self._h, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
     def info(self):
         nn, ne, _ = self.counts()
         return dict(dim=self.dim, nodxelem=self.nodxelem, n_nodes=nn, n_elems=ne, domtype=self._domtype)
