@@ -8,7 +8,7 @@ LIB = os.path.join(ROOT, "weldformfem_b200", "libwf_b200.so")
 OUT = sys.argv[1] if len(sys.argv) > 1 else os.path.join(ROOT, "profiles")
 KERNELS = {"E1_k_elem_vol_brick": r"wf_fast\d+k_elem_vol_brickILi304EE", "N1_k_node_vol": r"wf_fast\d+k_node_volILi8ELi5ELb0EE",
            "E2_k_elem_main_hex_brick": r"wf_fast\d+hexfast\d+k_elem_main_hex_brickILi304ELi176ELi4ELb1EE",
-           "N2_k_node_update": r"wf_fast\d+k_node_updateILi3ELb0ELi4ELb1ELb1ELi5ELb0EE"}
+           "N2_k_node_update": r"wf_fast\d+k_node_updateILi3ELb0ELi4ELb1ELb1ELi5ELb0ELin1EE"}
 names = subprocess.run(["cuobjdump", "-res-usage", LIB], capture_output=True, text=True).stdout
 for tag, pat in KERNELS.items():
     m = re.search(r"Function (\S*" + pat + r"\S*):\n\s*(REG:\S+ STACK:\S+ SHARED:\S+ LOCAL:\S+)", names)

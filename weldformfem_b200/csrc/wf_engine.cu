@@ -69,6 +69,7 @@ extern "C" int wf_create(wf_engine **out, int dim, int nodxelem, int domtype, in
   E->P.stab_simple = 1;
   E->P.hg_stiff = 0.1;
   if (const char *t = getenv("WF_ELEM_ORDER")) E->order_mode = atoi(t) != 0 ? 1 : 0;
+  if (const char *t = getenv("WF_VARIANT")) sscanf(t, "%d,%d,%d,%d", &E->P.variant[0], &E->P.variant[1], &E->P.variant[2], &E->P.variant[3]); // tuning runs
   select_flavour(E);
   *out = E;
   return 0;

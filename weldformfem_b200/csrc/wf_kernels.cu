@@ -324,7 +324,9 @@ WF_DI void tile_node_force(const WfDev &d, int n, double (&fi)[3]) {
   for (int j = 0; j < width; j++) {
     const unsigned o = __ldg(d.tf_slots + base + ((long long)j << 5) + (n & 31));
     if (o == 0xFFFFFFFFu) continue;
-    for (int c = 0; c < d.dim; c++) fi[c] += d.ftile[(long long)o + (long long)c * d.tf_stride];
+#pragma unroll
+    for (int c = 0; c < 3; c++)
+      if (c < d.dim) fi[c] += d.ftile[(long long)o + (long long)c * d.tf_stride];
   }
 }
 WF_DI void halo_node_force(const WfDev &d, int n, int sep, double (&fi)[3]) {
@@ -335,11 +337,15 @@ WF_DI void halo_node_force(const WfDev &d, int n, int sep, double (&fi)[3]) {
   const double *__restrict__ row = d.fsell + base * D + (n & 31);
   fi[0] = fi[1] = fi[2] = 0.0;
   for (int j = 0; j < width; j++)
-    for (int c = 0; c < D; c++) fi[c] += row[((long long)j * D + c) * 32];
+#pragma unroll
+    for (int c = 0; c < 3; c++)
+      if (c < D) fi[c] += row[((long long)j * D + c) * 32];
   if (sep) {
     const double *__restrict__ rowh = d.fsell_hg + base * D + (n & 31);
     for (int j = 0; j < width; j++)
-      for (int c = 0; c < D; c++) fi[c] -= rowh[((long long)j * D + c) * 32];
+#pragma unroll
+      for (int c = 0; c < 3; c++)
+        if (c < D) fi[c] -= rowh[((long long)j * D + c) * 32];
   }
 }
 // One CTA of a halo send: chunk `chunk` of neighbour `inb` (any block size).  Recomputes this rank's partial sums for
@@ -366,7 +372,9 @@ WF_DI void halo_send_cta(const WfDev &d, const WfPar &P, int sep, unsigned long 
       else { vals[0] = s; vals[1] = sq; nc = 2; }
     }
     double *dst = nb.dst + (long long)(seq & 1ull) * WF_HALO_NC * nb.count + j;
-    for (int c = 0; c < nc; c++) dst[(long long)c * nb.count] = vals[c];
+#pragma unroll
+    for (int c = 0; c < WF_HALO_NC; c++)
+      if (c < nc) dst[(long long)c * nb.count] = vals[c];
     __threadfence_system();
   }
   __syncthreads();
@@ -796,8 +804,11 @@ WF_DI void warp_add(double *dst, double x) {
   if (lane == __ffs(mask) - 1) atomicAdd(dst, t);
 }
 // ekin_acc: where the kinetic energy of the corrected velocities is accumulated (step monitor), or NULL
-template <int D, bool SEPARATE_HG, int UNROLL, bool TILE_F, bool PREFETCH, bool HALO>
-WF_DI void node_update_body(const WfDev &d, const WfPar &P, int fuse_flags, int phase, int vbx, double *ekin_acc) {
+// PHASE >= 0: the phase is known at compile time (the partitioned-mesh launches: phase 3 carries the send and no shared
+// node, phase 4 the wait and only shared nodes; each instantiation drops the other's code and registers)
+template <int D, bool SEPARATE_HG, int UNROLL, bool TILE_F, bool PREFETCH, bool HALO, int PHASE = -1>
+WF_DI void node_update_body(const WfDev &d, const WfPar &P, int fuse_flags, int phase_in, int vbx, double *ekin_acc) {
+  const int phase = PHASE >= 0 ? PHASE : phase_in;
   const bool fuse_predictor = fuse_flags & 1, udt_recompute = fuse_flags & 2, udt_skip_store = fuse_flags & 4;
   pdl_trigger();
   int bx = vbx;
@@ -819,7 +830,10 @@ WF_DI void node_update_body(const WfDev &d, const WfPar &P, int fuse_flags, int 
   }
   int slice = n >> 5;
   if (slice >= d.nslices) return;
-  if (phase == 3 && d.halo_slot && n < d.nn && d.halo_slot[n] >= 0) return; // shared nodes wait for phase 4
+  // phase 3: shared nodes wait for phase 4.  The flag is only LOADED here and tested after the force gathers (which have
+  // no side effects), so that its latency overlaps theirs instead of heading every thread's dependency chain
+  int hs3 = -1;
+  if (HALO && phase == 3 && d.halo_slot && n < d.nn) hs3 = __ldg(d.halo_slot + n);
   const int lane = n & 31;
   double fi[D];
 #pragma unroll
@@ -879,8 +893,8 @@ WF_DI void node_update_body(const WfDev &d, const WfPar &P, int fuse_flags, int 
         for (int c = 0; c < D; c++) fi[c] -= rowh[((long long)j * D + c) * 32];
     }
   }
-  if (n >= d.nn) return;
-  if (d.halo_slot && phase != 2) { // shared node: add the other sharers' partials, ascending rank order
+  if (n >= d.nn || hs3 >= 0) return;
+  if (d.halo_slot && phase != 2 && phase != 3) { // shared node (phase 3 has none): add the other sharers' partials, ascending rank order
     const int u = d.halo_slot[n];
     if (u >= 0) {
 #pragma unroll
@@ -965,9 +979,10 @@ WF_DI void node_update_body(const WfDev &d, const WfPar &P, int fuse_flags, int 
   }
 }
 
-template <int D, bool SEPARATE_HG, int UNROLL, bool TILE_F = false, bool PREFETCH = false, int MINB = 1, bool HALO = false>
+template <int D, bool SEPARATE_HG, int UNROLL, bool TILE_F = false, bool PREFETCH = false, int MINB = 1, bool HALO = false,
+          int PHASE = -1>
 __global__ void __launch_bounds__(TPB_N, MINB) k_node_update(WfDev d, WfPar P, int fuse_flags, int phase) {
-  node_update_body<D, SEPARATE_HG, UNROLL, TILE_F, PREFETCH, HALO>(d, P, fuse_flags, phase, blockIdx.x, d.ekin_acc);
+  node_update_body<D, SEPARATE_HG, UNROLL, TILE_F, PREFETCH, HALO, PHASE>(d, P, fuse_flags, phase, blockIdx.x, d.ekin_acc);
 }
 
 // ThermalCalcs, node part (Thermal.C:103-125): dTdt = sum of the element contributions in nodel order;
@@ -1655,7 +1670,10 @@ static void l_node_update(const WfDev &d, const WfPar &P, int separate_hg, int f
     const int g = phase == 4 ? cdiv(std::max(d.n_uniq, 1), TPB_N) : cdiv((long long)d.nslices * 32, TPB_N) + (phase == 3 ? P.send_ctas : 0);
     // measured on 10M hexes (tools/kbench.py): 5 resident CTAs (48 registers) + L2 prefetch of the state rows 0.60 ms;
     // 3 CTAs (67 registers) 0.66-0.75 ms; 6 CTAs (40 registers, spills) 0.61 ms; no prefetch 0.71 ms
-    if (d.n_neigh > 0) k_node_update<3, false, 4, true, true, 5, true><<<g, TPB_N, 0, s>>>(d, P, fuse, phase);
+    // (launching the pass as a programmatic dependent launch of E2 was measured: no gain on one GPU, 0.8 % slower on two)
+    if (d.n_neigh > 0 && phase == 3) k_node_update<3, false, 4, true, true, 5, true, 3><<<g, TPB_N, 0, s>>>(d, P, fuse, phase);
+    else if (d.n_neigh > 0 && phase == 4) k_node_update<3, false, 4, true, true, 5, true, 4><<<g, TPB_N, 0, s>>>(d, P, fuse, phase);
+    else if (d.n_neigh > 0) k_node_update<3, false, 4, true, true, 5, true><<<g, TPB_N, 0, s>>>(d, P, fuse, phase);
     else if (P.variant[3] == 5) k_node_update<3, false, 4, true, false, 5><<<g, TPB_N, 0, s>>>(d, P, fuse, phase);
     else if (P.variant[3] == 7) k_node_update<3, false, 4, true, true, 6><<<g, TPB_N, 0, s>>>(d, P, fuse, phase);
     else k_node_update<3, false, 4, true, true, 5><<<g, TPB_N, 0, s>>>(d, P, fuse, phase);
