@@ -842,6 +842,7 @@ WF_DI void node_update_body(const WfDev &d, const WfPar &P, int fuse_flags, int 
     // the node's own state is needed only after the force sum: ask L2 for it now, without holding registers
     // (loading it early instead costs 32 registers and a third of the occupancy: measured slower)
     prefetch_l2(d.mdiag + n);
+    prefetch_l2(d.bc_index + n);
 #pragma unroll
     for (int c = 0; c < D; c++) {
       const long long i = (long long)c * d.np + n;
@@ -1683,6 +1684,7 @@ static void l_node_update(const WfDev &d, const WfPar &P, int separate_hg, int f
   else if (P.variant[3] == 1) node_update_t<false, 2>(d, P, fuse, phase, s);
   else if (P.variant[3] == 2) node_update_t<false, 8>(d, P, fuse, phase, s);
   else if (P.variant[3] == 5) node_update_t<false, 4>(d, P, fuse, phase, s);
+  // (L2 prefetch of the state rows as in the tile path: no difference on 1 M quads, 0.0537 vs 0.0540 ms)
   else node_update_t<false, 4, 5>(d, P, fuse, phase, s); // 48 registers: 5 resident CTAs
 }
 static void l_node_thermal(const WfDev &d, const WfPar &P, cudaStream_t s) {
@@ -1812,6 +1814,7 @@ static void l_preload(int et, int dim, int k) {
   touch(k_node_vol<8>); touch(k_node_vol<8, 5>); touch(k_node_vol<4, 5>); touch(k_node_vol<3, 5>);
   touch(k_node_vol<8, 5, true>); touch(k_node_vol<4, 5, true>); touch(k_node_vol<3, 5, true>);
   touch(k_node_update<3, false, 4, true, true, 5, true>);
+  touch(k_node_update<3, false, 4, true, true, 5, true, 3>); touch(k_node_update<3, false, 4, true, true, 5, true, 4>);
   touch(k_node_update<3, true, 4, false, false, 1, true>); touch(k_node_update<3, false, 4, false, false, 5, true>); touch(k_node_update<3, false, 4, false, false, 1, true>);
   touch(k_node_update<3, false, 2, false, false, 1, true>); touch(k_node_update<3, false, 8, false, false, 1, true>);
   touch(k_node_update<2, true, 4, false, false, 1, true>); touch(k_node_update<2, false, 4, false, false, 5, true>); touch(k_node_update<2, false, 4, false, false, 1, true>);
