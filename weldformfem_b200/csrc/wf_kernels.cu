@@ -299,6 +299,8 @@ WF_DI void halo_wait_cta(const WfDev &d, unsigned long long seq, unsigned long l
   __syncthreads();
 }
 // partial sums over the local nodel list of node n, in list order
+// WITH_RHO: also the density sum and the count (init exchange only)
+template <bool WITH_RHO = true>
 WF_DI void halo_node_sums(const WfDev &d, int n, const double *__restrict__ src, double &s, double &sq, double &rs, int &cnt) {
   const long long base = d.sell_ptr[n >> 5];
   const int width = (int)((d.sell_ptr[(n >> 5) + 1] - base) >> 5);
@@ -311,8 +313,7 @@ WF_DI void halo_node_sums(const WfDev &d, int n, const double *__restrict__ src,
       const double ve = src[e];
       s += ve;
       sq += ve / 4.0;
-      rs += d.rho[e];
-      cnt++;
+      if (WITH_RHO) { rs += d.rho[e]; cnt++; }
     }
   }
 }
@@ -367,7 +368,7 @@ WF_DI void halo_send_cta(const WfDev &d, const WfPar &P, int sep, unsigned long 
     } else {
       double s, sq, rs;
       int cnt;
-      halo_node_sums(d, n, MODE == 0 ? d.vol_0 : d.vol, s, sq, rs, cnt);
+      halo_node_sums<MODE == 0>(d, n, MODE == 0 ? d.vol_0 : d.vol, s, sq, rs, cnt);
       if (MODE == 0) { vals[0] = (P.press == 3) ? sq : s; vals[1] = rs; vals[2] = (double)cnt; }
       else { vals[0] = s; vals[1] = sq; nc = 2; }
     }
@@ -375,11 +376,13 @@ WF_DI void halo_send_cta(const WfDev &d, const WfPar &P, int sep, unsigned long 
 #pragma unroll
     for (int c = 0; c < WF_HALO_NC; c++)
       if (c < nc) dst[(long long)c * nb.count] = vals[c];
-    __threadfence_system();
   }
+  // the CTA's stores are ordered before thread 0's system-scope fence by the barrier (fence cumulativity: the pattern
+  // of a barrier followed by ONE posting thread's fence + flag store); a fence per storing thread is not needed and kept
+  // every warp of the send CTAs waiting for its own NVLink round trip
   __syncthreads();
   if (threadIdx.x == 0) {
-    __threadfence();
+    __threadfence_system();
     const unsigned done = atomicAdd(nb.counter, 1u);
     if (done == (unsigned)chunks - 1u) {
       *nb.counter = 0u;
@@ -810,7 +813,9 @@ template <int D, bool SEPARATE_HG, int UNROLL, bool TILE_F, bool PREFETCH, bool 
 WF_DI void node_update_body(const WfDev &d, const WfPar &P, int fuse_flags, int phase_in, int vbx, double *ekin_acc) {
   const int phase = PHASE >= 0 ? PHASE : phase_in;
   const bool fuse_predictor = fuse_flags & 1, udt_recompute = fuse_flags & 2, udt_skip_store = fuse_flags & 4;
-  pdl_trigger();
+  // a launch that begins by spinning on the neighbours' flags (phase 4) lets its dependents in only after the wait: their
+  // resident CTAs would otherwise hold SM slots that another rank of a single-process cluster may need to get its sends out
+  if (!(HALO && phase == 4)) pdl_trigger();
   int bx = vbx;
   if (HALO && phase == 3 && P.send_ctas > 0) {
     // multi-GPU: the first CTAs of the launch send this rank's partial forces of the shared nodes; the rest of the grid
@@ -822,7 +827,10 @@ WF_DI void node_update_body(const WfDev &d, const WfPar &P, int fuse_flags, int 
     }
     bx -= P.send_ctas;
   }
-  if (HALO && phase == 4 && P.wait_seq) halo_wait_cta(d, P.wait_seq, P.wait_timeout_ns); // folded k_halo_wait (before any early exit)
+  if (HALO && phase == 4) {
+    if (P.wait_seq) halo_wait_cta(d, P.wait_seq, P.wait_timeout_ns); // folded k_halo_wait (before any early exit)
+    pdl_trigger();
+  }
   int n = bx * blockDim.x + threadIdx.x;
   if (phase == 4) { // shared nodes only, one thread per unique shared node (after the halo wait)
     if (n >= d.n_uniq) return;
@@ -1495,12 +1503,16 @@ __global__ void k_halo_wait(WfDev d, unsigned long long seq, unsigned long long 
 template <int MODE>
 __global__ void __launch_bounds__(128) k_halo_finish(WfDev d, WfPar P, int parity) {
   if (P.wait_seq) halo_wait_cta(d, P.wait_seq, P.wait_timeout_ns); // folded k_halo_wait
+  pdl_trigger(); // after the wait: see node_update_body
+  // as a programmatic dependent launch of N1 the CTAs are resident (and have seen the neighbours' flags) while N1's
+  // last wave drains; everything below reads what N1 / E1 wrote and overwrites N1's local-only sums of the shared nodes
+  pdl_wait();
   const int u = blockIdx.x * blockDim.x + threadIdx.x;
   if (u >= d.n_uniq) return;
   const int n = d.hu_node[u];
   double s, sq, rs;
   int cnt;
-  halo_node_sums(d, n, MODE == 0 ? d.vol_0 : d.vol, s, sq, rs, cnt);
+  halo_node_sums<MODE == 0>(d, n, MODE == 0 ? d.vol_0 : d.vol, s, sq, rs, cnt);
   if (MODE == 0) {
     const double t0 = halo_total(d, u, 0, parity, (P.press == 3) ? sq : s);
     const double t1 = halo_total(d, u, 1, parity, rs);
@@ -1672,6 +1684,8 @@ static void l_node_update(const WfDev &d, const WfPar &P, int separate_hg, int f
     // measured on 10M hexes (tools/kbench.py): 5 resident CTAs (48 registers) + L2 prefetch of the state rows 0.60 ms;
     // 3 CTAs (67 registers) 0.66-0.75 ms; 6 CTAs (40 registers, spills) 0.61 ms; no prefetch 0.71 ms
     // (launching the pass as a programmatic dependent launch of E2 was measured: no gain on one GPU, 0.8 % slower on two)
+    // phase 4 (shared nodes, begins with the flag wait) as a programmatic dependent launch of phase 3
+    if (d.n_neigh > 0 && phase == 4 && P.variant[3] != 8) { launch_pdl(k_node_update<3, false, 4, true, true, 5, true, 4>, g, TPB_N, 0, s, d, P, fuse, phase); return; }
     if (d.n_neigh > 0 && phase == 3) k_node_update<3, false, 4, true, true, 5, true, 3><<<g, TPB_N, 0, s>>>(d, P, fuse, phase);
     else if (d.n_neigh > 0 && phase == 4) k_node_update<3, false, 4, true, true, 5, true, 4><<<g, TPB_N, 0, s>>>(d, P, fuse, phase);
     else if (d.n_neigh > 0) k_node_update<3, false, 4, true, true, 5, true><<<g, TPB_N, 0, s>>>(d, P, fuse, phase);
@@ -1764,7 +1778,10 @@ static void l_halo_wait(const WfDev &d, unsigned long long seq, unsigned long lo
 static void l_halo_finish(const WfDev &d, const WfPar &P, int mode, int parity, cudaStream_t s) {
   if (d.n_uniq <= 0) return;
   if (mode == 0) k_halo_finish<0><<<cdiv(d.n_uniq, 128), 128, 0, s>>>(d, P, parity);
-  else k_halo_finish<1><<<cdiv(d.n_uniq, 128), 128, 0, s>>>(d, P, parity);
+  else if (P.variant[1] == 7) k_halo_finish<1><<<cdiv(d.n_uniq, 128), 128, 0, s>>>(d, P, parity);
+  // programmatic dependent launch of N1: launch latency and the flag wait overlap N1's last wave (2 GPUs, with the
+  // same for phase 4 of N2: 1.553 vs 1.562 ms per step)
+  else launch_pdl(k_halo_finish<1>, cdiv(d.n_uniq, 128), 128, 0, s, d, P, parity);
 }
 
 static void l_p_node(const WfDev &d, double *out, cudaStream_t s) {
