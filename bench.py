@@ -399,6 +399,7 @@ def ours(args):
         # where a distributed step spends its time: an event after each of its launches, max over ranks per slot.  The
         # folded waits sit at the head of "shared-node sums" and "N2 shared nodes": a late neighbour shows up there.
         dom.step_timed(3)
+        barrier()   # the ranks enter the measured batch together: host-side skew would be booked on the first flag wait
         kt = torch.tensor(dom.step_timed(args.steps), device="cuda", dtype=torch.float64) / args.steps
         dist.all_reduce(kt, op=dist.ReduceOp.MAX)
         kt = [float(v) for v in kt.tolist()]
