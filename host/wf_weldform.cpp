@@ -1,38 +1,41 @@
 // wf_weldform.cpp — run a WeldFormFEM input deck on the B200 engine: the counterpart of the reference's
 // `WeldFormFEM deck.json` (src/explicit/main.C) with the explicit loop executed by libwf_b200.so.
 //
-//   wf_weldform deck.json [--steps N] [--parse-only] [--dump FILE] [--strict] [--hexa-hg C]
+//   wf_weldform deck.json [--steps N] [--parse-only] [--dump FILE] [--vtk FILE] [--vtk-ascii] [--strict] [--hexa-hg C]
 //
 // Without --steps the loop runs `while (Time < simTime)` like Domain_d::SolveChungHulbert.  --parse-only reads and
 // checks deck + mesh without touching the GPU and prints the summary line.  --dump writes reference-layout arrays:
-// "<name> <count>\n" followed by <count> raw little-endian doubles each.  The reference's VTK / CSV output is not
-// reproduced; the arrays above are what a writer needs.
+// "<name> <count>\n" followed by <count> raw little-endian doubles each.  --vtk writes the final state as a legacy VTK
+// file with the array names of the reference's VTKWriter.C, binary by default (wf_vtk.hpp).
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <string>
 
 #include "wf_deck.hpp"
+#include "wf_vtk.hpp"
 
 using namespace wf_b200;
 
 int main(int argc, char **argv) {
-  std::string deck, dump;
+  std::string deck, dump, vtk;
   int steps = -1;
-  bool parse_only = false, strict = false;
+  bool parse_only = false, strict = false, vtk_ascii = false;
   double hexa_hg = 0.0;
   for (int i = 1; i < argc; i++) {
     std::string a = argv[i];
     auto val = [&]() -> const char * { return i + 1 < argc ? argv[++i] : ""; };
     if (a == "--steps") steps = atoi(val());
     else if (a == "--dump") dump = val();
+    else if (a == "--vtk") vtk = val();
+    else if (a == "--vtk-ascii") vtk_ascii = true;
     else if (a == "--parse-only") parse_only = true;
     else if (a == "--strict") strict = true;
     else if (a == "--hexa-hg") hexa_hg = atof(val());
     else if (a[0] != '-') deck = a;
     else { fprintf(stderr, "unknown argument %s\n", a.c_str()); return 2; }
   }
-  if (deck.empty()) { fprintf(stderr, "usage: wf_weldform deck.json [--steps N] [--parse-only] [--dump FILE] [--strict] [--hexa-hg C]\n"); return 2; }
+  if (deck.empty()) { fprintf(stderr, "usage: wf_weldform deck.json [--steps N] [--parse-only] [--dump FILE] [--vtk FILE] [--vtk-ascii] [--strict] [--hexa-hg C]\n"); return 2; }
   try {
     Domain_d dom(0);
     TriMesh_d msh;
@@ -58,13 +61,26 @@ int main(int argc, char **argv) {
       std::vector<const char *> names = {"x", "v", "a", "u", "prev_a", "m_fi", "m_mdiag", "vol", "p", "pl_strain", "sigma_y", "m_sigma", "m_tau"};
       if (S.contact) { names.push_back("contforce"); names.push_back("ut_prev"); names.push_back("node_area"); names.push_back("trimesh.node"); }
       if (S.thermal) { names.push_back("T"); names.push_back("m_q_plheat"); }
+      if (!vtk.empty()) { // everything else the VTK writer reads, so that a test can rebuild the file from the dump
+        for (const char *nm : {"vol_0", "rho", "p_node", "m_elem_area", "m_str_rate"})
+          if (wf_array_bytes(dom.handle(), nm)) names.push_back(nm);
+      }
       for (const char *nm : names) {
         std::vector<double> q = dom.get(nm);
         fprintf(f, "%s %zu\n", nm, q.size());
         fwrite(q.data(), sizeof(double), q.size(), f);
       }
+      if (!vtk.empty() && wf_array_bytes(dom.handle(), "ext_nodes")) {
+        std::vector<unsigned char> ext(wf_array_bytes(dom.handle(), "ext_nodes"));
+        if (wf_get_array(dom.handle(), "ext_nodes", ext.data(), ext.size()) == 0) {
+          std::vector<double> q(ext.begin(), ext.end());
+          fprintf(f, "ext_nodes %zu\n", q.size());
+          fwrite(q.data(), sizeof(double), q.size(), f);
+        }
+      }
       fclose(f);
     }
+    if (!vtk.empty()) wfvtk::write_vtk(dom.handle(), dom.getDim(), dom.getNodxElem(), vtk, !vtk_ascii);
   } catch (const std::exception &e) {
     fprintf(stderr, "%s\n", e.what());
     return 1;
