@@ -108,6 +108,7 @@ struct WfDev {
   const int *brick_elem;             /* [n_bcta * 128] */
   int n_bcta, brick_plan;
   int cta_lookahead;                 /* resident CTAs of the main element pass on the device (L2 look-ahead distance) */
+  int sm_count;                      /* multiprocessors of the device (look-ahead distance of the generic element pass) */
   /* tetrahedra: corners of different elements of a tile DO share nodes, so the tile sum is pulled instead: every
    * element drops its k*dim force values in shared memory and lane u adds up the entries of unique node u listed in
    * the tile's incidence table (ascending element, then corner: a fixed order).  Table of tile w at

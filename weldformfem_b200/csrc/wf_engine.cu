@@ -275,6 +275,8 @@ static int upload_mesh(wf_engine *E, int nn, int ne, const double *x, const unsi
     // tile-reduced force path (WfDev::ftile): tables built on the host (wf_force_tiles_build, wf_mesh.cpp)
     d.ftile = nullptr; d.tf_ptr = nullptr; d.tf_slots = nullptr; d.tf_idx = nullptr; d.tf_tab = nullptr;
     d.lidx_pk = nullptr; d.tile_pk = nullptr; d.blk_pad_b = nullptr; d.brick_elem = nullptr; d.cta_lookahead = 0;
+    d.sm_count = 0;
+    CK(cudaDeviceGetAttribute(&d.sm_count, cudaDevAttrMultiProcessorCount, E->device));
     d.n_bcta = 0; d.brick_plan = 0;
     d.tf_stride = 0; d.tf_tpitch = 0;
     if (dim == 3) { // 2D (1M quads, measured): rounds form E2 0.080 -> 0.099 ms, pull form 0.105 ms, N2 unchanged: not used
