@@ -559,7 +559,7 @@ WF_DI void gather_nodal_p(const WfDev &d, const int (&nid)[Elem<ET>::K], double 
 // STAGED: the CTA first loads x, v and the nodal ratio of its UNIQUE nodes into shared memory (WfDev::blk_off),
 // then every element reads its nodes through 16-bit block-local indices; otherwise every element gathers its own.
 // TILE: tile-reduced forces (WfDev::ftile, pull form: see WfDev::tf_tab) instead of one record per element node
-template <int ET, bool SEPARATE_HG, bool STAGED, bool THERMAL, bool TILE>
+template <int ET, bool SEPARATE_HG, bool STAGED, bool THERMAL, bool TILE, bool LOOKAHEAD = TILE>
 WF_DI void elem_main_body(const WfDev &d, const WfPar &P, int stride, int vbx) {
   constexpr int K = Elem<ET>::K, D = Elem<ET>::D;
   static_assert(!(STAGED && THERMAL), "the thermal terms gather by global node id");
@@ -604,9 +604,11 @@ WF_DI void elem_main_body(const WfDev &d, const WfPar &P, int stride, int vbx) {
       if (lane * 32 < d.tf_tpitch) prefetch_l2(d.tf_tab + (long long)(e >> 5) * d.tf_tpitch + lane * 32);
     }
     load_conn<ET>(d, e, nid);
-    {
+    if constexpr (LOOKAHEAD) {
       // connectivity of the CTA that will follow this one on the SM (about five resident CTAs): the gathers of a CTA begin
-      // with its node ids, so ask L2 for them one CTA lifetime ahead (K rows of 128 ints = 4 lines each)
+      // with its node ids, so ask L2 for them one CTA lifetime ahead (K rows of 128 ints = 4 lines each).  Only in the
+      // instantiations that were measured with it: in the quadrilateral kernel the two extra registers (128 -> 130)
+      // cost the fourth resident CTA (E2 0.081 -> 0.102 ms on 1 M quads), and capped at four CTAs it is 0.086 ms
       if (threadIdx.x < 4 * K) {
         const long long ne0 = ((long long)vbx + 5LL * d.sm_count) * TPB_E + (threadIdx.x & 3) * 32;
         if (ne0 < d.ne) prefetch_l2(d.elnod + (long long)(threadIdx.x >> 2) * d.ep + ne0);
@@ -769,9 +771,9 @@ WF_DI void elem_main_body(const WfDev &d, const WfPar &P, int stride, int vbx) {
   }
 }
 
-template <int ET, bool SEPARATE_HG, bool STAGED, bool THERMAL = false, bool TILE = false, int MINB = 1>
+template <int ET, bool SEPARATE_HG, bool STAGED, bool THERMAL = false, bool TILE = false, int MINB = 1, bool LOOKAHEAD = TILE>
 __global__ void __launch_bounds__(TPB_E, MINB) k_elem_main(WfDev d, WfPar P, int stride) {
-  elem_main_body<ET, SEPARATE_HG, STAGED, THERMAL, TILE>(d, P, stride, blockIdx.x);
+  elem_main_body<ET, SEPARATE_HG, STAGED, THERMAL, TILE, LOOKAHEAD>(d, P, stride, blockIdx.x);
 }
 
 // ---------------------------------------------------------------------------------------------
