@@ -10,6 +10,7 @@ Blocks taken (file:lines):
   several dts.txt:1-9, 30-38          F90 blocks after 10 and 100 steps (Disp)
   4elem_red_0.06_f90_1step.txt        F90, 2x2x2 elements, one step of dt = 2e-6: sigma / shear_stress of a loaded element
   1step_red_int_cube3D_hf_c_0.06.txt:6-9  initial dHdx*detJ matrix
+  4_el_hg_1e-3.txt:5-58               F90, 2x2x2 elements, hourglass 0.06, 501 steps of dt = 2e-6 (t = 1.002e-3): Disp / Vel, 27 nodes
 """
 import json
 import os
@@ -56,6 +57,9 @@ def main():
     dh = open(os.path.join(REF, "1step_red_int_cube3D_hf_c_0.06.txt")).read().split("\n")
     k = [i for i, s in enumerate(dh) if "INITIAL DERIVATIVE MATRIX" in s][0]
     pins["dHdx_detJ"] = table(dh, k + 1, 3)
+    f8 = open(os.path.join(REF, "4_el_hg_1e-3.txt")).read()
+    f8 = f8[:f8.index("C++")]
+    pins["f90_8elem_501_steps"] = {"Disp": f90_nodes(f8, "Disp", 27), "Vel": f90_nodes(f8, "Vel", 27)}
     json.dump(pins, open(OUT, "w"), indent=1)
     print("wrote", OUT)
 

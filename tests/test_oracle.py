@@ -171,6 +171,64 @@ def test_validation_f90_8_elements_one_step(oracle_port):
     assert np.allclose(tau[:, 0], pins["tau_xx"], rtol=1e-7) and np.allclose(tau[:, 2], pins["tau_zz"], rtol=1e-7)
 
 
+class _F90Cube8(cases.Case):
+    """2x2x2 hexes of 0.05: symmetry conditions on the bottom layer only (z = 0: u_z = 0; its x = 0 nodes u_x = 0, its
+    y = 0 nodes u_y = 0), top layer v_z = -1 — the conditions visible in validation/4_el_hg_1e-3.txt"""
+
+    def bc_nodes(self):
+        out = []
+        for n in range(27):
+            i, j, k = n % 3, (n // 3) % 3, n // 9
+            if k == 0:
+                out.append((n, 2, 0.0))
+                if i == 0:
+                    out.append((n, 0, 0.0))
+                if j == 0:
+                    out.append((n, 1, 0.0))
+            if k == 2:
+                out.append((n, 2, -1.0))
+        return out
+
+
+def _f90_cube8_run(oracle_port, nsteps, hexa_hg=0.06, press=2, equal_masses=True):
+    c = _F90Cube8("c8", 3, (2, 2, 2), 0.05, E=206e9, nu=0.3, rho0=7850.0, model=cases.BILINEAR, sy0=1e10, K=0.0, m=1.0,
+                  dt=2e-6, hexa_hg=hexa_hg, press=press)
+    d = oracle_port()
+    c.apply(d)
+    for _ in range(nsteps):
+        d.call("UpdatePrediction"); d.call("ImposeBCVAllDim")
+        d.call("calcElemJAndDerivatives"); d.call("CalcElemVol"); d.call("calcElemDensity")
+        d.call("CalcNodalVol"); d.call("CalcNodalMassFromVol")
+        if equal_masses:      # the F90 program lumps total mass / node count ("Affecting masses to equal")
+            m = d.get("m_mdiag")
+            d.set("m_mdiag", np.full(m.size, m.sum() / m.size))
+        d.call("calcElemStrainRates"); d.call("calcElemPressure"); d.call("CalcStressStrain", c.timestep)
+        d.call("calcElemForces"); d.call("calcElemHourglassForces"); d.call("assemblyForces")
+        d.call("calcAccel"); d.call("ImposeBCAAllDim"); d.call("UpdateCorrectionAccVel"); d.call("ImposeBCVAllDim")
+        d.call("UpdateCorrectionPos")
+    return d
+
+
+def test_validation_f90_8_elements_501_steps(oracle_port):
+    """validation/4_el_hg_1e-3.txt, F90 block: eight elements, hourglass 0.06, run to t = 1.002e-3 (501 steps of 2e-6; the
+    printed top displacement 1.00199999747e-3 = 501 x float32(2e-6)).  With the F90 program's mass lumping (total mass /
+    node count) the restated step reproduces its 27 nodal displacements to 3e-5 and velocities to 2e-4 of the array
+    maximum — hourglass modes of NEIGHBOURING elements interacting over 500 steps, which the one-element files cannot
+    show.  Negative controls: without hourglass forces 20 % off, with the current pressure law 1.2e-3, with the C++ nodal
+    masses 7e-4 (lateral displacements 2.5e-3).  (The file's C++ block was printed by an intermediate, x/y-asymmetric state
+    of the C++ code and is not reproducible by the algorithm at this commit.)"""
+    pins = _validation_pins()["f90_8elem_501_steps"]
+    want_u, want_v = np.array(pins["Disp"]), np.array(pins["Vel"])
+    d = _f90_cube8_run(oracle_port, 501)
+    u, v = d.get("u").reshape(-1, 3), d.get("v").reshape(-1, 3)
+    assert relerr(u, want_u) < 3e-5, relerr(u, want_u)
+    assert relerr(v, want_v) < 2e-4, relerr(v, want_v)
+    assert relerr(u[:, :2], want_u[:, :2]) < 1e-4      # the lateral field alone (it exists through Poisson + hourglass)
+    assert relerr(_f90_cube8_run(oracle_port, 501, hexa_hg=0.0).get("u").reshape(-1, 3), want_u) > 0.1
+    assert relerr(_f90_cube8_run(oracle_port, 501, press=0).get("u").reshape(-1, 3), want_u) > 5e-4
+    assert relerr(_f90_cube8_run(oracle_port, 501, equal_masses=False).get("u").reshape(-1, 3), want_u) > 3e-4
+
+
 def test_validation_shape_derivative_matrix(oracle_port):
     """validation/1step_red_int_cube3D_hf_c_0.06.txt:6-9: dHdx * detJ of the 0.1 cube (+-3.125e-4, signs per node)."""
     want = np.array(_validation_pins()["dHdx_detJ"])
