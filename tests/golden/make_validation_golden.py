@@ -11,6 +11,7 @@ Blocks taken (file:lines):
   4elem_red_0.06_f90_1step.txt        F90, 2x2x2 elements, one step of dt = 2e-6: sigma / shear_stress of a loaded element
   1step_red_int_cube3D_hf_c_0.06.txt:6-9  initial dHdx*detJ matrix
   4_el_hg_1e-3.txt:5-58               F90, 2x2x2 elements, hourglass 0.06, 501 steps of dt = 2e-6 (t = 1.002e-3): Disp / Vel, 27 nodes
+  4_el_NO_hg_1e-3.txt:3-29            the same run without hourglass forces: Disp
 """
 import json
 import os
@@ -60,6 +61,8 @@ def main():
     f8 = open(os.path.join(REF, "4_el_hg_1e-3.txt")).read()
     f8 = f8[:f8.index("C++")]
     pins["f90_8elem_501_steps"] = {"Disp": f90_nodes(f8, "Disp", 27), "Vel": f90_nodes(f8, "Vel", 27)}
+    n8 = open(os.path.join(REF, "4_el_NO_hg_1e-3.txt")).read()
+    pins["f90_8elem_501_steps_no_hg"] = {"Disp": f90_nodes(n8[:n8.index("C++")], "Disp", 27)}
     json.dump(pins, open(OUT, "w"), indent=1)
     print("wrote", OUT)
 

@@ -224,7 +224,11 @@ def test_validation_f90_8_elements_501_steps(oracle_port):
     assert relerr(u, want_u) < 3e-5, relerr(u, want_u)
     assert relerr(v, want_v) < 2e-4, relerr(v, want_v)
     assert relerr(u[:, :2], want_u[:, :2]) < 1e-4      # the lateral field alone (it exists through Poisson + hourglass)
-    assert relerr(_f90_cube8_run(oracle_port, 501, hexa_hg=0.0).get("u").reshape(-1, 3), want_u) > 0.1
+    u_nohg = _f90_cube8_run(oracle_port, 501, hexa_hg=0.0).get("u").reshape(-1, 3)
+    assert relerr(u_nohg, want_u) > 0.1
+    # validation/4_el_NO_hg_1e-3.txt: the same run without hourglass forces (its free hourglass modes amplify the
+    # single-precision contamination of the F90 constants: 2e-4)
+    assert relerr(u_nohg, np.array(_validation_pins()["f90_8elem_501_steps_no_hg"]["Disp"])) < 1e-3
     assert relerr(_f90_cube8_run(oracle_port, 501, press=0).get("u").reshape(-1, 3), want_u) > 5e-4
     assert relerr(_f90_cube8_run(oracle_port, 501, equal_masses=False).get("u").reshape(-1, 3), want_u) > 3e-4
 
