@@ -126,7 +126,7 @@ struct DeckSummary {
   int dim = 0, nodxelem = 0, n_nodes = 0, n_elems = 0, bc_nodes = 0, sym_nodes = 0, rigid_bodies = 0, rigid_facets = 0;
   int bc_count[3] = {0, 0, 0};  // entries per direction list, as Domain_d::bc_count after AllocateBCs
   bool contact = false, thermal = false;
-  double dt = 0, end_time = 0, min_length = 0;
+  double dt = 0, end_time = 0, min_length = 0, out_time = 0;
   std::string material;
 };
 
@@ -390,6 +390,7 @@ inline DeckSummary setup_from_deck(const std::string &deck_path, Domain_d &dom, 
   }
   dom.SetEndTime(sim_time);
   S.end_time = sim_time;
+  S.out_time = out_time;
   (void)out_time; (void)fixedTS;
 
   // symmetry planes, main.C:947-963

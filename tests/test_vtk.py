@@ -135,3 +135,46 @@ def test_cpp_writer_on_the_engine(deck, binary, tmp_path):
     out_p = str(tmp_path / "p.vtk")
     vtk.write_vtk(dom, out_p, binary=binary)
     assert open(out_c, "rb").read() == open(out_p, "rb").read()
+
+
+@pytest.mark.gpu
+def test_wf_weldform_output_cadence(tmp_path):
+    """`wf_weldform deck --out BASE` follows the reference loop (Solver_explicit.C:305, 1036-1041, 1155, 1167): a file after
+    every step whose START time is >= tout (tout = 0, then += outTime), numbered from 00000 and listed with that start
+    time in BASE_res.json; the steps in between run as fused batches."""
+    import json
+    from test_host_cpp import BIN
+    r = subprocess.run(["make", "-C", os.path.join(os.path.dirname(HERE), "host")], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    j = json.load(open(os.path.join(DECKS, "box_psquad.json")))
+    j["Configuration"]["simTime"] = 3.0e-6
+    j["Configuration"]["outTime"] = 1.0e-6
+    deck = str(tmp_path / "cadence.json")
+    json.dump(j, open(deck, "w"))
+    base = str(tmp_path / "run")
+    r = subprocess.run([os.path.join(BIN, "wf_weldform"), deck, "--out", base, "--strict"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    summary = json.loads(r.stdout.strip().splitlines()[-1])
+    dt, sim, out = summary["dt"], 3.0e-6, 1.0e-6
+    want, t, tout, steps = [], 0.0, 0.0, 0
+    while t < sim:
+        label = t
+        t += dt
+        steps += 1
+        if label >= tout:
+            want.append((steps, label))
+            tout += out
+    assert summary["steps"] == steps and len(want) == 3 and want[0] == (1, 0.0)
+    res = json.load(open(base + "_res.json"))["vtk_files"]
+    assert [e["file"] for e in res] == [base + "_%05d.vtk" % i for i in range(len(want))]
+    assert [e["time"] for e in res] == [w[1] for w in want]
+    rows = open(base + "_energy.csv").read().strip().split("\n")
+    assert rows[0] == "t,Ekin,dEint" and len(rows) == 1 + len(want)
+    assert [float(x.split(",")[0]) for x in rows[1:]] == [w[1] for w in want]
+    # file i holds the state after want[i][0] steps: same bytes as a run stopped there
+    for i, (nsteps, _) in enumerate(want):
+        single = str(tmp_path / ("single_%d.vtk" % i))
+        r = subprocess.run([os.path.join(BIN, "wf_weldform"), deck, "--steps", str(nsteps), "--vtk", single, "--strict"],
+                           capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+        assert open(single, "rb").read() == open(base + "_%05d.vtk" % i, "rb").read(), i
