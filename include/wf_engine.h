@@ -225,6 +225,12 @@ const int *wf_partition_halo_nodes(const wf_partition *);          /* local node
  * ids given to wf_add_bc_vel are GLOBAL ids (nodes of other ranks are skipped) and wf_get_array / wf_set_array
  * move LOCAL arrays (local node order = ascending global id, wf_halo_info -> node_l2g). */
 int wf_set_mesh_partition(wf_engine *, const wf_partition *, const double *x_local /*n_local*dim or NULL for box*/);
+/* Axisymmetric domains: the axis constraint (Solver_explicit.C:953-969) needs the minimum radial coordinate of the WHOLE
+ * mesh.  A partitioned axisymmetric engine keeps the rank-local minimum, which is the global one as long as the rank
+ * owns a node on the axis (those nodes never move radially) — true for every rank of an AddBoxLength box cut into
+ * contiguous element blocks.  Call this with the global minimum BEFORE wf_set_mesh_partition; the partition is refused
+ * when the rank has no node within 1e-6 of it (or when this was not called). */
+int wf_set_axis_xmin(wf_engine *, double global_xmin);
 int wf_halo_info(wf_engine *, int *rank, int *nranks, int *n_neigh, const int **neigh_ranks, const int **halo_offset,
                  const int **node_l2g);
 

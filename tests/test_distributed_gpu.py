@@ -25,6 +25,8 @@ CASES = {
     "tet_anp_nodal": R(cases.c2_tets(6, press=3), n=(4, 4, 7), top_vel=-200.0),
     "psquad": R(cases.plane_strain_quads(12), n=(10, 9), top_vel=-50.0),
     "pstri": R(cases.plane_strain_tris(12), n=(10, 9), top_vel=-50.0),
+    # axisymmetric: the axis constraint uses the rank-local minimum of x_r (wf_set_axis_xmin; every slab touches the axis)
+    "axiquad": R(cases.c4_axisymm_quads(12), n=(10, 9), top_vel=-50.0),
 }
 
 
@@ -190,3 +192,31 @@ def test_open_stepping_on_a_partitioned_mesh():
     # kinetic energy of the last step: shared nodes are counted by every sharer, so the sum over ranks is >= the global value
     assert ek >= one.energies()[0] * (1 - 1e-12)
     cl.close(); one.close()
+
+
+def test_axisymmetric_partition_needs_the_axis_on_every_rank():
+    """The axis constraint uses the rank-local minimum of x_r (wf_set_axis_xmin): a rank whose block does not touch the
+    axis is refused, and so is an axisymmetric partition that was never told the global minimum."""
+    import ctypes as C
+    from weldformfem_b200.distributed import Partition, RankDomain
+    from weldformfem_b200.domain import WfError
+    # a strip of 4 quads along x_r, numbered along x_r: the second half of the elements lies away from the axis
+    x = np.array([[i * 0.1, j * 0.1] for j in range(2) for i in range(5)], np.float64)
+    el = np.array([[i, i + 1, i + 6, i + 5] for i in range(4)], np.uint32)
+    ok = RankDomain(0, 2)
+    ok.setAxiSymm()
+    ok.set_mesh(2, 4, x, el)            # rank 0 owns the elements at the axis
+    assert ok.counts()[1] == 2
+    far = RankDomain(1, 2)
+    far.setAxiSymm()
+    with pytest.raises(WfError, match="no node on the axis"):
+        far.set_mesh(2, 4, x, el)
+    raw = RankDomain(0, 2)
+    raw.setAxiSymm()
+    raw._create(2, 4)
+    part = Partition(2, 0, mesh=(4, x.shape[0], el))
+    xl = np.ascontiguousarray(x[part.node_l2g])
+    rc = raw._lib.wf_set_mesh_partition(raw._h, part._h, xl.ctypes.data_as(C.POINTER(C.c_double)))
+    assert rc != 0 and b"wf_set_axis_xmin" in raw._lib.wf_last_error(raw._h)
+    for d in (ok, far, raw):
+        d.close()

@@ -38,7 +38,7 @@ DECLARED = (["wf_create", "wf_destroy", "wf_last_error", "wf_set_stream", "wf_ge
              "wf_get_array", "wf_set_array", "wf_array_bytes", "wf_device_ptr", "wf_partition_build",
              "wf_partition_build_box", "wf_partition_free", "wf_partition_info", "wf_partition_node_l2g",
              "wf_partition_local_elnod", "wf_partition_neigh_ranks", "wf_partition_halo_offset",
-             "wf_partition_halo_nodes", "wf_set_mesh_partition", "wf_step_phase", "wf_init_phase", "wf_halo_info",
+             "wf_partition_halo_nodes", "wf_set_mesh_partition", "wf_set_axis_xmin", "wf_step_phase", "wf_init_phase", "wf_halo_info",
              "wf_halo_comm_block", "wf_halo_slot_offsets", "wf_halo_ipc_export", "wf_halo_ipc_open", "wf_halo_connect",
              "wf_halo_status", "wf_connect_all", "wf_init_all", "wf_step_all", "wf_halo_set_transport", "wf_halo_exchange_ptrs",
              "wf_host_box_counts", "wf_host_gen_box", "wf_host_nodel", "wf_version",
@@ -125,6 +125,7 @@ def load():
         "wf_partition_halo_offset": (ip, [vp]),
         "wf_partition_halo_nodes": (ip, [vp]),
         "wf_set_mesh_partition": (C.c_int, [vp, vp, dp]),
+        "wf_set_axis_xmin": (C.c_int, [vp, C.c_double]),
         "wf_host_box_counts": (C.c_int, [dp, C.c_double, C.c_int, ip, ip, ip, ip]),
         "wf_host_gen_box": (C.c_int, [dp, dp, C.c_double, C.c_int, dp, up]),
         "wf_host_nodel": (C.c_int, [C.c_int, C.c_int, C.c_int, up, ip, ip, ip, ip]),

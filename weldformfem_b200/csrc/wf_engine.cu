@@ -464,6 +464,12 @@ extern "C" int wf_set_elem_order(wf_engine *E, int mode) { WF_NULLCHK(E);
   return 0;
 }
 
+extern "C" int wf_set_axis_xmin(wf_engine *E, double xmin) { WF_NULLCHK(E);
+  NEED(!E->meshed, "wf_set_axis_xmin before the mesh is set");
+  E->axis_xmin = xmin; E->axis_xmin_set = true;
+  return 0;
+}
+
 extern "C" int wf_brick_info(wf_engine *E, int *n_cta, int *plan) { WF_NULLCHK(E);
   NEED(E->meshed, "no mesh");
   if (n_cta) *n_cta = E->d.n_bcta;
@@ -1104,7 +1110,8 @@ extern "C" int wf_step_timed(wf_engine *E, int nsteps, float *ms) { WF_NULLCHK(E
 extern "C" int wf_set_mesh_partition(wf_engine *E, const wf_partition *p, const double *x_local) { WF_NULLCHK(E);
   NEED(p, "null partition");
   NEED(wf_partition_k(p) == E->k, "partition nodxelem does not match the engine");
-  NEED(E->domtype != WF_AXISYMM, "axisymmetric domains are not partitioned (the axis constraint needs a global min over x_r)");
+  NEED(E->domtype != WF_AXISYMM || E->axis_xmin_set,
+       "axisymmetric partition: call wf_set_axis_xmin with the minimum radial coordinate of the whole mesh first");
   int eb = 0, ee = 0, nl = 0, nng = 0;
   wf_partition_info(p, &eb, &ee, &nl, &nng);
   NEED(ee > eb && nl > 0, "this rank owns no elements");
@@ -1114,6 +1121,13 @@ extern "C" int wf_set_mesh_partition(wf_engine *E, const wf_partition *p, const 
     NEED(wf_partition_box_dim(p) == E->dim, "box dimension does not match the engine");
     wf_partition_box_coords(p, xb);
     x_local = xb.data();
+  }
+  if (E->domtype == WF_AXISYMM) {
+    // the axis constraint uses the rank-local minimum of x_r: it must be the global one (see wf_set_axis_xmin)
+    double lmin = x_local[0];
+    for (int n = 1; n < nl; n++) lmin = std::min(lmin, x_local[(size_t)n * E->dim]);
+    NEED(lmin <= E->axis_xmin + 1.e-6, "axisymmetric partition: this rank owns no node on the axis (x_r = global minimum); "
+                                       "the axis constraint cannot be evaluated locally");
   }
   CK(cudaSetDevice(E->device));
   if (E->stream == 0) { // engines of one process must not serialise on the legacy default stream

@@ -39,6 +39,7 @@ struct wf_engine {
   std::vector<int> h_nodel, h_nodel_loc, h_offset, h_count;
   std::vector<unsigned> h_pos; // [k][ep], see WfDev::pos; indexed by USER element id
   // internal element order (wf_host_elem_order): perm[internal] = user, iperm[user] = internal; empty = identity
+  bool axis_xmin_set = false; double axis_xmin = 0.0; // wf_set_axis_xmin (partitioned axisymmetric domains)
   int order_mode = -1;  // -1 = automatic: reorder hexahedra only (measured: tets 0.863 -> 0.968 ms, quads 0.173 -> 0.176 ms when reordered)
   std::vector<int> perm, iperm, perm_out;
   int *iperm_d = nullptr;

@@ -21,7 +21,7 @@ import ctypes as C
 import numpy as np
 
 from . import _lib
-from .domain import Domain_d, WfError
+from .domain import AXISYMM, Domain_d, WfError
 
 _ELEM_ARRAYS = {"vol", "vol_0", "rho", "rho_0", "p", "pl_strain", "sigma_y", "m_detJ", "m_radius", "m_tau", "m_eps",
                 "m_str_rate", "m_rot_rate", "m_sigma", "m_f_elem", "m_f_elem_hg", "m_hg_q", "m_dH_detJ_dx",
@@ -148,6 +148,8 @@ class RankDomain(Domain_d):
         k = (4 if tritetra else 8) if dim == 3 else (3 if tritetra else 4)
         self._create(dim, k)
         self.partition = Partition(self.nranks, self.rank, box=(V, L, r, tritetra))
+        if self._domtype == AXISYMM:     # every rank of a box cut into element blocks touches the axis x_r = V[0]
+            self._ck(self._lib.wf_set_axis_xmin(self._h, float(V[0])))
         self._ck(self._lib.wf_set_mesh_partition(self._h, self.partition._h, None))
         self._after_mesh()
 
@@ -160,6 +162,8 @@ class RankDomain(Domain_d):
         self._create(dim, k)
         self.partition = Partition(self.nranks, self.rank, mesh=(k, x.shape[0], elnod))
         xl = np.ascontiguousarray(x[self.partition.node_l2g])
+        if self._domtype == AXISYMM:
+            self._ck(self._lib.wf_set_axis_xmin(self._h, float(x[:, 0].min())))
         self._ck(self._lib.wf_set_mesh_partition(self._h, self.partition._h, xl.ctypes.data_as(C.POINTER(C.c_double))))
         self._after_mesh()
 
