@@ -12,6 +12,9 @@ Blocks taken (file:lines):
   1step_red_int_cube3D_hf_c_0.06.txt:6-9  initial dHdx*detJ matrix
   4_el_hg_1e-3.txt:5-58               F90, 2x2x2 elements, hourglass 0.06, 501 steps of dt = 2e-6 (t = 1.002e-3): Disp / Vel, 27 nodes
   4_el_NO_hg_1e-3.txt:3-29            the same run without hourglass forces: Disp
+  2step_1elem_red_no_hg_DIV.txt       F90, one element, state after the SECOND step of dt = 0.8e-5: Disp without hourglass (:12-19),
+                                      dHxy x detJ rows (:39-40) and the strain-rate tensor (:46-48) of that run; Disp / Vel / Acc
+                                      with hourglass 0.06 (:52-77)
 """
 import json
 import os
@@ -61,6 +64,14 @@ def main():
     f8 = open(os.path.join(REF, "4_el_hg_1e-3.txt")).read()
     f8 = f8[:f8.index("C++")]
     pins["f90_8elem_501_steps"] = {"Disp": f90_nodes(f8, "Disp", 27), "Vel": f90_nodes(f8, "Vel", 27)}
+    two = open(os.path.join(REF, "2step_1elem_red_no_hg_DIV.txt")).read()
+    nohg, hg = two.split("WITH HOURGLASS 0.06")[:2]
+    dh2 = [[float(t) for t in m.group(1).split()] for m in re.finditer(r"dHxy x detJ\s+(.*)", nohg)][:2]
+    sr = re.search(r"strain rate\s*\n(.*)\n(.*)\n(.*)\n", nohg)
+    pins["f90_1elem_2_steps"] = {
+        "Disp_no_hg": f90_nodes(nohg, "Disp"), "dHx_detJ": dh2[0], "dHy_detJ": dh2[1],
+        "strain_rate": [[float(t) for t in sr.group(i).split()] for i in (1, 2, 3)],
+        "Disp": f90_nodes(hg, "Disp"), "Vel": f90_nodes(hg, "Vel"), "Acc": f90_nodes(hg, "Acc")}
     n8 = open(os.path.join(REF, "4_el_NO_hg_1e-3.txt")).read()
     pins["f90_8elem_501_steps_no_hg"] = {"Disp": f90_nodes(n8[:n8.index("C++")], "Disp", 27)}
     json.dump(pins, open(OUT, "w"), indent=1)

@@ -171,6 +171,30 @@ def test_validation_f90_8_elements_one_step(oracle_port):
     assert np.allclose(tau[:, 0], pins["tau_xx"], rtol=1e-7) and np.allclose(tau[:, 2], pins["tau_zz"], rtol=1e-7)
 
 
+def test_validation_f90_one_element_second_step(oracle_port):
+    """validation/2step_1elem_red_no_hg_DIV.txt: the F90 program's state after the SECOND step of the one-element
+    compression (17 printed digits).  Intermediates of the run without hourglass forces: dH x detJ of the deformed element
+    to 1e-11 and the strain-rate tensor to 5e-9 (xx = yy 4.4720252..., zz -10.0008000640..., xz = yz -0.745397...); state of
+    the run with hourglass 0.06: displacements 2e-6, velocities 5e-6, accelerations 5e-5 of the array maximum (the F90
+    constants carry single-precision contamination, e.g. dt = float32(0.8e-5))."""
+    pins = _validation_pins()["f90_1elem_2_steps"]
+    d = _historical_run(oracle_port, 2, 0.0)
+    for c, key in (("x", "dHx_detJ"), ("y", "dHy_detJ")):
+        got = d.get(f"m_dH_detJ_d{c}").reshape(-1, 8)[0]
+        assert np.abs(got / np.array(pins[key]) - 1).max() < 1e-11, key
+    sr = d.get("m_str_rate").reshape(-1, 6)[0]          # xx yy zz xy yz xz
+    want = np.array(pins["strain_rate"])
+    got = np.array([[sr[0], sr[3], sr[5]], [sr[3], sr[1], sr[4]], [sr[5], sr[4], sr[2]]])
+    assert np.abs(got - want).max() < 5e-9 * np.abs(want).max()
+    assert relerr(d.get("u").reshape(-1, 3), np.array(pins["Disp_no_hg"])) < 2e-6
+    d = _historical_run(oracle_port, 2, 0.06)
+    assert relerr(d.get("u").reshape(-1, 3), np.array(pins["Disp"])) < 2e-6
+    assert relerr(d.get("v").reshape(-1, 3), np.array(pins["Vel"])) < 5e-6
+    assert relerr(d.get("a").reshape(-1, 3), np.array(pins["Acc"])) < 5e-5
+    # the two runs differ where the hourglass force acts: lateral displacement of the bottom node on the x axis
+    assert abs(np.array(pins["Disp"])[1, 0] / np.array(pins["Disp_no_hg"])[1, 0] - 1) > 0.05
+
+
 class _F90Cube8(cases.Case):
     """2x2x2 hexes of 0.05: symmetry conditions on the bottom layer only (z = 0: u_z = 0; its x = 0 nodes u_x = 0, its
     y = 0 nodes u_y = 0), top layer v_z = -1 — the conditions visible in validation/4_el_hg_1e-3.txt"""
