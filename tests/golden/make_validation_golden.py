@@ -14,7 +14,8 @@ Blocks taken (file:lines):
   4_el_NO_hg_1e-3.txt:3-29            the same run without hourglass forces: Disp
   2step_1elem_red_no_hg_DIV.txt       F90, one element, state after the SECOND step of dt = 0.8e-5: Disp without hourglass (:12-19),
                                       dHxy x detJ rows (:39-40) and the strain-rate tensor (:46-48) of that run; Disp / Vel / Acc
-                                      with hourglass 0.06 (:52-77)
+                                      with hourglass 0.06 (:52-77); "C++ with hourglass" block (:93-141): the four tables
+                                      after two steps and the hourglass force of every element node (6 decimals = 10 digits)
 """
 import json
 import os
@@ -72,6 +73,14 @@ def main():
         "Disp_no_hg": f90_nodes(nohg, "Disp"), "dHx_detJ": dh2[0], "dHy_detJ": dh2[1],
         "strain_rate": [[float(t) for t in sr.group(i).split()] for i in (1, 2, 3)],
         "Disp": f90_nodes(hg, "Disp"), "Vel": f90_nodes(hg, "Vel"), "Acc": f90_nodes(hg, "Acc")}
+    T = two.split("\n")
+    c0 = [i for i, q in enumerate(T) if "C++ with hourglass" in q][0]
+    blk = {}
+    for key in ("DISPLACEMENTS", "VELOCITIES", "ACCEL", "FORCES"):
+        j = [i for i in range(c0, len(T)) if T[i].strip() == key][0]
+        blk[key] = table(T, j + 1)
+    blk["HG_FORCES"] = [[float(t) for t in q.split(":")[1].split()] for q in T[c0:] if q.startswith("hg forces el 0")][:8]
+    pins["cxx_hg_0.06_2_steps"] = blk
     n8 = open(os.path.join(REF, "4_el_NO_hg_1e-3.txt")).read()
     pins["f90_8elem_501_steps_no_hg"] = {"Disp": f90_nodes(n8[:n8.index("C++")], "Disp", 27)}
     json.dump(pins, open(OUT, "w"), indent=1)

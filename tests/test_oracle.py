@@ -195,6 +195,22 @@ def test_validation_f90_one_element_second_step(oracle_port):
     assert abs(np.array(pins["Disp"])[1, 0] / np.array(pins["Disp_no_hg"])[1, 0] - 1) > 0.05
 
 
+def test_validation_cxx_second_step_and_hourglass_force_values(oracle_port):
+    """validation/2step_1elem_red_no_hg_DIV.txt:93-141, "C++ with hourglass": displacements, velocities, accelerations and
+    forces after two steps to every printed digit, and the HOURGLASS FORCE of each element node itself — printed with six
+    decimals, i.e. ten significant digits (3283.425868): the direct pin of calcElemHourglassForces' value, sign pattern and
+    coefficient."""
+    pins = _validation_pins()["cxx_hg_0.06_2_steps"]
+    d = _historical_run(oracle_port, 2, 0.06)
+    _printed_equal(d.get("u").reshape(-1, 3), pins["DISPLACEMENTS"])
+    _printed_equal(d.get("v").reshape(-1, 3), pins["VELOCITIES"])
+    _printed_equal(d.get("a").reshape(-1, 3), pins["ACCEL"])
+    _printed_equal(d.get("m_fi").reshape(-1, 3), pins["FORCES"])
+    hg = d.get("m_f_elem_hg").reshape(-1, 3)
+    want = np.array(pins["HG_FORCES"])
+    assert np.abs(hg - want).max() <= 5.0e-7 and np.abs(want).max() > 3283.0       # half a unit of the last printed decimal
+
+
 class _F90Cube8(cases.Case):
     """2x2x2 hexes of 0.05: symmetry conditions on the bottom layer only (z = 0: u_z = 0; its x = 0 nodes u_x = 0, its
     y = 0 nodes u_y = 0), top layer v_z = -1 — the conditions visible in validation/4_el_hg_1e-3.txt"""
