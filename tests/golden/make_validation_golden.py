@@ -16,6 +16,7 @@ Blocks taken (file:lines):
                                       dHxy x detJ rows (:39-40) and the strain-rate tensor (:46-48) of that run; Disp / Vel / Acc
                                       with hourglass 0.06 (:52-77); "C++ with hourglass" block (:93-141): the four tables
                                       after two steps and the hourglass force of every element node (6 decimals = 10 digits)
+  cxx/2time_step.txt:61,79-81         C++ log: sound speed CS_0 and the Chung-Hulbert alpha / beta / gamma the solver printed
 """
 import json
 import os
@@ -81,6 +82,8 @@ def main():
         blk[key] = table(T, j + 1)
     blk["HG_FORCES"] = [[float(t) for t in q.split(":")[1].split()] for q in T[c0:] if q.startswith("hg forces el 0")][:8]
     pins["cxx_hg_0.06_2_steps"] = blk
+    lg = open(os.path.join(REF, "cxx", "2time_step.txt")).read()
+    pins["cxx_log_constants"] = {k: float(re.search(r"^%s:? (\S+)" % k, lg, re.M).group(1)) for k in ("CS_0", "alpha", "beta", "gamma")}
     n8 = open(os.path.join(REF, "4_el_NO_hg_1e-3.txt")).read()
     pins["f90_8elem_501_steps_no_hg"] = {"Disp": f90_nodes(n8[:n8.index("C++")], "Disp", 27)}
     json.dump(pins, open(OUT, "w"), indent=1)

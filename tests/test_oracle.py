@@ -211,6 +211,20 @@ def test_validation_cxx_second_step_and_hourglass_force_values(oracle_port):
     assert np.abs(hg - want).max() <= 5.0e-7 and np.abs(want).max() > 3283.0       # half a unit of the last printed decimal
 
 
+def test_validation_integration_constants(oracle_port):
+    """validation/cxx/2time_step.txt:61,79-81: the Chung-Hulbert alpha / beta / gamma (rho_b = 0.8182) and the sound speed
+    the C++ solver printed for the one-element case (six decimals / six digits)."""
+    pins = _validation_pins()["cxx_log_constants"]
+    c = cases.c1_one_hex()
+    d = oracle_port()
+    c.apply(d)
+    k = d.consts()
+    for nm in ("alpha", "beta", "gamma"):
+        assert abs(k[nm] - pins[nm]) <= 5.0e-7, nm
+    cs0 = np.sqrt(c.E / (3.0 * (1.0 - 2.0 * c.nu)) / c.rho0)
+    assert abs(cs0 - pins["CS_0"]) <= 5.0e-3
+
+
 class _F90Cube8(cases.Case):
     """2x2x2 hexes of 0.05: symmetry conditions on the bottom layer only (z = 0: u_z = 0; its x = 0 nodes u_x = 0, its
     y = 0 nodes u_y = 0), top layer v_z = -1 — the conditions visible in validation/4_el_hg_1e-3.txt"""
