@@ -16,7 +16,9 @@ Blocks taken (file:lines):
                                       dHxy x detJ rows (:39-40) and the strain-rate tensor (:46-48) of that run; Disp / Vel / Acc
                                       with hourglass 0.06 (:52-77); "C++ with hourglass" block (:93-141): the four tables
                                       after two steps and the hourglass force of every element node (6 decimals = 10 digits)
-  cxx/2time_step.txt:61,79-81         C++ log: sound speed CS_0 and the Chung-Hulbert alpha / beta / gamma the solver printed
+  cxx/2time_step.txt:61,79-81         C++ log: sound speed CS_0 and the Chung-Hulbert alpha / beta / gamma the solver printed;
+                                      :377-433 corrected accelerations (6 decimals = 11 digits) and velocities of the FIRST step
+  1step_red_int_cube3D_hf_c_0.06.txt:82-  F90, first step: element stress, pressure, deviatoric stress, global forces, Disp / Vel / Acc
 """
 import json
 import os
@@ -84,6 +86,19 @@ def main():
     pins["cxx_hg_0.06_2_steps"] = blk
     lg = open(os.path.join(REF, "cxx", "2time_step.txt")).read()
     pins["cxx_log_constants"] = {k: float(re.search(r"^%s:? (\S+)" % k, lg, re.M).group(1)) for k in ("CS_0", "alpha", "beta", "gamma")}
+    acc = [[float(m.group(i)) for i in (1, 2, 3)] for m in re.finditer(r"Corr Acc (\S+) (\S+) (\S+)", lg)][:8]
+    vel = [[float(m.group(i)) for i in (1, 2, 3)] for m in re.finditer(r"Node \d Corr Vel (\S+) (\S+) (\S+)", lg)][:8]
+    pins["cxx_log_first_step"] = {"Acc": acc, "Vel": vel}
+    one_s = "\n".join(dh)
+    one_s = one_s[one_s.index("main loop, CHUNG HULBERT", one_s.index("WITH HOURGLASS")):]
+    sg = re.search(r"Element stresses.*\n\s*(\S+)\s+\S+\s+\S+\s*\n\s*\S+\s+(\S+)\s+\S+\s*\n\s*\S+\s+\S+\s+(\S+)", one_s)
+    sh = re.search(r"Element shear stresses\s*\n\s*(\S+)\s+\S+\s+\S+\s*\n\s*\S+\s+(\S+)\s+\S+\s*\n\s*\S+\s+\S+\s+(\S+)", one_s)
+    gf = re.search(r"Global forces\s*\n((?:\s*\S+\s+\S+\s+\S+\s*\n){8})", one_s)
+    pins["f90_1elem_first_step"] = {
+        "sigma_diag": [float(sg.group(i)) for i in (1, 2, 3)], "tau_diag": [float(sh.group(i)) for i in (1, 2, 3)],
+        "pressure": float(re.search(r"Element pressure\s+(\S+)", one_s).group(1)),
+        "forces": [[float(t) for t in q.split()] for q in gf.group(1).strip().split("\n")],
+        "Disp": f90_nodes(one_s, "Disp"), "Vel": f90_nodes(one_s, "Vel"), "Acc": f90_nodes(one_s, "Acc")}
     n8 = open(os.path.join(REF, "4_el_NO_hg_1e-3.txt")).read()
     pins["f90_8elem_501_steps_no_hg"] = {"Disp": f90_nodes(n8[:n8.index("C++")], "Disp", 27)}
     json.dump(pins, open(OUT, "w"), indent=1)

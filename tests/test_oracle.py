@@ -225,6 +225,29 @@ def test_validation_integration_constants(oracle_port):
     assert abs(cs0 - pins["CS_0"]) <= 5.0e-3
 
 
+def test_validation_first_step_intermediates(oracle_port):
+    """The FIRST step of the one-element compression with hourglass 0.06 (the hourglass force is still zero: no hourglass
+    velocity yet).  validation/1step_red_int_cube3D_hf_c_0.06.txt (F90, 17 digits): element stress, deviatoric stress,
+    pressure, global forces, accelerations, velocities, displacements to 2e-7 relative (its constants carry
+    single-precision contamination: M 0.98125004386, p 13733333.91 for 13733333.33).  validation/cxx/2time_step.txt:377-433
+    (the C++ solver's own log): corrected acceleration 37267.745852 to all eleven printed digits, velocity 0.342858."""
+    pins = _validation_pins()
+    f90, cxx = pins["f90_1elem_first_step"], pins["cxx_log_first_step"]
+    d = _historical_run(oracle_port, 1, 0.06)
+    sig, tau = d.get("m_sigma").reshape(-1, 6)[0], d.get("m_tau").reshape(-1, 6)[0]
+    assert np.abs(sig[:3] / np.array(f90["sigma_diag"]) - 1).max() < 2e-7 and not sig[3:].any()
+    assert np.abs(tau[:3] / np.array(f90["tau_diag"]) - 1).max() < 2e-7
+    assert abs(d.get("p")[0] / f90["pressure"] - 1) < 2e-7
+    # the F90 prints the internal force (+), rows in node order
+    assert relerr(d.get("m_fi").reshape(-1, 3), np.array(f90["forces"])) < 2e-7
+    assert relerr(d.get("a").reshape(-1, 3), np.array(f90["Acc"])) < 2e-7
+    assert relerr(d.get("v").reshape(-1, 3), np.array(f90["Vel"])) < 2e-7
+    assert relerr(d.get("u").reshape(-1, 3), np.array(f90["Disp"])) < 2e-7
+    assert np.abs(d.get("a").reshape(-1, 3) - np.array(cxx["Acc"])).max() <= 5.0e-7
+    assert np.abs(d.get("v").reshape(-1, 3) - np.array(cxx["Vel"])).max() <= 5.0e-7
+    assert not d.get("m_f_elem_hg").any()
+
+
 class _F90Cube8(cases.Case):
     """2x2x2 hexes of 0.05: symmetry conditions on the bottom layer only (z = 0: u_z = 0; its x = 0 nodes u_x = 0, its
     y = 0 nodes u_y = 0), top layer v_z = -1 — the conditions visible in validation/4_el_hg_1e-3.txt"""
