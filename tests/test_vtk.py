@@ -84,6 +84,29 @@ def test_writer_on_the_oracle_round_trips(key, binary, oracle_port, tmp_path):
                 assert np.array_equal(a[sec][nm], b[sec][nm]), nm
 
 
+def test_writer_contact_and_thermal_arrays_in_the_reference_order(oracle_port, tmp_path):
+    """A tet block pressed by a rigid plane with thermal coupling: the optional arrays appear, in the order the reference
+    writes them (VTKWriter.C:366-660: Temp and ContForce after Part_ID, ext_nodes / nod_area / nod_p between the nodal
+    stress and SIGMAT, ele_area first among the cell data)."""
+    case = cases.with_thermal(cases.contact_tets(4), heat_cond=25000.0, T_die=200.0)
+    dom = oracle_port()
+    case.apply(dom)
+    dom.step(30)
+    path = str(tmp_path / "contact.vtk")
+    written = vtk.write_vtk(dom, path)
+    want = ["DISP", "Acceleration", "Velocity", "Part_ID", "Temp", "ContForce", "nod_mass", "stress", "ext_nodes", "nod_area",
+            "nod_p", "SIGMAT"]
+    assert [w for w in written if w in want] == want and written.index("ele_area") < written.index("pressure")
+    r = _check_file(dom, path, True)
+    P, Cd = r["POINT_DATA"], r["CELL_DATA"]
+    nn = dom.info()["n_nodes"]
+    assert np.array_equal(P["Temp"], _f32(dom.get("T"))) and P["Temp"].max() > 20.0
+    assert np.array_equal(P["ContForce"], _f32(np.asarray(dom.get("contforce")).reshape(nn, 3))) and np.abs(P["ContForce"]).max() > 0
+    assert np.array_equal(P["ext_nodes"], (np.asarray(dom.get("ext_nodes")) != 0).astype(np.float64)) and 0 < P["ext_nodes"].sum() < nn
+    assert np.array_equal(P["nod_area"], _f32(dom.get("node_area"))) and np.array_equal(Cd["ele_area"], _f32(dom.get("m_elem_area")))
+    assert np.array_equal(P["nod_p"], _f32(dom.get("p_node")))
+
+
 class _DumpDomain:
     """Domain-shaped view of a `wf_weldform --dump` file + the connectivity of the VTK file itself."""
 
